@@ -1,0 +1,287 @@
+"""ctypes loaders for the two CPU checkers -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module (see oracle/glm_oracle.h).
+
+  PortOracle : oracle/_build/libglm_oracle.so   (plain-C restatement, oracle/glm_oracle.c)
+  RefOracle  : oracle/_ref/libref_oracle_v{4,3}.so (the reference itself, compiled from
+               /root/reference by oracle/Makefile; absent => RefOracle.available() is False)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BERNOULLI_LOGIT, POISSON_LOG, NORMAL_ID = 0, 1, 2
+FAMILY = {"bernoulli_logit": 0, "poisson_log": 1, "normal_id": 2}
+
+
+class GlmSpec(C.Structure):
+    _fields_ = [
+        ("family", C.c_int32), ("K", C.c_int32), ("N", C.c_int64),
+        ("X", C.c_void_p), ("ldx", C.c_int64),
+        ("y_int", C.c_void_p), ("y_real", C.c_void_p),
+        ("G", C.c_int32), ("_pad", C.c_int32), ("group", C.c_void_p),
+        ("prior_alpha_sd", C.c_double), ("prior_beta_sd", C.c_double),
+        ("prior_sigma_loc", C.c_double), ("prior_sigma_scale", C.c_double),
+        ("prior_sigma_a_scale", C.c_double),
+    ]
+
+
+DEFAULT_PRIORS = dict(prior_alpha_sd=2.5, prior_beta_sd=2.5, prior_sigma_loc=1.0,
+                      prior_sigma_scale=2.0, prior_sigma_a_scale=1.0)
+
+
+def make_spec(family, X, y, group=None, G=0, **priors):
+    """Returns (spec, keepalive).  X: (N,K) float64, any layout (copied to Fortran order)."""
+    fam = FAMILY[family] if isinstance(family, str) else int(family)
+    X = np.asfortranarray(X, dtype=np.float64)
+    N, K = X.shape
+    keep = [X]
+    s = GlmSpec()
+    s.family, s.K, s.N = fam, K, N
+    s.X = X.ctypes.data if X.size else None
+    s.ldx = max(N, 1) if X.size == 0 else N
+    if fam == NORMAL_ID:
+        yr = np.ascontiguousarray(y, dtype=np.float64)
+        keep.append(yr)
+        s.y_real, s.y_int = yr.ctypes.data, None
+    else:
+        yi = np.ascontiguousarray(y, dtype=np.int32)
+        keep.append(yi)
+        s.y_int, s.y_real = yi.ctypes.data, None
+    s.G = int(G)
+    if G:
+        gi = np.ascontiguousarray(group, dtype=np.int32)
+        keep.append(gi)
+        s.group = gi.ctypes.data
+    pri = dict(DEFAULT_PRIORS)
+    pri.update(priors)
+    for k, v in pri.items():
+        setattr(s, k, float(v))
+    return s, keep
+
+
+def num_params(family, K, G=0):
+    fam = FAMILY[family] if isinstance(family, str) else int(family)
+    return (2 + G if G else 1) + K + (1 if fam == NORMAL_ID else 0)
+
+
+class OracleError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+        self.msg = msg
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def build_port():
+    subprocess.run(["make", "-C", HERE, "port"], check=True, capture_output=True)
+
+
+class PortOracle:
+    """Plain-C port (kind="port")."""
+    kind = "port"
+
+    def __init__(self, family, X, y, group=None, G=0, **priors):
+        path = os.path.join(HERE, "_build", "libglm_oracle.so")
+        if not os.path.exists(path):
+            build_port()
+        self.lib = C.CDLL(path)
+        self.spec, self._keep = make_spec(family, X, y, group, G, **priors)
+        self.P = self.lib.glm_oracle_num_params(C.byref(self.spec))
+
+    def log_prob_grad(self, theta, propto=True, jacobian=True):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        lp = C.c_double()
+        g = np.empty(self.P)
+        err = C.create_string_buffer(512)
+        rc = self.lib.glm_oracle_log_prob_grad(C.byref(self.spec), _dp(th), int(propto), int(jacobian),
+                                               C.byref(lp), _dp(g), err, 512)
+        if rc:
+            raise OracleError(rc, err.value.decode())
+        return lp.value, g
+
+    def log_prob(self, theta, propto=False, jacobian=True):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        lp = C.c_double()
+        err = C.create_string_buffer(512)
+        rc = self.lib.glm_oracle_log_prob(C.byref(self.spec), _dp(th), int(propto), int(jacobian),
+                                          C.byref(lp), err, 512)
+        if rc:
+            raise OracleError(rc, err.value.decode())
+        return lp.value
+
+    def leapfrog(self, eps, inv_metric, q, p, g, V):
+        q, p, g = (np.array(a, dtype=np.float64) for a in (q, p, g))
+        im = np.ascontiguousarray(inv_metric, dtype=np.float64)
+        Vc = C.c_double(V)
+        err = C.create_string_buffer(512)
+        rc = self.lib.glm_oracle_leapfrog(C.byref(self.spec), C.c_double(eps), _dp(im), _dp(q), _dp(p), _dp(g),
+                                          C.byref(Vc), err, 512)
+        if rc:
+            raise OracleError(rc, err.value.decode())
+        return q, p, g, Vc.value
+
+
+def _cpu_flags():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return set(line.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+def ref_library_path():
+    flags = _cpu_flags()
+    v4 = {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= flags
+    v3 = {"avx2", "fma", "bmi2"} <= flags
+    cands = (["v4"] if v4 else []) + (["v3"] if v3 else [])
+    for isa in cands:
+        p = os.path.join(HERE, "_ref", f"libref_oracle_{isa}.so")
+        if os.path.exists(p):
+            return p, isa
+    return None, None
+
+
+class RefOracle:
+    """The compiled reference (kind="reference")."""
+    kind = "reference"
+    _lib = None
+    _isa = None
+
+    @classmethod
+    def available(cls):
+        return ref_library_path()[0] is not None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            path, isa = ref_library_path()
+            if path is None:
+                raise RuntimeError("oracle/_ref/libref_oracle_*.so not built (make -C oracle ref needs /root/reference)")
+            lib = C.CDLL(path)
+            lib.ref_glm_create.restype = C.c_void_p
+            lib.ref_glm_create.argtypes = [C.POINTER(GlmSpec)]
+            lib.ref_glm_destroy.argtypes = [C.c_void_p]
+            lib.ref_glm_num_params.argtypes = [C.c_void_p]
+            for fn in (lib.ref_ess, lib.ref_rhat, lib.ref_mcse_mean, lib.ref_mcse_sd):
+                fn.restype = C.c_double
+                fn.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int]
+            lib.ref_oracle_version.restype = C.c_char_p
+            cls._lib, cls._isa = lib, isa
+        return cls._lib
+
+    def __init__(self, family, X, y, group=None, G=0, **priors):
+        self.L = self.lib()
+        self.isa = self._isa
+        spec, keep = make_spec(family, X, y, group, G, **priors)
+        self.h = C.c_void_p(self.L.ref_glm_create(C.byref(spec)))
+        del keep  # the reference model copies its data
+        if not self.h:
+            raise RuntimeError("ref_glm_create failed")
+        self.P = self.L.ref_glm_num_params(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_glm_destroy(self.h)
+            self.h = None
+
+    def log_prob_grad(self, theta, propto=True, jacobian=True):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        lp = C.c_double()
+        g = np.empty(self.P)
+        err = C.create_string_buffer(1024)
+        rc = self.L.ref_glm_log_prob_grad(self.h, _dp(th), int(propto), int(jacobian), C.byref(lp), _dp(g), err, 1024)
+        if rc:
+            raise OracleError(rc, err.value.decode())
+        return lp.value, g
+
+    def log_prob(self, theta, propto=False, jacobian=True):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        lp = C.c_double()
+        err = C.create_string_buffer(1024)
+        rc = self.L.ref_glm_log_prob(self.h, _dp(th), int(propto), int(jacobian), C.byref(lp), err, 1024)
+        if rc:
+            raise OracleError(rc, err.value.decode())
+        return lp.value
+
+    def gradient(self, theta):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        lp = C.c_double()
+        g = np.empty(self.P)
+        err = C.create_string_buffer(1024)
+        rc = self.L.ref_glm_gradient(self.h, _dp(th), C.byref(lp), _dp(g), err, 1024)
+        if rc:
+            raise OracleError(rc, err.value.decode())
+        return lp.value, g
+
+    def leapfrog(self, eps, inv_metric, q, p, g=None, V=0.0, init=False):
+        q, p = (np.array(a, dtype=np.float64) for a in (q, p))
+        g = np.zeros(self.P) if g is None else np.array(g, dtype=np.float64)
+        im = np.ascontiguousarray(inv_metric, dtype=np.float64)
+        Vc = C.c_double(V)
+        err = C.create_string_buffer(1024)
+        rc = self.L.ref_glm_leapfrog(self.h, C.c_double(eps), _dp(im), int(init), _dp(q), _dp(p), _dp(g),
+                                     C.byref(Vc), err, 1024)
+        if rc:
+            raise OracleError(rc, err.value.decode())
+        return q, p, g, Vc.value
+
+    def nuts(self, num_chains=4, seed=1, init_chain_id=1, init_radius=2.0, num_warmup=1000, num_samples=1000,
+             stepsize=1.0, max_depth=10, delta=0.8, num_threads=0):
+        W = 7 + self.P
+        draws = np.empty((num_chains, num_samples, W))
+        step = np.empty(num_chains)
+        inv_metric = np.empty((num_chains, self.P))
+        warm_lf = np.empty(num_chains)
+        wall = C.c_double()
+        err = C.create_string_buffer(2048)
+        rc = self.L.ref_glm_nuts(self.h, num_chains, C.c_uint(seed), C.c_uint(init_chain_id), C.c_double(init_radius),
+                                 num_warmup, num_samples, C.c_double(stepsize), max_depth, C.c_double(delta),
+                                 num_threads, _dp(draws), _dp(step), _dp(inv_metric), _dp(warm_lf), C.byref(wall),
+                                 err, 2048)
+        if rc:
+            raise OracleError(rc, err.value.decode())
+        return dict(draws=draws, stepsize=step, inv_metric=inv_metric, warm_leapfrogs=warm_lf, wall=wall.value)
+
+    # ---- stan::analyze ----
+    @classmethod
+    def _chains(cls, draws):
+        d = np.asfortranarray(draws, dtype=np.float64)  # (n_draws, n_chains)
+        return d, d.shape[0], d.shape[1]
+
+    @classmethod
+    def ess(cls, draws):
+        d, n, c = cls._chains(draws)
+        return cls.lib().ref_ess(_dp(d), n, c)
+
+    @classmethod
+    def rhat(cls, draws):
+        d, n, c = cls._chains(draws)
+        return cls.lib().ref_rhat(_dp(d), n, c)
+
+    @classmethod
+    def mcse_mean(cls, draws):
+        d, n, c = cls._chains(draws)
+        return cls.lib().ref_mcse_mean(_dp(d), n, c)
+
+    @classmethod
+    def mcse_sd(cls, draws):
+        d, n, c = cls._chains(draws)
+        return cls.lib().ref_mcse_sd(_dp(d), n, c)
+
+    @classmethod
+    def split_rank_normalized_ess(cls, draws):
+        d, n, c = cls._chains(draws)
+        b, t = C.c_double(), C.c_double()
+        cls.lib().ref_split_rank_normalized_ess(_dp(d), n, c, C.byref(b), C.byref(t))
+        return b.value, t.value

@@ -1,0 +1,295 @@
+// oracle/ref/ref_oracle.cpp -- TEST INFRASTRUCTURE ONLY (see oracle/glm_oracle.h).
+//
+// C entry points over the UNMODIFIED reference, compiled from /root/reference by
+// oracle/Makefile into oracle/_ref/libref_oracle_<isa>.so:
+//   ref_glm_log_prob_grad -> stan::model::log_prob_grad<propto,jacobian>  (src/stan/model/log_prob_grad.hpp:29-50)
+//   ref_glm_log_prob      -> Model::log_prob<propto,jacobian>(double)     (as called at services/util/initialize.hpp:128)
+//   ref_glm_gradient      -> stan::model::gradient                        (src/stan/model/gradient.hpp:22-35)
+//   ref_glm_leapfrog      -> expl_leapfrog<diag_e_metric>::evolve         (mcmc/hmc/integrators/base_leapfrog.hpp:17-22)
+//   ref_glm_nuts          -> services::sample::hmc_nuts_diag_e_adapt      (services/sample/hmc_nuts_diag_e_adapt.hpp:58,331)
+//   ref_ess / ref_mcse_*  -> stan::analyze::{ess, mcse_mean, mcse_sd, rhat, split_rank_normalized_ess}
+#include "ref_glm_model.hpp"
+
+#include <stan/analyze/mcmc/ess.hpp>
+#include <stan/analyze/mcmc/mcse.hpp>
+#include <stan/analyze/mcmc/rhat.hpp>
+#include <stan/analyze/mcmc/split_rank_normalized_ess.hpp>
+#include <stan/callbacks/interrupt.hpp>
+#include <stan/callbacks/logger.hpp>
+#include <stan/callbacks/structured_writer.hpp>
+#include <stan/callbacks/writer.hpp>
+#include <stan/io/empty_var_context.hpp>
+#include <stan/mcmc/hmc/hamiltonians/diag_e_metric.hpp>
+#include <stan/mcmc/hmc/integrators/expl_leapfrog.hpp>
+#include <stan/model/gradient.hpp>
+#include <stan/model/log_prob_grad.hpp>
+#include <stan/services/sample/hmc_nuts_diag_e_adapt.hpp>
+#include <stan/services/util/create_unit_e_diag_inv_metric.hpp>
+
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <sstream>
+
+namespace {
+
+using oracle_ref::ref_glm_model;
+
+void set_err(char* buf, int len, const char* msg) {
+  if (buf && len > 0) {
+    std::strncpy(buf, msg, len - 1);
+    buf[len - 1] = 0;
+  }
+}
+
+template <typename F>
+int guarded(char* err, int errlen, F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::domain_error& e) {
+    set_err(err, errlen, e.what());
+    return 1;
+  } catch (const std::invalid_argument& e) {
+    set_err(err, errlen, e.what());
+    return 2;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return 3;
+  }
+}
+
+struct mem_writer : public stan::callbacks::writer {
+  std::vector<std::string> names;
+  std::vector<std::vector<double>> rows;
+  void operator()(const std::vector<std::string>& n) override { names = n; }
+  void operator()(const std::vector<double>& s) override { rows.push_back(s); }
+  void operator()() override {}
+  void operator()(const std::string&) override {}
+};
+
+struct mem_metric_writer : public stan::callbacks::structured_writer {
+  double stepsize = 0;
+  Eigen::VectorXd inv_metric;
+  void write(const std::string& key, double value) override {
+    if (key == "stepsize")
+      stepsize = value;
+  }
+  void write(const std::string& key, const Eigen::VectorXd& vec) override {
+    if (key == "inv_metric")
+      inv_metric = vec;
+  }
+};
+
+struct err_logger : public stan::callbacks::logger {
+  std::mutex m;
+  std::string errors;
+  void error(const std::string& s) override {
+    std::lock_guard<std::mutex> g(m);
+    errors += s + "\n";
+  }
+  void error(const std::stringstream& s) override { error(s.str()); }
+  void fatal(const std::string& s) override { error(s); }
+  void fatal(const std::stringstream& s) override { error(s.str()); }
+};
+
+template <bool propto, bool jacobian>
+double lp_grad(const ref_glm_model& m, std::vector<double>& th,
+               std::vector<double>& grad) {
+  std::vector<int> pi;
+  return stan::model::log_prob_grad<propto, jacobian>(m, th, pi, grad, nullptr);
+}
+template <bool propto, bool jacobian>
+double lp_only(const ref_glm_model& m, std::vector<double>& th) {
+  std::vector<int> pi;
+  return m.template log_prob<propto, jacobian>(th, pi, nullptr);
+}
+
+}  // namespace
+
+extern "C" {
+
+void* ref_glm_create(const glm_spec* s) {
+  try {
+    return new ref_glm_model(*s);
+  } catch (...) {
+    return nullptr;
+  }
+}
+void ref_glm_destroy(void* h) { delete static_cast<ref_glm_model*>(h); }
+int ref_glm_num_params(void* h) {
+  return static_cast<int>(static_cast<ref_glm_model*>(h)->num_params_r());
+}
+
+int ref_glm_log_prob_grad(void* h, const double* theta, int propto,
+                          int jacobian, double* lp, double* grad, char* err,
+                          int errlen) {
+  auto& m = *static_cast<ref_glm_model*>(h);
+  const size_t P = m.num_params_r();
+  return guarded(err, errlen, [&] {
+    std::vector<double> th(theta, theta + P), g;
+    double v;
+    if (propto)
+      v = jacobian ? lp_grad<true, true>(m, th, g) : lp_grad<true, false>(m, th, g);
+    else
+      v = jacobian ? lp_grad<false, true>(m, th, g)
+                   : lp_grad<false, false>(m, th, g);
+    *lp = v;
+    if (grad)
+      std::memcpy(grad, g.data(), P * sizeof(double));
+  });
+}
+
+int ref_glm_log_prob(void* h, const double* theta, int propto, int jacobian,
+                     double* lp, char* err, int errlen) {
+  auto& m = *static_cast<ref_glm_model*>(h);
+  const size_t P = m.num_params_r();
+  return guarded(err, errlen, [&] {
+    std::vector<double> th(theta, theta + P);
+    if (propto)
+      *lp = jacobian ? lp_only<true, true>(m, th) : lp_only<true, false>(m, th);
+    else
+      *lp = jacobian ? lp_only<false, true>(m, th)
+                     : lp_only<false, false>(m, th);
+  });
+}
+
+int ref_glm_gradient(void* h, const double* theta, double* lp, double* grad,
+                     char* err, int errlen) {
+  auto& m = *static_cast<ref_glm_model*>(h);
+  const size_t P = m.num_params_r();
+  return guarded(err, errlen, [&] {
+    Eigen::VectorXd x = Eigen::Map<const Eigen::VectorXd>(theta, P), g;
+    double f;
+    stan::callbacks::logger logger;
+    stan::model::gradient(m, x, f, g, logger);
+    *lp = f;
+    std::memcpy(grad, g.data(), P * sizeof(double));
+  });
+}
+
+// One step of the reference integrator on a diag_e_point.  On entry g,V may be
+// anything if init != 0 (hamiltonian.init recomputes them as base_nuts.hpp:85 does).
+int ref_glm_leapfrog(void* h, double eps, const double* inv_metric, int init,
+                     double* q, double* p, double* g, double* V, char* err,
+                     int errlen) {
+  auto& m = *static_cast<ref_glm_model*>(h);
+  const int P = static_cast<int>(m.num_params_r());
+  return guarded(err, errlen, [&] {
+    using H = stan::mcmc::diag_e_metric<ref_glm_model, stan::rng_t>;
+    H ham(m);
+    stan::mcmc::expl_leapfrog<H> integrator;
+    stan::mcmc::diag_e_point z(P);
+    stan::callbacks::logger logger;
+    z.q = Eigen::Map<const Eigen::VectorXd>(q, P);
+    z.p = Eigen::Map<const Eigen::VectorXd>(p, P);
+    z.g = Eigen::Map<const Eigen::VectorXd>(g, P);
+    z.V = *V;
+    if (inv_metric)
+      z.inv_e_metric_ = Eigen::Map<const Eigen::VectorXd>(inv_metric, P);
+    if (init)
+      ham.init(z, logger);
+    integrator.evolve(z, ham, eps, logger);
+    std::memcpy(q, z.q.data(), P * sizeof(double));
+    std::memcpy(p, z.p.data(), P * sizeof(double));
+    std::memcpy(g, z.g.data(), P * sizeof(double));
+    *V = z.V;
+  });
+}
+
+// Full NUTS through the reference entry point.  draws: [chain][sample][7 + P] doubles
+// (lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__, params...).
+// warm_leapfrogs[chain] receives sum(n_leapfrog__) over warm-up (save_warmup is forced on
+// internally so the column can be read; warm-up rows are not returned).
+int ref_glm_nuts(void* h, int num_chains, unsigned seed, unsigned init_chain_id,
+                 double init_radius, int num_warmup, int num_samples,
+                 double stepsize, int max_depth, double delta, int num_threads,
+                 double* draws, double* stepsize_out, double* inv_metric_out,
+                 double* warm_leapfrogs, double* wall_seconds, char* err,
+                 int errlen) {
+  auto& m = *static_cast<ref_glm_model*>(h);
+  const int P = static_cast<int>(m.num_params_r());
+  int rc = 0;
+  int g = guarded(err, errlen, [&] {
+    stan::math::init_threadpool_tbb(num_threads > 0 ? num_threads : num_chains);
+    std::vector<std::shared_ptr<stan::io::var_context>> inits, metrics;
+    for (int c = 0; c < num_chains; ++c) {
+      inits.emplace_back(std::make_shared<stan::io::empty_var_context>());
+      metrics.emplace_back(std::make_shared<stan::io::array_var_context>(
+          stan::services::util::create_unit_e_diag_inv_metric(P)));
+    }
+    stan::callbacks::interrupt interrupt;
+    err_logger logger;
+    std::vector<stan::callbacks::writer> init_w(num_chains), diag_w(num_chains);
+    std::vector<mem_writer> sample_w(num_chains);
+    std::vector<mem_metric_writer> metric_w(num_chains);
+    auto t0 = std::chrono::steady_clock::now();
+    rc = stan::services::sample::hmc_nuts_diag_e_adapt(
+        m, num_chains, inits, metrics, seed, init_chain_id, init_radius,
+        num_warmup, num_samples, 1, true, 0, stepsize, 0.0, max_depth, delta,
+        0.05, 0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w,
+        diag_w, metric_w);
+    auto t1 = std::chrono::steady_clock::now();
+    if (wall_seconds)
+      *wall_seconds = std::chrono::duration<double>(t1 - t0).count();
+    if (rc != 0)
+      throw std::runtime_error("hmc_nuts_diag_e_adapt rc=" + std::to_string(rc)
+                               + ": " + logger.errors);
+    const int W = 7 + P;
+    for (int c = 0; c < num_chains; ++c) {
+      auto& rows = sample_w[c].rows;
+      if (static_cast<int>(rows.size()) != num_warmup + num_samples)
+        throw std::runtime_error("unexpected number of draws");
+      double wl = 0;
+      for (int i = 0; i < num_warmup; ++i)
+        wl += rows[i][4];
+      if (warm_leapfrogs)
+        warm_leapfrogs[c] = wl;
+      for (int i = 0; i < num_samples; ++i) {
+        auto& r = rows[num_warmup + i];
+        if (static_cast<int>(r.size()) != W)
+          throw std::runtime_error("unexpected draw width");
+        std::memcpy(draws + (static_cast<size_t>(c) * num_samples + i) * W,
+                    r.data(), W * sizeof(double));
+      }
+      if (stepsize_out)
+        stepsize_out[c] = metric_w[c].stepsize;
+      if (inv_metric_out)
+        std::memcpy(inv_metric_out + static_cast<size_t>(c) * P,
+                    metric_w[c].inv_metric.data(), P * sizeof(double));
+    }
+  });
+  return g ? g : rc;
+}
+
+// draws: column-major n_draws x n_chains (one parameter)
+double ref_ess(const double* d, int n_draws, int n_chains) {
+  Eigen::MatrixXd m = Eigen::Map<const Eigen::MatrixXd>(d, n_draws, n_chains);
+  return stan::analyze::ess(m);
+}
+double ref_rhat(const double* d, int n_draws, int n_chains) {
+  Eigen::MatrixXd m = Eigen::Map<const Eigen::MatrixXd>(d, n_draws, n_chains);
+  return stan::analyze::rhat(m);
+}
+double ref_mcse_mean(const double* d, int n_draws, int n_chains) {
+  Eigen::MatrixXd m = Eigen::Map<const Eigen::MatrixXd>(d, n_draws, n_chains);
+  return stan::analyze::mcse_mean(m);
+}
+double ref_mcse_sd(const double* d, int n_draws, int n_chains) {
+  Eigen::MatrixXd m = Eigen::Map<const Eigen::MatrixXd>(d, n_draws, n_chains);
+  return stan::analyze::mcse_sd(m);
+}
+void ref_split_rank_normalized_ess(const double* d, int n_draws, int n_chains,
+                                   double* bulk, double* tail) {
+  Eigen::MatrixXd m = Eigen::Map<const Eigen::MatrixXd>(d, n_draws, n_chains);
+  auto r = stan::analyze::split_rank_normalized_ess(m);
+  *bulk = r.first;
+  *tail = r.second;
+}
+
+const char* ref_oracle_version() {
+  return "stan-dev/stan@9048555 + stan-dev/math@2fdd3ed, compiled from /root/reference";
+}
+
+}  // extern "C"

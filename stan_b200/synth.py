@@ -1,0 +1,52 @@
+"""Synthetic GLM data of the shapes BASELINE.json names.
+
+One generator for both sides of every parity test: data is generated ONCE (host numpy
+Philox for tests, device torch Philox for the HBM-scale bench) and the very same buffers
+are handed to the CUDA path and to the CPU checker, because host libm and CUDA
+transcendental last bits differ and independently regenerated X would not be identical.
+"""
+import numpy as np
+
+SEED = 20261017
+
+
+def _rng(seed, stream=0):
+    return np.random.Generator(np.random.Philox(key=[seed, stream]))
+
+
+def make_glm_data(family, N, K, G=0, seed=SEED, alpha_true=0.3):
+    """Returns dict(X (N,K) F-order float64, y, group (1-based int32 or None), truth)."""
+    r = _rng(seed, 0)
+    X = np.asfortranarray(r.standard_normal((K, N)).T) if N * K else np.zeros((N, K), order="F")
+    beta = _rng(seed, 1).standard_normal(K) / np.sqrt(max(K, 1))
+    eta = X @ beta if K else np.zeros(N)
+    group = None
+    a_true = None
+    if G:
+        rg = _rng(seed, 2)
+        group = rg.integers(1, G + 1, size=N, dtype=np.int32)
+        a_true = 0.5 * rg.standard_normal(G)
+        eta = eta + a_true[group - 1]
+    else:
+        eta = eta + alpha_true
+    ry = _rng(seed, 3)
+    if family == "bernoulli_logit":
+        y = (ry.random(N) < 1.0 / (1.0 + np.exp(-eta))).astype(np.int32)
+    elif family == "poisson_log":
+        y = ry.poisson(np.exp(np.clip(0.5 * eta + 0.5, -20, 5))).astype(np.int32)
+    elif family == "normal_id":
+        y = eta + ry.standard_normal(N)
+    else:
+        raise ValueError(family)
+    return dict(family=family, X=X, y=y, group=group, G=G,
+                truth=dict(alpha=alpha_true, beta=beta, a=a_true))
+
+
+def theta_points(P, seed=SEED, n_random=1, scale=0.1):
+    """theta = 0 and random N(0, scale^2) points (evaluate at >= 3 thetas;
+    the near-mode point comes from a short warm-up in the tests that need it)."""
+    pts = [np.zeros(P)]
+    r = _rng(seed, 7)
+    for _ in range(n_random):
+        pts.append(scale * r.standard_normal(P))
+    return pts
