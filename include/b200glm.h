@@ -1,0 +1,124 @@
+/*
+ * b200glm.h -- C ABI of the B200-native GLM log-density + gradient backend.
+ *
+ * This is the drop-in boundary.  Every entry point
+ * names the reference interface it replaces; paths are relative to the reference tree
+ * (ST = src/stan, SM = lib/stan_math/stan/math).  Plain pointers and sizes only: no C++ types,
+ * no exceptions and no torch types cross this line.  The reference-side binding (a
+ * stan::model::model_base_crtp model + explicit specialisations of stan::model::gradient and
+ * stan::mcmc::expl_leapfrog) is stan_b200/cpp/b200/stan_glm_model.hpp, see INTEGRATION.md.
+ *
+ * There is NO CPU fallback: every compute entry point returns B200GLM_CUDA if no sm_100
+ * device is usable.
+ *
+ * Model (the hand-written Stan program):
+ *   G == 0: theta = [alpha, beta_1..K (, log sigma)]
+ *   G  > 0: theta = [mu_a, log sigma_a, a_1..G, beta_1..K (, log sigma)]
+ *   priors alpha|mu_a ~ N(0, prior_alpha_sd), sigma_a ~ N(0, prior_sigma_a_scale),
+ *   a ~ N(mu_a, sigma_a), beta ~ N(0, prior_beta_sd), sigma ~ N(prior_sigma_loc, prior_sigma_scale)
+ *   likelihood y ~ {bernoulli_logit,poisson_log,normal_id}_glm(X, alpha | a[group], beta [, sigma]).
+ */
+#ifndef B200GLM_H
+#define B200GLM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GLM_ABI_VERSION 1
+
+/* status codes; the C++ shim maps them to the exceptions the reference throws:
+ * DOMAIN -> std::domain_error (recoverable: base_hamiltonian.hpp:65-68, initialize.hpp:104-112),
+ * INVALID -> std::invalid_argument (check_consistent_size), CUDA -> std::runtime_error (fatal). */
+enum { B200GLM_OK = 0, B200GLM_DOMAIN = 1, B200GLM_INVALID = 2, B200GLM_CUDA = 3 };
+
+/* SM/prim/prob/{bernoulli_logit_glm_lpmf.hpp:49, poisson_log_glm_lpmf.hpp:51, normal_id_glm_lpdf.hpp:54} */
+enum { B200GLM_BERNOULLI_LOGIT = 0, B200GLM_POISSON_LOG = 1, B200GLM_NORMAL_ID = 2 };
+
+typedef struct b200glm_handle b200glm_handle;
+
+typedef struct b200glm_desc {
+  int32_t family;
+  int32_t K;            /* columns of X ("attributes") */
+  int64_t N;            /* rows held by THIS handle (the local shard when world > 1) */
+  const double* X;      /* column-major N x K (Eigen::MatrixXd layout), leading dimension ldx */
+  int64_t ldx;
+  const int32_t* y_int; /* bernoulli / poisson */
+  const double* y_real; /* normal */
+  int32_t G;            /* 0 = scalar intercept, >0 = a[group] (ST/model/indexing/rvalue.hpp:154-172) */
+  int32_t data_on_device; /* 0: X,y,group are host pointers (copied); 1: device pointers on `device` */
+  const int32_t* group; /* 1-based */
+  double prior_alpha_sd, prior_beta_sd, prior_sigma_loc, prior_sigma_scale, prior_sigma_a_scale;
+  int32_t device;       /* CUDA device ordinal */
+  int32_t n_slots;      /* independent chain slots (each has its own stream + workspace); >= 1 */
+  int32_t rank, world;  /* row shard `rank` of `world` (world <= 1: unsharded).  With world > 1 the
+                           likelihood partials are summed across ranks (b200glm_comm_*) and the
+                           priors are added once, identically, on every rank. */
+  int64_t N_total;      /* rows over all shards (normal_id needs N for -N log sigma); 0 => N */
+  int32_t grid_ctas;    /* 0 = one persistent CTA per SM */
+  int32_t reserved;
+} b200glm_desc;
+
+/* Data upload + one-time re-layout of X into the row-panel format the kernel streams
+ * (replaces the Model constructor copying data out of a var_context, and SM/opencl/copy.hpp:45
+ * to_matrix_cl).  The caller keeps ownership of every pointer in desc. */
+int b200glm_create(const b200glm_desc* desc, b200glm_handle** out);
+void b200glm_destroy(b200glm_handle* h);
+
+/* prob_grad::num_params_r()  (ST/model/prob_grad.hpp:19-84) */
+int32_t b200glm_num_params(const b200glm_handle* h);
+
+/* Value and gradient with autodiff-variable semantics:
+ *   propto=1, jacobian=1 == stan::model::log_prob_grad<true,true>(model, theta, ., grad)
+ *   (ST/model/log_prob_grad.hpp:29-50) == stan::model::gradient (ST/model/gradient.hpp:22-35).
+ * theta/lp/grad are HOST pointers; grad may be NULL.  Synchronous on the slot's stream. */
+int b200glm_log_prob_grad(b200glm_handle* h, int32_t slot, const double* theta, int32_t propto,
+                          int32_t jacobian, double* lp, double* grad);
+
+/* Value with plain-double semantics: Model::log_prob<propto,jacobian>(vector<double>&, ...)
+ * as called from ST/services/util/initialize.hpp:128 (<false,jacobian>: all constants kept;
+ * propto=1 drops every density term, exactly as include_summand does for doubles). */
+int b200glm_log_prob(b200glm_handle* h, int32_t slot, const double* theta, int32_t propto,
+                     int32_t jacobian, double* lp);
+
+/* Device-resident leapfrog (replaces expl_leapfrog::evolve, ST/mcmc/hmc/integrators/
+ * base_leapfrog.hpp:17-22 + expl_leapfrog.hpp:16-32, and the update_potential_gradient it calls,
+ * base_hamiltonian.hpp:61-70).  set_state uploads z = (q, p, g, V) for a slot;
+ * leapfrog advances it by eps in ONE launch (half p, full q, gradient, half p) and mirrors the
+ * new (q, p, g, V) to the host pointers (any may be NULL).  inv_metric NULL = keep the last one
+ * (initially all ones).  On a domain error V=+inf and g is negated, as the reference does. */
+int b200glm_set_state(b200glm_handle* h, int32_t slot, const double* q, const double* p,
+                      const double* g, double V);
+int b200glm_leapfrog(b200glm_handle* h, int32_t slot, double eps, const double* inv_metric,
+                     double* q, double* p, double* g, double* V);
+
+/* Asynchronous forms for callers that keep theta on the device (bench `value`, batched driver):
+ * enqueue on the slot's stream, no host copies; b200glm_stream returns that cudaStream_t. */
+int b200glm_leapfrog_async(b200glm_handle* h, int32_t slot, double eps);
+int b200glm_grad_async(b200glm_handle* h, int32_t slot, const double* theta_device);
+int b200glm_sync(b200glm_handle* h, int32_t slot);
+void* b200glm_stream(b200glm_handle* h, int32_t slot);
+/* device pointer to the slot's result block [lp, grad[P], status] (doubles) */
+const double* b200glm_result_device(b200glm_handle* h, int32_t slot);
+
+/* Row-sharded operation: one process per GPU, likelihood partials combined by one NCCL
+ * all-reduce of P+2 doubles per gradient (replaces nothing in the reference's GLM path; the
+ * analogue is map_rect's gatherv, SM/prim/functor/mpi_parallel_call.hpp:354-392).
+ * unique_id is the 128-byte ncclUniqueId obtained on rank 0 and broadcast by the caller. */
+int b200glm_comm_unique_id(void* unique_id_128);
+int b200glm_comm_init(b200glm_handle* h, const void* unique_id_128, int32_t rank, int32_t world);
+
+/* launch accounting for the bench (`gpu_launches`) and algorithmic bytes per gradient */
+int64_t b200glm_launch_count(const b200glm_handle* h);
+int64_t b200glm_bytes_per_gradient(const b200glm_handle* h);
+/* milliseconds of the last `n` main-kernel launches of a slot (CUDA events on its stream) */
+const char* b200glm_last_error(const b200glm_handle* h);
+const char* b200glm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -45,6 +45,10 @@ void set_err(char* buf, int len, const char* msg) {
 
 template <typename F>
 int guarded(char* err, int errlen, F&& f) {
+  // With STAN_THREADS the AD tape is thread_local and must be created in every thread that
+  // evaluates a density (lib/stan_math/stan/math/rev/core/autodiffstackstorage.hpp:17-21, 60-130;
+  // TBB workers get theirs from init_chainablestack.hpp, foreign threads need this).
+  static thread_local stan::math::ChainableStack thread_tape;
   try {
     f();
     return 0;

@@ -1,0 +1,71 @@
+"""ctypes binding of include/b200glm.h.  Fails loudly when the CUDA extension is missing."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libb200glm.so")
+
+OK, DOMAIN, INVALID, CUDA = 0, 1, 2, 3
+FAMILY = {"bernoulli_logit": 0, "poisson_log": 1, "normal_id": 2}
+
+# every symbol include/b200glm.h declares
+SYMBOLS = [
+    "b200glm_create", "b200glm_destroy", "b200glm_num_params", "b200glm_log_prob_grad", "b200glm_log_prob",
+    "b200glm_set_state", "b200glm_leapfrog", "b200glm_leapfrog_async", "b200glm_grad_async", "b200glm_sync",
+    "b200glm_stream", "b200glm_result_device", "b200glm_comm_unique_id", "b200glm_comm_init",
+    "b200glm_launch_count", "b200glm_bytes_per_gradient", "b200glm_last_error", "b200glm_version",
+]
+
+
+class Desc(C.Structure):
+    _fields_ = [
+        ("family", C.c_int32), ("K", C.c_int32), ("N", C.c_int64),
+        ("X", C.c_void_p), ("ldx", C.c_int64),
+        ("y_int", C.c_void_p), ("y_real", C.c_void_p),
+        ("G", C.c_int32), ("data_on_device", C.c_int32), ("group", C.c_void_p),
+        ("prior_alpha_sd", C.c_double), ("prior_beta_sd", C.c_double),
+        ("prior_sigma_loc", C.c_double), ("prior_sigma_scale", C.c_double),
+        ("prior_sigma_a_scale", C.c_double),
+        ("device", C.c_int32), ("n_slots", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+        ("N_total", C.c_int64), ("grid_ctas", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m stan_b200.build` "
+                "(there is no CPU fallback for the GLM hot path)")
+        L = C.CDLL(LIB_PATH)
+        dp = C.POINTER(C.c_double)
+        L.b200glm_create.argtypes = [C.POINTER(Desc), C.POINTER(C.c_void_p)]
+        L.b200glm_destroy.argtypes = [C.c_void_p]
+        L.b200glm_destroy.restype = None
+        L.b200glm_num_params.argtypes = [C.c_void_p]
+        L.b200glm_log_prob_grad.argtypes = [C.c_void_p, C.c_int32, dp, C.c_int32, C.c_int32, dp, dp]
+        L.b200glm_log_prob.argtypes = [C.c_void_p, C.c_int32, dp, C.c_int32, C.c_int32, dp]
+        L.b200glm_set_state.argtypes = [C.c_void_p, C.c_int32, dp, dp, dp, C.c_double]
+        L.b200glm_leapfrog.argtypes = [C.c_void_p, C.c_int32, C.c_double, dp, dp, dp, dp, dp]
+        L.b200glm_leapfrog_async.argtypes = [C.c_void_p, C.c_int32, C.c_double]
+        L.b200glm_grad_async.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.b200glm_sync.argtypes = [C.c_void_p, C.c_int32]
+        L.b200glm_stream.argtypes = [C.c_void_p, C.c_int32]
+        L.b200glm_stream.restype = C.c_void_p
+        L.b200glm_result_device.argtypes = [C.c_void_p, C.c_int32]
+        L.b200glm_result_device.restype = C.c_void_p
+        L.b200glm_comm_unique_id.argtypes = [C.c_void_p]
+        L.b200glm_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+        L.b200glm_launch_count.argtypes = [C.c_void_p]
+        L.b200glm_launch_count.restype = C.c_int64
+        L.b200glm_bytes_per_gradient.argtypes = [C.c_void_p]
+        L.b200glm_bytes_per_gradient.restype = C.c_int64
+        L.b200glm_last_error.argtypes = [C.c_void_p]
+        L.b200glm_last_error.restype = C.c_char_p
+        L.b200glm_version.restype = C.c_char_p
+        _lib = L
+    return _lib

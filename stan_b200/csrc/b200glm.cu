@@ -1,0 +1,694 @@
+// b200glm.cu -- C-ABI implementation over the sm_100a kernels (include/b200glm.h).
+//
+// Host side of the boundary: owns device buffers (X in row-panel format, per-slot workspaces and
+// streams), launches, the NCCL all-reduce of the likelihood partials, and status mapping.
+// No CPU fallback: without a usable CUDA device every compute entry point returns B200GLM_CUDA.
+#include "../../include/b200glm.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "glm_kernels.cuh"
+
+using namespace b200glm;
+
+namespace {
+
+// ---------------------------------------------------------------------------- NCCL (dlopen)
+// NCCL is resolved at run time so the library loads on a box without it and shares the copy a
+// host process (e.g. torch) already mapped.  Only ncclAllReduce/ncclCommInitRank are used.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8, ncclSum = 0 };
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (!api.lib) return;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
+  });
+  return api;
+}
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  double* theta = nullptr;       // P
+  double* state[2] = {nullptr, nullptr};  // 3P+1 each
+  int cur = 0;
+  double* inv_metric = nullptr;  // P
+  double* partials = nullptr;    // grid * pstride
+  unsigned int* ticket = nullptr;
+  double* r_out = nullptr;       // n_panels*32 (G > 0)
+  double* lik = nullptr;         // P + 2
+  double* result = nullptr;      // P + 2
+  double* theta_used = nullptr;  // P
+  double* h_pinned = nullptr;    // pinned staging: max(3P+1, P+2) * 2
+  std::mutex mu;
+};
+
+}  // namespace
+
+struct b200glm_handle {
+  b200glm_desc d;
+  int P = 0, off_beta = 0, C = 0;
+  long long n_panels = 0;
+  double* panels = nullptr;
+  long long* seg_ptr = nullptr;  // G+1 (device)
+  int grid = 0, n_stages = 0, stage_a = 0;
+  size_t smem_bytes = 0;
+  int cpl = 0;
+  double lgamma_sum = 0.0;  // local shard
+  double lgamma_sum_total = 0.0;
+  bool bad_y = false;
+  std::vector<Slot*> slots;
+  ncclComm_t comm = nullptr;
+  std::atomic<long long> launches{0};
+  std::mutex err_mu;
+  std::string last_error;
+  void set_error(const std::string& s) {
+    std::lock_guard<std::mutex> g(err_mu);
+    last_error = s;
+  }
+};
+
+namespace {
+
+#define CUDA_TRY(h, expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      (h)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                  \
+      return B200GLM_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+const int kCplChoices[] = {2, 4, 7, 13, 16, 25, 32};
+
+typedef void (*kernel_fn)(const KernelParams);
+
+template <int FAMILY>
+kernel_fn pick_cpl(int cpl) {
+  switch (cpl) {
+    case 2: return glm_fused_kernel<FAMILY, 2>;
+    case 4: return glm_fused_kernel<FAMILY, 4>;
+    case 7: return glm_fused_kernel<FAMILY, 7>;
+    case 13: return glm_fused_kernel<FAMILY, 13>;
+    case 16: return glm_fused_kernel<FAMILY, 16>;
+    case 25: return glm_fused_kernel<FAMILY, 25>;
+    case 32: return glm_fused_kernel<FAMILY, 32>;
+  }
+  return nullptr;
+}
+kernel_fn pick_kernel(int family, int cpl) {
+  switch (family) {
+    case FAM_BERNOULLI_LOGIT: return pick_cpl<FAM_BERNOULLI_LOGIT>(cpl);
+    case FAM_POISSON_LOG: return pick_cpl<FAM_POISSON_LOG>(cpl);
+    case FAM_NORMAL_ID: return pick_cpl<FAM_NORMAL_ID>(cpl);
+  }
+  return nullptr;
+}
+
+size_t fixed_smem_bytes(int K, int G, int stage_a, int S) {
+  const int Kpad = (K + 3) & ~3;
+  size_t b = 0;
+  b += (size_t)Kpad * 8;                                 // sbeta
+  b += (size_t)NUM_CONSUMER_WARPS * 32 * 8;              // sr
+  b += (size_t)NUM_CONSUMER_WARPS * (Kpad + 4) * 8;      // red
+  if (stage_a) b += (size_t)((G + 1) & ~1) * 8;          // sa
+  b += (size_t)2 * S * 8;                                // barriers
+  return b;
+}
+
+int validate_slot(b200glm_handle* h, int slot) {
+  if (!h) return B200GLM_INVALID;
+  if (slot < 0 || slot >= (int)h->slots.size()) {
+    h->set_error("slot out of range");
+    return B200GLM_INVALID;
+  }
+  return B200GLM_OK;
+}
+
+void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int propto, int jacobian, int is_var,
+                 double eps) {
+  std::memset(&p, 0, sizeof(p));
+  p.panels = h->panels;
+  p.n_rows = h->d.N;
+  p.n_panels = h->n_panels;
+  p.K = h->d.K;
+  p.C = h->C;
+  p.G = h->d.G;
+  p.family = h->d.family;
+  p.P = h->P;
+  p.off_beta = h->off_beta;
+  p.n_stages = h->n_stages;
+  p.mode = mode;
+  p.fuse_finish = (h->d.world <= 1 && h->d.G == 0) ? 1 : 0;
+  p.stage_a_in_smem = h->stage_a;
+  p.theta_in = s->theta;
+  p.st_in = s->state[s->cur];
+  p.st_out = s->state[s->cur ^ 1];
+  p.inv_metric = s->inv_metric;
+  p.eps = eps;
+  p.partials = s->partials;
+  p.pstride = (h->d.K + 2 + 1) & ~1;
+  p.ticket = s->ticket;
+  p.r_out = s->r_out;
+  p.lik = s->lik;
+  p.result = s->result;
+  p.theta_used = s->theta_used;
+  ModelConst& mc = p.mc;
+  mc.family = h->d.family;
+  mc.K = h->d.K;
+  mc.G = h->d.G;
+  mc.P = h->P;
+  mc.off_beta = h->off_beta;
+  mc.propto = propto;
+  mc.jacobian = jacobian;
+  mc.is_var = is_var;
+  mc.N_total = (double)(h->d.N_total > 0 ? h->d.N_total : h->d.N);
+  mc.lgamma_sum = h->lgamma_sum_total;
+  mc.prior_alpha_sd = h->d.prior_alpha_sd;
+  mc.prior_beta_sd = h->d.prior_beta_sd;
+  mc.prior_sigma_loc = h->d.prior_sigma_loc;
+  mc.prior_sigma_scale = h->d.prior_sigma_scale;
+  mc.prior_sigma_a_scale = h->d.prior_sigma_a_scale;
+}
+
+// Enqueue one evaluation (all launches + the optional all-reduce) on the slot's stream.
+int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian, int is_var, double eps) {
+  KernelParams p;
+  fill_params(h, s, p, mode, propto, jacobian, is_var, eps);
+  const bool need_likelihood = ((!propto) || is_var) && h->d.N_total != -1;
+  const bool rows_anywhere = (h->d.N_total > 0 ? h->d.N_total : h->d.N) > 0;
+  if (need_likelihood && rows_anywhere) {
+    kernel_fn fn = pick_kernel(h->d.family, h->cpl);
+    fn<<<h->grid, NUM_THREADS, h->smem_bytes, s->stream>>>(p);
+    h->launches++;
+    if (h->d.G > 0) {
+      const int gb = std::min(h->d.G, 4 * 148);
+      group_reduce_kernel<<<gb, 256, 0, s->stream>>>(s->r_out, h->seg_ptr, h->d.G, s->lik + 2);
+      h->launches++;
+    }
+    if (h->d.world > 1) {
+      if (!h->comm) {
+        h->set_error("world > 1 but b200glm_comm_init was not called");
+        return B200GLM_INVALID;
+      }
+      ncclResult_t r = nccl().AllReduce(s->lik, s->lik, (size_t)h->P + 2, ncclFloat64, ncclSum, h->comm, s->stream);
+      if (r != 0) {
+        h->set_error(std::string("ncclAllReduce: ") + (nccl().GetErrorString ? nccl().GetErrorString(r) : "?"));
+        return B200GLM_CUDA;
+      }
+    }
+    if (!p.fuse_finish) {
+      finish_kernel<<<1, NUM_THREADS, 0, s->stream>>>(p);
+      h->launches++;
+    }
+  } else {
+    // nothing data-dependent left (double semantics with propto, or N == 0): epilogue only
+    CUDA_TRY(h, cudaMemsetAsync(s->lik, 0, sizeof(double) * (h->P + 2), s->stream));
+    if (mode == MODE_LEAPFROG) {
+      h->set_error("leapfrog requires the gradient path");
+      return B200GLM_INVALID;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(s->theta_used, s->theta, sizeof(double) * h->P, cudaMemcpyDeviceToDevice, s->stream));
+    finish_kernel<<<1, NUM_THREADS, 0, s->stream>>>(p);
+    h->launches++;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return B200GLM_OK;
+}
+
+int eval_host(b200glm_handle* h, int slot, const double* theta, int propto, int jacobian, int is_var, double* lp,
+              double* grad) {
+  int rc = validate_slot(h, slot);
+  if (rc) return rc;
+  if (!theta || !lp) {
+    h->set_error("null pointer argument");
+    return B200GLM_INVALID;
+  }
+  Slot* s = h->slots[slot];
+  std::lock_guard<std::mutex> g(s->mu);
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  const int P = h->P;
+  std::memcpy(s->h_pinned, theta, sizeof(double) * P);
+  CUDA_TRY(h, cudaMemcpyAsync(s->theta, s->h_pinned, sizeof(double) * P, cudaMemcpyHostToDevice, s->stream));
+  rc = enqueue_eval(h, s, MODE_THETA, propto, jacobian, is_var, 0.0);
+  if (rc) return rc;
+  double* hres = s->h_pinned + (3 * P + 1);
+  CUDA_TRY(h, cudaMemcpyAsync(hres, s->result, sizeof(double) * (P + 2), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(s->stream));
+  if (h->bad_y && (is_var || !propto)) {
+    h->set_error(h->d.family == B200GLM_BERNOULLI_LOGIT
+                     ? "bernoulli_logit_glm_lpmf: Vector of dependent variables is out of range [0, 1]"
+                     : "poisson_log_glm_lpmf: Vector of dependent variables is negative");
+    return B200GLM_DOMAIN;
+  }
+  if (hres[P + 1] != 0.0) {
+    h->set_error("non-finite log density or gradient (parameters, intercept or X*beta not finite)");
+    return B200GLM_DOMAIN;
+  }
+  *lp = hres[0];
+  if (grad) std::memcpy(grad, hres + 1, sizeof(double) * P);
+  return B200GLM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200glm_version(void) { return "b200glm 0.1 (sm_100a, abi 1)"; }
+
+int32_t b200glm_num_params(const b200glm_handle* h) { return h ? h->P : -1; }
+
+const char* b200glm_last_error(const b200glm_handle* h) {
+  static thread_local std::string copy;
+  if (!h) return "null handle";
+  auto* hh = const_cast<b200glm_handle*>(h);
+  std::lock_guard<std::mutex> g(hh->err_mu);
+  copy = hh->last_error;
+  return copy.c_str();
+}
+
+int64_t b200glm_launch_count(const b200glm_handle* h) { return h ? (int64_t)h->launches.load() : 0; }
+
+int64_t b200glm_bytes_per_gradient(const b200glm_handle* h) {
+  if (!h) return 0;
+  // 8*N*K (X once) + 4*N (y int32; 8*N for normal's fp64 y) [+ 4*N group index]
+  const int64_t N = h->d.N, K = h->d.K;
+  int64_t b = 8 * N * K + (h->d.family == B200GLM_NORMAL_ID ? 8 : 4) * N;
+  if (h->d.G > 0) b += 4 * N;
+  return b;
+}
+
+void b200glm_destroy(b200glm_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->d.device);
+  for (Slot* s : h->slots) {
+    if (!s) continue;
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->theta);
+    cudaFree(s->state[0]);
+    cudaFree(s->state[1]);
+    cudaFree(s->inv_metric);
+    cudaFree(s->partials);
+    cudaFree(s->ticket);
+    cudaFree(s->r_out);
+    cudaFree(s->lik);
+    cudaFree(s->result);
+    cudaFree(s->theta_used);
+    if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+  }
+  if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
+  cudaFree(h->panels);
+  cudaFree(h->seg_ptr);
+  delete h;
+}
+
+int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
+  if (!desc || !out) return B200GLM_INVALID;
+  *out = nullptr;
+  b200glm_handle* h = new b200glm_handle();
+  h->d = *desc;
+  auto fail = [&](int code, const std::string& msg) {
+    // keep the handle alive so the caller can read last_error, as documented
+    h->set_error(msg);
+    *out = h;
+    return code;
+  };
+  const b200glm_desc& d = h->d;
+  if (d.family < 0 || d.family > 2) return fail(B200GLM_INVALID, "unknown family");
+  if (d.N < 0 || d.K < 0 || d.G < 0) return fail(B200GLM_INVALID, "negative size");
+  if (d.N > 0 && d.K > 0 && (!d.X || d.ldx < d.N)) return fail(B200GLM_INVALID, "X null or ldx < N");
+  if (d.N > 0 && d.family == B200GLM_NORMAL_ID && !d.y_real) return fail(B200GLM_INVALID, "y_real is null");
+  if (d.N > 0 && d.family != B200GLM_NORMAL_ID && !d.y_int) return fail(B200GLM_INVALID, "y_int is null");
+  if (d.G > 0 && d.N > 0 && !d.group) return fail(B200GLM_INVALID, "group is null");
+  if (!(d.prior_alpha_sd > 0) || !(d.prior_beta_sd > 0)) return fail(B200GLM_INVALID, "prior scales must be > 0");
+  if (d.n_slots < 1) h->d.n_slots = 1;
+  if (d.K > 256) return fail(B200GLM_INVALID, "K > 256 is not supported by the single-CTA panel kernel yet");
+
+  h->P = (d.G > 0 ? 2 + d.G : 1) + d.K + (d.family == B200GLM_NORMAL_ID ? 1 : 0);
+  h->off_beta = d.G > 0 ? 2 + d.G : 1;
+  h->C = d.K + 1 + (d.G > 0 ? 1 : 0);
+  h->n_panels = (d.N + PANEL_ROWS - 1) / PANEL_ROWS;
+  const int P = h->P;
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(B200GLM_CUDA, "no CUDA device available (this backend has no CPU fallback)");
+  if (d.device < 0 || d.device >= ndev) return fail(B200GLM_INVALID, "device ordinal out of range");
+  CUDA_TRY(h, cudaSetDevice(d.device));
+  cudaDeviceProp prop;
+  CUDA_TRY(h, cudaGetDeviceProperties(&prop, d.device));
+  if (prop.major < 10) return fail(B200GLM_CUDA, "device is not sm_100 or newer");
+
+  // launch geometry
+  h->grid = d.grid_ctas > 0 ? d.grid_ctas : prop.multiProcessorCount;
+  const int need_cpl = std::max(1, (d.K + 7) / 8);
+  h->cpl = 0;
+  for (int c : kCplChoices)
+    if (c >= need_cpl) {
+      h->cpl = c;
+      break;
+    }
+  if (!h->cpl) return fail(B200GLM_INVALID, "K too large");
+  h->stage_a = (d.G > 0 && d.G <= SMEM_A_MAX_GROUPS) ? 1 : 0;
+  const size_t max_dyn = (size_t)prop.sharedMemPerBlockOptin - 1024;  // static scratch + slack
+  const size_t tile_bytes = (size_t)h->C * PANEL_ROWS * 8;
+  int S = MAX_STAGES;
+  while (S > 0 && fixed_smem_bytes(d.K, d.G, h->stage_a, S) + (size_t)S * tile_bytes > max_dyn) --S;
+  if (S < 1) return fail(B200GLM_INVALID, "panel does not fit in shared memory");
+  if (S > NUM_CONSUMER_WARPS) S = (S / NUM_CONSUMER_WARPS) * NUM_CONSUMER_WARPS;  // stage <-> warp ownership
+  h->n_stages = S;
+  h->smem_bytes = fixed_smem_bytes(d.K, d.G, h->stage_a, S) + (size_t)S * tile_bytes;
+  kernel_fn fn = pick_kernel(d.family, h->cpl);
+  CUDA_TRY(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+
+  // ---- data upload + re-layout ----
+  cudaStream_t st;
+  CUDA_TRY(h, cudaStreamCreate(&st));
+  const size_t panel_doubles = (size_t)h->n_panels * h->C * PANEL_ROWS;
+  if (panel_doubles) CUDA_TRY(h, cudaMalloc(&h->panels, panel_doubles * 8));
+
+  // y / group on host and device
+  std::vector<int32_t> h_group;
+  int32_t* d_y = nullptr;
+  double* d_yr = nullptr;
+  int32_t* d_group = nullptr;
+  long long* d_perm = nullptr;
+  bool own_y = false, own_group = false;
+  if (d.N > 0) {
+    if (d.data_on_device) {
+      d_y = const_cast<int32_t*>(d.y_int);
+      d_yr = const_cast<double*>(d.y_real);
+      d_group = const_cast<int32_t*>(d.group);
+    } else {
+      if (d.family == B200GLM_NORMAL_ID) {
+        CUDA_TRY(h, cudaMalloc(&d_yr, sizeof(double) * d.N));
+        CUDA_TRY(h, cudaMemcpy(d_yr, d.y_real, sizeof(double) * d.N, cudaMemcpyHostToDevice));
+      } else {
+        CUDA_TRY(h, cudaMalloc(&d_y, sizeof(int32_t) * d.N));
+        CUDA_TRY(h, cudaMemcpy(d_y, d.y_int, sizeof(int32_t) * d.N, cudaMemcpyHostToDevice));
+      }
+      own_y = true;
+      if (d.G > 0) {
+        CUDA_TRY(h, cudaMalloc(&d_group, sizeof(int32_t) * d.N));
+        CUDA_TRY(h, cudaMemcpy(d_group, d.group, sizeof(int32_t) * d.N, cudaMemcpyHostToDevice));
+        own_group = true;
+      }
+    }
+  }
+  // data checks + lgamma constant
+  if (d.N > 0 && d.family != B200GLM_NORMAL_ID) {
+    const int nb = 296;
+    double* d_stats;
+    CUDA_TRY(h, cudaMalloc(&d_stats, sizeof(double) * 2 * nb));
+    y_stats_kernel<<<nb, 256, 0, st>>>(d_y, d.N, d.family, d_stats);
+    std::vector<double> hs(2 * nb);
+    CUDA_TRY(h, cudaMemcpyAsync(hs.data(), d_stats, sizeof(double) * 2 * nb, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    cudaFree(d_stats);
+    double bad = 0, lg = 0;
+    for (int i = 0; i < nb; ++i) {
+      bad += hs[2 * i];
+      lg += hs[2 * i + 1];
+    }
+    h->bad_y = bad > 0;
+    h->lgamma_sum = lg;
+    h->lgamma_sum_total = lg;
+  }
+  // group sort (stable counting sort on the host; rows of a group become contiguous)
+  if (d.G > 0) {
+    h_group.resize(d.N);
+    if (d.N > 0) {
+      if (d.data_on_device)
+        CUDA_TRY(h, cudaMemcpy(h_group.data(), d_group, sizeof(int32_t) * d.N, cudaMemcpyDeviceToHost));
+      else
+        std::memcpy(h_group.data(), d.group, sizeof(int32_t) * d.N);
+    }
+    std::vector<long long> seg(d.G + 1, 0);
+    for (long long i = 0; i < d.N; ++i) {
+      const int g = h_group[i];
+      if (g < 1 || g > d.G) {
+        if (own_y) { cudaFree(d_y); cudaFree(d_yr); }
+        if (own_group) cudaFree(d_group);
+        return fail(B200GLM_INVALID, "group index out of range [1, G]");
+      }
+      seg[g]++;
+    }
+    for (int g = 0; g < d.G; ++g) seg[g + 1] += seg[g];
+    std::vector<long long> perm(std::max<long long>(d.N, 1));
+    {
+      std::vector<long long> cursor(seg.begin(), seg.end() - 1);
+      for (long long i = 0; i < d.N; ++i) perm[cursor[h_group[i] - 1]++] = i;
+    }
+    CUDA_TRY(h, cudaMalloc(&h->seg_ptr, sizeof(long long) * (d.G + 1)));
+    CUDA_TRY(h, cudaMemcpy(h->seg_ptr, seg.data(), sizeof(long long) * (d.G + 1), cudaMemcpyHostToDevice));
+    if (d.N > 0) {
+      CUDA_TRY(h, cudaMalloc(&d_perm, sizeof(long long) * d.N));
+      CUDA_TRY(h, cudaMemcpy(d_perm, perm.data(), sizeof(long long) * d.N, cudaMemcpyHostToDevice));
+    }
+  }
+  // X: device-resident or staged from the host in row chunks
+  if (d.N > 0) {
+    if (d.data_on_device || d.K == 0) {
+      relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(d.X, d.ldx, 0, d_y, d_yr, d_group, d_perm, 0, d.N,
+                                                                    d.N, d.K, h->C, 0, h->C, h->panels);
+      CUDA_TRY(h, cudaGetLastError());
+    } else if (d_perm) {
+      // permuted gather needs all of X on the device at once
+      double* dX;
+      CUDA_TRY(h, cudaMalloc(&dX, sizeof(double) * (size_t)d.N * d.K));
+      CUDA_TRY(h, cudaMemcpy2D(dX, sizeof(double) * d.N, d.X, sizeof(double) * d.ldx, sizeof(double) * d.N, d.K,
+                               cudaMemcpyHostToDevice));
+      relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(dX, d.N, 0, d_y, d_yr, d_group, d_perm, 0, d.N,
+                                                                    d.N, d.K, h->C, 0, h->C, h->panels);
+      CUDA_TRY(h, cudaStreamSynchronize(st));
+      cudaFree(dX);
+    } else {
+      const long long chunk_rows = std::max<long long>(32, ((long long)(256u << 20) / (8LL * d.K)) & ~31LL);
+      double* dX;
+      CUDA_TRY(h, cudaMalloc(&dX, sizeof(double) * (size_t)std::min(chunk_rows, (long long)d.N) * d.K));
+      for (long long r0 = 0; r0 < d.N; r0 += chunk_rows) {
+        const long long nr = std::min(chunk_rows, (long long)d.N - r0);
+        CUDA_TRY(h, cudaMemcpy2DAsync(dX, sizeof(double) * nr, d.X + r0, sizeof(double) * d.ldx, sizeof(double) * nr,
+                                      d.K, cudaMemcpyHostToDevice, st));
+        relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(dX, nr, r0, nullptr, nullptr, nullptr, nullptr,
+                                                                      r0, nr, d.N, d.K, h->C, 0, d.K, h->panels);
+        CUDA_TRY(h, cudaStreamSynchronize(st));
+      }
+      cudaFree(dX);
+      // aux columns (y, group) in one more pass
+      relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(nullptr, 0, 0, d_y, d_yr, d_group, nullptr, 0, d.N,
+                                                                    d.N, d.K, h->C, d.K, h->C, h->panels);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+  }
+  if (own_y) { cudaFree(d_y); cudaFree(d_yr); }
+  if (own_group) cudaFree(d_group);
+  cudaFree(d_perm);
+  cudaStreamDestroy(st);
+
+  // ---- slots ----
+  const int pstride = (d.K + 2 + 1) & ~1;
+  for (int i = 0; i < h->d.n_slots; ++i) {
+    Slot* s = new Slot();
+    h->slots.push_back(s);
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaMalloc(&s->theta, sizeof(double) * std::max(P, 1)));
+    for (int b = 0; b < 2; ++b) {
+      CUDA_TRY(h, cudaMalloc(&s->state[b], sizeof(double) * (3 * P + 1)));
+      CUDA_TRY(h, cudaMemset(s->state[b], 0, sizeof(double) * (3 * P + 1)));
+    }
+    CUDA_TRY(h, cudaMalloc(&s->inv_metric, sizeof(double) * std::max(P, 1)));
+    std::vector<double> ones(std::max(P, 1), 1.0);
+    CUDA_TRY(h, cudaMemcpy(s->inv_metric, ones.data(), sizeof(double) * P, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMalloc(&s->partials, sizeof(double) * (size_t)h->grid * pstride));
+    CUDA_TRY(h, cudaMalloc(&s->ticket, sizeof(unsigned int)));
+    CUDA_TRY(h, cudaMemset(s->ticket, 0, sizeof(unsigned int)));
+    if (d.G > 0 && h->n_panels > 0) CUDA_TRY(h, cudaMalloc(&s->r_out, sizeof(double) * h->n_panels * PANEL_ROWS));
+    CUDA_TRY(h, cudaMalloc(&s->lik, sizeof(double) * (P + 2)));
+    CUDA_TRY(h, cudaMemset(s->lik, 0, sizeof(double) * (P + 2)));
+    CUDA_TRY(h, cudaMalloc(&s->result, sizeof(double) * (P + 2)));
+    CUDA_TRY(h, cudaMalloc(&s->theta_used, sizeof(double) * std::max(P, 1)));
+    CUDA_TRY(h, cudaMallocHost(&s->h_pinned, sizeof(double) * (2 * (3 * P + 1) + P + 2)));
+  }
+  *out = h;
+  return B200GLM_OK;
+}
+
+int b200glm_log_prob_grad(b200glm_handle* h, int32_t slot, const double* theta, int32_t propto, int32_t jacobian,
+                          double* lp, double* grad) {
+  return eval_host(h, slot, theta, propto ? 1 : 0, jacobian ? 1 : 0, 1, lp, grad);
+}
+
+int b200glm_log_prob(b200glm_handle* h, int32_t slot, const double* theta, int32_t propto, int32_t jacobian,
+                     double* lp) {
+  return eval_host(h, slot, theta, propto ? 1 : 0, jacobian ? 1 : 0, 0, lp, nullptr);
+}
+
+int b200glm_set_state(b200glm_handle* h, int32_t slot, const double* q, const double* p, const double* g, double V) {
+  int rc = validate_slot(h, slot);
+  if (rc) return rc;
+  if (!q || !p || !g) {
+    h->set_error("null pointer argument");
+    return B200GLM_INVALID;
+  }
+  Slot* s = h->slots[slot];
+  std::lock_guard<std::mutex> lk(s->mu);
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  const int P = h->P;
+  double* hp = s->h_pinned;
+  std::memcpy(hp, q, sizeof(double) * P);
+  std::memcpy(hp + P, p, sizeof(double) * P);
+  std::memcpy(hp + 2 * P, g, sizeof(double) * P);
+  hp[3 * P] = V;
+  CUDA_TRY(h, cudaMemcpyAsync(s->state[s->cur], hp, sizeof(double) * (3 * P + 1), cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(s->stream));
+  return B200GLM_OK;
+}
+
+int b200glm_leapfrog_async(b200glm_handle* h, int32_t slot, double eps) {
+  int rc = validate_slot(h, slot);
+  if (rc) return rc;
+  Slot* s = h->slots[slot];
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  rc = enqueue_eval(h, s, MODE_LEAPFROG, 1, 1, 1, eps);
+  if (rc) return rc;
+  s->cur ^= 1;
+  return B200GLM_OK;
+}
+
+int b200glm_leapfrog(b200glm_handle* h, int32_t slot, double eps, const double* inv_metric, double* q, double* p,
+                     double* g, double* V) {
+  int rc = validate_slot(h, slot);
+  if (rc) return rc;
+  Slot* s = h->slots[slot];
+  std::lock_guard<std::mutex> lk(s->mu);
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  const int P = h->P;
+  if (inv_metric) {
+    double* hm = s->h_pinned + (3 * P + 1) + (P + 2);
+    std::memcpy(hm, inv_metric, sizeof(double) * P);
+    CUDA_TRY(h, cudaMemcpyAsync(s->inv_metric, hm, sizeof(double) * P, cudaMemcpyHostToDevice, s->stream));
+  }
+  rc = enqueue_eval(h, s, MODE_LEAPFROG, 1, 1, 1, eps);
+  if (rc) return rc;
+  s->cur ^= 1;
+  double* hp = s->h_pinned;
+  CUDA_TRY(h, cudaMemcpyAsync(hp, s->state[s->cur], sizeof(double) * (3 * P + 1), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(s->stream));
+  if (q) std::memcpy(q, hp, sizeof(double) * P);
+  if (p) std::memcpy(p, hp + P, sizeof(double) * P);
+  if (g) std::memcpy(g, hp + 2 * P, sizeof(double) * P);
+  if (V) *V = hp[3 * P];
+  if (h->bad_y) {
+    h->set_error("dependent variable out of range");
+    return B200GLM_DOMAIN;
+  }
+  return B200GLM_OK;
+}
+
+int b200glm_grad_async(b200glm_handle* h, int32_t slot, const double* theta_device) {
+  int rc = validate_slot(h, slot);
+  if (rc) return rc;
+  Slot* s = h->slots[slot];
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  if (theta_device)
+    CUDA_TRY(h, cudaMemcpyAsync(s->theta, theta_device, sizeof(double) * h->P, cudaMemcpyDeviceToDevice, s->stream));
+  return enqueue_eval(h, s, MODE_THETA, 1, 1, 1, 0.0);
+}
+
+int b200glm_sync(b200glm_handle* h, int32_t slot) {
+  int rc = validate_slot(h, slot);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->slots[slot]->stream));
+  return B200GLM_OK;
+}
+
+void* b200glm_stream(b200glm_handle* h, int32_t slot) {
+  if (validate_slot(h, slot)) return nullptr;
+  return (void*)h->slots[slot]->stream;
+}
+
+const double* b200glm_result_device(b200glm_handle* h, int32_t slot) {
+  if (validate_slot(h, slot)) return nullptr;
+  return h->slots[slot]->result;
+}
+
+int b200glm_comm_unique_id(void* unique_id_128) {
+  if (!unique_id_128 || !nccl().ok) return B200GLM_CUDA;
+  ncclUniqueId id;
+  if (nccl().GetUniqueId(&id) != 0) return B200GLM_CUDA;
+  std::memcpy(unique_id_128, &id, sizeof(id));
+  return B200GLM_OK;
+}
+
+int b200glm_comm_init(b200glm_handle* h, const void* unique_id_128, int32_t rank, int32_t world) {
+  if (!h || !unique_id_128) return B200GLM_INVALID;
+  if (!nccl().ok) {
+    h->set_error("libnccl.so.2 could not be loaded");
+    return B200GLM_CUDA;
+  }
+  if (rank != h->d.rank || world != h->d.world) {
+    h->set_error("rank/world differ from the ones given to b200glm_create");
+    return B200GLM_INVALID;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id_128, sizeof(id));
+  ncclResult_t r = nccl().CommInitRank(&h->comm, world, id, rank);
+  if (r != 0) {
+    h->set_error(std::string("ncclCommInitRank: ") + (nccl().GetErrorString ? nccl().GetErrorString(r) : "?"));
+    return B200GLM_CUDA;
+  }
+  // the propto=false poisson constant is a sum over all shards
+  if (h->d.family == B200GLM_POISSON_LOG) {
+    double* dv;
+    CUDA_TRY(h, cudaMalloc(&dv, sizeof(double)));
+    CUDA_TRY(h, cudaMemcpy(dv, &h->lgamma_sum, sizeof(double), cudaMemcpyHostToDevice));
+    cudaStream_t st = h->slots[0]->stream;
+    if (nccl().AllReduce(dv, dv, 1, ncclFloat64, ncclSum, h->comm, st) != 0) {
+      h->set_error("ncclAllReduce(lgamma_sum) failed");
+      return B200GLM_CUDA;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(&h->lgamma_sum_total, dv, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    cudaFree(dv);
+  }
+  return B200GLM_OK;
+}
+
+}  // extern "C"

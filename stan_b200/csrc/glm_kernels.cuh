@@ -1,0 +1,654 @@
+// glm_kernels.cuh -- hand-written sm_100a kernels for the GLM log-density + gradient hot path.
+//
+// What is computed is the arithmetic of the reference's three GLM densities
+//   stan::math::bernoulli_logit_glm_lpmf  (SM/prim/prob/bernoulli_logit_glm_lpmf.hpp:105-164)
+//   stan::math::poisson_log_glm_lpmf      (SM/prim/prob/poisson_log_glm_lpmf.hpp:107-161)
+//   stan::math::normal_id_glm_lpdf        (SM/prim/prob/normal_id_glm_lpdf.hpp:117-213)
+// plus the model wrapper (priors, lb_constrain Jacobian) and the leapfrog update
+// (ST/mcmc/hmc/integrators/expl_leapfrog.hpp:16-32).  How it is computed is new: ONE pass over X.
+//
+// Data layout in HBM ("row-panel format", built once at upload by relayout_kernel):
+//   rows are cut into panels of 32; panel p is one contiguous block of C = K + n_aux columns,
+//   each column 32 doubles:  panel[p][c][ r ^ swz(c) ],  swz(c) = (c & 3) << 2.
+//   aux column K holds y (as double), aux column K+1 the 1-based group id (as double) when G > 0.
+//   One panel = C*256 bytes = one cp.async.bulk (TMA, SASS UBLKCP) into one shared-memory stage.
+//   The XOR swizzle makes BOTH access patterns below bank-conflict free.
+//
+// Main kernel (persistent, one CTA per SM, 1 TMA producer warp + 8 consumer warps):
+//   producer : streams this CTA's panels (p = cta, cta+grid, ...) through an S-stage mbarrier ring.
+//   consumer warp w takes the CTA's n-th panel when n % 8 == w and, from that smem stage only,
+//     phase 1 (lane = row):        eta_r = sum_c X[r][c]*beta[c] + alpha|a[group_r];  link -> lp_r, r_r
+//     phase 2 (lane = (cg, rg)):   acc[s] += X[rg+4m][cg+8s] * r[rg+4m]   (private accumulators,
+//                                   reduced across lanes/warps/CTAs only once, at the end)
+//   last CTA (ticket) sums the per-CTA partials in fixed order -> deterministic result, then
+//   (single-GPU, no groups) runs the model epilogue: priors, Jacobian, leapfrog half-step.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace b200glm {
+
+constexpr int PANEL_ROWS = 32;
+constexpr int NUM_CONSUMER_WARPS = 8;
+constexpr int NUM_THREADS = (NUM_CONSUMER_WARPS + 1) * 32;
+constexpr int MAX_STAGES = 32;
+constexpr int SMEM_A_MAX_GROUPS = 2048;  // a[G] staged in smem up to this many groups
+
+enum { FAM_BERNOULLI_LOGIT = 0, FAM_POISSON_LOG = 1, FAM_NORMAL_ID = 2 };
+enum { MODE_THETA = 0, MODE_LEAPFROG = 1 };
+enum { ST_OK = 0, ST_DOMAIN = 1 };
+
+#define NEG_LOG_SQRT_TWO_PI_D (-0.91893853320467274178032973640562)
+
+// Everything the epilogue needs to turn likelihood sums into the model's lp / gradient.
+struct ModelConst {
+  int family, K, G, P, off_beta;
+  int propto, jacobian, is_var;  // semantics of this evaluation (see include/b200glm.h)
+  double N_total;                // rows over all shards
+  double lgamma_sum;             // sum lgamma(y+1) over all shards (poisson, propto=0)
+  double prior_alpha_sd, prior_beta_sd, prior_sigma_loc, prior_sigma_scale, prior_sigma_a_scale;
+};
+
+struct KernelParams {
+  const double* panels;
+  long long n_rows;    // local rows
+  long long n_panels;  // local panels
+  int K, C, G, family, P, off_beta;
+  int n_stages;
+  int mode;
+  int fuse_finish;     // last CTA also runs finish() (world == 1 && G == 0)
+  int stage_a_in_smem;
+  const double* theta_in;   // MODE_THETA: P doubles (device)
+  const double* st_in;      // MODE_LEAPFROG: [q(P) p(P) g(P) V]
+  double* st_out;
+  const double* inv_metric; // P doubles
+  double eps;
+  double* partials;         // [grid][pstride]: [0,K) beta grads, [K] lp-sum, [K+1] r-sum
+  int pstride;
+  unsigned int* ticket;
+  double* r_out;            // G > 0: residual per (sorted) row
+  double* lik;              // [P] likelihood gradient aligned with theta, [P] lp-sum, [P+1] spare
+  double* result;           // [lp, grad(P), status]
+  double* theta_used;       // P doubles: the theta this launch evaluated (q_new in leapfrog mode)
+  ModelConst mc;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA engine)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                            uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Link functions: per-row log-density term and residual (derivative wrt eta)
+// ------------------------------------------------------------------------------------------
+template <int FAMILY>
+__device__ __forceinline__ void link(double eta, double y, double inv_sigma, double& lp_i, double& r_i) {
+  if (FAMILY == FAM_BERNOULLI_LOGIT) {
+    // bernoulli_logit_glm_lpmf.hpp:105-106 signs, :114-115 ytheta, :121-126 logp, :137-142 derivative
+    const double sg = 2.0 * y - 1.0;
+    const double t = sg * eta;
+    const double e = exp(-t);
+    const double cutoff = 20.0;
+    if (t > cutoff) {
+      lp_i = -e;
+      r_i = -e;  // reference quirk kept: no sign factor on this branch
+    } else if (t < -cutoff) {
+      lp_i = t;
+      r_i = sg;
+    } else {
+      lp_i = -log1p(e);
+      r_i = sg * e / (e + 1.0);
+    }
+  } else if (FAMILY == FAM_POISSON_LOG) {
+    // poisson_log_glm_lpmf.hpp:117-118 theta_derivative, :131-132 logp
+    const double ex = exp(eta);
+    r_i = y - ex;
+    lp_i = y * eta - ex;
+  } else {
+    // normal_id_glm_lpdf.hpp:130-133 y_scaled, :140 mu_derivative; lp_i accumulates y_scaled^2
+    const double z = (y - eta) * inv_sigma;
+    r_i = inv_sigma * z;
+    lp_i = z * z;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Model epilogue, run by ONE CTA once the likelihood sums are complete in p.lik.
+//   theta: the evaluated point (p.theta_used).
+// ------------------------------------------------------------------------------------------
+__device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratch */) {
+  const ModelConst& mc = p.mc;
+  const int P = mc.P, K = mc.K, G = mc.G;
+  const double* theta = p.theta_used;
+  const double* lik = p.lik;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const bool dens = (!mc.propto) || mc.is_var;  // include_summand: anything left to compute?
+
+  const double alpha = G > 0 ? 0.0 : theta[0];
+  const double mu_a = G > 0 ? theta[0] : 0.0;
+  const double u_sa = G > 0 ? theta[1] : 0.0;
+  const double sigma_a = G > 0 ? exp(u_sa) : 1.0;
+  const double u_s = mc.family == FAM_NORMAL_ID ? theta[P - 1] : 0.0;
+  const double sigma = mc.family == FAM_NORMAL_ID ? exp(u_s) : 1.0;
+  const double ib2 = 1.0 / (mc.prior_beta_sd * mc.prior_beta_sd);
+  const double isa2 = 1.0 / (sigma_a * sigma_a);
+
+  // block-wide sums: [0] sum beta^2, [1] sum (a-mu)^2, [2] non-finite count
+  double sb = 0.0, sa = 0.0, bad = 0.0;
+  for (int k = tid; k < K; k += nt) {
+    const double b = theta[mc.off_beta + k];
+    sb += b * b;
+  }
+  for (int g = tid; g < G; g += nt) {
+    const double d = theta[2 + g] - mu_a;
+    sa += d * d;
+  }
+  for (int i = tid; i < P; i += nt) {
+    if (!isfinite(theta[i]) || !isfinite(lik[i])) bad += 1.0;
+  }
+  sb = warp_sum(sb);
+  sa = warp_sum(sa);
+  bad = warp_sum(bad);
+  __syncthreads();
+  const int w = tid >> 5, nw = (nt + 31) >> 5;
+  if ((tid & 31) == 0) {
+    sh[w] = sb;
+    sh[16 + w] = sa;
+    sh[32 + w] = bad;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int i = 0; i < nw; ++i) {
+      a0 += sh[i];
+      a1 += sh[16 + i];
+      a2 += sh[32 + i];
+    }
+    sh[48] = a0;
+    sh[49] = a1;
+    sh[50] = a2;
+  }
+  __syncthreads();
+  const double sum_b2 = sh[48], sum_d2 = sh[49];
+  const double n_bad = sh[50];
+
+  // ---- value (thread 0) ----
+  if (tid == 0) {
+    double lp = 0.0;
+    if (mc.jacobian) {
+      if (G > 0) lp += u_sa;                           // lb_constrain.hpp:64
+      if (mc.family == FAM_NORMAL_ID) lp += u_s;
+    }
+    if (dens) {
+      // priors: normal_lpdf.hpp:81-88
+      if (G > 0) {
+        const double z0 = mu_a / mc.prior_alpha_sd;
+        lp += -0.5 * z0 * z0;
+        const double z1 = sigma_a / mc.prior_sigma_a_scale;
+        lp += -0.5 * z1 * z1;
+        lp += -0.5 * sum_d2 * isa2 - G * u_sa;         // -G log sigma_a (sigma_a is a parameter)
+        if (!mc.propto)
+          lp += 2.0 * NEG_LOG_SQRT_TWO_PI_D - log(mc.prior_alpha_sd) - log(mc.prior_sigma_a_scale)
+                + G * NEG_LOG_SQRT_TWO_PI_D;
+      } else {
+        const double z0 = alpha / mc.prior_alpha_sd;
+        lp += -0.5 * z0 * z0;
+        if (!mc.propto) lp += NEG_LOG_SQRT_TWO_PI_D - log(mc.prior_alpha_sd);
+      }
+      if (K > 0) {
+        lp += -0.5 * sum_b2 * ib2;
+        if (!mc.propto) lp += K * (NEG_LOG_SQRT_TWO_PI_D - log(mc.prior_beta_sd));
+      }
+      if (mc.family == FAM_NORMAL_ID) {
+        const double z = (sigma - mc.prior_sigma_loc) / mc.prior_sigma_scale;
+        lp += -0.5 * z * z;
+        if (!mc.propto) lp += NEG_LOG_SQRT_TWO_PI_D - log(mc.prior_sigma_scale);
+      }
+      // likelihood
+      if (mc.N_total > 0) {
+        const double S = lik[P];
+        if (mc.family == FAM_BERNOULLI_LOGIT) {
+          lp += S;
+        } else if (mc.family == FAM_POISSON_LOG) {
+          lp += S;
+          if (!mc.propto) lp -= mc.lgamma_sum;         // poisson_log_glm_lpmf.hpp:127-129
+        } else {
+          if (!mc.propto) lp += NEG_LOG_SQRT_TWO_PI_D * mc.N_total;   // normal_id_glm_lpdf.hpp:202-204
+          lp -= mc.N_total * u_s;                                     // :205-212, log sigma = u_s
+          lp -= 0.5 * S;                                              // :213
+        }
+      }
+    }
+    const bool ok = isfinite(lp) && n_bad == 0.0;
+    sh[51] = lp;
+    sh[52] = ok ? 0.0 : 1.0;
+  }
+  __syncthreads();
+  const double lp = sh[51];
+  const bool domain = sh[52] != 0.0;
+
+  // ---- gradient wrt unconstrained theta, one thread per entry ----
+  for (int i = tid; i < P; i += nt) {
+    double g = lik[i];
+    if (G > 0) {
+      if (i == 0) {
+        g = -mu_a / (mc.prior_alpha_sd * mc.prior_alpha_sd) + 0.0;  // + sum_g (a_g-mu)/sigma_a^2 below
+      } else if (i == 1) {
+        g = 0.0;
+      } else if (i < 2 + G) {
+        g += -(theta[i] - mu_a) * isa2;
+      }
+    } else if (i == 0) {
+      g += -alpha / (mc.prior_alpha_sd * mc.prior_alpha_sd);
+    }
+    if (i >= mc.off_beta && i < mc.off_beta + K) g += -theta[i] * ib2;
+    if (mc.family == FAM_NORMAL_ID && i == P - 1) {
+      const double dlik = mc.N_total > 0 ? (lik[P] - mc.N_total) / sigma : 0.0;  // normal_id_glm_lpdf.hpp:181-183
+      const double dpri = -(sigma - mc.prior_sigma_loc) / (mc.prior_sigma_scale * mc.prior_sigma_scale);
+      g = (dlik + dpri) * sigma + (mc.jacobian ? 1.0 : 0.0);
+    }
+    p.result[1 + i] = g;
+  }
+  __syncthreads();
+  if (G > 0) {  // mu_a and sigma_a entries need sums over the G group intercepts
+    double sd = 0.0;
+    for (int g = tid; g < G; g += nt) sd += theta[2 + g] - mu_a;
+    sd = warp_sum(sd);
+    __syncthreads();
+    if ((tid & 31) == 0) sh[w] = sd;
+    __syncthreads();
+    if (tid == 0) {
+      double tot = 0;
+      for (int i = 0; i < nw; ++i) tot += sh[i];
+      p.result[1 + 0] += tot * isa2;
+      const double dsa = -sigma_a / (mc.prior_sigma_a_scale * mc.prior_sigma_a_scale)
+                         + sum_d2 * isa2 / sigma_a - G / sigma_a;
+      p.result[1 + 1] = dsa * sigma_a + (mc.jacobian ? 1.0 : 0.0);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    p.result[0] = lp;
+    p.result[1 + P] = domain ? (double)ST_DOMAIN : (double)ST_OK;
+  }
+
+  // ---- leapfrog tail (expl_leapfrog.hpp:28-32 end_update_p; base_hamiltonian.hpp:64-69) ----
+  if (p.mode == MODE_LEAPFROG) {
+    const double* q0 = p.st_in;
+    const double* p0 = p.st_in + P;
+    const double* g0 = p.st_in + 2 * P;
+    double* qn = p.st_out;
+    double* pn = p.st_out + P;
+    double* gn = p.st_out + 2 * P;
+    const double he = 0.5 * p.eps;
+    for (int i = tid; i < P; i += nt) {
+      const double ph = p0[i] - he * g0[i];
+      const double gnew = domain ? -g0[i] : -p.result[1 + i];
+      qn[i] = theta[i];
+      gn[i] = gnew;
+      pn[i] = ph - he * gnew;
+      (void)q0;
+    }
+    if (tid == 0) p.st_out[3 * P] = domain ? CUDART_INF : -lp;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// The main kernel
+// ------------------------------------------------------------------------------------------
+template <int FAMILY, int CPL>
+__global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int K = p.K, C = p.C, G = p.G, P = p.P;
+  const int S = p.n_stages;
+  const int tile_doubles = C * PANEL_ROWS;
+  const int Kpad = (K + 3) & ~3;
+
+  // carve shared memory
+  double* tiles = reinterpret_cast<double*>(smem_raw);                  // S * tile_doubles
+  double* sbeta = tiles + (size_t)S * tile_doubles;                     // Kpad
+  double* sr = sbeta + Kpad;                                            // 8 * 32
+  double* red = sr + NUM_CONSUMER_WARPS * 32;                           // 8 * (Kpad + 4)
+  double* sa = red + NUM_CONSUMER_WARPS * (Kpad + 4);                   // G (optional)
+  double* after_a = sa + (p.stage_a_in_smem ? ((G + 1) & ~1) : 0);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(after_a);            // S
+  uint64_t* empty_bar = full_bar + S;                                   // S
+  __shared__ double sh_scratch[64];
+  __shared__ int sh_is_last;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+
+  // ---- theta for this launch (leapfrog: begin_update_p + update_q, expl_leapfrog.hpp:16-26) ----
+  auto theta_at = [&](int i) -> double {
+    if (p.mode == MODE_LEAPFROG) {
+      const double ph = p.st_in[P + i] - (0.5 * p.eps) * p.st_in[2 * P + i];
+      return p.st_in[i] + p.eps * (p.inv_metric[i] * ph);
+    }
+    return p.theta_in[i];
+  };
+  for (int k = tid; k < Kpad; k += NUM_THREADS) sbeta[k] = k < K ? theta_at(p.off_beta + k) : 0.0;
+  if (p.stage_a_in_smem)
+    for (int g = tid; g < G; g += NUM_THREADS) sa[g] = theta_at(2 + g);
+  if (blockIdx.x == 0)
+    for (int i = tid; i < P; i += NUM_THREADS) p.theta_used[i] = theta_at(i);
+  const double alpha = G > 0 ? 0.0 : theta_at(0);
+  double inv_sigma = 1.0;
+  if (FAMILY == FAM_NORMAL_ID) inv_sigma = 1.0 / exp(theta_at(P - 1));  // normal_id_glm_lpdf.hpp:117
+  __syncthreads();
+
+  const long long n_panels = p.n_panels;
+  const int grid = gridDim.x;
+
+  double acc[CPL];
+#pragma unroll
+  for (int s = 0; s < CPL; ++s) acc[s] = 0.0;
+  double lp_acc = 0.0, r_acc = 0.0;
+
+  if (warp == NUM_CONSUMER_WARPS) {
+    // ===================== TMA producer (one elected lane) =====================
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_first();
+      const uint32_t bytes = (uint32_t)tile_doubles * 8u;
+      int s = 0;
+      uint32_t round = 0;
+      for (long long pi = blockIdx.x; pi < n_panels; pi += grid) {
+        if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+        mbar_arrive_expect_tx(&full_bar[s], bytes);
+        tma_load_1d(tiles + (size_t)s * tile_doubles, p.panels + (size_t)pi * tile_doubles, bytes,
+                    &full_bar[s], pol);
+        if (++s == S) {
+          s = 0;
+          ++round;
+        }
+      }
+    }
+  } else if (warp < (S < NUM_CONSUMER_WARPS ? S : NUM_CONSUMER_WARPS)) {
+    // ===================== consumers =====================
+    // Stage s is only ever consumed by warp s % W_act (S is a multiple of W_act), so every wait
+    // on full[s] is issued by a warp that has observed all earlier phases of that barrier.
+    const int W_act = S < NUM_CONSUMER_WARPS ? S : NUM_CONSUMER_WARPS;
+    const int rg = lane & 3, cg = lane >> 2, cgl = cg & 3;
+    const int o1 = lane ^ 4, o2 = lane ^ 8, o3 = lane ^ 12;
+    const int ycol = K * 32 + (lane ^ ((K & 3) << 2));
+    const int gcol = (K + 1) * 32 + (lane ^ (((K + 1) & 3) << 2));
+    int off[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) off[m] = rg + 4 * (m ^ cgl);
+    double* my_sr = sr + warp * 32;
+
+    long long n = warp;  // index of this panel in the CTA's sequence
+    for (long long pi = (long long)blockIdx.x + (long long)warp * grid; pi < n_panels;
+         pi += (long long)W_act * grid, n += W_act) {
+      const int s = (int)(n % S);
+      const uint32_t parity = (uint32_t)((n / S) & 1);
+      mbar_wait(&full_bar[s], parity);
+      const double* tile = tiles + (size_t)s * tile_doubles;
+
+      // ---- phase 1: eta for row `lane` ----
+      double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+      int c = 0;
+#pragma unroll 4
+      for (; c + 4 <= K; c += 4) {
+        const double2 b01 = *reinterpret_cast<const double2*>(sbeta + c);
+        const double2 b23 = *reinterpret_cast<const double2*>(sbeta + c + 2);
+        e0 = fma(tile[(c + 0) * 32 + lane], b01.x, e0);
+        e1 = fma(tile[(c + 1) * 32 + o1], b01.y, e1);
+        e2 = fma(tile[(c + 2) * 32 + o2], b23.x, e2);
+        e3 = fma(tile[(c + 3) * 32 + o3], b23.y, e3);
+      }
+      for (; c < K; ++c) e0 = fma(tile[c * 32 + (lane ^ ((c & 3) << 2))], sbeta[c], e0);
+      double eta = (e0 + e1) + (e2 + e3);
+      const double y = tile[ycol];
+      if (G > 0) {
+        const int gi = (int)tile[gcol] - 1;
+        const bool gok = gi >= 0 && gi < G;
+        eta += p.stage_a_in_smem ? sa[gok ? gi : 0] : theta_at(2 + (gok ? gi : 0));
+      } else {
+        eta += alpha;
+      }
+      const bool valid = (pi * PANEL_ROWS + lane) < p.n_rows;
+      double lp_i, r_i;
+      link<FAMILY>(eta, y, inv_sigma, lp_i, r_i);
+      if (!valid) {
+        lp_i = 0.0;
+        r_i = 0.0;
+      }
+      lp_acc += lp_i;
+      r_acc += r_i;
+      if (G > 0) p.r_out[pi * PANEL_ROWS + lane] = r_i;
+
+      // ---- phase 2: X^T r from the same smem tile ----
+      my_sr[lane] = r_i;
+      __syncwarp();
+      double rr[8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) rr[m] = my_sr[rg + 4 * m];
+      const double* base = tile + cg * 32;
+#pragma unroll
+      for (int s2 = 0; s2 < CPL; ++s2) {
+        if (s2 * 8 < K) {
+          if (cg + 8 * s2 < K) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) acc[s2] = fma(base[s2 * 256 + off[m]], rr[m], acc[s2]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+
+    // ---- per-warp reduction of the private accumulators ----
+#pragma unroll
+    for (int s2 = 0; s2 < CPL; ++s2) {
+      double v = acc[s2];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (rg == 0 && cg + 8 * s2 < K) red[warp * (Kpad + 4) + cg + 8 * s2] = v;
+    }
+    lp_acc = warp_sum(lp_acc);
+    r_acc = warp_sum(r_acc);
+    if (lane == 0) {
+      red[warp * (Kpad + 4) + Kpad] = lp_acc;
+      red[warp * (Kpad + 4) + Kpad + 1] = r_acc;
+    }
+  } else {
+    // idle consumer warp (fewer stages than warps): contributes zeros to the CTA reduction
+    for (int j = lane; j < Kpad + 4; j += 32) red[warp * (Kpad + 4) + j] = 0.0;
+  }
+  __syncthreads();
+
+  // ---- CTA partial -> global ----
+  double* my_part = p.partials + (size_t)blockIdx.x * p.pstride;
+  for (int j = tid; j < K + 2; j += NUM_THREADS) {
+    const int src = j < K ? j : Kpad + (j - K);
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < NUM_CONSUMER_WARPS; ++w) v += red[w * (Kpad + 4) + src];
+    my_part[j] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(p.ticket, 1u);
+    sh_is_last = (t == (unsigned int)(grid - 1));
+  }
+  __syncthreads();
+  if (!sh_is_last) return;
+
+  // ===================== last CTA: deterministic cross-CTA sum =====================
+  __threadfence();
+  for (int j = tid; j < K + 2; j += NUM_THREADS) {
+    double v = 0.0;
+    for (int b = 0; b < grid; ++b) v += __ldcg(p.partials + (size_t)b * p.pstride + j);
+    if (j < K)
+      p.lik[p.off_beta + j] = v;
+    else if (j == K)
+      p.lik[P] = v;
+    else if (G == 0)
+      p.lik[0] = v;
+  }
+  if (tid == 0) *p.ticket = 0u;
+  if (FAMILY == FAM_NORMAL_ID && tid == 0) p.lik[P - 1] = 0.0;  // sigma entry is derived in finish()
+  if (G > 0 && tid < 2) p.lik[tid] = 0.0;
+  __threadfence();
+  __syncthreads();
+  if (p.fuse_finish) finish(p, sh_scratch);
+}
+
+// G > 0: deterministic per-group sums of the residual (rows are sorted by group at upload).
+__global__ void __launch_bounds__(256) group_reduce_kernel(const double* __restrict__ r,
+                                                          const long long* __restrict__ seg_ptr, int G,
+                                                          double* __restrict__ lik_a /* lik + 2 */) {
+  __shared__ double sh[8];
+  for (int g = blockIdx.x; g < G; g += gridDim.x) {
+    const long long b = seg_ptr[g], e = seg_ptr[g + 1];
+    double v = 0.0;
+    for (long long i = b + threadIdx.x; i < e; i += blockDim.x) v += r[i];
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += sh[w];
+      lik_a[g] = t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS) finish_kernel(const KernelParams p) {
+  __shared__ double sh_scratch[64];
+  finish(p, sh_scratch);
+}
+
+// ------------------------------------------------------------------------------------------
+// One-time re-layout: column-major X (+ y, group) -> row-panel format (optionally through a row
+// permutation that sorts rows by group).  One thread per (panel, column, row).
+// ------------------------------------------------------------------------------------------
+__global__ void relayout_kernel(const double* __restrict__ X, long long ldx, long long x_row0,
+                                const int32_t* __restrict__ y_int, const double* __restrict__ y_real,
+                                const int32_t* __restrict__ group, const long long* __restrict__ perm,
+                                long long row0, long long n_rows_chunk, long long n_rows_total, int K, int C,
+                                int c_begin, int c_end, double* __restrict__ panels) {
+  // Writes columns [c_begin, c_end) of destination rows [row0, row0 + n_rows_chunk), row0 % 32 == 0.
+  // X may be a chunk whose first row is source row x_row0 (leading dimension ldx).
+  const long long n_panels_chunk = (n_rows_chunk + 31) / 32;
+  const int nc = c_end - c_begin;
+  const long long total = n_panels_chunk * nc * 32;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx & 31);
+    const long long t = idx >> 5;
+    const int c = c_begin + (int)(t % nc);
+    const long long pl = t / nc;
+    const long long dst_row = row0 + pl * 32 + r;
+    double v = 0.0;
+    if (dst_row < n_rows_total && dst_row < row0 + n_rows_chunk) {
+      const long long src = perm ? perm[dst_row] : dst_row;
+      if (c < K)
+        v = X[(src - x_row0) + (long long)c * ldx];
+      else if (c == K)
+        v = y_real ? y_real[src] : (double)y_int[src];
+      else
+        v = (double)group[src];
+    }
+    panels[((row0 >> 5) + pl) * (long long)C * 32 + (long long)c * 32 + (r ^ ((c & 3) << 2))] = v;
+  }
+}
+
+// data checks the reference performs on every call (bernoulli :85 check_bounded, poisson :84
+// check_nonnegative) + the propto=false constant sum lgamma(y+1) (poisson :127-129)
+__global__ void __launch_bounds__(256) y_stats_kernel(const int32_t* __restrict__ y, long long n, int family,
+                                                      double* out /* [gridDim.x][2] = bad, lgamma_sum */) {
+  __shared__ double sh[16];
+  double bad = 0.0, lg = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int v = y[i];
+    if (family == FAM_BERNOULLI_LOGIT) {
+      if (v < 0 || v > 1) bad += 1.0;
+    } else {
+      if (v < 0) bad += 1.0;
+      else lg += lgamma((double)v + 1.0);
+    }
+  }
+  bad = warp_sum(bad);
+  lg = warp_sum(lg);
+  if ((threadIdx.x & 31) == 0) {
+    sh[threadIdx.x >> 5] = bad;
+    sh[8 + (threadIdx.x >> 5)] = lg;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b = 0.0, l = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      b += sh[w];
+      l += sh[8 + w];
+    }
+    out[2 * blockIdx.x] = b;
+    out[2 * blockIdx.x + 1] = l;
+  }
+}
+
+}  // namespace b200glm

@@ -1,0 +1,189 @@
+"""Host-side mirror of the reference's model interface for the GLM hot path.
+
+`GLMModel` plays the role of a stanc-generated model class (stan::model::model_base_crtp,
+src/stan/model/model_base_crtp.hpp:74-301) whose log_prob is evaluated on the B200:
+  num_params_r()                    prob_grad.hpp:19-84
+  log_prob_grad(theta, propto, jac) stan::model::log_prob_grad  (log_prob_grad.hpp:29-50)
+  log_prob(theta, propto, jac)      Model::log_prob<propto,jacobian>(double)  (initialize.hpp:128)
+  leapfrog(...) / set_state(...)    expl_leapfrog::evolve on device-resident z (base_leapfrog.hpp:17-22)
+Error behaviour follows the reference: DomainError <-> std::domain_error (recoverable),
+InvalidArgument <-> std::invalid_argument, CudaError <-> any other std::exception (fatal).
+Everything goes through the C ABI in include/b200glm.h; there is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+
+class DomainError(ValueError):
+    """std::domain_error of the reference (proposal rejected / init retried)."""
+
+
+class InvalidArgument(ValueError):
+    """std::invalid_argument of the reference (size mismatch etc.)."""
+
+
+class CudaError(RuntimeError):
+    """CUDA / NCCL failure or missing device: fatal, never falls back to a CPU path."""
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+DEFAULT_PRIORS = dict(prior_alpha_sd=2.5, prior_beta_sd=2.5, prior_sigma_loc=1.0,
+                      prior_sigma_scale=2.0, prior_sigma_a_scale=1.0)
+
+
+class GLMModel:
+    def __init__(self, family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=1, N_total=0,
+                 grid_ctas=0, data_on_device=False, N=None, K=None, ldx=None, **priors):
+        """X, y, group: numpy arrays (host), or -- with data_on_device=True -- integer device
+        pointers (e.g. torch tensor .data_ptr()) with N, K, ldx given explicitly."""
+        self.L = _capi.lib()
+        self.family = family
+        fam = _capi.FAMILY[family]
+        d = _capi.Desc()
+        keep = []
+        if data_on_device:
+            d.N, d.K, d.ldx = int(N), int(K), int(ldx if ldx is not None else N)
+            d.X = int(X) if X else None
+            if fam == 2:
+                d.y_real, d.y_int = int(y), None
+            else:
+                d.y_int, d.y_real = int(y), None
+            d.group = int(group) if G else None
+        else:
+            X = np.asfortranarray(X, dtype=np.float64)
+            if X.ndim != 2:
+                raise InvalidArgument("X must be a matrix")
+            keep.append(X)
+            d.N, d.K = X.shape
+            d.ldx = max(X.shape[0], 1)
+            d.X = X.ctypes.data if X.size else None
+            y = np.ascontiguousarray(y, dtype=np.float64 if fam == 2 else np.int32)
+            if y.shape != (d.N,):
+                raise InvalidArgument("Vector of dependent variables has the wrong size")
+            keep.append(y)
+            if fam == 2:
+                d.y_real, d.y_int = (y.ctypes.data if y.size else None), None
+            else:
+                d.y_int, d.y_real = (y.ctypes.data if y.size else None), None
+            if G:
+                group = np.ascontiguousarray(group, dtype=np.int32)
+                if group.shape != (d.N,):
+                    raise InvalidArgument("Vector of intercepts has the wrong size")
+                keep.append(group)
+                d.group = group.ctypes.data if group.size else None
+        d.family, d.G, d.data_on_device = fam, int(G), int(bool(data_on_device))
+        pri = dict(DEFAULT_PRIORS)
+        pri.update(priors)
+        for k, v in pri.items():
+            setattr(d, k, float(v))
+        d.device, d.n_slots, d.rank, d.world = int(device), int(n_slots), int(rank), int(world)
+        d.N_total, d.grid_ctas = int(N_total), int(grid_ctas)
+        self.N, self.K, self.G = int(d.N), int(d.K), int(G)
+        self.rank, self.world = int(rank), int(world)
+        h = C.c_void_p()
+        rc = self.L.b200glm_create(C.byref(d), C.byref(h))
+        self.h = h
+        self._check(rc)
+        self.P = self.L.b200glm_num_params(self.h)
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        if rc == _capi.OK:
+            return
+        msg = self.L.b200glm_last_error(self.h).decode() if self.h else "b200glm_create failed"
+        if rc == _capi.DOMAIN:
+            raise DomainError(msg)
+        if rc == _capi.INVALID:
+            raise InvalidArgument(msg)
+        raise CudaError(msg)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b200glm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ model API
+    def num_params_r(self):
+        return self.P
+
+    def param_names(self):
+        n = (["mu_a", "sigma_a"] + [f"a.{g}" for g in range(1, self.G + 1)]) if self.G else ["alpha"]
+        n += [f"beta.{k}" for k in range(1, self.K + 1)]
+        if self.family == "normal_id":
+            n.append("sigma")
+        return n
+
+    def _theta(self, theta):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        if th.shape != (self.P,):
+            raise InvalidArgument(f"theta has {th.size} entries, model has {self.P} parameters")
+        return th
+
+    def log_prob_grad(self, theta, propto=True, jacobian=True, slot=0):
+        th = self._theta(theta)
+        lp = C.c_double()
+        g = np.empty(self.P)
+        self._check(self.L.b200glm_log_prob_grad(self.h, slot, _dp(th), int(propto), int(jacobian),
+                                                 C.byref(lp), _dp(g)))
+        return lp.value, g
+
+    def log_prob(self, theta, propto=False, jacobian=True, slot=0):
+        th = self._theta(theta)
+        lp = C.c_double()
+        self._check(self.L.b200glm_log_prob(self.h, slot, _dp(th), int(propto), int(jacobian), C.byref(lp)))
+        return lp.value
+
+    def set_state(self, q, p, g, V, slot=0):
+        q, p, g = (self._theta(a) for a in (q, p, g))
+        self._check(self.L.b200glm_set_state(self.h, slot, _dp(q), _dp(p), _dp(g), float(V)))
+
+    def leapfrog(self, eps, inv_metric=None, slot=0):
+        q, p, g = np.empty(self.P), np.empty(self.P), np.empty(self.P)
+        V = C.c_double()
+        im = None if inv_metric is None else self._theta(inv_metric)
+        self._check(self.L.b200glm_leapfrog(self.h, slot, float(eps), None if im is None else _dp(im),
+                                            _dp(q), _dp(p), _dp(g), C.byref(V)))
+        return q, p, g, V.value
+
+    # ------------------------------------------------------------------ async / device-resident
+    def leapfrog_async(self, eps, slot=0):
+        self._check(self.L.b200glm_leapfrog_async(self.h, slot, float(eps)))
+
+    def grad_async(self, theta_device_ptr=None, slot=0):
+        self._check(self.L.b200glm_grad_async(self.h, slot, theta_device_ptr))
+
+    def sync(self, slot=0):
+        self._check(self.L.b200glm_sync(self.h, slot))
+
+    def stream_ptr(self, slot=0):
+        return self.L.b200glm_stream(self.h, slot)
+
+    def launch_count(self):
+        return self.L.b200glm_launch_count(self.h)
+
+    def bytes_per_gradient(self):
+        return self.L.b200glm_bytes_per_gradient(self.h)
+
+    # ------------------------------------------------------------------ multi-GPU
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(128)
+        if _capi.lib().b200glm_comm_unique_id(buf) != 0:
+            raise CudaError("ncclGetUniqueId failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def comm_init(self, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.L.b200glm_comm_init(self.h, buf, self.rank, self.world))

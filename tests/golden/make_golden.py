@@ -1,0 +1,84 @@
+"""Generate tests/golden/glm_ref_golden.json from the COMPILED REFERENCE (oracle/_ref).
+
+Run in the build container (needs /root/reference to have been compiled by `make -C oracle ref`):
+    python tests/golden/make_golden.py
+Every case stores its full inputs (X, y, group, theta as float.hex strings, so they are exact)
+and the reference's outputs: stan::model::log_prob_grad<propto,jacobian> value + gradient,
+Model::log_prob<propto,jacobian>(double) values, and one expl_leapfrog step.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.oracle import RefOracle, num_params  # noqa: E402
+from stan_b200.synth import make_glm_data  # noqa: E402
+
+CASES = [
+    # name, family, N, K, G
+    ("bern_small", "bernoulli_logit", 64, 5, 0),
+    ("bern_ragged", "bernoulli_logit", 153, 7, 0),     # N not a multiple of the 32-row panel
+    ("bern_wide", "bernoulli_logit", 40, 33, 0),
+    ("bern_groups", "bernoulli_logit", 97, 4, 6),
+    ("pois_small", "poisson_log", 64, 5, 0),
+    ("pois_groups", "poisson_log", 130, 3, 11),
+    ("norm_small", "normal_id", 64, 5, 0),
+    ("norm_ragged", "normal_id", 71, 9, 0),
+    ("norm_groups", "normal_id", 90, 2, 5),
+    ("bern_k1", "bernoulli_logit", 33, 1, 0),
+    ("bern_k0", "bernoulli_logit", 20, 0, 0),          # zero attributes
+    ("pois_n1", "poisson_log", 1, 3, 0),
+]
+
+
+def hx(a):
+    return [float(v).hex() for v in np.asarray(a, dtype=np.float64).ravel()]
+
+
+def main():
+    out = {"reference": RefOracle.lib().ref_oracle_version().decode(), "cases": []}
+    for name, fam, N, K, G in CASES:
+        d = make_glm_data(fam, N, K, G, seed=4242 + len(out["cases"]))
+        ro = RefOracle(fam, d["X"], d["y"], d["group"], G)
+        P = num_params(fam, K, G)
+        assert P == ro.P
+        rng = np.random.default_rng(99 + len(out["cases"]))
+        thetas = [np.zeros(P), 0.3 * rng.standard_normal(P), 1.5 * rng.standard_normal(P)]
+        if fam == "bernoulli_logit" and K > 0:
+            big = np.zeros(P)
+            big[-K:] = 12.0   # drives |ytheta| beyond the cutoff of 20 on many rows (both branches)
+            thetas.append(big)
+        evals = []
+        for th in thetas:
+            e = {"theta": hx(th), "lp_grad": {}, "lp_double": {}}
+            for propto in (1, 0):
+                for jac in (1, 0):
+                    lp, g = ro.log_prob_grad(th, propto, jac)
+                    e["lp_grad"][f"{propto}{jac}"] = {"lp": float(lp).hex(), "grad": hx(g)}
+                    e["lp_double"][f"{propto}{jac}"] = float(ro.log_prob(th, propto, jac)).hex()
+            evals.append(e)
+        # one leapfrog step of the reference integrator from theta[1]
+        q0 = thetas[1]
+        p0 = rng.standard_normal(P)
+        im = np.exp(0.3 * rng.standard_normal(P))
+        lp0, g0 = ro.log_prob_grad(q0, 1, 1)
+        q1, p1, g1, V1 = ro.leapfrog(0.01, im, q0, p0, -g0, -lp0)
+        case = dict(name=name, family=fam, N=N, K=K, G=G,
+                    X=hx(np.asarray(d["X"]).ravel(order="F")), y=[float(v) for v in d["y"]],
+                    group=None if d["group"] is None else [int(v) for v in d["group"]],
+                    evals=evals,
+                    leapfrog=dict(eps=0.01, inv_metric=hx(im), q0=hx(q0), p0=hx(p0), g0=hx(-g0), V0=float(-lp0).hex(),
+                                  q1=hx(q1), p1=hx(p1), g1=hx(g1), V1=float(V1).hex()))
+        out["cases"].append(case)
+        print(name, "P=", P, "lp(theta1)=", ro.log_prob_grad(thetas[1])[0])
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "glm_ref_golden.json")
+    with open(path, "w") as f:
+        json.dump(out, f)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

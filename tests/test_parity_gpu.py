@@ -1,0 +1,206 @@
+"""GPU parity suite: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bar (BASELINE.json north_star): log_prob and gradient within 1e-10 relative of the reference's
+stan::model::log_prob_grad.  Gradient entries are scaled by max(|g_k|, ||g||_inf) (conftest.rel_err_vec).
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_NAMES, rel_err, rel_err_vec, unhex
+import stan_b200
+from stan_b200 import GLMModel, make_glm_data, theta_points
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def oracle_for(fam, d, G=0, **pri):
+    from oracle.oracle import PortOracle, RefOracle
+    cls = RefOracle if RefOracle.available() else PortOracle
+    return cls(fam, d["X"], d["y"], d["group"], G, **pri)
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_cuda_matches_reference_golden(golden, name):
+    c = golden[name]
+    m = GLMModel(c["family"], c["X"], c["y"], c["group"], c["G"])
+    assert m.num_params_r() == len(c["evals"][0]["theta"])
+    for e in c["evals"]:
+        th = unhex(e["theta"])
+        for key, ref in e["lp_grad"].items():
+            propto, jac = int(key[0]), int(key[1])
+            lp, g = m.log_prob_grad(th, propto, jac)
+            assert rel_err(lp, float.fromhex(ref["lp"])) < TOL, (name, key, lp, float.fromhex(ref["lp"]))
+            assert rel_err_vec(g, unhex(ref["grad"])) < TOL, (name, key)
+        for key, ref in e["lp_double"].items():
+            propto, jac = int(key[0]), int(key[1])
+            assert rel_err(m.log_prob(th, propto, jac), float.fromhex(ref)) < TOL, (name, key)
+    m.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_cuda_leapfrog_matches_reference_golden(golden, name):
+    c = golden[name]
+    lf = c["leapfrog"]
+    m = GLMModel(c["family"], c["X"], c["y"], c["group"], c["G"])
+    m.set_state(unhex(lf["q0"]), unhex(lf["p0"]), unhex(lf["g0"]), float.fromhex(lf["V0"]))
+    q, p, g, V = m.leapfrog(lf["eps"], unhex(lf["inv_metric"]))
+    assert rel_err_vec(q, unhex(lf["q1"])) < TOL
+    assert rel_err_vec(p, unhex(lf["p1"])) < TOL
+    assert rel_err_vec(g, unhex(lf["g1"])) < TOL
+    assert rel_err(V, float.fromhex(lf["V1"])) < TOL
+    m.close()
+
+
+SHAPES = [
+    # family, N, K, G  -- config 1 shape, ragged N, K around the accumulator-slot boundaries, groups
+    ("bernoulli_logit", 10_000, 20, 0),
+    ("bernoulli_logit", 50_001, 100, 0),
+    ("bernoulli_logit", 4_097, 13, 0),
+    ("bernoulli_logit", 3_000, 57, 0),
+    ("bernoulli_logit", 2_000, 200, 0),
+    ("bernoulli_logit", 1_000, 256, 0),
+    ("poisson_log", 60_000, 50, 0),
+    ("poisson_log", 80_000, 50, 1000),
+    ("poisson_log", 5_000, 8, 3000),      # G > SMEM_A_MAX_GROUPS: a[] read from global
+    ("normal_id", 40_000, 200, 0),
+    ("normal_id", 9_999, 31, 17),
+    ("bernoulli_logit", 7_777, 5, 12),
+]
+
+
+@pytest.mark.parametrize("fam,N,K,G", SHAPES)
+def test_cuda_matches_oracle_live(fam, N, K, G):
+    d = make_glm_data(fam, N, K, G)
+    orc = oracle_for(fam, d, G)
+    m = GLMModel(fam, d["X"], d["y"], d["group"], G)
+    assert m.num_params_r() == orc.P
+    for th in theta_points(m.P, n_random=2, scale=0.1):
+        lp, g = m.log_prob_grad(th)
+        lp_r, g_r = orc.log_prob_grad(th)
+        assert rel_err(lp, lp_r) < TOL, (lp, lp_r)
+        assert rel_err_vec(g, g_r) < TOL
+        assert rel_err(m.log_prob(th, False, True), orc.log_prob(th, False, True)) < TOL
+    m.close()
+
+
+def test_deterministic_bitwise():
+    d = make_glm_data("bernoulli_logit", 200_000, 100)
+    m = GLMModel("bernoulli_logit", d["X"], d["y"])
+    th = theta_points(m.P)[1]
+    a = [m.log_prob_grad(th) for _ in range(3)]
+    for lp, g in a[1:]:
+        assert lp == a[0][0] and np.array_equal(g, a[0][1])
+    m.close()
+
+
+def test_near_mode_gradient_cancellation():
+    """At the posterior mode the gradient entries are sums of O(N) terms cancelling to ~0."""
+    d = make_glm_data("bernoulli_logit", 100_000, 20)
+    orc = oracle_for("bernoulli_logit", d)
+    m = GLMModel("bernoulli_logit", d["X"], d["y"])
+    th = np.zeros(m.P)
+    for _ in range(25):   # Newton-free: a few damped gradient steps get close enough to the mode
+        lp, g = orc.log_prob_grad(th)
+        th = th + 4.0 * g / d["X"].shape[0]
+    lp, g = m.log_prob_grad(th)
+    lp_r, g_r = orc.log_prob_grad(th)
+    assert rel_err(lp, lp_r) < TOL
+    # against the sum of |terms| (~N/4) the absolute error must be tiny even though g ~ 0
+    assert np.max(np.abs(g - g_r)) < 1e-10 * d["X"].shape[0]
+    m.close()
+
+
+def test_leapfrog_trajectory_matches_oracle():
+    """20 consecutive device-resident leapfrog steps == 20 oracle steps (state never re-uploaded)."""
+    from oracle.oracle import PortOracle
+    d = make_glm_data("poisson_log", 20_000, 10)
+    po = PortOracle("poisson_log", d["X"], d["y"])
+    m = GLMModel("poisson_log", d["X"], d["y"])
+    rng = np.random.default_rng(5)
+    q = 0.05 * rng.standard_normal(m.P)
+    p = rng.standard_normal(m.P)
+    im = np.exp(0.2 * rng.standard_normal(m.P))
+    lp, g = po.log_prob_grad(q)
+    g, V = -g, -lp
+    m.set_state(q, p, g, V)
+    qd, pd, gd, Vd = m.leapfrog(1e-3, im)
+    q, p, g, V = po.leapfrog(1e-3, im, q, p, g, V)
+    for _ in range(19):
+        qd, pd, gd, Vd = m.leapfrog(1e-3)           # inv_metric NULL = unchanged
+        q, p, g, V = po.leapfrog(1e-3, im, q, p, g, V)
+    assert rel_err_vec(qd, q) < 1e-9 and rel_err_vec(pd, p) < 1e-9 and rel_err(Vd, V) < 1e-9
+    # negative eps (backward tree, base_nuts.hpp:254-255) returns along the trajectory
+    m.set_state(q, -p * 0 + p, g, V)
+    for _ in range(20):
+        qd, pd, gd, Vd = m.leapfrog(-1e-3)
+        q, p, g, V = po.leapfrog(-1e-3, im, q, p, g, V)
+    assert rel_err_vec(qd, q) < 1e-9
+    m.close()
+
+
+def test_error_behaviour_matches_reference():
+    d = make_glm_data("bernoulli_logit", 1000, 3)
+    y = d["y"].copy()
+    y[17] = 2
+    m = GLMModel("bernoulli_logit", d["X"], y)
+    with pytest.raises(stan_b200.DomainError):        # check_bounded(y, 0, 1): domain_error on every call
+        m.log_prob_grad(np.zeros(m.P))
+    m.close()
+    d = make_glm_data("poisson_log", 1000, 3)
+    m = GLMModel("poisson_log", d["X"], d["y"])
+    with pytest.raises(stan_b200.DomainError):
+        m.log_prob_grad(np.array([np.nan, 0, 0, 0]))
+    with pytest.raises(stan_b200.DomainError):        # exp overflow -> non-finite -> domain_error
+        m.log_prob_grad(np.array([800.0, 0, 0, 0]))
+    with pytest.raises(stan_b200.InvalidArgument):    # wrong theta length
+        m.log_prob_grad(np.zeros(m.P + 1))
+    lp, g = m.log_prob_grad(np.zeros(m.P))           # the handle is still usable afterwards
+    assert np.isfinite(lp)
+    # leapfrog into a domain error: V=+inf, g negated (base_hamiltonian.hpp:65-69)
+    q = np.zeros(m.P)
+    p = np.array([1e6, 0, 0, 0.0])
+    m.set_state(q, p, -g, -lp)
+    q1, p1, g1, V1 = m.leapfrog(1.0)
+    assert V1 == np.inf and np.array_equal(g1, g)
+    m.close()
+
+
+def test_empty_and_tiny():
+    m = GLMModel("bernoulli_logit", np.zeros((0, 3)), np.zeros(0, np.int32))
+    from oracle.oracle import PortOracle
+    po = PortOracle("bernoulli_logit", np.zeros((0, 3)), np.zeros(0, np.int32))
+    th = 0.1 * np.arange(1, m.P + 1)
+    lp, g = m.log_prob_grad(th)
+    lp_r, g_r = po.log_prob_grad(th)
+    assert rel_err(lp, lp_r) < TOL and rel_err_vec(g, g_r) < TOL
+    m.close()
+
+
+def test_slots_are_independent():
+    d = make_glm_data("normal_id", 30_000, 16)
+    m = GLMModel("normal_id", d["X"], d["y"], n_slots=3)
+    ths = theta_points(m.P, n_random=2)
+    ref = [m.log_prob_grad(th, slot=0) for th in ths]
+    for s in range(3):
+        lp, g = m.log_prob_grad(ths[s], slot=s)
+        assert lp == ref[s][0] and np.array_equal(g, ref[s][1])
+    m.close()
+
+
+def test_device_resident_data_path():
+    """data_on_device=1: X generated on the GPU (torch is only plumbing here)."""
+    import torch
+    N, K = 100_000, 24
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    Xd = torch.randn((K, N), generator=gen, device="cuda", dtype=torch.float64)   # column-major N x K
+    yd = (torch.rand(N, generator=gen, device="cuda") < 0.4).to(torch.int32)
+    m = GLMModel("bernoulli_logit", Xd.data_ptr(), yd.data_ptr(), data_on_device=True, N=N, K=K, ldx=N)
+    X = Xd.cpu().numpy().T
+    from oracle.oracle import PortOracle
+    po = PortOracle("bernoulli_logit", X, yd.cpu().numpy())
+    th = theta_points(m.P)[1]
+    lp, g = m.log_prob_grad(th)
+    lp_r, g_r = po.log_prob_grad(th)
+    assert rel_err(lp, lp_r) < TOL and rel_err_vec(g, g_r) < TOL
+    m.close()
