@@ -239,7 +239,7 @@ class RefOracle:
     def nuts(self, num_chains=4, seed=1, init_chain_id=1, init_radius=2.0, num_warmup=1000, num_samples=1000,
              stepsize=1.0, max_depth=10, delta=0.8, num_threads=0):
         W = 7 + self.P
-        draws = np.empty((num_chains, num_samples, W))
+        draws = np.empty((num_chains, num_warmup + num_samples, W))
         step = np.empty(num_chains)
         inv_metric = np.empty((num_chains, self.P))
         warm_lf = np.empty(num_chains)
@@ -251,7 +251,8 @@ class RefOracle:
                                  err, 2048)
         if rc:
             raise OracleError(rc, err.value.decode())
-        return dict(draws=draws, stepsize=step, inv_metric=inv_metric, warm_leapfrogs=warm_lf, wall=wall.value)
+        return dict(draws=draws[:, num_warmup:, :], warmup_draws=draws[:, :num_warmup, :], stepsize=step,
+                    inv_metric=inv_metric, warm_leapfrogs=warm_lf, wall=wall.value)
 
     # ---- stan::analyze ----
     @classmethod

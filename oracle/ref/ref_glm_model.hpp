@@ -115,14 +115,14 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
     if (family_ == GLM_NORMAL_ID)
       dimss.push_back({});
   }
+  // stanc-generated models APPEND here (mcmc_writer.hpp:66-77 passes a vector that already holds
+  // the sample and sampler column names)
   void constrained_param_names(std::vector<std::string>& names, bool = true,
                                bool = true) const override {
-    names.clear();
     base_names(names);
   }
   void unconstrained_param_names(std::vector<std::string>& names, bool = true,
                                  bool = true) const override {
-    names.clear();
     base_names(names);
   }
 

@@ -202,7 +202,7 @@ int ref_glm_leapfrog(void* h, double eps, const double* inv_metric, int init,
   });
 }
 
-// Full NUTS through the reference entry point.  draws: [chain][sample][7 + P] doubles
+// Full NUTS through the reference entry point.  draws: [chain][warmup+sample][7 + P] doubles
 // (lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__, params...).
 // warm_leapfrogs[chain] receives sum(n_leapfrog__) over warm-up (save_warmup is forced on
 // internally so the column can be read; warm-up rows are not returned).
@@ -250,12 +250,13 @@ int ref_glm_nuts(void* h, int num_chains, unsigned seed, unsigned init_chain_id,
         wl += rows[i][4];
       if (warm_leapfrogs)
         warm_leapfrogs[c] = wl;
-      for (int i = 0; i < num_samples; ++i) {
-        auto& r = rows[num_warmup + i];
+      const int T = num_warmup + num_samples;
+      for (int i = 0; i < T; ++i) {
+        auto& r = rows[i];
         if (static_cast<int>(r.size()) != W)
           throw std::runtime_error("unexpected draw width");
-        std::memcpy(draws + (static_cast<size_t>(c) * num_samples + i) * W,
-                    r.data(), W * sizeof(double));
+        std::memcpy(draws + (static_cast<size_t>(c) * T + i) * W, r.data(),
+                    W * sizeof(double));
       }
       if (stepsize_out)
         stepsize_out[c] = metric_w[c].stepsize;

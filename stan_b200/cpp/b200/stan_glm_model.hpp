@@ -1,0 +1,410 @@
+// b200/stan_glm_model.hpp -- reference-side binding of the B200 GLM backend.
+//
+// Include this header BEFORE the first use of stan::services::sample::hmc_nuts_diag_e_adapt with
+// b200::glm_model.  It provides
+//   (1) b200::glm_model : stan::model::model_base_crtp<glm_model>      (ST/model/model_base_crtp.hpp:74-301)
+//       -- log_prob<propto,jacobian,double> -> b200glm_log_prob            (value, all constants: initialize.hpp:128)
+//       -- log_prob<propto,jacobian,var>    -> b200glm_log_prob_grad + stan::math::precomputed_gradients
+//          (SM/rev/core/precomputed_gradients.hpp:211-224), so log_prob_grad (ST/model/log_prob_grad.hpp:29-50)
+//          and every other tape-based caller work unchanged;
+//   (2) an explicit specialisation of stan::model::gradient<b200::glm_model> (ST/model/gradient.hpp:22-35).
+//       base_hamiltonian::update_potential_gradient (ST/mcmc/hmc/hamiltonians/base_hamiltonian.hpp:61-70) calls
+//       it qualified, so only a specialisation (not a later overload) is seen; it skips the AD tape;
+//   (3) a full specialisation of stan::mcmc::expl_leapfrog<diag_e_metric<b200::glm_model, stan::rng_t>>
+//       (ST/mcmc/hmc/integrators/expl_leapfrog.hpp:16-32) whose evolve() is ONE fused device launch on
+//       device-resident (q,p,g); base_hmc only ever calls integrator_.evolve (base_hmc.hpp:113,132; base_nuts.hpp:254).
+// With these, the UNMODIFIED adapt_diag_e_nuts / base_nuts / diag_e_metric / services drive the GPU path.
+//
+// Threading: chains run as TBB tasks on several host threads sharing one const model (hmc_nuts_diag_e_adapt.hpp:387-401).
+// Each host thread is bound to its own device slot (stream + workspace); give the model n_slots >= number of threads.
+#ifndef B200_STAN_GLM_MODEL_HPP
+#define B200_STAN_GLM_MODEL_HPP
+
+#include <stan/model/model_header.hpp>
+#include <stan/model/gradient.hpp>
+#include <stan/mcmc/hmc/hamiltonians/diag_e_metric.hpp>
+#include <stan/mcmc/hmc/integrators/expl_leapfrog.hpp>
+
+#include <b200glm.h>
+
+#include <atomic>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+namespace b200 {
+
+class glm_model final : public stan::model::model_base_crtp<glm_model> {
+ public:
+  static size_t count_params(const b200glm_desc& d) {
+    return (d.G > 0 ? 2 + d.G : 1) + d.K + (d.family == B200GLM_NORMAL_ID ? 1 : 0);
+  }
+
+  explicit glm_model(const b200glm_desc& desc)
+      : model_base_crtp(count_params(desc)), desc_(desc), h_(nullptr) {
+    const int rc = b200glm_create(&desc_, &h_);
+    if (rc != B200GLM_OK) {
+      std::string msg = h_ ? b200glm_last_error(h_) : "b200glm_create failed";
+      if (h_)
+        b200glm_destroy(h_);
+      h_ = nullptr;
+      raise(rc, msg);
+    }
+    // the host pointers in desc are not retained
+    desc_.X = nullptr;
+    desc_.y_int = nullptr;
+    desc_.y_real = nullptr;
+    desc_.group = nullptr;
+  }
+  glm_model(const glm_model&) = delete;
+  glm_model& operator=(const glm_model&) = delete;
+  ~glm_model() override {
+    if (h_)
+      b200glm_destroy(h_);
+  }
+
+  b200glm_handle* handle() const { return h_; }
+  const b200glm_desc& desc() const { return desc_; }
+
+  // ---------------------------------------------------------------- device calls
+  [[noreturn]] static void raise(int rc, const std::string& msg) {
+    if (rc == B200GLM_DOMAIN)
+      throw std::domain_error(msg);
+    if (rc == B200GLM_INVALID)
+      throw std::invalid_argument(msg);
+    throw std::runtime_error("b200glm: " + msg);
+  }
+  void check(int rc) const {
+    if (rc != B200GLM_OK)
+      raise(rc, b200glm_last_error(h_));
+  }
+
+  // one device slot per host thread (round-robin over n_slots)
+  int slot() const {
+    static thread_local int tls_slot = -1;
+    static thread_local const glm_model* tls_owner = nullptr;
+    if (tls_owner != this) {
+      tls_owner = this;
+      tls_slot = next_slot_.fetch_add(1) % (desc_.n_slots > 0 ? desc_.n_slots : 1);
+    }
+    return tls_slot;
+  }
+
+  void device_log_prob_grad(const double* theta, bool propto, bool jacobian,
+                            double& lp, double* grad) const {
+    check(b200glm_log_prob_grad(h_, slot(), theta, propto, jacobian, &lp, grad));
+    n_gradients_.fetch_add(1, std::memory_order_relaxed);
+  }
+  double device_log_prob(const double* theta, bool propto, bool jacobian) const {
+    double lp = 0;
+    check(b200glm_log_prob(h_, slot(), theta, propto, jacobian, &lp));
+    return lp;
+  }
+
+  // thread-local "which model did this thread evaluate last" -- how the integrator
+  // specialisation finds the device without touching diag_e_metric (model_ is protected there)
+  static const glm_model*& current() {
+    static thread_local const glm_model* cur = nullptr;
+    return cur;
+  }
+
+  struct resident_state {
+    const glm_model* owner = nullptr;
+    bool valid = false, metric_valid = false;
+    std::vector<double> q, p, g, inv_metric;
+  };
+  static resident_state& resident() {
+    static thread_local resident_state rs;
+    return rs;
+  }
+
+  // expl_leapfrog::evolve on the device.  (q,p,g) stay resident between consecutive steps of a
+  // trajectory; they are re-uploaded only when the caller's z is not the state the device produced last.
+  void device_leapfrog(Eigen::VectorXd& q, Eigen::VectorXd& p, Eigen::VectorXd& g, double& V,
+                       const Eigen::VectorXd& inv_metric, double epsilon,
+                       stan::callbacks::logger& logger) const {
+    const size_t P = num_params_r();
+    const size_t bytes = P * sizeof(double);
+    resident_state& rs = resident();
+    const int sl = slot();
+    if (rs.owner != this) {
+      rs.owner = this;
+      rs.valid = rs.metric_valid = false;
+      rs.q.resize(P);
+      rs.p.resize(P);
+      rs.g.resize(P);
+      rs.inv_metric.resize(P);
+    }
+    const bool same = rs.valid && std::memcmp(rs.q.data(), q.data(), bytes) == 0
+                      && std::memcmp(rs.p.data(), p.data(), bytes) == 0
+                      && std::memcmp(rs.g.data(), g.data(), bytes) == 0;
+    if (!same) {
+      check(b200glm_set_state(h_, sl, q.data(), p.data(), g.data(), V));
+      n_uploads_.fetch_add(1, std::memory_order_relaxed);
+    }
+    const double* im = nullptr;
+    if (!rs.metric_valid || std::memcmp(rs.inv_metric.data(), inv_metric.data(), bytes) != 0) {
+      std::memcpy(rs.inv_metric.data(), inv_metric.data(), bytes);
+      rs.metric_valid = true;
+      im = rs.inv_metric.data();
+    }
+    const int rc = b200glm_leapfrog(h_, sl, epsilon, im, q.data(), p.data(), g.data(), &V);
+    n_leapfrogs_.fetch_add(1, std::memory_order_relaxed);
+    if (rc == B200GLM_DOMAIN) {
+      // data-level domain error (y out of range): same outcome as base_hamiltonian.hpp:65-69
+      V = std::numeric_limits<double>::infinity();
+      rs.valid = false;
+      reject_message(b200glm_last_error(h_), logger);
+      return;
+    }
+    check(rc);
+    if (V == std::numeric_limits<double>::infinity())
+      reject_message("non-finite log density or gradient", logger);
+    std::memcpy(rs.q.data(), q.data(), bytes);
+    std::memcpy(rs.p.data(), p.data(), bytes);
+    std::memcpy(rs.g.data(), g.data(), bytes);
+    rs.valid = true;
+  }
+
+  static void reject_message(const std::string& what, stan::callbacks::logger& logger) {
+    // wording of base_hamiltonian::write_error_msg_ (base_hamiltonian.hpp:83-96)
+    logger.error("Informational Message: The current Metropolis proposal is about to be rejected because of "
+                 "the following issue:");
+    logger.error(what);
+    logger.error("If this warning occurs sporadically, such as for highly constrained variable types like "
+                 "covariance matrices, then the sampler is fine,");
+    logger.error("but if this warning occurs often then your model may be either severely ill-conditioned or "
+                 "misspecified.");
+    logger.error("");
+  }
+
+  long n_gradients() const { return n_gradients_.load(); }
+  long n_leapfrogs() const { return n_leapfrogs_.load(); }
+  long n_uploads() const { return n_uploads_.load(); }
+
+  // ---------------------------------------------------------------- model_base interface
+  std::string model_name() const override { return "b200_glm_model"; }
+  std::vector<std::string> model_compile_info() const {
+    return {std::string("backend = ") + b200glm_version()};
+  }
+
+  // appends, as stanc-generated models do: mcmc_writer::write_sample_names (services/util/mcmc_writer.hpp:66-77)
+  // passes a vector that already holds the sample and sampler column names
+  void flat_names(std::vector<std::string>& names) const {
+    if (desc_.G > 0) {
+      names.emplace_back("mu_a");
+      names.emplace_back("sigma_a");
+      for (int g = 1; g <= desc_.G; ++g)
+        names.emplace_back("a." + std::to_string(g));
+    } else {
+      names.emplace_back("alpha");
+    }
+    for (int k = 1; k <= desc_.K; ++k)
+      names.emplace_back("beta." + std::to_string(k));
+    if (desc_.family == B200GLM_NORMAL_ID)
+      names.emplace_back("sigma");
+  }
+  void get_param_names(std::vector<std::string>& names, bool = true, bool = true) const override {
+    if (desc_.G > 0)
+      names = {"mu_a", "sigma_a", "a", "beta"};
+    else
+      names = {"alpha", "beta"};
+    if (desc_.family == B200GLM_NORMAL_ID)
+      names.emplace_back("sigma");
+  }
+  void get_dims(std::vector<std::vector<size_t>>& dimss, bool = true, bool = true) const override {
+    dimss.clear();
+    if (desc_.G > 0) {
+      dimss.push_back({});
+      dimss.push_back({});
+      dimss.push_back({static_cast<size_t>(desc_.G)});
+    } else {
+      dimss.push_back({});
+    }
+    dimss.push_back({static_cast<size_t>(desc_.K)});
+    if (desc_.family == B200GLM_NORMAL_ID)
+      dimss.push_back({});
+  }
+  void constrained_param_names(std::vector<std::string>& names, bool = true, bool = true) const override {
+    flat_names(names);
+  }
+  void unconstrained_param_names(std::vector<std::string>& names, bool = true, bool = true) const override {
+    flat_names(names);
+  }
+
+  template <bool propto, bool jacobian, typename T, typename Vec>
+  T log_prob_any(Vec& params_r) const {
+    const size_t P = num_params_r();
+    if (static_cast<size_t>(params_r.size()) != P)
+      throw std::invalid_argument("b200::glm_model::log_prob: wrong number of parameters");
+    if constexpr (std::is_same<T, double>::value) {
+      return device_log_prob(params_r.data(), propto, jacobian);
+    } else {
+      static_assert(std::is_same<T, stan::math::var>::value,
+                    "b200::glm_model supports double and reverse-mode var only (NUTS needs first order)");
+      std::vector<double> th(P), grad(P);
+      std::vector<stan::math::var> ops(P);
+      for (size_t i = 0; i < P; ++i) {
+        ops[i] = params_r[i];
+        th[i] = ops[i].val();
+      }
+      double lp = 0;
+      device_log_prob_grad(th.data(), propto, jacobian, lp, grad.data());
+      return stan::math::precomputed_gradients(lp, ops, grad);
+    }
+  }
+  template <bool propto, bool jacobian, typename T>
+  T log_prob(Eigen::Matrix<T, -1, 1>& params_r, std::ostream* = nullptr) const {
+    return log_prob_any<propto, jacobian, T>(params_r);
+  }
+  template <bool propto, bool jacobian, typename T>
+  T log_prob(std::vector<T>& params_r, std::vector<int>&, std::ostream* = nullptr) const {
+    return log_prob_any<propto, jacobian, T>(params_r);
+  }
+
+  template <typename VecIn, typename VecOut>
+  void constrain(const VecIn& u, VecOut& c) const {
+    const size_t P = num_params_r();
+    for (size_t i = 0; i < P; ++i)
+      c[i] = u[i];
+    if (desc_.G > 0)
+      c[1] = std::exp(u[1]);
+    if (desc_.family == B200GLM_NORMAL_ID)
+      c[P - 1] = std::exp(u[P - 1]);
+  }
+  template <typename VecIn, typename VecOut>
+  void unconstrain(const VecIn& c, VecOut& u) const {
+    const size_t P = num_params_r();
+    for (size_t i = 0; i < P; ++i)
+      u[i] = c[i];
+    if (desc_.G > 0)
+      u[1] = stan::math::lb_free(c[1], 0);
+    if (desc_.family == B200GLM_NORMAL_ID)
+      u[P - 1] = stan::math::lb_free(c[P - 1], 0);
+  }
+  template <typename RNG>
+  void write_array(RNG&, Eigen::VectorXd& params_r, Eigen::VectorXd& vars, bool = true, bool = true,
+                   std::ostream* = nullptr) const {
+    vars.resize(num_params_r());
+    constrain(params_r, vars);
+  }
+  template <typename RNG>
+  void write_array(RNG&, std::vector<double>& params_r, std::vector<int>&, std::vector<double>& vars,
+                   bool = true, bool = true, std::ostream* = nullptr) const {
+    vars.resize(num_params_r());
+    constrain(params_r, vars);
+  }
+  void read_inits(const stan::io::var_context& context, std::vector<double>& c) const {
+    std::vector<std::string> names;
+    get_param_names(names);
+    c.clear();
+    for (const auto& nm : names) {
+      std::vector<double> v = context.vals_r(nm);
+      c.insert(c.end(), v.begin(), v.end());
+    }
+    if (c.size() != num_params_r())
+      throw std::invalid_argument("init context has the wrong number of values");
+  }
+  void transform_inits(const stan::io::var_context& context, Eigen::VectorXd& params_r,
+                       std::ostream* = nullptr) const override {
+    std::vector<double> c;
+    read_inits(context, c);
+    params_r.resize(num_params_r());
+    unconstrain(c, params_r);
+  }
+  void transform_inits(const stan::io::var_context& context, std::vector<int>&, std::vector<double>& params_r,
+                       std::ostream* = nullptr) const override {
+    std::vector<double> c;
+    read_inits(context, c);
+    params_r.resize(num_params_r());
+    unconstrain(c, params_r);
+  }
+  void unconstrain_array(const Eigen::VectorXd& c, Eigen::VectorXd& u, std::ostream* = nullptr) const override {
+    u.resize(num_params_r());
+    unconstrain(c, u);
+  }
+  void unconstrain_array(const std::vector<double>& c, std::vector<double>& u,
+                         std::ostream* = nullptr) const override {
+    u.resize(num_params_r());
+    unconstrain(c, u);
+  }
+
+ private:
+  b200glm_desc desc_;
+  b200glm_handle* h_;
+  mutable std::atomic<int> next_slot_{0};
+  mutable std::atomic<long> n_gradients_{0}, n_leapfrogs_{0}, n_uploads_{0};
+};
+
+}  // namespace b200
+
+// ---------------------------------------------------------------------------------------------
+// (2) stan::model::gradient -- explicit specialisations (both signatures of gradient.hpp:14-35)
+// ---------------------------------------------------------------------------------------------
+namespace stan {
+namespace model {
+
+template <>
+inline void gradient<b200::glm_model>(const b200::glm_model& model, const Eigen::Matrix<double, Eigen::Dynamic, 1>& x,
+                                      double& f, Eigen::Matrix<double, Eigen::Dynamic, 1>& grad_f,
+                                      std::ostream* /*msgs*/) {
+  b200::glm_model::current() = &model;
+  Eigen::VectorXd g(x.size());
+  model.device_log_prob_grad(x.data(), true, true, f, g.data());  // throws before grad_f is touched
+  grad_f = std::move(g);
+}
+
+template <>
+inline void gradient<b200::glm_model>(const b200::glm_model& model, const Eigen::Matrix<double, Eigen::Dynamic, 1>& x,
+                                      double& f, Eigen::Matrix<double, Eigen::Dynamic, 1>& grad_f,
+                                      callbacks::logger& /*logger*/) {
+  gradient<b200::glm_model>(model, x, f, grad_f, static_cast<std::ostream*>(nullptr));
+}
+
+}  // namespace model
+
+// ---------------------------------------------------------------------------------------------
+// (3) the integrator slot: device-resident leapfrog
+// ---------------------------------------------------------------------------------------------
+namespace mcmc {
+
+template <>
+class expl_leapfrog<diag_e_metric<b200::glm_model, stan::rng_t>>
+    : public base_leapfrog<diag_e_metric<b200::glm_model, stan::rng_t>> {
+ public:
+  using hamiltonian_t = diag_e_metric<b200::glm_model, stan::rng_t>;
+  using point_t = typename hamiltonian_t::PointType;
+
+  expl_leapfrog() : base_leapfrog<hamiltonian_t>() {}
+
+  // one launch: p -= eps/2 g; q += eps M^-1 p; (V,g) = -(lp, grad lp)(q); p -= eps/2 g
+  void evolve(point_t& z, hamiltonian_t& hamiltonian, const double epsilon, callbacks::logger& logger) {
+    const b200::glm_model* m = b200::glm_model::current();
+    if (m == nullptr || static_cast<size_t>(z.q.size()) != m->num_params_r()) {
+      // no device evaluation on this thread yet: take the host sub-steps once (they reach the device
+      // through the gradient specialisation, which registers the model for the following calls)
+      base_leapfrog<hamiltonian_t>::evolve(z, hamiltonian, epsilon, logger);
+      return;
+    }
+    m->device_leapfrog(z.q, z.p, z.g, z.V, z.inv_e_metric_, epsilon, logger);
+  }
+
+  // host sub-steps, kept so the class still satisfies base_leapfrog's interface
+  void begin_update_p(point_t& z, hamiltonian_t& hamiltonian, double epsilon, callbacks::logger& logger) {
+    z.p -= epsilon * hamiltonian.dphi_dq(z, logger);
+  }
+  void update_q(point_t& z, hamiltonian_t& hamiltonian, double epsilon, callbacks::logger& logger) {
+    z.q += epsilon * hamiltonian.dtau_dp(z);
+    hamiltonian.update_potential_gradient(z, logger);
+  }
+  void end_update_p(point_t& z, hamiltonian_t& hamiltonian, double epsilon, callbacks::logger& logger) {
+    z.p -= epsilon * hamiltonian.dphi_dq(z, logger);
+  }
+};
+
+}  // namespace mcmc
+}  // namespace stan
+
+#endif

@@ -1,0 +1,243 @@
+// stan_capi.cpp -- C entry points over the UNMODIFIED reference services driving the B200 backend.
+//
+// Built only where the reference headers exist (the build container); the resulting
+// stan_b200/lib/libb200stan.so travels to the GPU box.  It is the executable proof of the drop-in:
+//   b200stan_nuts          -> stan::services::sample::hmc_nuts_diag_e_adapt  (ST/services/sample/hmc_nuts_diag_e_adapt.hpp:58,331)
+//                             with Model = b200::glm_model; base_nuts, diag_e_metric, adaptation, writers untouched
+//   b200stan_log_prob_grad -> stan::model::log_prob_grad<propto,jacobian>    (tape path via precomputed_gradients)
+//   b200stan_gradient      -> stan::model::gradient                          (explicit specialisation, no tape)
+//   b200stan_leapfrog      -> stan::mcmc::expl_leapfrog<diag_e_metric<...>>::evolve (device-resident specialisation)
+#include <b200/stan_glm_model.hpp>
+
+#include <stan/callbacks/interrupt.hpp>
+#include <stan/callbacks/logger.hpp>
+#include <stan/callbacks/structured_writer.hpp>
+#include <stan/callbacks/writer.hpp>
+#include <stan/io/empty_var_context.hpp>
+#include <stan/model/log_prob_grad.hpp>
+#include <stan/services/sample/hmc_nuts_diag_e_adapt.hpp>
+#include <stan/services/util/create_unit_e_diag_inv_metric.hpp>
+
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <sstream>
+
+namespace {
+
+using b200::glm_model;
+
+void set_err(char* buf, int len, const char* msg) {
+  if (buf && len > 0) {
+    std::strncpy(buf, msg, len - 1);
+    buf[len - 1] = 0;
+  }
+}
+
+template <typename F>
+int guarded(char* err, int errlen, F&& f) {
+  static thread_local stan::math::ChainableStack thread_tape;  // STAN_THREADS: one AD tape per thread
+  try {
+    f();
+    return 0;
+  } catch (const std::domain_error& e) {
+    set_err(err, errlen, e.what());
+    return 1;
+  } catch (const std::invalid_argument& e) {
+    set_err(err, errlen, e.what());
+    return 2;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return 3;
+  }
+}
+
+struct draw_writer : public stan::callbacks::writer {
+  std::vector<std::string> names;
+  std::vector<std::vector<double>> rows;
+  void operator()(const std::vector<std::string>& n) override { names = n; }
+  void operator()(const std::vector<double>& s) override { rows.push_back(s); }
+  void operator()() override {}
+  void operator()(const std::string&) override {}
+};
+
+struct metric_writer : public stan::callbacks::structured_writer {
+  double stepsize = 0;
+  Eigen::VectorXd inv_metric;
+  void write(const std::string& key, double value) override {
+    if (key == "stepsize")
+      stepsize = value;
+  }
+  void write(const std::string& key, const Eigen::VectorXd& vec) override {
+    if (key == "inv_metric")
+      inv_metric = vec;
+  }
+};
+
+struct collecting_logger : public stan::callbacks::logger {
+  std::mutex m;
+  std::string errors;
+  long n_reject = 0;
+  void error(const std::string& s) override {
+    std::lock_guard<std::mutex> g(m);
+    if (s.find("about to be rejected") != std::string::npos)
+      ++n_reject;
+    if (errors.size() < 4000)
+      errors += s + "\n";
+  }
+  void error(const std::stringstream& s) override { error(s.str()); }
+  void fatal(const std::string& s) override { error(s); }
+  void fatal(const std::stringstream& s) override { error(s.str()); }
+};
+
+template <bool propto, bool jacobian>
+double lp_grad(const glm_model& m, std::vector<double>& th, std::vector<double>& grad) {
+  std::vector<int> pi;
+  return stan::model::log_prob_grad<propto, jacobian>(m, th, pi, grad, nullptr);
+}
+
+}  // namespace
+
+extern "C" {
+
+void* b200stan_create(const b200glm_desc* d, char* err, int errlen) {
+  glm_model* m = nullptr;
+  guarded(err, errlen, [&] { m = new glm_model(*d); });
+  return m;
+}
+void b200stan_destroy(void* h) { delete static_cast<glm_model*>(h); }
+int b200stan_num_params(void* h) { return static_cast<int>(static_cast<glm_model*>(h)->num_params_r()); }
+void b200stan_counters(void* h, long* n_gradients, long* n_leapfrogs, long* n_uploads) {
+  auto* m = static_cast<glm_model*>(h);
+  *n_gradients = m->n_gradients();
+  *n_leapfrogs = m->n_leapfrogs();
+  *n_uploads = m->n_uploads();
+}
+
+int b200stan_log_prob_grad(void* h, const double* theta, int propto, int jacobian, double* lp, double* grad,
+                           char* err, int errlen) {
+  auto& m = *static_cast<glm_model*>(h);
+  const size_t P = m.num_params_r();
+  return guarded(err, errlen, [&] {
+    std::vector<double> th(theta, theta + P), g;
+    if (propto)
+      *lp = jacobian ? lp_grad<true, true>(m, th, g) : lp_grad<true, false>(m, th, g);
+    else
+      *lp = jacobian ? lp_grad<false, true>(m, th, g) : lp_grad<false, false>(m, th, g);
+    if (grad)
+      std::memcpy(grad, g.data(), P * sizeof(double));
+  });
+}
+
+int b200stan_log_prob(void* h, const double* theta, int propto, int jacobian, double* lp, char* err, int errlen) {
+  auto& m = *static_cast<glm_model*>(h);
+  const size_t P = m.num_params_r();
+  return guarded(err, errlen, [&] {
+    std::vector<double> th(theta, theta + P);
+    std::vector<int> pi;
+    if (propto)
+      *lp = jacobian ? m.template log_prob<true, true>(th, pi, nullptr) : m.template log_prob<true, false>(th, pi, nullptr);
+    else
+      *lp = jacobian ? m.template log_prob<false, true>(th, pi, nullptr)
+                     : m.template log_prob<false, false>(th, pi, nullptr);
+  });
+}
+
+int b200stan_gradient(void* h, const double* theta, double* lp, double* grad, char* err, int errlen) {
+  auto& m = *static_cast<glm_model*>(h);
+  const size_t P = m.num_params_r();
+  return guarded(err, errlen, [&] {
+    Eigen::VectorXd x = Eigen::Map<const Eigen::VectorXd>(theta, P), g;
+    double f;
+    stan::callbacks::logger logger;
+    stan::model::gradient(m, x, f, g, logger);
+    *lp = f;
+    std::memcpy(grad, g.data(), P * sizeof(double));
+  });
+}
+
+// n_steps consecutive evolve() calls of the (specialised) reference integrator on one diag_e_point,
+// after hamiltonian.init(z) as base_nuts.hpp:85 does.
+int b200stan_leapfrog(void* h, double eps, const double* inv_metric, int n_steps, double* q, double* p, double* g,
+                      double* V, char* err, int errlen) {
+  auto& m = *static_cast<glm_model*>(h);
+  const int P = static_cast<int>(m.num_params_r());
+  return guarded(err, errlen, [&] {
+    using H = stan::mcmc::diag_e_metric<glm_model, stan::rng_t>;
+    H ham(m);
+    stan::mcmc::expl_leapfrog<H> integrator;
+    stan::mcmc::diag_e_point z(P);
+    stan::callbacks::logger logger;
+    z.q = Eigen::Map<const Eigen::VectorXd>(q, P);
+    z.p = Eigen::Map<const Eigen::VectorXd>(p, P);
+    if (inv_metric)
+      z.inv_e_metric_ = Eigen::Map<const Eigen::VectorXd>(inv_metric, P);
+    ham.init(z, logger);
+    for (int i = 0; i < n_steps; ++i)
+      integrator.evolve(z, ham, eps, logger);
+    std::memcpy(q, z.q.data(), P * sizeof(double));
+    std::memcpy(p, z.p.data(), P * sizeof(double));
+    std::memcpy(g, z.g.data(), P * sizeof(double));
+    *V = z.V;
+  });
+}
+
+// draws: [chain][warmup+sample][7 + P] (lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__, params)
+int b200stan_nuts(void* h, int num_chains, unsigned seed, unsigned init_chain_id, double init_radius, int num_warmup,
+                  int num_samples, double stepsize, int max_depth, double delta, int num_threads, double* draws,
+                  double* stepsize_out, double* inv_metric_out, double* warm_leapfrogs, double* wall_seconds,
+                  char* err, int errlen) {
+  auto& m = *static_cast<glm_model*>(h);
+  const int P = static_cast<int>(m.num_params_r());
+  int rc = 0;
+  int g = guarded(err, errlen, [&] {
+    stan::math::init_threadpool_tbb(num_threads > 0 ? num_threads : num_chains);
+    std::vector<std::shared_ptr<stan::io::var_context>> inits, metrics;
+    for (int c = 0; c < num_chains; ++c) {
+      inits.emplace_back(std::make_shared<stan::io::empty_var_context>());
+      metrics.emplace_back(std::make_shared<stan::io::array_var_context>(
+          stan::services::util::create_unit_e_diag_inv_metric(P)));
+    }
+    stan::callbacks::interrupt interrupt;
+    collecting_logger logger;
+    std::vector<stan::callbacks::writer> init_w(num_chains), diag_w(num_chains);
+    std::vector<draw_writer> sample_w(num_chains);
+    std::vector<metric_writer> metric_w(num_chains);
+    auto t0 = std::chrono::steady_clock::now();
+    rc = stan::services::sample::hmc_nuts_diag_e_adapt(
+        m, num_chains, inits, metrics, seed, init_chain_id, init_radius, num_warmup, num_samples, 1, true, 0,
+        stepsize, 0.0, max_depth, delta, 0.05, 0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w, diag_w,
+        metric_w);
+    auto t1 = std::chrono::steady_clock::now();
+    if (wall_seconds)
+      *wall_seconds = std::chrono::duration<double>(t1 - t0).count();
+    if (rc != 0)
+      throw std::runtime_error("hmc_nuts_diag_e_adapt rc=" + std::to_string(rc) + ": " + logger.errors);
+    const int W = 7 + P;
+    for (int c = 0; c < num_chains; ++c) {
+      auto& rows = sample_w[c].rows;
+      if (static_cast<int>(rows.size()) != num_warmup + num_samples)
+        throw std::runtime_error("unexpected number of draws: " + logger.errors);
+      double wl = 0;
+      for (int i = 0; i < num_warmup; ++i)
+        wl += rows[i][4];
+      if (warm_leapfrogs)
+        warm_leapfrogs[c] = wl;
+      const int T = num_warmup + num_samples;
+      for (int i = 0; i < T; ++i)
+        std::memcpy(draws + (static_cast<size_t>(c) * T + i) * W, rows[i].data(), W * sizeof(double));
+      if (stepsize_out)
+        stepsize_out[c] = metric_w[c].stepsize;
+      if (inv_metric_out)
+        std::memcpy(inv_metric_out + static_cast<size_t>(c) * P, metric_w[c].inv_metric.data(), P * sizeof(double));
+    }
+  });
+  return g ? g : rc;
+}
+
+const char* b200stan_version() {
+  return "b200::glm_model behind stan::services::sample::hmc_nuts_diag_e_adapt (reference headers: stan@9048555, math@2fdd3ed)";
+}
+
+}  // extern "C"

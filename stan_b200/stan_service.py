@@ -1,0 +1,151 @@
+"""ctypes binding of stan_b200/lib/libb200stan.so: the reference's own services
+(stan::services::sample::hmc_nuts_diag_e_adapt, stan::model::log_prob_grad / gradient,
+stan::mcmc::expl_leapfrog) compiled against b200::glm_model (stan_b200/cpp/b200/stan_glm_model.hpp).
+
+This is the executable form of the drop-in claim: NUTS, adaptation, RNG, writers are the
+reference's unmodified code; only the model gradient / leapfrog run on the B200.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _capi
+from .model import DomainError, InvalidArgument, CudaError, DEFAULT_PRIORS
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libb200stan.so")
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError(f"{LIB_PATH} missing: build with `make -C stan_b200/cpp` where the reference headers exist")
+        _capi.lib()  # libb200glm.so first (same directory, also found through $ORIGIN)
+        L = C.CDLL(LIB_PATH)
+        L.b200stan_create.restype = C.c_void_p
+        L.b200stan_create.argtypes = [C.POINTER(_capi.Desc), C.c_char_p, C.c_int]
+        L.b200stan_destroy.argtypes = [C.c_void_p]
+        L.b200stan_num_params.argtypes = [C.c_void_p]
+        L.b200stan_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class StanGLM:
+    """b200::glm_model driven through the reference's C++ interfaces."""
+
+    def __init__(self, family, X, y, group=None, G=0, device=0, n_slots=8, **priors):
+        self.L = lib()
+        fam = _capi.FAMILY[family]
+        X = np.asfortranarray(X, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64 if fam == 2 else np.int32)
+        d = _capi.Desc()
+        d.family, d.N, d.K = fam, X.shape[0], X.shape[1]
+        d.X, d.ldx = (X.ctypes.data if X.size else None), max(X.shape[0], 1)
+        if fam == 2:
+            d.y_real = y.ctypes.data if y.size else None
+        else:
+            d.y_int = y.ctypes.data if y.size else None
+        d.G = int(G)
+        if G:
+            group = np.ascontiguousarray(group, dtype=np.int32)
+            d.group = group.ctypes.data
+        pri = dict(DEFAULT_PRIORS)
+        pri.update(priors)
+        for k, v in pri.items():
+            setattr(d, k, float(v))
+        d.device, d.n_slots, d.rank, d.world = device, n_slots, 0, 1
+        err = C.create_string_buffer(1024)
+        self.h = C.c_void_p(self.L.b200stan_create(C.byref(d), err, 1024))
+        if not self.h:
+            raise CudaError(err.value.decode() or "b200stan_create failed")
+        self.P = self.L.b200stan_num_params(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b200stan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _raise(rc, err):
+        msg = err.value.decode()
+        if rc == 1:
+            raise DomainError(msg)
+        if rc == 2:
+            raise InvalidArgument(msg)
+        raise CudaError(msg)
+
+    def counters(self):
+        a, b, c = C.c_long(), C.c_long(), C.c_long()
+        self.L.b200stan_counters(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return dict(gradients=a.value, leapfrogs=b.value, uploads=c.value)
+
+    def log_prob_grad(self, theta, propto=True, jacobian=True):
+        """stan::model::log_prob_grad<propto,jacobian> (AD tape + precomputed_gradients)."""
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        lp, g, err = C.c_double(), np.empty(self.P), C.create_string_buffer(1024)
+        rc = self.L.b200stan_log_prob_grad(self.h, _dp(th), int(propto), int(jacobian), C.byref(lp), _dp(g), err, 1024)
+        if rc:
+            self._raise(rc, err)
+        return lp.value, g
+
+    def log_prob(self, theta, propto=False, jacobian=True):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        lp, err = C.c_double(), C.create_string_buffer(1024)
+        rc = self.L.b200stan_log_prob(self.h, _dp(th), int(propto), int(jacobian), C.byref(lp), err, 1024)
+        if rc:
+            self._raise(rc, err)
+        return lp.value
+
+    def gradient(self, theta):
+        """stan::model::gradient (the explicit specialisation: no tape)."""
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        lp, g, err = C.c_double(), np.empty(self.P), C.create_string_buffer(1024)
+        rc = self.L.b200stan_gradient(self.h, _dp(th), C.byref(lp), _dp(g), err, 1024)
+        if rc:
+            self._raise(rc, err)
+        return lp.value, g
+
+    def leapfrog(self, eps, inv_metric, q, p, n_steps=1):
+        """hamiltonian.init(z) then n_steps x expl_leapfrog<diag_e_metric<b200::glm_model>>::evolve."""
+        q, p = (np.array(a, dtype=np.float64) for a in (q, p))
+        g = np.zeros(self.P)
+        im = np.ascontiguousarray(inv_metric, dtype=np.float64)
+        V, err = C.c_double(), C.create_string_buffer(1024)
+        rc = self.L.b200stan_leapfrog(self.h, C.c_double(eps), _dp(im), int(n_steps), _dp(q), _dp(p), _dp(g),
+                                      C.byref(V), err, 1024)
+        if rc:
+            self._raise(rc, err)
+        return q, p, g, V.value
+
+    def nuts(self, num_chains=4, seed=1, init_chain_id=1, init_radius=2.0, num_warmup=1000, num_samples=1000,
+             stepsize=1.0, max_depth=10, delta=0.8, num_threads=0):
+        """stan::services::sample::hmc_nuts_diag_e_adapt, unmodified, on b200::glm_model."""
+        W = 7 + self.P
+        draws = np.empty((num_chains, num_warmup + num_samples, W))
+        step, inv_metric = np.empty(num_chains), np.empty((num_chains, self.P))
+        warm_lf, wall, err = np.empty(num_chains), C.c_double(), C.create_string_buffer(4096)
+        rc = self.L.b200stan_nuts(self.h, num_chains, C.c_uint(seed), C.c_uint(init_chain_id), C.c_double(init_radius),
+                                  num_warmup, num_samples, C.c_double(stepsize), max_depth, C.c_double(delta),
+                                  num_threads, _dp(draws), _dp(step), _dp(inv_metric), _dp(warm_lf), C.byref(wall),
+                                  err, 4096)
+        if rc:
+            self._raise(rc, err)
+        return dict(draws=draws[:, num_warmup:, :], warmup_draws=draws[:, :num_warmup, :], stepsize=step,
+                    inv_metric=inv_metric, warm_leapfrogs=warm_lf, wall=wall.value)

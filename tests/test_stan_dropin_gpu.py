@@ -1,0 +1,119 @@
+"""GPU suite: the reference's OWN services (unmodified hmc_nuts_diag_e_adapt / base_nuts / diag_e_metric /
+adaptation / RNG) driving b200::glm_model, against the same services driving the reference CPU model.
+
+Bars (BASELINE.json north_star): lp/gradient 1e-10 relative; posterior means and variances within
+Monte-Carlo standard error (stan::analyze::mcse_mean / mcse_sd).
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err, rel_err_vec, unhex
+from stan_b200 import make_glm_data, theta_points
+from stan_b200 import stan_service
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not stan_service.available(), reason="libb200stan.so not built")]
+TOL = 1e-10
+
+
+def ref_oracle():
+    from oracle.oracle import RefOracle
+    if not RefOracle.available():
+        pytest.skip("oracle/_ref not present")
+    return RefOracle
+
+
+@pytest.mark.parametrize("name", ["bern_ragged", "pois_groups", "norm_groups", "norm_small"])
+def test_model_api_through_reference_functions(golden, name):
+    """stan::model::log_prob_grad (tape), stan::model::gradient (specialisation), Model::log_prob<double>."""
+    c = golden[name]
+    m = stan_service.StanGLM(c["family"], c["X"], c["y"], c["group"], c["G"])
+    for e in c["evals"]:
+        th = unhex(e["theta"])
+        for key, ref in e["lp_grad"].items():
+            lp, g = m.log_prob_grad(th, int(key[0]), int(key[1]))
+            assert rel_err(lp, float.fromhex(ref["lp"])) < TOL
+            assert rel_err_vec(g, unhex(ref["grad"])) < TOL
+        lp, g = m.gradient(th)
+        assert rel_err(lp, float.fromhex(e["lp_grad"]["11"]["lp"])) < TOL
+        assert rel_err_vec(g, unhex(e["lp_grad"]["11"]["grad"])) < TOL
+        for key, ref in e["lp_double"].items():
+            assert rel_err(m.log_prob(th, int(key[0]), int(key[1])), float.fromhex(ref)) < TOL
+    m.close()
+
+
+def test_specialised_integrator_matches_reference_integrator():
+    """expl_leapfrog<diag_e_metric<b200::glm_model>>::evolve (device-resident) == the reference's evolve."""
+    Ref = ref_oracle()
+    d = make_glm_data("bernoulli_logit", 20_000, 20)
+    m = stan_service.StanGLM("bernoulli_logit", d["X"], d["y"])
+    ro = Ref("bernoulli_logit", d["X"], d["y"])
+    rng = np.random.default_rng(1)
+    q0, p0 = 0.1 * rng.standard_normal(m.P), rng.standard_normal(m.P)
+    im = np.exp(0.3 * rng.standard_normal(m.P))
+    c0 = m.counters()
+    q, p, g, V = m.leapfrog(0.02, im, q0, p0, n_steps=25)
+    c1 = m.counters()
+    qr, pr, gr, Vr = q0, p0, None, 0.0
+    qr, pr, gr, Vr = ro.leapfrog(0.02, im, qr, pr, init=True)
+    for _ in range(24):
+        qr, pr, gr, Vr = ro.leapfrog(0.02, im, qr, pr, gr, Vr)
+    assert rel_err_vec(q, qr) < 1e-9 and rel_err_vec(p, pr) < 1e-9 and rel_err_vec(g, gr) < 1e-8
+    assert rel_err(V, Vr) < 1e-10
+    # 25 fused launches, state uploaded once (device-resident between steps), 1 init gradient
+    assert c1["leapfrogs"] - c0["leapfrogs"] == 25
+    assert c1["uploads"] - c0["uploads"] == 1
+    assert c1["gradients"] - c0["gradients"] == 1
+    m.close()
+
+
+@pytest.fixture(scope="module")
+def nuts_pair():
+    """BASELINE configs[0]: bernoulli_logit_glm N=10k K=20, NUTS diag_e, 4 chains, 1000+1000."""
+    Ref = ref_oracle()
+    d = make_glm_data("bernoulli_logit", 10_000, 20)
+    m = stan_service.StanGLM("bernoulli_logit", d["X"], d["y"])
+    ro = Ref("bernoulli_logit", d["X"], d["y"])
+    kw = dict(num_chains=4, seed=4711, num_warmup=1000, num_samples=1000, delta=0.8, num_threads=4)
+    dev = m.nuts(**kw)
+    dev["counters"] = m.counters()
+    ref = ro.nuts(**kw)
+    m.close()
+    return Ref, dev, ref
+
+
+def test_nuts_same_seed_same_first_draws(nuts_pair):
+    """Host code and RNG streams are identical, lp/grad agree to ~1e-14, so the chains coincide until
+    floating-point differences are amplified: the first warm-up draws must match closely."""
+    Ref, dev, ref = nuts_pair
+    a, b = dev["warmup_draws"][:, :5, :], ref["warmup_draws"][:, :5, :]
+    assert np.array_equal(a[:, :, 3:6], b[:, :, 3:6])            # treedepth, n_leapfrog, divergent
+    assert np.max(np.abs(a[:, :, 7:] - b[:, :, 7:])) < 1e-6
+    assert np.max(np.abs(a[:, :, 0] - b[:, :, 0]) / np.abs(b[:, :, 0])) < 1e-9   # lp__
+
+
+def test_nuts_posterior_within_mcse(nuts_pair):
+    Ref, dev, ref = nuts_pair
+    P = dev["draws"].shape[2] - 7
+    zs = []
+    for k in range(P):
+        a, b = dev["draws"][:, :, 7 + k].T, ref["draws"][:, :, 7 + k].T   # (draws, chains)
+        z_mean = abs(a.mean() - b.mean()) / np.hypot(Ref.mcse_mean(a), Ref.mcse_mean(b))
+        z_sd = abs(a.std(ddof=1) - b.std(ddof=1)) / np.hypot(Ref.mcse_sd(a), Ref.mcse_sd(b))
+        zs += [z_mean, z_sd]
+        assert Ref.rhat(a) < 1.02
+        assert Ref.ess(a) > 400
+    # 42 comparisons: 4 sigma keeps the family-wise false-alarm rate < 0.3 %
+    assert max(zs) < 4.0, zs
+    assert np.all(dev["draws"][:, :, 5] == 0)                     # no divergences
+    # adapted tuning parameters agree to Monte-Carlo noise
+    assert np.all(np.abs(dev["stepsize"] / ref["stepsize"] - 1) < 0.35)
+
+
+def test_nuts_leapfrogs_ran_on_device(nuts_pair):
+    Ref, dev, ref = nuts_pair
+    n_lf = dev["draws"][:, :, 4].sum() + dev["warm_leapfrogs"].sum()
+    c = dev["counters"]
+    # every leapfrog of every transition is one fused device launch (plus init_stepsize's)
+    assert c["leapfrogs"] >= n_lf
+    assert c["uploads"] < c["leapfrogs"]          # state stayed resident for the rest
