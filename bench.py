@@ -96,37 +96,11 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
-# ------------------------------------------------------------------------------------------
-# synthetic data on the device (torch is plumbing: device memory + RNG + distributed)
-# ------------------------------------------------------------------------------------------
-def make_device_shard(torch, dev, N_total, K, rank, world, seed=20261017):
-    """Rows [r0, r1) of the synthetic N_total x K problem, column-major fp64, generated on the GPU.
-    Each 1M-row block has its own seed so any sharding reproduces the same global X."""
-    per = (N_total + world - 1) // world
-    r0, r1 = min(rank * per, N_total), min((rank + 1) * per, N_total)
-    n = r1 - r0
-    g = torch.Generator(device=dev)
-    beta = torch.from_numpy(np.random.Generator(np.random.Philox(key=[seed, 1])).standard_normal(K) / np.sqrt(K)).to(dev)
-    X = torch.empty((K, n), device=dev, dtype=torch.float64)       # column-major N x K
-    y = torch.empty(n, device=dev, dtype=torch.int32)
-    blk = 1_000_000
-    for b0 in range((r0 // blk) * blk, r1, blk):
-        g.manual_seed(seed * 1000 + b0 // blk)
-        xb = torch.randn((K, blk), generator=g, device=dev, dtype=torch.float64)
-        ub = torch.rand(blk, generator=g, device=dev, dtype=torch.float64)
-        lo, hi = max(b0, r0), min(b0 + blk, r1)
-        xs = xb[:, lo - b0:hi - b0]
-        X[:, lo - r0:hi - r0] = xs
-        eta = 0.3 + beta @ xs
-        y[lo - r0:hi - r0] = (ub[lo - b0:hi - b0] < torch.sigmoid(eta)).to(torch.int32)
-        del xb, ub
-    return X, y, r0, r1
-
-
 def run_b200(args):
     import torch
     import torch.distributed as dist
     from stan_b200 import GLMModel
+    from stan_b200.synth import make_logistic_shard
 
     rank, local_rank, world = dist_env()
     if world != args.gpus:
@@ -137,7 +111,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N_total, K = args.rows, args.cols
-    X, y, r0, r1 = make_device_shard(torch, dev, N_total, K, rank, world)
+    X, y, r0, r1 = make_logistic_shard(torch, dev, N_total, K, rank, world)
     n_local = r1 - r0
     torch.cuda.synchronize()
     m = GLMModel(FAMILY, X.data_ptr(), y.data_ptr(), data_on_device=True, N=n_local, K=K, ldx=n_local,

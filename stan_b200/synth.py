@@ -50,3 +50,37 @@ def theta_points(P, seed=SEED, n_random=1, scale=0.1):
     for _ in range(n_random):
         pts.append(scale * r.standard_normal(P))
     return pts
+
+
+# ---------------------------------------------------------------------------------------------
+# HBM-scale synthetic data, generated on the device that will hold it (bench.py, multi-GPU tests)
+# ---------------------------------------------------------------------------------------------
+def shard_rows(N_total, rank, world):
+    """Contiguous row block [r0, r1) of rank `rank` of `world` (SURVEY 8e partitioning)."""
+    per = (N_total + world - 1) // world
+    r0 = min(rank * per, N_total)
+    return r0, min(r0 + per, N_total)
+
+
+def make_logistic_shard(torch, dev, N_total, K, rank=0, world=1, seed=SEED, block=1_000_000, alpha_true=0.3):
+    """Rows shard_rows(N_total, rank, world) of the synthetic logistic-regression problem,
+    column-major fp64 X (stored as a (K, n) torch tensor) and int32 y, generated with torch's
+    Philox on `dev`.  Every `block`-row block has its own seed, so any sharding of the same
+    (N_total, K, seed) reproduces the same global matrix on the same device type."""
+    r0, r1 = shard_rows(N_total, rank, world)
+    n = r1 - r0
+    g = torch.Generator(device=dev)
+    beta = torch.from_numpy(_rng(seed, 1).standard_normal(K) / np.sqrt(max(K, 1))).to(dev)
+    X = torch.empty((K, n), device=dev, dtype=torch.float64)
+    y = torch.empty(n, device=dev, dtype=torch.int32)
+    for b0 in range((r0 // block) * block, r1, block):
+        g.manual_seed(seed * 1000 + b0 // block)
+        xb = torch.randn((K, block), generator=g, device=dev, dtype=torch.float64)
+        ub = torch.rand(block, generator=g, device=dev, dtype=torch.float64)
+        lo, hi = max(b0, r0), min(b0 + block, r1)
+        xs = xb[:, lo - b0:hi - b0]
+        X[:, lo - r0:hi - r0] = xs
+        eta = alpha_true + beta @ xs
+        y[lo - r0:hi - r0] = (ub[lo - b0:hi - b0] < torch.sigmoid(eta)).to(torch.int32)
+        del xb, ub
+    return X, y, r0, r1

@@ -1,0 +1,84 @@
+"""CPU suite (gloo, world_size 2): the host-side logic of the row-sharded N>1 path.
+
+What the GPU path relies on, checked here without a GPU:
+  * shard_rows partitions [0, N) exactly, and every sharding regenerates the same global X/y;
+  * the likelihood part of (lp, grad) is additive over row shards, so ONE all-reduce (sum) of the
+    per-shard likelihood partials followed by adding the priors once reproduces the unsharded result
+    -- the arithmetic b200glm does with ncclAllReduce + finish_kernel, done here with the C oracle
+    per shard and torch.distributed(gloo).all_reduce.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from stan_b200.synth import make_logistic_shard, shard_rows  # noqa: E402
+
+
+def test_shard_rows_partition():
+    for N in (0, 1, 31, 32, 33, 1000, 10_000_000):
+        for world in (1, 2, 3, 4, 8):
+            ranges = [shard_rows(N, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == N
+            for (a0, a1), (b0, b1) in zip(ranges, ranges[1:]):
+                assert a1 == b0 and a0 <= a1
+            assert sum(b - a for a, b in ranges) == N
+
+
+def _worker(rank, world, port, N, K, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from oracle.oracle import PortOracle
+    X, y, r0, r1 = make_logistic_shard(torch, torch.device("cpu"), N, K, rank, world, block=1000)
+    Xn, yn = X.numpy().T, y.numpy()
+    # the 128-byte communicator id travels the same way in bench.py (rank 0 -> everyone)
+    uid = torch.arange(128, dtype=torch.uint8) if rank == 0 else torch.zeros(128, dtype=torch.uint8)
+    dist.broadcast(uid, 0)
+    assert uid[77].item() == 77
+    P = K + 1
+    th = 0.1 * np.random.default_rng(3).standard_normal(P)
+    shard = PortOracle("bernoulli_logit", Xn, yn)
+    empty = PortOracle("bernoulli_logit", np.zeros((0, K)), np.zeros(0, np.int32))
+    lp_s, g_s = shard.log_prob_grad(th)
+    lp_0, g_0 = empty.log_prob_grad(th)               # priors only
+    lik = torch.tensor(np.concatenate([g_s - g_0, [lp_s - lp_0]]))   # likelihood partials of this shard
+    dist.all_reduce(lik, op=dist.ReduceOp.SUM)        # the one collective per gradient
+    total = lik.numpy()
+    lp, g = total[-1] + lp_0, total[:-1] + g_0        # priors added once, identically on every rank
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (r0, r1, Xn, yn))
+    if rank == 0:
+        Xf = np.concatenate([t[2] for t in gathered], axis=0)
+        yf = np.concatenate([t[3] for t in gathered])
+        out.put((lp, g, Xf, yf, th))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_row_sharded_gradient_world2_gloo():
+    N, K, world = 5003, 7, 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, N, K, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    lp, g, Xf, yf, th = out.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # same global data as the unsharded generator
+    X1, y1, _, _ = make_logistic_shard(torch, torch.device("cpu"), N, K, 0, 1, block=1000)
+    assert np.array_equal(X1.numpy().T, Xf) and np.array_equal(y1.numpy(), yf)
+    from oracle.oracle import PortOracle
+    lp_ref, g_ref = PortOracle("bernoulli_logit", Xf, yf).log_prob_grad(th)
+    assert abs(lp - lp_ref) / abs(lp_ref) < 1e-13
+    assert np.max(np.abs(g - g_ref)) / np.max(np.abs(g_ref)) < 1e-13
