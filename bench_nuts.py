@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""bench_nuts.py -- ESS/s and gradient-evals/s INSIDE NUTS (BASELINE metric, second half).
+
+Runs the reference's unmodified stan::services::sample::hmc_nuts_diag_e_adapt
+  (a) on b200::glm_model (GPU, stan_b200/lib/libb200stan.so) and
+  (b) on the reference CPU model (oracle/_ref), same seeds, same settings,
+and reports, per arm: wall time, gradient evaluations (sum n_leapfrog__ + transitions), grad evals/s,
+min/median ESS over parameters (stan::analyze::ess), ESS/s, and the posterior z-scores between arms.
+
+    python bench_nuts.py --config 1                 # N=10k K=20, 4 chains, 1000+1000 (BASELINE configs[0])
+    python bench_nuts.py --config 2 --ref-iters 0   # N=10M K=100 on the GPU; CPU arm skipped (hours)
+Writes one JSON line; not part of the driver's bench contract (bench.py is).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def summarize(res, Ref, num_chains):
+    d = res["draws"]
+    P = d.shape[2] - 7
+    ess = [Ref.ess(d[:, :, 7 + k].T) for k in range(P)]
+    n_grad_sampling = float(d[:, :, 4].sum() + d.shape[0] * d.shape[1])
+    n_grad_warm = float(res["warm_leapfrogs"].sum() + res["warmup_draws"].shape[0] * res["warmup_draws"].shape[1])
+    return dict(wall_s=res["wall"], grad_evals=n_grad_warm + n_grad_sampling,
+                grad_evals_per_s=(n_grad_warm + n_grad_sampling) / res["wall"],
+                ess_min=float(np.min(ess)), ess_median=float(np.median(ess)),
+                ess_min_per_s=float(np.min(ess)) / res["wall"],
+                mean_treedepth=float(d[:, :, 3].mean()), mean_n_leapfrog=float(d[:, :, 4].mean()),
+                divergent=int(d[:, :, 5].sum()), stepsize=[float(s) for s in res["stepsize"]])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=1)
+    ap.add_argument("--chains", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=1000)
+    ap.add_argument("--samples", type=int, default=1000)
+    ap.add_argument("--ref-iters", type=int, default=-1, help="CPU arm iterations (warmup=samples); 0 skips, -1 same")
+    ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--cols", type=int, default=0)
+    args = ap.parse_args()
+    from oracle.oracle import RefOracle
+    from stan_b200 import make_glm_data, stan_service
+
+    N, K = {1: (10_000, 20), 2: (10_000_000, 100)}[args.config]
+    N, K = args.rows or N, args.cols or K
+    t0 = time.time()
+    d = make_glm_data("bernoulli_logit", N, K)
+    t_gen = time.time() - t0
+    kw = dict(num_chains=args.chains, seed=4711, num_warmup=args.warmup, num_samples=args.samples, delta=0.8,
+              num_threads=args.chains)
+    t0 = time.time()
+    m = stan_service.StanGLM("bernoulli_logit", d["X"], d["y"], n_slots=max(8, args.chains))
+    t_upload = time.time() - t0
+    dev = m.nuts(**kw)
+    out = {"workload": f"bernoulli_logit_glm N={N} K={K}, NUTS diag_e {args.chains} chains {args.warmup}+{args.samples} "
+                       "via unmodified hmc_nuts_diag_e_adapt", "host_threads": os.cpu_count(),
+           "data_gen_s": t_gen, "upload_relayout_s": t_upload,
+           "b200": dict(summarize(dev, RefOracle, args.chains), counters=m.counters())}
+    m.close()
+    if args.ref_iters != 0:
+        kr = dict(kw)
+        if args.ref_iters > 0:
+            kr.update(num_warmup=args.ref_iters, num_samples=args.ref_iters)
+        ro = RefOracle("bernoulli_logit", d["X"], d["y"])
+        ref = ro.nuts(**kr)
+        out["reference_cpu"] = dict(summarize(ref, RefOracle, args.chains), threads=args.chains, isa=ro.isa,
+                                    iters=f'{kr["num_warmup"]}+{kr["num_samples"]}')
+        if kr["num_samples"] == kw["num_samples"]:
+            zs = []
+            for k in range(dev["draws"].shape[2] - 7):
+                a, b = dev["draws"][:, :, 7 + k].T, ref["draws"][:, :, 7 + k].T
+                zs.append(abs(a.mean() - b.mean()) / np.hypot(RefOracle.mcse_mean(a), RefOracle.mcse_mean(b)))
+                zs.append(abs(a.std(ddof=1) - b.std(ddof=1)) / np.hypot(RefOracle.mcse_sd(a), RefOracle.mcse_sd(b)))
+            out["posterior_max_z"] = float(max(zs))
+        out["speedup_grad_evals_per_s"] = out["b200"]["grad_evals_per_s"] / out["reference_cpu"]["grad_evals_per_s"]
+        out["speedup_ess_per_s"] = out["b200"]["ess_min_per_s"] / out["reference_cpu"]["ess_min_per_s"]
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

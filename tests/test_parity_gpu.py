@@ -204,3 +204,41 @@ def test_device_resident_data_path():
     lp_r, g_r = po.log_prob_grad(th)
     assert rel_err(lp, lp_r) < TOL and rel_err_vec(g, g_r) < TOL
     m.close()
+
+
+def test_full_size_config2_against_reference():
+    """BASELINE configs[1] at full size: N=10M, K=100 (X = 8 GB, generated on the GPU), compared with
+    the reference itself evaluated on the host copy of the very same buffers, plus the additive
+    'checksum of checksums' property: the likelihood part of ten 1M-row shards sums to the whole."""
+    import torch
+    from oracle.oracle import PortOracle, RefOracle
+    from stan_b200.synth import make_logistic_shard
+    if not RefOracle.available():
+        pytest.skip("oracle/_ref not present")
+    N, K = 10_000_000, 100
+    dev = torch.device("cuda", 0)
+    X, y, _, _ = make_logistic_shard(torch, dev, N, K)
+    m = GLMModel("bernoulli_logit", X.data_ptr(), y.data_ptr(), data_on_device=True, N=N, K=K, ldx=N)
+    th = 0.05 * np.random.default_rng(11).standard_normal(K + 1)
+    lp, g = m.log_prob_grad(th)
+    # shards (device-resident views of the same buffers: column-major with ldx = N)
+    prior = PortOracle("bernoulli_logit", np.zeros((0, K)), np.zeros(0, np.int32))
+    lp0, g0 = prior.log_prob_grad(th)
+    lp_sum, g_sum = lp0, g0.copy()
+    for s in range(10):
+        r0 = s * 1_000_000
+        ms = GLMModel("bernoulli_logit", X.data_ptr() + 8 * r0, y.data_ptr() + 4 * r0, data_on_device=True,
+                      N=1_000_000, K=K, ldx=N)
+        lps, gs = ms.log_prob_grad(th)
+        lp_sum += lps - lp0
+        g_sum += gs - g0
+        ms.close()
+    assert rel_err(lp, lp_sum) < 1e-12 and rel_err_vec(g, g_sum) < 1e-12
+    Xh, yh = X.cpu().numpy().T, y.cpu().numpy()
+    del X, y
+    torch.cuda.empty_cache()
+    ro = RefOracle("bernoulli_logit", Xh, yh)
+    lp_r, g_r = ro.log_prob_grad(th)
+    assert rel_err(lp, lp_r) < TOL, (lp, lp_r)
+    assert rel_err_vec(g, g_r) < TOL
+    m.close()
