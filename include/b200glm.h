@@ -38,6 +38,10 @@ enum { B200GLM_OK = 0, B200GLM_DOMAIN = 1, B200GLM_INVALID = 2, B200GLM_CUDA = 3
 /* SM/prim/prob/{bernoulli_logit_glm_lpmf.hpp:49, poisson_log_glm_lpmf.hpp:51, normal_id_glm_lpdf.hpp:54} */
 enum { B200GLM_BERNOULLI_LOGIT = 0, B200GLM_POISSON_LOG = 1, B200GLM_NORMAL_ID = 2 };
 
+/* desc.flags: use the wide-matrix kernel (16-row panels split over the CTA; the default for K > 256)
+ * even for a narrow X -- for tests of that kernel at small K */
+#define B200GLM_FLAG_FORCE_WIDE 1
+
 typedef struct b200glm_handle b200glm_handle;
 
 typedef struct b200glm_desc {
@@ -59,7 +63,7 @@ typedef struct b200glm_desc {
                            priors are added once, identically, on every rank. */
   int64_t N_total;      /* rows over all shards (normal_id needs N for -N log sigma); 0 => N */
   int32_t grid_ctas;    /* 0 = one persistent CTA per SM */
-  int32_t reserved;
+  int32_t flags;        /* B200GLM_FLAG_* */
 } b200glm_desc;
 
 /* Data upload + one-time re-layout of X into the row-panel format the kernel streams

@@ -27,7 +27,7 @@ class Desc(C.Structure):
         ("prior_sigma_loc", C.c_double), ("prior_sigma_scale", C.c_double),
         ("prior_sigma_a_scale", C.c_double),
         ("device", C.c_int32), ("n_slots", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
-        ("N_total", C.c_int64), ("grid_ctas", C.c_int32), ("reserved", C.c_int32),
+        ("N_total", C.c_int64), ("grid_ctas", C.c_int32), ("flags", C.c_int32),
     ]
 
 

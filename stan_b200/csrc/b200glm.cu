@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "glm_kernels.cuh"
+#include "glm_wide_kernel.cuh"
 
 using namespace b200glm;
 
@@ -86,6 +87,9 @@ struct b200glm_handle {
   int grid = 0, n_stages = 0, stage_a = 0;
   size_t smem_bytes = 0;
   int cpl = 0;
+  // wide kernel (K > 256 or B200GLM_FLAG_FORCE_WIDE): 16-row panels streamed as J sub-panels
+  bool wide = false;
+  int panel_rows = PANEL_ROWS, Cpad = 0, Kc = 0, J = 0, spw = 0, spc = 0;
   double lgamma_sum = 0.0;  // local shard
   double lgamma_sum_total = 0.0;
   bool bad_y = false;
@@ -137,6 +141,26 @@ kernel_fn pick_kernel(int family, int cpl) {
   return nullptr;
 }
 
+template <int FAMILY>
+kernel_fn pick_wide_shape(int spw, int spc) {
+  if (spc == 4 && spw == 1) return glm_wide_kernel<FAMILY, 1, 4>;
+  if (spc == 4 && spw == 2) return glm_wide_kernel<FAMILY, 2, 4>;
+  if (spc == 8 && spw == 2) return glm_wide_kernel<FAMILY, 2, 8>;
+  if (spc == 8 && spw == 3) return glm_wide_kernel<FAMILY, 3, 8>;
+  return nullptr;
+}
+kernel_fn pick_wide_kernel(int family, int spw, int spc) {
+  switch (family) {
+    case FAM_BERNOULLI_LOGIT: return pick_wide_shape<FAM_BERNOULLI_LOGIT>(spw, spc);
+    case FAM_POISSON_LOG: return pick_wide_shape<FAM_POISSON_LOG>(spw, spc);
+    case FAM_NORMAL_ID: return pick_wide_shape<FAM_NORMAL_ID>(spw, spc);
+  }
+  return nullptr;
+}
+kernel_fn handle_kernel(const b200glm_handle* h) {
+  return h->wide ? pick_wide_kernel(h->d.family, h->spw, h->spc) : pick_kernel(h->d.family, h->cpl);
+}
+
 size_t fixed_smem_bytes(int K, int G, int stage_a, int S) {
   const int Kpad = (K + 3) & ~3;
   size_t b = 0;
@@ -170,6 +194,9 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
   p.P = h->P;
   p.off_beta = h->off_beta;
   p.n_stages = h->n_stages;
+  p.Cpad = h->Cpad;
+  p.Kc = h->Kc;
+  p.J = h->J;
   p.mode = mode;
   p.fuse_finish = (h->d.world <= 1 && h->d.G == 0) ? 1 : 0;
   p.stage_a_in_smem = h->stage_a;
@@ -210,8 +237,8 @@ int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian,
   const bool need_likelihood = ((!propto) || is_var) && h->d.N_total != -1;
   const bool rows_anywhere = (h->d.N_total > 0 ? h->d.N_total : h->d.N) > 0;
   if (need_likelihood && rows_anywhere) {
-    kernel_fn fn = pick_kernel(h->d.family, h->cpl);
-    fn<<<h->grid, NUM_THREADS, h->smem_bytes, s->stream>>>(p);
+    kernel_fn fn = handle_kernel(h);
+    fn<<<h->grid, h->wide ? WIDE_THREADS : NUM_THREADS, h->smem_bytes, s->stream>>>(p);
     h->launches++;
     if (h->d.G > 0) {
       const int gb = std::min(h->d.G, 4 * 148);
@@ -356,12 +383,12 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   if (d.G > 0 && d.N > 0 && !d.group) return fail(B200GLM_INVALID, "group is null");
   if (!(d.prior_alpha_sd > 0) || !(d.prior_beta_sd > 0)) return fail(B200GLM_INVALID, "prior scales must be > 0");
   if (d.n_slots < 1) h->d.n_slots = 1;
-  if (d.K > 256) return fail(B200GLM_INVALID, "K > 256 is not supported by the single-CTA panel kernel yet");
-
   h->P = (d.G > 0 ? 2 + d.G : 1) + d.K + (d.family == B200GLM_NORMAL_ID ? 1 : 0);
   h->off_beta = d.G > 0 ? 2 + d.G : 1;
   h->C = d.K + 1 + (d.G > 0 ? 1 : 0);
-  h->n_panels = (d.N + PANEL_ROWS - 1) / PANEL_ROWS;
+  h->wide = d.K > 256 || (d.flags & B200GLM_FLAG_FORCE_WIDE);
+  h->panel_rows = h->wide ? WIDE_ROWS : PANEL_ROWS;
+  h->n_panels = (d.N + h->panel_rows - 1) / h->panel_rows;
   const int P = h->P;
 
   int ndev = 0;
@@ -375,30 +402,50 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
 
   // launch geometry
   h->grid = d.grid_ctas > 0 ? d.grid_ctas : prop.multiProcessorCount;
-  const int need_cpl = std::max(1, (d.K + 7) / 8);
-  h->cpl = 0;
-  for (int c : kCplChoices)
-    if (c >= need_cpl) {
-      h->cpl = c;
-      break;
-    }
-  if (!h->cpl) return fail(B200GLM_INVALID, "K too large");
   h->stage_a = (d.G > 0 && d.G <= SMEM_A_MAX_GROUPS) ? 1 : 0;
   const size_t max_dyn = (size_t)prop.sharedMemPerBlockOptin - 1024;  // static scratch + slack
-  const size_t tile_bytes = (size_t)h->C * PANEL_ROWS * 8;
-  int S = MAX_STAGES;
-  while (S > 0 && fixed_smem_bytes(d.K, d.G, h->stage_a, S) + (size_t)S * tile_bytes > max_dyn) --S;
-  if (S < 1) return fail(B200GLM_INVALID, "panel does not fit in shared memory");
-  if (S > NUM_CONSUMER_WARPS) S = (S / NUM_CONSUMER_WARPS) * NUM_CONSUMER_WARPS;  // stage <-> warp ownership
-  h->n_stages = S;
-  h->smem_bytes = fixed_smem_bytes(d.K, d.G, h->stage_a, S) + (size_t)S * tile_bytes;
-  kernel_fn fn = pick_kernel(d.family, h->cpl);
+  if (!h->wide) {
+    h->Cpad = h->C;
+    const int need_cpl = std::max(1, (d.K + 7) / 8);
+    h->cpl = 0;
+    for (int c : kCplChoices)
+      if (c >= need_cpl) {
+        h->cpl = c;
+        break;
+      }
+    if (!h->cpl) return fail(B200GLM_INVALID, "K too large");
+    const size_t tile_bytes = (size_t)h->C * PANEL_ROWS * 8;
+    int S = MAX_STAGES;
+    while (S > 0 && fixed_smem_bytes(d.K, d.G, h->stage_a, S) + (size_t)S * tile_bytes > max_dyn) --S;
+    if (S < 1) return fail(B200GLM_INVALID, "panel does not fit in shared memory");
+    if (S > NUM_CONSUMER_WARPS) S = (S / NUM_CONSUMER_WARPS) * NUM_CONSUMER_WARPS;  // stage <-> warp ownership
+    h->n_stages = S;
+    h->smem_bytes = fixed_smem_bytes(d.K, d.G, h->stage_a, S) + (size_t)S * tile_bytes;
+  } else {
+    // sub-panel width: 32 columns while at most 16 sub-panels are needed, else 64
+    h->Cpad = (h->C + 7) & ~7;
+    h->spc = h->Cpad <= 512 ? 4 : 8;
+    h->Kc = 8 * h->spc;
+    h->J = (h->Cpad + h->Kc - 1) / h->Kc;
+    h->spw = (h->J + WIDE_CONSUMER_WARPS - 1) / WIDE_CONSUMER_WARPS;
+    if (h->spc == 8 && h->spw < 2) h->spw = 2;
+    if (!pick_wide_kernel(d.family, h->spw, h->spc))
+      return fail(B200GLM_INVALID, "K too large for the wide kernel (K <= 1534)");
+    const size_t fixed = wide_fixed_doubles(h->J, h->Kc, d.G, h->stage_a) * 8;
+    const size_t slot_bytes = (size_t)h->Kc * WIDE_ROWS * 8;
+    int T = fixed < max_dyn ? (int)((max_dyn - fixed) / (slot_bytes + 16)) : 0;
+    if (T > WIDE_MAX_SLOTS) T = WIDE_MAX_SLOTS;
+    if (T < h->J) return fail(B200GLM_INVALID, "one 16-row panel does not fit in shared memory (K too large)");
+    h->n_stages = T;
+    h->smem_bytes = fixed + (size_t)T * (slot_bytes + 16);
+  }
+  kernel_fn fn = handle_kernel(h);
   CUDA_TRY(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
 
   // ---- data upload + re-layout ----
   cudaStream_t st;
   CUDA_TRY(h, cudaStreamCreate(&st));
-  const size_t panel_doubles = (size_t)h->n_panels * h->C * PANEL_ROWS;
+  const size_t panel_doubles = (size_t)h->n_panels * h->Cpad * h->panel_rows;
   if (panel_doubles) CUDA_TRY(h, cudaMalloc(&h->panels, panel_doubles * 8));
 
   // y / group on host and device
@@ -481,10 +528,11 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     }
   }
   // X: device-resident or staged from the host in row chunks
+  const int PR = h->panel_rows, SWZ = h->wide ? 0 : 1;
   if (d.N > 0) {
     if (d.data_on_device || d.K == 0) {
       relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(d.X, d.ldx, 0, d_y, d_yr, d_group, d_perm, 0, d.N,
-                                                                    d.N, d.K, h->C, 0, h->C, h->panels);
+                                                                    d.N, d.K, h->C, 0, h->Cpad, h->panels, PR, h->Cpad, SWZ);
       CUDA_TRY(h, cudaGetLastError());
     } else if (d_perm) {
       // permuted gather needs all of X on the device at once
@@ -493,11 +541,11 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
       CUDA_TRY(h, cudaMemcpy2D(dX, sizeof(double) * d.N, d.X, sizeof(double) * d.ldx, sizeof(double) * d.N, d.K,
                                cudaMemcpyHostToDevice));
       relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(dX, d.N, 0, d_y, d_yr, d_group, d_perm, 0, d.N,
-                                                                    d.N, d.K, h->C, 0, h->C, h->panels);
+                                                                    d.N, d.K, h->C, 0, h->Cpad, h->panels, PR, h->Cpad, SWZ);
       CUDA_TRY(h, cudaStreamSynchronize(st));
       cudaFree(dX);
     } else {
-      const long long chunk_rows = std::max<long long>(32, ((long long)(256u << 20) / (8LL * d.K)) & ~31LL);
+      const long long chunk_rows = std::max<long long>(32, ((long long)(256u << 20) / (8LL * std::max(d.K, 1))) & ~31LL);
       double* dX;
       CUDA_TRY(h, cudaMalloc(&dX, sizeof(double) * (size_t)std::min(chunk_rows, (long long)d.N) * d.K));
       for (long long r0 = 0; r0 < d.N; r0 += chunk_rows) {
@@ -505,13 +553,13 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
         CUDA_TRY(h, cudaMemcpy2DAsync(dX, sizeof(double) * nr, d.X + r0, sizeof(double) * d.ldx, sizeof(double) * nr,
                                       d.K, cudaMemcpyHostToDevice, st));
         relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(dX, nr, r0, nullptr, nullptr, nullptr, nullptr,
-                                                                      r0, nr, d.N, d.K, h->C, 0, d.K, h->panels);
+                                                                      r0, nr, d.N, d.K, h->C, 0, d.K, h->panels, PR, h->Cpad, SWZ);
         CUDA_TRY(h, cudaStreamSynchronize(st));
       }
       cudaFree(dX);
       // aux columns (y, group) in one more pass
       relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(nullptr, 0, 0, d_y, d_yr, d_group, nullptr, 0, d.N,
-                                                                    d.N, d.K, h->C, d.K, h->C, h->panels);
+                                                                    d.N, d.K, h->C, d.K, h->Cpad, h->panels, PR, h->Cpad, SWZ);
     }
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaStreamSynchronize(st));
@@ -538,7 +586,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     CUDA_TRY(h, cudaMalloc(&s->partials, sizeof(double) * (size_t)h->grid * pstride));
     CUDA_TRY(h, cudaMalloc(&s->ticket, sizeof(unsigned int)));
     CUDA_TRY(h, cudaMemset(s->ticket, 0, sizeof(unsigned int)));
-    if (d.G > 0 && h->n_panels > 0) CUDA_TRY(h, cudaMalloc(&s->r_out, sizeof(double) * h->n_panels * PANEL_ROWS));
+    if (d.G > 0 && h->n_panels > 0) CUDA_TRY(h, cudaMalloc(&s->r_out, sizeof(double) * h->n_panels * h->panel_rows));
     CUDA_TRY(h, cudaMalloc(&s->lik, sizeof(double) * (P + 2)));
     CUDA_TRY(h, cudaMemset(s->lik, 0, sizeof(double) * (P + 2)));
     CUDA_TRY(h, cudaMalloc(&s->result, sizeof(double) * (P + 2)));

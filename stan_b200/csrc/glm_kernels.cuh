@@ -56,7 +56,8 @@ struct KernelParams {
   long long n_rows;    // local rows
   long long n_panels;  // local panels
   int K, C, G, family, P, off_beta;
-  int n_stages;
+  int n_stages;        // narrow kernel: panel stages; wide kernel: sub-panel slots in the ring
+  int Cpad, Kc, J;     // wide kernel: padded column count, sub-panel width, sub-panels per row panel
   int mode;
   int fuse_finish;     // last CTA also runs finish() (world == 1 && G == 0)
   int stage_a_in_smem;
@@ -347,6 +348,45 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
 }
 
 // ------------------------------------------------------------------------------------------
+// Shared tail of both main kernels.  Every CTA has written its partial sums
+// (my_part[0..K) = beta gradient, [K] = lp-sum, [K+1] = r-sum) to p.partials; the LAST CTA to
+// arrive (ticket) adds them in fixed CTA order -> bitwise deterministic, then (single GPU, no
+// groups) runs the model epilogue.  Must be called by all threads of the CTA.
+// ------------------------------------------------------------------------------------------
+template <int FAMILY>
+__device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& p, double* sh_scratch,
+                                                            int* sh_is_last) {
+  const int tid = threadIdx.x, nt = blockDim.x, grid = gridDim.x;
+  const int K = p.K, G = p.G, P = p.P;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(p.ticket, 1u);
+    *sh_is_last = (t == (unsigned int)(grid - 1));
+  }
+  __syncthreads();
+  if (!*sh_is_last) return;
+
+  __threadfence();
+  for (int j = tid; j < K + 2; j += nt) {
+    double v = 0.0;
+    for (int b = 0; b < grid; ++b) v += __ldcg(p.partials + (size_t)b * p.pstride + j);
+    if (j < K)
+      p.lik[p.off_beta + j] = v;
+    else if (j == K)
+      p.lik[P] = v;
+    else if (G == 0)
+      p.lik[0] = v;
+  }
+  if (tid == 0) *p.ticket = 0u;
+  if (FAMILY == FAM_NORMAL_ID && tid == 0) p.lik[P - 1] = 0.0;  // sigma entry is derived in finish()
+  if (G > 0 && tid < 2) p.lik[tid] = 0.0;
+  __threadfence();
+  __syncthreads();
+  if (p.fuse_finish) finish(p, sh_scratch);
+}
+
+// ------------------------------------------------------------------------------------------
 // The main kernel
 // ------------------------------------------------------------------------------------------
 template <int FAMILY, int CPL>
@@ -528,33 +568,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
     for (int w = 0; w < NUM_CONSUMER_WARPS; ++w) v += red[w * (Kpad + 4) + src];
     my_part[j] = v;
   }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int t = atomicAdd(p.ticket, 1u);
-    sh_is_last = (t == (unsigned int)(grid - 1));
-  }
-  __syncthreads();
-  if (!sh_is_last) return;
-
-  // ===================== last CTA: deterministic cross-CTA sum =====================
-  __threadfence();
-  for (int j = tid; j < K + 2; j += NUM_THREADS) {
-    double v = 0.0;
-    for (int b = 0; b < grid; ++b) v += __ldcg(p.partials + (size_t)b * p.pstride + j);
-    if (j < K)
-      p.lik[p.off_beta + j] = v;
-    else if (j == K)
-      p.lik[P] = v;
-    else if (G == 0)
-      p.lik[0] = v;
-  }
-  if (tid == 0) *p.ticket = 0u;
-  if (FAMILY == FAM_NORMAL_ID && tid == 0) p.lik[P - 1] = 0.0;  // sigma entry is derived in finish()
-  if (G > 0 && tid < 2) p.lik[tid] = 0.0;
-  __threadfence();
-  __syncthreads();
-  if (p.fuse_finish) finish(p, sh_scratch);
+  cross_cta_reduce_and_finish<FAMILY>(p, sh_scratch, &sh_is_last);
 }
 
 // G > 0: deterministic per-group sums of the residual (rows are sorted by group at upload).
@@ -586,26 +600,28 @@ __global__ void __launch_bounds__(NUM_THREADS) finish_kernel(const KernelParams 
 // ------------------------------------------------------------------------------------------
 // One-time re-layout: column-major X (+ y, group) -> row-panel format (optionally through a row
 // permutation that sorts rows by group).  One thread per (panel, column, row).
+//   narrow format: PR = 32 rows per panel, Cs = C columns, XOR swizzle (swz = 1)
+//   wide format:   PR = 16 rows per panel, Cs = Cpad columns (zero padded), no swizzle
 // ------------------------------------------------------------------------------------------
 __global__ void relayout_kernel(const double* __restrict__ X, long long ldx, long long x_row0,
                                 const int32_t* __restrict__ y_int, const double* __restrict__ y_real,
                                 const int32_t* __restrict__ group, const long long* __restrict__ perm,
                                 long long row0, long long n_rows_chunk, long long n_rows_total, int K, int C,
-                                int c_begin, int c_end, double* __restrict__ panels) {
-  // Writes columns [c_begin, c_end) of destination rows [row0, row0 + n_rows_chunk), row0 % 32 == 0.
+                                int c_begin, int c_end, double* __restrict__ panels, int PR, int Cs, int swz) {
+  // Writes columns [c_begin, c_end) of destination rows [row0, row0 + n_rows_chunk), row0 % PR == 0.
   // X may be a chunk whose first row is source row x_row0 (leading dimension ldx).
-  const long long n_panels_chunk = (n_rows_chunk + 31) / 32;
+  const long long n_panels_chunk = (n_rows_chunk + PR - 1) / PR;
   const int nc = c_end - c_begin;
-  const long long total = n_panels_chunk * nc * 32;
+  const long long total = n_panels_chunk * nc * PR;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(idx & 31);
-    const long long t = idx >> 5;
+    const int r = (int)(idx % PR);
+    const long long t = idx / PR;
     const int c = c_begin + (int)(t % nc);
     const long long pl = t / nc;
-    const long long dst_row = row0 + pl * 32 + r;
+    const long long dst_row = row0 + pl * PR + r;
     double v = 0.0;
-    if (dst_row < n_rows_total && dst_row < row0 + n_rows_chunk) {
+    if (dst_row < n_rows_total && dst_row < row0 + n_rows_chunk && c < C) {
       const long long src = perm ? perm[dst_row] : dst_row;
       if (c < K)
         v = X[(src - x_row0) + (long long)c * ldx];
@@ -614,7 +630,8 @@ __global__ void relayout_kernel(const double* __restrict__ X, long long ldx, lon
       else
         v = (double)group[src];
     }
-    panels[((row0 >> 5) + pl) * (long long)C * 32 + (long long)c * 32 + (r ^ ((c & 3) << 2))] = v;
+    const int rr = swz ? (r ^ ((c & 3) << 2)) : r;
+    panels[(row0 / PR + pl) * (long long)Cs * PR + (long long)c * PR + rr] = v;
   }
 }
 

@@ -1,0 +1,314 @@
+// glm_wide_kernel.cuh -- single-pass GLM log-density + gradient for WIDE design matrices
+// (K > 256, BASELINE configs[4]: K = 1000), where one 32-row panel no longer fits a warp's
+// registers / a CTA's shared memory.  Same arithmetic and same tail as glm_fused_kernel
+// (glm_kernels.cuh); what changes is how a row panel is spread over the CTA.
+//
+// Data layout in HBM ("wide row-panel format", relayout_kernel with PR = 16, no swizzle):
+//   rows are cut into panels of 16; panel n is one contiguous block of Cpad columns x 16 doubles
+//   (column-major inside the panel, Cpad = C rounded up to 8, padding columns are zero).
+//   A panel is streamed as J sub-panels of KC columns (KC*128 bytes = one cp.async.bulk each).
+//
+// CTA (persistent, one per SM) = 8 consumer warps + 1 TMA producer warp + 1 link warp.
+//   The shared-memory ring has T >= J sub-panel slots: one whole row panel stays resident between
+//   its eta pass and its X^T r pass, the other E = T - J slots hold the head of the NEXT panel.
+//   consumer warp w owns sub-panels j = w, w+8, ... of every row panel (so it owns those columns'
+//   gradient accumulators outright: no cross-warp reduction of the gradient):
+//     P1(n, j): partial eta for the 16 rows over the sub-panel's columns
+//     -> 8 partials/row meet in smem, ETA barrier -> link warp adds them in fixed order, applies
+//        the link function (lp_i, r_i), R barrier ->
+//     P2(n, j): acc[col] += X[row][col] * r[row] from the SAME smem bytes, then the slot is released.
+//   While the link warp works, the consumers already run P1 on the prefetched head of panel n+1,
+//   so the link latency (fp64 exp/log1p chain) is hidden.
+//   Lane mapping (both passes): lane = (rq = lane & 3, cq = lane >> 2) handles column cq + 8t and the
+//   four rows {2rq, 2rq+1, 2rq+8, 2rq+9} with two LDS.128; odd cq swaps the order of the two
+//   loads, which makes every quarter-warp cover all 32 banks (conflict free without a swizzle).
+#pragma once
+
+#include "glm_kernels.cuh"
+
+namespace b200glm {
+
+constexpr int WIDE_ROWS = 16;
+constexpr int WIDE_CONSUMER_WARPS = 8;
+constexpr int WIDE_THREADS = (WIDE_CONSUMER_WARPS + 2) * 32;
+constexpr int WIDE_MAX_SLOTS = 96;
+enum { WIDE_BAR_ETA = 1, WIDE_BAR_R = 2 };
+constexpr int WIDE_BAR_COUNT = (WIDE_CONSUMER_WARPS + 1) * 32;  // consumers + link warp
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// bytes of dynamic shared memory besides the ring slots and their barriers
+__host__ __device__ inline size_t wide_fixed_doubles(int J, int KC, int G, int stage_a) {
+  return (size_t)J * KC + WIDE_CONSUMER_WARPS * WIDE_ROWS + WIDE_ROWS + (stage_a ? ((G + 1) & ~1) : 0);
+}
+
+template <int FAMILY, int SPW, int SPC>
+__global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelParams p) {
+  constexpr int WR = WIDE_ROWS, LPC = WR / 4, CPS = 32 / LPC;  // lanes per column, columns per step
+  constexpr int KC = SPC * CPS;                                // sub-panel width (columns)
+  constexpr int SLOT = KC * WR;                                // doubles per ring slot
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int K = p.K, G = p.G, P = p.P, J = p.J, T = p.n_stages, Cpad = p.Cpad;
+
+  double* ring = reinterpret_cast<double*>(smem_raw);            // T * SLOT
+  double* sbeta = ring + (size_t)T * SLOT;                       // J * KC (zero beyond K)
+  double* eta_part = sbeta + J * KC;                             // 8 * WR
+  double* r_sh = eta_part + WIDE_CONSUMER_WARPS * WR;            // WR
+  double* sa = r_sh + WR;                                        // G (optional)
+  double* after_a = sa + (p.stage_a_in_smem ? ((G + 1) & ~1) : 0);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(after_a);     // T
+  uint64_t* empty_bar = full_bar + T;                            // T
+  __shared__ double sh_scratch[64];
+  __shared__ int sh_is_last;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grid = gridDim.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < T; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+
+  // ---- theta for this launch (leapfrog: begin_update_p + update_q, expl_leapfrog.hpp:16-26) ----
+  auto theta_at = [&](int i) -> double {
+    if (p.mode == MODE_LEAPFROG) {
+      const double ph = p.st_in[P + i] - (0.5 * p.eps) * p.st_in[2 * P + i];
+      return p.st_in[i] + p.eps * (p.inv_metric[i] * ph);
+    }
+    return p.theta_in[i];
+  };
+  for (int k = tid; k < J * KC; k += WIDE_THREADS) sbeta[k] = k < K ? theta_at(p.off_beta + k) : 0.0;
+  if (p.stage_a_in_smem)
+    for (int g = tid; g < G; g += WIDE_THREADS) sa[g] = theta_at(2 + g);
+  if (blockIdx.x == 0)
+    for (int i = tid; i < P; i += WIDE_THREADS) p.theta_used[i] = theta_at(i);
+  __syncthreads();
+
+  const long long n_panels = p.n_panels;
+  const long long n_my = (long long)blockIdx.x < n_panels ? (n_panels - blockIdx.x + grid - 1) / grid : 0;
+  const int E = T - J;  // look-ahead slots: sub-panels j < E of panel n+1 can land before P2(n) starts
+  double* my_part = p.partials + (size_t)blockIdx.x * p.pstride;
+
+  if (warp < WIDE_CONSUMER_WARPS) {
+    // =============================== consumers ===============================
+    const int rq = lane & (LPC - 1), cq = lane / LPC;
+    const int swap = cq & 1;
+    const int chunkA = swap ? rq + LPC : rq, chunkB = swap ? rq : rq + LPC;
+    const int offA = 2 * chunkA, offB = 2 * chunkB;
+
+    int slot[SPW];
+    uint32_t par[SPW];
+    int steps[SPW];  // 0 = this warp has no such sub-panel
+#pragma unroll
+    for (int i = 0; i < SPW; ++i) {
+      const int j = warp + WIDE_CONSUMER_WARPS * i;
+      slot[i] = j;
+      par[i] = 0;
+      const int cols = j < J ? min(KC, Cpad - j * KC) : 0;
+      steps[i] = cols / CPS;
+    }
+    double acc[SPW * SPC];
+#pragma unroll
+    for (int a = 0; a < SPW * SPC; ++a) acc[a] = 0.0;
+    double eA0 = 0.0, eA1 = 0.0, eB0 = 0.0, eB1 = 0.0;
+
+    auto pass1 = [&](int i, int sl, uint32_t pr) {
+      mbar_wait(&full_bar[sl], pr);
+      const double* tile = ring + (size_t)sl * SLOT + cq * WR;
+      const double* bj = sbeta + (warp + WIDE_CONSUMER_WARPS * i) * KC + cq;
+#pragma unroll
+      for (int t = 0; t < SPC; ++t) {
+        if (t < steps[i]) {
+          const double b = bj[CPS * t];
+          const double2 xa = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offA);
+          const double2 xb = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offB);
+          eA0 = fma(xa.x, b, eA0);
+          eA1 = fma(xa.y, b, eA1);
+          eB0 = fma(xb.x, b, eB0);
+          eB1 = fma(xb.y, b, eB1);
+        }
+      }
+    };
+
+    for (long long n = 0; n < n_my; ++n) {
+      // ---- P1 on the sub-panels of panel n that were not already done early ----
+#pragma unroll
+      for (int i = 0; i < SPW; ++i) {
+        const bool early = (warp + WIDE_CONSUMER_WARPS * i) < E;
+        if (steps[i] > 0 && (n == 0 || !early)) pass1(i, slot[i], par[i]);
+      }
+      // ---- publish this warp's partial eta of the 16 rows ----
+      {
+        double lo0 = swap ? eB0 : eA0, lo1 = swap ? eB1 : eA1;  // rows 2rq, 2rq+1
+        double hi0 = swap ? eA0 : eB0, hi1 = swap ? eA1 : eB1;  // rows 2rq+8, 2rq+9
+#pragma unroll
+        for (int o = LPC; o < 32; o <<= 1) {
+          lo0 += __shfl_xor_sync(0xffffffffu, lo0, o);
+          lo1 += __shfl_xor_sync(0xffffffffu, lo1, o);
+          hi0 += __shfl_xor_sync(0xffffffffu, hi0, o);
+          hi1 += __shfl_xor_sync(0xffffffffu, hi1, o);
+        }
+        if (cq == 0) {
+          double* ep = eta_part + warp * WR;
+          *reinterpret_cast<double2*>(ep + 2 * rq) = make_double2(lo0, lo1);
+          *reinterpret_cast<double2*>(ep + 2 * (rq + LPC)) = make_double2(hi0, hi1);
+        }
+        eA0 = eA1 = eB0 = eB1 = 0.0;
+      }
+      __threadfence_block();
+      named_bar_arrive(WIDE_BAR_ETA, WIDE_BAR_COUNT);
+
+      // ---- while the link warp works: P1 on the prefetched head of panel n+1 ----
+      if (n + 1 < n_my) {
+#pragma unroll
+        for (int i = 0; i < SPW; ++i) {
+          const bool early = (warp + WIDE_CONSUMER_WARPS * i) < E;
+          if (steps[i] > 0 && early) {
+            int ns = slot[i] + J;
+            uint32_t np = par[i];
+            if (ns >= T) {
+              ns -= T;
+              np ^= 1u;
+            }
+            pass1(i, ns, np);
+          }
+        }
+      }
+
+      // ---- P2: X^T r from the same resident sub-panels ----
+      named_bar_sync(WIDE_BAR_R, WIDE_BAR_COUNT);
+      const double2 rA = *reinterpret_cast<const double2*>(r_sh + offA);
+      const double2 rB = *reinterpret_cast<const double2*>(r_sh + offB);
+#pragma unroll
+      for (int i = 0; i < SPW; ++i) {
+        if (steps[i] > 0) {
+          const double* tile = ring + (size_t)slot[i] * SLOT + cq * WR;
+#pragma unroll
+          for (int t = 0; t < SPC; ++t) {
+            if (t < steps[i]) {
+              const double2 xa = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offA);
+              const double2 xb = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offB);
+              double a = acc[i * SPC + t];
+              a = fma(xa.x, rA.x, a);
+              a = fma(xa.y, rA.y, a);
+              a = fma(xb.x, rB.x, a);
+              a = fma(xb.y, rB.y, a);
+              acc[i * SPC + t] = a;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[slot[i]]);
+        }
+        slot[i] += J;
+        if (slot[i] >= T) {
+          slot[i] -= T;
+          par[i] ^= 1u;
+        }
+      }
+    }
+
+    // ---- this warp's columns of the CTA partial (sum over the 4 row-lanes of each column) ----
+#pragma unroll
+    for (int i = 0; i < SPW; ++i) {
+#pragma unroll
+      for (int t = 0; t < SPC; ++t) {
+        double v = acc[i * SPC + t];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        const int c = (warp + WIDE_CONSUMER_WARPS * i) * KC + cq + CPS * t;
+        if (rq == 0 && c < K) my_part[c] = v;
+      }
+    }
+  } else if (warp == WIDE_CONSUMER_WARPS) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_first();
+      int sl = 0;
+      uint32_t round = 0;
+      for (long long n = 0; n < n_my; ++n) {
+        const double* src = p.panels + (size_t)(blockIdx.x + n * grid) * Cpad * WR;
+        for (int j = 0; j < J; ++j) {
+          if (round > 0) mbar_wait(&empty_bar[sl], (round - 1) & 1);
+          const uint32_t bytes = (uint32_t)min(KC, Cpad - j * KC) * WR * 8u;
+          mbar_arrive_expect_tx(&full_bar[sl], bytes);
+          tma_load_1d(ring + (size_t)sl * SLOT, src + (size_t)j * KC * WR, bytes, &full_bar[sl], pol);
+          if (++sl == T) {
+            sl = 0;
+            ++round;
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== link warp ===============================
+    const int r = lane & (WR - 1);
+    const int jy = K / KC, coly = K - jy * KC;            // y lives in column K
+    const int jg = (K + 1) / KC, colg = K + 1 - jg * KC;  // group id in column K+1 (G > 0)
+    int slot_y = jy, slot_g = jg;
+    uint32_t par_y = 0, par_g = 0;
+    const double alpha = G > 0 ? 0.0 : theta_at(0);
+    double inv_sigma = 1.0;
+    if (FAMILY == FAM_NORMAL_ID) inv_sigma = 1.0 / exp(theta_at(P - 1));  // normal_id_glm_lpdf.hpp:117
+    double lp_acc = 0.0, r_acc = 0.0;
+    for (long long n = 0; n < n_my; ++n) {
+      const long long pi = blockIdx.x + n * grid;
+      mbar_wait(&full_bar[slot_y], par_y);
+      const double y = ring[(size_t)slot_y * SLOT + coly * WR + r];
+      double off = alpha;
+      if (G > 0) {
+        mbar_wait(&full_bar[slot_g], par_g);
+        const int gi = (int)ring[(size_t)slot_g * SLOT + colg * WR + r] - 1;
+        const bool gok = gi >= 0 && gi < G;
+        off = p.stage_a_in_smem ? sa[gok ? gi : 0] : theta_at(2 + (gok ? gi : 0));
+      }
+      named_bar_sync(WIDE_BAR_ETA, WIDE_BAR_COUNT);
+      double eta = 0.0;
+#pragma unroll
+      for (int w = 0; w < WIDE_CONSUMER_WARPS; ++w) eta += eta_part[w * WR + r];
+      eta += off;
+      double lp_i, r_i;
+      link<FAMILY>(eta, y, inv_sigma, lp_i, r_i);
+      if (pi * WR + r >= p.n_rows) {
+        lp_i = 0.0;
+        r_i = 0.0;
+      }
+      if (lane < WR) {
+        r_sh[lane] = r_i;
+        if (G > 0) p.r_out[pi * WR + lane] = r_i;
+        lp_acc += lp_i;
+        r_acc += r_i;
+      }
+      __threadfence_block();
+      named_bar_arrive(WIDE_BAR_R, WIDE_BAR_COUNT);
+      slot_y += J;
+      if (slot_y >= T) {
+        slot_y -= T;
+        par_y ^= 1u;
+      }
+      slot_g += J;
+      if (slot_g >= T) {
+        slot_g -= T;
+        par_g ^= 1u;
+      }
+    }
+    lp_acc = warp_sum(lp_acc);
+    r_acc = warp_sum(r_acc);
+    if (lane == 0) {
+      my_part[K] = lp_acc;
+      my_part[K + 1] = r_acc;
+    }
+  }
+
+  cross_cta_reduce_and_finish<FAMILY>(p, sh_scratch, &sh_is_last);
+}
+
+}  // namespace b200glm

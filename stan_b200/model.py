@@ -39,7 +39,7 @@ DEFAULT_PRIORS = dict(prior_alpha_sd=2.5, prior_beta_sd=2.5, prior_sigma_loc=1.0
 
 class GLMModel:
     def __init__(self, family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=1, N_total=0,
-                 grid_ctas=0, data_on_device=False, N=None, K=None, ldx=None, **priors):
+                 grid_ctas=0, flags=0, data_on_device=False, N=None, K=None, ldx=None, **priors):
         """X, y, group: numpy arrays (host), or -- with data_on_device=True -- integer device
         pointers (e.g. torch tensor .data_ptr()) with N, K, ldx given explicitly."""
         self.L = _capi.lib()
@@ -83,7 +83,7 @@ class GLMModel:
         for k, v in pri.items():
             setattr(d, k, float(v))
         d.device, d.n_slots, d.rank, d.world = int(device), int(n_slots), int(rank), int(world)
-        d.N_total, d.grid_ctas = int(N_total), int(grid_ctas)
+        d.N_total, d.grid_ctas, d.flags = int(N_total), int(grid_ctas), int(flags)
         self.N, self.K, self.G = int(d.N), int(d.K), int(G)
         self.rank, self.world = int(rank), int(world)
         h = C.c_void_p()

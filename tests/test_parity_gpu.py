@@ -84,6 +84,93 @@ def test_cuda_matches_oracle_live(fam, N, K, G):
     m.close()
 
 
+WIDE_SHAPES = [
+    # family, N, K, G, flags -- the wide-matrix kernel (16-row panels split over the CTA): K > 256 selects it,
+    # flags=1 (B200GLM_FLAG_FORCE_WIDE) runs it on narrow shapes too (sub-panel/warp-ownership edge cases)
+    ("bernoulli_logit", 3_000, 300, 0, 0),       # KC=32, J=10
+    ("bernoulli_logit", 20_011, 1000, 0, 0),     # config 5's K: KC=64, J=16
+    ("normal_id", 5_000, 511, 0, 0),             # Cpad = 512: last KC=32 shape, y in the last column
+    ("normal_id", 5_000, 512, 0, 0),             # first KC=64 shape
+    ("poisson_log", 8_000, 520, 100, 0),         # groups; y and group id in the last sub-panel
+    ("poisson_log", 4_000, 639, 50, 0),          # K+1 = 640: y and group id land in DIFFERENT sub-panels
+    ("bernoulli_logit", 2_500, 1400, 0, 0),      # SPW = 3
+    ("bernoulli_logit", 10_000, 20, 0, 1),
+    ("bernoulli_logit", 4_097, 13, 7, 1),
+    ("poisson_log", 5_000, 8, 3000, 1),          # a[] read from global memory
+    ("normal_id", 9_999, 100, 17, 1),
+    ("normal_id", 15, 3, 0, 1),                  # a single partial panel
+    ("bernoulli_logit", 16 * 148 * 3 + 5, 70, 0, 1),
+]
+
+
+@pytest.mark.parametrize("fam,N,K,G,flags", WIDE_SHAPES)
+def test_wide_kernel_matches_oracle_live(fam, N, K, G, flags):
+    d = make_glm_data(fam, N, K, G)
+    orc = oracle_for(fam, d, G)
+    m = GLMModel(fam, d["X"], d["y"], d["group"], G, flags=flags)
+    assert m.num_params_r() == orc.P
+    sc = 0.1 if K <= 300 else 0.03
+    for th in theta_points(m.P, n_random=2, scale=sc):
+        lp, g = m.log_prob_grad(th)
+        lp_r, g_r = orc.log_prob_grad(th)
+        assert rel_err(lp, lp_r) < TOL, (lp, lp_r)
+        assert rel_err_vec(g, g_r) < TOL
+        assert rel_err(m.log_prob(th, False, True), orc.log_prob(th, False, True)) < TOL
+    a = m.log_prob_grad(th)
+    b = m.log_prob_grad(th)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])      # deterministic
+    m.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_wide_kernel_matches_reference_golden(golden, name):
+    c = golden[name]
+    m = GLMModel(c["family"], c["X"], c["y"], c["group"], c["G"], flags=1)
+    for e in c["evals"]:
+        th = unhex(e["theta"])
+        for key, ref in e["lp_grad"].items():
+            lp, g = m.log_prob_grad(th, int(key[0]), int(key[1]))
+            assert rel_err(lp, float.fromhex(ref["lp"])) < TOL, (name, key)
+            assert rel_err_vec(g, unhex(ref["grad"])) < TOL, (name, key)
+    lf = c["leapfrog"]
+    m.set_state(unhex(lf["q0"]), unhex(lf["p0"]), unhex(lf["g0"]), float.fromhex(lf["V0"]))
+    q, p, g, V = m.leapfrog(lf["eps"], unhex(lf["inv_metric"]))
+    assert rel_err_vec(q, unhex(lf["q1"])) < TOL and rel_err_vec(p, unhex(lf["p1"])) < TOL
+    assert rel_err_vec(g, unhex(lf["g1"])) < TOL and rel_err(V, float.fromhex(lf["V1"])) < TOL
+    m.close()
+
+
+def test_wide_kernel_hbm_scale_additivity():
+    """K = 1000 (config 5's width) at a size well beyond L2: the likelihood part of 8 row shards sums
+    to the whole (size-independent 'checksum of checksums'), and one shard is checked against the oracle."""
+    import torch
+    from oracle.oracle import PortOracle
+    from stan_b200.synth import make_logistic_shard
+    N, K, S = 800_000, 1000, 8
+    dev = torch.device("cuda", 0)
+    X, y, _, _ = make_logistic_shard(torch, dev, N, K, block=100_000)
+    m = GLMModel("bernoulli_logit", X.data_ptr(), y.data_ptr(), data_on_device=True, N=N, K=K, ldx=N)
+    th = 0.02 * np.random.default_rng(11).standard_normal(K + 1)
+    lp, g = m.log_prob_grad(th)
+    prior = PortOracle("bernoulli_logit", np.zeros((0, K)), np.zeros(0, np.int32))
+    lp0, g0 = prior.log_prob_grad(th)
+    lp_sum, g_sum = lp0, g0.copy()
+    n = N // S
+    for s in range(S):
+        ms = GLMModel("bernoulli_logit", X.data_ptr() + 8 * s * n, y.data_ptr() + 4 * s * n, data_on_device=True,
+                      N=n, K=K, ldx=N)
+        lps, gs = ms.log_prob_grad(th)
+        if s == 3:
+            po = PortOracle("bernoulli_logit", X[:, s * n:(s + 1) * n].cpu().numpy().T, y[s * n:(s + 1) * n].cpu().numpy())
+            lp_r, g_r = po.log_prob_grad(th)
+            assert rel_err(lps, lp_r) < TOL and rel_err_vec(gs, g_r) < TOL
+        lp_sum += lps - lp0
+        g_sum += gs - g0
+        ms.close()
+    assert rel_err(lp, lp_sum) < 1e-12 and rel_err_vec(g, g_sum) < 1e-12
+    m.close()
+
+
 def test_deterministic_bitwise():
     d = make_glm_data("bernoulli_logit", 200_000, 100)
     m = GLMModel("bernoulli_logit", d["X"], d["y"])
