@@ -202,7 +202,7 @@ def run_b200(args):
     achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
-                "kernel": "glm_fused_kernel<bernoulli_logit,13>", "algorithmic_bytes_per_launch": bytes_per_launch,
+                "kernel": "glm_wide_kernel<bernoulli_logit>" if K > 256 else "glm_fused_kernel<bernoulli_logit>", "algorithmic_bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": ms_per_step}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
@@ -239,13 +239,104 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_b200_batched(args):
+    """BASELINE configs[2]: normal_id_glm N=1M K=200, 1024 batched chains on one B200.  A step = one
+    batched leapfrog (every chain advances once = `chains` gradient evaluations): fp64 DMMA GEMM pair."""
+    import torch
+    from stan_b200 import GLMModel
+    rank, local_rank, world = dist_env()
+    if world != 1:
+        raise SystemExit("--config 3 is a single-GPU configuration")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    N, K, C = args.rows, args.cols, args.chains
+    g = torch.Generator(device=dev).manual_seed(20261017)
+    X = torch.randn((K, N), generator=g, device=dev, dtype=torch.float64)
+    beta = torch.randn(K, generator=g, device=dev, dtype=torch.float64) / K ** 0.5
+    y = 0.3 + beta @ X + torch.randn(N, generator=g, device=dev, dtype=torch.float64)
+    m = GLMModel("normal_id", X.data_ptr(), y.data_ptr(), data_on_device=True, N=N, K=K, ldx=N, device=local_rank)
+    sample = None
+    if not args.no_cpu_baseline:
+        ns = min(args.cpu_sample_rows, N)
+        sample = (X[:, :ns].cpu().numpy().T, y[:ns].cpu().numpy())
+    del X, y
+    torch.cuda.empty_cache()
+    m.batch_reserve(C)
+    P = m.num_params_r()
+    rng = np.random.default_rng(11)
+    q0 = 0.05 * rng.standard_normal((C, P))
+    p0 = rng.standard_normal((C, P))
+    lp0, g0, st = m.log_prob_grad_batched(q0)
+    assert not st.any()
+    m.set_state_batched(q0, p0, -g0, -lp0)
+    eps = 1e-5
+    stream = torch.cuda.ExternalStream(m.batch_stream_ptr(), device=dev)
+    for _ in range(args.warmup):
+        m.leapfrog_batched_async(C, eps)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    time.sleep(0.3)
+    launches0 = m.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        m.leapfrog_batched_async(C, eps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    ms_per_step = e0.elapsed_time(e1) / args.steps
+    launches = m.launch_count() - launches0
+    clk = clocks.stop(t_wall0, t_wall1)
+    value = C * 1000.0 / ms_per_step
+    # e2e: host thetas in, host lp/grad out, every step
+    th = q0.copy()
+    for _ in range(3):
+        m.log_prob_grad_batched(th)
+    torch.cuda.synchronize()
+    ne = max(3, args.steps // 4)
+    t0 = time.perf_counter()
+    for i in range(ne):
+        th[0, 0] = q0[0, 0] + 1e-6 * i
+        m.log_prob_grad_batched(th)
+    e2e_value = C * ne / (time.perf_counter() - t0)
+    flops = 4.0 * N * K * C
+    peak = 37.18   # TFLOP/s: register-resident DMMA.8x8x4 loop measured on this pool's B200 (profiles/r1_fp64_peak_microbench.txt)
+    achieved = flops / (ms_per_step * 1e-3) / 1e12
+    cpu_baseline = None
+    if sample is not None:
+        cpu_baseline = cpu_baseline_leg(sample[0], sample[1], N, threads=1, evals=args.cpu_evals, family="normal_id")
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"normal_id_glm N={N} K={K} fp64, {C} batched chains (BASELINE configs[2])",
+                   "rows_total": N, "cols": K, "chains": C,
+                   "l2": f"X {8e-9 * N * K:.2f} GB >> 126 MB L2, no flush needed",
+                   "step": "one batched leapfrog: begin + fused DMMA GEMM pair + finish (device-resident state)"},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * P * C, "d2h_bytes_per_step": 8 * (P + 2) * C,
+                "call": "b200glm_log_prob_grad_batched(host thetas) -> host lp, grad"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": "measured fp64 DMMA microbenchmark (tools/fp64_peak.cu); cuBLAS DGEMM 35.4",
+                     "kernel": "glm_batched_kernel<normal_id,13>", "algorithmic_flops_per_launch": flops,
+                     "avg_launch_ms": ms_per_step},
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(out))
+    m.close()
+
+
 # ------------------------------------------------------------------------------------------
 # CPU legs (the only place bench.py executes anything under oracle/)
 # ------------------------------------------------------------------------------------------
-def cpu_baseline_leg(Xs, ys, N_total, threads=1, evals=5, check=None):
+def cpu_baseline_leg(Xs, ys, N_total, threads=1, evals=5, check=None, family=FAMILY):
     from oracle.oracle import PortOracle, RefOracle
     cls = RefOracle if RefOracle.available() else PortOracle
-    orc = cls(FAMILY, Xs, ys)
+    orc = cls(family, Xs, ys)
     ns, K = Xs.shape
     th = 0.05 * np.random.default_rng(11).standard_normal(orc.P)
     orc.log_prob_grad(th)     # warm
@@ -327,12 +418,24 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=N_ROWS)
-    ap.add_argument("--cols", type=int, default=K_COLS)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
+                    help="BASELINE configs index (1-based): 2 = single chain N=10M K=100 (default, the metric's config), "
+                         "3 = normal_id N=1M K=200 with 1024 batched chains")
+    ap.add_argument("--chains", type=int, default=1024)
+    ap.add_argument("--rows", type=int, default=None)
+    ap.add_argument("--cols", type=int, default=None)
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--cpu-evals", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.rows is None:
+        args.rows = N_ROWS if args.config == 2 else 1_000_000
+    if args.cols is None:
+        args.cols = K_COLS if args.config == 2 else 200
+    if args.config == 3 and args.impl == "b200":
+        args.steps = args.steps if args.steps is not None else 20
+        args.warmup = max(3, args.warmup if args.warmup is not None else 3)
+        return run_b200_batched(args)
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 3
         args.warmup = args.warmup if args.warmup is not None else 1

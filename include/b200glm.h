@@ -108,6 +108,31 @@ void* b200glm_stream(b200glm_handle* h, int32_t slot);
 /* device pointer to the slot's result block [lp, grad[P], status] (doubles) */
 const double* b200glm_result_device(b200glm_handle* h, int32_t slot);
 
+/* Batched chains: n chains evaluated in ONE pass over X; the per-chain GEMV pair becomes a pair of
+ * fp64 GEMMs on the DMMA tensor path (BASELINE configs[2]).  This is the device side of a multi-chain
+ * driver in ST/services/sample (hmc_nuts_diag_e_adapt.hpp:364-401 runs chains as independent TBB
+ * tasks, each calling stan::model::gradient on its own; here the calls of all chains that are waiting
+ * for a leapfrog step are served together).  Requires K <= 208, G == 0, world == 1.
+ * All per-chain arrays are chain-major HOST arrays: theta[i*P + k] belongs to lane i.
+ *   batch_reserve            allocate state for chain slots [0, max_chains) (inverse metric = 1)
+ *   log_prob_grad_batched    == n calls of b200glm_log_prob_grad; status[i] (may be NULL) gets the
+ *                            per-chain code (OK / DOMAIN); with status == NULL any DOMAIN is returned
+ *   set_state_batched        upload z = (q, p, g, V) [and the diagonal inverse metric] of n chain slots
+ *   leapfrog_batched         lane i advances chain slot chains[i] (NULL: slot i) by eps[i]; mirrors the
+ *                            new (q, p, g, V) to the host (any of q, p, g, V, status may be NULL).
+ *                            Domain error in a lane: V = +inf, g negated, status[i] = DOMAIN.
+ *   leapfrog_batched_async   slots [0, n) by the same eps, device-resident (bench `value`) */
+int b200glm_batch_reserve(b200glm_handle* h, int32_t max_chains);
+int b200glm_log_prob_grad_batched(b200glm_handle* h, int32_t n, const double* theta, int32_t propto,
+                                  int32_t jacobian, double* lp, double* grad, int32_t* status);
+int b200glm_set_state_batched(b200glm_handle* h, int32_t n, const int32_t* chains, const double* q,
+                              const double* p, const double* g, const double* V, const double* inv_metric);
+int b200glm_leapfrog_batched(b200glm_handle* h, int32_t n, const int32_t* chains, const double* eps,
+                             double* q, double* p, double* g, double* V, int32_t* status);
+int b200glm_leapfrog_batched_async(b200glm_handle* h, int32_t n, double eps);
+int b200glm_batch_sync(b200glm_handle* h);
+void* b200glm_batch_stream(b200glm_handle* h);
+
 /* Row-sharded operation: one process per GPU, likelihood partials combined by one NCCL
  * all-reduce of P+2 doubles per gradient (replaces nothing in the reference's GLM path; the
  * analogue is map_rect's gatherv, SM/prim/functor/mpi_parallel_call.hpp:354-392).

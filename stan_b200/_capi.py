@@ -13,6 +13,8 @@ SYMBOLS = [
     "b200glm_create", "b200glm_destroy", "b200glm_num_params", "b200glm_log_prob_grad", "b200glm_log_prob",
     "b200glm_set_state", "b200glm_leapfrog", "b200glm_leapfrog_async", "b200glm_grad_async", "b200glm_sync",
     "b200glm_stream", "b200glm_result_device", "b200glm_comm_unique_id", "b200glm_comm_init",
+    "b200glm_batch_reserve", "b200glm_log_prob_grad_batched", "b200glm_set_state_batched",
+    "b200glm_leapfrog_batched", "b200glm_leapfrog_batched_async", "b200glm_batch_sync", "b200glm_batch_stream",
     "b200glm_launch_count", "b200glm_bytes_per_gradient", "b200glm_last_error", "b200glm_version",
 ]
 
@@ -60,6 +62,15 @@ def lib():
         L.b200glm_result_device.restype = C.c_void_p
         L.b200glm_comm_unique_id.argtypes = [C.c_void_p]
         L.b200glm_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+        ip = C.POINTER(C.c_int32)
+        L.b200glm_batch_reserve.argtypes = [C.c_void_p, C.c_int32]
+        L.b200glm_log_prob_grad_batched.argtypes = [C.c_void_p, C.c_int32, dp, C.c_int32, C.c_int32, dp, dp, ip]
+        L.b200glm_set_state_batched.argtypes = [C.c_void_p, C.c_int32, ip, dp, dp, dp, dp, dp]
+        L.b200glm_leapfrog_batched.argtypes = [C.c_void_p, C.c_int32, ip, dp, dp, dp, dp, dp, ip]
+        L.b200glm_leapfrog_batched_async.argtypes = [C.c_void_p, C.c_int32, C.c_double]
+        L.b200glm_batch_sync.argtypes = [C.c_void_p]
+        L.b200glm_batch_stream.argtypes = [C.c_void_p]
+        L.b200glm_batch_stream.restype = C.c_void_p
         L.b200glm_launch_count.argtypes = [C.c_void_p]
         L.b200glm_launch_count.restype = C.c_int64
         L.b200glm_bytes_per_gradient.argtypes = [C.c_void_p]

@@ -19,6 +19,7 @@
 
 #include "glm_kernels.cuh"
 #include "glm_wide_kernel.cuh"
+#include "glm_batched_kernel.cuh"
 
 using namespace b200glm;
 
@@ -76,6 +77,21 @@ struct Slot {
   std::mutex mu;
 };
 
+// Workspace of the batched (many-chain) path: chain state is feature-major [P][ld] on the device.
+struct Batch {
+  int max_chains = 0, ld = 0;   // ld = max_chains rounded up to 64 (state and lane leading dimension)
+  int S = 0, mbh = 0, sms = 0;
+  size_t smem = 0;
+  cudaStream_t stream = nullptr;
+  double *Q = nullptr, *Pm = nullptr, *Gd = nullptr, *V = nullptr, *IM = nullptr;
+  double *theta_c = nullptr, *p_half = nullptr, *partials = nullptr, *result = nullptr, *state_out = nullptr;
+  double *theta_in = nullptr, *eps_d = nullptr;
+  int32_t* chains_d = nullptr;
+  double* h_pin = nullptr;      // pinned staging, max_chains * (3P + 1) doubles (+ ints)
+  int32_t* h_pin_i = nullptr;
+  std::mutex mu;
+};
+
 }  // namespace
 
 struct b200glm_handle {
@@ -94,6 +110,7 @@ struct b200glm_handle {
   double lgamma_sum_total = 0.0;
   bool bad_y = false;
   std::vector<Slot*> slots;
+  Batch* batch = nullptr;
   ncclComm_t comm = nullptr;
   std::atomic<long long> launches{0};
   std::mutex err_mu;
@@ -356,6 +373,17 @@ void b200glm_destroy(b200glm_handle* h) {
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
+  }
+  if (Batch* b = h->batch) {
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (double* q : {b->Q, b->Pm, b->Gd, b->V, b->IM, b->theta_c, b->p_half, b->partials, b->result, b->state_out,
+                      b->theta_in, b->eps_d})
+      cudaFree(q);
+    cudaFree(b->chains_d);
+    if (b->h_pin) cudaFreeHost(b->h_pin);
+    if (b->h_pin_i) cudaFreeHost(b->h_pin_i);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
   }
   if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
   cudaFree(h->panels);
@@ -695,6 +723,314 @@ const double* b200glm_result_device(b200glm_handle* h, int32_t slot) {
   if (validate_slot(h, slot)) return nullptr;
   return h->slots[slot]->result;
 }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Batched chains (fp64 DMMA path)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+typedef void (*batched_fn)(const BatchedParams);
+template <int FAMILY>
+batched_fn pick_batched_mbh(int mbh) {
+  switch (mbh) {
+    case 2: return glm_batched_kernel<FAMILY, 2>;
+    case 4: return glm_batched_kernel<FAMILY, 4>;
+    case 7: return glm_batched_kernel<FAMILY, 7>;
+    case 13: return glm_batched_kernel<FAMILY, 13>;
+  }
+  return nullptr;
+}
+batched_fn pick_batched(int family, int mbh) {
+  switch (family) {
+    case FAM_BERNOULLI_LOGIT: return pick_batched_mbh<FAM_BERNOULLI_LOGIT>(mbh);
+    case FAM_POISSON_LOG: return pick_batched_mbh<FAM_POISSON_LOG>(mbh);
+    case FAM_NORMAL_ID: return pick_batched_mbh<FAM_NORMAL_ID>(mbh);
+  }
+  return nullptr;
+}
+
+int batch_check(b200glm_handle* h, int n) {
+  if (!h) return B200GLM_INVALID;
+  if (!h->batch) {
+    h->set_error("b200glm_batch_reserve was not called");
+    return B200GLM_INVALID;
+  }
+  if (n < 1 || n > h->batch->max_chains) {
+    h->set_error("number of chains outside [1, max_chains]");
+    return B200GLM_INVALID;
+  }
+  return B200GLM_OK;
+}
+
+// begin -> main -> finish for n lanes on the batch stream.  chains_d / eps_d may be NULL.
+int enqueue_batched(b200glm_handle* h, int n, int mode, int propto, int jacobian, const int32_t* chains_d,
+                    const double* eps_d, double eps_scalar, bool mirror_state) {
+  Batch* b = h->batch;
+  const int NCB = (n + BATCH_CB - 1) / BATCH_CB;
+  int NS = std::max(1, b->sms / NCB);
+  if ((long long)NS > std::max<long long>(h->n_panels, 1)) NS = (int)std::max<long long>(h->n_panels, 1);
+  BatchedStepParams sp;
+  std::memset(&sp, 0, sizeof(sp));
+  sp.n = n;
+  sp.P = h->P;
+  sp.K = h->d.K;
+  sp.off_beta = h->off_beta;
+  sp.family = h->d.family;
+  sp.ldc = NCB * BATCH_CB;
+  sp.ld_state = b->ld;
+  sp.NCB = NCB;
+  sp.NS = NS;
+  sp.mode = mode;
+  sp.chains = chains_d;
+  sp.eps = eps_d;
+  sp.eps_scalar = eps_scalar;
+  sp.theta_in = b->theta_in;
+  sp.Q = b->Q;
+  sp.Pm = b->Pm;
+  sp.Gd = b->Gd;
+  sp.V = b->V;
+  sp.IM = b->IM;
+  sp.theta_c = b->theta_c;
+  sp.p_half = b->p_half;
+  sp.partials = b->partials;
+  sp.result = b->result;
+  sp.state_out = mirror_state ? b->state_out : nullptr;
+  KernelParams kp;
+  fill_params(h, h->slots[0], kp, mode, propto, jacobian, 1, 0.0);
+  sp.mc = kp.mc;
+  const long long tot = (long long)h->P * sp.ldc;
+  batched_begin_kernel<<<(int)std::min<long long>((tot + 255) / 256, 4 * b->sms), 256, 0, b->stream>>>(sp);
+  BatchedParams bp;
+  std::memset(&bp, 0, sizeof(bp));
+  bp.panels = h->panels;
+  bp.n_rows = h->d.N;
+  bp.n_panels = h->n_panels;
+  bp.K = h->d.K;
+  bp.C = h->C;
+  bp.P = h->P;
+  bp.off_beta = h->off_beta;
+  bp.family = h->d.family;
+  bp.n_stages = b->S;
+  bp.NCB = NCB;
+  bp.NS = NS;
+  bp.ldc = sp.ldc;
+  bp.theta_c = b->theta_c;
+  bp.partials = b->partials;
+  pick_batched(h->d.family, b->mbh)<<<NCB * NS, BATCH_THREADS, b->smem, b->stream>>>(bp);
+  batched_finish_kernel<<<(n + 31) / 32, 256, 0, b->stream>>>(sp);
+  h->launches += 3;
+  CUDA_TRY(h, cudaGetLastError());
+  return B200GLM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200glm_batch_reserve(b200glm_handle* h, int32_t max_chains) {
+  if (!h) return B200GLM_INVALID;
+  if (max_chains < 1) {
+    h->set_error("max_chains must be >= 1");
+    return B200GLM_INVALID;
+  }
+  if (h->batch) {
+    h->set_error("batch workspace already reserved");
+    return B200GLM_INVALID;
+  }
+  if (h->wide || h->d.G > 0 || h->d.world > 1 || h->d.K > BATCH_MAX_K) {
+    h->set_error("batched chains need K <= 208, a scalar intercept (G == 0) and an unsharded handle");
+    return B200GLM_INVALID;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  cudaDeviceProp prop;
+  CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->d.device));
+  Batch* b = new Batch();
+  b->max_chains = max_chains;
+  b->ld = ((max_chains + BATCH_CB - 1) / BATCH_CB) * BATCH_CB;
+  b->sms = h->d.grid_ctas > 0 ? h->d.grid_ctas : prop.multiProcessorCount;
+  const int MB0 = (((h->d.K + 7) >> 3) + 1) >> 1;
+  for (int c : {2, 4, 7, 13})
+    if (c >= MB0) {
+      b->mbh = c;
+      break;
+    }
+  const size_t max_dyn = (size_t)prop.sharedMemPerBlockOptin - 1024;
+  int S = 4;
+  while (S > 0 && batched_smem_bytes(h->d.K, h->C, S) > max_dyn) --S;
+  if (S < 1) {
+    delete b;
+    h->set_error("panel + beta block do not fit in shared memory");
+    return B200GLM_INVALID;
+  }
+  b->S = S;
+  b->smem = batched_smem_bytes(h->d.K, h->C, S);
+  CUDA_TRY(h, cudaFuncSetAttribute(pick_batched(h->d.family, b->mbh), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)b->smem));
+  const size_t P = h->P, ld = b->ld;
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  for (double** q : {&b->Q, &b->Pm, &b->Gd, &b->IM, &b->theta_c, &b->p_half}) {
+    CUDA_TRY(h, cudaMalloc(q, sizeof(double) * P * ld));
+    CUDA_TRY(h, cudaMemset(*q, 0, sizeof(double) * P * ld));
+  }
+  {
+    std::vector<double> ones(P * ld, 1.0);
+    CUDA_TRY(h, cudaMemcpy(b->IM, ones.data(), sizeof(double) * P * ld, cudaMemcpyHostToDevice));
+  }
+  CUDA_TRY(h, cudaMalloc(&b->V, sizeof(double) * ld));
+  CUDA_TRY(h, cudaMemset(b->V, 0, sizeof(double) * ld));
+  const size_t n_part = (size_t)(b->sms + ld / BATCH_CB) * (h->d.K + 2) * BATCH_CB;
+  CUDA_TRY(h, cudaMalloc(&b->partials, sizeof(double) * n_part));
+  CUDA_TRY(h, cudaMalloc(&b->result, sizeof(double) * ld * (P + 2)));
+  CUDA_TRY(h, cudaMalloc(&b->state_out, sizeof(double) * ld * (3 * P + 1)));
+  CUDA_TRY(h, cudaMalloc(&b->theta_in, sizeof(double) * ld * (4 * P + 1)));   // also set_state staging
+  CUDA_TRY(h, cudaMalloc(&b->eps_d, sizeof(double) * ld));
+  CUDA_TRY(h, cudaMalloc(&b->chains_d, sizeof(int32_t) * ld));
+  CUDA_TRY(h, cudaMallocHost(&b->h_pin, sizeof(double) * ld * (4 * P + 2)));
+  CUDA_TRY(h, cudaMallocHost(&b->h_pin_i, sizeof(int32_t) * ld));
+  h->batch = b;
+  return B200GLM_OK;
+}
+
+int b200glm_log_prob_grad_batched(b200glm_handle* h, int32_t n, const double* theta, int32_t propto,
+                                  int32_t jacobian, double* lp, double* grad, int32_t* status) {
+  int rc = batch_check(h, n);
+  if (rc) return rc;
+  if (!theta || !lp) {
+    h->set_error("null pointer argument");
+    return B200GLM_INVALID;
+  }
+  Batch* b = h->batch;
+  std::lock_guard<std::mutex> lk(b->mu);
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  const size_t P = h->P;
+  std::memcpy(b->h_pin, theta, sizeof(double) * n * P);
+  CUDA_TRY(h, cudaMemcpyAsync(b->theta_in, b->h_pin, sizeof(double) * n * P, cudaMemcpyHostToDevice, b->stream));
+  rc = enqueue_batched(h, n, MODE_THETA, propto ? 1 : 0, jacobian ? 1 : 0, nullptr, nullptr, 0.0, false);
+  if (rc) return rc;
+  double* hres = b->h_pin;
+  CUDA_TRY(h, cudaMemcpyAsync(hres, b->result, sizeof(double) * n * (P + 2), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(b->stream));
+  int worst = B200GLM_OK;
+  for (int i = 0; i < n; ++i) {
+    const double* r = hres + (size_t)i * (P + 2);
+    const int st = (h->bad_y || r[P + 1] != 0.0) ? B200GLM_DOMAIN : B200GLM_OK;
+    if (status) status[i] = st;
+    if (st) worst = st;
+    lp[i] = r[0];
+    if (grad) std::memcpy(grad + (size_t)i * P, r + 1, sizeof(double) * P);
+  }
+  if (worst && !status) {
+    h->set_error("non-finite log density or gradient in at least one chain");
+    return worst;
+  }
+  return B200GLM_OK;
+}
+
+int b200glm_set_state_batched(b200glm_handle* h, int32_t n, const int32_t* chains, const double* q,
+                              const double* p, const double* g, const double* V, const double* inv_metric) {
+  int rc = batch_check(h, n);
+  if (rc) return rc;
+  if (!q || !p || !g || !V) {
+    h->set_error("null pointer argument");
+    return B200GLM_INVALID;
+  }
+  Batch* b = h->batch;
+  std::lock_guard<std::mutex> lk(b->mu);
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  const size_t P = h->P;
+  for (int i = 0; i < n; ++i) {
+    const int c = chains ? chains[i] : i;
+    if (c < 0 || c >= b->max_chains) {
+      h->set_error("chain slot out of range");
+      return B200GLM_INVALID;
+    }
+  }
+  // host-side transpose into the feature-major state (set_state is off the hot path): one strided
+  // 2-D copy per array
+  auto put = [&](double* dst, const double* src) -> cudaError_t {
+    double* st = b->h_pin;
+    for (int i = 0; i < n; ++i) std::memcpy(st + (size_t)i * P, src + (size_t)i * P, sizeof(double) * P);
+    for (int i = 0; i < n; ++i) {
+      const int c = chains ? chains[i] : i;
+      cudaError_t e = cudaMemcpy2DAsync(dst + c, sizeof(double) * b->ld, st + (size_t)i * P, sizeof(double),
+                                        sizeof(double), P, cudaMemcpyHostToDevice, b->stream);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaStreamSynchronize(b->stream);
+  };
+  CUDA_TRY(h, put(b->Q, q));
+  CUDA_TRY(h, put(b->Pm, p));
+  CUDA_TRY(h, put(b->Gd, g));
+  if (inv_metric) CUDA_TRY(h, put(b->IM, inv_metric));
+  for (int i = 0; i < n; ++i) {
+    const int c = chains ? chains[i] : i;
+    CUDA_TRY(h, cudaMemcpyAsync(b->V + c, V + i, sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(b->stream));
+  return B200GLM_OK;
+}
+
+int b200glm_leapfrog_batched(b200glm_handle* h, int32_t n, const int32_t* chains, const double* eps, double* q,
+                             double* p, double* g, double* V, int32_t* status) {
+  int rc = batch_check(h, n);
+  if (rc) return rc;
+  if (!eps) {
+    h->set_error("null pointer argument");
+    return B200GLM_INVALID;
+  }
+  Batch* b = h->batch;
+  std::lock_guard<std::mutex> lk(b->mu);
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  const size_t P = h->P;
+  for (int i = 0; i < n; ++i) {
+    const int c = chains ? chains[i] : i;
+    if (c < 0 || c >= b->max_chains) {
+      h->set_error("chain slot out of range");
+      return B200GLM_INVALID;
+    }
+    b->h_pin_i[i] = c;
+    b->h_pin[i] = eps[i];
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(b->chains_d, b->h_pin_i, sizeof(int32_t) * n, cudaMemcpyHostToDevice, b->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(b->eps_d, b->h_pin, sizeof(double) * n, cudaMemcpyHostToDevice, b->stream));
+  rc = enqueue_batched(h, n, MODE_LEAPFROG, 1, 1, b->chains_d, b->eps_d, 0.0, true);
+  if (rc) return rc;
+  double* hs = b->h_pin;
+  const size_t W = 3 * P + 1;
+  CUDA_TRY(h, cudaMemcpyAsync(hs, b->state_out, sizeof(double) * n * W, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(b->stream));
+  for (int i = 0; i < n; ++i) {
+    const double* r = hs + (size_t)i * W;
+    if (q) std::memcpy(q + (size_t)i * P, r, sizeof(double) * P);
+    if (p) std::memcpy(p + (size_t)i * P, r + P, sizeof(double) * P);
+    if (g) std::memcpy(g + (size_t)i * P, r + 2 * P, sizeof(double) * P);
+    if (V) V[i] = r[3 * P];
+    if (status) status[i] = (h->bad_y || std::isinf(r[3 * P])) ? B200GLM_DOMAIN : B200GLM_OK;
+  }
+  return B200GLM_OK;
+}
+
+int b200glm_leapfrog_batched_async(b200glm_handle* h, int32_t n, double eps) {
+  int rc = batch_check(h, n);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  return enqueue_batched(h, n, MODE_LEAPFROG, 1, 1, nullptr, nullptr, eps, false);
+}
+
+int b200glm_batch_sync(b200glm_handle* h) {
+  int rc = batch_check(h, 1);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->batch->stream));
+  return B200GLM_OK;
+}
+
+void* b200glm_batch_stream(b200glm_handle* h) { return (h && h->batch) ? (void*)h->batch->stream : nullptr; }
+
+}  // extern "C"
+
+extern "C" {
 
 int b200glm_comm_unique_id(void* unique_id_128) {
   if (!unique_id_128 || !nccl().ok) return B200GLM_CUDA;

@@ -176,6 +176,59 @@ class GLMModel:
     def bytes_per_gradient(self):
         return self.L.b200glm_bytes_per_gradient(self.h)
 
+    # ------------------------------------------------------------------ batched chains (fp64 DMMA path)
+    def batch_reserve(self, max_chains):
+        self._check(self.L.b200glm_batch_reserve(self.h, int(max_chains)))
+        self.max_chains = int(max_chains)
+
+    def _mat(self, a, n):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.shape != (n, self.P):
+            raise InvalidArgument(f"expected a ({n}, {self.P}) chain-major array, got {a.shape}")
+        return a
+
+    @staticmethod
+    def _ip(a):
+        return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+    def log_prob_grad_batched(self, thetas, propto=True, jacobian=True):
+        """n chains in one pass over X: returns lp (n,), grad (n, P), status (n,) int32."""
+        th = np.ascontiguousarray(thetas, dtype=np.float64)
+        n = th.shape[0]
+        th = self._mat(th, n)
+        lp, g, st = np.empty(n), np.empty((n, self.P)), np.empty(n, dtype=np.int32)
+        self._check(self.L.b200glm_log_prob_grad_batched(self.h, n, _dp(th), int(propto), int(jacobian),
+                                                         _dp(lp), _dp(g), self._ip(st)))
+        return lp, g, st
+
+    def set_state_batched(self, q, p, g, V, inv_metric=None, chains=None):
+        n = np.asarray(q).shape[0]
+        q, p, g = self._mat(q, n), self._mat(p, n), self._mat(g, n)
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        im = None if inv_metric is None else self._mat(inv_metric, n)
+        ch = None if chains is None else np.ascontiguousarray(chains, dtype=np.int32)
+        self._check(self.L.b200glm_set_state_batched(self.h, n, None if ch is None else self._ip(ch), _dp(q), _dp(p),
+                                                     _dp(g), _dp(V), None if im is None else _dp(im)))
+
+    def leapfrog_batched(self, eps, chains=None):
+        eps = np.ascontiguousarray(eps, dtype=np.float64)
+        n = eps.shape[0]
+        ch = None if chains is None else np.ascontiguousarray(chains, dtype=np.int32)
+        q, p, g = (np.empty((n, self.P)) for _ in range(3))
+        V, st = np.empty(n), np.empty(n, dtype=np.int32)
+        self._check(self.L.b200glm_leapfrog_batched(self.h, n, None if ch is None else self._ip(ch), _dp(eps),
+                                                    _dp(q), _dp(p), _dp(g), _dp(V), self._ip(st)))
+        return q, p, g, V, st
+
+    def leapfrog_batched_async(self, n, eps):
+        self._check(self.L.b200glm_leapfrog_batched_async(self.h, int(n), float(eps)))
+
+    def batch_sync(self):
+        self._check(self.L.b200glm_batch_sync(self.h))
+
+    def batch_stream_ptr(self):
+        return self.L.b200glm_batch_stream(self.h)
+
     # ------------------------------------------------------------------ multi-GPU
     @staticmethod
     def comm_unique_id():

@@ -1,0 +1,131 @@
+"""GPU suite for the batched-chains path (fp64 DMMA GEMM pair, BASELINE configs[2]): every lane of a
+batched call must equal the single-chain reference evaluation of that chain (1e-10 relative)."""
+import numpy as np
+import pytest
+
+from conftest import rel_err, rel_err_vec
+import stan_b200
+from stan_b200 import GLMModel, make_glm_data
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def oracle_for(fam, d):
+    from oracle.oracle import PortOracle, RefOracle
+    cls = RefOracle if RefOracle.available() else PortOracle
+    return cls(fam, d["X"], d["y"])
+
+
+SHAPES = [
+    # family, N, K, chains
+    ("normal_id", 20_000, 200, 70),         # config 3's K; two chain blocks, the second one ragged
+    ("normal_id", 3_001, 16, 5),
+    ("bernoulli_logit", 10_000, 20, 64),    # config 1's shape
+    ("bernoulli_logit", 5_000, 101, 33),    # K % 4 == 1: y column next to the last k4 step
+    ("poisson_log", 8_000, 50, 130),
+    ("bernoulli_logit", 4_097, 13, 3),
+    ("normal_id", 2_000, 208, 9),           # largest supported K
+    ("poisson_log", 1_000, 7, 200),
+    ("bernoulli_logit", 31, 3, 2),          # a single partial panel
+]
+
+
+@pytest.mark.parametrize("fam,N,K,nch", SHAPES)
+def test_batched_matches_oracle_per_chain(fam, N, K, nch):
+    d = make_glm_data(fam, N, K)
+    orc = oracle_for(fam, d)
+    m = GLMModel(fam, d["X"], d["y"])
+    m.batch_reserve(nch)
+    rng = np.random.default_rng(3)
+    th = 0.1 * rng.standard_normal((nch, m.P))
+    th[0] = 0.0
+    for propto, jac in ((1, 1), (0, 1), (1, 0)):
+        lp, g, st = m.log_prob_grad_batched(th, propto, jac)
+        assert not st.any()
+        for c in range(nch) if nch <= 8 else (0, 1, nch // 2, nch - 1):
+            lp_r, g_r = orc.log_prob_grad(th[c], propto, jac)
+            assert rel_err(lp[c], lp_r) < TOL, (c, lp[c], lp_r)
+            assert rel_err_vec(g[c], g_r) < TOL, c
+    # a batched lane == the single-chain kernel on the same handle, to rounding
+    lp1, g1 = m.log_prob_grad(th[1])
+    lp, g, st = m.log_prob_grad_batched(th)
+    assert rel_err(lp[1], lp1) < 1e-12 and rel_err_vec(g[1], g1) < 1e-12
+    # deterministic, and independent of which lane / how many lanes a chain is evaluated in
+    lp2, g2, _ = m.log_prob_grad_batched(th)
+    assert np.array_equal(lp, lp2) and np.array_equal(g, g2)
+    lp3, g3, _ = m.log_prob_grad_batched(th[::-1].copy())
+    assert np.array_equal(lp3[::-1], lp) and np.array_equal(g3[::-1], g)
+    m.close()
+
+
+def test_batched_leapfrog_matches_oracle():
+    """Lanes advance different chain slots with different step sizes and metrics; 6 steps, state resident."""
+    from oracle.oracle import PortOracle
+    fam, N, K, nch = "normal_id", 6_000, 24, 37
+    d = make_glm_data(fam, N, K)
+    po = PortOracle(fam, d["X"], d["y"])
+    m = GLMModel(fam, d["X"], d["y"])
+    m.batch_reserve(64)
+    rng = np.random.default_rng(9)
+    q = 0.05 * rng.standard_normal((nch, m.P))
+    p = rng.standard_normal((nch, m.P))
+    im = np.exp(0.3 * rng.standard_normal((nch, m.P)))
+    eps = 1e-3 * (1 + rng.random(nch)) * np.where(rng.random(nch) < 0.3, -1.0, 1.0)
+    chains = rng.permutation(64)[:nch].astype(np.int32)
+    lp, g, _ = m.log_prob_grad_batched(q)
+    g, V = -g, -lp
+    m.set_state_batched(q, p, g, V, im, chains)
+    ref = [(q[i], p[i], g[i], V[i]) for i in range(nch)]
+    for step in range(6):
+        qd, pd, gd, Vd, st = m.leapfrog_batched(eps, chains)
+        assert not st.any()
+        ref = [po.leapfrog(eps[i], im[i], *ref[i]) for i in range(nch)]
+    for i in range(nch):
+        assert rel_err_vec(qd[i], ref[i][0]) < 1e-9 and rel_err_vec(pd[i], ref[i][1]) < 1e-9
+        assert rel_err_vec(gd[i], ref[i][2]) < 1e-9 and rel_err(Vd[i], ref[i][3]) < 1e-9
+    # a subset of the slots, in another order: the others keep their state
+    sub = np.array([chains[5], chains[2]], dtype=np.int32)
+    q2, p2, g2, V2, _ = m.leapfrog_batched(np.array([eps[5], eps[2]]), sub)
+    r5, r2 = po.leapfrog(eps[5], im[5], *ref[5]), po.leapfrog(eps[2], im[2], *ref[2])
+    assert rel_err_vec(q2[0], r5[0]) < 1e-9 and rel_err_vec(q2[1], r2[0]) < 1e-9
+    m.close()
+
+
+def test_batched_domain_error_is_per_chain():
+    d = make_glm_data("poisson_log", 2_000, 4)
+    m = GLMModel("poisson_log", d["X"], d["y"])
+    m.batch_reserve(8)
+    th = np.zeros((3, m.P))
+    th[1, 0] = 800.0                      # exp overflow in chain 1 only
+    lp, g, st = m.log_prob_grad_batched(th)
+    assert list(st) == [0, 1, 0]
+    lp0, g0 = m.log_prob_grad(th[0])
+    assert rel_err(lp[0], lp0) < 1e-12 and rel_err(lp[2], lp0) < 1e-12
+    # leapfrog into a domain error: V = +inf, g negated, the other lanes unaffected
+    q = np.zeros((2, m.P))
+    p = np.zeros((2, m.P))
+    p[1, 0] = 1e6
+    gg = np.stack([-g0, -g0])
+    m.set_state_batched(q, p, gg, np.array([-lp0, -lp0]))
+    q1, p1, g1, V1, st = m.leapfrog_batched(np.array([1e-3, 1.0]))
+    assert list(st) == [0, 1] and V1[1] == np.inf and np.array_equal(g1[1], g0) and np.isfinite(V1[0])
+    m.close()
+
+
+def test_batched_argument_errors():
+    d = make_glm_data("bernoulli_logit", 500, 3)
+    m = GLMModel("bernoulli_logit", d["X"], d["y"])
+    with pytest.raises(stan_b200.InvalidArgument):      # reserve first
+        m.log_prob_grad_batched(np.zeros((2, m.P)))
+    m.batch_reserve(4)
+    with pytest.raises(stan_b200.InvalidArgument):      # more lanes than reserved
+        m.log_prob_grad_batched(np.zeros((5, m.P)))
+    with pytest.raises(stan_b200.InvalidArgument):      # chain slot out of range
+        m.leapfrog_batched(np.array([0.1]), np.array([4], dtype=np.int32))
+    m.close()
+    d = make_glm_data("bernoulli_logit", 500, 300)
+    m = GLMModel("bernoulli_logit", d["X"], d["y"])
+    with pytest.raises(stan_b200.InvalidArgument):      # K > 208
+        m.batch_reserve(4)
+    m.close()
