@@ -116,7 +116,9 @@ def run_b200(args):
     torch.cuda.synchronize()
     m = GLMModel(FAMILY, X.data_ptr(), y.data_ptr(), data_on_device=True, N=n_local, K=K, ldx=n_local,
                  device=local_rank, rank=rank, world=world, N_total=N_total)
-    if world > 1:
+    if world > 1 and args.collective == "peer":
+        m.connect_peers_torch(dist, dev)      # in-kernel exchange through peer mailboxes (NVLink), no NCCL call
+    elif world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
             uid = torch.frombuffer(bytearray(GLMModel.comm_unique_id()), dtype=torch.uint8).to(dev)
@@ -223,7 +225,9 @@ def run_b200(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(N_total, K), "rows_total": N_total, "rows_per_gpu": n_local, "cols": K,
-                   "sharding": f"rows x{world}" + (", one NCCL all-reduce of P+2 doubles per gradient" if world > 1 else ""),
+                   "sharding": f"rows x{world}" + ((", likelihood partials exchanged inside the gradient launch (peer mailboxes over NVLink)"
+                                                    if args.collective == "peer" else
+                                                    ", one NCCL all-reduce of P+2 doubles per gradient") if world > 1 else ""),
                    "l2": f"X shard {bytes_per_launch / 1e9:.2f} GB >> 126 MB L2, no flush needed",
                    "step": "one fused leapfrog launch (device-resident theta)"},
         "clocks": clk,
@@ -422,6 +426,8 @@ def main():
                     help="BASELINE configs index (1-based): 2 = single chain N=10M K=100 (default, the metric's config), "
                          "3 = normal_id N=1M K=200 with 1024 batched chains")
     ap.add_argument("--chains", type=int, default=1024)
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the P+2 likelihood partials are summed over ranks")
     ap.add_argument("--rows", type=int, default=None)
     ap.add_argument("--cols", type=int, default=None)
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)

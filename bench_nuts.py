@@ -37,6 +37,31 @@ def summarize(res, Ref, num_chains):
                 divergent=int(d[:, :, 5].sum()), stepsize=[float(s) for s in res["stepsize"]])
 
 
+def config3(args):
+    """BASELINE configs[2]: normal_id_glm N=1M K=200, `--chains` (1024) batched chains on one B200 through
+    b200::hmc_nuts_diag_e_adapt_batched.  No CPU arm (1024 chains x N=1M on the host would take days)."""
+    from oracle.oracle import RefOracle
+    from stan_b200 import make_glm_data, stan_service
+    N, K = args.rows or 1_000_000, args.cols or 200
+    t0 = time.time()
+    d = make_glm_data("normal_id", N, K)
+    t_gen = time.time() - t0
+    m = stan_service.StanGLM("normal_id", d["X"], d["y"], n_slots=16)
+    res = m.nuts_batched(num_chains=args.chains, seed=4711, num_warmup=args.warmup, num_samples=args.samples, delta=0.8)
+    s = summarize(res, RefOracle, args.chains)
+    s.pop("stepsize")
+    s["stepsize_median"] = float(np.median(res["stepsize"]))
+    s.update(batches=res["batches"], lanes=res["lanes"], mean_lanes_per_batch=res["lanes"] / max(res["batches"], 1))
+    truth = np.concatenate([[d["truth"]["alpha"]], d["truth"]["beta"], [1.0]])
+    post_mean = res["draws"][:, :, 7:].mean(axis=(0, 1))
+    s["max_abs_post_mean_minus_truth"] = float(np.max(np.abs(post_mean - truth)))
+    out = {"workload": f"normal_id_glm N={N} K={K}, NUTS diag_e {args.chains} batched chains {args.warmup}+{args.samples} "
+                       "via b200::hmc_nuts_diag_e_adapt_batched (single-chain reference service per chain)",
+           "host_threads": os.cpu_count(), "data_gen_s": t_gen, "b200": dict(s, counters=m.counters())}
+    m.close()
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, default=1)
@@ -50,6 +75,8 @@ def main():
     from oracle.oracle import RefOracle
     from stan_b200 import make_glm_data, stan_service
 
+    if args.config == 3:
+        return config3(args)
     N, K = {1: (10_000, 20), 2: (10_000_000, 100)}[args.config]
     N, K = args.rows or N, args.cols or K
     t0 = time.time()

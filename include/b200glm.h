@@ -140,6 +140,20 @@ void* b200glm_batch_stream(b200glm_handle* h);
 int b200glm_comm_unique_id(void* unique_id_128);
 int b200glm_comm_init(b200glm_handle* h, const void* unique_id_128, int32_t rank, int32_t world);
 
+/* Row-sharded operation WITHOUT a collective launch (preferred on NVLink / NVSwitch boxes): every rank
+ * exports a small mailbox in its HBM (peer_export: 64-byte cudaIpcMemHandle_t), the caller gathers the
+ * world's handles (rank order) and hands them to peer_connect.  From then on the LAST CTA of each
+ * gradient launch pushes its likelihood partials into every peer's mailbox, waits for theirs and sums
+ * in rank order, so a gradient (or fused leapfrog step) is ONE launch per rank and no NCCL call; theta
+ * stays bitwise replicated.  All ranks must issue the same sequence of evaluations per slot; a rank
+ * that does not makes the others return B200GLM_CUDA after a 20 s timeout (no hang).
+ * The poisson propto=false constant sum lgamma(y+1) is per shard: read it with lgamma_sum_local, add
+ * over ranks on the host and store the total with set_lgamma_sum_total (comm_init does this itself). */
+int b200glm_peer_export(b200glm_handle* h, void* ipc_handle_64);
+int b200glm_peer_connect(b200glm_handle* h, const void* all_handles, int32_t world);
+double b200glm_lgamma_sum_local(const b200glm_handle* h);
+int b200glm_set_lgamma_sum_total(b200glm_handle* h, double total);
+
 /* launch accounting for the bench (`gpu_launches`) and algorithmic bytes per gradient */
 int64_t b200glm_launch_count(const b200glm_handle* h);
 int64_t b200glm_bytes_per_gradient(const b200glm_handle* h);

@@ -1,0 +1,271 @@
+// b200/batched_nuts.hpp -- multi-chain batched driver for b200::glm_model.
+//
+// The reference runs chains as independent tasks, each calling the model gradient on its own
+// (ST/services/sample/hmc_nuts_diag_e_adapt.hpp:364-401: tbb::parallel_for over chains, one
+// util::run_adaptive_sampler per chain).  Here every chain still runs the reference's UNMODIFIED
+// single-chain service (hmc_nuts_diag_e_adapt.hpp:58-117 -> adapt_diag_e_nuts -> base_nuts::transition,
+// same RNG stream create_rng(seed, init_chain_id + i) as the multi-chain overload :352), but on its own
+// host thread inside a glm_model::batch_scope: whenever a chain needs a leapfrog step
+// (expl_leapfrog::evolve, base_nuts.hpp:254) or a gradient (hamiltonian.init, base_nuts.hpp:85) it parks
+// at the batcher; once every live chain is parked, ONE b200glm_leapfrog_batched call -- one pass over
+// X, the fp64 DMMA GEMM pair -- serves them all, and the chains go on building their trees.  Chains
+// advance in lock-step by leapfrog call; trees of different depth simply make a chain take part in
+// more or fewer batches per transition.  A gradient request is served as a leapfrog lane with eps = 0
+// (q stays, V and g are refreshed), so a batch never needs two passes.
+#ifndef B200_BATCHED_NUTS_HPP
+#define B200_BATCHED_NUTS_HPP
+
+#include <b200/stan_glm_model.hpp>
+
+#include <stan/services/sample/hmc_nuts_diag_e_adapt.hpp>
+
+#include <condition_variable>
+#include <cstdint>
+#include <limits>
+#include <mutex>
+#include <thread>
+
+namespace b200 {
+
+class chain_batcher final : public glm_model::batch_hook {
+ public:
+  chain_batcher(const glm_model& m, int n_chains)
+      : m_(m), P_(m.num_params_r()), n_(n_chains), n_active_(n_chains), req_(n_chains), res_(n_chains) {
+    m_.check(b200glm_batch_reserve(m_.handle(), n_chains));
+    const size_t np = static_cast<size_t>(n_) * P_;
+    for (auto* v : {&uq_, &up_, &ug_, &uim_, &oq_, &op_, &og_})
+      v->resize(np);
+    uV_.resize(n_);
+    oV_.resize(n_);
+    eps_.resize(n_);
+    lanes_.resize(n_);
+    up_lanes_.resize(n_);
+    status_.resize(n_);
+    for (auto& r : res_) {
+      r.q.assign(P_, 0.0);
+      r.p.assign(P_, 0.0);
+      r.g.assign(P_, 0.0);
+      r.im.assign(P_, 1.0);
+    }
+  }
+
+  void gradient(int chain, const double* theta, double& lp, double* grad) override {
+    request& r = req_[chain];
+    r = request();
+    r.kind = GRAD;
+    r.theta = theta;
+    submit(chain);
+    if (r.status != B200GLM_OK)
+      throw std::domain_error("non-finite log density or gradient (parameters, intercept or X*beta not finite)");
+    lp = -r.V_out;
+    const double* g = og_.data() + static_cast<size_t>(r.lane) * P_;
+    for (size_t k = 0; k < P_; ++k)
+      grad[k] = -g[k];
+  }
+
+  void leapfrog(int chain, Eigen::VectorXd& q, Eigen::VectorXd& p, Eigen::VectorXd& g, double& V,
+                const Eigen::VectorXd& inv_metric, double epsilon, stan::callbacks::logger& logger) override {
+    request& r = req_[chain];
+    r = request();
+    r.kind = LEAPFROG;
+    r.q = q.data();
+    r.p = p.data();
+    r.g = g.data();
+    r.V_in = V;
+    r.im = inv_metric.data();
+    r.eps = epsilon;
+    submit(chain);
+    const size_t o = static_cast<size_t>(r.lane) * P_, bytes = P_ * sizeof(double);
+    std::memcpy(q.data(), oq_.data() + o, bytes);
+    std::memcpy(p.data(), op_.data() + o, bytes);
+    std::memcpy(g.data(), og_.data() + o, bytes);
+    V = r.V_out;
+    if (r.status != B200GLM_OK || V == std::numeric_limits<double>::infinity())
+      glm_model::reject_message("non-finite log density or gradient", logger);
+  }
+
+  // a chain has finished (or failed): the others no longer wait for it
+  void leave(int) override {
+    std::unique_lock<std::mutex> lk(mu_);
+    --n_active_;
+    if (n_active_ > 0 && n_waiting_ == n_active_)
+      run_batch();
+  }
+
+  long n_batches() const { return n_batches_; }
+  long n_lanes() const { return n_lanes_; }
+
+ private:
+  enum { GRAD = 0, LEAPFROG = 1 };
+  struct request {
+    int kind = GRAD;
+    bool pending = false;
+    const double* theta = nullptr;
+    double *q = nullptr, *p = nullptr, *g = nullptr;
+    const double* im = nullptr;
+    double V_in = 0, eps = 0, V_out = 0;
+    int lane = -1, status = 0;
+  };
+  struct resident {  // what the device holds for a chain slot (as last written / read back)
+    bool valid = false;
+    std::vector<double> q, p, g, im;
+  };
+
+  void submit(int chain) {
+    std::unique_lock<std::mutex> lk(mu_);
+    req_[chain].pending = true;
+    ++n_waiting_;
+    if (n_waiting_ == n_active_) {
+      run_batch();
+    } else {
+      const std::uint64_t gen = gen_;
+      cv_.wait(lk, [&] { return gen_ != gen; });
+    }
+    if (!fatal_.empty())
+      throw std::runtime_error(fatal_);
+  }
+
+  // mu_ held; every live chain is parked
+  void run_batch() {
+    try {
+      dispatch();
+    } catch (const std::exception& e) {
+      fatal_ = e.what();
+    }
+    for (auto& r : req_)
+      r.pending = false;
+    n_waiting_ = 0;
+    ++gen_;
+    cv_.notify_all();
+  }
+
+  void dispatch() {
+    const size_t bytes = P_ * sizeof(double);
+    int n = 0, n_up = 0;
+    for (int c = 0; c < n_; ++c) {
+      request& r = req_[c];
+      if (!r.pending)
+        continue;
+      resident& rs = res_[c];
+      r.lane = n;
+      lanes_[n] = c;
+      bool upload;
+      if (r.kind == GRAD) {
+        eps_[n] = 0.0;
+        upload = true;
+      } else {
+        eps_[n] = r.eps;
+        upload = !(rs.valid && std::memcmp(rs.q.data(), r.q, bytes) == 0 && std::memcmp(rs.p.data(), r.p, bytes) == 0
+                   && std::memcmp(rs.g.data(), r.g, bytes) == 0 && std::memcmp(rs.im.data(), r.im, bytes) == 0);
+      }
+      if (upload) {
+        const size_t o = static_cast<size_t>(n_up) * P_;
+        if (r.kind == GRAD) {
+          std::memcpy(uq_.data() + o, r.theta, bytes);
+          std::memset(up_.data() + o, 0, bytes);
+          std::memset(ug_.data() + o, 0, bytes);
+          uV_[n_up] = 0.0;
+        } else {
+          std::memcpy(uq_.data() + o, r.q, bytes);
+          std::memcpy(up_.data() + o, r.p, bytes);
+          std::memcpy(ug_.data() + o, r.g, bytes);
+          uV_[n_up] = r.V_in;
+          std::memcpy(rs.im.data(), r.im, bytes);
+        }
+        std::memcpy(uim_.data() + o, rs.im.data(), bytes);
+        up_lanes_[n_up++] = c;
+      }
+      ++n;
+    }
+    if (n == 0)
+      return;
+    b200glm_handle* h = m_.handle();
+    if (n_up > 0) {
+      m_.check(b200glm_set_state_batched(h, n_up, up_lanes_.data(), uq_.data(), up_.data(), ug_.data(), uV_.data(),
+                                         uim_.data()));
+      m_.count_upload(n_up);
+    }
+    m_.check(b200glm_leapfrog_batched(h, n, lanes_.data(), eps_.data(), oq_.data(), op_.data(), og_.data(),
+                                      oV_.data(), status_.data()));
+    ++n_batches_;
+    n_lanes_ += n;
+    for (int i = 0; i < n; ++i) {
+      const int c = lanes_[i];
+      request& r = req_[c];
+      resident& rs = res_[c];
+      r.V_out = oV_[i];
+      r.status = status_[i];
+      const size_t o = static_cast<size_t>(i) * P_;
+      std::memcpy(rs.q.data(), oq_.data() + o, bytes);
+      std::memcpy(rs.p.data(), op_.data() + o, bytes);
+      std::memcpy(rs.g.data(), og_.data() + o, bytes);
+      rs.valid = true;
+    }
+  }
+
+  const glm_model& m_;
+  const size_t P_;
+  const int n_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  int n_active_, n_waiting_ = 0;
+  std::uint64_t gen_ = 0;
+  std::string fatal_;
+  std::vector<request> req_;
+  std::vector<resident> res_;
+  std::vector<double> uq_, up_, ug_, uim_, uV_, oq_, op_, og_, oV_, eps_;
+  std::vector<int32_t> lanes_, up_lanes_, status_;
+  long n_batches_ = 0, n_lanes_ = 0;
+};
+
+// Same contract and argument list as the reference's multi-chain
+// stan::services::sample::hmc_nuts_diag_e_adapt (hmc_nuts_diag_e_adapt.hpp:331-404); chain i uses
+// create_rng(random_seed, init_chain_id + i) exactly as there.  stats (optional) receives
+// {batched launches, lanes served}.
+template <typename InitContextPtr, typename InitInvContextPtr, typename InitWriter, typename SampleWriter,
+          typename DiagnosticWriter, typename MetricWriter>
+int hmc_nuts_diag_e_adapt_batched(glm_model& model, size_t num_chains, const std::vector<InitContextPtr>& init,
+                                  const std::vector<InitInvContextPtr>& init_inv_metric, unsigned int random_seed,
+                                  unsigned int init_chain_id, double init_radius, int num_warmup, int num_samples,
+                                  int num_thin, bool save_warmup, int refresh, double stepsize,
+                                  double stepsize_jitter, int max_depth, double delta, double gamma, double kappa,
+                                  double t0, unsigned int init_buffer, unsigned int term_buffer, unsigned int window,
+                                  stan::callbacks::interrupt& interrupt, stan::callbacks::logger& logger,
+                                  std::vector<InitWriter>& init_writer, std::vector<SampleWriter>& sample_writer,
+                                  std::vector<DiagnosticWriter>& diagnostic_writer,
+                                  std::vector<MetricWriter>& metric_writer, long* stats = nullptr) {
+  chain_batcher batcher(model, static_cast<int>(num_chains));
+  std::vector<int> rc(num_chains, 0);
+  std::vector<std::thread> threads;
+  threads.reserve(num_chains);
+  for (size_t i = 0; i < num_chains; ++i) {
+    threads.emplace_back([&, i] {
+      stan::math::ChainableStack tape;  // STAN_THREADS: every thread owns an AD tape (init_chainablestack.hpp)
+      glm_model::batch_scope scope(&batcher, static_cast<int>(i));
+      try {
+        rc[i] = stan::services::sample::hmc_nuts_diag_e_adapt(
+            model, *init[i], *init_inv_metric[i], random_seed, init_chain_id + i, init_radius, num_warmup,
+            num_samples, num_thin, save_warmup, refresh, stepsize, stepsize_jitter, max_depth, delta, gamma, kappa,
+            t0, init_buffer, term_buffer, window, interrupt, logger, init_writer[i], sample_writer[i],
+            diagnostic_writer[i], metric_writer[i]);
+      } catch (const std::exception& e) {
+        logger.error(e.what());
+        rc[i] = stan::services::error_codes::SOFTWARE;
+      }
+    });
+  }
+  for (auto& t : threads)
+    t.join();
+  if (stats) {
+    stats[0] = batcher.n_batches();
+    stats[1] = batcher.n_lanes();
+  }
+  for (int r : rc)
+    if (r != 0)
+      return r;
+  return stan::services::error_codes::OK;
+}
+
+}  // namespace b200
+
+#endif

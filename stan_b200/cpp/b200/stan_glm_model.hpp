@@ -92,10 +92,46 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
     return tls_slot;
   }
 
+  // Batched-chains hook (b200/batched_nuts.hpp): while a host thread runs a chain inside a
+  // batch_scope, its gradient and leapfrog calls are not launched one by one but handed to the
+  // batcher, which serves all waiting chains with ONE pass over X (b200glm_leapfrog_batched).
+  struct batch_hook {
+    virtual ~batch_hook() {}
+    virtual void gradient(int chain, const double* theta, double& lp, double* grad) = 0;
+    virtual void leapfrog(int chain, Eigen::VectorXd& q, Eigen::VectorXd& p, Eigen::VectorXd& g, double& V,
+                          const Eigen::VectorXd& inv_metric, double epsilon, stan::callbacks::logger& logger) = 0;
+    virtual void leave(int chain) = 0;
+  };
+  static batch_hook*& tls_hook() {
+    static thread_local batch_hook* hook = nullptr;
+    return hook;
+  }
+  static int& tls_chain() {
+    static thread_local int chain = -1;
+    return chain;
+  }
+  struct batch_scope {
+    batch_scope(batch_hook* hook, int chain) {
+      tls_hook() = hook;
+      tls_chain() = chain;
+    }
+    ~batch_scope() {
+      batch_hook* hook = tls_hook();
+      tls_hook() = nullptr;
+      if (hook)
+        hook->leave(tls_chain());
+      tls_chain() = -1;
+    }
+  };
+
   void device_log_prob_grad(const double* theta, bool propto, bool jacobian,
                             double& lp, double* grad) const {
-    check(b200glm_log_prob_grad(h_, slot(), theta, propto, jacobian, &lp, grad));
     n_gradients_.fetch_add(1, std::memory_order_relaxed);
+    if (batch_hook* hook = tls_hook(); hook && propto && jacobian) {
+      hook->gradient(tls_chain(), theta, lp, grad);
+      return;
+    }
+    check(b200glm_log_prob_grad(h_, slot(), theta, propto, jacobian, &lp, grad));
   }
   double device_log_prob(const double* theta, bool propto, bool jacobian) const {
     double lp = 0;
@@ -125,6 +161,11 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
   void device_leapfrog(Eigen::VectorXd& q, Eigen::VectorXd& p, Eigen::VectorXd& g, double& V,
                        const Eigen::VectorXd& inv_metric, double epsilon,
                        stan::callbacks::logger& logger) const {
+    n_leapfrogs_.fetch_add(1, std::memory_order_relaxed);
+    if (batch_hook* hook = tls_hook()) {
+      hook->leapfrog(tls_chain(), q, p, g, V, inv_metric, epsilon, logger);
+      return;
+    }
     const size_t P = num_params_r();
     const size_t bytes = P * sizeof(double);
     resident_state& rs = resident();
@@ -151,7 +192,6 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
       im = rs.inv_metric.data();
     }
     const int rc = b200glm_leapfrog(h_, sl, epsilon, im, q.data(), p.data(), g.data(), &V);
-    n_leapfrogs_.fetch_add(1, std::memory_order_relaxed);
     if (rc == B200GLM_DOMAIN) {
       // data-level domain error (y out of range): same outcome as base_hamiltonian.hpp:65-69
       V = std::numeric_limits<double>::infinity();
@@ -183,6 +223,7 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
   long n_gradients() const { return n_gradients_.load(); }
   long n_leapfrogs() const { return n_leapfrogs_.load(); }
   long n_uploads() const { return n_uploads_.load(); }
+  void count_upload(long n = 1) const { n_uploads_.fetch_add(n, std::memory_order_relaxed); }
 
   // ---------------------------------------------------------------- model_base interface
   std::string model_name() const override { return "b200_glm_model"; }

@@ -4,10 +4,13 @@
 // stan_b200/lib/libb200stan.so travels to the GPU box.  It is the executable proof of the drop-in:
 //   b200stan_nuts          -> stan::services::sample::hmc_nuts_diag_e_adapt  (ST/services/sample/hmc_nuts_diag_e_adapt.hpp:58,331)
 //                             with Model = b200::glm_model; base_nuts, diag_e_metric, adaptation, writers untouched
+//   b200stan_nuts_batched  -> b200::hmc_nuts_diag_e_adapt_batched (b200/batched_nuts.hpp): the same single-chain service per
+//                             chain, all chains served by one batched DMMA launch per leapfrog step
 //   b200stan_log_prob_grad -> stan::model::log_prob_grad<propto,jacobian>    (tape path via precomputed_gradients)
 //   b200stan_gradient      -> stan::model::gradient                          (explicit specialisation, no tape)
 //   b200stan_leapfrog      -> stan::mcmc::expl_leapfrog<diag_e_metric<...>>::evolve (device-resident specialisation)
 #include <b200/stan_glm_model.hpp>
+#include <b200/batched_nuts.hpp>
 
 #include <stan/callbacks/interrupt.hpp>
 #include <stan/callbacks/logger.hpp>
@@ -184,15 +187,16 @@ int b200stan_leapfrog(void* h, double eps, const double* inv_metric, int n_steps
 }
 
 // draws: [chain][warmup+sample][7 + P] (lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__, params)
-int b200stan_nuts(void* h, int num_chains, unsigned seed, unsigned init_chain_id, double init_radius, int num_warmup,
-                  int num_samples, double stepsize, int max_depth, double delta, int num_threads, double* draws,
-                  double* stepsize_out, double* inv_metric_out, double* warm_leapfrogs, double* wall_seconds,
-                  char* err, int errlen) {
+static int nuts_impl(void* h, bool batched, int num_chains, unsigned seed, unsigned init_chain_id, double init_radius,
+                     int num_warmup, int num_samples, double stepsize, int max_depth, double delta, int num_threads,
+                     double* draws, double* stepsize_out, double* inv_metric_out, double* warm_leapfrogs,
+                     double* wall_seconds, long* batch_stats, char* err, int errlen) {
   auto& m = *static_cast<glm_model*>(h);
   const int P = static_cast<int>(m.num_params_r());
   int rc = 0;
   int g = guarded(err, errlen, [&] {
-    stan::math::init_threadpool_tbb(num_threads > 0 ? num_threads : num_chains);
+    if (!batched)
+      stan::math::init_threadpool_tbb(num_threads > 0 ? num_threads : num_chains);
     std::vector<std::shared_ptr<stan::io::var_context>> inits, metrics;
     for (int c = 0; c < num_chains; ++c) {
       inits.emplace_back(std::make_shared<stan::io::empty_var_context>());
@@ -205,10 +209,16 @@ int b200stan_nuts(void* h, int num_chains, unsigned seed, unsigned init_chain_id
     std::vector<draw_writer> sample_w(num_chains);
     std::vector<metric_writer> metric_w(num_chains);
     auto t0 = std::chrono::steady_clock::now();
-    rc = stan::services::sample::hmc_nuts_diag_e_adapt(
-        m, num_chains, inits, metrics, seed, init_chain_id, init_radius, num_warmup, num_samples, 1, true, 0,
-        stepsize, 0.0, max_depth, delta, 0.05, 0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w, diag_w,
-        metric_w);
+    if (batched)
+      rc = b200::hmc_nuts_diag_e_adapt_batched(
+          m, num_chains, inits, metrics, seed, init_chain_id, init_radius, num_warmup, num_samples, 1, true, 0,
+          stepsize, 0.0, max_depth, delta, 0.05, 0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w, diag_w,
+          metric_w, batch_stats);
+    else
+      rc = stan::services::sample::hmc_nuts_diag_e_adapt(
+          m, num_chains, inits, metrics, seed, init_chain_id, init_radius, num_warmup, num_samples, 1, true, 0,
+          stepsize, 0.0, max_depth, delta, 0.05, 0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w, diag_w,
+          metric_w);
     auto t1 = std::chrono::steady_clock::now();
     if (wall_seconds)
       *wall_seconds = std::chrono::duration<double>(t1 - t0).count();
@@ -234,6 +244,25 @@ int b200stan_nuts(void* h, int num_chains, unsigned seed, unsigned init_chain_id
     }
   });
   return g ? g : rc;
+}
+
+int b200stan_nuts(void* h, int num_chains, unsigned seed, unsigned init_chain_id, double init_radius, int num_warmup,
+                  int num_samples, double stepsize, int max_depth, double delta, int num_threads, double* draws,
+                  double* stepsize_out, double* inv_metric_out, double* warm_leapfrogs, double* wall_seconds,
+                  char* err, int errlen) {
+  return nuts_impl(h, false, num_chains, seed, init_chain_id, init_radius, num_warmup, num_samples, stepsize, max_depth,
+                   delta, num_threads, draws, stepsize_out, inv_metric_out, warm_leapfrogs, wall_seconds, nullptr, err,
+                   errlen);
+}
+
+// batch_stats[2] = {batched launches, lanes served}
+int b200stan_nuts_batched(void* h, int num_chains, unsigned seed, unsigned init_chain_id, double init_radius,
+                          int num_warmup, int num_samples, double stepsize, int max_depth, double delta, double* draws,
+                          double* stepsize_out, double* inv_metric_out, double* warm_leapfrogs, double* wall_seconds,
+                          long* batch_stats, char* err, int errlen) {
+  return nuts_impl(h, true, num_chains, seed, init_chain_id, init_radius, num_warmup, num_samples, stepsize, max_depth,
+                   delta, 0, draws, stepsize_out, inv_metric_out, warm_leapfrogs, wall_seconds, batch_stats, err,
+                   errlen);
 }
 
 const char* b200stan_version() {

@@ -74,6 +74,7 @@ struct Slot {
   double* result = nullptr;      // P + 2
   double* theta_used = nullptr;  // P
   double* h_pinned = nullptr;    // pinned staging: max(3P+1, P+2) * 2
+  unsigned long long peer_seq = 0;  // evaluations exchanged through the peer mailboxes so far
   std::mutex mu;
 };
 
@@ -112,6 +113,11 @@ struct b200glm_handle {
   std::vector<Slot*> slots;
   Batch* batch = nullptr;
   ncclComm_t comm = nullptr;
+  // peer mailboxes (CUDA IPC): [n_slots][2][world][peer_stride] doubles on every rank
+  double* mbox = nullptr;
+  double* peer_mbox[MAX_PEERS] = {nullptr};
+  int peer_stride = 0;
+  bool peer_on = false;
   std::atomic<long long> launches{0};
   std::mutex err_mu;
   std::string last_error;
@@ -215,7 +221,20 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
   p.Kc = h->Kc;
   p.J = h->J;
   p.mode = mode;
-  p.fuse_finish = (h->d.world <= 1 && h->d.G == 0) ? 1 : 0;
+  p.fuse_finish = ((h->d.world <= 1 || h->peer_on) && h->d.G == 0) ? 1 : 0;
+  if (h->peer_on) {
+    int slot_idx = 0;
+    for (size_t i = 0; i < h->slots.size(); ++i)
+      if (h->slots[i] == s) slot_idx = (int)i;
+    p.peer.enabled = 1;
+    p.peer.world = h->d.world;
+    p.peer.rank = h->d.rank;
+    p.peer.stride = h->peer_stride;
+    p.peer.seq = s->peer_seq;
+    p.peer.timeout_ns = 20ull * 1000000000ull;
+    for (int r = 0; r < h->d.world; ++r)
+      p.peer.mbox[r] = h->peer_mbox[r] + (size_t)slot_idx * 2 * h->d.world * h->peer_stride;
+  }
   p.stage_a_in_smem = h->stage_a;
   p.theta_in = s->theta;
   p.st_in = s->state[s->cur];
@@ -250,9 +269,13 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
 // Enqueue one evaluation (all launches + the optional all-reduce) on the slot's stream.
 int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian, int is_var, double eps) {
   KernelParams p;
-  fill_params(h, s, p, mode, propto, jacobian, is_var, eps);
   const bool need_likelihood = ((!propto) || is_var) && h->d.N_total != -1;
   const bool rows_anywhere = (h->d.N_total > 0 ? h->d.N_total : h->d.N) > 0;
+  const bool exchange = need_likelihood && rows_anywhere && h->peer_on;
+  if (exchange) ++s->peer_seq;
+  fill_params(h, s, p, mode, propto, jacobian, is_var, eps);
+  p.peer_in_main = (exchange && h->d.G == 0) ? 1 : 0;
+  p.peer_in_finish = (exchange && h->d.G > 0) ? 1 : 0;
   if (need_likelihood && rows_anywhere) {
     kernel_fn fn = handle_kernel(h);
     fn<<<h->grid, h->wide ? WIDE_THREADS : NUM_THREADS, h->smem_bytes, s->stream>>>(p);
@@ -262,9 +285,9 @@ int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian,
       group_reduce_kernel<<<gb, 256, 0, s->stream>>>(s->r_out, h->seg_ptr, h->d.G, s->lik + 2);
       h->launches++;
     }
-    if (h->d.world > 1) {
+    if (h->d.world > 1 && !h->peer_on) {
       if (!h->comm) {
-        h->set_error("world > 1 but b200glm_comm_init was not called");
+        h->set_error("world > 1 but neither b200glm_peer_connect nor b200glm_comm_init was called");
         return B200GLM_INVALID;
       }
       ncclResult_t r = nccl().AllReduce(s->lik, s->lik, (size_t)h->P + 2, ncclFloat64, ncclSum, h->comm, s->stream);
@@ -316,6 +339,10 @@ int eval_host(b200glm_handle* h, int slot, const double* theta, int propto, int 
                      ? "bernoulli_logit_glm_lpmf: Vector of dependent variables is out of range [0, 1]"
                      : "poisson_log_glm_lpmf: Vector of dependent variables is negative");
     return B200GLM_DOMAIN;
+  }
+  if (hres[P + 1] == (double)ST_PEER_TIMEOUT) {
+    h->set_error("peer exchange timed out: a rank did not launch the matching evaluation");
+    return B200GLM_CUDA;
   }
   if (hres[P + 1] != 0.0) {
     h->set_error("non-finite log density or gradient (parameters, intercept or X*beta not finite)");
@@ -386,6 +413,9 @@ void b200glm_destroy(b200glm_handle* h) {
     delete b;
   }
   if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
+  for (int r = 0; r < MAX_PEERS; ++r)
+    if (h->peer_mbox[r] && h->peer_mbox[r] != h->mbox) cudaIpcCloseMemHandle(h->peer_mbox[r]);
+  cudaFree(h->mbox);
   cudaFree(h->panels);
   cudaFree(h->seg_ptr);
   delete h;
@@ -690,6 +720,10 @@ int b200glm_leapfrog(b200glm_handle* h, int32_t slot, double eps, const double* 
   if (p) std::memcpy(p, hp + P, sizeof(double) * P);
   if (g) std::memcpy(g, hp + 2 * P, sizeof(double) * P);
   if (V) *V = hp[3 * P];
+  if (h->peer_on && std::isnan(hp[3 * P])) {
+    h->set_error("peer exchange timed out: a rank did not launch the matching leapfrog step");
+    return B200GLM_CUDA;
+  }
   if (h->bad_y) {
     h->set_error("dependent variable out of range");
     return B200GLM_DOMAIN;
@@ -836,7 +870,8 @@ int b200glm_batch_reserve(b200glm_handle* h, int32_t max_chains) {
     return B200GLM_INVALID;
   }
   if (h->batch) {
-    h->set_error("batch workspace already reserved");
+    if (max_chains <= h->batch->max_chains) return B200GLM_OK;  // idempotent for a smaller or equal request
+    h->set_error("batch workspace already reserved with fewer chain slots");
     return B200GLM_INVALID;
   }
   if (h->wide || h->d.G > 0 || h->d.world > 1 || h->d.K > BATCH_MAX_K) {
@@ -947,27 +982,24 @@ int b200glm_set_state_batched(b200glm_handle* h, int32_t n, const int32_t* chain
       return B200GLM_INVALID;
     }
   }
-  // host-side transpose into the feature-major state (set_state is off the hot path): one strided
-  // 2-D copy per array
-  auto put = [&](double* dst, const double* src) -> cudaError_t {
-    double* st = b->h_pin;
-    for (int i = 0; i < n; ++i) std::memcpy(st + (size_t)i * P, src + (size_t)i * P, sizeof(double) * P);
-    for (int i = 0; i < n; ++i) {
-      const int c = chains ? chains[i] : i;
-      cudaError_t e = cudaMemcpy2DAsync(dst + c, sizeof(double) * b->ld, st + (size_t)i * P, sizeof(double),
-                                        sizeof(double), P, cudaMemcpyHostToDevice, b->stream);
-      if (e != cudaSuccess) return e;
-    }
-    return cudaStreamSynchronize(b->stream);
-  };
-  CUDA_TRY(h, put(b->Q, q));
-  CUDA_TRY(h, put(b->Pm, p));
-  CUDA_TRY(h, put(b->Gd, g));
-  if (inv_metric) CUDA_TRY(h, put(b->IM, inv_metric));
+  // one pinned staging block [n][4P + 1] = (q, p, g, inv_metric, V), one H2D copy, one scatter kernel
+  const size_t W = 4 * P + 1;
   for (int i = 0; i < n; ++i) {
-    const int c = chains ? chains[i] : i;
-    CUDA_TRY(h, cudaMemcpyAsync(b->V + c, V + i, sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    double* st = b->h_pin + (size_t)i * W;
+    std::memcpy(st, q + (size_t)i * P, sizeof(double) * P);
+    std::memcpy(st + P, p + (size_t)i * P, sizeof(double) * P);
+    std::memcpy(st + 2 * P, g + (size_t)i * P, sizeof(double) * P);
+    if (inv_metric) std::memcpy(st + 3 * P, inv_metric + (size_t)i * P, sizeof(double) * P);
+    st[4 * P] = V[i];
+    b->h_pin_i[i] = chains ? chains[i] : i;
   }
+  CUDA_TRY(h, cudaMemcpyAsync(b->theta_in, b->h_pin, sizeof(double) * n * W, cudaMemcpyHostToDevice, b->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(b->chains_d, b->h_pin_i, sizeof(int32_t) * n, cudaMemcpyHostToDevice, b->stream));
+  const long long tot = (long long)n * (P + 1);
+  batched_scatter_state_kernel<<<(int)std::min<long long>((tot + 255) / 256, 4 * b->sms), 256, 0, b->stream>>>(
+      n, (int)P, b->ld, b->chains_d, b->theta_in, inv_metric ? 1 : 0, b->Q, b->Pm, b->Gd, b->IM, b->V);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
   CUDA_TRY(h, cudaStreamSynchronize(b->stream));
   return B200GLM_OK;
 }
@@ -1031,6 +1063,59 @@ void* b200glm_batch_stream(b200glm_handle* h) { return (h && h->batch) ? (void*)
 }  // extern "C"
 
 extern "C" {
+
+int b200glm_peer_export(b200glm_handle* h, void* ipc_handle_64) {
+  if (!h || !ipc_handle_64) return B200GLM_INVALID;
+  if (h->d.world < 2 || h->d.world > MAX_PEERS) {
+    h->set_error("peer mailboxes need 2 <= world <= 8");
+    return B200GLM_INVALID;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  if (!h->mbox) {
+    h->peer_stride = (h->P + 2 + 1 + 1) & ~1;  // payload + sequence word, even
+    const size_t n = (size_t)h->slots.size() * 2 * h->d.world * h->peer_stride;
+    CUDA_TRY(h, cudaMalloc(&h->mbox, sizeof(double) * n));
+    CUDA_TRY(h, cudaMemset(h->mbox, 0, sizeof(double) * n));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t ih;
+  CUDA_TRY(h, cudaIpcGetMemHandle(&ih, h->mbox));
+  static_assert(sizeof(ih) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(ipc_handle_64, &ih, sizeof(ih));
+  return B200GLM_OK;
+}
+
+int b200glm_peer_connect(b200glm_handle* h, const void* all_handles, int32_t world) {
+  if (!h || !all_handles) return B200GLM_INVALID;
+  if (world != h->d.world || !h->mbox) {
+    h->set_error("b200glm_peer_connect: world differs from b200glm_create, or b200glm_peer_export was not called");
+    return B200GLM_INVALID;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  for (int r = 0; r < world; ++r) {
+    if (r == h->d.rank) {
+      h->peer_mbox[r] = h->mbox;
+      continue;
+    }
+    cudaIpcMemHandle_t ih;
+    std::memcpy(&ih, static_cast<const char*>(all_handles) + (size_t)r * sizeof(ih), sizeof(ih));
+    void* ptr = nullptr;
+    CUDA_TRY(h, cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_mbox[r] = static_cast<double*>(ptr);
+  }
+  // the propto=false poisson constant is a sum over all shards: exchanged through the same mailboxes
+  // by the first evaluation is not possible (it is a create-time constant), so the caller passes it:
+  h->peer_on = true;
+  return B200GLM_OK;
+}
+
+int b200glm_set_lgamma_sum_total(b200glm_handle* h, double total) {
+  if (!h) return B200GLM_INVALID;
+  h->lgamma_sum_total = total;
+  return B200GLM_OK;
+}
+
+double b200glm_lgamma_sum_local(const b200glm_handle* h) { return h ? h->lgamma_sum : 0.0; }
 
 int b200glm_comm_unique_id(void* unique_id_128) {
   if (!unique_id_128 || !nccl().ok) return B200GLM_CUDA;

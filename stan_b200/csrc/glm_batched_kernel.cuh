@@ -300,6 +300,30 @@ __global__ void __launch_bounds__(256) batched_begin_kernel(const BatchedStepPar
   }
 }
 
+// set_state for n chain slots: chain-major staging [n][4P + 1] = (q, p, g, inv_metric, V) -> feature-major state
+__global__ void __launch_bounds__(256) batched_scatter_state_kernel(int n, int P, int ld_state,
+                                                                    const int32_t* __restrict__ chains,
+                                                                    const double* __restrict__ in, int has_metric,
+                                                                    double* Q, double* Pm, double* Gd, double* IM,
+                                                                    double* V) {
+  const int W = 4 * P + 1;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (long long)n * (P + 1);
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % n), k = (int)(idx / n);
+    const int c = chains ? chains[i] : i;
+    const double* src = in + (size_t)i * W;
+    if (k == P) {
+      V[c] = src[4 * P];
+    } else {
+      const size_t o = (size_t)k * ld_state + c;
+      Q[o] = src[k];
+      Pm[o] = src[P + k];
+      Gd[o] = src[2 * P + k];
+      if (has_metric) IM[o] = src[3 * P + k];
+    }
+  }
+}
+
 // Slice partials -> per-chain model lp / gradient (priors, Jacobian: same formulas as finish() for
 // G == 0) and, in leapfrog mode, end_update_p + state write-back.  One CTA per 32 lanes (lane = chain),
 // 8 warps stride over the features.

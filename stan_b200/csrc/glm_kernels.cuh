@@ -38,7 +38,7 @@ constexpr int SMEM_A_MAX_GROUPS = 2048;  // a[G] staged in smem up to this many 
 
 enum { FAM_BERNOULLI_LOGIT = 0, FAM_POISSON_LOG = 1, FAM_NORMAL_ID = 2 };
 enum { MODE_THETA = 0, MODE_LEAPFROG = 1 };
-enum { ST_OK = 0, ST_DOMAIN = 1 };
+enum { ST_OK = 0, ST_DOMAIN = 1, ST_PEER_TIMEOUT = 2 };
 
 #define NEG_LOG_SQRT_TWO_PI_D (-0.91893853320467274178032973640562)
 
@@ -51,6 +51,17 @@ struct ModelConst {
   double prior_alpha_sd, prior_beta_sd, prior_sigma_loc, prior_sigma_scale, prior_sigma_a_scale;
 };
 
+// Row-sharded operation without a separate collective launch: every rank owns a mailbox in its HBM,
+// mapped into every peer (CUDA IPC over NVLink / NVSwitch).  [2 parities][world][stride] doubles; the
+// last word of an entry is the sequence number of the evaluation it belongs to.
+constexpr int MAX_PEERS = 8;
+struct PeerParams {
+  int enabled, world, rank, stride;
+  unsigned long long seq;          // 1, 2, 3, ... identical on every rank for the same evaluation
+  unsigned long long timeout_ns;
+  double* mbox[MAX_PEERS];         // this slot's mailbox on rank r (mbox[rank] is local memory)
+};
+
 struct KernelParams {
   const double* panels;
   long long n_rows;    // local rows
@@ -59,7 +70,10 @@ struct KernelParams {
   int n_stages;        // narrow kernel: panel stages; wide kernel: sub-panel slots in the ring
   int Cpad, Kc, J;     // wide kernel: padded column count, sub-panel width, sub-panels per row panel
   int mode;
-  int fuse_finish;     // last CTA also runs finish() (world == 1 && G == 0)
+  int fuse_finish;     // last CTA also runs finish() (G == 0 and: world == 1, or peers connected)
+  int peer_in_main;    // last CTA of the main kernel exchanges the likelihood partials with the peers
+  int peer_in_finish;  // finish_kernel does (G > 0: the group sums are only complete by then)
+  PeerParams peer;
   int stage_a_in_smem;
   const double* theta_in;   // MODE_THETA: P doubles (device)
   const double* st_in;      // MODE_LEAPFROG: [q(P) p(P) g(P) V]
@@ -163,6 +177,72 @@ __device__ __forceinline__ void link(double eta, double y, double inv_sigma, dou
     const double z = (y - eta) * inv_sigma;
     r_i = inv_sigma * z;
     lp_i = z * z;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// All-reduce (sum) of the P+2 likelihood partials across the row shards, INSIDE the launch that
+// produced them: one CTA per rank pushes its partial into every rank's mailbox with peer stores,
+// releases a per-sender sequence flag, waits for the world's flags in its own mailbox and adds the
+// entries in rank order -- the same order on every rank, so theta stays bitwise replicated.
+// Replaces ncclAllReduce + a separate epilogue launch (two launches and ~20 us per gradient).
+// Called by every thread of that CTA after p.lik is complete; returns false on timeout.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* ptr, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* ptr) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ bool peer_allreduce_lik(const KernelParams& p, int* sh_ok) {
+  const PeerParams& pe = p.peer;
+  const int n = p.P + 2, tid = threadIdx.x, nt = blockDim.x;
+  const int buf = (int)(pe.seq & 1ull);
+  const size_t my_off = ((size_t)buf * pe.world + pe.rank) * pe.stride;
+  for (int r = 0; r < pe.world; ++r) {
+    double* dst = pe.mbox[r] + my_off;
+    for (int j = tid; j < n; j += nt) dst[j] = __ldcg(p.lik + j);
+  }
+  __threadfence_system();
+  if (tid == 0) *sh_ok = 1;
+  __syncthreads();
+  if (tid < pe.world)
+    st_release_sys_u64(reinterpret_cast<unsigned long long*>(pe.mbox[tid] + my_off + pe.stride - 1), pe.seq);
+  const double* mine = pe.mbox[pe.rank] + (size_t)buf * pe.world * pe.stride;
+  if (tid < pe.world) {
+    const unsigned long long* flag =
+        reinterpret_cast<const unsigned long long*>(mine + (size_t)tid * pe.stride + pe.stride - 1);
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys_u64(flag) != pe.seq) {
+      if (globaltimer_ns() - t0 > pe.timeout_ns) {
+        *sh_ok = 0;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  if (!*sh_ok) return false;
+  for (int j = tid; j < n; j += nt) {
+    double v = 0.0;
+    for (int r = 0; r < pe.world; ++r) v += __ldcg(mine + (size_t)r * pe.stride + j);
+    p.lik[j] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  return true;
+}
+__device__ void peer_timeout_result(const KernelParams& p) {
+  if (threadIdx.x == 0) {
+    p.result[0] = CUDART_NAN;
+    p.result[1 + p.P] = (double)ST_PEER_TIMEOUT;
+    if (p.mode == MODE_LEAPFROG) p.st_out[3 * p.P] = CUDART_NAN;
   }
 }
 
@@ -383,6 +463,10 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
   if (G > 0 && tid < 2) p.lik[tid] = 0.0;
   __threadfence();
   __syncthreads();
+  if (p.peer_in_main && !peer_allreduce_lik(p, sh_is_last)) {
+    peer_timeout_result(p);
+    return;
+  }
   if (p.fuse_finish) finish(p, sh_scratch);
 }
 
@@ -594,6 +678,11 @@ __global__ void __launch_bounds__(256) group_reduce_kernel(const double* __restr
 
 __global__ void __launch_bounds__(NUM_THREADS) finish_kernel(const KernelParams p) {
   __shared__ double sh_scratch[64];
+  __shared__ int sh_ok;
+  if (p.peer_in_finish && !peer_allreduce_lik(p, &sh_ok)) {
+    peer_timeout_result(p);
+    return;
+  }
   finish(p, sh_scratch);
 }
 

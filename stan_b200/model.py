@@ -240,3 +240,35 @@ class GLMModel:
     def comm_init(self, unique_id):
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self._check(self.L.b200glm_comm_init(self.h, buf, self.rank, self.world))
+
+    def peer_export(self):
+        """64-byte IPC handle of this rank's mailbox (gather over ranks, then peer_connect)."""
+        buf = C.create_string_buffer(64)
+        self._check(self.L.b200glm_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_connect(self, all_handles):
+        """all_handles: world x 64 bytes in rank order."""
+        raw = bytes(all_handles)
+        if len(raw) != 64 * self.world:
+            raise InvalidArgument("expected world x 64 bytes of IPC handles")
+        self._check(self.L.b200glm_peer_connect(self.h, C.create_string_buffer(raw, len(raw)), self.world))
+
+    def lgamma_sum_local(self):
+        return self.L.b200glm_lgamma_sum_local(self.h)
+
+    def set_lgamma_sum_total(self, total):
+        self._check(self.L.b200glm_set_lgamma_sum_total(self.h, float(total)))
+
+    def connect_peers_torch(self, dist, dev):
+        """Convenience for torch.distributed callers: all-gather the mailbox handles (and the poisson
+        constant) and connect.  torch.distributed is plumbing here, the exchange itself is in-kernel."""
+        import torch
+        mine = torch.frombuffer(bytearray(self.peer_export()), dtype=torch.uint8).to(dev)
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine)
+        self.peer_connect(b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh))
+        lg = torch.tensor([self.lgamma_sum_local()], dtype=torch.float64, device=dev)
+        dist.all_reduce(lg)
+        self.set_lgamma_sum_total(float(lg.item()))
+        dist.barrier()

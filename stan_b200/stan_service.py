@@ -149,3 +149,22 @@ class StanGLM:
             self._raise(rc, err)
         return dict(draws=draws[:, num_warmup:, :], warmup_draws=draws[:, :num_warmup, :], stepsize=step,
                     inv_metric=inv_metric, warm_leapfrogs=warm_lf, wall=wall.value)
+
+    def nuts_batched(self, num_chains=4, seed=1, init_chain_id=1, init_radius=2.0, num_warmup=1000, num_samples=1000,
+                     stepsize=1.0, max_depth=10, delta=0.8):
+        """b200::hmc_nuts_diag_e_adapt_batched: one host thread per chain running the reference's single-chain
+        service; all chains' leapfrog steps served together by one batched fp64 DMMA launch."""
+        W = 7 + self.P
+        draws = np.empty((num_chains, num_warmup + num_samples, W))
+        step, inv_metric = np.empty(num_chains), np.empty((num_chains, self.P))
+        warm_lf, wall, err = np.empty(num_chains), C.c_double(), C.create_string_buffer(4096)
+        stats = (C.c_long * 2)()
+        rc = self.L.b200stan_nuts_batched(self.h, num_chains, C.c_uint(seed), C.c_uint(init_chain_id),
+                                          C.c_double(init_radius), num_warmup, num_samples, C.c_double(stepsize),
+                                          max_depth, C.c_double(delta), _dp(draws), _dp(step), _dp(inv_metric),
+                                          _dp(warm_lf), C.byref(wall), stats, err, 4096)
+        if rc:
+            self._raise(rc, err)
+        return dict(draws=draws[:, num_warmup:, :], warmup_draws=draws[:, :num_warmup, :], stepsize=step,
+                    inv_metric=inv_metric, warm_leapfrogs=warm_lf, wall=wall.value,
+                    batches=int(stats[0]), lanes=int(stats[1]))

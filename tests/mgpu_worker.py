@@ -1,4 +1,6 @@
-"""Worker for tests/test_multigpu_gpu.py: one rank per GPU, row-sharded model, NCCL all-reduce.
+"""Worker for tests/test_multigpu_gpu.py: one rank per GPU, row-sharded model; the likelihood partials
+are combined either inside the gradient launch through peer mailboxes (MGPU_TRANSPORT=peer) or by one
+NCCL all-reduce per gradient (MGPU_TRANSPORT=nccl).
 Launched by torch.distributed.run; prints 'MGPU-OK' from rank 0 when every check passes."""
 import os
 import sys
@@ -26,15 +28,21 @@ def main():
         r0, r1 = shard_rows(N, rank, world)
         grp = None if d["group"] is None else d["group"][r0:r1]
         m = GLMModel(fam, d["X"][r0:r1], d["y"][r0:r1], grp, G, device=local, rank=rank, world=world, N_total=N)
-        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            uid = torch.frombuffer(bytearray(GLMModel.comm_unique_id()), dtype=torch.uint8).to(dev)
-        dist.broadcast(uid, 0)
-        m.comm_init(uid.cpu().numpy().tobytes())
+        if os.environ.get("MGPU_TRANSPORT", "peer") == "peer":
+            m.connect_peers_torch(dist, dev)
+        else:
+            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                uid = torch.frombuffer(bytearray(GLMModel.comm_unique_id()), dtype=torch.uint8).to(dev)
+            dist.broadcast(uid, 0)
+            m.comm_init(uid.cpu().numpy().tobytes())
+        launches0 = m.launch_count()
         P = m.num_params_r()
         rng = np.random.default_rng(5)
         th = 0.1 * rng.standard_normal(P)
         lp, g = m.log_prob_grad(th)
+        if os.environ.get("MGPU_TRANSPORT", "peer") == "peer" and G == 0 and m.launch_count() - launches0 != 1:
+            failures.append(f"{fam}: a sharded gradient took {m.launch_count() - launches0} launches, expected 1")
         lpd = m.log_prob(th, False, True)
         p0 = rng.standard_normal(P)
         m.set_state(th, p0, -g, -lp)

@@ -117,3 +117,55 @@ def test_nuts_leapfrogs_ran_on_device(nuts_pair):
     # every leapfrog of every transition is one fused device launch (plus init_stepsize's)
     assert c["leapfrogs"] >= n_lf
     assert c["uploads"] < c["leapfrogs"]          # state stayed resident for the rest
+
+
+# ---------------------------------------------------------------------------------------------------
+# batched driver: every chain runs the reference's single-chain service on its own host thread, the
+# leapfrog steps of all chains are served by one batched DMMA launch (b200/batched_nuts.hpp)
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def batched_pair():
+    Ref = ref_oracle()
+    d = make_glm_data("normal_id", 5_000, 12)
+    m = stan_service.StanGLM("normal_id", d["X"], d["y"])
+    kw = dict(num_chains=16, seed=99, num_warmup=300, num_samples=300, delta=0.8)
+    bat = m.nuts_batched(**kw)
+    bat["counters"] = m.counters()
+    seq = m.nuts(num_threads=4, **kw)
+    m.close()
+    ro = Ref("normal_id", d["X"], d["y"])
+    ref = ro.nuts(num_threads=4, **kw)
+    return Ref, bat, seq, ref
+
+
+def test_batched_driver_matches_unbatched_chains(batched_pair):
+    """Same seeds => same RNG streams and the same host code: batched chains coincide with the chains of
+    the reference's own multi-chain service (on the same device model) until rounding differences between
+    the batched and the single-chain kernel are amplified (the parallel_match property of
+    T/unit/services/sample/hmc_nuts_diag_e_adapt_parallel_match_test.cpp, to rounding)."""
+    Ref, bat, seq, ref = batched_pair
+    a, b = bat["warmup_draws"][:, :5, :], seq["warmup_draws"][:, :5, :]
+    assert np.array_equal(a[:, :, 3:6], b[:, :, 3:6])
+    assert np.max(np.abs(a[:, :, 7:] - b[:, :, 7:])) < 1e-6
+    assert np.max(np.abs(a[:, :, 0] - b[:, :, 0]) / np.abs(b[:, :, 0])) < 1e-9
+
+
+def test_batched_driver_posterior_within_mcse(batched_pair):
+    Ref, bat, seq, ref = batched_pair
+    P = bat["draws"].shape[2] - 7
+    zs = []
+    for k in range(P):
+        a, b = bat["draws"][:, :, 7 + k].T, ref["draws"][:, :, 7 + k].T
+        zs.append(abs(a.mean() - b.mean()) / np.hypot(Ref.mcse_mean(a), Ref.mcse_mean(b)))
+        zs.append(abs(a.std(ddof=1) - b.std(ddof=1)) / np.hypot(Ref.mcse_sd(a), Ref.mcse_sd(b)))
+        assert Ref.rhat(a) < 1.03
+    assert max(zs) < 4.0, zs
+    assert np.all(bat["draws"][:, :, 5] == 0)
+
+
+def test_batched_driver_batches_chains(batched_pair):
+    Ref, bat, seq, ref = batched_pair
+    n_eval = bat["draws"][:, :, 4].sum() + bat["warm_leapfrogs"].sum() + 16 * 600   # leapfrogs + one init gradient each
+    assert bat["lanes"] >= n_eval
+    # lock-step: far fewer launches than evaluations (16 chains, trees of similar depth)
+    assert bat["batches"] < 0.25 * bat["lanes"], (bat["batches"], bat["lanes"])
