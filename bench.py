@@ -34,8 +34,9 @@ K_COLS = 100
 FAMILY = "bernoulli_logit"
 
 
-def workload_name(N, K):
-    return f"bernoulli_logit_glm N={N} K={K} fp64, single chain (BASELINE configs[1])"
+def workload_name(N, K, family=FAMILY, G=0, config=2):
+    grp = f" with {G} group intercepts" if G else ""
+    return f"{family}_glm N={N} K={K}{grp} fp64, single chain (BASELINE configs[{config - 1}])"
 
 
 def measured_peaks():
@@ -100,7 +101,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from stan_b200 import GLMModel
-    from stan_b200.synth import make_logistic_shard
+    from stan_b200.synth import make_shard
 
     rank, local_rank, world = dist_env()
     if world != args.gpus:
@@ -110,12 +111,14 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    N_total, K = args.rows, args.cols
-    X, y, r0, r1 = make_logistic_shard(torch, dev, N_total, K, rank, world)
+    N_total, K, G, family = args.rows, args.cols, args.groups, args.family
+    if args.weak:
+        N_total *= world                      # --weak: --rows is per GPU
+    X, y, grp, r0, r1 = make_shard(torch, dev, family, N_total, K, G, rank, world)
     n_local = r1 - r0
     torch.cuda.synchronize()
-    m = GLMModel(FAMILY, X.data_ptr(), y.data_ptr(), data_on_device=True, N=n_local, K=K, ldx=n_local,
-                 device=local_rank, rank=rank, world=world, N_total=N_total)
+    m = GLMModel(family, X.data_ptr(), y.data_ptr(), grp.data_ptr() if G else None, G, data_on_device=True,
+                 N=n_local, K=K, ldx=n_local, device=local_rank, rank=rank, world=world, N_total=N_total)
     if world > 1 and args.collective == "peer":
         m.connect_peers_torch(dist, dev)      # in-kernel exchange through peer mailboxes (NVLink), no NCCL call
     elif world > 1:
@@ -129,8 +132,8 @@ def run_b200(args):
     sample = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ns = min(args.cpu_sample_rows, n_local)
-        sample = (X[:, :ns].cpu().numpy().T, y[:ns].cpu().numpy())
-    del X, y
+        sample = (X[:, :ns].cpu().numpy().T, y[:ns].cpu().numpy(), grp[:ns].cpu().numpy() if G else None)
+    del X, y, grp
     torch.cuda.empty_cache()
 
     P = m.num_params_r()
@@ -204,27 +207,29 @@ def run_b200(args):
     achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
-                "kernel": "glm_wide_kernel<bernoulli_logit>" if K > 256 else "glm_fused_kernel<bernoulli_logit>", "algorithmic_bytes_per_launch": bytes_per_launch,
+                "kernel": f"glm_wide_kernel<{family}>" if K > 256 else f"glm_fused_kernel<{family}>", "algorithmic_bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": ms_per_step}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as f:
                 tj = json.load(f)
-            if tj.get("N") == n_local and tj.get("K") == K:
-                roofline["traffic"] = tj.get("dram_bytes_per_launch")
+            for ent in tj.get("entries", [tj]):
+                if ent.get("N") == n_local and ent.get("K") == K:
+                    roofline["traffic"] = ent.get("dram_bytes_per_launch")
         except Exception:
             pass
 
     cpu_baseline = None
     if sample is not None:
         cpu_baseline = cpu_baseline_leg(sample[0], sample[1], N_total, threads=1, evals=args.cpu_evals,
-                                        check=(m, q0))
+                                        family=family, group=sample[2], G=G)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(N_total, K), "rows_total": N_total, "rows_per_gpu": n_local, "cols": K,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.weak else "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(N_total, K, family, G, args.config), "rows_total": N_total,
+                   "rows_per_gpu": n_local, "cols": K, "groups": G,
                    "sharding": f"rows x{world}" + ((", likelihood partials exchanged inside the gradient launch (peer mailboxes over NVLink)"
                                                     if args.collective == "peer" else
                                                     ", one NCCL all-reduce of P+2 doubles per gradient") if world > 1 else ""),
@@ -337,10 +342,10 @@ def run_b200_batched(args):
 # ------------------------------------------------------------------------------------------
 # CPU legs (the only place bench.py executes anything under oracle/)
 # ------------------------------------------------------------------------------------------
-def cpu_baseline_leg(Xs, ys, N_total, threads=1, evals=5, check=None, family=FAMILY):
+def cpu_baseline_leg(Xs, ys, N_total, threads=1, evals=5, family=FAMILY, group=None, G=0):
     from oracle.oracle import PortOracle, RefOracle
     cls = RefOracle if RefOracle.available() else PortOracle
-    orc = cls(family, Xs, ys)
+    orc = cls(family, Xs, ys, group, G)
     ns, K = Xs.shape
     th = 0.05 * np.random.default_rng(11).standard_normal(orc.P)
     orc.log_prob_grad(th)     # warm
@@ -422,9 +427,14 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE configs index (1-based): 2 = single chain N=10M K=100 (default, the metric's config), "
-                         "3 = normal_id N=1M K=200 with 1024 batched chains")
+                         "3 = normal_id N=1M K=200 with 1024 batched chains, 4 = poisson N=50M K=50 with 1000 group "
+                         "intercepts (row-sharded), 5 = bernoulli K=1000, 8M rows per GPU (weak scaling; the stated "
+                         "N=200M x K=1000 = 1.6 TB does not fit 8 x 180 GB)")
+    ap.add_argument("--family", default=None)
+    ap.add_argument("--groups", type=int, default=None)
+    ap.add_argument("--weak", action="store_true", help="--rows is per GPU (weak scaling)")
     ap.add_argument("--chains", type=int, default=1024)
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the P+2 likelihood partials are summed over ranks")
@@ -434,10 +444,13 @@ def main():
     ap.add_argument("--cpu-evals", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.rows is None:
-        args.rows = N_ROWS if args.config == 2 else 1_000_000
-    if args.cols is None:
-        args.cols = K_COLS if args.config == 2 else 200
+    preset = {2: (N_ROWS, K_COLS, FAMILY, 0, False), 3: (1_000_000, 200, "normal_id", 0, False),
+              4: (50_000_000, 50, "poisson_log", 1000, False), 5: (8_000_000, 1000, "bernoulli_logit", 0, True)}[args.config]
+    args.rows = preset[0] if args.rows is None else args.rows
+    args.cols = preset[1] if args.cols is None else args.cols
+    args.family = preset[2] if args.family is None else args.family
+    args.groups = preset[3] if args.groups is None else args.groups
+    args.weak = args.weak or preset[4]
     if args.config == 3 and args.impl == "b200":
         args.steps = args.steps if args.steps is not None else 20
         args.warmup = max(3, args.warmup if args.warmup is not None else 3)

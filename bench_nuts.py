@@ -52,6 +52,11 @@ def config3(args):
     s.pop("stepsize")
     s["stepsize_median"] = float(np.median(res["stepsize"]))
     s.update(batches=res["batches"], lanes=res["lanes"], mean_lanes_per_batch=res["lanes"] / max(res["batches"], 1))
+    per_chain = res["warm_leapfrogs"] + res["draws"][:, :, 4].sum(axis=1)
+    pc = lambda a: [float(np.percentile(a, q)) for q in (50, 90, 99, 100)]
+    s["per_chain_leapfrogs_p50_p90_p99_max"] = pc(per_chain)
+    s["per_chain_stepsize_p0_p1_p50_p100"] = [float(np.percentile(res["stepsize"], q)) for q in (0, 1, 50, 100)]
+    s["chains_with_mean_treedepth_ge_8"] = int((res["draws"][:, :, 3].mean(axis=1) >= 8).sum())
     truth = np.concatenate([[d["truth"]["alpha"]], d["truth"]["beta"], [1.0]])
     post_mean = res["draws"][:, :, 7:].mean(axis=(0, 1))
     s["max_abs_post_mean_minus_truth"] = float(np.max(np.abs(post_mean - truth)))

@@ -49,9 +49,16 @@ def main():
     with open(os.path.join(here, name + "_summary.txt"), "w") as f:
         f.write("\n".join(lines) + "\n")
     if N is not None:
-        with open(os.path.join(here, "traffic.json"), "w") as f:
-            json.dump({"N": N, "K": K, "dram_bytes_per_launch": sum(traffic) / len(traffic),
-                       "source": name + "_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, mean over captured launches)"}, f)
+        tp = os.path.join(here, "traffic.json")
+        ents = []
+        if os.path.exists(tp):
+            with open(tp) as f:
+                old = json.load(f)
+            ents = [e for e in old.get("entries", [old]) if not (e.get("N") == N and e.get("K") == K)]
+        ents.append({"N": N, "K": K, "dram_bytes_per_launch": sum(traffic) / len(traffic),
+                     "source": name + "_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, mean over captured launches)"})
+        with open(tp, "w") as f:
+            json.dump({"entries": ents}, f, indent=1)
     print("\n".join(lines))
 
 

@@ -92,7 +92,9 @@ class chain_batcher final : public glm_model::batch_hook {
       run_batch();
   }
 
+  static constexpr int kSingleLaneThreshold = 2;
   long n_batches() const { return n_batches_; }
+  long n_single() const { return n_single_; }
   long n_lanes() const { return n_lanes_; }
 
  private:
@@ -180,6 +182,38 @@ class chain_batcher final : public glm_model::batch_hook {
     if (n == 0)
       return;
     b200glm_handle* h = m_.handle();
+    if (n <= kSingleLaneThreshold) {
+      // a straggler or two: the single-chain kernel (one HBM-bound launch each) beats a 64-chain DMMA block
+      for (int i = 0; i < n; ++i) {
+        const int c = lanes_[i];
+        request& r = req_[c];
+        resident& rs = res_[c];
+        const size_t o = static_cast<size_t>(i) * P_;
+        rs.valid = false;   // the batch slot of this chain is stale from now on
+        if (r.kind == GRAD) {
+          double lp = 0;
+          const int rc = b200glm_log_prob_grad(h, 0, r.theta, 1, 1, &lp, og_.data() + o);
+          if (rc != B200GLM_OK && rc != B200GLM_DOMAIN)
+            m_.check(rc);
+          r.status = rc;
+          r.V_out = -lp;
+          for (size_t k = 0; k < P_; ++k)
+            og_[o + k] = -og_[o + k];
+        } else {
+          m_.check(b200glm_set_state(h, 0, r.q, r.p, r.g, r.V_in));
+          const int rc = b200glm_leapfrog(h, 0, r.eps, r.im, oq_.data() + o, op_.data() + o, og_.data() + o, &oV_[i]);
+          if (rc != B200GLM_OK && rc != B200GLM_DOMAIN)
+            m_.check(rc);
+          r.status = (rc == B200GLM_DOMAIN || oV_[i] == std::numeric_limits<double>::infinity()) ? B200GLM_DOMAIN
+                                                                                                  : B200GLM_OK;
+          r.V_out = rc == B200GLM_DOMAIN ? std::numeric_limits<double>::infinity() : oV_[i];
+        }
+      }
+      ++n_batches_;
+      n_lanes_ += n;
+      n_single_ += n;
+      return;
+    }
     if (n_up > 0) {
       m_.check(b200glm_set_state_batched(h, n_up, up_lanes_.data(), uq_.data(), up_.data(), ug_.data(), uV_.data(),
                                          uim_.data()));
@@ -215,7 +249,7 @@ class chain_batcher final : public glm_model::batch_hook {
   std::vector<resident> res_;
   std::vector<double> uq_, up_, ug_, uim_, uV_, oq_, op_, og_, oV_, eps_;
   std::vector<int32_t> lanes_, up_lanes_, status_;
-  long n_batches_ = 0, n_lanes_ = 0;
+  long n_batches_ = 0, n_lanes_ = 0, n_single_ = 0;
 };
 
 // Same contract and argument list as the reference's multi-chain

@@ -165,23 +165,24 @@ kernel_fn pick_kernel(int family, int cpl) {
 }
 
 template <int FAMILY>
-kernel_fn pick_wide_shape(int spw, int spc) {
-  if (spc == 4 && spw == 1) return glm_wide_kernel<FAMILY, 1, 4>;
-  if (spc == 4 && spw == 2) return glm_wide_kernel<FAMILY, 2, 4>;
-  if (spc == 8 && spw == 2) return glm_wide_kernel<FAMILY, 2, 8>;
-  if (spc == 8 && spw == 3) return glm_wide_kernel<FAMILY, 3, 8>;
+kernel_fn pick_wide_shape(int wr, int spw, int spc) {
+  if (wr == 16 && spw == 1 && spc == 4) return glm_wide_kernel<FAMILY, 16, 1, 4>;
+  if (wr == 16 && spw == 1 && spc == 8) return glm_wide_kernel<FAMILY, 16, 1, 8>;
+  if (wr == 8 && spw == 1 && spc == 8) return glm_wide_kernel<FAMILY, 8, 1, 8>;
+  if (wr == 4 && spw == 1 && spc == 8) return glm_wide_kernel<FAMILY, 4, 1, 8>;
+  if (wr == 4 && spw == 2 && spc == 8) return glm_wide_kernel<FAMILY, 4, 2, 8>;
   return nullptr;
 }
-kernel_fn pick_wide_kernel(int family, int spw, int spc) {
+kernel_fn pick_wide_kernel(int family, int wr, int spw, int spc) {
   switch (family) {
-    case FAM_BERNOULLI_LOGIT: return pick_wide_shape<FAM_BERNOULLI_LOGIT>(spw, spc);
-    case FAM_POISSON_LOG: return pick_wide_shape<FAM_POISSON_LOG>(spw, spc);
-    case FAM_NORMAL_ID: return pick_wide_shape<FAM_NORMAL_ID>(spw, spc);
+    case FAM_BERNOULLI_LOGIT: return pick_wide_shape<FAM_BERNOULLI_LOGIT>(wr, spw, spc);
+    case FAM_POISSON_LOG: return pick_wide_shape<FAM_POISSON_LOG>(wr, spw, spc);
+    case FAM_NORMAL_ID: return pick_wide_shape<FAM_NORMAL_ID>(wr, spw, spc);
   }
   return nullptr;
 }
 kernel_fn handle_kernel(const b200glm_handle* h) {
-  return h->wide ? pick_wide_kernel(h->d.family, h->spw, h->spc) : pick_kernel(h->d.family, h->cpl);
+  return h->wide ? pick_wide_kernel(h->d.family, h->panel_rows, h->spw, h->spc) : pick_kernel(h->d.family, h->cpl);
 }
 
 size_t fixed_smem_bytes(int K, int G, int stage_a, int S) {
@@ -445,7 +446,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   h->off_beta = d.G > 0 ? 2 + d.G : 1;
   h->C = d.K + 1 + (d.G > 0 ? 1 : 0);
   h->wide = d.K > 256 || (d.flags & B200GLM_FLAG_FORCE_WIDE);
-  h->panel_rows = h->wide ? WIDE_ROWS : PANEL_ROWS;
+  h->panel_rows = h->wide ? wide_rows_for(h->C) : PANEL_ROWS;
   h->n_panels = (d.N + h->panel_rows - 1) / h->panel_rows;
   const int P = h->P;
 
@@ -480,20 +481,21 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     h->n_stages = S;
     h->smem_bytes = fixed_smem_bytes(d.K, d.G, h->stage_a, S) + (size_t)S * tile_bytes;
   } else {
-    // sub-panel width: 32 columns while at most 16 sub-panels are needed, else 64
-    h->Cpad = (h->C + 7) & ~7;
-    h->spc = h->Cpad <= 512 ? 4 : 8;
-    h->Kc = 8 * h->spc;
+    // sub-panels: 8 warp steps wide unless 4 steps already give every warp at most one sub-panel
+    const int WR = h->panel_rows, cps = wide_cps(WR);
+    h->Cpad = ((h->C + cps - 1) / cps) * cps;
+    h->spc = h->Cpad <= WIDE_CONSUMER_WARPS * 4 * cps ? 4 : 8;
+    if (WR != 16) h->spc = 8;
+    h->Kc = cps * h->spc;
     h->J = (h->Cpad + h->Kc - 1) / h->Kc;
     h->spw = (h->J + WIDE_CONSUMER_WARPS - 1) / WIDE_CONSUMER_WARPS;
-    if (h->spc == 8 && h->spw < 2) h->spw = 2;
-    if (!pick_wide_kernel(d.family, h->spw, h->spc))
-      return fail(B200GLM_INVALID, "K too large for the wide kernel (K <= 1534)");
-    const size_t fixed = wide_fixed_doubles(h->J, h->Kc, d.G, h->stage_a) * 8;
-    const size_t slot_bytes = (size_t)h->Kc * WIDE_ROWS * 8;
+    if (!pick_wide_kernel(d.family, WR, h->spw, h->spc))
+      return fail(B200GLM_INVALID, "K too large for the wide kernel (K <= 3000)");
+    const size_t fixed = wide_fixed_doubles(WR, h->J, h->Kc, d.G, h->stage_a) * 8;
+    const size_t slot_bytes = (size_t)h->Kc * WR * 8;
     int T = fixed < max_dyn ? (int)((max_dyn - fixed) / (slot_bytes + 16)) : 0;
     if (T > WIDE_MAX_SLOTS) T = WIDE_MAX_SLOTS;
-    if (T < h->J) return fail(B200GLM_INVALID, "one 16-row panel does not fit in shared memory (K too large)");
+    if (T < 2 * h->J) return fail(B200GLM_INVALID, "two row panels do not fit in shared memory (K too large)");
     h->n_stages = T;
     h->smem_bytes = fixed + (size_t)T * (slot_bytes + 16);
   }
@@ -850,6 +852,7 @@ int enqueue_batched(b200glm_handle* h, int n, int mode, int propto, int jacobian
   bp.NCB = NCB;
   bp.NS = NS;
   bp.ldc = sp.ldc;
+  bp.n_lanes = n;
   bp.theta_c = b->theta_c;
   bp.partials = b->partials;
   pick_batched(h->d.family, b->mbh)<<<NCB * NS, BATCH_THREADS, b->smem, b->stream>>>(bp);

@@ -37,6 +37,7 @@ struct BatchedParams {
   int n_stages;
   int NCB, NS;             // chain blocks x row slices = grid
   int ldc;                 // padded number of chain lanes (NCB * 64)
+  int n_lanes;             // active lanes; warp pairs whose 16 chains are all padding do no work
   const double* theta_c;   // [P][ldc] feature-major: the point each lane is evaluated at
   double* partials;        // [NS][NCB][K + 2][64]: rows [0,K) = X^T r, row K = lp-sum, row K+1 = r-sum
 };
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
   constexpr int CB = BATCH_CB;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int K = p.K, C = p.C, S = p.n_stages, NS = p.NS, NCB = p.NCB;
-  const int K4 = (K + 3) & ~3;
+  const int K4 = (K + 3) & ~3, Kfull = K & ~3;
   const int tile_doubles = C * 32;
   double* tiles = reinterpret_cast<double*>(smem_raw);            // S * C * 32
   double* sB = tiles + (size_t)S * tile_doubles;                  // K4 x 64, column index XOR-swizzled
@@ -78,10 +79,13 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
   const int cb = blockIdx.x % NCB, sl = blockIdx.x / NCB;
   const long long n_panels = p.n_panels;
 
+  // pairs of this chain block that hold at least one real chain (the last block of a small batch is
+  // mostly padding: the straggler batches of a lock-step NUTS run have a handful of lanes)
+  const int act_pairs = min(4, (p.n_lanes - cb * CB + 15) / 16);
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 8);
+      mbar_init(&empty_bar[s], 2 * act_pairs);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -116,6 +120,7 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
 
   // ===================== DMMA warps =====================
   const int mp = warp & 1, nq = warp >> 1;
+  if (nq >= act_pairs) return;   // nothing but padding lanes (never warp 0: pair 0 always has lane 0)
   const int l4 = lane & 3, lq = lane >> 2;
   const int sw = l4 << 2;
   double* sRp = sR + nq * (32 * 16);
@@ -143,12 +148,29 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
     const double* tile = tiles + (size_t)s * tile_doubles;
 
     // ---- GEMM1: E (16 rows of this warp x 16 chains of this pair) ----
+    // two accumulator sets (even / odd k4 steps): 8 independent DMMA chains per warp instead of 4
     double e[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+    double f[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
     const double* ta = tile + l4 * 32;
+    int k0 = 0;
 #pragma unroll 2
-    for (int k0 = 0; k0 < K4; k0 += 4) {
+    for (; k0 + 8 <= Kfull; k0 += 8) {
+      const double a0 = ta[k0 * 32 + ra0], a1 = ta[k0 * 32 + ra1];
+      const double b0 = tb[k0 * CB + cb0], b1 = tb[k0 * CB + cb1];
+      const double c0 = ta[(k0 + 4) * 32 + ra0], c1 = ta[(k0 + 4) * 32 + ra1];
+      const double d0 = tb[(k0 + 4) * CB + cb0], d1 = tb[(k0 + 4) * CB + cb1];
+      dmma884(e[0][0], a0, b0);
+      dmma884(e[0][1], a0, b1);
+      dmma884(e[1][0], a1, b0);
+      dmma884(e[1][1], a1, b1);
+      dmma884(f[0][0], c0, d0);
+      dmma884(f[0][1], c0, d1);
+      dmma884(f[1][0], c1, d0);
+      dmma884(f[1][1], c1, d1);
+    }
+    for (; k0 < K4; k0 += 4) {  // at most one full step and one partial step (K % 4 != 0)
       double a0 = ta[k0 * 32 + ra0], a1 = ta[k0 * 32 + ra1];
-      if (k0 + l4 >= K) {  // K not a multiple of 4: the y column must not leak into eta
+      if (k0 + l4 >= K) {  // the y column must not leak into eta
         a0 = 0.0;
         a1 = 0.0;
       }
@@ -158,6 +180,13 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
       dmma884(e[1][0], a1, b0);
       dmma884(e[1][1], a1, b1);
     }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) {
+        e[mi][ni][0] += f[mi][ni][0];
+        e[mi][ni][1] += f[mi][ni][1];
+      }
 
     // ---- link: C-fragment (row = lq, chains 2*l4 + {0,1}) -> residual patch of the pair ----
     pair_bar_sync(1 + nq);  // the partner has finished reading the previous patch

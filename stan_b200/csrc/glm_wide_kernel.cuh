@@ -3,36 +3,41 @@
 // registers / a CTA's shared memory.  Same arithmetic and same tail as glm_fused_kernel
 // (glm_kernels.cuh); what changes is how a row panel is spread over the CTA.
 //
-// Data layout in HBM ("wide row-panel format", relayout_kernel with PR = 16, no swizzle):
-//   rows are cut into panels of 16; panel n is one contiguous block of Cpad columns x 16 doubles
-//   (column-major inside the panel, Cpad = C rounded up to 8, padding columns are zero).
-//   A panel is streamed as J sub-panels of KC columns (KC*128 bytes = one cp.async.bulk each).
+// Data layout in HBM ("wide row-panel format", relayout_kernel with PR = WR, no swizzle):
+//   rows are cut into panels of WR = 16, 8 or 4 rows (wide_rows_for: the panel is kept near 64 KB);
+//   panel n is one contiguous block of Cpad columns x WR doubles (column-major inside the panel,
+//   Cpad = C rounded up to the columns a warp covers per step, padding columns are zero).
+//   A panel is streamed as J <= 16 sub-panels of KC columns (one cp.async.bulk of 4-8 KB each).
+//   Why ~64 KB panels: with 16 rows at K = 1000 (128 KB resident, 80 KB look-ahead) loads could only be
+//   issued in bursts while P2 freed slots and HBM idled one latency per panel (ncu: 57 % DRAM, 71 % of
+//   the copy roof); with the ring holding >= 2 panels the stream is continuous (89 %).
 //
 // CTA (persistent, one per SM) = 8 consumer warps + 1 TMA producer warp + 1 link warp.
-//   The shared-memory ring has T >= J sub-panel slots: one whole row panel stays resident between
-//   its eta pass and its X^T r pass, the other E = T - J slots hold the head of the NEXT panel.
+//   The shared-memory ring has T >= 2J sub-panel slots: the panel between its eta pass and its X^T r
+//   pass stays resident, the rest holds the following panel(s).
 //   consumer warp w owns sub-panels j = w, w+8, ... of every row panel (so it owns those columns'
 //   gradient accumulators outright: no cross-warp reduction of the gradient):
-//     P1(n, j): partial eta for the 16 rows over the sub-panel's columns
+//     P1(n, j): partial eta for the panel's rows over the sub-panel's columns
 //     -> 8 partials/row meet in smem, ETA barrier -> link warp adds them in fixed order, applies
 //        the link function (lp_i, r_i), R barrier ->
 //     P2(n, j): acc[col] += X[row][col] * r[row] from the SAME smem bytes, then the slot is released.
-//   While the link warp works, the consumers already run P1 on the prefetched head of panel n+1,
-//   so the link latency (fp64 exp/log1p chain) is hidden.
-//   Lane mapping (both passes): lane = (rq = lane & 3, cq = lane >> 2) handles column cq + 8t and the
-//   four rows {2rq, 2rq+1, 2rq+8, 2rq+9} with two LDS.128; odd cq swaps the order of the two
-//   loads, which makes every quarter-warp cover all 32 banks (conflict free without a swizzle).
+//   Software pipeline: a consumer publishes eta(n+1) BEFORE it waits for r(n), so the link warp's
+//   fp64 exp/log1p dependency chain for panel n+1 overlaps P2(n); eta / r buffers and the two named
+//   barriers are double-buffered by panel parity.
+//   Lane mapping (both passes): lane = (rq, cq) handles column cq + CPS*t and four rows
+//   {2rq, 2rq+1, 2(rq+LPC), 2(rq+LPC)+1} with two LDS.128; half of the columns swap the order of the
+//   two loads, which makes every quarter-warp cover all 32 banks (conflict free without a swizzle).
 #pragma once
 
 #include "glm_kernels.cuh"
 
 namespace b200glm {
 
-constexpr int WIDE_ROWS = 16;
 constexpr int WIDE_CONSUMER_WARPS = 8;
 constexpr int WIDE_THREADS = (WIDE_CONSUMER_WARPS + 2) * 32;
 constexpr int WIDE_MAX_SLOTS = 96;
-enum { WIDE_BAR_ETA = 1, WIDE_BAR_R = 2 };
+// named barriers: ETA / R, double-buffered by panel parity
+enum { WIDE_BAR_ETA = 1, WIDE_BAR_R = 3 };
 constexpr int WIDE_BAR_COUNT = (WIDE_CONSUMER_WARPS + 1) * 32;  // consumers + link warp
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
@@ -42,14 +47,20 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-// bytes of dynamic shared memory besides the ring slots and their barriers
-__host__ __device__ inline size_t wide_fixed_doubles(int J, int KC, int G, int stage_a) {
-  return (size_t)J * KC + WIDE_CONSUMER_WARPS * WIDE_ROWS + WIDE_ROWS + (stage_a ? ((G + 1) & ~1) : 0);
+// rows per panel: the panel (WR x Cpad doubles) should be about 64 KB so that the ring holds the
+// resident panel plus at least one more in flight, and long enough (>= 1 us of HBM time) for the link
+// warp's fp64 exp/log1p chain to stay off the critical path
+__host__ __device__ inline int wide_rows_for(int C) { return C <= 512 ? 16 : (C <= 1024 ? 8 : 4); }
+__host__ __device__ inline int wide_cps(int WR) { return 32 / (WR / 4); }
+
+// doubles of dynamic shared memory besides the ring slots and their barriers
+__host__ __device__ inline size_t wide_fixed_doubles(int WR, int J, int KC, int G, int stage_a) {
+  return (size_t)J * KC + 2 * WIDE_CONSUMER_WARPS * WR + 2 * WR + (stage_a ? ((G + 1) & ~1) : 0);
 }
 
-template <int FAMILY, int SPW, int SPC>
+template <int FAMILY, int WR, int SPW, int SPC>
 __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelParams p) {
-  constexpr int WR = WIDE_ROWS, LPC = WR / 4, CPS = 32 / LPC;  // lanes per column, columns per step
+  constexpr int LPC = WR / 4, CPS = 32 / LPC;                  // lanes per column, columns per warp step
   constexpr int KC = SPC * CPS;                                // sub-panel width (columns)
   constexpr int SLOT = KC * WR;                                // doubles per ring slot
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -57,9 +68,9 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelP
 
   double* ring = reinterpret_cast<double*>(smem_raw);            // T * SLOT
   double* sbeta = ring + (size_t)T * SLOT;                       // J * KC (zero beyond K)
-  double* eta_part = sbeta + J * KC;                             // 8 * WR
-  double* r_sh = eta_part + WIDE_CONSUMER_WARPS * WR;            // WR
-  double* sa = r_sh + WR;                                        // G (optional)
+  double* eta_part = sbeta + J * KC;                             // 2 parities x 8 warps x WR
+  double* r_sh = eta_part + 2 * WIDE_CONSUMER_WARPS * WR;        // 2 parities x WR
+  double* sa = r_sh + 2 * WR;                                    // G (optional)
   double* after_a = sa + (p.stage_a_in_smem ? ((G + 1) & ~1) : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(after_a);     // T
   uint64_t* empty_bar = full_bar + T;                            // T
@@ -95,19 +106,18 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelP
 
   const long long n_panels = p.n_panels;
   const long long n_my = (long long)blockIdx.x < n_panels ? (n_panels - blockIdx.x + grid - 1) / grid : 0;
-  const int E = T - J;  // look-ahead slots: sub-panels j < E of panel n+1 can land before P2(n) starts
   double* my_part = p.partials + (size_t)blockIdx.x * p.pstride;
 
   if (warp < WIDE_CONSUMER_WARPS) {
     // =============================== consumers ===============================
     const int rq = lane & (LPC - 1), cq = lane / LPC;
-    const int swap = cq & 1;
+    const int swap = (cq / (4 / LPC)) & 1;  // which half of the 128-byte bank window the first load takes
     const int chunkA = swap ? rq + LPC : rq, chunkB = swap ? rq : rq + LPC;
     const int offA = 2 * chunkA, offB = 2 * chunkB;
 
-    int slot[SPW];
+    int slot[SPW];      // ring slot / phase parity of this warp's sub-panels of the panel P2 works on
     uint32_t par[SPW];
-    int steps[SPW];  // 0 = this warp has no such sub-panel
+    int steps[SPW];     // 0 = this warp has no such sub-panel
 #pragma unroll
     for (int i = 0; i < SPW; ++i) {
       const int j = warp + WIDE_CONSUMER_WARPS * i;
@@ -119,75 +129,69 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelP
     double acc[SPW * SPC];
 #pragma unroll
     for (int a = 0; a < SPW * SPC; ++a) acc[a] = 0.0;
-    double eA0 = 0.0, eA1 = 0.0, eB0 = 0.0, eB1 = 0.0;
 
-    auto pass1 = [&](int i, int sl, uint32_t pr) {
-      mbar_wait(&full_bar[sl], pr);
-      const double* tile = ring + (size_t)sl * SLOT + cq * WR;
-      const double* bj = sbeta + (warp + WIDE_CONSUMER_WARPS * i) * KC + cq;
-#pragma unroll
-      for (int t = 0; t < SPC; ++t) {
-        if (t < steps[i]) {
-          const double b = bj[CPS * t];
-          const double2 xa = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offA);
-          const double2 xb = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offB);
-          eA0 = fma(xa.x, b, eA0);
-          eA1 = fma(xa.y, b, eA1);
-          eB0 = fma(xb.x, b, eB0);
-          eB1 = fma(xb.y, b, eB1);
-        }
-      }
-    };
-
-    for (long long n = 0; n < n_my; ++n) {
-      // ---- P1 on the sub-panels of panel n that were not already done early ----
+    // P1 of one whole panel (this warp's sub-panels, at ring position `ahead` panels past slot[]),
+    // then publish the warp's partial eta of the panel's rows into parity buffer `buf`
+    auto pass1_publish = [&](int ahead, int buf) {
+      double eA0 = 0.0, eA1 = 0.0, eB0 = 0.0, eB1 = 0.0;
 #pragma unroll
       for (int i = 0; i < SPW; ++i) {
-        const bool early = (warp + WIDE_CONSUMER_WARPS * i) < E;
-        if (steps[i] > 0 && (n == 0 || !early)) pass1(i, slot[i], par[i]);
-      }
-      // ---- publish this warp's partial eta of the 16 rows ----
-      {
-        double lo0 = swap ? eB0 : eA0, lo1 = swap ? eB1 : eA1;  // rows 2rq, 2rq+1
-        double hi0 = swap ? eA0 : eB0, hi1 = swap ? eA1 : eB1;  // rows 2rq+8, 2rq+9
-#pragma unroll
-        for (int o = LPC; o < 32; o <<= 1) {
-          lo0 += __shfl_xor_sync(0xffffffffu, lo0, o);
-          lo1 += __shfl_xor_sync(0xffffffffu, lo1, o);
-          hi0 += __shfl_xor_sync(0xffffffffu, hi0, o);
-          hi1 += __shfl_xor_sync(0xffffffffu, hi1, o);
-        }
-        if (cq == 0) {
-          double* ep = eta_part + warp * WR;
-          *reinterpret_cast<double2*>(ep + 2 * rq) = make_double2(lo0, lo1);
-          *reinterpret_cast<double2*>(ep + 2 * (rq + LPC)) = make_double2(hi0, hi1);
-        }
-        eA0 = eA1 = eB0 = eB1 = 0.0;
-      }
-      __threadfence_block();
-      named_bar_arrive(WIDE_BAR_ETA, WIDE_BAR_COUNT);
-
-      // ---- while the link warp works: P1 on the prefetched head of panel n+1 ----
-      if (n + 1 < n_my) {
-#pragma unroll
-        for (int i = 0; i < SPW; ++i) {
-          const bool early = (warp + WIDE_CONSUMER_WARPS * i) < E;
-          if (steps[i] > 0 && early) {
-            int ns = slot[i] + J;
-            uint32_t np = par[i];
-            if (ns >= T) {
-              ns -= T;
-              np ^= 1u;
+        if (steps[i] > 0) {
+          int sl = slot[i];
+          uint32_t pr = par[i];
+          if (ahead) {
+            sl += J;
+            if (sl >= T) {
+              sl -= T;
+              pr ^= 1u;
             }
-            pass1(i, ns, np);
+          }
+          mbar_wait(&full_bar[sl], pr);
+          const double* tile = ring + (size_t)sl * SLOT + cq * WR;
+          const double* bj = sbeta + (warp + WIDE_CONSUMER_WARPS * i) * KC + cq;
+#pragma unroll
+          for (int t = 0; t < SPC; ++t) {
+            if (t < steps[i]) {
+              const double b = bj[CPS * t];
+              const double2 xa = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offA);
+              const double2 xb = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offB);
+              eA0 = fma(xa.x, b, eA0);
+              eA1 = fma(xa.y, b, eA1);
+              eB0 = fma(xb.x, b, eB0);
+              eB1 = fma(xb.y, b, eB1);
+            }
           }
         }
       }
+      double lo0 = swap ? eB0 : eA0, lo1 = swap ? eB1 : eA1;  // rows 2rq, 2rq+1
+      double hi0 = swap ? eA0 : eB0, hi1 = swap ? eA1 : eB1;  // rows 2(rq+LPC), 2(rq+LPC)+1
+#pragma unroll
+      for (int o = LPC; o < 32; o <<= 1) {
+        lo0 += __shfl_xor_sync(0xffffffffu, lo0, o);
+        lo1 += __shfl_xor_sync(0xffffffffu, lo1, o);
+        hi0 += __shfl_xor_sync(0xffffffffu, hi0, o);
+        hi1 += __shfl_xor_sync(0xffffffffu, hi1, o);
+      }
+      if (cq == 0) {
+        double* ep = eta_part + (buf * WIDE_CONSUMER_WARPS + warp) * WR;
+        *reinterpret_cast<double2*>(ep + 2 * rq) = make_double2(lo0, lo1);
+        *reinterpret_cast<double2*>(ep + 2 * (rq + LPC)) = make_double2(hi0, hi1);
+      }
+      __threadfence_block();
+      named_bar_arrive(WIDE_BAR_ETA + buf, WIDE_BAR_COUNT);
+    };
+
+    if (n_my > 0) pass1_publish(0, 0);
+    for (long long n = 0; n < n_my; ++n) {
+      const int buf = (int)(n & 1);
+      // eta of panel n+1 goes to the link warp BEFORE this warp waits for r of panel n: the link
+      // function of n+1 then overlaps P2(n) (the ring holds at least two panels: T >= 2J)
+      if (n + 1 < n_my) pass1_publish(1, buf ^ 1);
 
       // ---- P2: X^T r from the same resident sub-panels ----
-      named_bar_sync(WIDE_BAR_R, WIDE_BAR_COUNT);
-      const double2 rA = *reinterpret_cast<const double2*>(r_sh + offA);
-      const double2 rB = *reinterpret_cast<const double2*>(r_sh + offB);
+      named_bar_sync(WIDE_BAR_R + buf, WIDE_BAR_COUNT);
+      const double2 rA = *reinterpret_cast<const double2*>(r_sh + buf * WR + offA);
+      const double2 rB = *reinterpret_cast<const double2*>(r_sh + buf * WR + offB);
 #pragma unroll
       for (int i = 0; i < SPW; ++i) {
         if (steps[i] > 0) {
@@ -216,14 +220,14 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelP
       }
     }
 
-    // ---- this warp's columns of the CTA partial (sum over the 4 row-lanes of each column) ----
+    // ---- this warp's columns of the CTA partial (sum over the row-lanes of each column) ----
 #pragma unroll
     for (int i = 0; i < SPW; ++i) {
 #pragma unroll
       for (int t = 0; t < SPC; ++t) {
         double v = acc[i * SPC + t];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
+#pragma unroll
+        for (int o = 1; o < LPC; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         const int c = (warp + WIDE_CONSUMER_WARPS * i) * KC + cq + CPS * t;
         if (rq == 0 && c < K) my_part[c] = v;
       }
@@ -260,6 +264,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelP
     if (FAMILY == FAM_NORMAL_ID) inv_sigma = 1.0 / exp(theta_at(P - 1));  // normal_id_glm_lpdf.hpp:117
     double lp_acc = 0.0, r_acc = 0.0;
     for (long long n = 0; n < n_my; ++n) {
+      const int buf = (int)(n & 1);
       const long long pi = blockIdx.x + n * grid;
       mbar_wait(&full_bar[slot_y], par_y);
       const double y = ring[(size_t)slot_y * SLOT + coly * WR + r];
@@ -270,10 +275,10 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelP
         const bool gok = gi >= 0 && gi < G;
         off = p.stage_a_in_smem ? sa[gok ? gi : 0] : theta_at(2 + (gok ? gi : 0));
       }
-      named_bar_sync(WIDE_BAR_ETA, WIDE_BAR_COUNT);
+      named_bar_sync(WIDE_BAR_ETA + buf, WIDE_BAR_COUNT);
       double eta = 0.0;
 #pragma unroll
-      for (int w = 0; w < WIDE_CONSUMER_WARPS; ++w) eta += eta_part[w * WR + r];
+      for (int w = 0; w < WIDE_CONSUMER_WARPS; ++w) eta += eta_part[(buf * WIDE_CONSUMER_WARPS + w) * WR + r];
       eta += off;
       double lp_i, r_i;
       link<FAMILY>(eta, y, inv_sigma, lp_i, r_i);
@@ -282,13 +287,13 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelP
         r_i = 0.0;
       }
       if (lane < WR) {
-        r_sh[lane] = r_i;
+        r_sh[buf * WR + lane] = r_i;
         if (G > 0) p.r_out[pi * WR + lane] = r_i;
         lp_acc += lp_i;
         r_acc += r_i;
       }
       __threadfence_block();
-      named_bar_arrive(WIDE_BAR_R, WIDE_BAR_COUNT);
+      named_bar_arrive(WIDE_BAR_R + buf, WIDE_BAR_COUNT);
       slot_y += J;
       if (slot_y >= T) {
         slot_y -= T;

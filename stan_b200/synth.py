@@ -84,3 +84,41 @@ def make_logistic_shard(torch, dev, N_total, K, rank=0, world=1, seed=SEED, bloc
         y[lo - r0:hi - r0] = (ub[lo - b0:hi - b0] < torch.sigmoid(eta)).to(torch.int32)
         del xb, ub
     return X, y, r0, r1
+
+
+def make_shard(torch, dev, family, N_total, K, G=0, rank=0, world=1, seed=SEED, block=1_000_000, alpha_true=0.3):
+    """Rows shard_rows(N_total, rank, world) of the synthetic problem for any family / grouping
+    (SURVEY 8d generator), on `dev`: returns X (K, n) fp64 = column-major N x K, y (int32 or fp64),
+    group (int32, 1-based, or None), r0, r1.  Per-block seeds as in make_logistic_shard."""
+    if family == "bernoulli_logit" and G == 0:
+        X, y, r0, r1 = make_logistic_shard(torch, dev, N_total, K, rank, world, seed, block, alpha_true)
+        return X, y, None, r0, r1
+    r0, r1 = shard_rows(N_total, rank, world)
+    n = r1 - r0
+    g = torch.Generator(device=dev)
+    beta = torch.from_numpy(_rng(seed, 1).standard_normal(K) / np.sqrt(max(K, 1))).to(dev)
+    a_true = torch.from_numpy(0.5 * _rng(seed, 2).standard_normal(max(G, 1))).to(dev)
+    X = torch.empty((K, n), device=dev, dtype=torch.float64)
+    y = torch.empty(n, device=dev, dtype=torch.float64 if family == "normal_id" else torch.int32)
+    group = torch.empty(n, device=dev, dtype=torch.int32) if G else None
+    for b0 in range((r0 // block) * block, r1, block):
+        g.manual_seed(seed * 1000 + b0 // block)
+        xb = torch.randn((K, block), generator=g, device=dev, dtype=torch.float64)
+        ub = torch.rand(block, generator=g, device=dev, dtype=torch.float64)
+        gb = torch.randint(1, max(G, 1) + 1, (block,), generator=g, device=dev, dtype=torch.int32)
+        lo, hi = max(b0, r0), min(b0 + block, r1)
+        X[:, lo - r0:hi - r0] = xb[:, lo - b0:hi - b0]
+        # y is drawn for the WHOLE block and then sliced, so every sharding sees the same random stream
+        eta = beta @ xb
+        eta = eta + (a_true[(gb - 1).long()] if G else alpha_true)
+        if family == "bernoulli_logit":
+            yb = (ub < torch.sigmoid(eta)).to(torch.int32)
+        elif family == "poisson_log":
+            yb = torch.poisson(torch.exp(torch.clamp(0.5 * eta + 0.5, -20, 5)), generator=g).to(torch.int32)
+        else:
+            yb = eta + torch.randn(block, generator=g, device=dev, dtype=torch.float64)
+        y[lo - r0:hi - r0] = yb[lo - b0:hi - b0]
+        if G:
+            group[lo - r0:hi - r0] = gb[lo - b0:hi - b0]
+        del xb, ub, gb
+    return X, y, group, r0, r1

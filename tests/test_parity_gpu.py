@@ -87,13 +87,14 @@ def test_cuda_matches_oracle_live(fam, N, K, G):
 WIDE_SHAPES = [
     # family, N, K, G, flags -- the wide-matrix kernel (16-row panels split over the CTA): K > 256 selects it,
     # flags=1 (B200GLM_FLAG_FORCE_WIDE) runs it on narrow shapes too (sub-panel/warp-ownership edge cases)
-    ("bernoulli_logit", 3_000, 300, 0, 0),       # KC=32, J=10
-    ("bernoulli_logit", 20_011, 1000, 0, 0),     # config 5's K: KC=64, J=16
-    ("normal_id", 5_000, 511, 0, 0),             # Cpad = 512: last KC=32 shape, y in the last column
-    ("normal_id", 5_000, 512, 0, 0),             # first KC=64 shape
+    ("bernoulli_logit", 3_000, 300, 0, 0),       # KC=64, J=5
+    ("bernoulli_logit", 20_011, 1000, 0, 0),     # config 5's K: KC=128, J=8
+    ("normal_id", 5_000, 511, 0, 0),             # Cpad = 512: last KC=64 shape, y in the last column
+    ("normal_id", 5_000, 512, 0, 0),             # first KC=128 shape
     ("poisson_log", 8_000, 520, 100, 0),         # groups; y and group id in the last sub-panel
     ("poisson_log", 4_000, 639, 50, 0),          # K+1 = 640: y and group id land in DIFFERENT sub-panels
-    ("bernoulli_logit", 2_500, 1400, 0, 0),      # SPW = 3
+    ("bernoulli_logit", 2_500, 1400, 0, 0),      # two sub-panels per warp
+    ("normal_id", 1_201, 2_500, 0, 0),           # three sub-panels per warp
     ("bernoulli_logit", 10_000, 20, 0, 1),
     ("bernoulli_logit", 4_097, 13, 7, 1),
     ("poisson_log", 5_000, 8, 3000, 1),          # a[] read from global memory

@@ -82,3 +82,16 @@ def test_row_sharded_gradient_world2_gloo():
     lp_ref, g_ref = PortOracle("bernoulli_logit", Xf, yf).log_prob_grad(th)
     assert abs(lp - lp_ref) / abs(lp_ref) < 1e-13
     assert np.max(np.abs(g - g_ref)) / np.max(np.abs(g_ref)) < 1e-13
+
+
+def test_make_shard_is_sharding_invariant_for_every_family():
+    """bench.py --config 4/5 data: any row sharding regenerates the same global X, y, group."""
+    from stan_b200.synth import make_shard
+    dev = torch.device("cpu")
+    for fam, G in (("poisson_log", 7), ("normal_id", 0), ("bernoulli_logit", 3)):
+        X, y, g, _, _ = make_shard(torch, dev, fam, 2500, 5, G, 0, 1, block=1000)
+        parts = [make_shard(torch, dev, fam, 2500, 5, G, r, 3, block=1000) for r in range(3)]
+        assert torch.equal(X, torch.cat([p[0] for p in parts], 1))
+        assert torch.equal(y, torch.cat([p[1] for p in parts]))
+        if G:
+            assert torch.equal(g, torch.cat([p[2] for p in parts])) and 1 <= int(g.min()) and int(g.max()) <= G
