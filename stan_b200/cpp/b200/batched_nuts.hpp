@@ -31,7 +31,13 @@ class chain_batcher final : public glm_model::batch_hook {
  public:
   chain_batcher(const glm_model& m, int n_chains)
       : m_(m), P_(m.num_params_r()), n_(n_chains), n_active_(n_chains), req_(n_chains), res_(n_chains) {
-    m_.check(b200glm_batch_reserve(m_.handle(), n_chains));
+    // shapes the DMMA kernel does not cover (K > 208, group intercepts) are still served in lock-step,
+    // lane by lane, by the single-chain kernels
+    const int rc = b200glm_batch_reserve(m_.handle(), n_chains);
+    if (rc == B200GLM_INVALID)
+      dmma_ok_ = false;
+    else
+      m_.check(rc);
     const size_t np = static_cast<size_t>(n_) * P_;
     for (auto* v : {&uq_, &up_, &ug_, &uim_, &oq_, &op_, &og_})
       v->resize(np);
@@ -182,7 +188,7 @@ class chain_batcher final : public glm_model::batch_hook {
     if (n == 0)
       return;
     b200glm_handle* h = m_.handle();
-    if (n <= kSingleLaneThreshold) {
+    if (!dmma_ok_ || n <= kSingleLaneThreshold) {
       // a straggler or two: the single-chain kernel (one HBM-bound launch each) beats a 64-chain DMMA block
       for (int i = 0; i < n; ++i) {
         const int c = lanes_[i];
@@ -250,6 +256,7 @@ class chain_batcher final : public glm_model::batch_hook {
   std::vector<double> uq_, up_, ug_, uim_, uV_, oq_, op_, og_, oV_, eps_;
   std::vector<int32_t> lanes_, up_lanes_, status_;
   long n_batches_ = 0, n_lanes_ = 0, n_single_ = 0;
+  bool dmma_ok_ = true;
 };
 
 // Same contract and argument list as the reference's multi-chain

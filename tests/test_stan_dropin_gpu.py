@@ -169,3 +169,22 @@ def test_batched_driver_batches_chains(batched_pair):
     assert bat["lanes"] >= n_eval
     # lock-step: far fewer launches than evaluations (16 chains, trees of similar depth)
     assert bat["batches"] < 0.25 * bat["lanes"], (bat["batches"], bat["lanes"])
+
+
+def test_batched_driver_serves_shapes_without_dmma_kernel():
+    """Group intercepts are outside the DMMA kernel's scope (G == 0 only): the driver still runs the chains
+    in lock-step and serves them lane by lane with the single-chain kernel; posterior == reference CPU."""
+    Ref = ref_oracle()
+    d = make_glm_data("poisson_log", 3_000, 4, 5)
+    m = stan_service.StanGLM("poisson_log", d["X"], d["y"], d["group"], 5)
+    kw = dict(num_chains=4, seed=7, num_warmup=200, num_samples=200, delta=0.8)
+    bat = m.nuts_batched(**kw)
+    m.close()
+    ref = Ref("poisson_log", d["X"], d["y"], d["group"], 5).nuts(num_threads=4, **kw)
+    a, b = bat["warmup_draws"][:, :3, :], ref["warmup_draws"][:, :3, :]
+    assert np.array_equal(a[:, :, 3:6], b[:, :, 3:6])
+    zs = []
+    for k in range(bat["draws"].shape[2] - 7):
+        x, y = bat["draws"][:, :, 7 + k].T, ref["draws"][:, :, 7 + k].T
+        zs.append(abs(x.mean() - y.mean()) / np.hypot(Ref.mcse_mean(x), Ref.mcse_mean(y)))
+    assert max(zs) < 4.5, zs
