@@ -88,6 +88,19 @@ int b200glm_log_prob_grad(b200glm_handle* h, int32_t slot, const double* theta, 
 int b200glm_log_prob(b200glm_handle* h, int32_t slot, const double* theta, int32_t propto,
                      int32_t jacobian, double* lp);
 
+/* Function-level entry: the GLM term ALONE (no priors, no Jacobian), the slot where the reference's OpenCL
+ * backend plugs in -- an overload of the density selected by argument type that returns
+ * ops_partials.build(logp) (SM/opencl/prim/bernoulli_logit_glm_lpmf.hpp:52-58, :105-138).  Value and
+ * partials of {bernoulli_logit,poisson_log,normal_id}_glm_lp*f<propto>(y, X, alpha, beta [, sigma]) for the
+ * (y, X [, group]) the handle holds; alpha: 1 value (G == 0) or G values (alpha = a[group]).
+ * operands_are_var = 0 with propto = 1 returns 0 as the reference does (all-constant, include_summand);
+ * sigma_is_var only matters for normal_id under propto (-N log sigma kept iff sigma is an autodiff
+ * variable, normal_id_glm_lpdf.hpp:205-212).  d_alpha / d_beta / d_sigma may be NULL.
+ * The C++ binding (stan::math overloads on b200::glm_data views) is stan_b200/cpp/b200/glm_functions.hpp. */
+int b200glm_glm_lpmf(b200glm_handle* h, int32_t slot, int32_t propto, int32_t operands_are_var,
+                     int32_t sigma_is_var, const double* alpha, const double* beta, double sigma,
+                     double* logp, double* d_alpha, double* d_beta, double* d_sigma);
+
 /* Device-resident leapfrog (replaces expl_leapfrog::evolve, ST/mcmc/hmc/integrators/
  * base_leapfrog.hpp:17-22 + expl_leapfrog.hpp:16-32, and the update_potential_gradient it calls,
  * base_hamiltonian.hpp:61-70).  set_state uploads z = (q, p, g, V) for a slot;

@@ -180,6 +180,31 @@ class RefOracle:
             cls._lib, cls._isa = lib, isa
         return cls._lib
 
+    @classmethod
+    def glm_function(cls, family, X, y, alpha, beta, sigma=1.0, group=None, G=0, propto=True, operands_are_var=True,
+                     sigma_is_var=True):
+        """The bare reference density stan::math::<family>_glm_lp*f<propto>(y, X, alpha | a[group], beta [, sigma])
+        and its adjoints (ref_glm_function in oracle/ref/ref_oracle.cpp): returns lp, d_alpha, d_beta, d_sigma."""
+        L = cls.lib()
+        fam = FAMILY[family] if isinstance(family, str) else int(family)
+        X = np.asfortranarray(X, dtype=np.float64)
+        N, K = X.shape
+        y = np.ascontiguousarray(y, dtype=np.float64 if fam == 2 else np.int32)
+        a = np.ascontiguousarray(np.atleast_1d(alpha), dtype=np.float64)
+        b = np.ascontiguousarray(beta, dtype=np.float64)
+        grp = None if group is None else np.ascontiguousarray(group, dtype=np.int32)
+        lp, ds, err = C.c_double(), C.c_double(), C.create_string_buffer(1024)
+        da, db = np.zeros_like(a), np.zeros(max(K, 1))
+        ip = C.POINTER(C.c_int)
+        rc = L.ref_glm_function(
+            C.c_int(fam), C.c_int(int(propto)), C.c_int(int(operands_are_var)), C.c_int(int(sigma_is_var)),
+            C.c_longlong(N), C.c_int(K), _dp(X), y.ctypes.data_as(ip) if fam != 2 else None,
+            _dp(y) if fam == 2 else None, grp.ctypes.data_as(ip) if grp is not None else None, C.c_int(int(G)),
+            _dp(a), _dp(b), C.c_double(float(sigma)), C.byref(lp), _dp(da), _dp(db), C.byref(ds), err, 1024)
+        if rc:
+            raise OracleError(rc, err.value.decode())
+        return lp.value, da, db[:K], ds.value
+
     def __init__(self, family, X, y, group=None, G=0, **priors):
         self.L = self.lib()
         self.isa = self._isa

@@ -269,6 +269,71 @@ int ref_glm_nuts(void* h, int num_chains, unsigned seed, unsigned init_chain_id,
 }
 
 // draws: column-major n_draws x n_chains (one parameter)
+// The bare reference GLM densities (function level), for the parity test of b200glm_glm_lpmf:
+//   stan::math::{bernoulli_logit,poisson_log,normal_id}_glm_lp*f<propto>(y, X, alpha | a[group], beta [, sigma])
+// with alpha/beta (and sigma iff sigma_is_var) as reverse-mode vars when operands_are_var, else doubles.
+int ref_glm_function(int family, int propto, int operands_are_var, int sigma_is_var, long long N, int K,
+                     const double* X, const int* y_int, const double* y_real, const int* group, int G,
+                     const double* alpha, const double* beta, double sigma, double* logp, double* d_alpha,
+                     double* d_beta, double* d_sigma, char* err, int errlen) {
+  return guarded(err, errlen, [&] {
+    using stan::math::var;
+    Eigen::Map<const Eigen::MatrixXd> Xm(X, N, K);
+    Eigen::MatrixXd Xc = Xm;
+    std::vector<int> yi(y_int ? y_int : nullptr, y_int ? y_int + N : nullptr);
+    Eigen::VectorXd yr = y_real ? Eigen::VectorXd(Eigen::Map<const Eigen::VectorXd>(y_real, N)) : Eigen::VectorXd();
+    std::vector<int> grp(group ? group : nullptr, group ? group + N : nullptr);
+    const int nA = G > 0 ? G : 1;
+    auto run = [&](auto tag_alpha, auto tag_sigma) {
+      using TA = decltype(tag_alpha);
+      using TS = decltype(tag_sigma);
+      stan::math::nested_rev_autodiff nested;
+      Eigen::Matrix<TA, -1, 1> a(nA), b(K);
+      for (int g = 0; g < nA; ++g) a[g] = alpha[g];
+      for (int k = 0; k < K; ++k) b[k] = beta[k];
+      TS sg = sigma;
+      auto call = [&](const auto& intercept) -> stan::return_type_t<TA, TS> {
+        if (family == 0)
+          return propto ? stan::math::bernoulli_logit_glm_lpmf<true>(yi, Xc, intercept, b)
+                        : stan::math::bernoulli_logit_glm_lpmf<false>(yi, Xc, intercept, b);
+        if (family == 1)
+          return propto ? stan::math::poisson_log_glm_lpmf<true>(yi, Xc, intercept, b)
+                        : stan::math::poisson_log_glm_lpmf<false>(yi, Xc, intercept, b);
+        return propto ? stan::math::normal_id_glm_lpdf<true>(yr, Xc, intercept, b, sg)
+                      : stan::math::normal_id_glm_lpdf<false>(yr, Xc, intercept, b, sg);
+      };
+      stan::return_type_t<TA, TS> lp = 0;
+      if (G > 0) {
+        Eigen::Matrix<TA, -1, 1> an(N);
+        for (long long i = 0; i < N; ++i) an[i] = a[grp[i] - 1];
+        lp = call(an);
+      } else {
+        TA a0 = a[0];
+        lp = call(a0);
+        a[0] = a0;
+      }
+      *logp = stan::math::value_of(lp);
+      if constexpr (std::is_same<TA, var>::value) {
+        lp.grad();
+        for (int g = 0; g < nA; ++g) d_alpha[g] = a[g].adj();
+        for (int k = 0; k < K; ++k) d_beta[k] = b[k].adj();
+        if constexpr (std::is_same<TS, var>::value) *d_sigma = sg.adj();
+      }
+    };
+    for (int g = 0; g < nA; ++g) d_alpha[g] = 0;
+    for (int k = 0; k < K; ++k) d_beta[k] = 0;
+    *d_sigma = 0;
+    if (operands_are_var) {
+      if (sigma_is_var && family == 2)
+        run(var(0), var(0));
+      else
+        run(var(0), double(0));
+    } else {
+      run(double(0), double(0));
+    }
+  });
+}
+
 double ref_ess(const double* d, int n_draws, int n_chains) {
   Eigen::MatrixXd m = Eigen::Map<const Eigen::MatrixXd>(d, n_draws, n_chains);
   return stan::analyze::ess(m);

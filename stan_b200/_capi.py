@@ -16,6 +16,7 @@ SYMBOLS = [
     "b200glm_batch_reserve", "b200glm_log_prob_grad_batched", "b200glm_set_state_batched",
     "b200glm_leapfrog_batched", "b200glm_leapfrog_batched_async", "b200glm_batch_sync", "b200glm_batch_stream",
     "b200glm_peer_export", "b200glm_peer_connect", "b200glm_lgamma_sum_local", "b200glm_set_lgamma_sum_total",
+    "b200glm_glm_lpmf",
     "b200glm_launch_count", "b200glm_bytes_per_gradient", "b200glm_last_error", "b200glm_version",
 ]
 
@@ -77,6 +78,8 @@ def lib():
         L.b200glm_lgamma_sum_local.argtypes = [C.c_void_p]
         L.b200glm_lgamma_sum_local.restype = C.c_double
         L.b200glm_set_lgamma_sum_total.argtypes = [C.c_void_p, C.c_double]
+        L.b200glm_glm_lpmf.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, dp, dp, C.c_double,
+                                       dp, dp, dp, dp]
         L.b200glm_launch_count.argtypes = [C.c_void_p]
         L.b200glm_launch_count.restype = C.c_int64
         L.b200glm_bytes_per_gradient.argtypes = [C.c_void_p]

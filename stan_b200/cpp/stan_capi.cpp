@@ -6,11 +6,14 @@
 //                             with Model = b200::glm_model; base_nuts, diag_e_metric, adaptation, writers untouched
 //   b200stan_nuts_batched  -> b200::hmc_nuts_diag_e_adapt_batched (b200/batched_nuts.hpp): the same single-chain service per
 //                             chain, all chains served by one batched DMMA launch per leapfrog step
+//   b200stan_func_eval     -> stan::math::{bernoulli_logit,poisson_log,normal_id}_glm_lp*f overloads on b200::glm_data views
+//                             (b200/glm_functions.hpp): the function-level slot the OpenCL backend uses
 //   b200stan_log_prob_grad -> stan::model::log_prob_grad<propto,jacobian>    (tape path via precomputed_gradients)
 //   b200stan_gradient      -> stan::model::gradient                          (explicit specialisation, no tape)
 //   b200stan_leapfrog      -> stan::mcmc::expl_leapfrog<diag_e_metric<...>>::evolve (device-resident specialisation)
 #include <b200/stan_glm_model.hpp>
 #include <b200/batched_nuts.hpp>
+#include <b200/glm_functions.hpp>
 
 #include <stan/callbacks/interrupt.hpp>
 #include <stan/callbacks/logger.hpp>
@@ -263,6 +266,77 @@ int b200stan_nuts_batched(void* h, int num_chains, unsigned seed, unsigned init_
   return nuts_impl(h, true, num_chains, seed, init_chain_id, init_radius, num_warmup, num_samples, stepsize, max_depth,
                    delta, 0, draws, stepsize_out, inv_metric_out, warm_leapfrogs, wall_seconds, batch_stats, err,
                    errlen);
+}
+
+// ---- function-level binding (b200/glm_functions.hpp) -------------------------------------------------
+void* b200stan_func_create(int family, long long N, int K, const double* X, const void* y, const int* group, int G,
+                           char* err, int errlen) {
+  b200::glm_data* d = nullptr;
+  guarded(err, errlen, [&] { d = new b200::glm_data(family, N, K, X, y, group, G); });
+  return d;
+}
+void b200stan_func_destroy(void* d) { delete static_cast<b200::glm_data*>(d); }
+
+// Calls the stan::math overload with alpha/beta (and sigma iff sigma_is_var) as vars when
+// operands_are_var, runs the reverse sweep on f = scale * glm(...) + 0.5 * sum(beta^2) (so the op is
+// exercised as ONE node of a larger tape) and returns value and adjoints.
+int b200stan_func_eval(void* dv, int propto, int operands_are_var, int sigma_is_var, const double* alpha, int n_alpha,
+                       const double* beta, double sigma, double scale, double* f, double* d_alpha, double* d_beta,
+                       double* d_sigma, char* err, int errlen) {
+  const b200::glm_data& d = *static_cast<b200::glm_data*>(dv);
+  const int K = d.K(), G = d.G();
+  return guarded(err, errlen, [&] {
+    using stan::math::var;
+    auto run = [&](auto tag_op, auto tag_sigma) {
+      using TO = decltype(tag_op);
+      using TS = decltype(tag_sigma);
+      stan::math::nested_rev_autodiff nested;
+      Eigen::Matrix<TO, -1, 1> a(n_alpha), b(K);
+      for (int g = 0; g < n_alpha; ++g) a[g] = alpha[g];
+      for (int k = 0; k < K; ++k) b[k] = beta[k];
+      TS sg = sigma;
+      TO a0 = a[0];
+      stan::return_type_t<TO, TS> lp = 0;
+      auto call = [&](auto pt) {
+        constexpr bool P = decltype(pt)::value;
+        if (d.family() == B200GLM_BERNOULLI_LOGIT)
+          lp = G > 0 ? stan::math::bernoulli_logit_glm_lpmf<P>(d.y(), d.x(), b200::by_group(a), b)
+                     : stan::math::bernoulli_logit_glm_lpmf<P>(d.y(), d.x(), a0, b);
+        else if (d.family() == B200GLM_POISSON_LOG)
+          lp = G > 0 ? stan::math::poisson_log_glm_lpmf<P>(d.y(), d.x(), b200::by_group(a), b)
+                     : stan::math::poisson_log_glm_lpmf<P>(d.y(), d.x(), a0, b);
+        else
+          lp = G > 0 ? stan::math::normal_id_glm_lpdf<P>(d.y(), d.x(), b200::by_group(a), b, sg)
+                     : stan::math::normal_id_glm_lpdf<P>(d.y(), d.x(), a0, b, sg);
+      };
+      if (propto)
+        call(std::true_type());
+      else
+        call(std::false_type());
+      stan::return_type_t<TO, TS> total = scale * lp + 0.5 * stan::math::dot_self(b);
+      *f = stan::math::value_of(total);
+      for (int g = 0; g < n_alpha; ++g) d_alpha[g] = 0;
+      for (int k = 0; k < K; ++k) d_beta[k] = 0;
+      *d_sigma = 0;
+      if constexpr (std::is_same<TO, var>::value) {
+        total.grad();
+        if (G > 0)
+          for (int g = 0; g < n_alpha; ++g) d_alpha[g] = a[g].adj();
+        else
+          d_alpha[0] = a0.adj();
+        for (int k = 0; k < K; ++k) d_beta[k] = b[k].adj();
+        if constexpr (std::is_same<TS, var>::value) *d_sigma = sg.adj();
+      }
+    };
+    if (operands_are_var) {
+      if (sigma_is_var && d.family() == B200GLM_NORMAL_ID)
+        run(var(0), var(0));
+      else
+        run(var(0), double(0));
+    } else {
+      run(double(0), double(0));
+    }
+  });
 }
 
 const char* b200stan_version() {

@@ -206,7 +206,7 @@ int validate_slot(b200glm_handle* h, int slot) {
 }
 
 void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int propto, int jacobian, int is_var,
-                 double eps) {
+                 double eps, int lik_only = 0, int sigma_is_var = 0) {
   std::memset(&p, 0, sizeof(p));
   p.panels = h->panels;
   p.n_rows = h->d.N;
@@ -258,6 +258,8 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
   mc.propto = propto;
   mc.jacobian = jacobian;
   mc.is_var = is_var;
+  mc.lik_only = lik_only;
+  mc.sigma_is_var = sigma_is_var;
   mc.N_total = (double)(h->d.N_total > 0 ? h->d.N_total : h->d.N);
   mc.lgamma_sum = h->lgamma_sum_total;
   mc.prior_alpha_sd = h->d.prior_alpha_sd;
@@ -268,13 +270,14 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
 }
 
 // Enqueue one evaluation (all launches + the optional all-reduce) on the slot's stream.
-int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian, int is_var, double eps) {
+int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian, int is_var, double eps,
+                 int lik_only = 0, int sigma_is_var = 0) {
   KernelParams p;
   const bool need_likelihood = ((!propto) || is_var) && h->d.N_total != -1;
   const bool rows_anywhere = (h->d.N_total > 0 ? h->d.N_total : h->d.N) > 0;
   const bool exchange = need_likelihood && rows_anywhere && h->peer_on;
   if (exchange) ++s->peer_seq;
-  fill_params(h, s, p, mode, propto, jacobian, is_var, eps);
+  fill_params(h, s, p, mode, propto, jacobian, is_var, eps, lik_only, sigma_is_var);
   p.peer_in_main = (exchange && h->d.G == 0) ? 1 : 0;
   p.peer_in_finish = (exchange && h->d.G > 0) ? 1 : 0;
   if (need_likelihood && rows_anywhere) {
@@ -317,7 +320,7 @@ int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian,
 }
 
 int eval_host(b200glm_handle* h, int slot, const double* theta, int propto, int jacobian, int is_var, double* lp,
-              double* grad) {
+              double* grad, int lik_only = 0, int sigma_is_var = 0) {
   int rc = validate_slot(h, slot);
   if (rc) return rc;
   if (!theta || !lp) {
@@ -330,7 +333,7 @@ int eval_host(b200glm_handle* h, int slot, const double* theta, int propto, int 
   const int P = h->P;
   std::memcpy(s->h_pinned, theta, sizeof(double) * P);
   CUDA_TRY(h, cudaMemcpyAsync(s->theta, s->h_pinned, sizeof(double) * P, cudaMemcpyHostToDevice, s->stream));
-  rc = enqueue_eval(h, s, MODE_THETA, propto, jacobian, is_var, 0.0);
+  rc = enqueue_eval(h, s, MODE_THETA, propto, jacobian, is_var, 0.0, lik_only, sigma_is_var);
   if (rc) return rc;
   double* hres = s->h_pinned + (3 * P + 1);
   CUDA_TRY(h, cudaMemcpyAsync(hres, s->result, sizeof(double) * (P + 2), cudaMemcpyDeviceToHost, s->stream));
@@ -665,6 +668,36 @@ int b200glm_log_prob_grad(b200glm_handle* h, int32_t slot, const double* theta, 
 int b200glm_log_prob(b200glm_handle* h, int32_t slot, const double* theta, int32_t propto, int32_t jacobian,
                      double* lp) {
   return eval_host(h, slot, theta, propto ? 1 : 0, jacobian ? 1 : 0, 0, lp, nullptr);
+}
+
+int b200glm_glm_lpmf(b200glm_handle* h, int32_t slot, int32_t propto, int32_t operands_are_var,
+                     int32_t sigma_is_var, const double* alpha, const double* beta, double sigma, double* logp,
+                     double* d_alpha, double* d_beta, double* d_sigma) {
+  if (!h) return B200GLM_INVALID;
+  if (!logp || (h->d.K > 0 && !beta) || !alpha) {
+    h->set_error("null pointer argument");
+    return B200GLM_INVALID;
+  }
+  const int P = h->P, G = h->d.G, K = h->d.K;
+  const bool normal = h->d.family == B200GLM_NORMAL_ID;
+  if (normal && !(sigma > 0.0 && std::isfinite(sigma))) {
+    h->set_error("normal_id_glm_lpdf: Scale vector is not positive finite");   // normal_id_glm_lpdf.hpp:93
+    return B200GLM_DOMAIN;
+  }
+  std::vector<double> th(P, 0.0), g(P, 0.0);
+  if (G > 0)
+    std::memcpy(th.data() + 2, alpha, sizeof(double) * G);
+  else
+    th[0] = alpha[0];
+  if (K > 0) std::memcpy(th.data() + h->off_beta, beta, sizeof(double) * K);
+  if (normal) th[P - 1] = std::log(sigma);
+  const int rc = eval_host(h, slot, th.data(), propto ? 1 : 0, 0, operands_are_var ? 1 : 0, logp, g.data(), 1,
+                           sigma_is_var ? 1 : 0);
+  if (rc) return rc;
+  if (d_alpha) std::memcpy(d_alpha, G > 0 ? g.data() + 2 : g.data(), sizeof(double) * (G > 0 ? G : 1));
+  if (d_beta && K > 0) std::memcpy(d_beta, g.data() + h->off_beta, sizeof(double) * K);
+  if (d_sigma) *d_sigma = normal ? g[P - 1] : 0.0;
+  return B200GLM_OK;
 }
 
 int b200glm_set_state(b200glm_handle* h, int32_t slot, const double* q, const double* p, const double* g, double V) {

@@ -46,6 +46,9 @@ enum { ST_OK = 0, ST_DOMAIN = 1, ST_PEER_TIMEOUT = 2 };
 struct ModelConst {
   int family, K, G, P, off_beta;
   int propto, jacobian, is_var;  // semantics of this evaluation (see include/b200glm.h)
+  int lik_only;                  // function-level call (b200glm_glm_lpmf): the GLM term alone -- no priors, no
+                                 // Jacobian; the sigma entry of the gradient is d/d sigma, not d/d log sigma
+  int sigma_is_var;              // lik_only + normal_id: keep -N log sigma under propto (normal_id_glm_lpdf.hpp:205)
   double N_total;                // rows over all shards
   double lgamma_sum;             // sum lgamma(y+1) over all shards (poisson, propto=0)
   double prior_alpha_sd, prior_beta_sd, prior_sigma_loc, prior_sigma_scale, prior_sigma_a_scale;
@@ -309,11 +312,11 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
   // ---- value (thread 0) ----
   if (tid == 0) {
     double lp = 0.0;
-    if (mc.jacobian) {
+    if (mc.jacobian && !mc.lik_only) {
       if (G > 0) lp += u_sa;                           // lb_constrain.hpp:64
       if (mc.family == FAM_NORMAL_ID) lp += u_s;
     }
-    if (dens) {
+    if (dens && !mc.lik_only) {
       // priors: normal_lpdf.hpp:81-88
       if (G > 0) {
         const double z0 = mu_a / mc.prior_alpha_sd;
@@ -338,6 +341,8 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
         lp += -0.5 * z * z;
         if (!mc.propto) lp += NEG_LOG_SQRT_TWO_PI_D - log(mc.prior_sigma_scale);
       }
+    }
+    if (dens) {
       // likelihood
       if (mc.N_total > 0) {
         const double S = lik[P];
@@ -348,7 +353,8 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
           if (!mc.propto) lp -= mc.lgamma_sum;         // poisson_log_glm_lpmf.hpp:127-129
         } else {
           if (!mc.propto) lp += NEG_LOG_SQRT_TWO_PI_D * mc.N_total;   // normal_id_glm_lpdf.hpp:202-204
-          lp -= mc.N_total * u_s;                                     // :205-212, log sigma = u_s
+          if (!mc.lik_only || !mc.propto || mc.sigma_is_var)
+            lp -= mc.N_total * u_s;                                   // :205-212, log sigma = u_s
           lp -= 0.5 * S;                                              // :213
         }
       }
@@ -364,6 +370,14 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
   // ---- gradient wrt unconstrained theta, one thread per entry ----
   for (int i = tid; i < P; i += nt) {
     double g = lik[i];
+    if (mc.lik_only) {
+      if (mc.family == FAM_NORMAL_ID && i == P - 1)
+        g = mc.N_total > 0 ? (lik[P] - mc.N_total) / sigma : 0.0;    // normal_id_glm_lpdf.hpp:181-183
+      else if (G > 0 && i < 2)
+        g = 0.0;
+      p.result[1 + i] = g;
+      continue;
+    }
     if (G > 0) {
       if (i == 0) {
         g = -mu_a / (mc.prior_alpha_sd * mc.prior_alpha_sd) + 0.0;  // + sum_g (a_g-mu)/sigma_a^2 below
@@ -384,7 +398,7 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
     p.result[1 + i] = g;
   }
   __syncthreads();
-  if (G > 0) {  // mu_a and sigma_a entries need sums over the G group intercepts
+  if (G > 0 && !mc.lik_only) {  // mu_a and sigma_a entries need sums over the G group intercepts
     double sd = 0.0;
     for (int g = tid; g < G; g += nt) sd += theta[2 + g] - mu_a;
     sd = warp_sum(sd);

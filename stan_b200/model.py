@@ -145,6 +145,18 @@ class GLMModel:
         self._check(self.L.b200glm_log_prob(self.h, slot, _dp(th), int(propto), int(jacobian), C.byref(lp)))
         return lp.value
 
+    def glm_lpmf(self, alpha, beta, sigma=1.0, propto=True, operands_are_var=True, sigma_is_var=True, slot=0):
+        """Function-level entry: the GLM density term alone and its partials (d_alpha, d_beta, d_sigma)."""
+        a = np.ascontiguousarray(np.atleast_1d(alpha), dtype=np.float64)
+        b = np.ascontiguousarray(beta, dtype=np.float64)
+        if a.shape != (max(self.G, 1),) or b.shape != (self.K,):
+            raise InvalidArgument("alpha / beta have the wrong size")
+        lp, ds = C.c_double(), C.c_double()
+        da, db = np.empty_like(a), np.empty(max(self.K, 1))
+        self._check(self.L.b200glm_glm_lpmf(self.h, slot, int(propto), int(operands_are_var), int(sigma_is_var),
+                                            _dp(a), _dp(b), float(sigma), C.byref(lp), _dp(da), _dp(db), C.byref(ds)))
+        return lp.value, da, db[:self.K], ds.value
+
     def set_state(self, q, p, g, V, slot=0):
         q, p, g = (self._theta(a) for a in (q, p, g))
         self._check(self.L.b200glm_set_state(self.h, slot, _dp(q), _dp(p), _dp(g), float(V)))

@@ -168,3 +168,41 @@ class StanGLM:
         return dict(draws=draws[:, num_warmup:, :], warmup_draws=draws[:, :num_warmup, :], stepsize=step,
                     inv_metric=inv_metric, warm_leapfrogs=warm_lf, wall=wall.value,
                     batches=int(stats[0]), lanes=int(stats[1]))
+
+
+class FuncGLM:
+    """b200::glm_data + the stan::math overloads of b200/glm_functions.hpp (function-level binding),
+    exercised as one node of a reverse-mode tape: f = scale * glm_lpmf(...) + 0.5 * sum(beta^2)."""
+
+    def __init__(self, family, X, y, group=None, G=0):
+        self.L = lib()
+        self.L.b200stan_func_create.restype = C.c_void_p
+        self.L.b200stan_func_destroy.argtypes = [C.c_void_p]
+        self.fam = _capi.FAMILY[family]
+        X = np.asfortranarray(X, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64 if self.fam == 2 else np.int32)
+        grp = None if group is None else np.ascontiguousarray(group, dtype=np.int32)
+        self.K, self.G = X.shape[1], int(G)
+        err = C.create_string_buffer(1024)
+        self.h = C.c_void_p(self.L.b200stan_func_create(
+            C.c_int(self.fam), C.c_longlong(X.shape[0]), C.c_int(self.K), _dp(X), C.c_void_p(y.ctypes.data),
+            None if grp is None else grp.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(self.G), err, 1024))
+        if not self.h:
+            raise CudaError(err.value.decode() or "b200stan_func_create failed")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b200stan_func_destroy(self.h)
+            self.h = None
+
+    def eval(self, alpha, beta, sigma=1.0, propto=True, operands_are_var=True, sigma_is_var=True, scale=1.0):
+        a = np.ascontiguousarray(np.atleast_1d(alpha), dtype=np.float64)
+        b = np.ascontiguousarray(beta, dtype=np.float64)
+        f, ds, err = C.c_double(), C.c_double(), C.create_string_buffer(1024)
+        da, db = np.zeros_like(a), np.zeros(max(self.K, 1))
+        rc = self.L.b200stan_func_eval(self.h, int(propto), int(operands_are_var), int(sigma_is_var), _dp(a),
+                                       C.c_int(a.size), _dp(b), C.c_double(float(sigma)), C.c_double(float(scale)),
+                                       C.byref(f), _dp(da), _dp(db), C.byref(ds), err, 1024)
+        if rc:
+            StanGLM._raise(rc, err)
+        return f.value, da, db[:self.K], ds.value

@@ -21,8 +21,10 @@ def _ngpu():
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 @pytest.mark.parametrize("transport", ["peer", "nccl"])
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 8])
 def test_row_sharded_matches_oracle(world, transport):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29733" if transport == "peer" else "29734",
            os.path.join(ROOT, "tests", "mgpu_worker.py")]

@@ -5,10 +5,12 @@
 Tolerance 1e-12 relative: the port sums with compensated accumulation, the reference with Eigen's
 vectorised reductions; both are fp64, agreement is ~1e-15..1e-13.
 """
+import os
+
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_NAMES, rel_err, rel_err_vec, unhex
+from conftest import GOLDEN_NAMES, ROOT, rel_err, rel_err_vec, unhex
 from oracle.oracle import OracleError, PortOracle, RefOracle
 from stan_b200.synth import make_glm_data, theta_points
 
@@ -116,3 +118,39 @@ def test_reference_ess_golden():
             x[i, c] = 0.5 * x[i - 1, c] + rng.standard_normal()
     ess = RefOracle.ess(x)
     assert 800 < ess < 2200   # theory: 4000 * (1-0.5)/(1+0.5) = 1333
+
+
+def test_port_oracle_consistent_with_function_level_goldens():
+    """tests/golden/glm_function_golden.json holds the BARE reference densities (no priors).  The plain-C
+    port evaluates the whole model; model lp (propto, no Jacobian) minus the closed-form normal priors must
+    reproduce them, and likewise for the beta gradient."""
+    import json
+    from oracle.oracle import PortOracle
+    with open(os.path.join(ROOT, "tests", "golden", "glm_function_golden.json")) as f:
+        cases = json.load(f)["cases"]
+    unhex = lambda a: np.array([float.fromhex(v) for v in a])
+    for c in cases:
+        N, K, G, fam = c["N"], c["K"], c["G"], c["family"]
+        X = unhex(c["X"]).reshape((N, K), order="F")
+        y = np.array(c["y"], dtype=np.float64 if fam == "normal_id" else np.int32)
+        grp = None if c["group"] is None else np.array(c["group"], dtype=np.int32)
+        po = PortOracle(fam, X, y, grp, G)
+        a, b, sigma = unhex(c["alpha"]), unhex(c["beta"]), c["sigma"]
+        th = np.concatenate([[0.1, -0.2], a, b] if G else [a, b])
+        if fam == "normal_id":
+            th = np.concatenate([th, [np.log(sigma)]])
+        lp, g = po.log_prob_grad(th, True, False)
+        if G:
+            mu, sa = th[0], np.exp(th[1])
+            pri = -0.5 * (mu / 2.5) ** 2 - 0.5 * sa ** 2 - 0.5 * np.sum(((a - mu) / sa) ** 2) - G * np.log(sa)
+        else:
+            pri = -0.5 * (a[0] / 2.5) ** 2
+        pri += -0.5 * np.sum((b / 2.5) ** 2)
+        if fam == "normal_id":
+            pri += -0.5 * ((sigma - 1.0) / 2.0) ** 2
+        e = [e for e in c["evals"] if e["propto"] == 1 and e["operands_are_var"] == 1
+             and e["sigma_is_var"] == (1 if fam == "normal_id" else 0)][0]
+        ref_lp, ref_db = float.fromhex(e["lp"]), unhex(e["d_beta"])
+        assert abs((lp - pri) - ref_lp) <= 1e-11 * abs(ref_lp), c["name"]
+        ob = 2 + G if G else 1
+        assert np.max(np.abs(g[ob:ob + K] + b / 2.5 ** 2 - ref_db)) <= 1e-11 * np.max(np.abs(ref_db)), c["name"]
