@@ -104,9 +104,11 @@ class glm_data {
   // value + partials; alpha has 1 (G == 0) or G entries
   void evaluate(bool propto, bool operands_are_var, bool sigma_is_var, const double* alpha, const double* beta,
                 double sigma, double& logp, double* d_alpha, double* d_beta, double* d_sigma) const {
-    static thread_local int slot = -1;
-    if (slot < 0)
-      slot = next_slot_++ % (n_slots_ > 0 ? n_slots_ : 1);
+    // evaluations are stateless and serialised per slot inside the library, so any mapping of
+    // threads to slots is safe; a per-thread ordinal spreads concurrent callers over the slots
+    static std::atomic<int> next_thread{0};
+    static thread_local const int thread_ordinal = next_thread.fetch_add(1);
+    const int slot = thread_ordinal % (n_slots_ > 0 ? n_slots_ : 1);
     const int rc = b200glm_glm_lpmf(h_, slot, propto, operands_are_var, sigma_is_var, alpha, beta, sigma, &logp,
                                     d_alpha, d_beta, d_sigma);
     if (rc != B200GLM_OK)
@@ -116,7 +118,6 @@ class glm_data {
  private:
   b200glm_handle* h_ = nullptr;
   int family_ = 0, K_ = 0, G_ = 0, n_slots_ = 1;
-  mutable std::atomic<int> next_slot_{0};
 };
 
 namespace internal {

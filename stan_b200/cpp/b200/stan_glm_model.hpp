@@ -29,6 +29,9 @@
 
 #include <atomic>
 #include <cstring>
+#include <memory>
+#include <mutex>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -43,7 +46,10 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
   }
 
   explicit glm_model(const b200glm_desc& desc)
-      : model_base_crtp(count_params(desc)), desc_(desc), h_(nullptr) {
+      : model_base_crtp(count_params(desc)), desc_(desc), h_(nullptr), uid_(next_uid()) {
+    if (desc_.n_slots < 1)
+      desc_.n_slots = 1;
+    guards_.reset(new slot_guard[desc_.n_slots]);
     const int rc = b200glm_create(&desc_, &h_);
     if (rc != B200GLM_OK) {
       std::string msg = h_ ? b200glm_last_error(h_) : "b200glm_create failed";
@@ -57,12 +63,38 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
     desc_.y_int = nullptr;
     desc_.y_real = nullptr;
     desc_.group = nullptr;
+    registry(+1, uid_);
   }
   glm_model(const glm_model&) = delete;
   glm_model& operator=(const glm_model&) = delete;
   ~glm_model() override {
+    registry(-1, uid_);
     if (h_)
       b200glm_destroy(h_);
+  }
+
+  // Thread-local caches (slot binding, resident leapfrog state, "current model") are keyed by a
+  // process-unique id, never by address: a new model may be allocated where a destroyed one lived.
+  static unsigned long long next_uid() {
+    static std::atomic<unsigned long long> n{1};
+    return n.fetch_add(1);
+  }
+  unsigned long long uid() const { return uid_; }
+  // op = +1 register, -1 unregister, 0 query
+  static bool registry(int op, unsigned long long uid) {
+    static std::mutex mu;
+    static std::set<unsigned long long> live;
+    std::lock_guard<std::mutex> lock(mu);
+    if (op > 0)
+      live.insert(uid);
+    else if (op < 0)
+      live.erase(uid);
+    return live.count(uid) != 0;
+  }
+  static unsigned long long thread_token() {
+    static std::atomic<unsigned long long> n{1};
+    static thread_local unsigned long long tok = n.fetch_add(1);
+    return tok;
   }
 
   b200glm_handle* handle() const { return h_; }
@@ -81,16 +113,23 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
       raise(rc, b200glm_last_error(h_));
   }
 
-  // one device slot per host thread (round-robin over n_slots)
+  // one device slot per host thread (round-robin over n_slots; with more threads than slots two
+  // threads share one, which is safe -- see slot_guard -- but costs a state upload per switch)
   int slot() const {
     static thread_local int tls_slot = -1;
-    static thread_local const glm_model* tls_owner = nullptr;
-    if (tls_owner != this) {
-      tls_owner = this;
-      tls_slot = next_slot_.fetch_add(1) % (desc_.n_slots > 0 ? desc_.n_slots : 1);
+    static thread_local unsigned long long tls_owner = 0;
+    if (tls_owner != uid_) {
+      tls_owner = uid_;
+      tls_slot = next_slot_.fetch_add(1) % desc_.n_slots;
     }
     return tls_slot;
   }
+  // Serialises the {set_state, leapfrog} pair on a slot and remembers which thread's trajectory the
+  // slot's device-resident state belongs to.
+  struct slot_guard {
+    std::mutex mu;
+    unsigned long long state_token = 0, metric_token = 0;
+  };
 
   // Batched-chains hook (b200/batched_nuts.hpp): while a host thread runs a chain inside a
   // batch_scope, its gradient and leapfrog calls are not launched one by one but handed to the
@@ -141,13 +180,26 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
 
   // thread-local "which model did this thread evaluate last" -- how the integrator
   // specialisation finds the device without touching diag_e_metric (model_ is protected there)
-  static const glm_model*& current() {
-    static thread_local const glm_model* cur = nullptr;
+  struct current_ref {
+    const glm_model* model = nullptr;
+    unsigned long long uid = 0;
+  };
+  static current_ref& current_slot() {
+    static thread_local current_ref cur;
     return cur;
+  }
+  static void set_current(const glm_model* m) {
+    current_slot().model = m;
+    current_slot().uid = m->uid_;
+  }
+  // nullptr if this thread has not evaluated a model yet or that model no longer exists
+  static const glm_model* current() {
+    const current_ref& c = current_slot();
+    return (c.model != nullptr && registry(0, c.uid)) ? c.model : nullptr;
   }
 
   struct resident_state {
-    const glm_model* owner = nullptr;
+    unsigned long long owner = 0;
     bool valid = false, metric_valid = false;
     std::vector<double> q, p, g, inv_metric;
   };
@@ -170,15 +222,18 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
     const size_t bytes = P * sizeof(double);
     resident_state& rs = resident();
     const int sl = slot();
-    if (rs.owner != this) {
-      rs.owner = this;
+    slot_guard& guard = guards_[sl];
+    const unsigned long long me = thread_token();
+    std::lock_guard<std::mutex> lock(guard.mu);
+    if (rs.owner != uid_) {
+      rs.owner = uid_;
       rs.valid = rs.metric_valid = false;
       rs.q.resize(P);
       rs.p.resize(P);
       rs.g.resize(P);
       rs.inv_metric.resize(P);
     }
-    const bool same = rs.valid && std::memcmp(rs.q.data(), q.data(), bytes) == 0
+    const bool same = rs.valid && guard.state_token == me && std::memcmp(rs.q.data(), q.data(), bytes) == 0
                       && std::memcmp(rs.p.data(), p.data(), bytes) == 0
                       && std::memcmp(rs.g.data(), g.data(), bytes) == 0;
     if (!same) {
@@ -186,11 +241,14 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
       n_uploads_.fetch_add(1, std::memory_order_relaxed);
     }
     const double* im = nullptr;
-    if (!rs.metric_valid || std::memcmp(rs.inv_metric.data(), inv_metric.data(), bytes) != 0) {
+    if (!rs.metric_valid || guard.metric_token != me
+        || std::memcmp(rs.inv_metric.data(), inv_metric.data(), bytes) != 0) {
       std::memcpy(rs.inv_metric.data(), inv_metric.data(), bytes);
       rs.metric_valid = true;
+      guard.metric_token = me;
       im = rs.inv_metric.data();
     }
+    guard.state_token = me;
     const int rc = b200glm_leapfrog(h_, sl, epsilon, im, q.data(), p.data(), g.data(), &V);
     if (rc == B200GLM_DOMAIN) {
       // data-level domain error (y out of range): same outcome as base_hamiltonian.hpp:65-69
@@ -375,6 +433,8 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
  private:
   b200glm_desc desc_;
   b200glm_handle* h_;
+  unsigned long long uid_;
+  mutable std::unique_ptr<slot_guard[]> guards_;
   mutable std::atomic<int> next_slot_{0};
   mutable std::atomic<long> n_gradients_{0}, n_leapfrogs_{0}, n_uploads_{0};
 };
@@ -391,7 +451,7 @@ template <>
 inline void gradient<b200::glm_model>(const b200::glm_model& model, const Eigen::Matrix<double, Eigen::Dynamic, 1>& x,
                                       double& f, Eigen::Matrix<double, Eigen::Dynamic, 1>& grad_f,
                                       std::ostream* /*msgs*/) {
-  b200::glm_model::current() = &model;
+  b200::glm_model::set_current(&model);
   Eigen::VectorXd g(x.size());
   model.device_log_prob_grad(x.data(), true, true, f, g.data());  // throws before grad_f is touched
   grad_f = std::move(g);

@@ -119,6 +119,25 @@ def test_nuts_leapfrogs_ran_on_device(nuts_pair):
     assert c["uploads"] < c["leapfrogs"]          # state stayed resident for the rest
 
 
+def test_chains_do_not_depend_on_thread_to_slot_assignment():
+    """Regression: thread-local slot / resident-state caches were keyed by the model's ADDRESS, so a model
+    allocated where a destroyed one had lived inherited stale slot bindings and two concurrently running
+    chains could share one device-resident leapfrog state.  Draws of a chain are a function of (seed, chain
+    id) only: 4 chains on 4 threads must be bitwise identical whether every thread has its own slot, all
+    threads share ONE slot, or other models lived (and died) on these threads before."""
+    d = make_glm_data("bernoulli_logit", 4_000, 6)
+    kw = dict(num_chains=4, seed=31, num_warmup=150, num_samples=100, delta=0.8, num_threads=4)
+    runs = []
+    for n_slots in (8, 1, 2, 8):
+        m = stan_service.StanGLM("bernoulli_logit", d["X"], d["y"], n_slots=n_slots)
+        th = np.zeros(m.P)
+        m.gradient(th)                      # touches the model on the calling thread before the service does
+        runs.append(m.nuts(**kw)["draws"])
+        m.close()
+    for r in runs[1:]:
+        assert np.array_equal(runs[0], r)
+
+
 # ---------------------------------------------------------------------------------------------------
 # batched driver: every chain runs the reference's single-chain service on its own host thread, the
 # leapfrog steps of all chains are served by one batched DMMA launch (b200/batched_nuts.hpp)
