@@ -9,6 +9,8 @@ min/median ESS over parameters (stan::analyze::ess), ESS/s, and the posterior z-
 
     python bench_nuts.py --config 1                 # N=10k K=20, 4 chains, 1000+1000 (BASELINE configs[0])
     python bench_nuts.py --config 2 --ref-iters 0   # N=10M K=100 on the GPU; CPU arm skipped (hours)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 bench_nuts.py --config 2
+                                                    # the same single chain with the rows sharded over N GPUs
 Writes one JSON line; not part of the driver's bench contract (bench.py is).
 """
 import argparse
@@ -67,6 +69,40 @@ def config3(args):
     print(json.dumps(out))
 
 
+def sharded(args, world, rank, local):
+    """BASELINE configs[1] on N GPUs: ONE chain (the config is single-chain) through the unmodified
+    hmc_nuts_diag_e_adapt, rows of X sharded over the ranks.  Every rank runs the same host code on the same
+    seed; each leapfrog is one fused launch per rank with the likelihood partials exchanged inside it."""
+    import torch
+    import torch.distributed as dist
+    from oracle.oracle import RefOracle
+    from stan_b200 import stan_service
+    from stan_b200.synth import make_shard
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    N, K = args.rows or 10_000_000, args.cols or 100
+    X, y, _, r0, r1 = make_shard(torch, dev, "bernoulli_logit", N, K, 0, rank, world)
+    torch.cuda.synchronize()
+    m = stan_service.StanGLM("bernoulli_logit", X.data_ptr(), y.data_ptr(), device=local, n_slots=1, rank=rank,
+                             world=world, N_total=N, data_on_device=True, N=r1 - r0, K=K, ldx=r1 - r0)
+    del X, y
+    torch.cuda.empty_cache()
+    m.connect_peers_torch(dist, dev)
+    res = m.nuts(num_chains=1, seed=4711, num_warmup=args.warmup, num_samples=args.samples, delta=0.8, num_threads=1)
+    wall = torch.tensor([res["wall"]], device=dev, dtype=torch.float64)
+    dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+    res["wall"] = float(wall.item())
+    if rank == 0:
+        s = summarize(res, RefOracle, 1)
+        print(json.dumps({"workload": f"bernoulli_logit_glm N={N} K={K}, NUTS diag_e 1 chain {args.warmup}+{args.samples} "
+                                      f"via unmodified hmc_nuts_diag_e_adapt, rows sharded over {world} GPUs "
+                                      "(exchange inside the leapfrog launch)", "n_gpus": world,
+                          "b200": dict(s, counters=m.counters())}))
+    m.close()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, default=1)
@@ -80,6 +116,9 @@ def main():
     from oracle.oracle import RefOracle
     from stan_b200 import make_glm_data, stan_service
 
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
+    if world > 1:
+        return sharded(args, world, rank, local)
     if args.config == 3:
         return config3(args)
     N, K = {1: (10_000, 20), 2: (10_000_000, 100)}[args.config]

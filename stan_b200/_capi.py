@@ -89,3 +89,27 @@ def lib():
         L.b200glm_version.restype = C.c_char_p
         _lib = L
     return _lib
+
+
+def connect_peers_torch(handle, world, dist, dev):
+    """Wire the peer mailboxes of a row-sharded handle (b200glm_handle*) using torch.distributed as the
+    out-of-band channel: all-gather the 64-byte IPC handles (rank order) and the per-shard poisson
+    constant.  torch.distributed is plumbing here; the exchange itself happens inside the gradient launch."""
+    import torch
+    L = lib()
+
+    def check(rc):
+        if rc != OK:
+            raise RuntimeError((L.b200glm_last_error(handle) or b"b200glm error").decode())
+
+    buf = C.create_string_buffer(64)
+    check(L.b200glm_peer_export(handle, buf))
+    mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev)
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    raw = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+    check(L.b200glm_peer_connect(handle, C.create_string_buffer(raw, len(raw)), world))
+    lg = torch.tensor([L.b200glm_lgamma_sum_local(handle)], dtype=torch.float64, device=dev)
+    dist.all_reduce(lg)
+    check(L.b200glm_set_lgamma_sum_total(handle, float(lg.item())))
+    dist.barrier()

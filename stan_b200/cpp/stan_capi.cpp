@@ -113,6 +113,8 @@ void* b200stan_create(const b200glm_desc* d, char* err, int errlen) {
   return m;
 }
 void b200stan_destroy(void* h) { delete static_cast<glm_model*>(h); }
+// the b200glm_handle* behind the model (row-sharded runs: b200glm_peer_export / peer_connect / comm_init on it)
+void* b200stan_backend_handle(void* h) { return static_cast<glm_model*>(h)->handle(); }
 int b200stan_num_params(void* h) { return static_cast<int>(static_cast<glm_model*>(h)->num_params_r()); }
 void b200stan_counters(void* h, long* n_gradients, long* n_leapfrogs, long* n_uploads) {
   auto* m = static_cast<glm_model*>(h);

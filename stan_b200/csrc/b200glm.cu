@@ -285,7 +285,7 @@ int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian,
     fn<<<h->grid, h->wide ? WIDE_THREADS : NUM_THREADS, h->smem_bytes, s->stream>>>(p);
     h->launches++;
     if (h->d.G > 0) {
-      const int gb = std::min(h->d.G, 4 * 148);
+      const int gb = std::min(h->d.G, 8 * 148);   // 8 CTAs of 256 threads are resident per SM
       group_reduce_kernel<<<gb, 256, 0, s->stream>>>(s->r_out, h->seg_ptr, h->d.G, s->lik + 2);
       h->launches++;
     }

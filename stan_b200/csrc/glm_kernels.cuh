@@ -669,16 +669,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
   cross_cta_reduce_and_finish<FAMILY>(p, sh_scratch, &sh_is_last);
 }
 
-// G > 0: deterministic per-group sums of the residual (rows are sorted by group at upload).
+// G > 0: deterministic per-group sums of the residual (rows are sorted by group at upload, so a group
+// is one contiguous segment).  One CTA per group; four independent accumulators per thread keep four
+// loads in flight, and the order of every addition is fixed -> bitwise reproducible.
 __global__ void __launch_bounds__(256) group_reduce_kernel(const double* __restrict__ r,
                                                           const long long* __restrict__ seg_ptr, int G,
                                                           double* __restrict__ lik_a /* lik + 2 */) {
   __shared__ double sh[8];
   for (int g = blockIdx.x; g < G; g += gridDim.x) {
     const long long b = seg_ptr[g], e = seg_ptr[g + 1];
-    double v = 0.0;
-    for (long long i = b + threadIdx.x; i < e; i += blockDim.x) v += r[i];
-    v = warp_sum(v);
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    long long i = b + threadIdx.x;
+    for (; i + 768 < e; i += 1024) {
+      v0 += __ldcs(r + i);
+      v1 += __ldcs(r + i + 256);
+      v2 += __ldcs(r + i + 512);
+      v3 += __ldcs(r + i + 768);
+    }
+    for (; i < e; i += 256) v0 += __ldcs(r + i);
+    double v = warp_sum((v0 + v1) + (v2 + v3));
     __syncthreads();
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
     __syncthreads();

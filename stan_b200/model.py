@@ -37,6 +37,54 @@ DEFAULT_PRIORS = dict(prior_alpha_sd=2.5, prior_beta_sd=2.5, prior_sigma_loc=1.0
                       prior_sigma_scale=2.0, prior_sigma_a_scale=1.0)
 
 
+def make_desc(family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=1, N_total=0,
+              grid_ctas=0, flags=0, data_on_device=False, N=None, K=None, ldx=None, **priors):
+    """Fill a b200glm_desc.  X, y, group: numpy arrays (host), or -- with data_on_device=True -- integer
+    device pointers (e.g. torch tensor .data_ptr()) with N, K, ldx given explicitly.  Returns (desc, keep):
+    `keep` holds the host arrays the descriptor points into (they must outlive the create call)."""
+    fam = _capi.FAMILY[family]
+    d = _capi.Desc()
+    keep = []
+    if data_on_device:
+        d.N, d.K, d.ldx = int(N), int(K), int(ldx if ldx is not None else N)
+        d.X = int(X) if X else None
+        if fam == 2:
+            d.y_real, d.y_int = int(y), None
+        else:
+            d.y_int, d.y_real = int(y), None
+        d.group = int(group) if G else None
+    else:
+        X = np.asfortranarray(X, dtype=np.float64)
+        if X.ndim != 2:
+            raise InvalidArgument("X must be a matrix")
+        keep.append(X)
+        d.N, d.K = X.shape
+        d.ldx = max(X.shape[0], 1)
+        d.X = X.ctypes.data if X.size else None
+        y = np.ascontiguousarray(y, dtype=np.float64 if fam == 2 else np.int32)
+        if y.shape != (d.N,):
+            raise InvalidArgument("Vector of dependent variables has the wrong size")
+        keep.append(y)
+        if fam == 2:
+            d.y_real, d.y_int = (y.ctypes.data if y.size else None), None
+        else:
+            d.y_int, d.y_real = (y.ctypes.data if y.size else None), None
+        if G:
+            group = np.ascontiguousarray(group, dtype=np.int32)
+            if group.shape != (d.N,):
+                raise InvalidArgument("Vector of intercepts has the wrong size")
+            keep.append(group)
+            d.group = group.ctypes.data if group.size else None
+    d.family, d.G, d.data_on_device = fam, int(G), int(bool(data_on_device))
+    pri = dict(DEFAULT_PRIORS)
+    pri.update(priors)
+    for k, v in pri.items():
+        setattr(d, k, float(v))
+    d.device, d.n_slots, d.rank, d.world = int(device), int(n_slots), int(rank), int(world)
+    d.N_total, d.grid_ctas, d.flags = int(N_total), int(grid_ctas), int(flags)
+    return d, keep
+
+
 class GLMModel:
     def __init__(self, family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=1, N_total=0,
                  grid_ctas=0, flags=0, data_on_device=False, N=None, K=None, ldx=None, **priors):
@@ -44,46 +92,8 @@ class GLMModel:
         pointers (e.g. torch tensor .data_ptr()) with N, K, ldx given explicitly."""
         self.L = _capi.lib()
         self.family = family
-        fam = _capi.FAMILY[family]
-        d = _capi.Desc()
-        keep = []
-        if data_on_device:
-            d.N, d.K, d.ldx = int(N), int(K), int(ldx if ldx is not None else N)
-            d.X = int(X) if X else None
-            if fam == 2:
-                d.y_real, d.y_int = int(y), None
-            else:
-                d.y_int, d.y_real = int(y), None
-            d.group = int(group) if G else None
-        else:
-            X = np.asfortranarray(X, dtype=np.float64)
-            if X.ndim != 2:
-                raise InvalidArgument("X must be a matrix")
-            keep.append(X)
-            d.N, d.K = X.shape
-            d.ldx = max(X.shape[0], 1)
-            d.X = X.ctypes.data if X.size else None
-            y = np.ascontiguousarray(y, dtype=np.float64 if fam == 2 else np.int32)
-            if y.shape != (d.N,):
-                raise InvalidArgument("Vector of dependent variables has the wrong size")
-            keep.append(y)
-            if fam == 2:
-                d.y_real, d.y_int = (y.ctypes.data if y.size else None), None
-            else:
-                d.y_int, d.y_real = (y.ctypes.data if y.size else None), None
-            if G:
-                group = np.ascontiguousarray(group, dtype=np.int32)
-                if group.shape != (d.N,):
-                    raise InvalidArgument("Vector of intercepts has the wrong size")
-                keep.append(group)
-                d.group = group.ctypes.data if group.size else None
-        d.family, d.G, d.data_on_device = fam, int(G), int(bool(data_on_device))
-        pri = dict(DEFAULT_PRIORS)
-        pri.update(priors)
-        for k, v in pri.items():
-            setattr(d, k, float(v))
-        d.device, d.n_slots, d.rank, d.world = int(device), int(n_slots), int(rank), int(world)
-        d.N_total, d.grid_ctas, d.flags = int(N_total), int(grid_ctas), int(flags)
+        d, keep = make_desc(family, X, y, group, G, device, n_slots, rank, world, N_total, grid_ctas, flags,
+                            data_on_device, N, K, ldx, **priors)
         self.N, self.K, self.G = int(d.N), int(d.K), int(G)
         self.rank, self.world = int(rank), int(world)
         h = C.c_void_p()
@@ -275,12 +285,4 @@ class GLMModel:
     def connect_peers_torch(self, dist, dev):
         """Convenience for torch.distributed callers: all-gather the mailbox handles (and the poisson
         constant) and connect.  torch.distributed is plumbing here, the exchange itself is in-kernel."""
-        import torch
-        mine = torch.frombuffer(bytearray(self.peer_export()), dtype=torch.uint8).to(dev)
-        allh = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(allh, mine)
-        self.peer_connect(b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh))
-        lg = torch.tensor([self.lgamma_sum_local()], dtype=torch.float64, device=dev)
-        dist.all_reduce(lg)
-        self.set_lgamma_sum_total(float(lg.item()))
-        dist.barrier()
+        _capi.connect_peers_torch(self.h, self.world, dist, dev)

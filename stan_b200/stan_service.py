@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 from . import _capi
-from .model import DomainError, InvalidArgument, CudaError, DEFAULT_PRIORS
+from .model import DomainError, InvalidArgument, CudaError, make_desc
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libb200stan.so")
 _lib = None
@@ -32,6 +32,8 @@ def lib():
         L.b200stan_create.argtypes = [C.POINTER(_capi.Desc), C.c_char_p, C.c_int]
         L.b200stan_destroy.argtypes = [C.c_void_p]
         L.b200stan_num_params.argtypes = [C.c_void_p]
+        L.b200stan_backend_handle.restype = C.c_void_p
+        L.b200stan_backend_handle.argtypes = [C.c_void_p]
         L.b200stan_version.restype = C.c_char_p
         _lib = L
     return _lib
@@ -44,32 +46,26 @@ def _dp(a):
 class StanGLM:
     """b200::glm_model driven through the reference's C++ interfaces."""
 
-    def __init__(self, family, X, y, group=None, G=0, device=0, n_slots=8, **priors):
+    def __init__(self, family, X, y, group=None, G=0, device=0, n_slots=8, rank=0, world=1, N_total=0,
+                 data_on_device=False, N=None, K=None, ldx=None, **priors):
+        """Arguments as GLMModel.  rank/world/N_total: this process holds row shard `rank` of `world` (one
+        process per GPU); call connect_peers_torch() before the first evaluation and use n_slots=1 and one
+        host thread: every rank must issue the same sequence of evaluations, which the reference's
+        deterministic host code does by construction when it is given the same seeds."""
         self.L = lib()
-        fam = _capi.FAMILY[family]
-        X = np.asfortranarray(X, dtype=np.float64)
-        y = np.ascontiguousarray(y, dtype=np.float64 if fam == 2 else np.int32)
-        d = _capi.Desc()
-        d.family, d.N, d.K = fam, X.shape[0], X.shape[1]
-        d.X, d.ldx = (X.ctypes.data if X.size else None), max(X.shape[0], 1)
-        if fam == 2:
-            d.y_real = y.ctypes.data if y.size else None
-        else:
-            d.y_int = y.ctypes.data if y.size else None
-        d.G = int(G)
-        if G:
-            group = np.ascontiguousarray(group, dtype=np.int32)
-            d.group = group.ctypes.data
-        pri = dict(DEFAULT_PRIORS)
-        pri.update(priors)
-        for k, v in pri.items():
-            setattr(d, k, float(v))
-        d.device, d.n_slots, d.rank, d.world = device, n_slots, 0, 1
+        d, keep = make_desc(family, X, y, group, G, device, n_slots, rank, world, N_total,
+                            data_on_device=data_on_device, N=N, K=K, ldx=ldx, **priors)
+        self.rank, self.world = int(rank), int(world)
         err = C.create_string_buffer(1024)
         self.h = C.c_void_p(self.L.b200stan_create(C.byref(d), err, 1024))
         if not self.h:
             raise CudaError(err.value.decode() or "b200stan_create failed")
         self.P = self.L.b200stan_num_params(self.h)
+
+    def connect_peers_torch(self, dist, dev):
+        """Row-sharded model: map every rank's mailbox (the likelihood partials are then exchanged inside
+        the gradient / leapfrog launch over NVLink; no collective call per gradient)."""
+        _capi.connect_peers_torch(C.c_void_p(self.L.b200stan_backend_handle(self.h)), self.world, dist, dev)
 
     def close(self):
         if getattr(self, "h", None):

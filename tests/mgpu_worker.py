@@ -15,6 +15,48 @@ from stan_b200 import GLMModel, make_glm_data  # noqa: E402
 from stan_b200.synth import shard_rows  # noqa: E402
 
 
+def nuts_through_the_reference_service(rank, world, local, dev):
+    """The reference's unmodified hmc_nuts_diag_e_adapt driving a ROW-SHARDED b200::glm_model: every rank
+    runs the same deterministic host code on the same seed, every gradient / fused leapfrog is one launch
+    per rank with the exchange inside it.  Draws must be bitwise identical on all ranks and agree with the
+    unsharded model (same seed) until rounding is amplified."""
+    from stan_b200 import stan_service
+    if not stan_service.available():
+        return []
+    failures = []
+    N, K = 60_001, 12
+    d = make_glm_data("bernoulli_logit", N, K)
+    r0, r1 = shard_rows(N, rank, world)
+    kw = dict(num_chains=1, seed=77, num_warmup=120, num_samples=80, delta=0.8, num_threads=1)
+    m = stan_service.StanGLM("bernoulli_logit", d["X"][r0:r1], d["y"][r0:r1], device=local, n_slots=1,
+                             rank=rank, world=world, N_total=N)
+    m.connect_peers_torch(dist, dev)
+    res = m.nuts(**kw)
+    c = m.counters()
+    m.close()
+    buf = torch.tensor(np.concatenate([res["draws"].ravel(), res["warmup_draws"].ravel()]), device=dev)
+    ref = buf.clone()
+    dist.broadcast(ref, 0)
+    if not torch.equal(buf, ref):
+        failures.append("sharded NUTS: ranks hold different draws")
+    if rank == 0:
+        one = stan_service.StanGLM("bernoulli_logit", d["X"], d["y"], device=local, n_slots=1)
+        full = one.nuts(**kw)
+        one.close()
+        a, b = res["warmup_draws"][:, :5, :], full["warmup_draws"][:, :5, :]
+        if not (np.array_equal(a[:, :, 3:6], b[:, :, 3:6]) and np.max(np.abs(a[:, :, 7:] - b[:, :, 7:])) < 1e-6):
+            failures.append("sharded NUTS: first draws differ from the unsharded model")
+        ma, mb = res["draws"][:, :, 7:].mean(axis=(0, 1)), full["draws"][:, :, 7:].mean(axis=(0, 1))
+        sd = full["draws"][:, :, 7:].std(axis=(0, 1))
+        if not np.all(np.abs(ma - mb) < 1.0 * sd):       # 80 draws each: a loose sanity bound, not the MCSE bar
+            failures.append("sharded NUTS: posterior means off")
+        if c["leapfrogs"] < res["draws"][:, :, 4].sum():
+            failures.append("sharded NUTS: leapfrogs did not run on the device")
+        print(f"sharded NUTS world={world}: {int(c['leapfrogs'])} fused leapfrog launches per rank, "
+              f"max |mean diff|/sd = {float(np.max(np.abs(ma - mb) / sd)):.2f}", flush=True)
+    return failures
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -69,9 +111,13 @@ def main():
                 failures.append(f"{fam}: err {e}")
             print(f"{fam} N={N} K={K} G={G} world={world}: max err {e:.2e}", flush=True)
         m.close()
-    dist.barrier()
+    failures += nuts_through_the_reference_service(rank, world, local, dev)
+    n_fail = torch.tensor([len(failures)], device=dev)
+    dist.all_reduce(n_fail)                     # a rank other than 0 may be the one that saw a mismatch
+    if failures:
+        print(f"rank {rank}: " + "; ".join(failures), flush=True)
     if rank == 0:
-        print("MGPU-OK" if not failures else "MGPU-FAIL " + "; ".join(failures), flush=True)
+        print("MGPU-OK" if int(n_fail.item()) == 0 else "MGPU-FAIL " + "; ".join(failures), flush=True)
     dist.destroy_process_group()
 
 
