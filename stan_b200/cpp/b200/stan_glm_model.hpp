@@ -39,8 +39,102 @@
 
 namespace b200 {
 
+// What the var_context constructor needs to know about the data block of the Stan program the model
+// stands for (a stanc-generated model has this baked in): the names of the data variables, the
+// likelihood family, the prior scales and where to put the data.
+struct glm_config {
+  int family = B200GLM_BERNOULLI_LOGIT;
+  std::string name_N = "N", name_K = "K", name_X = "X", name_y = "y", name_G = "G", name_group = "group";
+  // brms-style `transformed data`: Xc[, k] = X[, k] - mean(X[, k]); the intercept parameter is then the
+  // intercept for centred predictors and b_Intercept = Intercept - dot(means_X, b) (glm_model::means_x())
+  bool center_x = false;
+  double prior_alpha_sd = 2.5, prior_beta_sd = 2.5, prior_sigma_loc = 1.0, prior_sigma_scale = 2.0,
+         prior_sigma_a_scale = 1.0;
+  int device = 0, n_slots = 1;
+};
+
 class glm_model final : public stan::model::model_base_crtp<glm_model> {
+  // data read from a var_context, alive until b200glm_create has copied it to the device
+  struct loaded_data {
+    b200glm_desc desc;
+    std::vector<double> X, y_real, means;
+    std::vector<int> y_int, group;
+  };
+  static loaded_data load(const stan::io::var_context& context, const glm_config& cfg) {
+    // same checks and messages a stanc-generated constructor performs (validate_dims / vals_i / vals_r)
+    loaded_data L;
+    std::memset(&L.desc, 0, sizeof(L.desc));
+    const char* stage = "data initialization";
+    context.validate_dims(stage, cfg.name_N, "int", std::vector<size_t>{});
+    const int N = context.vals_i(cfg.name_N)[0];
+    stan::math::check_greater_or_equal("model constructor", cfg.name_N.c_str(), N, 0);
+    context.validate_dims(stage, cfg.name_K, "int", std::vector<size_t>{});
+    const int K = context.vals_i(cfg.name_K)[0];
+    stan::math::check_greater_or_equal("model constructor", cfg.name_K.c_str(), K, 0);
+    context.validate_dims(stage, cfg.name_X, "double", std::vector<size_t>{static_cast<size_t>(N), static_cast<size_t>(K)});
+    L.X = context.vals_r(cfg.name_X);               // matrix[N, K]: column-major, as Eigen::MatrixXd
+    if (cfg.center_x) {
+      L.means.assign(K, 0.0);
+      for (int k = 0; k < K; ++k) {
+        double* col = L.X.data() + static_cast<size_t>(k) * N;
+        // stan::math::mean == Eigen's mean(): sum / N
+        const double mu = N > 0 ? Eigen::Map<const Eigen::VectorXd>(col, N).mean() : 0.0;
+        L.means[k] = mu;
+        for (int i = 0; i < N; ++i)
+          col[i] -= mu;
+      }
+    }
+    if (cfg.family == B200GLM_NORMAL_ID) {
+      context.validate_dims(stage, cfg.name_y, "double", std::vector<size_t>{static_cast<size_t>(N)});
+      L.y_real = context.vals_r(cfg.name_y);
+    } else {
+      context.validate_dims(stage, cfg.name_y, "int", std::vector<size_t>{static_cast<size_t>(N)});
+      L.y_int = context.vals_i(cfg.name_y);
+    }
+    int G = 0;
+    if (context.contains_i(cfg.name_G)) {
+      context.validate_dims(stage, cfg.name_G, "int", std::vector<size_t>{});
+      G = context.vals_i(cfg.name_G)[0];
+      stan::math::check_greater_or_equal("model constructor", cfg.name_G.c_str(), G, 0);
+    }
+    if (G > 0) {
+      context.validate_dims(stage, cfg.name_group, "int", std::vector<size_t>{static_cast<size_t>(N)});
+      L.group = context.vals_i(cfg.name_group);
+      stan::math::check_bounded("model constructor", cfg.name_group.c_str(), L.group, 1, G);
+    }
+    b200glm_desc& d = L.desc;
+    d.family = cfg.family;
+    d.N = N;
+    d.K = K;
+    d.X = L.X.data();
+    d.ldx = N > 0 ? N : 1;
+    d.y_int = L.y_int.empty() ? nullptr : L.y_int.data();
+    d.y_real = L.y_real.empty() ? nullptr : L.y_real.data();
+    d.G = G;
+    d.group = L.group.empty() ? nullptr : L.group.data();
+    d.prior_alpha_sd = cfg.prior_alpha_sd;
+    d.prior_beta_sd = cfg.prior_beta_sd;
+    d.prior_sigma_loc = cfg.prior_sigma_loc;
+    d.prior_sigma_scale = cfg.prior_sigma_scale;
+    d.prior_sigma_a_scale = cfg.prior_sigma_a_scale;
+    d.device = cfg.device;
+    d.n_slots = cfg.n_slots;
+    d.world = 1;
+    return L;
+  }
+  explicit glm_model(loaded_data&& L) : glm_model(L.desc) { means_x_ = std::move(L.means); }
+
  public:
+  // The constructor signature of a stanc-generated model (model(var_context&, seed, ostream*)): reads the
+  // data block from any stan::io::var_context -- stan::json::json_data (ST/io/json/json_data.hpp:42),
+  // stan::io::dump, array_var_context -- and uploads it.  `cfg` stands for what stanc would have compiled in.
+  glm_model(const stan::io::var_context& context, const glm_config& cfg, unsigned int /*random_seed*/ = 0,
+            std::ostream* /*pstream*/ = nullptr)
+      : glm_model(load(context, cfg)) {}
+
+  // column means removed from X by glm_config::center_x (empty otherwise)
+  const std::vector<double>& means_x() const { return means_x_; }
+
   static size_t count_params(const b200glm_desc& d) {
     return (d.G > 0 ? 2 + d.G : 1) + d.K + (d.family == B200GLM_NORMAL_ID ? 1 : 0);
   }
@@ -434,6 +528,7 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
   b200glm_desc desc_;
   b200glm_handle* h_;
   unsigned long long uid_;
+  std::vector<double> means_x_;
   mutable std::unique_ptr<slot_guard[]> guards_;
   mutable std::atomic<int> next_slot_{0};
   mutable std::atomic<long> n_gradients_{0}, n_leapfrogs_{0}, n_uploads_{0};

@@ -20,12 +20,17 @@
 #include <stan/callbacks/structured_writer.hpp>
 #include <stan/callbacks/writer.hpp>
 #include <stan/io/empty_var_context.hpp>
+#include <stan/io/json/json_data.hpp>
+#include <stan/io/stan_csv_reader.hpp>
+#include <stan/callbacks/json_writer.hpp>
+#include <stan/callbacks/unique_stream_writer.hpp>
 #include <stan/model/log_prob_grad.hpp>
 #include <stan/services/sample/hmc_nuts_diag_e_adapt.hpp>
 #include <stan/services/util/create_unit_e_diag_inv_metric.hpp>
 
 #include <chrono>
 #include <cstring>
+#include <fstream>
 #include <memory>
 #include <mutex>
 #include <sstream>
@@ -111,6 +116,44 @@ void* b200stan_create(const b200glm_desc* d, char* err, int errlen) {
   glm_model* m = nullptr;
   guarded(err, errlen, [&] { m = new glm_model(*d); });
   return m;
+}
+// The stanc-style constructor: data block read by the reference's own JSON var_context
+// (stan::json::json_data, ST/io/json/json_data.hpp:42-73) from a file in CmdStan's data format.
+// names: NULL or "" keeps the default ("N", "K", "X", "y", "G", "group").
+void* b200stan_create_from_json(const char* path, int family, const char* name_y, const char* name_X, int center_x,
+                                double prior_alpha_sd, double prior_beta_sd, double prior_sigma_loc,
+                                double prior_sigma_scale, double prior_sigma_a_scale, int device, int n_slots,
+                                char* err, int errlen) {
+  glm_model* m = nullptr;
+  guarded(err, errlen, [&] {
+    std::ifstream in(path);
+    if (!in.good())
+      throw std::invalid_argument(std::string("cannot open ") + path);
+    stan::json::json_data context(in);
+    b200::glm_config cfg;
+    cfg.family = family;
+    if (name_y && *name_y)
+      cfg.name_y = name_y;
+    if (name_X && *name_X)
+      cfg.name_X = name_X;
+    cfg.center_x = center_x != 0;
+    cfg.prior_alpha_sd = prior_alpha_sd;
+    cfg.prior_beta_sd = prior_beta_sd;
+    cfg.prior_sigma_loc = prior_sigma_loc;
+    cfg.prior_sigma_scale = prior_sigma_scale;
+    cfg.prior_sigma_a_scale = prior_sigma_a_scale;
+    cfg.device = device;
+    cfg.n_slots = n_slots;
+    m = new glm_model(context, cfg);
+  });
+  return m;
+}
+// column means removed by center_x (K doubles); returns the number written (0 if not centred)
+int b200stan_means_x(void* h, double* out) {
+  const auto& mu = static_cast<glm_model*>(h)->means_x();
+  for (size_t k = 0; k < mu.size(); ++k)
+    out[k] = mu[k];
+  return static_cast<int>(mu.size());
 }
 void b200stan_destroy(void* h) { delete static_cast<glm_model*>(h); }
 // the b200glm_handle* behind the model (row-sharded runs: b200glm_peer_export / peer_connect / comm_init on it)
@@ -268,6 +311,83 @@ int b200stan_nuts_batched(void* h, int num_chains, unsigned seed, unsigned init_
   return nuts_impl(h, true, num_chains, seed, init_chain_id, init_radius, num_warmup, num_samples, stepsize, max_depth,
                    delta, 0, draws, stepsize_out, inv_metric_out, warm_leapfrogs, wall_seconds, batch_stats, err,
                    errlen);
+}
+
+// ---- output formats: the reference's own writers and reader -------------------------
+// b200stan_nuts_csv runs the same service as b200stan_nuts but hands it the writers CmdStan uses:
+//   sample  -> stan::callbacks::unique_stream_writer<std::ofstream>  (ST/callbacks/unique_stream_writer.hpp:22-36)
+//              "<prefix>_<chain>.csv": header, draws, "# Adaptation terminated / Step size / Diagonal elements
+//              of inverse mass matrix" block (mcmc_writer.hpp, run_adaptive_sampler.hpp:87-90), timing comments
+//   metric  -> stan::callbacks::json_writer<std::ofstream>            (ST/callbacks/json_writer.hpp:170-188)
+//              "<prefix>_metric_<chain>.json": {"stepsize": .., "inv_metric": [..]}
+// Warm-up draws are not saved: stan_csv_reader skips them only with CmdStan's "# save_warmup" metadata, which is
+// CmdStan's preamble, not Stan's.  Values are written with 17 significant digits so that a round trip is exact.
+int b200stan_nuts_csv(void* h, int num_chains, unsigned seed, unsigned init_chain_id, double init_radius,
+                      int num_warmup, int num_samples, double stepsize, int max_depth, double delta, int num_threads,
+                      const char* prefix, char* err, int errlen) {
+  auto& m = *static_cast<glm_model*>(h);
+  const int P = static_cast<int>(m.num_params_r());
+  int rc = 0;
+  int g = guarded(err, errlen, [&] {
+    stan::math::init_threadpool_tbb(num_threads > 0 ? num_threads : num_chains);
+    std::vector<std::shared_ptr<stan::io::var_context>> inits, metrics;
+    using csv_writer = stan::callbacks::unique_stream_writer<std::ofstream>;
+    using json_writer = stan::callbacks::json_writer<std::ofstream>;
+    std::vector<csv_writer> sample_w;
+    std::vector<json_writer> metric_w;
+    for (int c = 0; c < num_chains; ++c) {
+      inits.emplace_back(std::make_shared<stan::io::empty_var_context>());
+      metrics.emplace_back(std::make_shared<stan::io::array_var_context>(
+          stan::services::util::create_unit_e_diag_inv_metric(P)));
+      const std::string id = std::to_string(init_chain_id + c);
+      auto os = std::make_unique<std::ofstream>(std::string(prefix) + "_" + id + ".csv");
+      auto js = std::make_unique<std::ofstream>(std::string(prefix) + "_metric_" + id + ".json");
+      if (!os->good() || !js->good())
+        throw std::invalid_argument(std::string("cannot write ") + prefix + "_*.csv");
+      os->precision(17);
+      js->precision(17);
+      sample_w.emplace_back(std::move(os), "# ");
+      metric_w.emplace_back(std::move(js));
+    }
+    stan::callbacks::interrupt interrupt;
+    collecting_logger logger;
+    std::vector<stan::callbacks::writer> init_w(num_chains), diag_w(num_chains);
+    rc = stan::services::sample::hmc_nuts_diag_e_adapt(
+        m, num_chains, inits, metrics, seed, init_chain_id, init_radius, num_warmup, num_samples, 1, false, 0,
+        stepsize, 0.0, max_depth, delta, 0.05, 0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w, diag_w,
+        metric_w);
+    if (rc != 0)
+      throw std::runtime_error("hmc_nuts_diag_e_adapt rc=" + std::to_string(rc) + ": " + logger.errors);
+  });
+  return g ? g : rc;
+}
+
+// stan::io::stan_csv_reader::parse (ST/io/stan_csv_reader.hpp:350-383) on a file written above.
+// samples: [max_rows][max_cols] row-major (may be NULL to query the shape); header: comma-joined names.
+int b200stan_read_csv(const char* path, double* samples, int max_rows, int max_cols, int* n_rows, int* n_cols,
+                      double* step_size, double* metric_diag, int max_metric, int* n_metric, char* header,
+                      int header_len, char* err, int errlen) {
+  return guarded(err, errlen, [&] {
+    std::ifstream in(path);
+    if (!in.good())
+      throw std::invalid_argument(std::string("cannot open ") + path);
+    std::stringstream msgs;
+    stan::io::stan_csv csv = stan::io::stan_csv_reader::parse(in, &msgs);
+    *n_rows = static_cast<int>(csv.samples.rows());
+    *n_cols = static_cast<int>(csv.samples.cols());
+    *step_size = csv.adaptation.step_size;
+    *n_metric = static_cast<int>(csv.adaptation.metric.size());
+    for (int i = 0; i < *n_metric && i < max_metric; ++i)
+      metric_diag[i] = csv.adaptation.metric(i);
+    std::string hd;
+    for (size_t i = 0; i < csv.header.size(); ++i)
+      hd += (i ? "," : "") + csv.header[i];
+    set_err(header, header_len, hd.c_str());
+    if (samples)
+      for (int r = 0; r < *n_rows && r < max_rows; ++r)
+        for (int c = 0; c < *n_cols && c < max_cols; ++c)
+          samples[static_cast<size_t>(r) * max_cols + c] = csv.samples(r, c);
+  });
 }
 
 // ---- function-level binding (b200/glm_functions.hpp) -------------------------------------------------

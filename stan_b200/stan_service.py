@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 from . import _capi
-from .model import DomainError, InvalidArgument, CudaError, make_desc
+from .model import DomainError, InvalidArgument, CudaError, DEFAULT_PRIORS, make_desc
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libb200stan.so")
 _lib = None
@@ -61,6 +61,35 @@ class StanGLM:
         if not self.h:
             raise CudaError(err.value.decode() or "b200stan_create failed")
         self.P = self.L.b200stan_num_params(self.h)
+
+    @classmethod
+    def from_json(cls, path, family, name_y="y", name_X="X", center_x=False, device=0, n_slots=8, **priors):
+        """The stanc-style constructor b200::glm_model(var_context&, glm_config): the data block is parsed by
+        the reference's own stan::json::json_data from a CmdStan-format JSON file."""
+        self = cls.__new__(cls)
+        self.L = lib()
+        self.rank, self.world = 0, 1
+        pri = dict(DEFAULT_PRIORS)
+        pri.update(priors)
+        f = self.L.b200stan_create_from_json
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int] + [C.c_double] * 5 + [C.c_int, C.c_int,
+                                                                                                   C.c_char_p, C.c_int]
+        err = C.create_string_buffer(1024)
+        self.h = C.c_void_p(f(os.fsencode(path), _capi.FAMILY[family], name_y.encode(), name_X.encode(), int(center_x),
+                              pri["prior_alpha_sd"], pri["prior_beta_sd"], pri["prior_sigma_loc"],
+                              pri["prior_sigma_scale"], pri["prior_sigma_a_scale"], device, n_slots, err, 1024))
+        if not self.h:
+            raise InvalidArgument(err.value.decode() or "b200stan_create_from_json failed")
+        self.P = self.L.b200stan_num_params(self.h)
+        return self
+
+    def means_x(self):
+        """Column means removed from X by center_x (brms-style transformed data); empty if not centred."""
+        self.L.b200stan_means_x.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        out = np.empty(max(self.P, 1))
+        n = self.L.b200stan_means_x(self.h, _dp(out))
+        return out[:n].copy()
 
     def connect_peers_torch(self, dist, dev):
         """Row-sharded model: map every rank's mailbox (the likelihood partials are then exchanged inside
@@ -146,6 +175,18 @@ class StanGLM:
         return dict(draws=draws[:, num_warmup:, :], warmup_draws=draws[:, :num_warmup, :], stepsize=step,
                     inv_metric=inv_metric, warm_leapfrogs=warm_lf, wall=wall.value)
 
+    def nuts_csv(self, prefix, num_chains=4, seed=1, init_chain_id=1, init_radius=2.0, num_warmup=1000,
+                 num_samples=1000, stepsize=1.0, max_depth=10, delta=0.8, num_threads=0):
+        """The same service writing through the reference's CmdStan-format writers: `<prefix>_<chain>.csv`
+        (unique_stream_writer) and `<prefix>_metric_<chain>.json` (json_writer).  Returns the csv paths."""
+        err = C.create_string_buffer(4096)
+        rc = self.L.b200stan_nuts_csv(self.h, num_chains, C.c_uint(seed), C.c_uint(init_chain_id),
+                                      C.c_double(init_radius), num_warmup, num_samples, C.c_double(stepsize), max_depth,
+                                      C.c_double(delta), num_threads, os.fsencode(prefix), err, 4096)
+        if rc:
+            self._raise(rc, err)
+        return [f"{prefix}_{init_chain_id + c}.csv" for c in range(num_chains)]
+
     def nuts_batched(self, num_chains=4, seed=1, init_chain_id=1, init_radius=2.0, num_warmup=1000, num_samples=1000,
                      stepsize=1.0, max_depth=10, delta=0.8):
         """b200::hmc_nuts_diag_e_adapt_batched: one host thread per chain running the reference's single-chain
@@ -202,3 +243,22 @@ class FuncGLM:
         if rc:
             StanGLM._raise(rc, err)
         return f.value, da, db[:self.K], ds.value
+
+
+def read_stan_csv(path):
+    """stan::io::stan_csv_reader::parse: returns dict(header, samples (rows, cols), step_size, metric)."""
+    L = lib()
+    n_rows, n_cols, n_metric, step = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+    header, err = C.create_string_buffer(1 << 20), C.create_string_buffer(1024)
+    metric = np.empty(1 << 16)
+    args = lambda buf, mr, mc: (os.fsencode(path), buf, mr, mc, C.byref(n_rows), C.byref(n_cols), C.byref(step),
+                                _dp(metric), metric.size, C.byref(n_metric), header, len(header), err, 1024)
+    rc = L.b200stan_read_csv(*args(None, 0, 0))
+    if rc:
+        StanGLM._raise(rc, err)
+    samples = np.empty((n_rows.value, n_cols.value))
+    rc = L.b200stan_read_csv(*args(_dp(samples) if samples.size else None, n_rows.value, n_cols.value))
+    if rc:
+        StanGLM._raise(rc, err)
+    return dict(header=header.value.decode().split(","), samples=samples, step_size=step.value,
+                metric=metric[:n_metric.value].copy())

@@ -56,3 +56,48 @@ def test_product_does_not_import_oracle():
 def test_argument_validation_host_side():
     with pytest.raises(stan_b200.InvalidArgument):
         stan_b200.GLMModel("bernoulli_logit", np.zeros((4, 2)), np.zeros(5, np.int32))
+
+
+def test_json_data_block_is_validated_like_a_stanc_model(tmp_path):
+    """Host logic of the stanc-style constructor b200::glm_model(var_context&, glm_config): the data block is
+    read through the reference's stan::json::json_data and checked with var_context::validate_dims, so the
+    messages are the reference's.  Valid data then fails LOUDLY here (no GPU, no CPU fallback)."""
+    import json
+    from stan_b200 import stan_service
+    from stan_b200.model import InvalidArgument
+    if not stan_service.available():
+        pytest.skip("libb200stan.so not built (needs the reference headers)")
+    p = tmp_path / "d.json"
+    p.write_text(json.dumps({"N": 3, "K": 2, "X": [[1, 2], [3, 4]], "y": [0, 1, 1]}))
+    with pytest.raises(InvalidArgument, match="variable name=X.*dims declared=\\(3,2\\).*dims found=\\(2,2\\)"):
+        stan_service.StanGLM.from_json(str(p), "bernoulli_logit")
+    p.write_text(json.dumps({"N": 2, "K": 2, "X": [[1, 2], [3, 4]]}))
+    with pytest.raises(InvalidArgument, match="variable name=y"):
+        stan_service.StanGLM.from_json(str(p), "bernoulli_logit")
+    p.write_text(json.dumps({"N": 2, "K": 2, "X": [[1, 2], [3, 4]], "y": [0, 1], "G": 2, "group": [1, 3]}))
+    with pytest.raises(InvalidArgument, match="group"):
+        stan_service.StanGLM.from_json(str(p), "bernoulli_logit")
+    import torch
+    if not torch.cuda.is_available():
+        p.write_text(json.dumps({"N": 2, "K": 2, "X": [[1, 2], [3, 4]], "y": [0, 1]}))
+        with pytest.raises(InvalidArgument, match="no CUDA device"):
+            stan_service.StanGLM.from_json(str(p), "bernoulli_logit")
+
+
+def test_stan_csv_reader_binding(tmp_path):
+    """read_stan_csv is the reference's stan::io::stan_csv_reader::parse; a hand-written file in the layout the
+    services write (header, adaptation block, draws, timing) must come back value for value."""
+    from stan_b200 import stan_service
+    if not stan_service.available():
+        pytest.skip("libb200stan.so not built (needs the reference headers)")
+    p = tmp_path / "x.csv"
+    p.write_text("lp__,accept_stat__,alpha,beta.1,beta.2\n"
+                 "# Adaptation terminated\n# Step size = 0.25\n# Diagonal elements of inverse mass matrix:\n"
+                 "# 1.5, 2, 0.125\n"
+                 "-1.5,0.9,0.1,0.2,0.3\n-2.5,1,0.4,0.5,0.6\n"
+                 "# \n#  Elapsed Time: 0.1 seconds (Warm-up)\n#                0.2 seconds (Sampling)\n"
+                 "#                0.3 seconds (Total)\n# \n")
+    csv = stan_service.read_stan_csv(str(p))
+    assert csv["header"] == ["lp__", "accept_stat__", "alpha", "beta[1]", "beta[2]"]
+    assert np.array_equal(csv["samples"], [[-1.5, 0.9, 0.1, 0.2, 0.3], [-2.5, 1, 0.4, 0.5, 0.6]])
+    assert csv["step_size"] == 0.25 and np.array_equal(csv["metric"], [1.5, 2, 0.125])

@@ -5,6 +5,7 @@
 Tolerance 1e-12 relative: the port sums with compensated accumulation, the reference with Eigen's
 vectorised reductions; both are fp64, agreement is ~1e-15..1e-13.
 """
+import json
 import os
 
 import numpy as np
@@ -154,3 +155,52 @@ def test_port_oracle_consistent_with_function_level_goldens():
         assert abs((lp - pri) - ref_lp) <= 1e-11 * abs(ref_lp), c["name"]
         ob = 2 + G if G else 1
         assert np.max(np.abs(g[ob:ob + K] + b / 2.5 ** 2 - ref_db)) <= 1e-11 * np.max(np.abs(ref_db)), c["name"]
+
+
+def load_normal_glm_fixture():
+    """The reference's own normal_id_glm posterior fixture (tests/golden/make_normal_glm_fixture.py)."""
+    with open(os.path.join(ROOT, "tests", "golden", "normal_glm_data.json")) as f:
+        d = json.load(f)
+    with open(os.path.join(ROOT, "tests", "golden", "normal_glm_expected.json")) as f:
+        exp = json.load(f)
+    X, y = np.array(d["X"], dtype=np.float64), np.array(d["Y"], dtype=np.float64)
+    assert X.shape == (d["N"], d["K"])
+    return X, y, exp
+
+
+def check_against_normal_glm_answers(draws, means_X, exp):
+    """draws: (chains, iterations, P) constrained draws in OUR order [Intercept, b_1..b_K, sigma].  normal_glm.stan
+    computes the centred Xc but hands the UN-centred X to normal_id_glm_lupdf (line 27), so `Intercept` is the
+    intercept on the raw predictors and b_Intercept = Intercept - dot(means_X, b) is just a derived column.
+    Compares with the reference's published posterior means / SDs of b, Intercept, sigma and b_Intercept at the
+    reference's own bars (normal_glm_test.cpp:130-135)."""
+    K = len(means_X)
+    flat = draws.reshape(-1, draws.shape[2])
+    cols = {f"b.{k + 1}": flat[:, 1 + k] for k in range(K)}
+    cols["Intercept"] = flat[:, 0]
+    cols["sigma"] = flat[:, K + 1]
+    cols["b_Intercept"] = flat[:, 0] - flat[:, 1:1 + K] @ means_X
+    worst = 0.0
+    for name, m_ref, s_ref in zip(exp["names"], exp["mean"], exp["sd"]):
+        if name in ("lp_approx__", "lp__"):
+            continue                       # the reference's test skips these two columns as well
+        x = cols[name]
+        assert abs(x.mean() - m_ref) < exp["bars"]["mean_abs"], (name, x.mean(), m_ref)
+        assert abs(x.std(ddof=1) - s_ref) < exp["bars"]["sd_abs"], (name, x.std(ddof=1), s_ref)
+        worst = max(worst, abs(x.mean() - m_ref) / s_ref)
+    # far tighter than the reference's bar: every mean within a quarter of a posterior SD of the published value
+    assert worst < 0.25, worst
+    return worst
+
+
+def test_compiled_reference_reproduces_the_references_posterior_fixture():
+    """Pins the oracle model (priors, Jacobian, parameterisation) to the one known-answer posterior the
+    reference holds for a GLM: normal_glm.stan on normal_glm_test.json, answers from pathfinder/util.hpp."""
+    from oracle.oracle import RefOracle
+    if not RefOracle.available():
+        pytest.skip("oracle/_ref not built")
+    X, y, exp = load_normal_glm_fixture()
+    means = X.mean(axis=0)
+    ro = RefOracle("normal_id", X, y, **{k: v for k, v in exp["priors"].items() if k != "source"})
+    res = ro.nuts(num_chains=4, seed=2026, num_warmup=500, num_samples=500, delta=0.8, num_threads=4)
+    check_against_normal_glm_answers(res["draws"][:, :, 7:], means, exp)

@@ -207,3 +207,92 @@ def test_batched_driver_serves_shapes_without_dmma_kernel():
         x, y = bat["draws"][:, :, 7 + k].T, ref["draws"][:, :, 7 + k].T
         zs.append(abs(x.mean() - y.mean()) / np.hypot(Ref.mcse_mean(x), Ref.mcse_mean(y)))
     assert max(zs) < 4.5, zs
+
+
+# ---------------------------------------------------------------------------------------------------
+# data ingest + the reference's own known-answer posterior
+# ---------------------------------------------------------------------------------------------------
+def test_json_ingest_reproduces_the_references_posterior_fixture():
+    """b200::glm_model(var_context&, glm_config) fed by the reference's stan::json::json_data from a CmdStan-format
+    file, sampled by the unmodified hmc_nuts_diag_e_adapt on the GPU, against the posterior means / SDs the reference
+    publishes for this data (pathfinder/util.hpp:494-504) at the reference's bars -- and 40x tighter."""
+    import os
+    from conftest import ROOT
+    from test_oracle import check_against_normal_glm_answers, load_normal_glm_fixture
+    X, y, exp = load_normal_glm_fixture()
+    pri = {k: v for k, v in exp["priors"].items() if k != "source"}
+    path = os.path.join(ROOT, "tests", "golden", "normal_glm_data.json")
+    m = stan_service.StanGLM.from_json(path, "normal_id", name_y="Y", **pri)
+    assert m.P == X.shape[1] + 2 and m.means_x().size == 0
+    # the ingested model is the model built from the same arrays
+    m2 = stan_service.StanGLM("normal_id", X, y, **pri)
+    th = np.concatenate([[-1.0], [-4, -2, 0, 1, 3], [0.0]]) + 0.01
+    lp1, g1 = m.gradient(th)
+    lp2, g2 = m2.gradient(th)
+    assert lp1 == lp2 and np.array_equal(g1, g2)
+    m2.close()
+    kw = dict(num_chains=4, seed=2026, num_warmup=500, num_samples=500, delta=0.8, num_threads=4)
+    res = m.nuts(**kw)
+    m.close()
+    means = X.mean(axis=0)
+    check_against_normal_glm_answers(res["draws"][:, :, 7:], means, exp)
+    # brms-style centring as the Stan program INTENDED it (Xc in the likelihood): the intercept moves by
+    # dot(means_X, b), everything else is the same posterior
+    mc = stan_service.StanGLM.from_json(path, "normal_id", name_y="Y", center_x=True, **pri)
+    assert np.allclose(mc.means_x(), means, rtol=0, atol=1e-15)
+    rc = mc.nuts(**kw)["draws"][:, :, 7:]
+    mc.close()
+    K = X.shape[1]
+    flat = rc.reshape(-1, rc.shape[2])
+    raw_intercept = flat[:, 0] - flat[:, 1:1 + K] @ means
+    i_int = exp["names"].index("Intercept")
+    assert abs(raw_intercept.mean() - exp["mean"][i_int]) < 0.25 * exp["sd"][i_int]
+    for k in range(K):
+        assert abs(flat[:, 1 + k].mean() - exp["mean"][2 + k]) < 0.25 * exp["sd"][2 + k]
+
+
+def test_json_ingest_error_behaviour(tmp_path):
+    """A stanc-generated constructor rejects a data block with missing variables or wrong dimensions
+    (var_context::validate_dims -> std::runtime_error / invalid_argument); so does this one."""
+    import json as js
+    from stan_b200.model import CudaError, InvalidArgument
+    p = tmp_path / "bad.json"
+    p.write_text(js.dumps({"N": 3, "K": 2, "X": [[1, 2], [3, 4]], "y": [0, 1, 1]}))       # X has 2 rows, N = 3
+    with pytest.raises((InvalidArgument, CudaError)):
+        stan_service.StanGLM.from_json(str(p), "bernoulli_logit")
+    p.write_text(js.dumps({"N": 2, "K": 2, "X": [[1, 2], [3, 4]]}))                          # y missing
+    with pytest.raises((InvalidArgument, CudaError)):
+        stan_service.StanGLM.from_json(str(p), "bernoulli_logit")
+    with pytest.raises(InvalidArgument):
+        stan_service.StanGLM.from_json(str(tmp_path / "absent.json"), "bernoulli_logit")
+    p.write_text(js.dumps({"N": 2, "K": 2, "X": [[1, 2], [3, 4]], "y": [0, 1]}))
+    m = stan_service.StanGLM.from_json(str(p), "bernoulli_logit")
+    assert m.P == 3
+    lp, g = m.gradient(np.zeros(3))
+    assert abs(lp - 2 * np.log(0.5)) < 1e-12
+    m.close()
+
+
+def test_csv_and_json_writers_round_trip_through_stan_csv_reader(tmp_path):
+    """Output side of the path: the reference's unique_stream_writer / json_writer receive the GPU run's draws
+    and adaptation block; stan::io::stan_csv_reader parses the file back to exactly the in-memory draws."""
+    import json as js
+    d = make_glm_data("poisson_log", 3_000, 4, 3)
+    m = stan_service.StanGLM("poisson_log", d["X"], d["y"], d["group"], 3)
+    kw = dict(num_chains=2, seed=5, num_warmup=120, num_samples=60, delta=0.8, num_threads=2)
+    mem = m.nuts(**kw)
+    paths = m.nuts_csv(str(tmp_path / "out"), **kw)
+    m.close()
+    for c, path in enumerate(paths):
+        csv = stan_service.read_stan_csv(path)
+        assert csv["header"][:7] == ["lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__",
+                                     "divergent__", "energy__"]
+        # stan_csv_reader rewrites "a.2" to "a[2]" (stan_csv_reader.hpp:20-29)
+        assert csv["header"][7:] == ["mu_a", "sigma_a", "a[1]", "a[2]", "a[3]", "beta[1]", "beta[2]", "beta[3]", "beta[4]"]
+        assert csv["samples"].shape == (60, 7 + m.P)
+        assert np.array_equal(csv["samples"], mem["draws"][c])
+        assert csv["step_size"] == mem["stepsize"][c]
+        assert np.array_equal(csv["metric"], mem["inv_metric"][c])
+        with open(str(tmp_path / f"out_metric_{c + 1}.json")) as f:
+            mj = js.load(f)
+        assert mj["stepsize"] == mem["stepsize"][c] and np.array_equal(mj["inv_metric"], mem["inv_metric"][c])
