@@ -14,9 +14,12 @@
  * Model (the hand-written Stan program):
  *   G == 0: theta = [alpha, beta_1..K (, log sigma)]
  *   G  > 0: theta = [mu_a, log sigma_a, a_1..G, beta_1..K (, log sigma)]
+ *   (neg_binomial_2_log: the trailing entry is log phi, the precision, with the prior sigma has for normal_id)
  *   priors alpha|mu_a ~ N(0, prior_alpha_sd), sigma_a ~ N(0, prior_sigma_a_scale),
  *   a ~ N(mu_a, sigma_a), beta ~ N(0, prior_beta_sd), sigma ~ N(prior_sigma_loc, prior_sigma_scale)
- *   likelihood y ~ {bernoulli_logit,poisson_log,normal_id}_glm(X, alpha | a[group], beta [, sigma]).
+ *   likelihood y ~ {bernoulli_logit,poisson_log,normal_id}_glm(X, alpha | a[group], beta [, sigma]),
+ *              y ~ binomial_logit_glm(trials, X, alpha | a[group], beta),
+ *              y ~ neg_binomial_2_log_glm(X, alpha | a[group], beta, phi).
  */
 #ifndef B200GLM_H
 #define B200GLM_H
@@ -28,15 +31,18 @@
 extern "C" {
 #endif
 
-#define B200GLM_ABI_VERSION 1
+#define B200GLM_ABI_VERSION 2   /* 2: b200glm_desc gained `trials` (appended), families 3 and 4 */
 
 /* status codes; the C++ shim maps them to the exceptions the reference throws:
  * DOMAIN -> std::domain_error (recoverable: base_hamiltonian.hpp:65-68, initialize.hpp:104-112),
  * INVALID -> std::invalid_argument (check_consistent_size), CUDA -> std::runtime_error (fatal). */
 enum { B200GLM_OK = 0, B200GLM_DOMAIN = 1, B200GLM_INVALID = 2, B200GLM_CUDA = 3 };
 
-/* SM/prim/prob/{bernoulli_logit_glm_lpmf.hpp:49, poisson_log_glm_lpmf.hpp:51, normal_id_glm_lpdf.hpp:54} */
-enum { B200GLM_BERNOULLI_LOGIT = 0, B200GLM_POISSON_LOG = 1, B200GLM_NORMAL_ID = 2 };
+/* SM/prim/prob/{bernoulli_logit_glm_lpmf.hpp:49, poisson_log_glm_lpmf.hpp:51, normal_id_glm_lpdf.hpp:54,
+ * binomial_logit_glm_lpmf.hpp:55, neg_binomial_2_log_glm_lpmf.hpp:64}.  The last two run in
+ * the single-chain kernel for K <= 256; the wide-matrix and batched DMMA kernels serve families 0-2. */
+enum { B200GLM_BERNOULLI_LOGIT = 0, B200GLM_POISSON_LOG = 1, B200GLM_NORMAL_ID = 2, B200GLM_BINOMIAL_LOGIT = 3,
+       B200GLM_NEG_BINOMIAL_2_LOG = 4 };
 
 /* desc.flags: use the wide-matrix kernel (16-row panels split over the CTA; the default for K > 256)
  * even for a narrow X -- for tests of that kernel at small K */
@@ -50,7 +56,7 @@ typedef struct b200glm_desc {
   int64_t N;            /* rows held by THIS handle (the local shard when world > 1) */
   const double* X;      /* column-major N x K (Eigen::MatrixXd layout), leading dimension ldx */
   int64_t ldx;
-  const int32_t* y_int; /* bernoulli / poisson */
+  const int32_t* y_int; /* bernoulli / poisson / binomial (successes) / neg_binomial_2 */
   const double* y_real; /* normal */
   int32_t G;            /* 0 = scalar intercept, >0 = a[group] (ST/model/indexing/rvalue.hpp:154-172) */
   int32_t data_on_device; /* 0: X,y,group are host pointers (copied); 1: device pointers on `device` */
@@ -64,6 +70,7 @@ typedef struct b200glm_desc {
   int64_t N_total;      /* rows over all shards (normal_id needs N for -N log sigma); 0 => N */
   int32_t grid_ctas;    /* 0 = one persistent CTA per SM */
   int32_t flags;        /* B200GLM_FLAG_* */
+  const int32_t* trials; /* binomial_logit: population sizes (N entries; host or device like y_int); else NULL */
 } b200glm_desc;
 
 /* Data upload + one-time re-layout of X into the row-panel format the kernel streams
@@ -91,8 +98,11 @@ int b200glm_log_prob(b200glm_handle* h, int32_t slot, const double* theta, int32
 /* Function-level entry: the GLM term ALONE (no priors, no Jacobian), the slot where the reference's OpenCL
  * backend plugs in -- an overload of the density selected by argument type that returns
  * ops_partials.build(logp) (SM/opencl/prim/bernoulli_logit_glm_lpmf.hpp:52-58, :105-138).  Value and
- * partials of {bernoulli_logit,poisson_log,normal_id}_glm_lp*f<propto>(y, X, alpha, beta [, sigma]) for the
- * (y, X [, group]) the handle holds; alpha: 1 value (G == 0) or G values (alpha = a[group]).
+ * partials of {bernoulli_logit,poisson_log,normal_id}_glm_lp*f<propto>(y, X, alpha, beta [, sigma]),
+ * binomial_logit_glm_lpmf<propto>(y, trials, X, alpha, beta) or neg_binomial_2_log_glm_lpmf<propto>(y, X, alpha,
+ * beta, phi) (phi passed as `sigma`, its partial returned in d_sigma, sigma_is_var = 1 "phi is a var", 2 "phi is
+ * the ONLY var operand": y * theta then drops under propto, neg_binomial_2_log_glm_lpmf.hpp:188-190) for the
+ * (y, X [, trials] [, group]) the handle holds; alpha: 1 value (G == 0) or G values (alpha = a[group]).
  * operands_are_var = 0 with propto = 1 returns 0 as the reference does (all-constant, include_summand);
  * sigma_is_var only matters for normal_id under propto (-N log sigma kept iff sigma is an autodiff
  * variable, normal_id_glm_lpdf.hpp:205-212).  d_alpha / d_beta / d_sigma may be NULL.

@@ -18,6 +18,7 @@
  *     G  > 0:  real mu_a; real<lower=0> sigma_a; vector[G] a;   theta[0], theta[1]=log sigma_a, theta[2..2+G)
  *     vector[K] beta;
  *     family == NORMAL_ID: real<lower=0> sigma;             last entry = log sigma
+ *     family == NEG_BINOMIAL_2_LOG: real<lower=0> phi;      last entry = log phi
  *   }
  *   model {
  *     G == 0:  alpha ~ normal(0, prior_alpha_sd);
@@ -25,6 +26,7 @@
  *              a ~ normal(mu_a, sigma_a);
  *     beta ~ normal(0, prior_beta_sd);
  *     NORMAL_ID: sigma ~ normal(prior_sigma_loc, prior_sigma_scale);
+ *     NEG_BINOMIAL_2_LOG: phi ~ normal(prior_sigma_loc, prior_sigma_scale);
  *     y ~ <family>_glm(X, G == 0 ? alpha : a[group], beta [, sigma]);
  *   }
  */
@@ -37,7 +39,11 @@
 extern "C" {
 #endif
 
-enum { GLM_BERNOULLI_LOGIT = 0, GLM_POISSON_LOG = 1, GLM_NORMAL_ID = 2 };
+enum { GLM_BERNOULLI_LOGIT = 0, GLM_POISSON_LOG = 1, GLM_NORMAL_ID = 2,
+       GLM_BINOMIAL_LOGIT = 3,      /* y ~ binomial_logit_glm(trials, X, alpha, beta)          */
+       GLM_NEG_BINOMIAL_2_LOG = 4   /* y ~ neg_binomial_2_log_glm(X, alpha, beta, phi); phi is the
+                                       last parameter (log phi unconstrained), phi ~ normal(prior_sigma_loc,
+                                       prior_sigma_scale) -- the slot sigma has for NORMAL_ID */ };
 
 typedef struct glm_spec {
   int32_t family;
@@ -55,6 +61,7 @@ typedef struct glm_spec {
   double prior_sigma_loc;
   double prior_sigma_scale;
   double prior_sigma_a_scale;
+  const int32_t* trials; /* BINOMIAL_LOGIT: population sizes (N entries); NULL otherwise */
 } glm_spec;
 
 /* number of unconstrained parameters of the model the spec describes */

@@ -14,8 +14,9 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-BERNOULLI_LOGIT, POISSON_LOG, NORMAL_ID = 0, 1, 2
-FAMILY = {"bernoulli_logit": 0, "poisson_log": 1, "normal_id": 2}
+BERNOULLI_LOGIT, POISSON_LOG, NORMAL_ID, BINOMIAL_LOGIT, NEG_BINOMIAL_2_LOG = 0, 1, 2, 3, 4
+FAMILY = {"bernoulli_logit": 0, "poisson_log": 1, "normal_id": 2, "binomial_logit": 3, "neg_binomial_2_log": 4}
+HAS_SCALE = (NORMAL_ID, NEG_BINOMIAL_2_LOG)      # families with a trailing positive scalar (sigma | phi)
 
 
 class GlmSpec(C.Structure):
@@ -26,7 +27,7 @@ class GlmSpec(C.Structure):
         ("G", C.c_int32), ("_pad", C.c_int32), ("group", C.c_void_p),
         ("prior_alpha_sd", C.c_double), ("prior_beta_sd", C.c_double),
         ("prior_sigma_loc", C.c_double), ("prior_sigma_scale", C.c_double),
-        ("prior_sigma_a_scale", C.c_double),
+        ("prior_sigma_a_scale", C.c_double), ("trials", C.c_void_p),
     ]
 
 
@@ -34,7 +35,7 @@ DEFAULT_PRIORS = dict(prior_alpha_sd=2.5, prior_beta_sd=2.5, prior_sigma_loc=1.0
                       prior_sigma_scale=2.0, prior_sigma_a_scale=1.0)
 
 
-def make_spec(family, X, y, group=None, G=0, **priors):
+def make_spec(family, X, y, group=None, G=0, trials=None, **priors):
     """Returns (spec, keepalive).  X: (N,K) float64, any layout (copied to Fortran order)."""
     fam = FAMILY[family] if isinstance(family, str) else int(family)
     X = np.asfortranarray(X, dtype=np.float64)
@@ -52,6 +53,10 @@ def make_spec(family, X, y, group=None, G=0, **priors):
         yi = np.ascontiguousarray(y, dtype=np.int32)
         keep.append(yi)
         s.y_int, s.y_real = yi.ctypes.data, None
+    if fam == BINOMIAL_LOGIT:
+        ti = np.ascontiguousarray(trials, dtype=np.int32)
+        keep.append(ti)
+        s.trials = ti.ctypes.data
     s.G = int(G)
     if G:
         gi = np.ascontiguousarray(group, dtype=np.int32)
@@ -66,7 +71,7 @@ def make_spec(family, X, y, group=None, G=0, **priors):
 
 def num_params(family, K, G=0):
     fam = FAMILY[family] if isinstance(family, str) else int(family)
-    return (2 + G if G else 1) + K + (1 if fam == NORMAL_ID else 0)
+    return (2 + G if G else 1) + K + (1 if fam in HAS_SCALE else 0)
 
 
 class OracleError(RuntimeError):
@@ -182,7 +187,7 @@ class RefOracle:
 
     @classmethod
     def glm_function(cls, family, X, y, alpha, beta, sigma=1.0, group=None, G=0, propto=True, operands_are_var=True,
-                     sigma_is_var=True):
+                     sigma_is_var=True, trials=None):
         """The bare reference density stan::math::<family>_glm_lp*f<propto>(y, X, alpha | a[group], beta [, sigma])
         and its adjoints (ref_glm_function in oracle/ref/ref_oracle.cpp): returns lp, d_alpha, d_beta, d_sigma."""
         L = cls.lib()
@@ -193,6 +198,7 @@ class RefOracle:
         a = np.ascontiguousarray(np.atleast_1d(alpha), dtype=np.float64)
         b = np.ascontiguousarray(beta, dtype=np.float64)
         grp = None if group is None else np.ascontiguousarray(group, dtype=np.int32)
+        nt = None if trials is None else np.ascontiguousarray(trials, dtype=np.int32)
         lp, ds, err = C.c_double(), C.c_double(), C.create_string_buffer(1024)
         da, db = np.zeros_like(a), np.zeros(max(K, 1))
         ip = C.POINTER(C.c_int)
@@ -200,7 +206,8 @@ class RefOracle:
             C.c_int(fam), C.c_int(int(propto)), C.c_int(int(operands_are_var)), C.c_int(int(sigma_is_var)),
             C.c_longlong(N), C.c_int(K), _dp(X), y.ctypes.data_as(ip) if fam != 2 else None,
             _dp(y) if fam == 2 else None, grp.ctypes.data_as(ip) if grp is not None else None, C.c_int(int(G)),
-            _dp(a), _dp(b), C.c_double(float(sigma)), C.byref(lp), _dp(da), _dp(db), C.byref(ds), err, 1024)
+            _dp(a), _dp(b), C.c_double(float(sigma)), C.byref(lp), _dp(da), _dp(db), C.byref(ds), err, 1024,
+            nt.ctypes.data_as(ip) if nt is not None else None)
         if rc:
             raise OracleError(rc, err.value.decode())
         return lp.value, da, db[:K], ds.value

@@ -6,6 +6,8 @@
 //   stan::math::bernoulli_logit_glm_lpmf  (lib/stan_math/stan/math/prim/prob/bernoulli_logit_glm_lpmf.hpp:49)
 //   stan::math::poisson_log_glm_lpmf      (.../poisson_log_glm_lpmf.hpp:51)
 //   stan::math::normal_id_glm_lpdf        (.../normal_id_glm_lpdf.hpp:54)
+//   stan::math::binomial_logit_glm_lpmf   (.../binomial_logit_glm_lpmf.hpp:55)
+//   stan::math::neg_binomial_2_log_glm_lpmf (.../neg_binomial_2_log_glm_lpmf.hpp:64)
 //   stan::math::normal_lpdf, stan::math::lb_constrain (prim/constraint/lb_constrain.hpp:60-67),
 //   stan::model::rvalue(v, name, index_multi) (src/stan/model/indexing/rvalue.hpp:154-172)
 // It is compiled against the headers where they lie under /root/reference; no reference
@@ -32,14 +34,22 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
   std::vector<int> y_int_;
   Eigen::VectorXd y_real_;
   std::vector<int> group_;
+  std::vector<int> trials_;
   double prior_alpha_sd_, prior_beta_sd_, prior_sigma_loc_, prior_sigma_scale_,
       prior_sigma_a_scale_;
 
   static size_t count_params(const glm_spec& s) {
     size_t p = (s.G > 0 ? 2 + s.G : 1) + s.K;
-    if (s.family == GLM_NORMAL_ID)
+    if (s.family == GLM_NORMAL_ID || s.family == GLM_NEG_BINOMIAL_2_LOG)
       p += 1;
     return p;
+  }
+  // the trailing positive scalar: sigma (normal_id) or phi (neg_binomial_2_log)
+  bool has_scale() const {
+    return family_ == GLM_NORMAL_ID || family_ == GLM_NEG_BINOMIAL_2_LOG;
+  }
+  const char* scale_name() const {
+    return family_ == GLM_NEG_BINOMIAL_2_LOG ? "phi" : "sigma";
   }
 
   explicit ref_glm_model(const glm_spec& s)
@@ -66,6 +76,8 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
     }
     if (G_ > 0)
       group_.assign(s.group, s.group + N_);
+    if (family_ == GLM_BINOMIAL_LOGIT)
+      trials_.assign(s.trials, s.trials + N_);
   }
 
   ~ref_glm_model() override {}
@@ -86,8 +98,8 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
     }
     for (int k = 1; k <= K_; ++k)
       names.emplace_back("beta." + std::to_string(k));
-    if (family_ == GLM_NORMAL_ID)
-      names.emplace_back("sigma");
+    if (has_scale())
+      names.emplace_back(scale_name());
   }
 
   void get_param_names(std::vector<std::string>& names, bool = true,
@@ -98,8 +110,8 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
     } else {
       names = {"alpha", "beta"};
     }
-    if (family_ == GLM_NORMAL_ID)
-      names.emplace_back("sigma");
+    if (has_scale())
+      names.emplace_back(scale_name());
   }
   void get_dims(std::vector<std::vector<size_t>>& dimss, bool = true,
                 bool = true) const override {
@@ -112,7 +124,7 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
       dimss.push_back({});
     }
     dimss.push_back({static_cast<size_t>(K_)});
-    if (family_ == GLM_NORMAL_ID)
+    if (has_scale())
       dimss.push_back({});
   }
   // stanc-generated models APPEND here (mcmc_writer.hpp:66-77 passes a vector that already holds
@@ -152,7 +164,7 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
     }
     for (int k = 0; k < K_; ++k)
       beta[k] = params_r[pos++];
-    if (family_ == GLM_NORMAL_ID) {
+    if (has_scale()) {
       T u = params_r[pos++];
       sigma = jacobian ? stan::math::lb_constrain(u, 0, lp__)
                        : stan::math::lb_constrain(u, 0);
@@ -166,7 +178,7 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
       lp_accum__.add(normal_lpdf<propto>(alpha, 0, prior_alpha_sd_));
     }
     lp_accum__.add(normal_lpdf<propto>(beta, 0, prior_beta_sd_));
-    if (family_ == GLM_NORMAL_ID)
+    if (has_scale())
       lp_accum__.add(
           normal_lpdf<propto>(sigma, prior_sigma_loc_, prior_sigma_scale_));
 
@@ -178,6 +190,12 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
         case GLM_POISSON_LOG:
           return stan::math::poisson_log_glm_lpmf<propto>(y_int_, X_, intercept,
                                                           beta);
+        case GLM_BINOMIAL_LOGIT:
+          return stan::math::binomial_logit_glm_lpmf<propto>(
+              y_int_, trials_, X_, intercept, beta);
+        case GLM_NEG_BINOMIAL_2_LOG:
+          return stan::math::neg_binomial_2_log_glm_lpmf<propto>(
+              y_int_, X_, intercept, beta, sigma);
         default:
           return stan::math::normal_id_glm_lpdf<propto>(y_real_, X_, intercept,
                                                         beta, sigma);
@@ -211,7 +229,7 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
       c[i] = u[i];
     if (G_ > 0)
       c[1] = std::exp(u[1]);
-    if (family_ == GLM_NORMAL_ID)
+    if (has_scale())
       c[P - 1] = std::exp(u[P - 1]);
   }
   template <typename VecIn, typename VecOut>
@@ -221,7 +239,7 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
       u[i] = c[i];
     if (G_ > 0)
       u[1] = stan::math::lb_free(c[1], 0);
-    if (family_ == GLM_NORMAL_ID)
+    if (has_scale())
       u[P - 1] = stan::math::lb_free(c[P - 1], 0);
   }
 

@@ -270,14 +270,16 @@ int ref_glm_nuts(void* h, int num_chains, unsigned seed, unsigned init_chain_id,
 
 // draws: column-major n_draws x n_chains (one parameter)
 // The bare reference GLM densities (function level), for the parity test of b200glm_glm_lpmf:
-//   stan::math::{bernoulli_logit,poisson_log,normal_id}_glm_lp*f<propto>(y, X, alpha | a[group], beta [, sigma])
+//   stan::math::{bernoulli_logit,poisson_log,normal_id,binomial_logit,neg_binomial_2_log}_glm_lp*f<propto>(
+//       y, [trials,] X, alpha | a[group], beta [, sigma | phi])
 // with alpha/beta (and sigma iff sigma_is_var) as reverse-mode vars when operands_are_var, else doubles.
 int ref_glm_function(int family, int propto, int operands_are_var, int sigma_is_var, long long N, int K,
                      const double* X, const int* y_int, const double* y_real, const int* group, int G,
                      const double* alpha, const double* beta, double sigma, double* logp, double* d_alpha,
-                     double* d_beta, double* d_sigma, char* err, int errlen) {
+                     double* d_beta, double* d_sigma, char* err, int errlen, const int* trials) {
   return guarded(err, errlen, [&] {
     using stan::math::var;
+    std::vector<int> nt(trials ? trials : nullptr, trials ? trials + N : nullptr);
     Eigen::Map<const Eigen::MatrixXd> Xm(X, N, K);
     Eigen::MatrixXd Xc = Xm;
     std::vector<int> yi(y_int ? y_int : nullptr, y_int ? y_int + N : nullptr);
@@ -299,6 +301,12 @@ int ref_glm_function(int family, int propto, int operands_are_var, int sigma_is_
         if (family == 1)
           return propto ? stan::math::poisson_log_glm_lpmf<true>(yi, Xc, intercept, b)
                         : stan::math::poisson_log_glm_lpmf<false>(yi, Xc, intercept, b);
+        if (family == 3)
+          return propto ? stan::math::binomial_logit_glm_lpmf<true>(yi, nt, Xc, intercept, b)
+                        : stan::math::binomial_logit_glm_lpmf<false>(yi, nt, Xc, intercept, b);
+        if (family == 4)
+          return propto ? stan::math::neg_binomial_2_log_glm_lpmf<true>(yi, Xc, intercept, b, sg)
+                        : stan::math::neg_binomial_2_log_glm_lpmf<false>(yi, Xc, intercept, b, sg);
         return propto ? stan::math::normal_id_glm_lpdf<true>(yr, Xc, intercept, b, sg)
                       : stan::math::normal_id_glm_lpdf<false>(yr, Xc, intercept, b, sg);
       };
@@ -313,10 +321,12 @@ int ref_glm_function(int family, int propto, int operands_are_var, int sigma_is_
         a[0] = a0;
       }
       *logp = stan::math::value_of(lp);
-      if constexpr (std::is_same<TA, var>::value) {
+      if constexpr (std::is_same<TA, var>::value || std::is_same<TS, var>::value) {
         lp.grad();
-        for (int g = 0; g < nA; ++g) d_alpha[g] = a[g].adj();
-        for (int k = 0; k < K; ++k) d_beta[k] = b[k].adj();
+        if constexpr (std::is_same<TA, var>::value) {
+          for (int g = 0; g < nA; ++g) d_alpha[g] = a[g].adj();
+          for (int k = 0; k < K; ++k) d_beta[k] = b[k].adj();
+        }
         if constexpr (std::is_same<TS, var>::value) *d_sigma = sg.adj();
       }
     };
@@ -324,10 +334,12 @@ int ref_glm_function(int family, int propto, int operands_are_var, int sigma_is_
     for (int k = 0; k < K; ++k) d_beta[k] = 0;
     *d_sigma = 0;
     if (operands_are_var) {
-      if (sigma_is_var && family == 2)
+      if (sigma_is_var && (family == 2 || family == 4))
         run(var(0), var(0));
       else
         run(var(0), double(0));
+    } else if (sigma_is_var && (family == 2 || family == 4)) {
+      run(double(0), var(0));     // the scale / precision is the only autodiff operand
     } else {
       run(double(0), double(0));
     }

@@ -10,6 +10,8 @@
 //   b200::glm_data d(B200GLM_BERNOULLI_LOGIT, N, K, X.data(), y.data());      // uploads once
 //   lp += stan::math::bernoulli_logit_glm_lpmf<propto>(d.y(), d.x(), alpha, beta);   // alpha, beta: var or double
 //   lp += stan::math::poisson_log_glm_lpmf<propto>(d.y(), d.x(), b200::by_group(a), beta);   // alpha = a[group]
+//   lp += stan::math::binomial_logit_glm_lpmf<propto>(d.y(), d.trials(), d.x(), alpha, beta);
+//   lp += stan::math::neg_binomial_2_log_glm_lpmf<propto>(d.y(), d.x(), alpha, beta, phi);   // phi: var or double
 //
 // Each call is one fused single-pass launch (b200glm_glm_lpmf); the result enters the tape through
 // stan::math::precomputed_gradients.  Errors map as in stan_glm_model.hpp (DOMAIN -> std::domain_error ...).
@@ -35,6 +37,9 @@ struct y_view {
 struct x_view {
   const glm_data* d;
 };
+struct trials_view {   // binomial_logit: the population sizes held next to y
+  const glm_data* d;
+};
 // intercept given per group: alpha_i = a[group_i] with the group index the glm_data holds
 // (the model-level construct stan::model::rvalue(a, index_multi(group)), ST/model/indexing/rvalue.hpp:154-172)
 template <typename Vec>
@@ -50,7 +55,7 @@ grouped_intercept<Vec> by_group(const Vec& a) {
 class glm_data {
  public:
   glm_data(int family, long long N, int K, const double* X, const void* y, const int* group = nullptr, int G = 0,
-           int device = 0, int n_slots = 4) {
+           int device = 0, int n_slots = 4, const int* trials = nullptr) {
     b200glm_desc d = {};
     d.family = family;
     d.N = N;
@@ -63,6 +68,7 @@ class glm_data {
       d.y_int = static_cast<const int32_t*>(y);
     d.group = group;
     d.G = G;
+    d.trials = trials;
     d.prior_alpha_sd = d.prior_beta_sd = d.prior_sigma_scale = d.prior_sigma_a_scale = 1.0;  // unused: no priors here
     d.device = device;
     d.n_slots = n_slots;
@@ -88,6 +94,7 @@ class glm_data {
   }
   y_view y() const { return {this}; }
   x_view x() const { return {this}; }
+  trials_view trials() const { return {this}; }
   int family() const { return family_; }
   int K() const { return K_; }
   int G() const { return G_; }
@@ -102,7 +109,7 @@ class glm_data {
   }
 
   // value + partials; alpha has 1 (G == 0) or G entries
-  void evaluate(bool propto, bool operands_are_var, bool sigma_is_var, const double* alpha, const double* beta,
+  void evaluate(bool propto, bool operands_are_var, int sigma_is_var, const double* alpha, const double* beta,
                 double sigma, double& logp, double* d_alpha, double* d_beta, double* d_sigma) const {
     // evaluations are stateless and serialised per slot inside the library, so any mapping of
     // threads to slots is safe; a per-thread ordinal spreads concurrent callers over the slots
@@ -134,7 +141,7 @@ inline void push_vector(const Vec& v, std::vector<double>& vals, std::vector<sta
     push_scalar(v.coeff(i), vals, ops);
 }
 
-// common body of the three overloads
+// common body of all overloads
 template <bool propto, typename AlphaPush, typename T_alpha, typename T_beta, typename T_sigma>
 stan::return_type_t<T_alpha, T_beta, T_sigma> glm_call(const char* function, int family, const y_view& y,
                                                          const x_view& x, int n_alpha, AlphaPush&& push_alpha,
@@ -161,7 +168,10 @@ stan::return_type_t<T_alpha, T_beta, T_sigma> glm_call(const char* function, int
   push_scalar(sigma, vs, ops);
   double logp = 0, ds = 0;
   std::vector<double> da(va.size()), db(vb.size() + 1);
-  d.evaluate(propto, any_var, sigma_var, va.data(), vb.data(), vs[0], logp, da.data(), db.data(), &ds);
+  // sigma_is_var = 2: the scale / precision is the only autodiff operand (the terms that involve only alpha and
+  // beta drop under propto: neg_binomial_2_log_glm_lpmf.hpp:188-190)
+  d.evaluate(propto, any_var, sigma_var ? ((alpha_var || beta_var) ? 1 : 2) : 0, va.data(), vb.data(), vs[0], logp,
+             da.data(), db.data(), &ds);
   if constexpr (!any_var) {
     return logp;
   } else {
@@ -216,7 +226,53 @@ return_type_t<T_alpha, T_beta, T_sigma> normal_id_glm_lpdf(const b200::y_view& y
       static_cast<T_alpha*>(nullptr));
 }
 
+// binomial_logit_glm_lpmf(n | N, x, alpha, beta)  (SM/prim/prob/binomial_logit_glm_lpmf.hpp:55-161,
+// OpenCL counterpart SM/opencl/prim/binomial_logit_glm_lpmf.hpp)
+template <bool propto = false, typename T_alpha, typename T_beta,
+          std::enable_if_t<b200::internal::is_scalar_operand<T_alpha>::value>* = nullptr>
+return_type_t<T_alpha, T_beta> binomial_logit_glm_lpmf(const b200::y_view& n, const b200::trials_view& N,
+                                                        const b200::x_view& x, const T_alpha& alpha,
+                                                        const T_beta& beta) {
+  if (N.d != n.d)
+    throw std::invalid_argument("binomial_logit_glm_lpmf: n and N must be views of the same b200::glm_data");
+  return b200::internal::glm_call<propto>(
+      "binomial_logit_glm_lpmf", B200GLM_BINOMIAL_LOGIT, n, x, 1,
+      [&](std::vector<double>& v, std::vector<var>& o) { b200::internal::push_scalar(alpha, v, o); }, beta, 1.0,
+      static_cast<T_alpha*>(nullptr));
+}
+// neg_binomial_2_log_glm_lpmf(y | x, alpha, beta, phi)  (SM/prim/prob/neg_binomial_2_log_glm_lpmf.hpp:64-249)
+template <bool propto = false, typename T_alpha, typename T_beta, typename T_phi,
+          std::enable_if_t<b200::internal::is_scalar_operand<T_alpha>::value>* = nullptr>
+return_type_t<T_alpha, T_beta, T_phi> neg_binomial_2_log_glm_lpmf(const b200::y_view& y, const b200::x_view& x,
+                                                                   const T_alpha& alpha, const T_beta& beta,
+                                                                   const T_phi& phi) {
+  return b200::internal::glm_call<propto>(
+      "neg_binomial_2_log_glm_lpmf", B200GLM_NEG_BINOMIAL_2_LOG, y, x, 1,
+      [&](std::vector<double>& v, std::vector<var>& o) { b200::internal::push_scalar(alpha, v, o); }, beta, phi,
+      static_cast<T_alpha*>(nullptr));
+}
+
 // ---- intercept by group: alpha = a[group] ---------------------------------------------------------
+template <bool propto = false, typename Vec, typename T_beta>
+return_type_t<Vec, T_beta> binomial_logit_glm_lpmf(const b200::y_view& n, const b200::trials_view& N,
+                                                    const b200::x_view& x, const b200::grouped_intercept<Vec>& alpha,
+                                                    const T_beta& beta) {
+  if (N.d != n.d)
+    throw std::invalid_argument("binomial_logit_glm_lpmf: n and N must be views of the same b200::glm_data");
+  return b200::internal::glm_call<propto>(
+      "binomial_logit_glm_lpmf", B200GLM_BINOMIAL_LOGIT, n, x, static_cast<int>(alpha.a.size()),
+      [&](std::vector<double>& v, std::vector<var>& o) { b200::internal::push_vector(alpha.a, v, o); }, beta, 1.0,
+      static_cast<Vec*>(nullptr));
+}
+template <bool propto = false, typename Vec, typename T_beta, typename T_phi>
+return_type_t<Vec, T_beta, T_phi> neg_binomial_2_log_glm_lpmf(const b200::y_view& y, const b200::x_view& x,
+                                                               const b200::grouped_intercept<Vec>& alpha,
+                                                               const T_beta& beta, const T_phi& phi) {
+  return b200::internal::glm_call<propto>(
+      "neg_binomial_2_log_glm_lpmf", B200GLM_NEG_BINOMIAL_2_LOG, y, x, static_cast<int>(alpha.a.size()),
+      [&](std::vector<double>& v, std::vector<var>& o) { b200::internal::push_vector(alpha.a, v, o); }, beta, phi,
+      static_cast<Vec*>(nullptr));
+}
 template <bool propto = false, typename Vec, typename T_beta>
 return_type_t<Vec, T_beta> bernoulli_logit_glm_lpmf(const b200::y_view& y, const b200::x_view& x,
                                                      const b200::grouped_intercept<Vec>& alpha, const T_beta& beta) {

@@ -44,7 +44,8 @@ namespace b200 {
 // likelihood family, the prior scales and where to put the data.
 struct glm_config {
   int family = B200GLM_BERNOULLI_LOGIT;
-  std::string name_N = "N", name_K = "K", name_X = "X", name_y = "y", name_G = "G", name_group = "group";
+  std::string name_N = "N", name_K = "K", name_X = "X", name_y = "y", name_G = "G", name_group = "group",
+              name_trials = "trials";   // binomial_logit: array[N] int of population sizes
   // brms-style `transformed data`: Xc[, k] = X[, k] - mean(X[, k]); the intercept parameter is then the
   // intercept for centred predictors and b_Intercept = Intercept - dot(means_X, b) (glm_model::means_x())
   bool center_x = false;
@@ -58,7 +59,7 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
   struct loaded_data {
     b200glm_desc desc;
     std::vector<double> X, y_real, means;
-    std::vector<int> y_int, group;
+    std::vector<int> y_int, group, trials;
   };
   static loaded_data load(const stan::io::var_context& context, const glm_config& cfg) {
     // same checks and messages a stanc-generated constructor performs (validate_dims / vals_i / vals_r)
@@ -91,6 +92,10 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
       context.validate_dims(stage, cfg.name_y, "int", std::vector<size_t>{static_cast<size_t>(N)});
       L.y_int = context.vals_i(cfg.name_y);
     }
+    if (cfg.family == B200GLM_BINOMIAL_LOGIT) {
+      context.validate_dims(stage, cfg.name_trials, "int", std::vector<size_t>{static_cast<size_t>(N)});
+      L.trials = context.vals_i(cfg.name_trials);
+    }
     int G = 0;
     if (context.contains_i(cfg.name_G)) {
       context.validate_dims(stage, cfg.name_G, "int", std::vector<size_t>{});
@@ -112,6 +117,7 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
     d.y_real = L.y_real.empty() ? nullptr : L.y_real.data();
     d.G = G;
     d.group = L.group.empty() ? nullptr : L.group.data();
+    d.trials = L.trials.empty() ? nullptr : L.trials.data();
     d.prior_alpha_sd = cfg.prior_alpha_sd;
     d.prior_beta_sd = cfg.prior_beta_sd;
     d.prior_sigma_loc = cfg.prior_sigma_loc;
@@ -136,8 +142,11 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
   const std::vector<double>& means_x() const { return means_x_; }
 
   static size_t count_params(const b200glm_desc& d) {
-    return (d.G > 0 ? 2 + d.G : 1) + d.K + (d.family == B200GLM_NORMAL_ID ? 1 : 0);
+    return (d.G > 0 ? 2 + d.G : 1) + d.K + (has_scale(d.family) ? 1 : 0);
   }
+  // families with a trailing positive scalar parameter: sigma (normal_id) or phi (neg_binomial_2_log)
+  static bool has_scale(int family) { return family == B200GLM_NORMAL_ID || family == B200GLM_NEG_BINOMIAL_2_LOG; }
+  const char* scale_name() const { return desc_.family == B200GLM_NEG_BINOMIAL_2_LOG ? "phi" : "sigma"; }
 
   explicit glm_model(const b200glm_desc& desc)
       : model_base_crtp(count_params(desc)), desc_(desc), h_(nullptr), uid_(next_uid()) {
@@ -396,16 +405,16 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
     }
     for (int k = 1; k <= desc_.K; ++k)
       names.emplace_back("beta." + std::to_string(k));
-    if (desc_.family == B200GLM_NORMAL_ID)
-      names.emplace_back("sigma");
+    if (has_scale(desc_.family))
+      names.emplace_back(scale_name());
   }
   void get_param_names(std::vector<std::string>& names, bool = true, bool = true) const override {
     if (desc_.G > 0)
       names = {"mu_a", "sigma_a", "a", "beta"};
     else
       names = {"alpha", "beta"};
-    if (desc_.family == B200GLM_NORMAL_ID)
-      names.emplace_back("sigma");
+    if (has_scale(desc_.family))
+      names.emplace_back(scale_name());
   }
   void get_dims(std::vector<std::vector<size_t>>& dimss, bool = true, bool = true) const override {
     dimss.clear();
@@ -417,7 +426,7 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
       dimss.push_back({});
     }
     dimss.push_back({static_cast<size_t>(desc_.K)});
-    if (desc_.family == B200GLM_NORMAL_ID)
+    if (has_scale(desc_.family))
       dimss.push_back({});
   }
   void constrained_param_names(std::vector<std::string>& names, bool = true, bool = true) const override {
@@ -464,7 +473,7 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
       c[i] = u[i];
     if (desc_.G > 0)
       c[1] = std::exp(u[1]);
-    if (desc_.family == B200GLM_NORMAL_ID)
+    if (has_scale(desc_.family))
       c[P - 1] = std::exp(u[P - 1]);
   }
   template <typename VecIn, typename VecOut>
@@ -474,7 +483,7 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
       u[i] = c[i];
     if (desc_.G > 0)
       u[1] = stan::math::lb_free(c[1], 0);
-    if (desc_.family == B200GLM_NORMAL_ID)
+    if (has_scale(desc_.family))
       u[P - 1] = stan::math::lb_free(c[P - 1], 0);
   }
   template <typename RNG>

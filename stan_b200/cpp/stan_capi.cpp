@@ -392,9 +392,9 @@ int b200stan_read_csv(const char* path, double* samples, int max_rows, int max_c
 
 // ---- function-level binding (b200/glm_functions.hpp) -------------------------------------------------
 void* b200stan_func_create(int family, long long N, int K, const double* X, const void* y, const int* group, int G,
-                           char* err, int errlen) {
+                           char* err, int errlen, const int* trials) {
   b200::glm_data* d = nullptr;
-  guarded(err, errlen, [&] { d = new b200::glm_data(family, N, K, X, y, group, G); });
+  guarded(err, errlen, [&] { d = new b200::glm_data(family, N, K, X, y, group, G, 0, 4, trials); });
   return d;
 }
 void b200stan_func_destroy(void* d) { delete static_cast<b200::glm_data*>(d); }
@@ -427,6 +427,12 @@ int b200stan_func_eval(void* dv, int propto, int operands_are_var, int sigma_is_
         else if (d.family() == B200GLM_POISSON_LOG)
           lp = G > 0 ? stan::math::poisson_log_glm_lpmf<P>(d.y(), d.x(), b200::by_group(a), b)
                      : stan::math::poisson_log_glm_lpmf<P>(d.y(), d.x(), a0, b);
+        else if (d.family() == B200GLM_BINOMIAL_LOGIT)
+          lp = G > 0 ? stan::math::binomial_logit_glm_lpmf<P>(d.y(), d.trials(), d.x(), b200::by_group(a), b)
+                     : stan::math::binomial_logit_glm_lpmf<P>(d.y(), d.trials(), d.x(), a0, b);
+        else if (d.family() == B200GLM_NEG_BINOMIAL_2_LOG)
+          lp = G > 0 ? stan::math::neg_binomial_2_log_glm_lpmf<P>(d.y(), d.x(), b200::by_group(a), b, sg)
+                     : stan::math::neg_binomial_2_log_glm_lpmf<P>(d.y(), d.x(), a0, b, sg);
         else
           lp = G > 0 ? stan::math::normal_id_glm_lpdf<P>(d.y(), d.x(), b200::by_group(a), b, sg)
                      : stan::math::normal_id_glm_lpdf<P>(d.y(), d.x(), a0, b, sg);
@@ -440,21 +446,26 @@ int b200stan_func_eval(void* dv, int propto, int operands_are_var, int sigma_is_
       for (int g = 0; g < n_alpha; ++g) d_alpha[g] = 0;
       for (int k = 0; k < K; ++k) d_beta[k] = 0;
       *d_sigma = 0;
-      if constexpr (std::is_same<TO, var>::value) {
+      if constexpr (std::is_same<TO, var>::value || std::is_same<TS, var>::value) {
         total.grad();
-        if (G > 0)
-          for (int g = 0; g < n_alpha; ++g) d_alpha[g] = a[g].adj();
-        else
-          d_alpha[0] = a0.adj();
-        for (int k = 0; k < K; ++k) d_beta[k] = b[k].adj();
+        if constexpr (std::is_same<TO, var>::value) {
+          if (G > 0)
+            for (int g = 0; g < n_alpha; ++g) d_alpha[g] = a[g].adj();
+          else
+            d_alpha[0] = a0.adj();
+          for (int k = 0; k < K; ++k) d_beta[k] = b[k].adj();
+        }
         if constexpr (std::is_same<TS, var>::value) *d_sigma = sg.adj();
       }
     };
+    const bool has_scale = d.family() == B200GLM_NORMAL_ID || d.family() == B200GLM_NEG_BINOMIAL_2_LOG;
     if (operands_are_var) {
-      if (sigma_is_var && d.family() == B200GLM_NORMAL_ID)
+      if (sigma_is_var && has_scale)
         run(var(0), var(0));
       else
         run(var(0), double(0));
+    } else if (sigma_is_var && has_scale) {
+      run(double(0), var(0));     // the scale / precision is the only autodiff operand
     } else {
       run(double(0), double(0));
     }

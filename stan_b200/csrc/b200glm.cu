@@ -160,6 +160,8 @@ kernel_fn pick_kernel(int family, int cpl) {
     case FAM_BERNOULLI_LOGIT: return pick_cpl<FAM_BERNOULLI_LOGIT>(cpl);
     case FAM_POISSON_LOG: return pick_cpl<FAM_POISSON_LOG>(cpl);
     case FAM_NORMAL_ID: return pick_cpl<FAM_NORMAL_ID>(cpl);
+    case FAM_BINOMIAL_LOGIT: return pick_cpl<FAM_BINOMIAL_LOGIT>(cpl);
+    case FAM_NEG_BINOMIAL_2_LOG: return pick_cpl<FAM_NEG_BINOMIAL_2_LOG>(cpl);
   }
   return nullptr;
 }
@@ -205,6 +207,13 @@ int validate_slot(b200glm_handle* h, int slot) {
   return B200GLM_OK;
 }
 
+// Rows the likelihood term runs over (all shards).  Reference quirk kept: binomial_logit_glm_lpmf returns 0 for
+// an empty weight vector (size_zero(n, N, alpha, beta, x), binomial_logit_glm_lpmf.hpp:77-79).
+long long lik_rows_total(const b200glm_handle* h) {
+  if (h->d.family == B200GLM_BINOMIAL_LOGIT && h->d.K == 0) return 0;
+  return h->d.N_total > 0 ? h->d.N_total : h->d.N;
+}
+
 void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int propto, int jacobian, int is_var,
                  double eps, int lik_only = 0, int sigma_is_var = 0) {
   std::memset(&p, 0, sizeof(p));
@@ -243,7 +252,7 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
   p.inv_metric = s->inv_metric;
   p.eps = eps;
   p.partials = s->partials;
-  p.pstride = (h->d.K + 2 + 1) & ~1;
+  p.pstride = partial_stride(h->d.K);
   p.ticket = s->ticket;
   p.r_out = s->r_out;
   p.lik = s->lik;
@@ -260,7 +269,7 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
   mc.is_var = is_var;
   mc.lik_only = lik_only;
   mc.sigma_is_var = sigma_is_var;
-  mc.N_total = (double)(h->d.N_total > 0 ? h->d.N_total : h->d.N);
+  mc.N_total = (double)lik_rows_total(h);
   mc.lgamma_sum = h->lgamma_sum_total;
   mc.prior_alpha_sd = h->d.prior_alpha_sd;
   mc.prior_beta_sd = h->d.prior_beta_sd;
@@ -274,7 +283,7 @@ int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian,
                  int lik_only = 0, int sigma_is_var = 0) {
   KernelParams p;
   const bool need_likelihood = ((!propto) || is_var) && h->d.N_total != -1;
-  const bool rows_anywhere = (h->d.N_total > 0 ? h->d.N_total : h->d.N) > 0;
+  const bool rows_anywhere = lik_rows_total(h) > 0;
   const bool exchange = need_likelihood && rows_anywhere && h->peer_on;
   if (exchange) ++s->peer_seq;
   fill_params(h, s, p, mode, propto, jacobian, is_var, eps, lik_only, sigma_is_var);
@@ -308,10 +317,11 @@ int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian,
     // nothing data-dependent left (double semantics with propto, or N == 0): epilogue only
     CUDA_TRY(h, cudaMemsetAsync(s->lik, 0, sizeof(double) * (h->P + 2), s->stream));
     if (mode == MODE_LEAPFROG) {
-      h->set_error("leapfrog requires the gradient path");
-      return B200GLM_INVALID;
+      theta_from_state_kernel<<<1, NUM_THREADS, 0, s->stream>>>(p);
+      h->launches++;
+    } else {
+      CUDA_TRY(h, cudaMemcpyAsync(s->theta_used, s->theta, sizeof(double) * h->P, cudaMemcpyDeviceToDevice, s->stream));
     }
-    CUDA_TRY(h, cudaMemcpyAsync(s->theta_used, s->theta, sizeof(double) * h->P, cudaMemcpyDeviceToDevice, s->stream));
     finish_kernel<<<1, NUM_THREADS, 0, s->stream>>>(p);
     h->launches++;
   }
@@ -338,10 +348,14 @@ int eval_host(b200glm_handle* h, int slot, const double* theta, int propto, int 
   double* hres = s->h_pinned + (3 * P + 1);
   CUDA_TRY(h, cudaMemcpyAsync(hres, s->result, sizeof(double) * (P + 2), cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(h, cudaStreamSynchronize(s->stream));
-  if (h->bad_y && (is_var || !propto)) {
-    h->set_error(h->d.family == B200GLM_BERNOULLI_LOGIT
-                     ? "bernoulli_logit_glm_lpmf: Vector of dependent variables is out of range [0, 1]"
-                     : "poisson_log_glm_lpmf: Vector of dependent variables is negative");
+  // neg_binomial_2_log checks y before its include_summand early return (neg_binomial_2_log_glm_lpmf.hpp:130-135)
+  if (h->bad_y && (is_var || !propto || h->d.family == B200GLM_NEG_BINOMIAL_2_LOG) && lik_rows_total(h) > 0) {
+    static const char* const msg[] = {
+        "bernoulli_logit_glm_lpmf: Vector of dependent variables is out of range [0, 1]",
+        "poisson_log_glm_lpmf: Vector of dependent variables is negative", "",
+        "binomial_logit_glm_lpmf: Successes variable is out of range [0, Population size parameter]",
+        "neg_binomial_2_log_glm_lpmf: Failures variables is negative"};
+    h->set_error(msg[h->d.family]);
     return B200GLM_DOMAIN;
   }
   if (hres[P + 1] == (double)ST_PEER_TIMEOUT) {
@@ -381,6 +395,7 @@ int64_t b200glm_bytes_per_gradient(const b200glm_handle* h) {
   // 8*N*K (X once) + 4*N (y int32; 8*N for normal's fp64 y) [+ 4*N group index]
   const int64_t N = h->d.N, K = h->d.K;
   int64_t b = 8 * N * K + (h->d.family == B200GLM_NORMAL_ID ? 8 : 4) * N;
+  if (h->d.family == B200GLM_BINOMIAL_LOGIT) b += 4 * N;   // population sizes
   if (h->d.G > 0) b += 4 * N;
   return b;
 }
@@ -437,7 +452,8 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     return code;
   };
   const b200glm_desc& d = h->d;
-  if (d.family < 0 || d.family > 2) return fail(B200GLM_INVALID, "unknown family");
+  if (d.family < 0 || d.family > 4) return fail(B200GLM_INVALID, "unknown family");
+  if (d.N > 0 && d.family == B200GLM_BINOMIAL_LOGIT && !d.trials) return fail(B200GLM_INVALID, "trials is null");
   if (d.N < 0 || d.K < 0 || d.G < 0) return fail(B200GLM_INVALID, "negative size");
   if (d.N > 0 && d.K > 0 && (!d.X || d.ldx < d.N)) return fail(B200GLM_INVALID, "X null or ldx < N");
   if (d.N > 0 && d.family == B200GLM_NORMAL_ID && !d.y_real) return fail(B200GLM_INVALID, "y_real is null");
@@ -445,10 +461,12 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   if (d.G > 0 && d.N > 0 && !d.group) return fail(B200GLM_INVALID, "group is null");
   if (!(d.prior_alpha_sd > 0) || !(d.prior_beta_sd > 0)) return fail(B200GLM_INVALID, "prior scales must be > 0");
   if (d.n_slots < 1) h->d.n_slots = 1;
-  h->P = (d.G > 0 ? 2 + d.G : 1) + d.K + (d.family == B200GLM_NORMAL_ID ? 1 : 0);
+  h->P = (d.G > 0 ? 2 + d.G : 1) + d.K + (fam_has_scale(d.family) ? 1 : 0);
   h->off_beta = d.G > 0 ? 2 + d.G : 1;
-  h->C = d.K + 1 + (d.G > 0 ? 1 : 0);
+  h->C = fam_group_col(d.family, d.K) + (d.G > 0 ? 1 : 0);
   h->wide = d.K > 256 || (d.flags & B200GLM_FLAG_FORCE_WIDE);
+  if (h->wide && d.family > B200GLM_NORMAL_ID)
+    return fail(B200GLM_INVALID, "binomial_logit / neg_binomial_2_log are served by the single-chain kernel for K <= 256 only");
   h->panel_rows = h->wide ? wide_rows_for(h->C) : PANEL_ROWS;
   h->n_panels = (d.N + h->panel_rows - 1) / h->panel_rows;
   const int P = h->P;
@@ -516,6 +534,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   int32_t* d_y = nullptr;
   double* d_yr = nullptr;
   int32_t* d_group = nullptr;
+  int32_t* d_trials = nullptr;
   long long* d_perm = nullptr;
   bool own_y = false, own_group = false;
   if (d.N > 0) {
@@ -523,6 +542,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
       d_y = const_cast<int32_t*>(d.y_int);
       d_yr = const_cast<double*>(d.y_real);
       d_group = const_cast<int32_t*>(d.group);
+      d_trials = const_cast<int32_t*>(d.trials);
     } else {
       if (d.family == B200GLM_NORMAL_ID) {
         CUDA_TRY(h, cudaMalloc(&d_yr, sizeof(double) * d.N));
@@ -530,6 +550,10 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
       } else {
         CUDA_TRY(h, cudaMalloc(&d_y, sizeof(int32_t) * d.N));
         CUDA_TRY(h, cudaMemcpy(d_y, d.y_int, sizeof(int32_t) * d.N, cudaMemcpyHostToDevice));
+        if (d.family == B200GLM_BINOMIAL_LOGIT) {
+          CUDA_TRY(h, cudaMalloc(&d_trials, sizeof(int32_t) * d.N));
+          CUDA_TRY(h, cudaMemcpy(d_trials, d.trials, sizeof(int32_t) * d.N, cudaMemcpyHostToDevice));
+        }
       }
       own_y = true;
       if (d.G > 0) {
@@ -544,7 +568,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     const int nb = 296;
     double* d_stats;
     CUDA_TRY(h, cudaMalloc(&d_stats, sizeof(double) * 2 * nb));
-    y_stats_kernel<<<nb, 256, 0, st>>>(d_y, d.N, d.family, d_stats);
+    y_stats_kernel<<<nb, 256, 0, st>>>(d_y, d_trials, d.N, d.family, d_stats);
     std::vector<double> hs(2 * nb);
     CUDA_TRY(h, cudaMemcpyAsync(hs.data(), d_stats, sizeof(double) * 2 * nb, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
@@ -571,7 +595,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     for (long long i = 0; i < d.N; ++i) {
       const int g = h_group[i];
       if (g < 1 || g > d.G) {
-        if (own_y) { cudaFree(d_y); cudaFree(d_yr); }
+        if (own_y) { cudaFree(d_y); cudaFree(d_yr); cudaFree(d_trials); }
         if (own_group) cudaFree(d_group);
         return fail(B200GLM_INVALID, "group index out of range [1, G]");
       }
@@ -594,7 +618,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   const int PR = h->panel_rows, SWZ = h->wide ? 0 : 1;
   if (d.N > 0) {
     if (d.data_on_device || d.K == 0) {
-      relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(d.X, d.ldx, 0, d_y, d_yr, d_group, d_perm, 0, d.N,
+      relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(d.X, d.ldx, 0, d_y, d_yr, d_group, d_trials, d_perm, 0, d.N,
                                                                     d.N, d.K, h->C, 0, h->Cpad, h->panels, PR, h->Cpad, SWZ);
       CUDA_TRY(h, cudaGetLastError());
     } else if (d_perm) {
@@ -603,7 +627,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
       CUDA_TRY(h, cudaMalloc(&dX, sizeof(double) * (size_t)d.N * d.K));
       CUDA_TRY(h, cudaMemcpy2D(dX, sizeof(double) * d.N, d.X, sizeof(double) * d.ldx, sizeof(double) * d.N, d.K,
                                cudaMemcpyHostToDevice));
-      relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(dX, d.N, 0, d_y, d_yr, d_group, d_perm, 0, d.N,
+      relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(dX, d.N, 0, d_y, d_yr, d_group, d_trials, d_perm, 0, d.N,
                                                                     d.N, d.K, h->C, 0, h->Cpad, h->panels, PR, h->Cpad, SWZ);
       CUDA_TRY(h, cudaStreamSynchronize(st));
       cudaFree(dX);
@@ -615,25 +639,25 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
         const long long nr = std::min(chunk_rows, (long long)d.N - r0);
         CUDA_TRY(h, cudaMemcpy2DAsync(dX, sizeof(double) * nr, d.X + r0, sizeof(double) * d.ldx, sizeof(double) * nr,
                                       d.K, cudaMemcpyHostToDevice, st));
-        relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(dX, nr, r0, nullptr, nullptr, nullptr, nullptr,
+        relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(dX, nr, r0, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                                       r0, nr, d.N, d.K, h->C, 0, d.K, h->panels, PR, h->Cpad, SWZ);
         CUDA_TRY(h, cudaStreamSynchronize(st));
       }
       cudaFree(dX);
       // aux columns (y, group) in one more pass
-      relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(nullptr, 0, 0, d_y, d_yr, d_group, nullptr, 0, d.N,
+      relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(nullptr, 0, 0, d_y, d_yr, d_group, d_trials, nullptr, 0, d.N,
                                                                     d.N, d.K, h->C, d.K, h->Cpad, h->panels, PR, h->Cpad, SWZ);
     }
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaStreamSynchronize(st));
   }
-  if (own_y) { cudaFree(d_y); cudaFree(d_yr); }
+  if (own_y) { cudaFree(d_y); cudaFree(d_yr); cudaFree(d_trials); }
   if (own_group) cudaFree(d_group);
   cudaFree(d_perm);
   cudaStreamDestroy(st);
 
   // ---- slots ----
-  const int pstride = (d.K + 2 + 1) & ~1;
+  const int pstride = partial_stride(d.K);
   for (int i = 0; i < h->d.n_slots; ++i) {
     Slot* s = new Slot();
     h->slots.push_back(s);
@@ -679,9 +703,11 @@ int b200glm_glm_lpmf(b200glm_handle* h, int32_t slot, int32_t propto, int32_t op
     return B200GLM_INVALID;
   }
   const int P = h->P, G = h->d.G, K = h->d.K;
-  const bool normal = h->d.family == B200GLM_NORMAL_ID;
+  const bool normal = fam_has_scale(h->d.family);   // a trailing positive scalar: sigma | phi
   if (normal && !(sigma > 0.0 && std::isfinite(sigma))) {
-    h->set_error("normal_id_glm_lpdf: Scale vector is not positive finite");   // normal_id_glm_lpdf.hpp:93
+    h->set_error(h->d.family == B200GLM_NORMAL_ID
+                     ? "normal_id_glm_lpdf: Scale vector is not positive finite"                 // normal_id_glm_lpdf.hpp:93
+                     : "neg_binomial_2_log_glm_lpmf: Precision parameter is not positive finite");  // neg_binomial_2_log_glm_lpmf.hpp:131
     return B200GLM_DOMAIN;
   }
   std::vector<double> th(P, 0.0), g(P, 0.0);
@@ -692,7 +718,7 @@ int b200glm_glm_lpmf(b200glm_handle* h, int32_t slot, int32_t propto, int32_t op
   if (K > 0) std::memcpy(th.data() + h->off_beta, beta, sizeof(double) * K);
   if (normal) th[P - 1] = std::log(sigma);
   const int rc = eval_host(h, slot, th.data(), propto ? 1 : 0, 0, operands_are_var ? 1 : 0, logp, g.data(), 1,
-                           sigma_is_var ? 1 : 0);
+                           sigma_is_var == 2 ? 2 : (sigma_is_var ? 1 : 0));
   if (rc) return rc;
   if (d_alpha) std::memcpy(d_alpha, G > 0 ? g.data() + 2 : g.data(), sizeof(double) * (G > 0 ? G : 1));
   if (d_beta && K > 0) std::memcpy(d_beta, g.data() + h->off_beta, sizeof(double) * K);
@@ -910,8 +936,9 @@ int b200glm_batch_reserve(b200glm_handle* h, int32_t max_chains) {
     h->set_error("batch workspace already reserved with fewer chain slots");
     return B200GLM_INVALID;
   }
-  if (h->wide || h->d.G > 0 || h->d.world > 1 || h->d.K > BATCH_MAX_K) {
-    h->set_error("batched chains need K <= 208, a scalar intercept (G == 0) and an unsharded handle");
+  if (h->wide || h->d.G > 0 || h->d.world > 1 || h->d.K > BATCH_MAX_K || h->d.family > B200GLM_NORMAL_ID) {
+    h->set_error("batched chains need K <= 208, a scalar intercept (G == 0), an unsharded handle and one of the "
+                 "bernoulli_logit / poisson_log / normal_id families");
     return B200GLM_INVALID;
   }
   CUDA_TRY(h, cudaSetDevice(h->d.device));

@@ -4,13 +4,17 @@
 //   stan::math::bernoulli_logit_glm_lpmf  (SM/prim/prob/bernoulli_logit_glm_lpmf.hpp:105-164)
 //   stan::math::poisson_log_glm_lpmf      (SM/prim/prob/poisson_log_glm_lpmf.hpp:107-161)
 //   stan::math::normal_id_glm_lpdf        (SM/prim/prob/normal_id_glm_lpdf.hpp:117-213)
+// and, in the single-chain kernel for K <= 256 ("the remaining GLMs"),
+//   stan::math::binomial_logit_glm_lpmf      (SM/prim/prob/binomial_logit_glm_lpmf.hpp:104-157)
+//   stan::math::neg_binomial_2_log_glm_lpmf  (SM/prim/prob/neg_binomial_2_log_glm_lpmf.hpp:145-246)
 // plus the model wrapper (priors, lb_constrain Jacobian) and the leapfrog update
 // (ST/mcmc/hmc/integrators/expl_leapfrog.hpp:16-32).  How it is computed is new: ONE pass over X.
 //
 // Data layout in HBM ("row-panel format", built once at upload by relayout_kernel):
 //   rows are cut into panels of 32; panel p is one contiguous block of C = K + n_aux columns,
 //   each column 32 doubles:  panel[p][c][ r ^ swz(c) ],  swz(c) = (c & 3) << 2.
-//   aux column K holds y (as double), aux column K+1 the 1-based group id (as double) when G > 0.
+//   aux column K holds y (as double), then the binomial population sizes (binomial_logit only), then
+//   the 1-based group id (as double) when G > 0.
 //   One panel = C*256 bytes = one cp.async.bulk (TMA, SASS UBLKCP) into one shared-memory stage.
 //   The XOR swizzle makes BOTH access patterns below bank-conflict free.
 //
@@ -36,7 +40,14 @@ constexpr int NUM_THREADS = (NUM_CONSUMER_WARPS + 1) * 32;
 constexpr int MAX_STAGES = 32;
 constexpr int SMEM_A_MAX_GROUPS = 2048;  // a[G] staged in smem up to this many groups
 
-enum { FAM_BERNOULLI_LOGIT = 0, FAM_POISSON_LOG = 1, FAM_NORMAL_ID = 2 };
+enum { FAM_BERNOULLI_LOGIT = 0, FAM_POISSON_LOG = 1, FAM_NORMAL_ID = 2, FAM_BINOMIAL_LOGIT = 3,
+       FAM_NEG_BINOMIAL_2_LOG = 4 };
+// families with a trailing positive scalar parameter: sigma (normal_id) or phi (neg_binomial_2_log)
+__host__ __device__ constexpr bool fam_has_scale(int f) { return f == FAM_NORMAL_ID || f == FAM_NEG_BINOMIAL_2_LOG; }
+// aux columns of a panel: y at K, trials at K+1 (binomial_logit only), group id after those (G > 0 only)
+__host__ __device__ constexpr int fam_group_col(int f, int K) { return K + 1 + (f == FAM_BINOMIAL_LOGIT ? 1 : 0); }
+// doubles per CTA partial row: K beta gradients, lp-sum, r-sum, aux-sum (d/dphi terms of neg_binomial_2_log)
+__host__ __device__ constexpr int partial_stride(int K) { return (K + 3 + 1) & ~1; }
 enum { MODE_THETA = 0, MODE_LEAPFROG = 1 };
 enum { ST_OK = 0, ST_DOMAIN = 1, ST_PEER_TIMEOUT = 2 };
 
@@ -48,9 +59,12 @@ struct ModelConst {
   int propto, jacobian, is_var;  // semantics of this evaluation (see include/b200glm.h)
   int lik_only;                  // function-level call (b200glm_glm_lpmf): the GLM term alone -- no priors, no
                                  // Jacobian; the sigma entry of the gradient is d/d sigma, not d/d log sigma
-  int sigma_is_var;              // lik_only + normal_id: keep -N log sigma under propto (normal_id_glm_lpdf.hpp:205)
+  int sigma_is_var;              // lik_only + normal_id: keep -N log sigma under propto (normal_id_glm_lpdf.hpp:205);
+                                 // lik_only + neg_binomial_2_log: phi is an autodiff variable (the phi-only terms
+                                 // stay); 2 = phi is the ONLY variable operand (y * theta drops under propto)
   double N_total;                // rows over all shards
-  double lgamma_sum;             // sum lgamma(y+1) over all shards (poisson, propto=0)
+  double lgamma_sum;             // propto=0 constant over all shards, subtracted: sum lgamma(y+1) (poisson,
+                                 // neg_binomial_2_log), -sum binomial_coefficient_log(trials, y) (binomial_logit)
   double prior_alpha_sd, prior_beta_sd, prior_sigma_loc, prior_sigma_scale, prior_sigma_a_scale;
 };
 
@@ -183,6 +197,60 @@ __device__ __forceinline__ void link(double eta, double y, double inv_sigma, dou
   }
 }
 
+// digamma(x), x > 0 (the reference calls boost::math::digamma): recurrence up to x >= 12, two steps per
+// division, then the asymptotic series through x^-14 (truncation < 1e-17 there).
+__device__ __forceinline__ double digamma_pos(double x) {
+  double acc = 0.0;
+  while (x < 12.0) {
+    const double x1 = x + 1.0;
+    acc -= (x + x1) / (x * x1);
+    x += 2.0;
+  }
+  const double i2 = 1.0 / (x * x);
+  const double ser = i2 * (1.0 / 12 - i2 * (1.0 / 120 - i2 * (1.0 / 252 - i2 * (1.0 / 240 - i2 * (1.0 / 132
+                     - i2 * (691.0 / 32760 - i2 * (1.0 / 12)))))));
+  return acc + log(x) - 0.5 / x - ser;
+}
+
+// Per-launch constants of the link step.
+struct LinkConst {
+  double inv_sigma;               // normal_id: 1 / sigma
+  double phi, log_phi, dg_phi;    // neg_binomial_2_log: phi, log(phi), digamma(phi)
+  int inc_phi_terms;              // neg_binomial_2_log: lgamma(y + phi) belongs to logp (phi is a parameter or !propto)
+  int inc_ytheta;                 // neg_binomial_2_log: y * theta belongs to logp (alpha / beta are parameters or !propto)
+};
+
+// Link step of the single-chain kernel: link<> above plus the two families that need more than (eta, y):
+// `aux` is the binomial population size, x_i the per-row term of d logp / d phi (neg_binomial_2_log).
+template <int FAMILY>
+__device__ __forceinline__ void link_ext(double eta, double y, double aux, const LinkConst& lc, double& lp_i,
+                                         double& r_i, double& x_i) {
+  x_i = 0.0;
+  if (FAMILY == FAM_BINOMIAL_LOGIT) {
+    // log_inv_logit.hpp:34-40, log1m_inv_logit.hpp:36-42 (both share exp(-|eta|) and its log1p),
+    // binomial_logit_glm_lpmf.hpp:117-118 logp, :135-136 theta_derivative
+    const double l = log1p(exp(-fabs(eta)));
+    const double lil = eta < 0.0 ? eta - l : -l;
+    const double l1m = eta > 0.0 ? -eta - l : -l;
+    lp_i = y * lil + (aux - y) * l1m;
+    r_i = y - aux * exp(lil);
+  } else if (FAMILY == FAM_NEG_BINOMIAL_2_LOG) {
+    // neg_binomial_2_log_glm_lpmf.hpp:153-157 logsumexp_theta_logphi, :186-197 logp, :205-208 theta_derivative,
+    // :240-245 d/dphi (per-row form; the leading N of the scalar-phi branch is the 1 added to every row)
+    const double ypp = y + lc.phi;
+    const double lse = eta > lc.log_phi ? eta + log1p(exp(lc.log_phi - eta)) : lc.log_phi + log1p(exp(eta - lc.log_phi));
+    const double te = exp(eta);
+    const double den = te + lc.phi;
+    lp_i = -ypp * lse;
+    if (lc.inc_ytheta) lp_i += y * eta;          // :188-190 include_summand<propto, T_x, T_alpha, T_beta>
+    if (lc.inc_phi_terms) lp_i += lgamma(ypp);   // :191-197 include_summand<propto, T_precision>
+    r_i = y - te * ypp / den;
+    x_i = 1.0 - ypp / den + lc.log_phi - lse + digamma_pos(ypp) - lc.dg_phi;
+  } else {
+    link<FAMILY>(eta, y, lc.inv_sigma, lp_i, r_i);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // All-reduce (sum) of the P+2 likelihood partials across the row shards, INSIDE the launch that
 // produced them: one CTA per rank pushes its partial into every rank's mailbox with peer stores,
@@ -265,8 +333,9 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
   const double mu_a = G > 0 ? theta[0] : 0.0;
   const double u_sa = G > 0 ? theta[1] : 0.0;
   const double sigma_a = G > 0 ? exp(u_sa) : 1.0;
-  const double u_s = mc.family == FAM_NORMAL_ID ? theta[P - 1] : 0.0;
-  const double sigma = mc.family == FAM_NORMAL_ID ? exp(u_s) : 1.0;
+  const bool has_scale = fam_has_scale(mc.family);   // sigma (normal_id) | phi (neg_binomial_2_log)
+  const double u_s = has_scale ? theta[P - 1] : 0.0;
+  const double sigma = has_scale ? exp(u_s) : 1.0;
   const double ib2 = 1.0 / (mc.prior_beta_sd * mc.prior_beta_sd);
   const double isa2 = 1.0 / (sigma_a * sigma_a);
 
@@ -314,7 +383,7 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
     double lp = 0.0;
     if (mc.jacobian && !mc.lik_only) {
       if (G > 0) lp += u_sa;                           // lb_constrain.hpp:64
-      if (mc.family == FAM_NORMAL_ID) lp += u_s;
+      if (has_scale) lp += u_s;
     }
     if (dens && !mc.lik_only) {
       // priors: normal_lpdf.hpp:81-88
@@ -336,7 +405,7 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
         lp += -0.5 * sum_b2 * ib2;
         if (!mc.propto) lp += K * (NEG_LOG_SQRT_TWO_PI_D - log(mc.prior_beta_sd));
       }
-      if (mc.family == FAM_NORMAL_ID) {
+      if (has_scale) {
         const double z = (sigma - mc.prior_sigma_loc) / mc.prior_sigma_scale;
         lp += -0.5 * z * z;
         if (!mc.propto) lp += NEG_LOG_SQRT_TWO_PI_D - log(mc.prior_sigma_scale);
@@ -348,9 +417,14 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
         const double S = lik[P];
         if (mc.family == FAM_BERNOULLI_LOGIT) {
           lp += S;
-        } else if (mc.family == FAM_POISSON_LOG) {
+        } else if (mc.family == FAM_POISSON_LOG || mc.family == FAM_BINOMIAL_LOGIT) {
           lp += S;
-          if (!mc.propto) lp -= mc.lgamma_sum;         // poisson_log_glm_lpmf.hpp:127-129
+          if (!mc.propto) lp -= mc.lgamma_sum;         // poisson_log_glm_lpmf.hpp:127-129, binomial_logit_glm_lpmf.hpp:127-130
+        } else if (mc.family == FAM_NEG_BINOMIAL_2_LOG) {
+          lp += S;                                     // neg_binomial_2_log_glm_lpmf.hpp:186-197 (row terms)
+          if (!mc.propto) lp -= mc.lgamma_sum;         // :163-169
+          if (!mc.lik_only || !mc.propto || mc.sigma_is_var)
+            lp += mc.N_total * (sigma * log(sigma) - lgamma(sigma));   // :170-185 multiply_log(phi, phi) - lgamma(phi)
         } else {
           if (!mc.propto) lp += NEG_LOG_SQRT_TWO_PI_D * mc.N_total;   // normal_id_glm_lpdf.hpp:202-204
           if (!mc.lik_only || !mc.propto || mc.sigma_is_var)
@@ -373,6 +447,8 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
     if (mc.lik_only) {
       if (mc.family == FAM_NORMAL_ID && i == P - 1)
         g = mc.N_total > 0 ? (lik[P] - mc.N_total) / sigma : 0.0;    // normal_id_glm_lpdf.hpp:181-183
+      else if (mc.family == FAM_NEG_BINOMIAL_2_LOG && i == P - 1)
+        g = mc.N_total > 0 ? lik[P + 1] : 0.0;                       // neg_binomial_2_log_glm_lpmf.hpp:240-245
       else if (G > 0 && i < 2)
         g = 0.0;
       p.result[1 + i] = g;
@@ -390,8 +466,11 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
       g += -alpha / (mc.prior_alpha_sd * mc.prior_alpha_sd);
     }
     if (i >= mc.off_beta && i < mc.off_beta + K) g += -theta[i] * ib2;
-    if (mc.family == FAM_NORMAL_ID && i == P - 1) {
-      const double dlik = mc.N_total > 0 ? (lik[P] - mc.N_total) / sigma : 0.0;  // normal_id_glm_lpdf.hpp:181-183
+    if (has_scale && i == P - 1) {
+      double dlik = 0.0;
+      if (mc.N_total > 0)
+        dlik = mc.family == FAM_NORMAL_ID ? (lik[P] - mc.N_total) / sigma   // normal_id_glm_lpdf.hpp:181-183
+                                          : lik[P + 1];                     // neg_binomial_2_log_glm_lpmf.hpp:240-245
       const double dpri = -(sigma - mc.prior_sigma_loc) / (mc.prior_sigma_scale * mc.prior_sigma_scale);
       g = (dlik + dpri) * sigma + (mc.jacobian ? 1.0 : 0.0);
     }
@@ -462,18 +541,21 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
   if (!*sh_is_last) return;
 
   __threadfence();
-  for (int j = tid; j < K + 2; j += nt) {
+  const int n_sums = FAMILY == FAM_NEG_BINOMIAL_2_LOG ? K + 3 : K + 2;
+  for (int j = tid; j < n_sums; j += nt) {
     double v = 0.0;
     for (int b = 0; b < grid; ++b) v += __ldcg(p.partials + (size_t)b * p.pstride + j);
     if (j < K)
       p.lik[p.off_beta + j] = v;
     else if (j == K)
       p.lik[P] = v;
+    else if (j == K + 2)
+      p.lik[P + 1] = v;      // neg_binomial_2_log: sum of the per-row d/dphi terms
     else if (G == 0)
       p.lik[0] = v;
   }
   if (tid == 0) *p.ticket = 0u;
-  if (FAMILY == FAM_NORMAL_ID && tid == 0) p.lik[P - 1] = 0.0;  // sigma entry is derived in finish()
+  if (fam_has_scale(FAMILY) && tid == 0) p.lik[P - 1] = 0.0;  // sigma | phi entry is derived in finish()
   if (G > 0 && tid < 2) p.lik[tid] = 0.0;
   __threadfence();
   __syncthreads();
@@ -532,8 +614,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
   if (blockIdx.x == 0)
     for (int i = tid; i < P; i += NUM_THREADS) p.theta_used[i] = theta_at(i);
   const double alpha = G > 0 ? 0.0 : theta_at(0);
-  double inv_sigma = 1.0;
-  if (FAMILY == FAM_NORMAL_ID) inv_sigma = 1.0 / exp(theta_at(P - 1));  // normal_id_glm_lpdf.hpp:117
+  LinkConst lc;
+  lc.inv_sigma = 1.0;
+  lc.phi = 1.0;
+  lc.log_phi = 0.0;
+  lc.dg_phi = 0.0;
+  lc.inc_phi_terms = (!p.mc.propto || !p.mc.lik_only || p.mc.sigma_is_var) ? 1 : 0;
+  lc.inc_ytheta = (!p.mc.propto || !p.mc.lik_only || p.mc.sigma_is_var != 2) ? 1 : 0;
+  if (FAMILY == FAM_NORMAL_ID) lc.inv_sigma = 1.0 / exp(theta_at(P - 1));  // normal_id_glm_lpdf.hpp:117
+  if (FAMILY == FAM_NEG_BINOMIAL_2_LOG) {
+    lc.phi = exp(theta_at(P - 1));           // lb_constrain.hpp:65
+    lc.log_phi = log(lc.phi);                // neg_binomial_2_log_glm_lpmf.hpp:152
+    lc.dg_phi = digamma_pos(lc.phi);
+  }
   __syncthreads();
 
   const long long n_panels = p.n_panels;
@@ -542,7 +635,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
   double acc[CPL];
 #pragma unroll
   for (int s = 0; s < CPL; ++s) acc[s] = 0.0;
-  double lp_acc = 0.0, r_acc = 0.0;
+  double lp_acc = 0.0, r_acc = 0.0, x_acc = 0.0;
 
   if (warp == NUM_CONSUMER_WARPS) {
     // ===================== TMA producer (one elected lane) =====================
@@ -570,7 +663,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
     const int rg = lane & 3, cg = lane >> 2, cgl = cg & 3;
     const int o1 = lane ^ 4, o2 = lane ^ 8, o3 = lane ^ 12;
     const int ycol = K * 32 + (lane ^ ((K & 3) << 2));
-    const int gcol = (K + 1) * 32 + (lane ^ (((K + 1) & 3) << 2));
+    const int tcol = (K + 1) * 32 + (lane ^ (((K + 1) & 3) << 2));   // binomial population sizes
+    const int Kg = fam_group_col(FAMILY, K);
+    const int gcol = Kg * 32 + (lane ^ ((Kg & 3) << 2));
     int off[8];
 #pragma unroll
     for (int m = 0; m < 8; ++m) off[m] = rg + 4 * (m ^ cgl);
@@ -607,14 +702,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
         eta += alpha;
       }
       const bool valid = (pi * PANEL_ROWS + lane) < p.n_rows;
-      double lp_i, r_i;
-      link<FAMILY>(eta, y, inv_sigma, lp_i, r_i);
+      double lp_i, r_i, x_i;
+      link_ext<FAMILY>(eta, y, FAMILY == FAM_BINOMIAL_LOGIT ? tile[tcol] : 0.0, lc, lp_i, r_i, x_i);
       if (!valid) {
         lp_i = 0.0;
         r_i = 0.0;
+        x_i = 0.0;
       }
       lp_acc += lp_i;
       r_acc += r_i;
+      if (FAMILY == FAM_NEG_BINOMIAL_2_LOG) x_acc += x_i;
       if (G > 0) p.r_out[pi * PANEL_ROWS + lane] = r_i;
 
       // ---- phase 2: X^T r from the same smem tile ----
@@ -647,9 +744,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
     }
     lp_acc = warp_sum(lp_acc);
     r_acc = warp_sum(r_acc);
+    x_acc = warp_sum(x_acc);
     if (lane == 0) {
       red[warp * (Kpad + 4) + Kpad] = lp_acc;
       red[warp * (Kpad + 4) + Kpad + 1] = r_acc;
+      red[warp * (Kpad + 4) + Kpad + 2] = x_acc;
     }
   } else {
     // idle consumer warp (fewer stages than warps): contributes zeros to the CTA reduction
@@ -659,7 +758,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
 
   // ---- CTA partial -> global ----
   double* my_part = p.partials + (size_t)blockIdx.x * p.pstride;
-  for (int j = tid; j < K + 2; j += NUM_THREADS) {
+  for (int j = tid; j < K + 3; j += NUM_THREADS) {
     const int src = j < K ? j : Kpad + (j - K);
     double v = 0.0;
 #pragma unroll
@@ -699,6 +798,15 @@ __global__ void __launch_bounds__(256) group_reduce_kernel(const double* __restr
   }
 }
 
+// Leapfrog step of a model whose likelihood term is empty (no rows anywhere, or the binomial size_zero quirk):
+// begin_update_p + update_q (expl_leapfrog.hpp:16-26) without a pass over X; finish_kernel does the rest.
+__global__ void __launch_bounds__(NUM_THREADS) theta_from_state_kernel(const KernelParams p) {
+  for (int i = threadIdx.x; i < p.P; i += blockDim.x) {
+    const double ph = p.st_in[p.P + i] - (0.5 * p.eps) * p.st_in[2 * p.P + i];
+    p.theta_used[i] = p.st_in[i] + p.eps * (p.inv_metric[i] * ph);
+  }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS) finish_kernel(const KernelParams p) {
   __shared__ double sh_scratch[64];
   __shared__ int sh_ok;
@@ -717,8 +825,8 @@ __global__ void __launch_bounds__(NUM_THREADS) finish_kernel(const KernelParams 
 // ------------------------------------------------------------------------------------------
 __global__ void relayout_kernel(const double* __restrict__ X, long long ldx, long long x_row0,
                                 const int32_t* __restrict__ y_int, const double* __restrict__ y_real,
-                                const int32_t* __restrict__ group, const long long* __restrict__ perm,
-                                long long row0, long long n_rows_chunk, long long n_rows_total, int K, int C,
+                                const int32_t* __restrict__ group, const int32_t* __restrict__ trials,
+                                const long long* __restrict__ perm, long long row0, long long n_rows_chunk, long long n_rows_total, int K, int C,
                                 int c_begin, int c_end, double* __restrict__ panels, int PR, int Cs, int swz) {
   // Writes columns [c_begin, c_end) of destination rows [row0, row0 + n_rows_chunk), row0 % PR == 0.
   // X may be a chunk whose first row is source row x_row0 (leading dimension ldx).
@@ -739,6 +847,8 @@ __global__ void relayout_kernel(const double* __restrict__ X, long long ldx, lon
         v = X[(src - x_row0) + (long long)c * ldx];
       else if (c == K)
         v = y_real ? y_real[src] : (double)y_int[src];
+      else if (trials && c == K + 1)
+        v = (double)trials[src];
       else
         v = (double)group[src];
     }
@@ -749,7 +859,17 @@ __global__ void relayout_kernel(const double* __restrict__ X, long long ldx, lon
 
 // data checks the reference performs on every call (bernoulli :85 check_bounded, poisson :84
 // check_nonnegative) + the propto=false constant sum lgamma(y+1) (poisson :127-129)
-__global__ void __launch_bounds__(256) y_stats_kernel(const int32_t* __restrict__ y, long long n, int family,
+// binomial_coefficient_log.hpp:81-112 (value; the symmetric branch keeps k <= n/2)
+__device__ __forceinline__ double binomial_coefficient_log_d(double n, double k) {
+  if (k > n / 2.0 + 1e-8) k = n - k;
+  if (k == 0.0) return 0.0;
+  return lgamma(n + 1.0) - lgamma(k + 1.0) - lgamma(n + 1.0 - k);
+}
+// + binomial_logit :101-102 check_bounded(n, 0, N) / check_nonnegative(N) and :127-130 the propto=false
+// constant sum binomial_coefficient_log(N, n), stored NEGATED (finish() subtracts the constant);
+// neg_binomial_2_log :130 check_nonnegative(y), :163-169 sum lgamma(y+1)
+__global__ void __launch_bounds__(256) y_stats_kernel(const int32_t* __restrict__ y, const int32_t* __restrict__ trials,
+                                                      long long n, int family,
                                                       double* out /* [gridDim.x][2] = bad, lgamma_sum */) {
   __shared__ double sh[16];
   double bad = 0.0, lg = 0.0;
@@ -757,6 +877,10 @@ __global__ void __launch_bounds__(256) y_stats_kernel(const int32_t* __restrict_
     const int v = y[i];
     if (family == FAM_BERNOULLI_LOGIT) {
       if (v < 0 || v > 1) bad += 1.0;
+    } else if (family == FAM_BINOMIAL_LOGIT) {
+      const int t = trials[i];
+      if (v < 0 || v > t || t < 0) bad += 1.0;
+      else lg -= binomial_coefficient_log_d((double)t, (double)v);
     } else {
       if (v < 0) bad += 1.0;
       else lg += lgamma((double)v + 1.0);

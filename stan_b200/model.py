@@ -38,7 +38,7 @@ DEFAULT_PRIORS = dict(prior_alpha_sd=2.5, prior_beta_sd=2.5, prior_sigma_loc=1.0
 
 
 def make_desc(family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=1, N_total=0,
-              grid_ctas=0, flags=0, data_on_device=False, N=None, K=None, ldx=None, **priors):
+              grid_ctas=0, flags=0, data_on_device=False, N=None, K=None, ldx=None, trials=None, **priors):
     """Fill a b200glm_desc.  X, y, group: numpy arrays (host), or -- with data_on_device=True -- integer
     device pointers (e.g. torch tensor .data_ptr()) with N, K, ldx given explicitly.  Returns (desc, keep):
     `keep` holds the host arrays the descriptor points into (they must outlive the create call)."""
@@ -53,6 +53,7 @@ def make_desc(family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=
         else:
             d.y_int, d.y_real = int(y), None
         d.group = int(group) if G else None
+        d.trials = int(trials) if fam == 3 else None
     else:
         X = np.asfortranarray(X, dtype=np.float64)
         if X.ndim != 2:
@@ -75,6 +76,12 @@ def make_desc(family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=
                 raise InvalidArgument("Vector of intercepts has the wrong size")
             keep.append(group)
             d.group = group.ctypes.data if group.size else None
+        if fam == 3:     # binomial_logit: population sizes (binomial_logit_glm_lpmf.hpp:93-97 check_consistent_sizes)
+            trials = np.ascontiguousarray(trials, dtype=np.int32)
+            if trials.shape != (d.N,):
+                raise InvalidArgument("Population size parameter has the wrong size")
+            keep.append(trials)
+            d.trials = trials.ctypes.data if trials.size else None
     d.family, d.G, d.data_on_device = fam, int(G), int(bool(data_on_device))
     pri = dict(DEFAULT_PRIORS)
     pri.update(priors)
@@ -87,13 +94,13 @@ def make_desc(family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=
 
 class GLMModel:
     def __init__(self, family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=1, N_total=0,
-                 grid_ctas=0, flags=0, data_on_device=False, N=None, K=None, ldx=None, **priors):
-        """X, y, group: numpy arrays (host), or -- with data_on_device=True -- integer device
+                 grid_ctas=0, flags=0, data_on_device=False, N=None, K=None, ldx=None, trials=None, **priors):
+        """X, y, group, trials: numpy arrays (host), or -- with data_on_device=True -- integer device
         pointers (e.g. torch tensor .data_ptr()) with N, K, ldx given explicitly."""
         self.L = _capi.lib()
         self.family = family
         d, keep = make_desc(family, X, y, group, G, device, n_slots, rank, world, N_total, grid_ctas, flags,
-                            data_on_device, N, K, ldx, **priors)
+                            data_on_device, N, K, ldx, trials, **priors)
         self.N, self.K, self.G = int(d.N), int(d.K), int(G)
         self.rank, self.world = int(rank), int(world)
         h = C.c_void_p()
@@ -133,6 +140,8 @@ class GLMModel:
         n += [f"beta.{k}" for k in range(1, self.K + 1)]
         if self.family == "normal_id":
             n.append("sigma")
+        if self.family == "neg_binomial_2_log":
+            n.append("phi")
         return n
 
     def _theta(self, theta):

@@ -211,7 +211,7 @@ class FuncGLM:
     """b200::glm_data + the stan::math overloads of b200/glm_functions.hpp (function-level binding),
     exercised as one node of a reverse-mode tape: f = scale * glm_lpmf(...) + 0.5 * sum(beta^2)."""
 
-    def __init__(self, family, X, y, group=None, G=0):
+    def __init__(self, family, X, y, group=None, G=0, trials=None):
         self.L = lib()
         self.L.b200stan_func_create.restype = C.c_void_p
         self.L.b200stan_func_destroy.argtypes = [C.c_void_p]
@@ -219,11 +219,13 @@ class FuncGLM:
         X = np.asfortranarray(X, dtype=np.float64)
         y = np.ascontiguousarray(y, dtype=np.float64 if self.fam == 2 else np.int32)
         grp = None if group is None else np.ascontiguousarray(group, dtype=np.int32)
+        nt = None if trials is None else np.ascontiguousarray(trials, dtype=np.int32)
         self.K, self.G = X.shape[1], int(G)
         err = C.create_string_buffer(1024)
         self.h = C.c_void_p(self.L.b200stan_func_create(
             C.c_int(self.fam), C.c_longlong(X.shape[0]), C.c_int(self.K), _dp(X), C.c_void_p(y.ctypes.data),
-            None if grp is None else grp.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(self.G), err, 1024))
+            None if grp is None else grp.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(self.G), err, 1024,
+            None if nt is None else nt.ctypes.data_as(C.POINTER(C.c_int))))
         if not self.h:
             raise CudaError(err.value.decode() or "b200stan_func_create failed")
 

@@ -36,10 +36,19 @@ def make_glm_data(family, N, K, G=0, seed=SEED, alpha_true=0.3):
         y = ry.poisson(np.exp(np.clip(0.5 * eta + 0.5, -20, 5))).astype(np.int32)
     elif family == "normal_id":
         y = eta + ry.standard_normal(N)
+    elif family == "binomial_logit":
+        trials = ry.integers(0, 41, size=N, dtype=np.int32)          # includes empty populations
+        y = ry.binomial(trials, 1.0 / (1.0 + np.exp(-eta))).astype(np.int32)
+    elif family == "neg_binomial_2_log":
+        mu, phi_true = np.exp(np.clip(0.5 * eta + 0.5, -20, 5)), 2.0
+        y = ry.poisson(ry.gamma(phi_true, mu / phi_true)).astype(np.int32)   # gamma-poisson mixture
     else:
         raise ValueError(family)
-    return dict(family=family, X=X, y=y, group=group, G=G,
-                truth=dict(alpha=alpha_true, beta=beta, a=a_true))
+    out = dict(family=family, X=X, y=y, group=group, G=G,
+               truth=dict(alpha=alpha_true, beta=beta, a=a_true))
+    if family == "binomial_logit":
+        out["trials"] = trials
+    return out
 
 
 def theta_points(P, seed=SEED, n_random=1, scale=0.1):

@@ -33,9 +33,8 @@ def rel_err(got, ref):
     return abs(got - ref) / max(abs(ref), 1e-300) if ref != 0 else abs(got)
 
 
-@pytest.fixture(scope="session")
-def golden():
-    with open(os.path.join(ROOT, "tests", "golden", "glm_ref_golden.json")) as f:
+def _load_golden(filename):
+    with open(os.path.join(ROOT, "tests", "golden", filename)) as f:
         g = json.load(f)
     cases = {}
     for c in g["cases"]:
@@ -43,9 +42,22 @@ def golden():
         c["X"] = unhex(c["X"]).reshape((N, K), order="F")
         c["y"] = np.array(c["y"], dtype=np.float64 if c["family"] == "normal_id" else np.int32)
         c["group"] = None if c["group"] is None else np.array(c["group"], dtype=np.int32)
+        c["trials"] = None if c.get("trials") is None else np.array(c["trials"], dtype=np.int32)
         cases[c["name"]] = c
     return cases
 
 
+@pytest.fixture(scope="session")
+def golden():
+    return _load_golden("glm_ref_golden.json")
+
+
+@pytest.fixture(scope="session")
+def golden_more():
+    """binomial_logit / neg_binomial_2_log cases (tests/golden/make_golden.py more)."""
+    return _load_golden("glm_more_families_golden.json")
+
+
 GOLDEN_NAMES = ["bern_small", "bern_ragged", "bern_wide", "bern_groups", "pois_small", "pois_groups",
                 "norm_small", "norm_ragged", "norm_groups", "bern_k1", "bern_k0", "pois_n1"]
+MORE_GOLDEN_NAMES = ["binom_small", "binom_groups", "binom_k0", "nb2_small", "nb2_ragged", "nb2_groups"]

@@ -1,7 +1,8 @@
 """Generate tests/golden/glm_ref_golden.json from the COMPILED REFERENCE (oracle/_ref).
 
 Run in the build container (needs /root/reference to have been compiled by `make -C oracle ref`):
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py          # glm_ref_golden.json (bernoulli_logit, poisson_log, normal_id)
+    python tests/golden/make_golden.py more     # glm_more_families_golden.json (binomial_logit, neg_binomial_2_log)
 Every case stores its full inputs (X, y, group, theta as float.hex strings, so they are exact)
 and the reference's outputs: stan::model::log_prob_grad<propto,jacobian> value + gradient,
 Model::log_prob<propto,jacobian>(double) values, and one expl_leapfrog step.
@@ -34,15 +35,26 @@ CASES = [
 ]
 
 
+MORE_CASES = [
+    ("binom_small", "binomial_logit", 64, 5, 0),
+    ("binom_groups", "binomial_logit", 97, 4, 6),       # ragged N, a[group]
+    ("binom_k0", "binomial_logit", 20, 0, 0),           # empty weight vector: the reference returns 0 (size_zero)
+    ("nb2_small", "neg_binomial_2_log", 64, 5, 0),
+    ("nb2_ragged", "neg_binomial_2_log", 71, 9, 0),
+    ("nb2_groups", "neg_binomial_2_log", 130, 3, 11),
+]
+
+
 def hx(a):
     return [float(v).hex() for v in np.asarray(a, dtype=np.float64).ravel()]
 
 
-def main():
+def main(cases=CASES, filename="glm_ref_golden.json", seed0=4242):
     out = {"reference": RefOracle.lib().ref_oracle_version().decode(), "cases": []}
-    for name, fam, N, K, G in CASES:
-        d = make_glm_data(fam, N, K, G, seed=4242 + len(out["cases"]))
-        ro = RefOracle(fam, d["X"], d["y"], d["group"], G)
+    for name, fam, N, K, G in cases:
+        d = make_glm_data(fam, N, K, G, seed=seed0 + len(out["cases"]))
+        kw = {"trials": d["trials"]} if "trials" in d else {}
+        ro = RefOracle(fam, d["X"], d["y"], d["group"], G, **kw)
         P = num_params(fam, K, G)
         assert P == ro.P
         rng = np.random.default_rng(99 + len(out["cases"]))
@@ -69,16 +81,20 @@ def main():
         case = dict(name=name, family=fam, N=N, K=K, G=G,
                     X=hx(np.asarray(d["X"]).ravel(order="F")), y=[float(v) for v in d["y"]],
                     group=None if d["group"] is None else [int(v) for v in d["group"]],
+                    trials=[int(v) for v in d["trials"]] if "trials" in d else None,
                     evals=evals,
                     leapfrog=dict(eps=0.01, inv_metric=hx(im), q0=hx(q0), p0=hx(p0), g0=hx(-g0), V0=float(-lp0).hex(),
                                   q1=hx(q1), p1=hx(p1), g1=hx(g1), V1=float(V1).hex()))
         out["cases"].append(case)
         print(name, "P=", P, "lp(theta1)=", ro.log_prob_grad(thetas[1])[0])
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "glm_ref_golden.json")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), filename)
     with open(path, "w") as f:
         json.dump(out, f)
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "more":
+        main(MORE_CASES, "glm_more_families_golden.json", seed0=5151)
+    else:
+        main()
