@@ -101,7 +101,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from stan_b200 import GLMModel
-    from stan_b200.synth import make_shard
+    from stan_b200.synth import make_shard_ex
 
     rank, local_rank, world = dist_env()
     if world != args.gpus:
@@ -114,11 +114,12 @@ def run_b200(args):
     N_total, K, G, family = args.rows, args.cols, args.groups, args.family
     if args.weak:
         N_total *= world                      # --weak: --rows is per GPU
-    X, y, grp, r0, r1 = make_shard(torch, dev, family, N_total, K, G, rank, world)
+    X, y, grp, trials, r0, r1 = make_shard_ex(torch, dev, family, N_total, K, G, rank, world)
     n_local = r1 - r0
     torch.cuda.synchronize()
     m = GLMModel(family, X.data_ptr(), y.data_ptr(), grp.data_ptr() if G else None, G, data_on_device=True,
-                 N=n_local, K=K, ldx=n_local, device=local_rank, rank=rank, world=world, N_total=N_total)
+                 N=n_local, K=K, ldx=n_local, device=local_rank, rank=rank, world=world, N_total=N_total,
+                 trials=trials.data_ptr() if trials is not None else None)
     if world > 1 and args.collective == "peer":
         m.connect_peers_torch(dist, dev)      # in-kernel exchange through peer mailboxes (NVLink), no NCCL call
     elif world > 1:
@@ -132,8 +133,9 @@ def run_b200(args):
     sample = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ns = min(args.cpu_sample_rows, n_local)
-        sample = (X[:, :ns].cpu().numpy().T, y[:ns].cpu().numpy(), grp[:ns].cpu().numpy() if G else None)
-    del X, y, grp
+        sample = (X[:, :ns].cpu().numpy().T, y[:ns].cpu().numpy(), grp[:ns].cpu().numpy() if G else None,
+                  trials[:ns].cpu().numpy() if trials is not None else None)
+    del X, y, grp, trials
     torch.cuda.empty_cache()
 
     P = m.num_params_r()
@@ -223,7 +225,7 @@ def run_b200(args):
     cpu_baseline = None
     if sample is not None:
         cpu_baseline = cpu_baseline_leg(sample[0], sample[1], N_total, threads=1, evals=args.cpu_evals,
-                                        family=family, group=sample[2], G=G)
+                                        family=family, group=sample[2], G=G, trials=sample[3])
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.weak else "strong",
@@ -342,10 +344,10 @@ def run_b200_batched(args):
 # ------------------------------------------------------------------------------------------
 # CPU legs (the only place bench.py executes anything under oracle/)
 # ------------------------------------------------------------------------------------------
-def cpu_baseline_leg(Xs, ys, N_total, threads=1, evals=5, family=FAMILY, group=None, G=0):
+def cpu_baseline_leg(Xs, ys, N_total, threads=1, evals=5, family=FAMILY, group=None, G=0, trials=None):
     from oracle.oracle import PortOracle, RefOracle
     cls = RefOracle if RefOracle.available() else PortOracle
-    orc = cls(family, Xs, ys, group, G)
+    orc = cls(family, Xs, ys, group, G, **({"trials": trials} if trials is not None else {}))
     ns, K = Xs.shape
     th = 0.05 * np.random.default_rng(11).standard_normal(orc.P)
     orc.log_prob_grad(th)     # warm

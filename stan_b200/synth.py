@@ -98,10 +98,17 @@ def make_logistic_shard(torch, dev, N_total, K, rank=0, world=1, seed=SEED, bloc
 def make_shard(torch, dev, family, N_total, K, G=0, rank=0, world=1, seed=SEED, block=1_000_000, alpha_true=0.3):
     """Rows shard_rows(N_total, rank, world) of the synthetic problem for any family / grouping
     (SURVEY 8d generator), on `dev`: returns X (K, n) fp64 = column-major N x K, y (int32 or fp64),
-    group (int32, 1-based, or None), r0, r1.  Per-block seeds as in make_logistic_shard."""
+    group (int32, 1-based, or None), r0, r1.  Per-block seeds as in make_logistic_shard.
+    (binomial_logit also needs the population sizes: use make_shard_ex.)"""
+    X, y, group, trials, r0, r1 = make_shard_ex(torch, dev, family, N_total, K, G, rank, world, seed, block, alpha_true)
+    return X, y, group, r0, r1
+
+
+def make_shard_ex(torch, dev, family, N_total, K, G=0, rank=0, world=1, seed=SEED, block=1_000_000, alpha_true=0.3):
+    """make_shard plus the binomial population sizes: returns X, y, group, trials (int32 or None), r0, r1."""
     if family == "bernoulli_logit" and G == 0:
         X, y, r0, r1 = make_logistic_shard(torch, dev, N_total, K, rank, world, seed, block, alpha_true)
-        return X, y, None, r0, r1
+        return X, y, None, None, r0, r1
     r0, r1 = shard_rows(N_total, rank, world)
     n = r1 - r0
     g = torch.Generator(device=dev)
@@ -110,6 +117,7 @@ def make_shard(torch, dev, family, N_total, K, G=0, rank=0, world=1, seed=SEED, 
     X = torch.empty((K, n), device=dev, dtype=torch.float64)
     y = torch.empty(n, device=dev, dtype=torch.float64 if family == "normal_id" else torch.int32)
     group = torch.empty(n, device=dev, dtype=torch.int32) if G else None
+    trials = torch.empty(n, device=dev, dtype=torch.int32) if family == "binomial_logit" else None
     for b0 in range((r0 // block) * block, r1, block):
         g.manual_seed(seed * 1000 + b0 // block)
         xb = torch.randn((K, block), generator=g, device=dev, dtype=torch.float64)
@@ -124,10 +132,24 @@ def make_shard(torch, dev, family, N_total, K, G=0, rank=0, world=1, seed=SEED, 
             yb = (ub < torch.sigmoid(eta)).to(torch.int32)
         elif family == "poisson_log":
             yb = torch.poisson(torch.exp(torch.clamp(0.5 * eta + 0.5, -20, 5)), generator=g).to(torch.int32)
+        elif family == "binomial_logit":
+            tb = torch.randint(0, 41, (block,), generator=g, device=dev, dtype=torch.int32)
+            # successes: sum of `trials` Bernoulli draws, 40 uniform columns at a time
+            u = torch.rand((40, block), generator=g, device=dev, dtype=torch.float32)
+            hit = (u < torch.sigmoid(eta).to(torch.float32)) & (torch.arange(40, device=dev)[:, None] < tb[None, :])
+            yb = hit.sum(0).to(torch.int32)
+            trials[lo - r0:hi - r0] = tb[lo - b0:hi - b0]
+            del u, hit, tb
+        elif family == "neg_binomial_2_log":
+            mu = torch.exp(torch.clamp(0.5 * eta + 0.5, -20, 5))
+            # gamma(shape 2, mean mu) as a sum of two exponentials (keeps every draw on generator g): phi = 2 mixture
+            e2 = torch.rand((2, block), generator=g, device=dev, dtype=torch.float64).clamp_min(1e-300)
+            lam = -(mu / 2.0) * torch.log(e2).sum(0)
+            yb = torch.poisson(lam, generator=g).to(torch.int32)
         else:
             yb = eta + torch.randn(block, generator=g, device=dev, dtype=torch.float64)
         y[lo - r0:hi - r0] = yb[lo - b0:hi - b0]
         if G:
             group[lo - r0:hi - r0] = gb[lo - b0:hi - b0]
         del xb, ub, gb
-    return X, y, group, r0, r1
+    return X, y, group, trials, r0, r1
