@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -110,6 +111,7 @@ struct b200glm_handle {
   double lgamma_sum = 0.0;  // local shard
   double lgamma_sum_total = 0.0;
   bool bad_y = false;
+  bool pdl = true;          // B200GLM_NO_PDL=1 in the environment turns programmatic dependent launch off (A/B runs)
   std::vector<Slot*> slots;
   Batch* batch = nullptr;
   ncclComm_t comm = nullptr;
@@ -290,8 +292,21 @@ int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian,
   p.peer_in_main = (exchange && h->d.G == 0) ? 1 : 0;
   p.peer_in_finish = (exchange && h->d.G > 0) ? 1 : 0;
   if (need_likelihood && rows_anywhere) {
+    // Programmatic dependent launch: this launch's CTAs may take SMs (barrier set-up, first TMA loads of X) while
+    // the previous launch on the stream is still in its one-CTA epilogue; the kernels order every read of that
+    // launch's results behind griddepcontrol.wait (glm_kernels.cuh).
     kernel_fn fn = handle_kernel(h);
-    fn<<<h->grid, h->wide ? WIDE_THREADS : NUM_THREADS, h->smem_bytes, s->stream>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(h->grid);
+    cfg.blockDim = dim3(h->wide ? WIDE_THREADS : NUM_THREADS);
+    cfg.dynamicSmemBytes = h->smem_bytes;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(h, cudaLaunchKernelEx(&cfg, fn, p));
     h->launches++;
     if (h->d.G > 0) {
       const int gb = std::min(h->d.G, 8 * 148);   // 8 CTAs of 256 threads are resident per SM
@@ -461,6 +476,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   if (d.G > 0 && d.N > 0 && !d.group) return fail(B200GLM_INVALID, "group is null");
   if (!(d.prior_alpha_sd > 0) || !(d.prior_beta_sd > 0)) return fail(B200GLM_INVALID, "prior scales must be > 0");
   if (d.n_slots < 1) h->d.n_slots = 1;
+  if (const char* e = std::getenv("B200GLM_NO_PDL")) h->pdl = !(e[0] == '1');
   h->P = (d.G > 0 ? 2 + d.G : 1) + d.K + (fam_has_scale(d.family) ? 1 : 0);
   h->off_beta = d.G > 0 ? 2 + d.G : 1;
   h->C = fam_group_col(d.family, d.K) + (d.G > 0 ? 1 : 0);

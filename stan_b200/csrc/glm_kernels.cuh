@@ -157,6 +157,17 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   return pol;
 }
 
+// Programmatic dependent launch (PDL): consecutive evaluations of a slot are consecutive launches on one stream.
+// launch_dependents lets the NEXT launch's CTAs take an SM as soon as this launch's CTA on it has exited (they
+// set up barriers and start streaming X, which is constant data); grid_dependency_wait is what orders every read
+// of the previous launch's results (theta / leapfrog state) after that launch has completed and flushed.
+// Both are no-ops for a launch without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void named_barrier_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -215,7 +226,7 @@ __device__ __forceinline__ double digamma_pos(double x) {
 // Per-launch constants of the link step.
 struct LinkConst {
   double inv_sigma;               // normal_id: 1 / sigma
-  double phi, log_phi, dg_phi;    // neg_binomial_2_log: phi, log(phi), digamma(phi)
+  double phi, log_phi, dg_phi, lg_phi;   // neg_binomial_2_log: phi, log(phi), digamma(phi), lgamma(phi)
   int inc_phi_terms;              // neg_binomial_2_log: lgamma(y + phi) belongs to logp (phi is a parameter or !propto)
   int inc_ytheta;                 // neg_binomial_2_log: y * theta belongs to logp (alpha / beta are parameters or !propto)
 };
@@ -236,16 +247,41 @@ __device__ __forceinline__ void link_ext(double eta, double y, double aux, const
     r_i = y - aux * exp(lil);
   } else if (FAMILY == FAM_NEG_BINOMIAL_2_LOG) {
     // neg_binomial_2_log_glm_lpmf.hpp:153-157 logsumexp_theta_logphi, :186-197 logp, :205-208 theta_derivative,
-    // :240-245 d/dphi (per-row form; the leading N of the scalar-phi branch is the 1 added to every row)
+    // :240-245 d/dphi (per-row form; the leading N of the scalar-phi branch is the 1 added to every row).
+    // The special functions of y + phi cost one log and one division per row: y is a count, so for y <= 16
+    //   lgamma(y + phi) = lgamma(phi) + log prod_{j<y}(phi + j),  digamma(y + phi) - digamma(phi) = sum_{j<y} 1/(phi + j)
+    // (numerator and denominator of that sum built with two FMAs per term), and for larger y the Stirling /
+    // asymptotic series apply to y + phi > 16 without any shift (next term < 1e-19).  lgamma(phi) and
+    // digamma(phi) are per-launch constants.  logsumexp(theta, log phi) is log(exp(theta) + phi): exp(theta) is
+    // needed for the residual anyway, and where it overflows the reference's residual is NaN too (:207).
     const double ypp = y + lc.phi;
-    const double lse = eta > lc.log_phi ? eta + log1p(exp(lc.log_phi - eta)) : lc.log_phi + log1p(exp(eta - lc.log_phi));
     const double te = exp(eta);
     const double den = te + lc.phi;
+    const double rden = 1.0 / den;
+    const double lse = log(den);
+    double lgam, ddg;   // lgamma(y + phi), digamma(y + phi) - digamma(phi)
+    if (y <= 16.0) {
+      double pr = 1.0, nu = 0.0, t = lc.phi;
+      for (int j = 0; j < (int)y; ++j) {
+        nu = fma(nu, t, pr);
+        pr *= t;
+        t += 1.0;
+      }
+      lgam = lc.lg_phi + log(pr);
+      ddg = nu / pr;
+    } else {
+      const double rx = 1.0 / ypp, i2 = rx * rx, lx = log(ypp);
+      lgam = (ypp - 0.5) * lx - ypp + 0.91893853320467274178 +
+             rx * (1.0 / 12 - i2 * (1.0 / 360 - i2 * (1.0 / 1260 - i2 * (1.0 / 1680 - i2 * (1.0 / 1188
+                   - i2 * (691.0 / 360360 - i2 * (1.0 / 156 - i2 * (3617.0 / 122400))))))));
+      ddg = lx - 0.5 * rx - i2 * (1.0 / 12 - i2 * (1.0 / 120 - i2 * (1.0 / 252 - i2 * (1.0 / 240 - i2 * (1.0 / 132
+                   - i2 * (691.0 / 32760 - i2 * (1.0 / 12))))))) - lc.dg_phi;
+    }
     lp_i = -ypp * lse;
     if (lc.inc_ytheta) lp_i += y * eta;          // :188-190 include_summand<propto, T_x, T_alpha, T_beta>
-    if (lc.inc_phi_terms) lp_i += lgamma(ypp);   // :191-197 include_summand<propto, T_precision>
-    r_i = y - te * ypp / den;
-    x_i = 1.0 - ypp / den + lc.log_phi - lse + digamma_pos(ypp) - lc.dg_phi;
+    if (lc.inc_phi_terms) lp_i += lgam;          // :191-197 include_summand<propto, T_precision>
+    r_i = y - te * ypp * rden;
+    x_i = 1.0 - ypp * rden + lc.log_phi - lse + ddg;
   } else {
     link<FAMILY>(eta, y, lc.inv_sigma, lp_i, r_i);
   }
@@ -541,10 +577,33 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
   if (!*sh_is_last) return;
 
   __threadfence();
+  // Sum of the grid's partial rows, column by column, in a FIXED tree (bitwise reproducible): the rows are cut
+  // into R contiguous segments taken by R adjacent lanes (R = 1, 2, 4 or 8, as many as the CTA has threads for),
+  // each lane keeps 8 independent accumulators so 8 L2 loads are in flight per thread (this loop is on the
+  // critical path of every launch: ~13 us as one dependent chain of 148 loads, ~2 us like this), the segments
+  // meet in a shuffle butterfly.
   const int n_sums = FAMILY == FAM_NEG_BINOMIAL_2_LOG ? K + 3 : K + 2;
-  for (int j = tid; j < n_sums; j += nt) {
-    double v = 0.0;
-    for (int b = 0; b < grid; ++b) v += __ldcg(p.partials + (size_t)b * p.pstride + j);
+  int R = 1;
+  while (R < 8 && 2 * R * n_sums <= nt) R *= 2;
+  const int seg_len = (grid + R - 1) / R;
+  for (int base = 0; base < n_sums; base += nt / R) {       // warp-uniform trip count (nt and R are multiples)
+    const int j = base + tid / R, r = tid & (R - 1);
+    double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (j < n_sums) {
+      const int b1 = min(grid, (r + 1) * seg_len);
+      int b = r * seg_len;
+      const double* src = p.partials + j;
+      for (; b + 8 <= b1; b += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] += __ldcg(src + (size_t)(b + u) * p.pstride);
+      }
+#pragma unroll
+      for (int u = 0; u < 7; ++u)
+        if (b + u < b1) a[u] += __ldcg(src + (size_t)(b + u) * p.pstride);
+    }
+    double v = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    for (int o = 1; o < R; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (j >= n_sums || r != 0) continue;
     if (j < K)
       p.lik[p.off_beta + j] = v;
     else if (j == K)
@@ -591,6 +650,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -599,6 +659,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
     fence_barrier_init();
     fence_proxy_async();
   }
+  __syncthreads();
+  // From here the TMA producer streams X (constant data) while the consumer warps wait for the previous launch
+  // on this stream -- whose epilogue may still be running in one CTA -- before they read theta / the state.
+  if (warp != NUM_CONSUMER_WARPS) pdl_grid_dependency_wait();
 
   // ---- theta for this launch (leapfrog: begin_update_p + update_q, expl_leapfrog.hpp:16-26) ----
   auto theta_at = [&](int i) -> double {
@@ -608,26 +672,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
     }
     return p.theta_in[i];
   };
-  for (int k = tid; k < Kpad; k += NUM_THREADS) sbeta[k] = k < K ? theta_at(p.off_beta + k) : 0.0;
-  if (p.stage_a_in_smem)
-    for (int g = tid; g < G; g += NUM_THREADS) sa[g] = theta_at(2 + g);
-  if (blockIdx.x == 0)
-    for (int i = tid; i < P; i += NUM_THREADS) p.theta_used[i] = theta_at(i);
-  const double alpha = G > 0 ? 0.0 : theta_at(0);
+  constexpr int NC = NUM_CONSUMER_WARPS * 32;   // the consumer warps stage theta; the producer is already loading
+  double alpha = 0.0;
   LinkConst lc;
+  if (warp != NUM_CONSUMER_WARPS) {
+    for (int k = tid; k < Kpad; k += NC) sbeta[k] = k < K ? theta_at(p.off_beta + k) : 0.0;
+    if (p.stage_a_in_smem)
+      for (int g = tid; g < G; g += NC) sa[g] = theta_at(2 + g);
+    if (blockIdx.x == 0)
+      for (int i = tid; i < P; i += NC) p.theta_used[i] = theta_at(i);
+    alpha = G > 0 ? 0.0 : theta_at(0);
+  }
   lc.inv_sigma = 1.0;
   lc.phi = 1.0;
   lc.log_phi = 0.0;
   lc.dg_phi = 0.0;
+  lc.lg_phi = 0.0;
   lc.inc_phi_terms = (!p.mc.propto || !p.mc.lik_only || p.mc.sigma_is_var) ? 1 : 0;
   lc.inc_ytheta = (!p.mc.propto || !p.mc.lik_only || p.mc.sigma_is_var != 2) ? 1 : 0;
-  if (FAMILY == FAM_NORMAL_ID) lc.inv_sigma = 1.0 / exp(theta_at(P - 1));  // normal_id_glm_lpdf.hpp:117
-  if (FAMILY == FAM_NEG_BINOMIAL_2_LOG) {
-    lc.phi = exp(theta_at(P - 1));           // lb_constrain.hpp:65
-    lc.log_phi = log(lc.phi);                // neg_binomial_2_log_glm_lpmf.hpp:152
-    lc.dg_phi = digamma_pos(lc.phi);
+  if (warp != NUM_CONSUMER_WARPS) {
+    if (FAMILY == FAM_NORMAL_ID) lc.inv_sigma = 1.0 / exp(theta_at(P - 1));  // normal_id_glm_lpdf.hpp:117
+    if (FAMILY == FAM_NEG_BINOMIAL_2_LOG) {
+      lc.phi = exp(theta_at(P - 1));           // lb_constrain.hpp:65
+      lc.log_phi = log(lc.phi);                // neg_binomial_2_log_glm_lpmf.hpp:152
+      lc.dg_phi = digamma_pos(lc.phi);
+      lc.lg_phi = lgamma(lc.phi);
+    }
+    named_barrier_sync(1, NC);                 // sbeta / sa visible to every consumer warp
   }
-  __syncthreads();
 
   const long long n_panels = p.n_panels;
   const int grid = gridDim.x;
@@ -655,6 +727,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
         }
       }
     }
+    pdl_grid_dependency_wait();   // the tail below writes what the previous launch's epilogue may still be reading
   } else if (warp < (S < NUM_CONSUMER_WARPS ? S : NUM_CONSUMER_WARPS)) {
     // ===================== consumers =====================
     // Stage s is only ever consumed by warp s % W_act (S is a multiple of W_act), so every wait

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelP
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grid = gridDim.x;
 
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int s = 0; s < T; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelP
     }
     return p.theta_in[i];
   };
+  pdl_grid_dependency_wait();   // theta / the leapfrog state come from the previous launch on this stream
   for (int k = tid; k < J * KC; k += WIDE_THREADS) sbeta[k] = k < K ? theta_at(p.off_beta + k) : 0.0;
   if (p.stage_a_in_smem)
     for (int g = tid; g < G; g += WIDE_THREADS) sa[g] = theta_at(2 + g);
