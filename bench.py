@@ -217,7 +217,7 @@ def run_b200(args):
             with open(traffic_file) as f:
                 tj = json.load(f)
             for ent in tj.get("entries", [tj]):
-                if ent.get("N") == n_local and ent.get("K") == K:
+                if ent.get("N") == n_local and ent.get("K") == K and ent.get("family", FAMILY) == family:
                     roofline["traffic"] = ent.get("dram_bytes_per_launch")
         except Exception:
             pass
@@ -326,7 +326,7 @@ def run_b200_batched(args):
         "config": {"workload": f"normal_id_glm N={N} K={K} fp64, {C} batched chains (BASELINE configs[2])",
                    "rows_total": N, "cols": K, "chains": C,
                    "l2": f"X {8e-9 * N * K:.2f} GB >> 126 MB L2, no flush needed",
-                   "step": "one batched leapfrog: begin + fused DMMA GEMM pair + finish (device-resident state)"},
+                   "step": "one batched leapfrog: begin + fused DMMA GEMM pair + slice reduce + finish (device-resident state)"},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * P * C, "d2h_bytes_per_step": 8 * (P + 2) * C,
                 "call": "b200glm_log_prob_grad_batched(host thetas) -> host lp, grad"},
@@ -402,7 +402,18 @@ def run_reference(args):
         for t in ts:
             t.join()
 
-    for _ in range(args.warmup):
+    # bounded sample: shrink the row sample until the whole --steps/--warmup run fits in ~2 minutes of wall time
+    budget_s = 120.0
+    while True:
+        t0 = time.perf_counter()
+        step()
+        t_step = time.perf_counter() - t0
+        if t_step * (args.steps + args.warmup) <= budget_s or ns <= 20_000:
+            break
+        ns = max(20_000, int(ns * min(0.5, budget_s / (t_step * (args.steps + args.warmup)))))
+        Xs, ys = np.asfortranarray(Xs[:ns]), ys[:ns]
+        orc = cls(FAMILY, Xs, ys)
+    for _ in range(max(0, args.warmup - 1)):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):

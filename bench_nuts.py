@@ -53,7 +53,8 @@ def config3(args):
     s = summarize(res, RefOracle, args.chains)
     s.pop("stepsize")
     s["stepsize_median"] = float(np.median(res["stepsize"]))
-    s.update(batches=res["batches"], lanes=res["lanes"], mean_lanes_per_batch=res["lanes"] / max(res["batches"], 1))
+    s.update(batches=res["batches"], lanes=res["lanes"], mean_lanes_per_batch=res["lanes"] / max(res["batches"], 1),
+             batch_size_hist=res["batch_size_hist"])
     per_chain = res["warm_leapfrogs"] + res["draws"][:, :, 4].sum(axis=1)
     pc = lambda a: [float(np.percentile(a, q)) for q in (50, 90, 99, 100)]
     s["per_chain_leapfrogs_p50_p90_p99_max"] = pc(per_chain)

@@ -101,6 +101,9 @@ class chain_batcher final : public glm_model::batch_hook {
   static constexpr int kSingleLaneThreshold = 2;
   long n_batches() const { return n_batches_; }
   long n_single() const { return n_single_; }
+  // batches by size: lanes <= 2, 16, 32, 64, 128, 256, 512, more
+  static constexpr int kHistBuckets = 8;
+  long hist(int b) const { return hist_[b]; }
   long n_lanes() const { return n_lanes_; }
 
  private:
@@ -187,6 +190,13 @@ class chain_batcher final : public glm_model::batch_hook {
     }
     if (n == 0)
       return;
+    {
+      static constexpr int edge[kHistBuckets - 1] = {2, 16, 32, 64, 128, 256, 512};
+      int b = 0;
+      while (b < kHistBuckets - 1 && n > edge[b])
+        ++b;
+      ++hist_[b];
+    }
     b200glm_handle* h = m_.handle();
     if (!dmma_ok_ || n <= kSingleLaneThreshold) {
       // a straggler or two: the single-chain kernel (one HBM-bound launch each) beats a 64-chain DMMA block
@@ -256,12 +266,13 @@ class chain_batcher final : public glm_model::batch_hook {
   std::vector<double> uq_, up_, ug_, uim_, uV_, oq_, op_, og_, oV_, eps_;
   std::vector<int32_t> lanes_, up_lanes_, status_;
   long n_batches_ = 0, n_lanes_ = 0, n_single_ = 0;
+  long hist_[kHistBuckets] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool dmma_ok_ = true;
 };
 
 // Same contract and argument list as the reference's multi-chain
 // stan::services::sample::hmc_nuts_diag_e_adapt (hmc_nuts_diag_e_adapt.hpp:331-404); chain i uses
-// create_rng(random_seed, init_chain_id + i) exactly as there.  stats (optional) receives
+// create_rng(random_seed, init_chain_id + i) exactly as there.  stats (optional, 10 longs) receives
 // {batched launches, lanes served}.
 template <typename InitContextPtr, typename InitInvContextPtr, typename InitWriter, typename SampleWriter,
           typename DiagnosticWriter, typename MetricWriter>
@@ -300,6 +311,8 @@ int hmc_nuts_diag_e_adapt_batched(glm_model& model, size_t num_chains, const std
   if (stats) {
     stats[0] = batcher.n_batches();
     stats[1] = batcher.n_lanes();
+    for (int b = 0; b < chain_batcher::kHistBuckets; ++b)
+      stats[2 + b] = batcher.hist(b);   // batches with <= 2, 16, 32, 64, 128, 256, 512, more lanes
   }
   for (int r : rc)
     if (r != 0)

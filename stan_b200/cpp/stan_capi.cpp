@@ -303,7 +303,7 @@ int b200stan_nuts(void* h, int num_chains, unsigned seed, unsigned init_chain_id
                    errlen);
 }
 
-// batch_stats[2] = {batched launches, lanes served}
+// batch_stats[10] = {batched launches, lanes served, batches with <= 2, 16, 32, 64, 128, 256, 512, more lanes}
 int b200stan_nuts_batched(void* h, int num_chains, unsigned seed, unsigned init_chain_id, double init_radius,
                           int num_warmup, int num_samples, double stepsize, int max_depth, double delta, double* draws,
                           double* stepsize_out, double* inv_metric_out, double* warm_leapfrogs, double* wall_seconds,

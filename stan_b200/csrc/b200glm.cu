@@ -84,9 +84,12 @@ struct Batch {
   int max_chains = 0, ld = 0;   // ld = max_chains rounded up to 64 (state and lane leading dimension)
   int S = 0, mbh = 0, sms = 0;
   size_t smem = 0;
+  int rs_pairs = 0, rs_S = 0;   // row-split variant (<= 16 lanes): active warp pairs, ring stages per pair
+  size_t rs_smem = 0;
   cudaStream_t stream = nullptr;
   double *Q = nullptr, *Pm = nullptr, *Gd = nullptr, *V = nullptr, *IM = nullptr;
-  double *theta_c = nullptr, *p_half = nullptr, *partials = nullptr, *result = nullptr, *state_out = nullptr;
+  double *theta_c = nullptr, *p_half = nullptr, *partials = nullptr, *reduced = nullptr, *result = nullptr,
+         *state_out = nullptr;
   double *theta_in = nullptr, *eps_d = nullptr;
   int32_t* chains_d = nullptr;
   double* h_pin = nullptr;      // pinned staging, max_chains * (3P + 1) doubles (+ ints)
@@ -437,7 +440,7 @@ void b200glm_destroy(b200glm_handle* h) {
   }
   if (Batch* b = h->batch) {
     if (b->stream) cudaStreamSynchronize(b->stream);
-    for (double* q : {b->Q, b->Pm, b->Gd, b->V, b->IM, b->theta_c, b->p_half, b->partials, b->result, b->state_out,
+    for (double* q : {b->Q, b->Pm, b->Gd, b->V, b->IM, b->theta_c, b->p_half, b->partials, b->reduced, b->result, b->state_out,
                       b->theta_in, b->eps_d})
       cudaFree(q);
     cudaFree(b->chains_d);
@@ -843,23 +846,28 @@ const double* b200glm_result_device(b200glm_handle* h, int32_t slot) {
 namespace {
 
 typedef void (*batched_fn)(const BatchedParams);
-template <int FAMILY>
+template <int FAMILY, bool RS>
 batched_fn pick_batched_mbh(int mbh) {
   switch (mbh) {
-    case 2: return glm_batched_kernel<FAMILY, 2>;
-    case 4: return glm_batched_kernel<FAMILY, 4>;
-    case 7: return glm_batched_kernel<FAMILY, 7>;
-    case 13: return glm_batched_kernel<FAMILY, 13>;
+    case 2: return glm_batched_kernel<FAMILY, 2, RS>;
+    case 4: return glm_batched_kernel<FAMILY, 4, RS>;
+    case 7: return glm_batched_kernel<FAMILY, 7, RS>;
+    case 13: return glm_batched_kernel<FAMILY, 13, RS>;
   }
   return nullptr;
 }
-batched_fn pick_batched(int family, int mbh) {
+template <bool RS>
+batched_fn pick_batched_rs(int family, int mbh) {
   switch (family) {
-    case FAM_BERNOULLI_LOGIT: return pick_batched_mbh<FAM_BERNOULLI_LOGIT>(mbh);
-    case FAM_POISSON_LOG: return pick_batched_mbh<FAM_POISSON_LOG>(mbh);
-    case FAM_NORMAL_ID: return pick_batched_mbh<FAM_NORMAL_ID>(mbh);
+    case FAM_BERNOULLI_LOGIT: return pick_batched_mbh<FAM_BERNOULLI_LOGIT, RS>(mbh);
+    case FAM_POISSON_LOG: return pick_batched_mbh<FAM_POISSON_LOG, RS>(mbh);
+    case FAM_NORMAL_ID: return pick_batched_mbh<FAM_NORMAL_ID, RS>(mbh);
   }
   return nullptr;
+}
+// row_split: the variant for batches of <= 16 lanes (glm_batched_kernel.cuh)
+batched_fn pick_batched(int family, int mbh, bool row_split = false) {
+  return row_split ? pick_batched_rs<true>(family, mbh) : pick_batched_rs<false>(family, mbh);
 }
 
 int batch_check(b200glm_handle* h, int n) {
@@ -906,6 +914,7 @@ int enqueue_batched(b200glm_handle* h, int n, int mode, int propto, int jacobian
   sp.theta_c = b->theta_c;
   sp.p_half = b->p_half;
   sp.partials = b->partials;
+  sp.reduced = b->reduced;
   sp.result = b->result;
   sp.state_out = mirror_state ? b->state_out : nullptr;
   KernelParams kp;
@@ -923,16 +932,20 @@ int enqueue_batched(b200glm_handle* h, int n, int mode, int propto, int jacobian
   bp.P = h->P;
   bp.off_beta = h->off_beta;
   bp.family = h->d.family;
-  bp.n_stages = b->S;
+  const bool row_split = n <= 16 && b->rs_pairs >= 2;
+  bp.n_stages = row_split ? b->rs_S : b->S;
+  bp.pairs = row_split ? b->rs_pairs : 4;
+  sp.fold = row_split ? b->rs_pairs : 0;
   bp.NCB = NCB;
   bp.NS = NS;
   bp.ldc = sp.ldc;
   bp.n_lanes = n;
   bp.theta_c = b->theta_c;
   bp.partials = b->partials;
-  pick_batched(h->d.family, b->mbh)<<<NCB * NS, BATCH_THREADS, b->smem, b->stream>>>(bp);
+  pick_batched(h->d.family, b->mbh, row_split)<<<NCB * NS, BATCH_THREADS, row_split ? b->rs_smem : b->smem, b->stream>>>(bp);
+  batched_reduce_kernel<<<(h->d.K + 2) * NCB, BATCH_CB, 0, b->stream>>>(sp);
   batched_finish_kernel<<<(n + 31) / 32, 256, 0, b->stream>>>(sp);
-  h->launches += 3;
+  h->launches += 4;
   CUDA_TRY(h, cudaGetLastError());
   return B200GLM_OK;
 }
@@ -982,6 +995,21 @@ int b200glm_batch_reserve(b200glm_handle* h, int32_t max_chains) {
   b->smem = batched_smem_bytes(h->d.K, h->C, S);
   CUDA_TRY(h, cudaFuncSetAttribute(pick_batched(h->d.family, b->mbh), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)b->smem));
+  // row-split variant: beta block is K x 16, every pair has a private ring; as many pairs as panels fit, then
+  // as many stages per pair (up to 3) as still fit
+  {
+    int fit = 0;
+    while (fit < 12 && batched_smem_bytes(h->d.K, h->C, fit + 1, 16) <= max_dyn) ++fit;
+    b->rs_pairs = std::min(4, fit);
+    if (b->rs_pairs >= 2 && !std::getenv("B200GLM_NO_ROWSPLIT")) {
+      b->rs_S = std::min(3, fit / b->rs_pairs);
+      b->rs_smem = batched_smem_bytes(h->d.K, h->C, b->rs_pairs * b->rs_S, 16);
+      CUDA_TRY(h, cudaFuncSetAttribute(pick_batched(h->d.family, b->mbh, true),
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->rs_smem));
+    } else {
+      b->rs_pairs = 0;
+    }
+  }
   const size_t P = h->P, ld = b->ld;
   CUDA_TRY(h, cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   for (double** q : {&b->Q, &b->Pm, &b->Gd, &b->IM, &b->theta_c, &b->p_half}) {
@@ -996,6 +1024,7 @@ int b200glm_batch_reserve(b200glm_handle* h, int32_t max_chains) {
   CUDA_TRY(h, cudaMemset(b->V, 0, sizeof(double) * ld));
   const size_t n_part = (size_t)(b->sms + ld / BATCH_CB) * (h->d.K + 2) * BATCH_CB;
   CUDA_TRY(h, cudaMalloc(&b->partials, sizeof(double) * n_part));
+  CUDA_TRY(h, cudaMalloc(&b->reduced, sizeof(double) * (size_t)(h->d.K + 2) * ld));
   CUDA_TRY(h, cudaMalloc(&b->result, sizeof(double) * ld * (P + 2)));
   CUDA_TRY(h, cudaMalloc(&b->state_out, sizeof(double) * ld * (3 * P + 1)));
   CUDA_TRY(h, cudaMalloc(&b->theta_in, sizeof(double) * ld * (4 * P + 1)));   // also set_state staging

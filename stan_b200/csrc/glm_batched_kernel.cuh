@@ -19,7 +19,15 @@
 // Warp w = (mp = w & 1, nq = w >> 1): the pair {2nq, 2nq+1} owns chains [16nq, 16nq+16) end to end --
 // GEMM1 splits the 32 rows between the two warps, GEMM2 splits the features -- so R only ever has to
 // cross between two warps (a 4 KB smem patch and a 64-thread named barrier), never the whole CTA.
-// Slice partials are combined in fixed order by batched_finish_kernel (deterministic).
+// Slice partials are combined in fixed order by batched_reduce_kernel (deterministic).
+//
+// Row-split mode (template RS, batches of <= 16 lanes -- most batches of a lock-step NUTS run are the last few
+// straggler chains): one warp pair is all the DMMA work 16 chains have per panel, and a single pair per SM is
+// latency-bound (1.1 ms per batch at N = 1M, K = 200 against 0.25 ms of HBM time).  So the 16 chains' beta is
+// staged ONCE (K x 16) and every pair works on its OWN row panels for the same 16 chains: pair q takes the CTA's
+// panels q, q + PA, q + 2 PA, ... through a private ring of SP stages with its own barriers and its own TMA
+// issuer, keeps its own K x 16 accumulator block and writes it to columns [16q, 16q + 16) of the CTA's partial
+// row -- the slot pair q's chains have in the normal mode -- where batched_reduce_kernel folds the PA blocks.
 #pragma once
 
 #include "glm_kernels.cuh"
@@ -38,6 +46,7 @@ struct BatchedParams {
   int NCB, NS;             // chain blocks x row slices = grid
   int ldc;                 // padded number of chain lanes (NCB * 64)
   int n_lanes;             // active lanes; warp pairs whose 16 chains are all padding do no work
+  int pairs;               // row-split mode: active warp pairs PA (n_stages is then the stages PER PAIR)
   const double* theta_c;   // [P][ldc] feature-major: the point each lane is evaluated at
   double* partials;        // [NS][NCB][K + 2][64]: rows [0,K) = X^T r, row K = lp-sum, row K+1 = r-sum
 };
@@ -55,25 +64,29 @@ __device__ __forceinline__ void tma_load_1d_nohint(void* dst_smem, const void* s
 }
 __device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
-__host__ __device__ inline size_t batched_smem_bytes(int K, int C, int S) {
+// S = ring stages in all (row-split mode: pairs x stages per pair), cbw = chains staged in smem (64, or 16)
+__host__ __device__ inline size_t batched_smem_bytes(int K, int C, int S, int cbw = BATCH_CB) {
   const int K4 = (K + 3) & ~3;
-  return ((size_t)S * C * 32 + (size_t)K4 * BATCH_CB + 4 * 32 * 16 + 2 * BATCH_CB) * 8 + (size_t)2 * S * 8;
+  return ((size_t)S * C * 32 + (size_t)K4 * cbw + 4 * 32 * 16 + 2 * BATCH_CB) * 8 + (size_t)2 * S * 8;
 }
 
-template <int FAMILY, int MBH>
+template <int FAMILY, int MBH, bool RS>
 __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const BatchedParams p) {
-  constexpr int CB = BATCH_CB;
+  constexpr int CB = BATCH_CB;            // width of a partial row (chain slots of a CTA)
+  constexpr int CBW = RS ? 16 : CB;       // chains whose beta is staged in shared memory
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int K = p.K, C = p.C, S = p.n_stages, NS = p.NS, NCB = p.NCB;
+  const int PA = RS ? p.pairs : 4;
+  const int S_all = RS ? PA * S : S;
   const int K4 = (K + 3) & ~3, Kfull = K & ~3;
   const int tile_doubles = C * 32;
-  double* tiles = reinterpret_cast<double*>(smem_raw);            // S * C * 32
-  double* sB = tiles + (size_t)S * tile_doubles;                  // K4 x 64, column index XOR-swizzled
-  double* sR = sB + (size_t)K4 * CB;                              // 4 pairs x (32 rows x 16 chains)
+  double* tiles = reinterpret_cast<double*>(smem_raw);            // S_all * C * 32
+  double* sB = tiles + (size_t)S_all * tile_doubles;              // K4 x CBW, column index XOR-swizzled
+  double* sR = sB + (size_t)K4 * CBW;                             // 4 pairs x (32 rows x 16 chains)
   double* sAl = sR + 4 * 32 * 16;                                 // alpha of the 64 chains
   double* sIs = sAl + CB;                                         // 1 / sigma of the 64 chains
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sIs + CB);
-  uint64_t* empty_bar = full_bar + S;
+  uint64_t* empty_bar = full_bar + S_all;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cb = blockIdx.x % NCB, sl = blockIdx.x / NCB;
@@ -81,19 +94,19 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
 
   // pairs of this chain block that hold at least one real chain (the last block of a small batch is
   // mostly padding: the straggler batches of a lock-step NUTS run have a handful of lanes)
-  const int act_pairs = min(4, (p.n_lanes - cb * CB + 15) / 16);
+  const int act_pairs = RS ? PA : min(4, (p.n_lanes - cb * CB + 15) / 16);
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < S_all; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 2 * act_pairs);
+      mbar_init(&empty_bar[s], RS ? 2 : 2 * act_pairs);   // row-split: a stage belongs to one pair
     }
     fence_barrier_init();
     fence_proxy_async();
   }
-  // this CTA's 64 chains' beta: sB[k][c ^ ((k & 3) << 2)]
-  for (int idx = tid; idx < K4 * CB; idx += BATCH_THREADS) {
-    const int k = idx / CB, c = idx % CB;
-    sB[k * CB + (c ^ ((k & 3) << 2))] = k < K ? p.theta_c[(size_t)(p.off_beta + k) * p.ldc + cb * CB + c] : 0.0;
+  // this CTA's chains' beta: sB[k][c ^ ((k & 3) << 2)]
+  for (int idx = tid; idx < K4 * CBW; idx += BATCH_THREADS) {
+    const int k = idx / CBW, c = idx % CBW;
+    sB[k * CBW + (c ^ ((k & 3) << 2))] = k < K ? p.theta_c[(size_t)(p.off_beta + k) * p.ldc + cb * CB + c] : 0.0;
   }
   for (int c = tid; c < CB; c += BATCH_THREADS) {
     sAl[c] = p.theta_c[(size_t)cb * CB + c];
@@ -105,22 +118,27 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
   // Tile m goes to stage m % S; it is requested at the top of iteration m - (S - 1), once all 8 warps
   // have released that stage (they finished GEMM2 of tile m - S one iteration ago).  No separate
   // producer warp: 8 warps = 2 per SM sub-partition leaves each thread the full 255-register budget.
+  // Row-split mode: the same scheme per pair -- pair nq's m-th tile is the CTA's tile nq + m * PA, its ring is
+  // stages [nq * S, (nq + 1) * S), its issuer lane 0 of its first warp.
   const uint32_t tile_bytes = (uint32_t)tile_doubles * 8u;
+  const int mp = warp & 1, nq = warp >> 1;
+  const int st0 = RS ? nq * S : 0;                     // first stage of the ring this warp works on
+  const long long tile0 = RS ? nq : 0, tile_step = RS ? PA : 1;
+  const bool issuer = RS ? (mp == 0 && lane == 0) : (tid == 0);
   auto request_tile = [&](long long m) {
-    const long long pm = sl + m * NS;
+    const long long pm = sl + (tile0 + m * tile_step) * NS;
     if (pm >= n_panels) return;
-    const int sm = (int)(m % S);
+    const int sm = st0 + (int)(m % S);
     if (m >= S) mbar_wait(&empty_bar[sm], (uint32_t)(((m / S) - 1) & 1));
     mbar_arrive_expect_tx(&full_bar[sm], tile_bytes);
     tma_load_1d_nohint(tiles + (size_t)sm * tile_doubles, p.panels + (size_t)pm * tile_doubles, tile_bytes,
                        &full_bar[sm]);
   };
-  if (tid == 0)
+  if (nq >= act_pairs) return;   // nothing but padding lanes (never warp 0: pair 0 always has lane 0)
+  if (issuer)
     for (int m = 0; m < S - 1; ++m) request_tile(m);
 
   // ===================== DMMA warps =====================
-  const int mp = warp & 1, nq = warp >> 1;
-  if (nq >= act_pairs) return;   // nothing but padding lanes (never warp 0: pair 0 always has lane 0)
   const int l4 = lane & 3, lq = lane >> 2;
   const int sw = l4 << 2;
   double* sRp = sR + nq * (32 * 16);
@@ -134,15 +152,16 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
 
   // fragment addressing (see header): A1 = X[row][k] for GEMM1, B1 = beta[k][chain]
   const int ra0 = (16 * mp + lq) ^ sw, ra1 = (16 * mp + 8 + lq) ^ sw;
-  const int cb0 = (16 * nq + lq) ^ sw, cb1 = (16 * nq + 8 + lq) ^ sw;
-  const double* tb = sB + l4 * CB;
+  const int coff = RS ? 0 : 16 * nq;     // this pair's chains within the staged beta block
+  const int cb0 = (coff + lq) ^ sw, cb1 = (coff + 8 + lq) ^ sw;
+  const double* tb = sB + l4 * CBW;
   const int fsw = (lq & 3) << 2;
   const int ycol = K * 32, ysw = (K & 3) << 2;
 
   long long n = 0;
-  for (long long pi = sl; pi < n_panels; pi += NS, ++n) {
-    const int s = (int)(n % S);
-    if (tid == 0) request_tile(n + S - 1);
+  for (long long pi = sl + tile0 * NS; pi < n_panels; pi += tile_step * NS, ++n) {
+    const int s = st0 + (int)(n % S);
+    if (issuer) request_tile(n + S - 1);
     __syncwarp();
     mbar_wait(&full_bar[s], (uint32_t)((n / S) & 1));
     const double* tile = tiles + (size_t)s * tile_doubles;
@@ -156,9 +175,9 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
 #pragma unroll 2
     for (; k0 + 8 <= Kfull; k0 += 8) {
       const double a0 = ta[k0 * 32 + ra0], a1 = ta[k0 * 32 + ra1];
-      const double b0 = tb[k0 * CB + cb0], b1 = tb[k0 * CB + cb1];
+      const double b0 = tb[k0 * CBW + cb0], b1 = tb[k0 * CBW + cb1];
       const double c0 = ta[(k0 + 4) * 32 + ra0], c1 = ta[(k0 + 4) * 32 + ra1];
-      const double d0 = tb[(k0 + 4) * CB + cb0], d1 = tb[(k0 + 4) * CB + cb1];
+      const double d0 = tb[(k0 + 4) * CBW + cb0], d1 = tb[(k0 + 4) * CBW + cb1];
       dmma884(e[0][0], a0, b0);
       dmma884(e[0][1], a0, b1);
       dmma884(e[1][0], a1, b0);
@@ -174,7 +193,7 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
         a0 = 0.0;
         a1 = 0.0;
       }
-      const double b0 = tb[k0 * CB + cb0], b1 = tb[k0 * CB + cb1];
+      const double b0 = tb[k0 * CBW + cb0], b1 = tb[k0 * CBW + cb1];
       dmma884(e[0][0], a0, b0);
       dmma884(e[0][1], a0, b1);
       dmma884(e[1][0], a1, b0);
@@ -198,8 +217,8 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
 #pragma unroll
       for (int ni = 0; ni < 2; ++ni) {
         double rr[2];
-        const double2 al = *reinterpret_cast<const double2*>(sAl + 16 * nq + 8 * ni + 2 * l4);
-        const double2 is = *reinterpret_cast<const double2*>(sIs + 16 * nq + 8 * ni + 2 * l4);
+        const double2 al = *reinterpret_cast<const double2*>(sAl + coff + 8 * ni + 2 * l4);
+        const double2 is = *reinterpret_cast<const double2*>(sIs + coff + 8 * ni + 2 * l4);
 #pragma unroll
         for (int e2 = 0; e2 < 2; ++e2) {
           double lp_i, r_i;
@@ -300,6 +319,8 @@ struct BatchedStepParams {
   double* theta_c;          // [P][ldc] evaluation points (out of begin, in of main + finish)
   double* p_half;           // [P][ldc] momenta after the first half step
   const double* partials;
+  double* reduced;          // [K + 2][ldc]: the slice partials summed over the NS row slices (batched_reduce_kernel)
+  int fold;                 // row-split mode: the PA 16-column blocks of a partial row belong to the same 16 chains
   double* result;           // [n][P + 2] chain-major: lp, grad[P], status
   double* state_out;        // MODE_LEAPFROG: [n][3P + 1] chain-major mirror of (q, p, g, V) or NULL
   ModelConst mc;
@@ -353,6 +374,35 @@ __global__ void __launch_bounds__(256) batched_scatter_state_kernel(int n, int P
   }
 }
 
+// Sum of the NS slice partials of every (row, chain) in fixed slice order (deterministic), 8 loads in flight per
+// thread.  One CTA of 64 threads per (row of [0, K+2), chain block).  Its own launch because a small batch -- the
+// straggler batches of a lock-step NUTS run -- has NS = 148 slices and a single finish CTA: summing them there was
+// a dependent chain of 148 x (K+2)/8 L2 loads per thread, ~1.3 ms per batch at K = 200, twice the DMMA kernel.
+__global__ void __launch_bounds__(BATCH_CB) batched_reduce_kernel(const BatchedStepParams p) {
+  const int row = blockIdx.x / p.NCB, cb = blockIdx.x % p.NCB, cl = threadIdx.x;
+  const size_t stride = (size_t)p.NCB * (p.K + 2) * BATCH_CB;
+  const double* src = p.partials + ((size_t)cb * (p.K + 2) + row) * BATCH_CB + cl;
+  double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  int s = 0;
+  for (; s + 8 <= p.NS; s += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] += __ldcg(src + (size_t)(s + u) * stride);
+  }
+#pragma unroll
+  for (int u = 0; u < 7; ++u)
+    if (s + u < p.NS) a[u] += __ldcg(src + (size_t)(s + u) * stride);
+  double v = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  if (p.fold > 0) {   // row-split mode (NCB == 1): chain cl < 16 is the sum of columns cl, 16 + cl, ... in pair order
+    __shared__ double sh[BATCH_CB];
+    sh[cl] = v;
+    __syncthreads();
+    if (cl >= 16) return;
+    v = sh[cl];
+    for (int q = 1; q < p.fold; ++q) v += sh[16 * q + cl];
+  }
+  p.reduced[(size_t)row * p.ldc + cb * BATCH_CB + cl] = v;
+}
+
 // Slice partials -> per-chain model lp / gradient (priors, Jacobian: same formulas as finish() for
 // G == 0) and, in leapfrog mode, end_update_p + state write-back.  One CTA per 32 lanes (lane = chain),
 // 8 warps stride over the features.
@@ -364,15 +414,9 @@ __global__ void __launch_bounds__(256) batched_finish_kernel(const BatchedStepPa
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   const bool act = i < p.n;
-  const int cbk = i / BATCH_CB, cl = i % BATCH_CB;
   const double ib2 = 1.0 / (mc.prior_beta_sd * mc.prior_beta_sd);
   double* res = p.result + (size_t)(act ? i : 0) * (P + 2);
-  auto slice_sum = [&](int row) {
-    double v = 0.0;
-    for (int s = 0; s < p.NS; ++s)
-      v += p.partials[(((size_t)s * p.NCB + cbk) * (K + 2) + row) * BATCH_CB + cl];
-    return v;
-  };
+  auto slice_sum = [&](int row) { return p.reduced[(size_t)row * p.ldc + i]; };
 
   double sb = 0.0, bad = 0.0;
   if (act) {

@@ -195,7 +195,7 @@ class StanGLM:
         draws = np.empty((num_chains, num_warmup + num_samples, W))
         step, inv_metric = np.empty(num_chains), np.empty((num_chains, self.P))
         warm_lf, wall, err = np.empty(num_chains), C.c_double(), C.create_string_buffer(4096)
-        stats = (C.c_long * 2)()
+        stats = (C.c_long * 10)()
         rc = self.L.b200stan_nuts_batched(self.h, num_chains, C.c_uint(seed), C.c_uint(init_chain_id),
                                           C.c_double(init_radius), num_warmup, num_samples, C.c_double(stepsize),
                                           max_depth, C.c_double(delta), _dp(draws), _dp(step), _dp(inv_metric),
@@ -204,7 +204,9 @@ class StanGLM:
             self._raise(rc, err)
         return dict(draws=draws[:, num_warmup:, :], warmup_draws=draws[:, :num_warmup, :], stepsize=step,
                     inv_metric=inv_metric, warm_leapfrogs=warm_lf, wall=wall.value,
-                    batches=int(stats[0]), lanes=int(stats[1]))
+                    batches=int(stats[0]), lanes=int(stats[1]),
+                    batch_size_hist={k: int(stats[2 + i]) for i, k in enumerate(
+                        ["<=2", "<=16", "<=32", "<=64", "<=128", "<=256", "<=512", ">512"])})
 
 
 class FuncGLM:
