@@ -9,6 +9,8 @@ min/median ESS over parameters (stan::analyze::ess), ESS/s, and the posterior z-
 
     python bench_nuts.py --config 1                 # N=10k K=20, 4 chains, 1000+1000 (BASELINE configs[0])
     python bench_nuts.py --config 2 --ref-iters 0   # N=10M K=100 on the GPU; CPU arm skipped (hours)
+    python bench_nuts.py --config 3 --chains 1024 --warmup 150 --samples 100   # batched chains (DMMA path)
+    python bench_nuts.py --config 4 --chains 2 --warmup 150 --samples 150      # poisson + 1000 group intercepts
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 bench_nuts.py --config 2
                                                     # the same single chain with the rows sharded over N GPUs
 Writes one JSON line; not part of the driver's bench contract (bench.py is).
@@ -70,6 +72,39 @@ def config3(args):
     print(json.dumps(out))
 
 
+def config4(args):
+    """BASELINE configs[3] on ONE GPU: poisson_log_glm hierarchical count model N=50M K=50 with 1000 group
+    intercepts (P = 1052 parameters), `--chains` chains through the unmodified hmc_nuts_diag_e_adapt; data is
+    generated on the device (20 GB of X).  No CPU arm (one gradient of this model takes ~10 s on a host core)."""
+    import torch
+    from oracle.oracle import RefOracle
+    from stan_b200 import stan_service
+    from stan_b200.synth import make_shard_ex
+    N, K, G = args.rows or 50_000_000, args.cols or 50, 1000
+    dev = torch.device("cuda", 0)
+    t0 = time.time()
+    X, y, grp, _, _, _ = make_shard_ex(torch, dev, "poisson_log", N, K, G, 0, 1)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t0
+    t0 = time.time()
+    m = stan_service.StanGLM("poisson_log", X.data_ptr(), y.data_ptr(), grp.data_ptr(), G, device=0,
+                             n_slots=max(2, args.chains), data_on_device=True, N=N, K=K, ldx=N)
+    del X, y, grp
+    torch.cuda.empty_cache()
+    t_upload = time.time() - t0
+    res = m.nuts(num_chains=args.chains, seed=4711, num_warmup=args.warmup, num_samples=args.samples, delta=0.8,
+                 num_threads=args.chains)
+    s = summarize(res, RefOracle, args.chains)
+    names = ["mu_a", "sigma_a"]
+    post = res["draws"][:, :, 7:].mean(axis=(0, 1))
+    s["posterior_mean_mu_a_sigma_a"] = [float(post[0]), float(post[1])]
+    print(json.dumps({"workload": f"poisson_log_glm N={N} K={K} with {G} group intercepts (P={m.P}), NUTS diag_e "
+                                  f"{args.chains} chains {args.warmup}+{args.samples} via unmodified hmc_nuts_diag_e_adapt",
+                      "host_threads": os.cpu_count(), "data_gen_s": t_gen, "upload_relayout_s": t_upload,
+                      "b200": dict(s, counters=m.counters())}))
+    m.close()
+
+
 def sharded(args, world, rank, local):
     """BASELINE configs[1] on N GPUs: ONE chain (the config is single-chain) through the unmodified
     hmc_nuts_diag_e_adapt, rows of X sharded over the ranks.  Every rank runs the same host code on the same
@@ -122,6 +157,8 @@ def main():
         return sharded(args, world, rank, local)
     if args.config == 3:
         return config3(args)
+    if args.config == 4:
+        return config4(args)
     N, K = {1: (10_000, 20), 2: (10_000_000, 100)}[args.config]
     N, K = args.rows or N, args.cols or K
     t0 = time.time()

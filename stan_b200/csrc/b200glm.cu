@@ -185,6 +185,8 @@ kernel_fn pick_wide_kernel(int family, int wr, int spw, int spc) {
     case FAM_BERNOULLI_LOGIT: return pick_wide_shape<FAM_BERNOULLI_LOGIT>(wr, spw, spc);
     case FAM_POISSON_LOG: return pick_wide_shape<FAM_POISSON_LOG>(wr, spw, spc);
     case FAM_NORMAL_ID: return pick_wide_shape<FAM_NORMAL_ID>(wr, spw, spc);
+    case FAM_BINOMIAL_LOGIT: return pick_wide_shape<FAM_BINOMIAL_LOGIT>(wr, spw, spc);
+    case FAM_NEG_BINOMIAL_2_LOG: return pick_wide_shape<FAM_NEG_BINOMIAL_2_LOG>(wr, spw, spc);
   }
   return nullptr;
 }
@@ -484,8 +486,6 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   h->off_beta = d.G > 0 ? 2 + d.G : 1;
   h->C = fam_group_col(d.family, d.K) + (d.G > 0 ? 1 : 0);
   h->wide = d.K > 256 || (d.flags & B200GLM_FLAG_FORCE_WIDE);
-  if (h->wide && d.family > B200GLM_NORMAL_ID)
-    return fail(B200GLM_INVALID, "binomial_logit / neg_binomial_2_log are served by the single-chain kernel for K <= 256 only");
   h->panel_rows = h->wide ? wide_rows_for(h->C) : PANEL_ROWS;
   h->n_panels = (d.N + h->panel_rows - 1) / h->panel_rows;
   const int P = h->P;

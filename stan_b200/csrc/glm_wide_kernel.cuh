@@ -258,18 +258,36 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelP
     // =============================== link warp ===============================
     const int r = lane & (WR - 1);
     const int jy = K / KC, coly = K - jy * KC;            // y lives in column K
-    const int jg = (K + 1) / KC, colg = K + 1 - jg * KC;  // group id in column K+1 (G > 0)
-    int slot_y = jy, slot_g = jg;
-    uint32_t par_y = 0, par_g = 0;
+    const int jt = (K + 1) / KC, colt = K + 1 - jt * KC;  // binomial population sizes in column K+1
+    const int Kg = fam_group_col(FAMILY, K);
+    const int jg = Kg / KC, colg = Kg - jg * KC;          // group id after the y (and trials) columns (G > 0)
+    int slot_y = jy, slot_g = jg, slot_t = jt;
+    uint32_t par_y = 0, par_g = 0, par_t = 0;
     const double alpha = G > 0 ? 0.0 : theta_at(0);
-    double inv_sigma = 1.0;
-    if (FAMILY == FAM_NORMAL_ID) inv_sigma = 1.0 / exp(theta_at(P - 1));  // normal_id_glm_lpdf.hpp:117
-    double lp_acc = 0.0, r_acc = 0.0;
+    LinkConst lc;
+    lc.inv_sigma = 1.0;
+    lc.phi = 1.0;
+    lc.log_phi = lc.dg_phi = lc.lg_phi = 0.0;
+    lc.inc_phi_terms = (!p.mc.propto || !p.mc.lik_only || p.mc.sigma_is_var) ? 1 : 0;
+    lc.inc_ytheta = (!p.mc.propto || !p.mc.lik_only || p.mc.sigma_is_var != 2) ? 1 : 0;
+    if (FAMILY == FAM_NORMAL_ID) lc.inv_sigma = 1.0 / exp(theta_at(P - 1));  // normal_id_glm_lpdf.hpp:117
+    if (FAMILY == FAM_NEG_BINOMIAL_2_LOG) {
+      lc.phi = exp(theta_at(P - 1));
+      lc.log_phi = log(lc.phi);
+      lc.dg_phi = digamma_pos(lc.phi);
+      lc.lg_phi = lgamma(lc.phi);
+    }
+    double lp_acc = 0.0, r_acc = 0.0, x_acc = 0.0;
     for (long long n = 0; n < n_my; ++n) {
       const int buf = (int)(n & 1);
       const long long pi = blockIdx.x + n * grid;
       mbar_wait(&full_bar[slot_y], par_y);
       const double y = ring[(size_t)slot_y * SLOT + coly * WR + r];
+      double trials = 0.0;
+      if (FAMILY == FAM_BINOMIAL_LOGIT) {
+        mbar_wait(&full_bar[slot_t], par_t);
+        trials = ring[(size_t)slot_t * SLOT + colt * WR + r];
+      }
       double off = alpha;
       if (G > 0) {
         mbar_wait(&full_bar[slot_g], par_g);
@@ -282,17 +300,19 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelP
 #pragma unroll
       for (int w = 0; w < WIDE_CONSUMER_WARPS; ++w) eta += eta_part[(buf * WIDE_CONSUMER_WARPS + w) * WR + r];
       eta += off;
-      double lp_i, r_i;
-      link<FAMILY>(eta, y, inv_sigma, lp_i, r_i);
+      double lp_i, r_i, x_i;
+      link_ext<FAMILY>(eta, y, trials, lc, lp_i, r_i, x_i);
       if (pi * WR + r >= p.n_rows) {
         lp_i = 0.0;
         r_i = 0.0;
+        x_i = 0.0;
       }
       if (lane < WR) {
         r_sh[buf * WR + lane] = r_i;
         if (G > 0) p.r_out[pi * WR + lane] = r_i;
         lp_acc += lp_i;
         r_acc += r_i;
+        x_acc += x_i;
       }
       __threadfence_block();
       named_bar_arrive(WIDE_BAR_R + buf, WIDE_BAR_COUNT);
@@ -306,12 +326,19 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelP
         slot_g -= T;
         par_g ^= 1u;
       }
+      slot_t += J;
+      if (slot_t >= T) {
+        slot_t -= T;
+        par_t ^= 1u;
+      }
     }
     lp_acc = warp_sum(lp_acc);
     r_acc = warp_sum(r_acc);
+    x_acc = warp_sum(x_acc);
     if (lane == 0) {
       my_part[K] = lp_acc;
       my_part[K + 1] = r_acc;
+      my_part[K + 2] = x_acc;   // neg_binomial_2_log: sum of the per-row d/dphi terms
     }
   }
 
