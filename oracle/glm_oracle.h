@@ -41,9 +41,17 @@ extern "C" {
 
 enum { GLM_BERNOULLI_LOGIT = 0, GLM_POISSON_LOG = 1, GLM_NORMAL_ID = 2,
        GLM_BINOMIAL_LOGIT = 3,      /* y ~ binomial_logit_glm(trials, X, alpha, beta)          */
-       GLM_NEG_BINOMIAL_2_LOG = 4   /* y ~ neg_binomial_2_log_glm(X, alpha, beta, phi); phi is the
+       GLM_NEG_BINOMIAL_2_LOG = 4,  /* y ~ neg_binomial_2_log_glm(X, alpha, beta, phi); phi is the
                                        last parameter (log phi unconstrained), phi ~ normal(prior_sigma_loc,
-                                       prior_sigma_scale) -- the slot sigma has for NORMAL_ID */ };
+                                       prior_sigma_scale) -- the slot sigma has for NORMAL_ID */
+       /* The two GLMs below have their own parameter blocks (G must be 0); the oracle for them is ahead of the
+        * CUDA path (not built on the device yet). */
+       GLM_ORDERED_LOGISTIC = 5,    /* parameters { vector[K] beta; ordered[C-1] c; }   theta = [beta, c unconstrained]
+                                       beta ~ normal(0, prior_beta_sd); c ~ normal(0, prior_alpha_sd);
+                                       y ~ ordered_logistic_glm(X, beta, c);           y in 1..C */
+       GLM_CATEGORICAL_LOGIT = 6    /* parameters { vector[C] alpha; matrix[K, C] beta; }  theta = [alpha, beta col-major]
+                                       alpha ~ normal(0, prior_alpha_sd); to_vector(beta) ~ normal(0, prior_beta_sd);
+                                       y ~ categorical_logit_glm(X, alpha, beta);      y in 1..C */ };
 
 typedef struct glm_spec {
   int32_t family;
@@ -62,6 +70,8 @@ typedef struct glm_spec {
   double prior_sigma_scale;
   double prior_sigma_a_scale;
   const int32_t* trials; /* BINOMIAL_LOGIT: population sizes (N entries); NULL otherwise */
+  int32_t n_classes;     /* ORDERED_LOGISTIC / CATEGORICAL_LOGIT: number of outcome classes C (>= 1) */
+  int32_t _pad2;
 } glm_spec;
 
 /* number of unconstrained parameters of the model the spec describes */

@@ -15,7 +15,9 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 BERNOULLI_LOGIT, POISSON_LOG, NORMAL_ID, BINOMIAL_LOGIT, NEG_BINOMIAL_2_LOG = 0, 1, 2, 3, 4
-FAMILY = {"bernoulli_logit": 0, "poisson_log": 1, "normal_id": 2, "binomial_logit": 3, "neg_binomial_2_log": 4}
+ORDERED_LOGISTIC, CATEGORICAL_LOGIT = 5, 6       # oracle only so far: not built on the device
+FAMILY = {"bernoulli_logit": 0, "poisson_log": 1, "normal_id": 2, "binomial_logit": 3, "neg_binomial_2_log": 4,
+          "ordered_logistic": 5, "categorical_logit": 6}
 HAS_SCALE = (NORMAL_ID, NEG_BINOMIAL_2_LOG)      # families with a trailing positive scalar (sigma | phi)
 
 
@@ -28,6 +30,7 @@ class GlmSpec(C.Structure):
         ("prior_alpha_sd", C.c_double), ("prior_beta_sd", C.c_double),
         ("prior_sigma_loc", C.c_double), ("prior_sigma_scale", C.c_double),
         ("prior_sigma_a_scale", C.c_double), ("trials", C.c_void_p),
+        ("n_classes", C.c_int32), ("_pad2", C.c_int32),
     ]
 
 
@@ -35,7 +38,7 @@ DEFAULT_PRIORS = dict(prior_alpha_sd=2.5, prior_beta_sd=2.5, prior_sigma_loc=1.0
                       prior_sigma_scale=2.0, prior_sigma_a_scale=1.0)
 
 
-def make_spec(family, X, y, group=None, G=0, trials=None, **priors):
+def make_spec(family, X, y, group=None, G=0, trials=None, n_classes=0, **priors):
     """Returns (spec, keepalive).  X: (N,K) float64, any layout (copied to Fortran order)."""
     fam = FAMILY[family] if isinstance(family, str) else int(family)
     X = np.asfortranarray(X, dtype=np.float64)
@@ -57,6 +60,7 @@ def make_spec(family, X, y, group=None, G=0, trials=None, **priors):
         ti = np.ascontiguousarray(trials, dtype=np.int32)
         keep.append(ti)
         s.trials = ti.ctypes.data
+    s.n_classes = int(n_classes)
     s.G = int(G)
     if G:
         gi = np.ascontiguousarray(group, dtype=np.int32)
@@ -69,8 +73,12 @@ def make_spec(family, X, y, group=None, G=0, trials=None, **priors):
     return s, keep
 
 
-def num_params(family, K, G=0):
+def num_params(family, K, G=0, n_classes=0):
     fam = FAMILY[family] if isinstance(family, str) else int(family)
+    if fam == ORDERED_LOGISTIC:
+        return K + max(n_classes - 1, 0)
+    if fam == CATEGORICAL_LOGIT:
+        return n_classes * (1 + K)
     return (2 + G if G else 1) + K + (1 if fam in HAS_SCALE else 0)
 
 

@@ -8,6 +8,8 @@
 //   stan::math::normal_id_glm_lpdf        (.../normal_id_glm_lpdf.hpp:54)
 //   stan::math::binomial_logit_glm_lpmf   (.../binomial_logit_glm_lpmf.hpp:55)
 //   stan::math::neg_binomial_2_log_glm_lpmf (.../neg_binomial_2_log_glm_lpmf.hpp:64)
+//   stan::math::ordered_logistic_glm_lpmf (.../ordered_logistic_glm_lpmf.hpp:49) with stan::math::ordered_constrain
+//   stan::math::categorical_logit_glm_lpmf (.../categorical_logit_glm_lpmf.hpp:43)
 //   stan::math::normal_lpdf, stan::math::lb_constrain (prim/constraint/lb_constrain.hpp:60-67),
 //   stan::model::rvalue(v, name, index_multi) (src/stan/model/indexing/rvalue.hpp:154-172)
 // It is compiled against the headers where they lie under /root/reference; no reference
@@ -38,7 +40,16 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
   double prior_alpha_sd_, prior_beta_sd_, prior_sigma_loc_, prior_sigma_scale_,
       prior_sigma_a_scale_;
 
+  int C_ = 0;   // ORDERED_LOGISTIC / CATEGORICAL_LOGIT: number of classes
+  bool class_model() const {
+    return family_ == GLM_ORDERED_LOGISTIC || family_ == GLM_CATEGORICAL_LOGIT;
+  }
+
   static size_t count_params(const glm_spec& s) {
+    if (s.family == GLM_ORDERED_LOGISTIC)
+      return s.K + (s.n_classes > 0 ? s.n_classes - 1 : 0);
+    if (s.family == GLM_CATEGORICAL_LOGIT)
+      return static_cast<size_t>(s.n_classes) * (1 + s.K);
     size_t p = (s.G > 0 ? 2 + s.G : 1) + s.K;
     if (s.family == GLM_NORMAL_ID || s.family == GLM_NEG_BINOMIAL_2_LOG)
       p += 1;
@@ -78,6 +89,8 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
       group_.assign(s.group, s.group + N_);
     if (family_ == GLM_BINOMIAL_LOGIT)
       trials_.assign(s.trials, s.trials + N_);
+    if (class_model())
+      C_ = s.n_classes;
   }
 
   ~ref_glm_model() override {}
@@ -88,6 +101,21 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
   }
 
   void base_names(std::vector<std::string>& names) const {
+    if (family_ == GLM_ORDERED_LOGISTIC) {
+      for (int k = 1; k <= K_; ++k)
+        names.emplace_back("beta." + std::to_string(k));
+      for (int c = 1; c < C_; ++c)
+        names.emplace_back("c." + std::to_string(c));
+      return;
+    }
+    if (family_ == GLM_CATEGORICAL_LOGIT) {
+      for (int c = 1; c <= C_; ++c)
+        names.emplace_back("alpha." + std::to_string(c));
+      for (int c = 1; c <= C_; ++c)
+        for (int k = 1; k <= K_; ++k)
+          names.emplace_back("beta." + std::to_string(k) + "." + std::to_string(c));
+      return;
+    }
     if (G_ > 0) {
       names.emplace_back("mu_a");
       names.emplace_back("sigma_a");
@@ -105,6 +133,14 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
   void get_param_names(std::vector<std::string>& names, bool = true,
                        bool = true) const override {
     names.clear();
+    if (family_ == GLM_ORDERED_LOGISTIC) {
+      names = {"beta", "c"};
+      return;
+    }
+    if (family_ == GLM_CATEGORICAL_LOGIT) {
+      names = {"alpha", "beta"};
+      return;
+    }
     if (G_ > 0) {
       names = {"mu_a", "sigma_a", "a", "beta"};
     } else {
@@ -116,6 +152,16 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
   void get_dims(std::vector<std::vector<size_t>>& dimss, bool = true,
                 bool = true) const override {
     dimss.clear();
+    if (family_ == GLM_ORDERED_LOGISTIC) {
+      dimss.push_back({static_cast<size_t>(K_)});
+      dimss.push_back({static_cast<size_t>(C_ > 0 ? C_ - 1 : 0)});
+      return;
+    }
+    if (family_ == GLM_CATEGORICAL_LOGIT) {
+      dimss.push_back({static_cast<size_t>(C_)});
+      dimss.push_back({static_cast<size_t>(K_), static_cast<size_t>(C_)});
+      return;
+    }
     if (G_ > 0) {
       dimss.push_back({});
       dimss.push_back({});
@@ -148,6 +194,36 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
     T lp__(0.0);
     stan::math::accumulator<T> lp_accum__;
     size_t pos = 0;
+
+    if (family_ == GLM_ORDERED_LOGISTIC) {
+      // parameters { vector[K] beta; ordered[C-1] c; }
+      vec_t beta_o(K_), u(C_ > 0 ? C_ - 1 : 0);
+      for (int k = 0; k < K_; ++k)
+        beta_o[k] = params_r[pos++];
+      for (int c = 0; c + 1 < C_; ++c)
+        u[c] = params_r[pos++];
+      vec_t cuts = stan::math::ordered_constrain<jacobian>(u, lp__);
+      lp_accum__.add(normal_lpdf<propto>(beta_o, 0, prior_beta_sd_));
+      lp_accum__.add(normal_lpdf<propto>(cuts, 0, prior_alpha_sd_));
+      lp_accum__.add(stan::math::ordered_logistic_glm_lpmf<propto>(y_int_, X_, beta_o, cuts));
+      lp_accum__.add(lp__);
+      return lp_accum__.sum();
+    }
+    if (family_ == GLM_CATEGORICAL_LOGIT) {
+      // parameters { vector[C] alpha; matrix[K, C] beta; }
+      vec_t alpha_c(C_);
+      Eigen::Matrix<T, -1, -1> beta_m(K_, C_);
+      for (int c = 0; c < C_; ++c)
+        alpha_c[c] = params_r[pos++];
+      for (int c = 0; c < C_; ++c)
+        for (int k = 0; k < K_; ++k)
+          beta_m(k, c) = params_r[pos++];
+      lp_accum__.add(normal_lpdf<propto>(alpha_c, 0, prior_alpha_sd_));
+      lp_accum__.add(normal_lpdf<propto>(stan::math::to_vector(beta_m), 0, prior_beta_sd_));
+      lp_accum__.add(stan::math::categorical_logit_glm_lpmf<propto>(y_int_, X_, alpha_c, beta_m));
+      lp_accum__.add(lp__);
+      return lp_accum__.sum();
+    }
 
     T alpha(0.0), mu_a(0.0), sigma_a(0.0), sigma(0.0);
     vec_t a, beta(K_);
@@ -227,6 +303,13 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
     const size_t P = num_params_r();
     for (size_t i = 0; i < P; ++i)
       c[i] = u[i];
+    if (family_ == GLM_ORDERED_LOGISTIC) {
+      for (int k = 1; k + 1 < C_; ++k)
+        c[K_ + k] = c[K_ + k - 1] + std::exp(u[K_ + k]);
+      return;
+    }
+    if (family_ == GLM_CATEGORICAL_LOGIT)
+      return;
     if (G_ > 0)
       c[1] = std::exp(u[1]);
     if (has_scale())
@@ -237,6 +320,13 @@ class ref_glm_model final : public stan::model::model_base_crtp<ref_glm_model> {
     const size_t P = num_params_r();
     for (size_t i = 0; i < P; ++i)
       u[i] = c[i];
+    if (family_ == GLM_ORDERED_LOGISTIC) {
+      for (int k = 1; k + 1 < C_; ++k)
+        u[K_ + k] = std::log(c[K_ + k] - c[K_ + k - 1]);   // ordered_free
+      return;
+    }
+    if (family_ == GLM_CATEGORICAL_LOGIT)
+      return;
     if (G_ > 0)
       u[1] = stan::math::lb_free(c[1], 0);
     if (has_scale())

@@ -14,8 +14,9 @@ def _rng(seed, stream=0):
     return np.random.Generator(np.random.Philox(key=[seed, stream]))
 
 
-def make_glm_data(family, N, K, G=0, seed=SEED, alpha_true=0.3):
-    """Returns dict(X (N,K) F-order float64, y, group (1-based int32 or None), truth)."""
+def make_glm_data(family, N, K, G=0, seed=SEED, alpha_true=0.3, n_classes=4):
+    """Returns dict(X (N,K) F-order float64, y, group (1-based int32 or None), truth); binomial_logit adds
+    `trials`, the class models (ordered_logistic, categorical_logit: oracle-side only so far) `n_classes`."""
     r = _rng(seed, 0)
     X = np.asfortranarray(r.standard_normal((K, N)).T) if N * K else np.zeros((N, K), order="F")
     beta = _rng(seed, 1).standard_normal(K) / np.sqrt(max(K, 1))
@@ -42,12 +43,23 @@ def make_glm_data(family, N, K, G=0, seed=SEED, alpha_true=0.3):
     elif family == "neg_binomial_2_log":
         mu, phi_true = np.exp(np.clip(0.5 * eta + 0.5, -20, 5)), 2.0
         y = ry.poisson(ry.gamma(phi_true, mu / phi_true)).astype(np.int32)   # gamma-poisson mixture
+    elif family == "ordered_logistic":
+        cuts = np.linspace(-1.5, 1.5, max(n_classes - 1, 0))
+        lat = eta - alpha_true + ry.logistic(size=N)
+        y = (1 + (lat[:, None] > cuts[None, :]).sum(axis=1)).astype(np.int32)
+    elif family == "categorical_logit":
+        Bc = _rng(seed, 4).standard_normal((K, n_classes)) / np.sqrt(max(K, 1))
+        lin = (X @ Bc if K else np.zeros((N, n_classes))) + 0.2 * np.arange(n_classes)
+        gum = ry.gumbel(size=(N, n_classes))
+        y = (1 + np.argmax(lin + gum, axis=1)).astype(np.int32) if N else np.zeros(0, np.int32)
     else:
         raise ValueError(family)
     out = dict(family=family, X=X, y=y, group=group, G=G,
                truth=dict(alpha=alpha_true, beta=beta, a=a_true))
     if family == "binomial_logit":
         out["trials"] = trials
+    if family in ("ordered_logistic", "categorical_logit"):
+        out["n_classes"] = n_classes
     return out
 
 

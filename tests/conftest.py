@@ -53,6 +53,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_classes():
+    """ordered_logistic / categorical_logit cases (tests/golden/make_golden.py classes): oracle-side only so far."""
+    return _load_golden("glm_class_models_golden.json")
+
+
+@pytest.fixture(scope="session")
 def golden_more():
     """binomial_logit / neg_binomial_2_log cases (tests/golden/make_golden.py more)."""
     return _load_golden("glm_more_families_golden.json")
@@ -61,3 +67,5 @@ def golden_more():
 GOLDEN_NAMES = ["bern_small", "bern_ragged", "bern_wide", "bern_groups", "pois_small", "pois_groups",
                 "norm_small", "norm_ragged", "norm_groups", "bern_k1", "bern_k0", "pois_n1"]
 MORE_GOLDEN_NAMES = ["binom_small", "binom_groups", "binom_k0", "nb2_small", "nb2_ragged", "nb2_groups"]
+CLASS_GOLDEN_NAMES = ["ordlog_small", "ordlog_ragged", "ordlog_binary", "ordlog_k0", "catlog_small", "catlog_ragged",
+                      "catlog_one_class"]

@@ -3,6 +3,7 @@
 Run in the build container (needs /root/reference to have been compiled by `make -C oracle ref`):
     python tests/golden/make_golden.py          # glm_ref_golden.json (bernoulli_logit, poisson_log, normal_id)
     python tests/golden/make_golden.py more     # glm_more_families_golden.json (binomial_logit, neg_binomial_2_log)
+    python tests/golden/make_golden.py classes  # glm_class_models_golden.json (ordered_logistic, categorical_logit)
 Every case stores its full inputs (X, y, group, theta as float.hex strings, so they are exact)
 and the reference's outputs: stan::model::log_prob_grad<propto,jacobian> value + gradient,
 Model::log_prob<propto,jacobian>(double) values, and one expl_leapfrog step.
@@ -45,6 +46,18 @@ MORE_CASES = [
 ]
 
 
+CLASS_CASES = [
+    # name, family, N, K, n_classes  (oracle-side goldens: these two GLMs are not built on the device yet)
+    ("ordlog_small", "ordered_logistic", 64, 5, 4),
+    ("ordlog_ragged", "ordered_logistic", 153, 7, 6),
+    ("ordlog_binary", "ordered_logistic", 40, 3, 2),
+    ("ordlog_k0", "ordered_logistic", 30, 0, 3),
+    ("catlog_small", "categorical_logit", 64, 5, 4),
+    ("catlog_ragged", "categorical_logit", 97, 9, 3),
+    ("catlog_one_class", "categorical_logit", 20, 2, 1),       # N_classes == 1: the reference returns 0
+]
+
+
 def hx(a):
     return [float(v).hex() for v in np.asarray(a, dtype=np.float64).ravel()]
 
@@ -52,10 +65,15 @@ def hx(a):
 def main(cases=CASES, filename="glm_ref_golden.json", seed0=4242):
     out = {"reference": RefOracle.lib().ref_oracle_version().decode(), "cases": []}
     for name, fam, N, K, G in cases:
-        d = make_glm_data(fam, N, K, G, seed=seed0 + len(out["cases"]))
+        n_classes = 0
+        if fam in ("ordered_logistic", "categorical_logit"):
+            n_classes, G = G, 0                      # CLASS_CASES carry the class count in the fifth field
+        d = make_glm_data(fam, N, K, G, seed=seed0 + len(out["cases"]), **({"n_classes": n_classes} if n_classes else {}))
         kw = {"trials": d["trials"]} if "trials" in d else {}
+        if n_classes:
+            kw["n_classes"] = n_classes
         ro = RefOracle(fam, d["X"], d["y"], d["group"], G, **kw)
-        P = num_params(fam, K, G)
+        P = num_params(fam, K, G, n_classes)
         assert P == ro.P
         rng = np.random.default_rng(99 + len(out["cases"]))
         thetas = [np.zeros(P), 0.3 * rng.standard_normal(P), 1.5 * rng.standard_normal(P)]
@@ -81,7 +99,7 @@ def main(cases=CASES, filename="glm_ref_golden.json", seed0=4242):
         case = dict(name=name, family=fam, N=N, K=K, G=G,
                     X=hx(np.asarray(d["X"]).ravel(order="F")), y=[float(v) for v in d["y"]],
                     group=None if d["group"] is None else [int(v) for v in d["group"]],
-                    trials=[int(v) for v in d["trials"]] if "trials" in d else None,
+                    trials=[int(v) for v in d["trials"]] if "trials" in d else None, n_classes=n_classes,
                     evals=evals,
                     leapfrog=dict(eps=0.01, inv_metric=hx(im), q0=hx(q0), p0=hx(p0), g0=hx(-g0), V0=float(-lp0).hex(),
                                   q1=hx(q1), p1=hx(p1), g1=hx(g1), V1=float(V1).hex()))
@@ -96,5 +114,7 @@ def main(cases=CASES, filename="glm_ref_golden.json", seed0=4242):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "more":
         main(MORE_CASES, "glm_more_families_golden.json", seed0=5151)
+    elif len(sys.argv) > 1 and sys.argv[1] == "classes":
+        main(CLASS_CASES, "glm_class_models_golden.json", seed0=6161)
     else:
         main()
