@@ -101,3 +101,30 @@ def test_stan_csv_reader_binding(tmp_path):
     assert csv["header"] == ["lp__", "accept_stat__", "alpha", "beta[1]", "beta[2]"]
     assert np.array_equal(csv["samples"], [[-1.5, 0.9, 0.1, 0.2, 0.3], [-2.5, 1, 0.4, 0.5, 0.6]])
     assert csv["step_size"] == 0.25 and np.array_equal(csv["metric"], [1.5, 2, 0.125])
+
+
+def test_desc_struct_layout_matches_the_header(tmp_path):
+    """The ctypes mirrors of b200glm_desc (stan_b200/_capi.py) and glm_spec (oracle/oracle.py) must have the
+    field offsets and size the C compiler gives the structs in include/b200glm.h and oracle/glm_oracle.h."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from oracle.oracle import GlmSpec
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    checks = (("b200glm_desc", os.path.join(ROOT, "include", "b200glm.h"), _capi.Desc),
+              ("glm_spec", os.path.join(ROOT, "oracle", "glm_oracle.h"), GlmSpec))
+    for struct, header, mirror in checks:
+        fields = [f[0] for f in mirror._fields_]
+        prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{header}"', "int main(void) {",
+                f'  printf("%zu\\n", sizeof({struct}));']
+        prog += [f'  printf("%zu\\n", offsetof({struct}, {f}));' for f in fields]
+        prog += ["  return 0;", "}"]
+        src, exe = tmp_path / f"{struct}.c", tmp_path / f"{struct}.bin"
+        src.write_text("\n".join(prog))
+        subprocess.run([cc, "-std=c11", "-o", str(exe), str(src)], check=True, capture_output=True)
+        out = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+        assert out[0] == C.sizeof(mirror), (struct, out[0], C.sizeof(mirror))
+        for name, off in zip(fields, out[1:]):
+            assert getattr(mirror, name).offset == off, (struct, name, off)
