@@ -20,6 +20,10 @@
  *   likelihood y ~ {bernoulli_logit,poisson_log,normal_id}_glm(X, alpha | a[group], beta [, sigma]),
  *              y ~ binomial_logit_glm(trials, X, alpha | a[group], beta),
  *              y ~ neg_binomial_2_log_glm(X, alpha | a[group], beta, phi).
+ *
+ * Environment switches (read at b200glm_create / b200glm_batch_reserve; for A/B measurements only):
+ *   B200GLM_NO_PDL=1       launch without the programmatic-dependent-launch attribute
+ *   B200GLM_NO_ROWSPLIT=1  serve batches of <= 16 lanes with the normal batched kernel, not its row-split variant
  */
 #ifndef B200GLM_H
 #define B200GLM_H
