@@ -95,3 +95,14 @@ def test_make_shard_is_sharding_invariant_for_every_family():
         assert torch.equal(y, torch.cat([p[1] for p in parts]))
         if G:
             assert torch.equal(g, torch.cat([p[2] for p in parts])) and 1 <= int(g.min()) and int(g.max()) <= G
+    # binomial_logit / neg_binomial_2_log (make_shard_ex also returns the population sizes)
+    from stan_b200.synth import make_shard_ex
+    for fam, G in (("binomial_logit", 0), ("binomial_logit", 4), ("neg_binomial_2_log", 0)):
+        X, y, g, t, _, _ = make_shard_ex(torch, dev, fam, 2500, 5, G, 0, 1, block=1000)
+        parts = [make_shard_ex(torch, dev, fam, 2500, 5, G, r, 3, block=1000) for r in range(3)]
+        assert torch.equal(X, torch.cat([p[0] for p in parts], 1))
+        assert torch.equal(y, torch.cat([p[1] for p in parts])) and int(y.min()) >= 0
+        if fam == "binomial_logit":
+            assert torch.equal(t, torch.cat([p[3] for p in parts])) and bool((y <= t).all())
+        else:
+            assert t is None
