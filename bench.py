@@ -114,7 +114,30 @@ def run_b200(args):
     N_total, K, G, family = args.rows, args.cols, args.groups, args.family
     if args.weak:
         N_total *= world                      # --weak: --rows is per GPU
-    X, y, grp, trials, r0, r1 = make_shard_ex(torch, dev, family, N_total, K, G, rank, world)
+    rows, weights = None, None
+    if args.balance and world > 1:
+        # a row-sharded step waits for its slowest shard: split the rows in proportion to each GPU's measured copy
+        # bandwidth instead of equally (opt-in)
+        from stan_b200.synth import shard_rows_weighted
+        a = torch.empty(1 << 27, device=dev, dtype=torch.float64)        # 1 GiB
+        b = torch.empty_like(a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 0.0
+        for i in range(8):
+            e0.record()
+            b.copy_(a)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                best = max(best, 2 * a.numel() * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        del a, b
+        torch.cuda.empty_cache()
+        bw = torch.tensor([best], device=dev, dtype=torch.float64)
+        allbw = [torch.empty_like(bw) for _ in range(world)]
+        dist.all_gather(allbw, bw)
+        weights = [float(t.item()) for t in allbw]
+        rows = shard_rows_weighted(N_total, weights, rank)
+    X, y, grp, trials, r0, r1 = make_shard_ex(torch, dev, family, N_total, K, G, rank, world, rows=rows)
     n_local = r1 - r0
     torch.cuda.synchronize()
     m = GLMModel(family, X.data_ptr(), y.data_ptr(), grp.data_ptr() if G else None, G, data_on_device=True,
@@ -232,7 +255,8 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(N_total, K, family, G, args.config), "rows_total": N_total,
                    "rows_per_gpu": n_local, "cols": K, "groups": G,
-                   "sharding": f"rows x{world}" + ((", likelihood partials exchanged inside the gradient launch (peer mailboxes over NVLink)"
+                   "sharding": f"rows x{world}" + (f" weighted by per-GPU copy bandwidth {[round(w) for w in weights]} GB/s"
+                                                   if weights else "") + ((", likelihood partials exchanged inside the gradient launch (peer mailboxes over NVLink)"
                                                     if args.collective == "peer" else
                                                     ", one NCCL all-reduce of P+2 doubles per gradient") if world > 1 else ""),
                    "l2": f"X shard {bytes_per_launch / 1e9:.2f} GB >> 126 MB L2, no flush needed",
@@ -448,6 +472,8 @@ def main():
     ap.add_argument("--family", default=None)
     ap.add_argument("--groups", type=int, default=None)
     ap.add_argument("--weak", action="store_true", help="--rows is per GPU (weak scaling)")
+    ap.add_argument("--balance", action="store_true",
+                    help="N > 1: split the rows in proportion to each GPU's measured copy bandwidth (default: equal)")
     ap.add_argument("--chains", type=int, default=1024)
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the P+2 likelihood partials are summed over ranks")

@@ -83,12 +83,30 @@ def shard_rows(N_total, rank, world):
     return r0, min(r0 + per, N_total)
 
 
-def make_logistic_shard(torch, dev, N_total, K, rank=0, world=1, seed=SEED, block=1_000_000, alpha_true=0.3):
+def shard_rows_weighted(N_total, weights, rank, align=32):
+    """Row block of `rank` when the rows are split in proportion to `weights` (one positive number per rank, e.g.
+    a measured per-GPU memory bandwidth: a row-sharded step waits for its slowest shard, so a slower GPU should
+    hold fewer rows).  Boundaries are multiples of `align` rows (the panel height); the blocks are contiguous,
+    disjoint and cover [0, N_total)."""
+    w = np.asarray(weights, dtype=np.float64)
+    if w.ndim != 1 or w.size < 1 or not np.all(w > 0) or not np.all(np.isfinite(w)):
+        raise ValueError("weights must be positive and finite, one per rank")
+    cum = np.concatenate([[0.0], np.cumsum(w)]) / w.sum()
+    bounds = [min(N_total, int(round(N_total * c / align)) * align) for c in cum]
+    bounds[0], bounds[-1] = 0, N_total
+    for i in range(1, len(bounds)):
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return bounds[rank], bounds[rank + 1]
+
+
+def make_logistic_shard(torch, dev, N_total, K, rank=0, world=1, seed=SEED, block=1_000_000, alpha_true=0.3,
+                        rows=None):
     """Rows shard_rows(N_total, rank, world) of the synthetic logistic-regression problem,
     column-major fp64 X (stored as a (K, n) torch tensor) and int32 y, generated with torch's
     Philox on `dev`.  Every `block`-row block has its own seed, so any sharding of the same
-    (N_total, K, seed) reproduces the same global matrix on the same device type."""
-    r0, r1 = shard_rows(N_total, rank, world)
+    (N_total, K, seed) reproduces the same global matrix on the same device type.  rows=(r0, r1) overrides the
+    equal split (shard_rows_weighted)."""
+    r0, r1 = rows if rows is not None else shard_rows(N_total, rank, world)
     n = r1 - r0
     g = torch.Generator(device=dev)
     beta = torch.from_numpy(_rng(seed, 1).standard_normal(K) / np.sqrt(max(K, 1))).to(dev)
@@ -116,12 +134,14 @@ def make_shard(torch, dev, family, N_total, K, G=0, rank=0, world=1, seed=SEED, 
     return X, y, group, r0, r1
 
 
-def make_shard_ex(torch, dev, family, N_total, K, G=0, rank=0, world=1, seed=SEED, block=1_000_000, alpha_true=0.3):
-    """make_shard plus the binomial population sizes: returns X, y, group, trials (int32 or None), r0, r1."""
+def make_shard_ex(torch, dev, family, N_total, K, G=0, rank=0, world=1, seed=SEED, block=1_000_000, alpha_true=0.3,
+                  rows=None):
+    """make_shard plus the binomial population sizes: returns X, y, group, trials (int32 or None), r0, r1.
+    rows=(r0, r1) overrides the equal split."""
     if family == "bernoulli_logit" and G == 0:
-        X, y, r0, r1 = make_logistic_shard(torch, dev, N_total, K, rank, world, seed, block, alpha_true)
+        X, y, r0, r1 = make_logistic_shard(torch, dev, N_total, K, rank, world, seed, block, alpha_true, rows)
         return X, y, None, None, r0, r1
-    r0, r1 = shard_rows(N_total, rank, world)
+    r0, r1 = rows if rows is not None else shard_rows(N_total, rank, world)
     n = r1 - r0
     g = torch.Generator(device=dev)
     beta = torch.from_numpy(_rng(seed, 1).standard_normal(K) / np.sqrt(max(K, 1))).to(dev)

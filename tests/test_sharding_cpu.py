@@ -106,3 +106,26 @@ def test_make_shard_is_sharding_invariant_for_every_family():
             assert torch.equal(t, torch.cat([p[3] for p in parts])) and bool((y <= t).all())
         else:
             assert t is None
+
+
+def test_weighted_row_shards():
+    """bench.py --balance: rows split in proportion to per-GPU bandwidth; the blocks stay contiguous, aligned to
+    the panel height, and regenerate the same global data as the equal split."""
+    from stan_b200.synth import make_shard_ex, shard_rows_weighted
+    N = 100_003
+    for w in ([1.0], [1, 1, 1], [6.5, 6.1, 6.5, 6.4, 6.5, 6.5, 6.2, 6.5], [1e-3, 1.0], [5, 1, 1, 1, 1, 1, 1, 1]):
+        b = [shard_rows_weighted(N, w, r) for r in range(len(w))]
+        assert b[0][0] == 0 and b[-1][1] == N
+        assert all(b[i][1] == b[i + 1][0] for i in range(len(w) - 1))
+        assert all(r0 % 32 == 0 and r1 >= r0 for r0, r1 in b)
+        share = np.array([r1 - r0 for r0, r1 in b]) / N
+        assert np.max(np.abs(share - np.asarray(w, float) / np.sum(w))) < 64 / N + 1e-12
+    with pytest.raises(ValueError):
+        shard_rows_weighted(N, [1.0, 0.0], 0)
+    dev = torch.device("cpu")
+    X, y, _, _, _, _ = make_shard_ex(torch, dev, "bernoulli_logit", 2500, 5, 0, 0, 1, block=1000)
+    w = [2.0, 1.0, 3.0]
+    parts = [make_shard_ex(torch, dev, "bernoulli_logit", 2500, 5, 0, r, 3, block=1000,
+                           rows=shard_rows_weighted(2500, w, r)) for r in range(3)]
+    assert torch.equal(X, torch.cat([p[0] for p in parts], 1)) and torch.equal(y, torch.cat([p[1] for p in parts]))
+    assert [p[5] - p[4] for p in parts] == [r1 - r0 for r0, r1 in (shard_rows_weighted(2500, w, r) for r in range(3))]
