@@ -1,0 +1,44 @@
+// tests/host/link_host.cpp -- TEST INFRASTRUCTURE: the kernels' per-row arithmetic (stan_b200/csrc/glm_link.cuh,
+// the very source the GPU executes) compiled for the HOST, so tests/test_link_math_host.py can check it row by
+// row against the CPU oracle without a GPU.  Built by the test with g++ into a temporary shared object.
+#include "../../stan_b200/csrc/glm_link.cuh"
+
+using namespace b200glm;
+
+template <int FAMILY>
+static void rows(int n, const double* eta, const double* y, const double* aux, const LinkConst& lc, double* lp,
+                 double* r, double* x) {
+  for (int i = 0; i < n; ++i) link_ext<FAMILY>(eta[i], y[i], aux ? aux[i] : 0.0, lc, lp[i], r[i], x[i]);
+}
+
+extern "C" {
+
+// what the kernel prologue derives from the scale parameter (glm_kernels.cuh) + one link_ext call per row
+int link_rows(int family, int n, const double* eta, const double* y, const double* aux, double scale,
+              int inc_phi_terms, int inc_ytheta, double* lp, double* r, double* x) {
+  LinkConst lc;
+  lc.inv_sigma = 1.0;
+  lc.phi = 1.0;
+  lc.log_phi = lc.dg_phi = lc.lg_phi = 0.0;
+  lc.inc_phi_terms = inc_phi_terms;
+  lc.inc_ytheta = inc_ytheta;
+  if (family == FAM_NORMAL_ID) lc.inv_sigma = 1.0 / scale;
+  if (family == FAM_NEG_BINOMIAL_2_LOG) {
+    lc.phi = scale;
+    lc.log_phi = log(scale);
+    lc.dg_phi = digamma_pos(scale);
+    lc.lg_phi = lgamma(scale);
+  }
+  switch (family) {
+    case FAM_BERNOULLI_LOGIT: rows<FAM_BERNOULLI_LOGIT>(n, eta, y, aux, lc, lp, r, x); return 0;
+    case FAM_POISSON_LOG: rows<FAM_POISSON_LOG>(n, eta, y, aux, lc, lp, r, x); return 0;
+    case FAM_NORMAL_ID: rows<FAM_NORMAL_ID>(n, eta, y, aux, lc, lp, r, x); return 0;
+    case FAM_BINOMIAL_LOGIT: rows<FAM_BINOMIAL_LOGIT>(n, eta, y, aux, lc, lp, r, x); return 0;
+    case FAM_NEG_BINOMIAL_2_LOG: rows<FAM_NEG_BINOMIAL_2_LOG>(n, eta, y, aux, lc, lp, r, x); return 0;
+  }
+  return 1;
+}
+
+double digamma_host(double v) { return digamma_pos(v); }
+
+}  // extern "C"
