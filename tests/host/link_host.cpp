@@ -1,6 +1,8 @@
 // tests/host/link_host.cpp -- TEST INFRASTRUCTURE: the kernels' per-row arithmetic (stan_b200/csrc/glm_link.cuh,
 // the very source the GPU executes) compiled for the HOST, so tests/test_link_math_host.py can check it row by
 // row against the CPU oracle without a GPU.  Built by the test with g++ into a temporary shared object.
+#include <stddef.h>
+
 #include "../../stan_b200/csrc/glm_link.cuh"
 
 using namespace b200glm;
@@ -40,5 +42,16 @@ int link_rows(int family, int n, const double* eta, const double* y, const doubl
 }
 
 double digamma_host(double v) { return digamma_pos(v); }
+
+// ordered_logistic: out[4 * i + {0,1,2,3}] = lp_i, w_i, d1, d2
+void ordered_logistic_rows(int n, const double* loc, const int* c, int C, const double* cuts, double* out) {
+  for (int i = 0; i < n; ++i)
+    ordered_logistic_row(loc[i], c[i], C, cuts, out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+}
+
+// categorical_logit: lin is n x C row-major, overwritten with the per-class weights; lp[i] = the row's log-density
+void categorical_logit_rows(int n, int C, const int* y, double* lin, double* lp) {
+  for (int i = 0; i < n; ++i) lp[i] = categorical_logit_row(C, y[i], lin + (size_t)i * C);
+}
 
 }  // extern "C"

@@ -35,6 +35,11 @@ def host_lib(tmp_path_factory):
     L.link_rows.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_int, C.c_int, dp, dp, dp]
     L.digamma_host.argtypes = [C.c_double]
     L.digamma_host.restype = C.c_double
+    ip = C.POINTER(C.c_int)
+    L.ordered_logistic_rows.argtypes = [C.c_int, dp, ip, C.c_int, dp, dp]
+    L.ordered_logistic_rows.restype = None
+    L.categorical_logit_rows.argtypes = [C.c_int, C.c_int, ip, dp, dp]
+    L.categorical_logit_rows.restype = None
     return L
 
 
@@ -118,3 +123,54 @@ def test_rows_neg_binomial_2_log(host_lib):
             assert abs(r[i] - g_o[0]) <= 1e-12 * sc, (phi, eta[i], y[i])
             dphi = (x[i] - (phi - LOC) / SCALE ** 2) * phi          # chain through phi = exp(u), no Jacobian
             assert abs(dphi - g_o[2]) <= 1e-11 * max(abs(g_o[2]), phi * 1e-2, 1.0), (phi, eta[i], y[i], dphi, g_o[2])
+
+
+def test_rows_ordered_logistic(host_lib):
+    """ordered_logistic_row (not used by a kernel yet) against the oracle's ordered_logistic model on one-row data:
+    theta = [beta = 1, unconstrained cut-points]; lp, d/dbeta = loc * w and the cut-point partials d1 / d2."""
+    rng = np.random.default_rng(6)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    for Cn in (2, 3, 6):
+        u = np.concatenate([[-1.2], np.log(rng.uniform(0.3, 1.5, Cn - 2))]) if Cn > 2 else np.array([-0.4])
+        cuts = np.concatenate([[u[0]], u[0] + np.cumsum(np.exp(u[1:]))])
+        loc = np.concatenate([rng.normal(0, 2.5, 90), [0.0, 30.0, -30.0, cuts[0], cuts[-1]]])
+        cls = rng.integers(1, Cn + 1, loc.size).astype(np.int32)
+        out = np.empty(4 * loc.size)
+        host_lib.ordered_logistic_rows(loc.size, dp(loc), cls.ctypes.data_as(C.POINTER(C.c_int)), Cn, dp(cuts), dp(out))
+        out = out.reshape(-1, 4)
+        for i in range(loc.size):
+            po = PortOracle("ordered_logistic", np.array([[loc[i]]]), np.array([cls[i]]), n_classes=Cn)
+            lp_o, g_o = po.log_prob_grad(np.concatenate([[1.0], u]), propto=True, jacobian=False)
+            prior = PRIOR_B - 0.5 * np.sum((cuts / SD) ** 2)
+            assert abs(out[i, 0] + prior - lp_o) <= 1e-13 * max(abs(lp_o), 1.0), (Cn, loc[i], cls[i])
+            assert abs(loc[i] * out[i, 1] - 1.0 / SD ** 2 - g_o[0]) <= 1e-12 * max(abs(g_o[0]), 1.0)
+            dc = -cuts / SD ** 2                                 # prior on the constrained cut-points
+            if cls[i] != Cn:
+                dc[cls[i] - 1] += out[i, 3]
+            if cls[i] != 1:
+                dc[cls[i] - 2] -= out[i, 2]
+            du = np.array([dc[k:].sum() * (1.0 if k == 0 else np.exp(u[k])) for k in range(Cn - 1)])
+            assert np.max(np.abs(du - g_o[1:])) <= 1e-12 * max(np.max(np.abs(g_o[1:])), 1.0), (Cn, loc[i], cls[i])
+
+
+def test_rows_categorical_logit(host_lib):
+    """categorical_logit_row (not used by a kernel yet) against the oracle's categorical model on one-row data with
+    K = 1, x = 1: lin_c = alpha_c + beta_c; d/dalpha_c = d/dbeta_c (before the priors) = the per-class weight."""
+    rng = np.random.default_rng(8)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    for Cn in (2, 4, 9):
+        n = 60
+        alpha, beta = rng.normal(0, 1.5, (n, Cn)), rng.normal(0, 1.5, (n, Cn))
+        alpha[0], beta[0] = 0.0, 0.0
+        alpha[1, 0] = 40.0                                       # one class dominating: exp underflow in the others
+        y = rng.integers(1, Cn + 1, n).astype(np.int32)
+        lin = np.ascontiguousarray(alpha + beta)
+        lp = np.empty(n)
+        host_lib.categorical_logit_rows(n, Cn, y.ctypes.data_as(C.POINTER(C.c_int)), dp(lin), dp(lp))
+        for i in range(n):
+            po = PortOracle("categorical_logit", np.array([[1.0]]), np.array([y[i]]), n_classes=Cn)
+            lp_o, g_o = po.log_prob_grad(np.concatenate([alpha[i], beta[i]]), propto=True, jacobian=False)
+            prior = -0.5 * np.sum((alpha[i] / SD) ** 2) - 0.5 * np.sum((beta[i] / SD) ** 2)
+            assert abs(lp[i] + prior - lp_o) <= 1e-13 * max(abs(lp_o), 1.0), (Cn, i)
+            assert np.max(np.abs(lin[i] - alpha[i] / SD ** 2 - g_o[:Cn])) <= 1e-13 * max(np.max(np.abs(g_o)), 1.0)
+            assert np.max(np.abs(lin[i] - beta[i] / SD ** 2 - g_o[Cn:])) <= 1e-13 * max(np.max(np.abs(g_o)), 1.0)
