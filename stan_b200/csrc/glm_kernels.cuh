@@ -33,6 +33,7 @@
 #include <stdint.h>
 
 #include "glm_link.cuh"   // family ids, link<> / link_ext<> and their special functions (also compiled for the host)
+#include "glm_model.cuh"  // KernelParams, ModelConst and the model epilogue finish() (also compiled for the host)
 
 namespace b200glm {
 
@@ -46,65 +47,6 @@ constexpr int SMEM_A_MAX_GROUPS = 2048;  // a[G] staged in smem up to this many 
 __host__ __device__ constexpr int fam_group_col(int f, int K) { return K + 1 + (f == FAM_BINOMIAL_LOGIT ? 1 : 0); }
 // doubles per CTA partial row: K beta gradients, lp-sum, r-sum, aux-sum (d/dphi terms of neg_binomial_2_log)
 __host__ __device__ constexpr int partial_stride(int K) { return (K + 3 + 1) & ~1; }
-enum { MODE_THETA = 0, MODE_LEAPFROG = 1 };
-enum { ST_OK = 0, ST_DOMAIN = 1, ST_PEER_TIMEOUT = 2 };
-
-#define NEG_LOG_SQRT_TWO_PI_D (-0.91893853320467274178032973640562)
-
-// Everything the epilogue needs to turn likelihood sums into the model's lp / gradient.
-struct ModelConst {
-  int family, K, G, P, off_beta;
-  int propto, jacobian, is_var;  // semantics of this evaluation (see include/b200glm.h)
-  int lik_only;                  // function-level call (b200glm_glm_lpmf): the GLM term alone -- no priors, no
-                                 // Jacobian; the sigma entry of the gradient is d/d sigma, not d/d log sigma
-  int sigma_is_var;              // lik_only + normal_id: keep -N log sigma under propto (normal_id_glm_lpdf.hpp:205);
-                                 // lik_only + neg_binomial_2_log: phi is an autodiff variable (the phi-only terms
-                                 // stay); 2 = phi is the ONLY variable operand (y * theta drops under propto)
-  double N_total;                // rows over all shards
-  double lgamma_sum;             // propto=0 constant over all shards, subtracted: sum lgamma(y+1) (poisson,
-                                 // neg_binomial_2_log), -sum binomial_coefficient_log(trials, y) (binomial_logit)
-  double prior_alpha_sd, prior_beta_sd, prior_sigma_loc, prior_sigma_scale, prior_sigma_a_scale;
-};
-
-// Row-sharded operation without a separate collective launch: every rank owns a mailbox in its HBM,
-// mapped into every peer (CUDA IPC over NVLink / NVSwitch).  [2 parities][world][stride] doubles; the
-// last word of an entry is the sequence number of the evaluation it belongs to.
-constexpr int MAX_PEERS = 8;
-struct PeerParams {
-  int enabled, world, rank, stride;
-  unsigned long long seq;          // 1, 2, 3, ... identical on every rank for the same evaluation
-  unsigned long long timeout_ns;
-  double* mbox[MAX_PEERS];         // this slot's mailbox on rank r (mbox[rank] is local memory)
-};
-
-struct KernelParams {
-  const double* panels;
-  long long n_rows;    // local rows
-  long long n_panels;  // local panels
-  int K, C, G, family, P, off_beta;
-  int n_stages;        // narrow kernel: panel stages; wide kernel: sub-panel slots in the ring
-  int Cpad, Kc, J;     // wide kernel: padded column count, sub-panel width, sub-panels per row panel
-  int mode;
-  int fuse_finish;     // last CTA also runs finish() (G == 0 and: world == 1, or peers connected)
-  int peer_in_main;    // last CTA of the main kernel exchanges the likelihood partials with the peers
-  int peer_in_finish;  // finish_kernel does (G > 0: the group sums are only complete by then)
-  PeerParams peer;
-  int stage_a_in_smem;
-  const double* theta_in;   // MODE_THETA: P doubles (device)
-  const double* st_in;      // MODE_LEAPFROG: [q(P) p(P) g(P) V]
-  double* st_out;
-  const double* inv_metric; // P doubles
-  double eps;
-  double* partials;         // [grid][pstride]: [0,K) beta grads, [K] lp-sum, [K+1] r-sum
-  int pstride;
-  unsigned int* ticket;
-  double* r_out;            // G > 0: residual per (sorted) row
-  double* lik;              // [P] likelihood gradient aligned with theta, [P] lp-sum, [P+1] spare
-  double* result;           // [lp, grad(P), status]
-  double* theta_used;       // P doubles: the theta this launch evaluated (q_new in leapfrog mode)
-  ModelConst mc;
-};
-
 // ------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk async copy (TMA engine)
 // ------------------------------------------------------------------------------------------
@@ -164,12 +106,6 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void named_barrier_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -235,209 +171,6 @@ __device__ void peer_timeout_result(const KernelParams& p) {
     p.result[0] = CUDART_NAN;
     p.result[1 + p.P] = (double)ST_PEER_TIMEOUT;
     if (p.mode == MODE_LEAPFROG) p.st_out[3 * p.P] = CUDART_NAN;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Model epilogue, run by ONE CTA once the likelihood sums are complete in p.lik.
-//   theta: the evaluated point (p.theta_used).
-// ------------------------------------------------------------------------------------------
-__device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratch */) {
-  const ModelConst& mc = p.mc;
-  const int P = mc.P, K = mc.K, G = mc.G;
-  const double* theta = p.theta_used;
-  const double* lik = p.lik;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const bool dens = (!mc.propto) || mc.is_var;  // include_summand: anything left to compute?
-
-  const double alpha = G > 0 ? 0.0 : theta[0];
-  const double mu_a = G > 0 ? theta[0] : 0.0;
-  const double u_sa = G > 0 ? theta[1] : 0.0;
-  const double sigma_a = G > 0 ? exp(u_sa) : 1.0;
-  const bool has_scale = fam_has_scale(mc.family);   // sigma (normal_id) | phi (neg_binomial_2_log)
-  const double u_s = has_scale ? theta[P - 1] : 0.0;
-  const double sigma = has_scale ? exp(u_s) : 1.0;
-  const double ib2 = 1.0 / (mc.prior_beta_sd * mc.prior_beta_sd);
-  const double isa2 = 1.0 / (sigma_a * sigma_a);
-
-  // block-wide sums: [0] sum beta^2, [1] sum (a-mu)^2, [2] non-finite count
-  double sb = 0.0, sa = 0.0, bad = 0.0;
-  for (int k = tid; k < K; k += nt) {
-    const double b = theta[mc.off_beta + k];
-    sb += b * b;
-  }
-  for (int g = tid; g < G; g += nt) {
-    const double d = theta[2 + g] - mu_a;
-    sa += d * d;
-  }
-  for (int i = tid; i < P; i += nt) {
-    if (!isfinite(theta[i]) || !isfinite(lik[i])) bad += 1.0;
-  }
-  sb = warp_sum(sb);
-  sa = warp_sum(sa);
-  bad = warp_sum(bad);
-  __syncthreads();
-  const int w = tid >> 5, nw = (nt + 31) >> 5;
-  if ((tid & 31) == 0) {
-    sh[w] = sb;
-    sh[16 + w] = sa;
-    sh[32 + w] = bad;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    double a0 = 0, a1 = 0, a2 = 0;
-    for (int i = 0; i < nw; ++i) {
-      a0 += sh[i];
-      a1 += sh[16 + i];
-      a2 += sh[32 + i];
-    }
-    sh[48] = a0;
-    sh[49] = a1;
-    sh[50] = a2;
-  }
-  __syncthreads();
-  const double sum_b2 = sh[48], sum_d2 = sh[49];
-  const double n_bad = sh[50];
-
-  // ---- value (thread 0) ----
-  if (tid == 0) {
-    double lp = 0.0;
-    if (mc.jacobian && !mc.lik_only) {
-      if (G > 0) lp += u_sa;                           // lb_constrain.hpp:64
-      if (has_scale) lp += u_s;
-    }
-    if (dens && !mc.lik_only) {
-      // priors: normal_lpdf.hpp:81-88
-      if (G > 0) {
-        const double z0 = mu_a / mc.prior_alpha_sd;
-        lp += -0.5 * z0 * z0;
-        const double z1 = sigma_a / mc.prior_sigma_a_scale;
-        lp += -0.5 * z1 * z1;
-        lp += -0.5 * sum_d2 * isa2 - G * u_sa;         // -G log sigma_a (sigma_a is a parameter)
-        if (!mc.propto)
-          lp += 2.0 * NEG_LOG_SQRT_TWO_PI_D - log(mc.prior_alpha_sd) - log(mc.prior_sigma_a_scale)
-                + G * NEG_LOG_SQRT_TWO_PI_D;
-      } else {
-        const double z0 = alpha / mc.prior_alpha_sd;
-        lp += -0.5 * z0 * z0;
-        if (!mc.propto) lp += NEG_LOG_SQRT_TWO_PI_D - log(mc.prior_alpha_sd);
-      }
-      if (K > 0) {
-        lp += -0.5 * sum_b2 * ib2;
-        if (!mc.propto) lp += K * (NEG_LOG_SQRT_TWO_PI_D - log(mc.prior_beta_sd));
-      }
-      if (has_scale) {
-        const double z = (sigma - mc.prior_sigma_loc) / mc.prior_sigma_scale;
-        lp += -0.5 * z * z;
-        if (!mc.propto) lp += NEG_LOG_SQRT_TWO_PI_D - log(mc.prior_sigma_scale);
-      }
-    }
-    if (dens) {
-      // likelihood
-      if (mc.N_total > 0) {
-        const double S = lik[P];
-        if (mc.family == FAM_BERNOULLI_LOGIT) {
-          lp += S;
-        } else if (mc.family == FAM_POISSON_LOG || mc.family == FAM_BINOMIAL_LOGIT) {
-          lp += S;
-          if (!mc.propto) lp -= mc.lgamma_sum;         // poisson_log_glm_lpmf.hpp:127-129, binomial_logit_glm_lpmf.hpp:127-130
-        } else if (mc.family == FAM_NEG_BINOMIAL_2_LOG) {
-          lp += S;                                     // neg_binomial_2_log_glm_lpmf.hpp:186-197 (row terms)
-          if (!mc.propto) lp -= mc.lgamma_sum;         // :163-169
-          if (!mc.lik_only || !mc.propto || mc.sigma_is_var)
-            lp += mc.N_total * (sigma * log(sigma) - lgamma(sigma));   // :170-185 multiply_log(phi, phi) - lgamma(phi)
-        } else {
-          if (!mc.propto) lp += NEG_LOG_SQRT_TWO_PI_D * mc.N_total;   // normal_id_glm_lpdf.hpp:202-204
-          if (!mc.lik_only || !mc.propto || mc.sigma_is_var)
-            lp -= mc.N_total * u_s;                                   // :205-212, log sigma = u_s
-          lp -= 0.5 * S;                                              // :213
-        }
-      }
-    }
-    const bool ok = isfinite(lp) && n_bad == 0.0;
-    sh[51] = lp;
-    sh[52] = ok ? 0.0 : 1.0;
-  }
-  __syncthreads();
-  const double lp = sh[51];
-  const bool domain = sh[52] != 0.0;
-
-  // ---- gradient wrt unconstrained theta, one thread per entry ----
-  for (int i = tid; i < P; i += nt) {
-    double g = lik[i];
-    if (mc.lik_only) {
-      if (mc.family == FAM_NORMAL_ID && i == P - 1)
-        g = mc.N_total > 0 ? (lik[P] - mc.N_total) / sigma : 0.0;    // normal_id_glm_lpdf.hpp:181-183
-      else if (mc.family == FAM_NEG_BINOMIAL_2_LOG && i == P - 1)
-        g = mc.N_total > 0 ? lik[P + 1] : 0.0;                       // neg_binomial_2_log_glm_lpmf.hpp:240-245
-      else if (G > 0 && i < 2)
-        g = 0.0;
-      p.result[1 + i] = g;
-      continue;
-    }
-    if (G > 0) {
-      if (i == 0) {
-        g = -mu_a / (mc.prior_alpha_sd * mc.prior_alpha_sd) + 0.0;  // + sum_g (a_g-mu)/sigma_a^2 below
-      } else if (i == 1) {
-        g = 0.0;
-      } else if (i < 2 + G) {
-        g += -(theta[i] - mu_a) * isa2;
-      }
-    } else if (i == 0) {
-      g += -alpha / (mc.prior_alpha_sd * mc.prior_alpha_sd);
-    }
-    if (i >= mc.off_beta && i < mc.off_beta + K) g += -theta[i] * ib2;
-    if (has_scale && i == P - 1) {
-      double dlik = 0.0;
-      if (mc.N_total > 0)
-        dlik = mc.family == FAM_NORMAL_ID ? (lik[P] - mc.N_total) / sigma   // normal_id_glm_lpdf.hpp:181-183
-                                          : lik[P + 1];                     // neg_binomial_2_log_glm_lpmf.hpp:240-245
-      const double dpri = -(sigma - mc.prior_sigma_loc) / (mc.prior_sigma_scale * mc.prior_sigma_scale);
-      g = (dlik + dpri) * sigma + (mc.jacobian ? 1.0 : 0.0);
-    }
-    p.result[1 + i] = g;
-  }
-  __syncthreads();
-  if (G > 0 && !mc.lik_only) {  // mu_a and sigma_a entries need sums over the G group intercepts
-    double sd = 0.0;
-    for (int g = tid; g < G; g += nt) sd += theta[2 + g] - mu_a;
-    sd = warp_sum(sd);
-    __syncthreads();
-    if ((tid & 31) == 0) sh[w] = sd;
-    __syncthreads();
-    if (tid == 0) {
-      double tot = 0;
-      for (int i = 0; i < nw; ++i) tot += sh[i];
-      p.result[1 + 0] += tot * isa2;
-      const double dsa = -sigma_a / (mc.prior_sigma_a_scale * mc.prior_sigma_a_scale)
-                         + sum_d2 * isa2 / sigma_a - G / sigma_a;
-      p.result[1 + 1] = dsa * sigma_a + (mc.jacobian ? 1.0 : 0.0);
-    }
-    __syncthreads();
-  }
-  if (tid == 0) {
-    p.result[0] = lp;
-    p.result[1 + P] = domain ? (double)ST_DOMAIN : (double)ST_OK;
-  }
-
-  // ---- leapfrog tail (expl_leapfrog.hpp:28-32 end_update_p; base_hamiltonian.hpp:64-69) ----
-  if (p.mode == MODE_LEAPFROG) {
-    const double* q0 = p.st_in;
-    const double* p0 = p.st_in + P;
-    const double* g0 = p.st_in + 2 * P;
-    double* qn = p.st_out;
-    double* pn = p.st_out + P;
-    double* gn = p.st_out + 2 * P;
-    const double he = 0.5 * p.eps;
-    for (int i = tid; i < P; i += nt) {
-      const double ph = p0[i] - he * g0[i];
-      const double gnew = domain ? -g0[i] : -p.result[1 + i];
-      qn[i] = theta[i];
-      gn[i] = gnew;
-      pn[i] = ph - he * gnew;
-      (void)q0;
-    }
-    if (tid == 0) p.st_out[3 * P] = domain ? CUDART_INF : -lp;
   }
 }
 

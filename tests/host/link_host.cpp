@@ -1,9 +1,26 @@
 // tests/host/link_host.cpp -- TEST INFRASTRUCTURE: the kernels' per-row arithmetic (stan_b200/csrc/glm_link.cuh,
 // the very source the GPU executes) compiled for the HOST, so tests/test_link_math_host.py can check it row by
 // row against the CPU oracle without a GPU.  Built by the test with g++ into a temporary shared object.
+#include <math.h>
 #include <stddef.h>
+#include <string.h>
+
+// one-thread CTA: what the CUDA built-ins finish() uses mean when a single host thread runs the whole block
+#define __device__
+#define __forceinline__ inline
+#define CUDART_INF INFINITY
+#define CUDART_NAN NAN
+namespace b200glm {
+struct host_dim3 {
+  int x;
+};
+static const host_dim3 threadIdx = {0}, blockDim = {1};
+inline void __syncthreads() {}
+inline double warp_sum(double v) { return v; }   // a warp of one lane
+}  // namespace b200glm
 
 #include "../../stan_b200/csrc/glm_link.cuh"
+#include "../../stan_b200/csrc/glm_model.cuh"
 
 using namespace b200glm;
 
@@ -42,6 +59,48 @@ int link_rows(int family, int n, const double* eta, const double* y, const doubl
 }
 
 double digamma_host(double v) { return digamma_pos(v); }
+
+// The model epilogue finish() (glm_model.cuh) as one host thread.
+//   ic = {family, K, G, P, off_beta, propto, jacobian, is_var, lik_only, sigma_is_var, mode}
+//   dc = {N_total, lgamma_sum, prior_alpha_sd, prior_beta_sd, prior_sigma_loc, prior_sigma_scale, prior_sigma_a_scale, eps}
+//   lik: P + 2 likelihood sums laid out as the kernels leave them; result: P + 2; st_in / st_out: 3P + 1 (leapfrog mode)
+void finish_host(const int* ic, const double* dc, const double* theta_used, double* lik, double* result,
+                 const double* st_in, double* st_out) {
+  KernelParams p;
+  memset(&p, 0, sizeof(p));
+  ModelConst& mc = p.mc;
+  mc.family = ic[0];
+  mc.K = ic[1];
+  mc.G = ic[2];
+  mc.P = ic[3];
+  mc.off_beta = ic[4];
+  mc.propto = ic[5];
+  mc.jacobian = ic[6];
+  mc.is_var = ic[7];
+  mc.lik_only = ic[8];
+  mc.sigma_is_var = ic[9];
+  p.mode = ic[10];
+  mc.N_total = dc[0];
+  mc.lgamma_sum = dc[1];
+  mc.prior_alpha_sd = dc[2];
+  mc.prior_beta_sd = dc[3];
+  mc.prior_sigma_loc = dc[4];
+  mc.prior_sigma_scale = dc[5];
+  mc.prior_sigma_a_scale = dc[6];
+  p.eps = dc[7];
+  p.K = mc.K;
+  p.G = mc.G;
+  p.P = mc.P;
+  p.family = mc.family;
+  p.off_beta = mc.off_beta;
+  p.theta_used = const_cast<double*>(theta_used);
+  p.lik = lik;
+  p.result = result;
+  p.st_in = st_in;
+  p.st_out = st_out;
+  double scratch[64];
+  finish(p, scratch);
+}
 
 // ordered_logistic: out[4 * i + {0,1,2,3}] = lp_i, w_i, d1, d2
 void ordered_logistic_rows(int n, const double* loc, const int* c, int C, const double* cuts, double* out) {
