@@ -288,4 +288,116 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Model epilogues of the two class models (ordered_logistic_glm, categorical_logit_glm).  No kernel calls them
+// yet: like their row arithmetic in glm_link.cuh they are written ahead of the kernels
+// and pinned to the oracle through the host build (tests/test_model_epilogue_host.py).  The Stan programs:
+//   ordered_logistic:   parameters { vector[K] beta; ordered[C-1] c; }            theta = [beta, c unconstrained]
+//                       beta ~ normal(0, prior_beta_sd); c ~ normal(0, prior_alpha_sd);
+//   categorical_logit:  parameters { vector[C] alpha; matrix[K, C] beta; }        theta = [alpha, beta col-major]
+//                       alpha ~ normal(0, prior_alpha_sd); to_vector(beta) ~ normal(0, prior_beta_sd);
+// ------------------------------------------------------------------------------------------
+struct ClassModelParams {
+  int family_ordered;        // 1 = ordered_logistic, 0 = categorical_logit
+  int K, C, P;               // attributes, classes, parameters
+  int propto, jacobian, is_var;
+  int mode;                  // MODE_THETA / MODE_LEAPFROG
+  double N_total;            // rows over all shards
+  double prior_alpha_sd, prior_beta_sd;
+  double eps;
+  const double* theta_used;  // P
+  const double* lik;         // P + 1: d logp / d (constrained parameter) sums aligned with theta, then the lp-sum.
+                             // ordered_logistic: entries [K, K + C - 1) are the partials wrt the cut-points c
+  double* cuts;              // ordered_logistic: 2 (C - 1) doubles of scratch (cut-points, their partials)
+  double* result;            // [lp, grad(P), status]
+  const double* st_in;       // MODE_LEAPFROG: [q(P) p(P) g(P) V]
+  double* st_out;
+};
+
+__device__ void finish_class_model(const ClassModelParams& p, double* sh /* >= 8 doubles scratch */) {
+  const int K = p.K, C = p.C, P = p.P;
+  const double* theta = p.theta_used;
+  const double* lik = p.lik;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const bool dens = (!p.propto) || p.is_var;   // include_summand: anything left to compute?
+  const double ia2 = 1.0 / (p.prior_alpha_sd * p.prior_alpha_sd), ib2 = 1.0 / (p.prior_beta_sd * p.prior_beta_sd);
+  const int nc = p.family_ordered ? (C > 0 ? C - 1 : 0) : 0;
+  // the likelihood term is empty without rows, with one class (categorical...:70-72) or without cut-points (ordered...:93-95)
+  const bool lik_on = dens && p.N_total > 0 && C > 1;
+
+  if (tid == 0) {
+    double lp = 0.0, bad = 0.0;
+    for (int i = 0; i < P; ++i)
+      if (!isfinite(theta[i]) || !isfinite(lik[i])) bad += 1.0;
+    double sb = 0.0, sa = 0.0;
+    if (p.family_ordered) {
+      // ordered_constrain.hpp:34-37 (+ Jacobian :56-58), then check_ordered / check_finite (ordered...:85-91)
+      for (int k = 0; k < nc; ++k) {
+        p.cuts[k] = k == 0 ? theta[K] : p.cuts[k - 1] + exp(theta[K + k]);
+        if (p.jacobian && k > 0) lp += theta[K + k];
+        if (k > 0 && !(p.cuts[k] > p.cuts[k - 1])) bad += 1.0;
+        sa += p.cuts[k] * p.cuts[k];
+      }
+      if (nc > 0 && (!isfinite(p.cuts[0]) || !isfinite(p.cuts[nc - 1]))) bad += 1.0;
+      for (int k = 0; k < K; ++k) sb += theta[k] * theta[k];
+    } else {
+      for (int c = 0; c < C; ++c) sa += theta[c] * theta[c];
+      for (int i = C; i < P; ++i) sb += theta[i] * theta[i];
+    }
+    if (dens) {   // normal_lpdf.hpp:81-88 on vectors, the scale is data
+      const int n_a = p.family_ordered ? nc : C, n_b = p.family_ordered ? K : K * C;
+      if (n_a > 0) {
+        lp += -0.5 * sa * ia2;
+        if (!p.propto) lp += n_a * (NEG_LOG_SQRT_TWO_PI_D - log(p.prior_alpha_sd));
+      }
+      if (n_b > 0) {
+        lp += -0.5 * sb * ib2;
+        if (!p.propto) lp += n_b * (NEG_LOG_SQRT_TWO_PI_D - log(p.prior_beta_sd));
+      }
+    }
+    if (lik_on) lp += lik[P];
+    sh[0] = lp;
+    sh[1] = (isfinite(lp) && bad == 0.0) ? 0.0 : 1.0;
+    // ordered_logistic: partials wrt the cut-points (likelihood + prior), then the chain rule through
+    // ordered_constrain: d c_j / d u_k = exp(u_k) for j >= k (1 for k = 0), + the Jacobian term
+    if (p.family_ordered) {
+      double tail = 0.0;
+      for (int k = nc - 1; k >= 0; --k) {
+        tail += (lik_on ? lik[K + k] : 0.0) - (dens ? p.cuts[k] * ia2 : 0.0);
+        p.cuts[nc + k] = k == 0 ? tail : tail * exp(theta[K + k]) + (p.jacobian ? 1.0 : 0.0);
+      }
+    }
+  }
+  __syncthreads();
+  const double lp = sh[0];
+  const bool domain = sh[1] != 0.0;
+  for (int i = tid; i < P; i += nt) {
+    double g;
+    if (p.family_ordered) {
+      g = i < K ? (lik_on ? lik[i] : 0.0) - (dens ? theta[i] * ib2 : 0.0) : p.cuts[nc + (i - K)];
+    } else {
+      g = (lik_on ? lik[i] : 0.0) - (dens ? theta[i] * (i < C ? ia2 : ib2) : 0.0);
+    }
+    p.result[1 + i] = g;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    p.result[0] = lp;
+    p.result[1 + P] = domain ? (double)ST_DOMAIN : (double)ST_OK;
+  }
+  if (p.mode == MODE_LEAPFROG) {   // expl_leapfrog.hpp:28-32 end_update_p; base_hamiltonian.hpp:64-69
+    const double* p0 = p.st_in + P;
+    const double* g0 = p.st_in + 2 * P;
+    const double he = 0.5 * p.eps;
+    for (int i = tid; i < P; i += nt) {
+      const double ph = p0[i] - he * g0[i];
+      const double gnew = domain ? -g0[i] : -p.result[1 + i];
+      p.st_out[i] = theta[i];
+      p.st_out[2 * P + i] = gnew;
+      p.st_out[P + i] = ph - he * gnew;
+    }
+    if (tid == 0) p.st_out[3 * P] = domain ? CUDART_INF : -lp;
+  }
+}
+
 }  // namespace b200glm

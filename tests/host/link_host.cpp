@@ -113,4 +113,32 @@ void categorical_logit_rows(int n, int C, const int* y, double* lin, double* lp)
   for (int i = 0; i < n; ++i) lp[i] = categorical_logit_row(C, y[i], lin + (size_t)i * C);
 }
 
+// finish_class_model() as one host thread.
+//   ic = {family_ordered, K, C, P, propto, jacobian, is_var, mode};  dc = {N_total, prior_alpha_sd, prior_beta_sd, eps}
+void finish_class_model_host(const int* ic, const double* dc, const double* theta_used, const double* lik, double* cuts,
+                             double* result, const double* st_in, double* st_out) {
+  ClassModelParams p;
+  memset(&p, 0, sizeof(p));
+  p.family_ordered = ic[0];
+  p.K = ic[1];
+  p.C = ic[2];
+  p.P = ic[3];
+  p.propto = ic[4];
+  p.jacobian = ic[5];
+  p.is_var = ic[6];
+  p.mode = ic[7];
+  p.N_total = dc[0];
+  p.prior_alpha_sd = dc[1];
+  p.prior_beta_sd = dc[2];
+  p.eps = dc[3];
+  p.theta_used = theta_used;
+  p.lik = lik;
+  p.cuts = cuts;
+  p.result = result;
+  p.st_in = st_in;
+  p.st_out = st_out;
+  double scratch[8];
+  finish_class_model(p, scratch);
+}
+
 }  // extern "C"

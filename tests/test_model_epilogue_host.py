@@ -135,3 +135,102 @@ def test_epilogue_domain_error_status(host_lib):
     with np.errstate(all="ignore"):
         _, st = hp.finish(th, 1, 1, 1, mode=1, eps=0.1, st_in=np.concatenate([q0, p0, g0, [5.0]]))
     assert st[12] == np.inf and np.array_equal(st[8:12], -g0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The class models (ordered_logistic_glm, categorical_logit_glm): row arithmetic + epilogue written ahead of their
+# kernels and pinned here, through the host build, to the oracle.
+# ---------------------------------------------------------------------------------------------------------------
+class HostClassModelPath:
+    def __init__(self, L, family, d, Cn):
+        self.L, self.ordered, self.Cn = L, family == "ordered_logistic", Cn
+        self.X, self.y = np.asarray(d["X"]), np.ascontiguousarray(d["y"], dtype=np.int32)
+        self.N, self.K = self.X.shape
+        self.P = self.K + Cn - 1 if self.ordered else Cn * (1 + self.K)
+        ip = C.POINTER(C.c_int)
+        L.finish_class_model_host.argtypes = [ip, C.POINTER(C.c_double)] + [C.POINTER(C.c_double)] * 6
+        L.finish_class_model_host.restype = None
+
+    def lik_sums(self, theta):
+        K, Cn, N = self.K, self.Cn, self.N
+        lik = np.zeros(self.P + 1)
+        ip = C.POINTER(C.c_int)
+        if self.ordered:
+            u = theta[K:]
+            cuts = np.concatenate([[u[0]], u[0] + np.cumsum(np.exp(u[1:]))]) if Cn > 1 else np.zeros(0)
+            loc = np.ascontiguousarray(self.X @ theta[:K])
+            out = np.empty(4 * N)
+            self.L.ordered_logistic_rows(N, dp(loc), self.y.ctypes.data_as(ip), Cn, dp(np.ascontiguousarray(cuts)), dp(out))
+            out = out.reshape(-1, 4)
+            lik[:K] = self.X.T @ out[:, 1]
+            for i in range(N):                                  # ordered_logistic_glm_lpmf.hpp:202-207
+                c = self.y[i]
+                if c != Cn:
+                    lik[K + c - 1] += out[i, 3]
+                if c != 1:
+                    lik[K + c - 2] -= out[i, 2]
+            lik[self.P] = out[:, 0].sum()
+        else:
+            alpha, B = theta[:Cn], theta[Cn:].reshape(Cn, K).T    # beta[k + K c]
+            lin = np.ascontiguousarray(self.X @ B + alpha)
+            lp = np.empty(N)
+            self.L.categorical_logit_rows(N, Cn, self.y.ctypes.data_as(ip), dp(lin), dp(lp))
+            lik[:Cn] = lin.sum(axis=0)
+            lik[Cn:self.P] = (self.X.T @ lin).T.ravel()
+            lik[self.P] = lp.sum()
+        return lik
+
+    def finish(self, theta, propto, jacobian, is_var, mode=0, eps=0.0, st_in=None):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        ic = (C.c_int * 8)(int(self.ordered), self.K, self.Cn, self.P, int(propto), int(jacobian), int(is_var), mode)
+        dc = (C.c_double * 4)(float(self.N), PRIORS["prior_alpha_sd"], PRIORS["prior_beta_sd"], eps)
+        lik = self.lik_sums(theta) if self.Cn > 1 and self.N > 0 else np.zeros(self.P + 1)
+        res, cuts = np.zeros(self.P + 2), np.zeros(2 * max(self.Cn, 1))
+        st_in = np.zeros(3 * self.P + 1) if st_in is None else np.ascontiguousarray(st_in)
+        st_out = np.zeros(3 * self.P + 1)
+        self.L.finish_class_model_host(ic, dc, dp(theta), dp(lik), dp(cuts), dp(res), dp(st_in), dp(st_out))
+        return res, st_out
+
+
+@pytest.mark.parametrize("family,N,K,Cn", [("ordered_logistic", 301, 5, 4), ("ordered_logistic", 97, 3, 2),
+                                           ("ordered_logistic", 64, 0, 3), ("ordered_logistic", 40, 2, 1),
+                                           ("categorical_logit", 301, 5, 4), ("categorical_logit", 97, 2, 2),
+                                           ("categorical_logit", 40, 3, 1)])
+def test_class_model_epilogue_matches_oracle(host_lib, family, N, K, Cn):
+    d = make_glm_data(family, N, K, n_classes=Cn, seed=91)
+    po = PortOracle(family, d["X"], d["y"], n_classes=Cn, **PRIORS)
+    hp = HostClassModelPath(host_lib, family, d, Cn)
+    assert hp.P == po.P
+    rng = np.random.default_rng(13)
+    for sc in (0.0, 0.3, 0.9):
+        th = sc * rng.standard_normal(hp.P)
+        for propto in (1, 0):
+            for jac in (1, 0):
+                res, _ = hp.finish(th, propto, jac, is_var=1)
+                lp_o, g_o = po.log_prob_grad(th, propto, jac)
+                assert res[hp.P + 1] == 0.0
+                assert rel_err(res[0], lp_o) < TOL, (family, Cn, sc, propto, jac, res[0], lp_o)
+                assert rel_err_vec(res[1:1 + hp.P], g_o) < TOL, (family, Cn, sc, propto, jac)
+                res, _ = hp.finish(th, propto, jac, is_var=0)
+                assert rel_err(res[0], po.log_prob(th, propto, jac)) < TOL, (family, Cn, sc, propto, jac)
+    # one leapfrog step
+    if hp.P:
+        q0, p0 = 0.1 * rng.standard_normal(hp.P), rng.standard_normal(hp.P)
+        im = np.exp(0.3 * rng.standard_normal(hp.P))
+        lp0, gr0 = po.log_prob_grad(q0)
+        g0, V0, eps = -gr0, -lp0, 0.011
+        q_new = q0 + eps * (im * (p0 - 0.5 * eps * g0))
+        _, st = hp.finish(q_new, 1, 1, 1, mode=1, eps=eps, st_in=np.concatenate([q0, p0, g0, [V0]]))
+        q1, p1, g1, V1 = po.leapfrog(eps, im, q0, p0, g0, V0)
+        P = hp.P
+        assert rel_err_vec(st[:P], q1) < TOL and rel_err_vec(st[P:2 * P], p1) < 1e-11
+        assert rel_err_vec(st[2 * P:3 * P], g1) < 1e-11 and rel_err(st[3 * P], V1) < TOL
+
+
+def test_class_model_epilogue_domain_status(host_lib):
+    """exp(u) underflows -> cut-points not strictly increasing -> ST_DOMAIN (check_ordered, ordered...:85)."""
+    d = make_glm_data("ordered_logistic", 50, 2, n_classes=3, seed=5)
+    hp = HostClassModelPath(host_lib, "ordered_logistic", d, 3)
+    with np.errstate(all="ignore"):
+        res, _ = hp.finish(np.array([0.0, 0.0, 0.3, -800.0]), 1, 1, 1)
+    assert res[hp.P + 1] == 1.0
