@@ -35,7 +35,8 @@
 extern "C" {
 #endif
 
-#define B200GLM_ABI_VERSION 2   /* 2: b200glm_desc gained `trials` (appended), families 3 and 4 */
+#define B200GLM_ABI_VERSION 3   /* 2: b200glm_desc gained `trials` (appended), families 3 and 4
+                                   3: b200glm_abi_version, shard constants, timeline, (no struct change) */
 
 /* status codes; the C++ shim maps them to the exceptions the reference throws:
  * DOMAIN -> std::domain_error (recoverable: base_hamiltonian.hpp:65-68, initialize.hpp:104-112),
@@ -180,13 +181,31 @@ int b200glm_peer_export(b200glm_handle* h, void* ipc_handle_64);
 int b200glm_peer_connect(b200glm_handle* h, const void* all_handles, int32_t world);
 double b200glm_lgamma_sum_local(const b200glm_handle* h);
 int b200glm_set_lgamma_sum_total(b200glm_handle* h, double total);
+/* Both create-time per-shard constants at once: out[0] = the propto=false constant of this shard (poisson_log,
+ * binomial_logit, neg_binomial_2_log; 0 otherwise), out[1] = 1 if this shard holds an out-of-range y (the data
+ * checks bernoulli_logit_glm_lpmf.hpp:85, poisson_log_glm_lpmf.hpp:84, ... perform on every call).  Sum both over
+ * the ranks and store the totals, so that every rank subtracts the same constant and reports the same
+ * B200GLM_DOMAIN status (b200glm_comm_init does this itself over NCCL). */
+int b200glm_shard_constants_local(const b200glm_handle* h, double out[2]);
+int b200glm_set_shard_constants_total(b200glm_handle* h, const double total[2]);
 
 /* launch accounting for the bench (`gpu_launches`) and algorithmic bytes per gradient */
 int64_t b200glm_launch_count(const b200glm_handle* h);
 int64_t b200glm_bytes_per_gradient(const b200glm_handle* h);
-/* milliseconds of the last `n` main-kernel launches of a slot (CUDA events on its stream) */
+/* Per-phase time stamps of a slot's gradient launches (measurement only; narrow kernel + the shared tail).
+ * enable(on=1) allocates the buffer, from then on every launch of the slot overwrites it; read copies the
+ * stamps of the LAST launch: rows = grid + 1 rows of 16 words, word k = %globaltimer in ns (comparable across
+ * the SMs and GPUs of one box), word 8 + k = clock64 of that SM.  Rows [0, grid) are the CTAs: 0 entry,
+ * 1 previous launch complete (griddepcontrol.wait over), 2 theta staged, 3 first panel landed, 4 last panel
+ * consumed by every warp, 5 partial row written + ticket taken.  Row `grid` is the last CTA's tail: 0 ticket
+ * won (word 7 = its CTA id), 1 sum of the grid's partial rows done, 2 peers' partials received and summed,
+ * 3 model epilogue / leapfrog tail written.  read(out = NULL) only returns the row count. */
+int b200glm_timeline_enable(b200glm_handle* h, int32_t slot, int32_t on);
+int b200glm_timeline_read(b200glm_handle* h, int32_t slot, uint64_t* out, int32_t* rows);
 const char* b200glm_last_error(const b200glm_handle* h);
 const char* b200glm_version(void);
+/* B200GLM_ABI_VERSION the library was built with; bindings refuse to run on a mismatch */
+int32_t b200glm_abi_version(void);
 
 #ifdef __cplusplus
 }

@@ -6,6 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libb200glm.so")
 
 OK, DOMAIN, INVALID, CUDA = 0, 1, 2, 3
+ABI_VERSION = 3          # B200GLM_ABI_VERSION of include/b200glm.h this binding (Desc layout, signatures) was written for
 FAMILY = {"bernoulli_logit": 0, "poisson_log": 1, "normal_id": 2, "binomial_logit": 3, "neg_binomial_2_log": 4}
 
 # every symbol include/b200glm.h declares
@@ -16,7 +17,8 @@ SYMBOLS = [
     "b200glm_batch_reserve", "b200glm_log_prob_grad_batched", "b200glm_set_state_batched",
     "b200glm_leapfrog_batched", "b200glm_leapfrog_batched_async", "b200glm_batch_sync", "b200glm_batch_stream",
     "b200glm_peer_export", "b200glm_peer_connect", "b200glm_lgamma_sum_local", "b200glm_set_lgamma_sum_total",
-    "b200glm_glm_lpmf",
+    "b200glm_glm_lpmf", "b200glm_shard_constants_local", "b200glm_set_shard_constants_total",
+    "b200glm_timeline_enable", "b200glm_timeline_read", "b200glm_abi_version",
     "b200glm_launch_count", "b200glm_bytes_per_gradient", "b200glm_last_error", "b200glm_version",
 ]
 
@@ -47,6 +49,14 @@ def lib():
                 f"{LIB_PATH} is missing: build it with `python -m stan_b200.build` "
                 "(there is no CPU fallback for the GLM hot path)")
         L = C.CDLL(LIB_PATH)
+        try:
+            L.b200glm_abi_version.restype = C.c_int32
+            abi = L.b200glm_abi_version()
+        except AttributeError:
+            abi = None
+        if abi != ABI_VERSION:
+            raise RuntimeError(f"{LIB_PATH} was built for ABI {abi}, this binding needs {ABI_VERSION}: "
+                               "rebuild with `python -m stan_b200.build`")
         dp = C.POINTER(C.c_double)
         L.b200glm_create.argtypes = [C.POINTER(Desc), C.POINTER(C.c_void_p)]
         L.b200glm_destroy.argtypes = [C.c_void_p]
@@ -81,6 +91,10 @@ def lib():
         L.b200glm_set_lgamma_sum_total.argtypes = [C.c_void_p, C.c_double]
         L.b200glm_glm_lpmf.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, dp, dp, C.c_double,
                                        dp, dp, dp, dp]
+        L.b200glm_shard_constants_local.argtypes = [C.c_void_p, dp]
+        L.b200glm_set_shard_constants_total.argtypes = [C.c_void_p, dp]
+        L.b200glm_timeline_enable.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.b200glm_timeline_read.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64), ip]
         L.b200glm_launch_count.argtypes = [C.c_void_p]
         L.b200glm_launch_count.restype = C.c_int64
         L.b200glm_bytes_per_gradient.argtypes = [C.c_void_p]
@@ -94,8 +108,8 @@ def lib():
 
 def connect_peers_torch(handle, world, dist, dev):
     """Wire the peer mailboxes of a row-sharded handle (b200glm_handle*) using torch.distributed as the
-    out-of-band channel: all-gather the 64-byte IPC handles (rank order) and the per-shard poisson
-    constant.  torch.distributed is plumbing here; the exchange itself happens inside the gradient launch."""
+    out-of-band channel: all-gather the 64-byte IPC handles (rank order) and sum the per-shard create-time
+    constants (propto=false constant, data-check flag).  torch.distributed is plumbing here; the exchange itself happens inside the gradient launch."""
     import torch
     L = lib()
 
@@ -110,7 +124,10 @@ def connect_peers_torch(handle, world, dist, dev):
     dist.all_gather(allh, mine)
     raw = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
     check(L.b200glm_peer_connect(handle, C.create_string_buffer(raw, len(raw)), world))
-    lg = torch.tensor([L.b200glm_lgamma_sum_local(handle)], dtype=torch.float64, device=dev)
+    loc = (C.c_double * 2)()
+    check(L.b200glm_shard_constants_local(handle, loc))
+    lg = torch.tensor([loc[0], loc[1]], dtype=torch.float64, device=dev)
     dist.all_reduce(lg)
-    check(L.b200glm_set_lgamma_sum_total(handle, float(lg.item())))
+    tot = (C.c_double * 2)(float(lg[0].item()), float(lg[1].item()))
+    check(L.b200glm_set_shard_constants_total(handle, tot))
     dist.barrier()

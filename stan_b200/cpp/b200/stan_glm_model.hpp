@@ -153,6 +153,9 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
     if (desc_.n_slots < 1)
       desc_.n_slots = 1;
     guards_.reset(new slot_guard[desc_.n_slots]);
+    if (b200glm_abi_version() != B200GLM_ABI_VERSION)   // a stale libb200glm.so would misread b200glm_desc
+      throw std::runtime_error("b200glm: library ABI " + std::to_string(b200glm_abi_version()) + " != header ABI "
+                               + std::to_string(B200GLM_ABI_VERSION));
     const int rc = b200glm_create(&desc_, &h_);
     if (rc != B200GLM_OK) {
       std::string msg = h_ ? b200glm_last_error(h_) : "b200glm_create failed";
@@ -166,6 +169,7 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
     desc_.y_int = nullptr;
     desc_.y_real = nullptr;
     desc_.group = nullptr;
+    desc_.trials = nullptr;
     registry(+1, uid_);
   }
   glm_model(const glm_model&) = delete;

@@ -76,6 +76,7 @@ struct Slot {
   double* theta_used = nullptr;  // P
   double* h_pinned = nullptr;    // pinned staging: max(3P+1, P+2) * 2
   unsigned long long peer_seq = 0;  // evaluations exchanged through the peer mailboxes so far
+  unsigned long long* tl = nullptr; // (grid + 1) x 16 time stamps of the last launch (b200glm_timeline_enable)
   std::mutex mu;
 };
 
@@ -113,12 +114,13 @@ struct b200glm_handle {
   int panel_rows = PANEL_ROWS, Cpad = 0, Kc = 0, J = 0, spw = 0, spc = 0;
   double lgamma_sum = 0.0;  // local shard
   double lgamma_sum_total = 0.0;
-  bool bad_y = false;
+  bool bad_y = false;        // any shard holds an out-of-range y (after b200glm_comm_init / set_shard_constants_total)
+  bool bad_y_local = false;  // this shard does
   bool pdl = true;          // B200GLM_NO_PDL=1 in the environment turns programmatic dependent launch off (A/B runs)
   std::vector<Slot*> slots;
   Batch* batch = nullptr;
   ncclComm_t comm = nullptr;
-  // peer mailboxes (CUDA IPC): [n_slots][2][world][peer_stride] doubles on every rank
+  // peer mailboxes (CUDA IPC): [n_slots][PEER_BUFS][world][peer_stride] doubles on every rank
   double* mbox = nullptr;
   double* peer_mbox[MAX_PEERS] = {nullptr};
   int peer_stride = 0;
@@ -250,7 +252,7 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
     p.peer.seq = s->peer_seq;
     p.peer.timeout_ns = 20ull * 1000000000ull;
     for (int r = 0; r < h->d.world; ++r)
-      p.peer.mbox[r] = h->peer_mbox[r] + (size_t)slot_idx * 2 * h->d.world * h->peer_stride;
+      p.peer.mbox[r] = h->peer_mbox[r] + (size_t)slot_idx * PEER_BUFS * h->d.world * h->peer_stride;
   }
   p.stage_a_in_smem = h->stage_a;
   p.theta_in = s->theta;
@@ -265,6 +267,7 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
   p.lik = s->lik;
   p.result = s->result;
   p.theta_used = s->theta_used;
+  p.tl = s->tl;
   ModelConst& mc = p.mc;
   mc.family = h->d.family;
   mc.K = h->d.K;
@@ -395,7 +398,10 @@ int eval_host(b200glm_handle* h, int slot, const double* theta, int propto, int 
 
 extern "C" {
 
-const char* b200glm_version(void) { return "b200glm 0.1 (sm_100a, abi 1)"; }
+#define B200GLM_STR2(x) #x
+#define B200GLM_STR(x) B200GLM_STR2(x)
+const char* b200glm_version(void) { return "b200glm 0.2 (sm_100a, abi " B200GLM_STR(B200GLM_ABI_VERSION) ")"; }
+int32_t b200glm_abi_version(void) { return B200GLM_ABI_VERSION; }
 
 int32_t b200glm_num_params(const b200glm_handle* h) { return h ? h->P : -1; }
 
@@ -436,6 +442,7 @@ void b200glm_destroy(b200glm_handle* h) {
     cudaFree(s->lik);
     cudaFree(s->result);
     cudaFree(s->theta_used);
+    cudaFree(s->tl);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -466,11 +473,28 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   b200glm_handle* h = new b200glm_handle();
   h->d = *desc;
   auto fail = [&](int code, const std::string& msg) {
-    // keep the handle alive so the caller can read last_error, as documented
+    // keep the handle alive so the caller can read last_error (and must b200glm_destroy it), as documented;
+    // whatever the handle owns by now is freed there, the upload temporaries by `tmp` below
     h->set_error(msg);
     *out = h;
     return code;
   };
+#define CREATE_TRY(expr)                                                                         \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return fail(B200GLM_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+  // device temporaries of the upload: freed on every exit path
+  struct DevTmp {
+    std::vector<void**> v;
+    cudaStream_t* st = nullptr;
+    void track(void** p) { v.push_back(p); }
+    ~DevTmp() {
+      for (void** p : v)
+        if (*p) cudaFree(*p);
+      if (st && *st) cudaStreamDestroy(*st);
+    }
+  } tmp;
   const b200glm_desc& d = h->d;
   if (d.family < 0 || d.family > 4) return fail(B200GLM_INVALID, "unknown family");
   if (d.N > 0 && d.family == B200GLM_BINOMIAL_LOGIT && !d.trials) return fail(B200GLM_INVALID, "trials is null");
@@ -494,9 +518,9 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(B200GLM_CUDA, "no CUDA device available (this backend has no CPU fallback)");
   if (d.device < 0 || d.device >= ndev) return fail(B200GLM_INVALID, "device ordinal out of range");
-  CUDA_TRY(h, cudaSetDevice(d.device));
+  CREATE_TRY(cudaSetDevice(d.device));
   cudaDeviceProp prop;
-  CUDA_TRY(h, cudaGetDeviceProperties(&prop, d.device));
+  CREATE_TRY(cudaGetDeviceProperties(&prop, d.device));
   if (prop.major < 10) return fail(B200GLM_CUDA, "device is not sm_100 or newer");
 
   // launch geometry
@@ -540,13 +564,14 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     h->smem_bytes = fixed + (size_t)T * (slot_bytes + 16);
   }
   kernel_fn fn = handle_kernel(h);
-  CUDA_TRY(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CREATE_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
 
   // ---- data upload + re-layout ----
-  cudaStream_t st;
-  CUDA_TRY(h, cudaStreamCreate(&st));
+  cudaStream_t st = nullptr;
+  tmp.st = &st;
+  CREATE_TRY(cudaStreamCreate(&st));
   const size_t panel_doubles = (size_t)h->n_panels * h->Cpad * h->panel_rows;
-  if (panel_doubles) CUDA_TRY(h, cudaMalloc(&h->panels, panel_doubles * 8));
+  if (panel_doubles) CREATE_TRY(cudaMalloc(&h->panels, panel_doubles * 8));
 
   // y / group on host and device
   std::vector<int32_t> h_group;
@@ -556,6 +581,9 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   int32_t* d_trials = nullptr;
   long long* d_perm = nullptr;
   bool own_y = false, own_group = false;
+  void *t_y = nullptr, *t_yr = nullptr, *t_trials = nullptr, *t_group = nullptr, *t_perm = nullptr, *t_X = nullptr,
+       *t_stats = nullptr;   // what `tmp` frees: the OWNED temporaries only (never the caller's device pointers)
+  for (void** q : {&t_y, &t_yr, &t_trials, &t_group, &t_perm, &t_X, &t_stats}) tmp.track(q);
   if (d.N > 0) {
     if (d.data_on_device) {
       d_y = const_cast<int32_t*>(d.y_int);
@@ -564,20 +592,24 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
       d_trials = const_cast<int32_t*>(d.trials);
     } else {
       if (d.family == B200GLM_NORMAL_ID) {
-        CUDA_TRY(h, cudaMalloc(&d_yr, sizeof(double) * d.N));
-        CUDA_TRY(h, cudaMemcpy(d_yr, d.y_real, sizeof(double) * d.N, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMalloc(&d_yr, sizeof(double) * d.N));
+        t_yr = d_yr;
+        CREATE_TRY(cudaMemcpy(d_yr, d.y_real, sizeof(double) * d.N, cudaMemcpyHostToDevice));
       } else {
-        CUDA_TRY(h, cudaMalloc(&d_y, sizeof(int32_t) * d.N));
-        CUDA_TRY(h, cudaMemcpy(d_y, d.y_int, sizeof(int32_t) * d.N, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMalloc(&d_y, sizeof(int32_t) * d.N));
+        t_y = d_y;
+        CREATE_TRY(cudaMemcpy(d_y, d.y_int, sizeof(int32_t) * d.N, cudaMemcpyHostToDevice));
         if (d.family == B200GLM_BINOMIAL_LOGIT) {
-          CUDA_TRY(h, cudaMalloc(&d_trials, sizeof(int32_t) * d.N));
-          CUDA_TRY(h, cudaMemcpy(d_trials, d.trials, sizeof(int32_t) * d.N, cudaMemcpyHostToDevice));
+          CREATE_TRY(cudaMalloc(&d_trials, sizeof(int32_t) * d.N));
+          t_trials = d_trials;
+          CREATE_TRY(cudaMemcpy(d_trials, d.trials, sizeof(int32_t) * d.N, cudaMemcpyHostToDevice));
         }
       }
       own_y = true;
       if (d.G > 0) {
-        CUDA_TRY(h, cudaMalloc(&d_group, sizeof(int32_t) * d.N));
-        CUDA_TRY(h, cudaMemcpy(d_group, d.group, sizeof(int32_t) * d.N, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMalloc(&d_group, sizeof(int32_t) * d.N));
+        t_group = d_group;
+        CREATE_TRY(cudaMemcpy(d_group, d.group, sizeof(int32_t) * d.N, cudaMemcpyHostToDevice));
         own_group = true;
       }
     }
@@ -586,18 +618,20 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   if (d.N > 0 && d.family != B200GLM_NORMAL_ID) {
     const int nb = 296;
     double* d_stats;
-    CUDA_TRY(h, cudaMalloc(&d_stats, sizeof(double) * 2 * nb));
+    CREATE_TRY(cudaMalloc(&d_stats, sizeof(double) * 2 * nb));
+    t_stats = d_stats;
     y_stats_kernel<<<nb, 256, 0, st>>>(d_y, d_trials, d.N, d.family, d_stats);
     std::vector<double> hs(2 * nb);
-    CUDA_TRY(h, cudaMemcpyAsync(hs.data(), d_stats, sizeof(double) * 2 * nb, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(h, cudaStreamSynchronize(st));
+    CREATE_TRY(cudaMemcpyAsync(hs.data(), d_stats, sizeof(double) * 2 * nb, cudaMemcpyDeviceToHost, st));
+    CREATE_TRY(cudaStreamSynchronize(st));
     cudaFree(d_stats);
+    t_stats = nullptr;
     double bad = 0, lg = 0;
     for (int i = 0; i < nb; ++i) {
       bad += hs[2 * i];
       lg += hs[2 * i + 1];
     }
-    h->bad_y = bad > 0;
+    h->bad_y = h->bad_y_local = bad > 0;
     h->lgamma_sum = lg;
     h->lgamma_sum_total = lg;
   }
@@ -606,18 +640,14 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     h_group.resize(d.N);
     if (d.N > 0) {
       if (d.data_on_device)
-        CUDA_TRY(h, cudaMemcpy(h_group.data(), d_group, sizeof(int32_t) * d.N, cudaMemcpyDeviceToHost));
+        CREATE_TRY(cudaMemcpy(h_group.data(), d_group, sizeof(int32_t) * d.N, cudaMemcpyDeviceToHost));
       else
         std::memcpy(h_group.data(), d.group, sizeof(int32_t) * d.N);
     }
     std::vector<long long> seg(d.G + 1, 0);
     for (long long i = 0; i < d.N; ++i) {
       const int g = h_group[i];
-      if (g < 1 || g > d.G) {
-        if (own_y) { cudaFree(d_y); cudaFree(d_yr); cudaFree(d_trials); }
-        if (own_group) cudaFree(d_group);
-        return fail(B200GLM_INVALID, "group index out of range [1, G]");
-      }
+      if (g < 1 || g > d.G) return fail(B200GLM_INVALID, "group index out of range [1, G]");
       seg[g]++;
     }
     for (int g = 0; g < d.G; ++g) seg[g + 1] += seg[g];
@@ -626,11 +656,12 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
       std::vector<long long> cursor(seg.begin(), seg.end() - 1);
       for (long long i = 0; i < d.N; ++i) perm[cursor[h_group[i] - 1]++] = i;
     }
-    CUDA_TRY(h, cudaMalloc(&h->seg_ptr, sizeof(long long) * (d.G + 1)));
-    CUDA_TRY(h, cudaMemcpy(h->seg_ptr, seg.data(), sizeof(long long) * (d.G + 1), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMalloc(&h->seg_ptr, sizeof(long long) * (d.G + 1)));
+    CREATE_TRY(cudaMemcpy(h->seg_ptr, seg.data(), sizeof(long long) * (d.G + 1), cudaMemcpyHostToDevice));
     if (d.N > 0) {
-      CUDA_TRY(h, cudaMalloc(&d_perm, sizeof(long long) * d.N));
-      CUDA_TRY(h, cudaMemcpy(d_perm, perm.data(), sizeof(long long) * d.N, cudaMemcpyHostToDevice));
+      CREATE_TRY(cudaMalloc(&d_perm, sizeof(long long) * d.N));
+      t_perm = d_perm;
+      CREATE_TRY(cudaMemcpy(d_perm, perm.data(), sizeof(long long) * d.N, cudaMemcpyHostToDevice));
     }
   }
   // X: device-resident or staged from the host in row chunks
@@ -639,68 +670,71 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     if (d.data_on_device || d.K == 0) {
       relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(d.X, d.ldx, 0, d_y, d_yr, d_group, d_trials, d_perm, 0, d.N,
                                                                     d.N, d.K, h->C, 0, h->Cpad, h->panels, PR, h->Cpad, SWZ);
-      CUDA_TRY(h, cudaGetLastError());
+      CREATE_TRY(cudaGetLastError());
     } else if (d_perm) {
       // permuted gather needs all of X on the device at once
       double* dX;
-      CUDA_TRY(h, cudaMalloc(&dX, sizeof(double) * (size_t)d.N * d.K));
-      CUDA_TRY(h, cudaMemcpy2D(dX, sizeof(double) * d.N, d.X, sizeof(double) * d.ldx, sizeof(double) * d.N, d.K,
+      CREATE_TRY(cudaMalloc(&dX, sizeof(double) * (size_t)d.N * d.K));
+      t_X = dX;
+      CREATE_TRY(cudaMemcpy2D(dX, sizeof(double) * d.N, d.X, sizeof(double) * d.ldx, sizeof(double) * d.N, d.K,
                                cudaMemcpyHostToDevice));
       relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(dX, d.N, 0, d_y, d_yr, d_group, d_trials, d_perm, 0, d.N,
                                                                     d.N, d.K, h->C, 0, h->Cpad, h->panels, PR, h->Cpad, SWZ);
-      CUDA_TRY(h, cudaStreamSynchronize(st));
+      CREATE_TRY(cudaStreamSynchronize(st));
       cudaFree(dX);
+      t_X = nullptr;
     } else {
       const long long chunk_rows = std::max<long long>(32, ((long long)(256u << 20) / (8LL * std::max(d.K, 1))) & ~31LL);
       double* dX;
-      CUDA_TRY(h, cudaMalloc(&dX, sizeof(double) * (size_t)std::min(chunk_rows, (long long)d.N) * d.K));
+      CREATE_TRY(cudaMalloc(&dX, sizeof(double) * (size_t)std::min(chunk_rows, (long long)d.N) * d.K));
+      t_X = dX;
       for (long long r0 = 0; r0 < d.N; r0 += chunk_rows) {
         const long long nr = std::min(chunk_rows, (long long)d.N - r0);
-        CUDA_TRY(h, cudaMemcpy2DAsync(dX, sizeof(double) * nr, d.X + r0, sizeof(double) * d.ldx, sizeof(double) * nr,
+        CREATE_TRY(cudaMemcpy2DAsync(dX, sizeof(double) * nr, d.X + r0, sizeof(double) * d.ldx, sizeof(double) * nr,
                                       d.K, cudaMemcpyHostToDevice, st));
         relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(dX, nr, r0, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                                       r0, nr, d.N, d.K, h->C, 0, d.K, h->panels, PR, h->Cpad, SWZ);
-        CUDA_TRY(h, cudaStreamSynchronize(st));
+        CREATE_TRY(cudaStreamSynchronize(st));
       }
       cudaFree(dX);
+      t_X = nullptr;
       // aux columns (y, group) in one more pass
       relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(nullptr, 0, 0, d_y, d_yr, d_group, d_trials, nullptr, 0, d.N,
                                                                     d.N, d.K, h->C, d.K, h->Cpad, h->panels, PR, h->Cpad, SWZ);
     }
-    CUDA_TRY(h, cudaGetLastError());
-    CUDA_TRY(h, cudaStreamSynchronize(st));
+    CREATE_TRY(cudaGetLastError());
+    CREATE_TRY(cudaStreamSynchronize(st));
   }
-  if (own_y) { cudaFree(d_y); cudaFree(d_yr); cudaFree(d_trials); }
-  if (own_group) cudaFree(d_group);
-  cudaFree(d_perm);
-  cudaStreamDestroy(st);
+  (void)own_y;
+  (void)own_group;   // the upload temporaries and the stream are released by `tmp`
 
   // ---- slots ----
   const int pstride = partial_stride(d.K);
   for (int i = 0; i < h->d.n_slots; ++i) {
     Slot* s = new Slot();
     h->slots.push_back(s);
-    CUDA_TRY(h, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    CUDA_TRY(h, cudaMalloc(&s->theta, sizeof(double) * std::max(P, 1)));
+    CREATE_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaMalloc(&s->theta, sizeof(double) * std::max(P, 1)));
     for (int b = 0; b < 2; ++b) {
-      CUDA_TRY(h, cudaMalloc(&s->state[b], sizeof(double) * (3 * P + 1)));
-      CUDA_TRY(h, cudaMemset(s->state[b], 0, sizeof(double) * (3 * P + 1)));
+      CREATE_TRY(cudaMalloc(&s->state[b], sizeof(double) * (3 * P + 1)));
+      CREATE_TRY(cudaMemset(s->state[b], 0, sizeof(double) * (3 * P + 1)));
     }
-    CUDA_TRY(h, cudaMalloc(&s->inv_metric, sizeof(double) * std::max(P, 1)));
+    CREATE_TRY(cudaMalloc(&s->inv_metric, sizeof(double) * std::max(P, 1)));
     std::vector<double> ones(std::max(P, 1), 1.0);
-    CUDA_TRY(h, cudaMemcpy(s->inv_metric, ones.data(), sizeof(double) * P, cudaMemcpyHostToDevice));
-    CUDA_TRY(h, cudaMalloc(&s->partials, sizeof(double) * (size_t)h->grid * pstride));
-    CUDA_TRY(h, cudaMalloc(&s->ticket, sizeof(unsigned int)));
-    CUDA_TRY(h, cudaMemset(s->ticket, 0, sizeof(unsigned int)));
-    if (d.G > 0 && h->n_panels > 0) CUDA_TRY(h, cudaMalloc(&s->r_out, sizeof(double) * h->n_panels * h->panel_rows));
-    CUDA_TRY(h, cudaMalloc(&s->lik, sizeof(double) * (P + 2)));
-    CUDA_TRY(h, cudaMemset(s->lik, 0, sizeof(double) * (P + 2)));
-    CUDA_TRY(h, cudaMalloc(&s->result, sizeof(double) * (P + 2)));
-    CUDA_TRY(h, cudaMalloc(&s->theta_used, sizeof(double) * std::max(P, 1)));
-    CUDA_TRY(h, cudaMallocHost(&s->h_pinned, sizeof(double) * (2 * (3 * P + 1) + P + 2)));
+    CREATE_TRY(cudaMemcpy(s->inv_metric, ones.data(), sizeof(double) * P, cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMalloc(&s->partials, sizeof(double) * (size_t)h->grid * pstride));
+    CREATE_TRY(cudaMalloc(&s->ticket, sizeof(unsigned int)));
+    CREATE_TRY(cudaMemset(s->ticket, 0, sizeof(unsigned int)));
+    if (d.G > 0 && h->n_panels > 0) CREATE_TRY(cudaMalloc(&s->r_out, sizeof(double) * h->n_panels * h->panel_rows));
+    CREATE_TRY(cudaMalloc(&s->lik, sizeof(double) * (P + 2)));
+    CREATE_TRY(cudaMemset(s->lik, 0, sizeof(double) * (P + 2)));
+    CREATE_TRY(cudaMalloc(&s->result, sizeof(double) * (P + 2)));
+    CREATE_TRY(cudaMalloc(&s->theta_used, sizeof(double) * std::max(P, 1)));
+    CREATE_TRY(cudaMallocHost(&s->h_pinned, sizeof(double) * (2 * (3 * P + 1) + P + 2)));
   }
   *out = h;
   return B200GLM_OK;
+#undef CREATE_TRY
 }
 
 int b200glm_log_prob_grad(b200glm_handle* h, int32_t slot, const double* theta, int32_t propto, int32_t jacobian,
@@ -1168,6 +1202,39 @@ int b200glm_batch_sync(b200glm_handle* h) {
 
 void* b200glm_batch_stream(b200glm_handle* h) { return (h && h->batch) ? (void*)h->batch->stream : nullptr; }
 
+int b200glm_timeline_enable(b200glm_handle* h, int32_t slot, int32_t on) {
+  int rc = validate_slot(h, slot);
+  if (rc) return rc;
+  Slot* s = h->slots[slot];
+  std::lock_guard<std::mutex> lk(s->mu);
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  CUDA_TRY(h, cudaStreamSynchronize(s->stream));
+  if (on && !s->tl) {
+    CUDA_TRY(h, cudaMalloc(&s->tl, sizeof(unsigned long long) * 16 * (h->grid + 1)));
+    CUDA_TRY(h, cudaMemset(s->tl, 0, sizeof(unsigned long long) * 16 * (h->grid + 1)));
+  } else if (!on && s->tl) {
+    cudaFree(s->tl);
+    s->tl = nullptr;
+  }
+  return B200GLM_OK;
+}
+
+int b200glm_timeline_read(b200glm_handle* h, int32_t slot, uint64_t* out, int32_t* rows) {
+  int rc = validate_slot(h, slot);
+  if (rc) return rc;
+  Slot* s = h->slots[slot];
+  if (rows) *rows = h->grid + 1;
+  if (!out) return B200GLM_OK;
+  if (!s->tl) {
+    h->set_error("b200glm_timeline_enable was not called for this slot");
+    return B200GLM_INVALID;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  CUDA_TRY(h, cudaStreamSynchronize(s->stream));
+  CUDA_TRY(h, cudaMemcpy(out, s->tl, sizeof(unsigned long long) * 16 * (h->grid + 1), cudaMemcpyDeviceToHost));
+  return B200GLM_OK;
+}
+
 }  // extern "C"
 
 extern "C" {
@@ -1180,10 +1247,10 @@ int b200glm_peer_export(b200glm_handle* h, void* ipc_handle_64) {
   }
   CUDA_TRY(h, cudaSetDevice(h->d.device));
   if (!h->mbox) {
-    h->peer_stride = (h->P + 2 + 1 + 1) & ~1;  // payload + sequence word, even
-    const size_t n = (size_t)h->slots.size() * 2 * h->d.world * h->peer_stride;
+    h->peer_stride = (h->P + 2 + 15) & ~15;  // payload, rounded up to whole 128-byte lines
+    const size_t n = (size_t)h->slots.size() * PEER_BUFS * h->d.world * h->peer_stride;
     CUDA_TRY(h, cudaMalloc(&h->mbox, sizeof(double) * n));
-    CUDA_TRY(h, cudaMemset(h->mbox, 0, sizeof(double) * n));
+    CUDA_TRY(h, cudaMemset(h->mbox, 0xFF, sizeof(double) * n));   // every word = PEER_EMPTY
     CUDA_TRY(h, cudaDeviceSynchronize());
   }
   cudaIpcMemHandle_t ih;
@@ -1225,6 +1292,20 @@ int b200glm_set_lgamma_sum_total(b200glm_handle* h, double total) {
 
 double b200glm_lgamma_sum_local(const b200glm_handle* h) { return h ? h->lgamma_sum : 0.0; }
 
+int b200glm_shard_constants_local(const b200glm_handle* h, double out[2]) {
+  if (!h || !out) return B200GLM_INVALID;
+  out[0] = h->lgamma_sum;
+  out[1] = h->bad_y_local ? 1.0 : 0.0;
+  return B200GLM_OK;
+}
+
+int b200glm_set_shard_constants_total(b200glm_handle* h, const double total[2]) {
+  if (!h || !total) return B200GLM_INVALID;
+  h->lgamma_sum_total = total[0];
+  h->bad_y = total[1] > 0.0;
+  return B200GLM_OK;
+}
+
 int b200glm_comm_unique_id(void* unique_id_128) {
   if (!unique_id_128 || !nccl().ok) return B200GLM_CUDA;
   ncclUniqueId id;
@@ -1251,19 +1332,25 @@ int b200glm_comm_init(b200glm_handle* h, const void* unique_id_128, int32_t rank
     h->set_error(std::string("ncclCommInitRank: ") + (nccl().GetErrorString ? nccl().GetErrorString(r) : "?"));
     return B200GLM_CUDA;
   }
-  // the propto=false poisson constant is a sum over all shards
-  if (h->d.family == B200GLM_POISSON_LOG) {
+  // per-shard create-time constants are sums over all shards: the propto=false constant of poisson_log /
+  // binomial_logit / neg_binomial_2_log (0 for the other families) and the count of out-of-range y, so that
+  // every rank reports the same data-check status
+  {
+    double hv[2] = {h->lgamma_sum, h->bad_y_local ? 1.0 : 0.0};
     double* dv;
-    CUDA_TRY(h, cudaMalloc(&dv, sizeof(double)));
-    CUDA_TRY(h, cudaMemcpy(dv, &h->lgamma_sum, sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMalloc(&dv, sizeof(hv)));
+    CUDA_TRY(h, cudaMemcpy(dv, hv, sizeof(hv), cudaMemcpyHostToDevice));
     cudaStream_t st = h->slots[0]->stream;
-    if (nccl().AllReduce(dv, dv, 1, ncclFloat64, ncclSum, h->comm, st) != 0) {
-      h->set_error("ncclAllReduce(lgamma_sum) failed");
+    if (nccl().AllReduce(dv, dv, 2, ncclFloat64, ncclSum, h->comm, st) != 0) {
+      cudaFree(dv);
+      h->set_error("ncclAllReduce(shard constants) failed");
       return B200GLM_CUDA;
     }
-    CUDA_TRY(h, cudaMemcpyAsync(&h->lgamma_sum_total, dv, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(hv, dv, sizeof(hv), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
     cudaFree(dv);
+    h->lgamma_sum_total = hv[0];
+    h->bad_y = hv[1] > 0.0;
   }
   return B200GLM_OK;
 }

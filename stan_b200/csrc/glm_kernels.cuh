@@ -110,18 +110,25 @@ __device__ __forceinline__ void named_barrier_sync(int id, int count) {
 
 // ------------------------------------------------------------------------------------------
 // All-reduce (sum) of the P+2 likelihood partials across the row shards, INSIDE the launch that
-// produced them: one CTA per rank pushes its partial into every rank's mailbox with peer stores,
-// releases a per-sender sequence flag, waits for the world's flags in its own mailbox and adds the
-// entries in rank order -- the same order on every rank, so theta stays bitwise replicated.
+// produced them.  One CTA per rank pushes its partial into every peer's mailbox with plain 8-byte peer
+// stores and reads the world's entries from its own mailbox; the sum runs in rank order -- the same
+// order on every rank, so theta stays bitwise replicated.
+// Protocol (Lamport-style, no fence, no flag): every mailbox word is self-validating -- it holds
+// PEER_EMPTY until the sender's value lands, and an aligned 8-byte store is indivisible -- so the receiver
+// simply polls the words it needs.  One NVLink one-way latency per exchange; the first version (payload
+// stores, __threadfence_system, st.release flag, ld.acquire spin) paid two round trips.
+// Three buffers rotate by evaluation number n: n % 3 is read now, (n + 1) % 3 may already be receiving the
+// next evaluation from a faster peer, (n + 2) % 3 -- last read at n - 1, next written at n + 2, which no
+// peer can start before it has this rank's n + 1 contribution (a later LAUNCH) -- is re-armed here.
 // Replaces ncclAllReduce + a separate epilogue launch (two launches and ~20 us per gradient).
 // Called by every thread of that CTA after p.lik is complete; returns false on timeout.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* ptr, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* ptr, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* ptr) {
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* ptr) {
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory");
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -129,42 +136,64 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// Per-phase time stamps of a launch (b200glm_timeline_enable): row `row` of [grid + 1][16] words,
+// word k = %globaltimer (ns, comparable across SMs and GPUs of a box), word 8 + k = clock64 of the SM.
+__device__ __forceinline__ void tl_stamp(const KernelParams& p, int row, int k) {
+  if (p.tl) {
+    p.tl[(size_t)row * 16 + k] = globaltimer_ns();
+    p.tl[(size_t)row * 16 + 8 + k] = (unsigned long long)clock64();
+  }
+}
 __device__ bool peer_allreduce_lik(const KernelParams& p, int* sh_ok) {
   const PeerParams& pe = p.peer;
   const int n = p.P + 2, tid = threadIdx.x, nt = blockDim.x;
-  const int buf = (int)(pe.seq & 1ull);
+  const int buf = (int)(pe.seq % PEER_BUFS), buf_rearm = (int)((pe.seq + 2) % PEER_BUFS);
   const size_t my_off = ((size_t)buf * pe.world + pe.rank) * pe.stride;
-  for (int r = 0; r < pe.world; ++r) {
-    double* dst = pe.mbox[r] + my_off;
-    for (int j = tid; j < n; j += nt) dst[j] = __ldcg(p.lik + j);
-  }
-  __threadfence_system();
   if (tid == 0) *sh_ok = 1;
   __syncthreads();
-  if (tid < pe.world)
-    st_release_sys_u64(reinterpret_cast<unsigned long long*>(pe.mbox[tid] + my_off + pe.stride - 1), pe.seq);
-  const double* mine = pe.mbox[pe.rank] + (size_t)buf * pe.world * pe.stride;
-  if (tid < pe.world) {
-    const unsigned long long* flag =
-        reinterpret_cast<const unsigned long long*>(mine + (size_t)tid * pe.stride + pe.stride - 1);
-    const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_sys_u64(flag) != pe.seq) {
-      if (globaltimer_ns() - t0 > pe.timeout_ns) {
+  unsigned long long* mine = reinterpret_cast<unsigned long long*>(pe.mbox[pe.rank]);
+  auto own_word = [&](int j) {
+    unsigned long long own = (unsigned long long)__double_as_longlong(__ldcg(p.lik + j));
+    return own == PEER_EMPTY_BITS ? 0x7FF8000000000000ull : own;
+  };
+  for (int j = tid; j < n; j += nt) {            // every send is in flight before the first poll
+    const unsigned long long own = own_word(j);
+#pragma unroll
+    for (int r = 0; r < MAX_PEERS; ++r)
+      if (r < pe.world && r != pe.rank)
+        st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(pe.mbox[r]) + my_off + j, own);
+#pragma unroll
+    for (int r = 0; r < MAX_PEERS; ++r)          // re-arm the buffer of evaluation n + 2
+      if (r < pe.world) mine[((size_t)buf_rearm * pe.world + r) * pe.stride + j] = PEER_EMPTY_BITS;
+  }
+  const unsigned long long t0 = globaltimer_ns();
+  for (int j = tid; j < n; j += nt) {
+    const unsigned long long own = own_word(j);
+    const unsigned long long* src = mine + (size_t)buf * pe.world * pe.stride + j;
+    unsigned long long w[MAX_PEERS];
+    bool all;
+    do {
+      all = true;
+#pragma unroll
+      for (int r = 0; r < MAX_PEERS; ++r)
+        if (r < pe.world) {
+          w[r] = r == pe.rank ? own : ld_relaxed_sys_u64(src + (size_t)r * pe.stride);
+          all = all && (w[r] != PEER_EMPTY_BITS);
+        }
+      if (!all && globaltimer_ns() - t0 > pe.timeout_ns) {
         *sh_ok = 0;
         break;
       }
-    }
-  }
-  __syncthreads();
-  if (!*sh_ok) return false;
-  for (int j = tid; j < n; j += nt) {
+    } while (!all);
     double v = 0.0;
-    for (int r = 0; r < pe.world; ++r) v += __ldcg(mine + (size_t)r * pe.stride + j);
+#pragma unroll
+    for (int r = 0; r < MAX_PEERS; ++r)
+      if (r < pe.world) v += __longlong_as_double((long long)w[r]);
     p.lik[j] = v;
   }
   __threadfence();
   __syncthreads();
-  return true;
+  return *sh_ok != 0;
 }
 __device__ void peer_timeout_result(const KernelParams& p) {
   if (threadIdx.x == 0) {
@@ -192,7 +221,12 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
     *sh_is_last = (t == (unsigned int)(grid - 1));
   }
   __syncthreads();
+  if (tid == 0) tl_stamp(p, blockIdx.x, 5);      // partial written, ticket taken
   if (!*sh_is_last) return;
+  if (tid == 0) {
+    tl_stamp(p, grid, 0);                        // last CTA: ticket won
+    if (p.tl) p.tl[(size_t)grid * 16 + 7] = blockIdx.x;
+  }
 
   __threadfence();
   // Sum of the grid's partial rows, column by column, in a FIXED tree (bitwise reproducible): the rows are cut
@@ -236,11 +270,14 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
   if (G > 0 && tid < 2) p.lik[tid] = 0.0;
   __threadfence();
   __syncthreads();
+  if (tid == 0) tl_stamp(p, grid, 1);            // sum of the grid's partial rows done
   if (p.peer_in_main && !peer_allreduce_lik(p, sh_is_last)) {
     peer_timeout_result(p);
     return;
   }
+  if (tid == 0) tl_stamp(p, grid, 2);            // peers' partials received and summed
   if (p.fuse_finish) finish(p, sh_scratch);
+  if (tid == 0) tl_stamp(p, grid, 3);            // model epilogue / leapfrog tail written
 }
 
 // ------------------------------------------------------------------------------------------
@@ -270,6 +307,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
 
   pdl_launch_dependents();
   if (tid == 0) {
+    tl_stamp(p, blockIdx.x, 0);                  // CTA entry
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -281,6 +319,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
   // From here the TMA producer streams X (constant data) while the consumer warps wait for the previous launch
   // on this stream -- whose epilogue may still be running in one CTA -- before they read theta / the state.
   if (warp != NUM_CONSUMER_WARPS) pdl_grid_dependency_wait();
+  if (tid == 0) tl_stamp(p, blockIdx.x, 1);      // previous launch on the stream complete (PDL wait over)
 
   // ---- theta for this launch (leapfrog: begin_update_p + update_q, expl_leapfrog.hpp:16-26) ----
   auto theta_at = [&](int i) -> double {
@@ -318,6 +357,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
     }
     named_barrier_sync(1, NC);                 // sbeta / sa visible to every consumer warp
   }
+  if (tid == 0) tl_stamp(p, blockIdx.x, 2);      // theta staged
 
   const long long n_panels = p.n_panels;
   const int grid = gridDim.x;
@@ -368,6 +408,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
       const int s = (int)(n % S);
       const uint32_t parity = (uint32_t)((n / S) & 1);
       mbar_wait(&full_bar[s], parity);
+      if (n == 0 && tid == 0) tl_stamp(p, blockIdx.x, 3);   // first panel landed
       const double* tile = tiles + (size_t)s * tile_doubles;
 
       // ---- phase 1: eta for row `lane` ----
@@ -446,6 +487,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
     for (int j = lane; j < Kpad + 4; j += 32) red[warp * (Kpad + 4) + j] = 0.0;
   }
   __syncthreads();
+  if (tid == 0) tl_stamp(p, blockIdx.x, 4);      // every warp has consumed its last panel
 
   // ---- CTA partial -> global ----
   double* my_part = p.partials + (size_t)blockIdx.x * p.pstride;

@@ -39,9 +39,13 @@ struct ModelConst {
 };
 
 // Row-sharded operation without a separate collective launch: every rank owns a mailbox in its HBM,
-// mapped into every peer (CUDA IPC over NVLink / NVSwitch).  [2 parities][world][stride] doubles; the
-// last word of an entry is the sequence number of the evaluation it belongs to.
+// mapped into every peer (CUDA IPC over NVLink / NVSwitch).  [PEER_BUFS][world][stride] doubles.
 constexpr int MAX_PEERS = 8;
+constexpr int PEER_BUFS = 3;       // mailbox buffers rotated by evaluation number (see peer_allreduce_lik)
+// Every 8-byte word of a mailbox is self-validating: it holds PEER_EMPTY until the sender's value lands.
+// PEER_EMPTY is a NaN bit pattern no arithmetic produces; a payload that happens to carry it (a NaN handed in
+// by the caller) is sent as the canonical quiet NaN instead.
+#define PEER_EMPTY_BITS 0xFFFFFFFFFFFFFFFFull
 struct PeerParams {
   int enabled, world, rank, stride;
   unsigned long long seq;          // 1, 2, 3, ... identical on every rank for the same evaluation
@@ -74,6 +78,7 @@ struct KernelParams {
   double* lik;              // [P] likelihood gradient aligned with theta, [P] lp-sum, [P+1] spare
   double* result;           // [lp, grad(P), status]
   double* theta_used;       // P doubles: the theta this launch evaluated (q_new in leapfrog mode)
+  unsigned long long* tl;   // NULL, or the per-phase time stamps of this launch (b200glm_timeline_*): [grid + 1][16]
   ModelConst mc;
 };
 

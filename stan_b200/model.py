@@ -106,7 +106,11 @@ class GLMModel:
         h = C.c_void_p()
         rc = self.L.b200glm_create(C.byref(d), C.byref(h))
         self.h = h
-        self._check(rc)
+        try:
+            self._check(rc)
+        except Exception:
+            self.close()       # a failed create still returns a handle (for last_error); release it
+            raise
         self.P = self.L.b200glm_num_params(self.h)
 
     # ------------------------------------------------------------------ plumbing
@@ -206,6 +210,18 @@ class GLMModel:
 
     def bytes_per_gradient(self):
         return self.L.b200glm_bytes_per_gradient(self.h)
+
+    def timeline_enable(self, on=True, slot=0):
+        self._check(self.L.b200glm_timeline_enable(self.h, slot, int(on)))
+
+    def timeline_read(self, slot=0):
+        """Per-phase time stamps of the slot's last gradient launch: uint64 array (grid + 1, 16), see b200glm.h."""
+        rows = C.c_int32()
+        self._check(self.L.b200glm_timeline_read(self.h, slot, None, C.byref(rows)))
+        out = np.zeros((rows.value, 16), dtype=np.uint64)
+        self._check(self.L.b200glm_timeline_read(self.h, slot, out.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                 C.byref(rows)))
+        return out
 
     # ------------------------------------------------------------------ batched chains (fp64 DMMA path)
     def batch_reserve(self, max_chains):

@@ -57,6 +57,37 @@ def nuts_through_the_reference_service(rank, world, local, dev):
     return failures
 
 
+def bad_y_is_reported_by_every_rank(rank, world, local, dev):
+    """An out-of-range y held by ONE shard (the reference checks y on every call, poisson_log_glm_lpmf.hpp:84) must
+    make every rank return the domain error, not only the rank that holds it -- otherwise the replicated host code
+    diverges and the next exchange times out."""
+    from stan_b200.model import DomainError
+    failures = []
+    N, K = 40_000, 8
+    d = make_glm_data("poisson_log", N, K)
+    y = d["y"].copy()
+    y[N - 3] = -1                                            # lives in the last rank's shard only
+    r0, r1 = shard_rows(N, rank, world)
+    m = GLMModel("poisson_log", d["X"][r0:r1], y[r0:r1], device=local, rank=rank, world=world, N_total=N)
+    if os.environ.get("MGPU_TRANSPORT", "peer") == "peer":
+        m.connect_peers_torch(dist, dev)
+    else:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(GLMModel.comm_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(uid, 0)
+        m.comm_init(uid.cpu().numpy().tobytes())
+    th = np.zeros(m.num_params_r())
+    for _ in range(2):                                       # twice: the ranks must stay in step after the error
+        try:
+            m.log_prob_grad(th)
+            failures.append(f"rank {rank}: out-of-range y in another shard was not reported")
+        except DomainError:
+            pass
+    m.close()
+    return failures
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -65,11 +96,13 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     failures = []
     for fam, N, K, G in [("bernoulli_logit", 200_003, 100, 0), ("poisson_log", 150_000, 50, 1000),
-                         ("normal_id", 90_001, 33, 0)]:
+                         ("normal_id", 90_001, 33, 0), ("binomial_logit", 70_001, 21, 0),
+                         ("neg_binomial_2_log", 80_003, 17, 0), ("neg_binomial_2_log", 40_000, 9, 37)]:
         d = make_glm_data(fam, N, K, G)                     # every rank builds the same global data
         r0, r1 = shard_rows(N, rank, world)
         grp = None if d["group"] is None else d["group"][r0:r1]
-        m = GLMModel(fam, d["X"][r0:r1], d["y"][r0:r1], grp, G, device=local, rank=rank, world=world, N_total=N)
+        kw = {"trials": d["trials"][r0:r1]} if fam == "binomial_logit" else {}
+        m = GLMModel(fam, d["X"][r0:r1], d["y"][r0:r1], grp, G, device=local, rank=rank, world=world, N_total=N, **kw)
         if os.environ.get("MGPU_TRANSPORT", "peer") == "peer":
             m.connect_peers_torch(dist, dev)
         else:
@@ -98,7 +131,8 @@ def main():
             failures.append(f"{fam}: ranks disagree")
         if rank == 0:
             from oracle.oracle import PortOracle
-            po = PortOracle(fam, d["X"], d["y"], d["group"], G)
+            po = PortOracle(fam, d["X"], d["y"], d["group"], G,
+                            **({"trials": d["trials"]} if fam == "binomial_logit" else {}))
             lp_r, g_r = po.log_prob_grad(th)
             sc = np.maximum(np.abs(g_r), np.abs(g_r).max())
             e = max(abs(lp - lp_r) / abs(lp_r), float(np.max(np.abs(g - g_r) / sc)),
@@ -111,6 +145,7 @@ def main():
                 failures.append(f"{fam}: err {e}")
             print(f"{fam} N={N} K={K} G={G} world={world}: max err {e:.2e}", flush=True)
         m.close()
+    failures += bad_y_is_reported_by_every_rank(rank, world, local, dev)
     failures += nuts_through_the_reference_service(rank, world, local, dev)
     n_fail = torch.tensor([len(failures)], device=dev)
     dist.all_reduce(n_fail)                     # a rank other than 0 may be the one that saw a mismatch
