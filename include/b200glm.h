@@ -202,6 +202,11 @@ int64_t b200glm_bytes_per_gradient(const b200glm_handle* h);
  * 3 model epilogue / leapfrog tail written.  read(out = NULL) only returns the row count. */
 int b200glm_timeline_enable(b200glm_handle* h, int32_t slot, int32_t on);
 int b200glm_timeline_read(b200glm_handle* h, int32_t slot, uint64_t* out, int32_t* rows);
+/* Roofline denominators measured on `device` in the caller's process (either pointer may be NULL):
+ * read_gbs    = bandwidth of a read-only stream over 4 GiB (the gradient kernels read X once and write nothing;
+ *               the driver's MEASURED_PEAKS hbm_gbs is a read+write copy);
+ * dmma_tflops = register-resident mma.sync.m8n8k4.f64 loop, the fp64 tensor-pipe peak that bounds the batched kernel. */
+int b200glm_measure_peaks(int32_t device, double* read_gbs, double* dmma_tflops);
 const char* b200glm_last_error(const b200glm_handle* h);
 const char* b200glm_version(void);
 /* B200GLM_ABI_VERSION the library was built with; bindings refuse to run on a mismatch */

@@ -18,7 +18,7 @@ SYMBOLS = [
     "b200glm_leapfrog_batched", "b200glm_leapfrog_batched_async", "b200glm_batch_sync", "b200glm_batch_stream",
     "b200glm_peer_export", "b200glm_peer_connect", "b200glm_lgamma_sum_local", "b200glm_set_lgamma_sum_total",
     "b200glm_glm_lpmf", "b200glm_shard_constants_local", "b200glm_set_shard_constants_total",
-    "b200glm_timeline_enable", "b200glm_timeline_read", "b200glm_abi_version",
+    "b200glm_timeline_enable", "b200glm_timeline_read", "b200glm_abi_version", "b200glm_measure_peaks",
     "b200glm_launch_count", "b200glm_bytes_per_gradient", "b200glm_last_error", "b200glm_version",
 ]
 
@@ -95,6 +95,7 @@ def lib():
         L.b200glm_set_shard_constants_total.argtypes = [C.c_void_p, dp]
         L.b200glm_timeline_enable.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.b200glm_timeline_read.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64), ip]
+        L.b200glm_measure_peaks.argtypes = [C.c_int32, dp, dp]
         L.b200glm_launch_count.argtypes = [C.c_void_p]
         L.b200glm_launch_count.restype = C.c_int64
         L.b200glm_bytes_per_gradient.argtypes = [C.c_void_p]
@@ -131,3 +132,12 @@ def connect_peers_torch(handle, world, dist, dev):
     tot = (C.c_double * 2)(float(lg[0].item()), float(lg[1].item()))
     check(L.b200glm_set_shard_constants_total(handle, tot))
     dist.barrier()
+
+
+def measure_peaks(device=0, read=True, dmma=False):
+    """(read-only-stream HBM GB/s, fp64 DMMA TFLOP/s) measured now on `device`; None for what was not asked."""
+    r, t = C.c_double(), C.c_double()
+    rc = lib().b200glm_measure_peaks(int(device), C.byref(r) if read else None, C.byref(t) if dmma else None)
+    if rc != OK:
+        raise RuntimeError("b200glm_measure_peaks failed (no sm_100 device?)")
+    return (r.value if read else None), (t.value if dmma else None)

@@ -15,6 +15,9 @@
 #include <b200/batched_nuts.hpp>
 #include <b200/glm_functions.hpp>
 
+#include <stan/analyze/mcmc/ess.hpp>
+#include <stan/analyze/mcmc/mcse.hpp>
+#include <stan/analyze/mcmc/rhat.hpp>
 #include <stan/callbacks/interrupt.hpp>
 #include <stan/callbacks/logger.hpp>
 #include <stan/callbacks/structured_writer.hpp>
@@ -470,6 +473,19 @@ int b200stan_func_eval(void* dv, int propto, int operands_are_var, int sigma_is_
       run(double(0), double(0));
     }
   });
+}
+
+// The reference's own diagnostics (ST/analyze/mcmc/{ess,mcse,rhat}.hpp) on draws produced through this library:
+// d is column-major n_draws x n_chains for one parameter.  which: 0 ess, 1 rhat, 2 mcse_mean, 3 mcse_sd
+double b200stan_diagnostic(int which, const double* d, int n_draws, int n_chains) {
+  Eigen::MatrixXd m = Eigen::Map<const Eigen::MatrixXd>(d, n_draws, n_chains);
+  switch (which) {
+    case 0: return stan::analyze::ess(m);
+    case 1: return stan::analyze::rhat(m);
+    case 2: return stan::analyze::mcse_mean(m);
+    case 3: return stan::analyze::mcse_sd(m);
+  }
+  return std::numeric_limits<double>::quiet_NaN();
 }
 
 const char* b200stan_version() {

@@ -21,6 +21,7 @@
 #include "glm_kernels.cuh"
 #include "glm_wide_kernel.cuh"
 #include "glm_batched_kernel.cuh"
+#include "measure.cuh"
 
 using namespace b200glm;
 
@@ -76,6 +77,9 @@ struct Slot {
   double* theta_used = nullptr;  // P
   double* h_pinned = nullptr;    // pinned staging: max(3P+1, P+2) * 2
   unsigned long long peer_seq = 0;  // evaluations exchanged through the peer mailboxes so far
+  unsigned long long host_seq = 0;  // launches that mirrored their outputs into h_out so far
+  double* h_out_dev = nullptr;      // device-side address of h_out
+  double* h_out = nullptr;          // pinned: [result P+2][state 3P+1][sequence word], written by the epilogue itself
   unsigned long long* tl = nullptr; // (grid + 1) x 16 time stamps of the last launch (b200glm_timeline_enable)
   std::mutex mu;
 };
@@ -107,6 +111,7 @@ struct b200glm_handle {
   double* panels = nullptr;
   long long* seg_ptr = nullptr;  // G+1 (device)
   int grid = 0, n_stages = 0, stage_a = 0;
+  int state_smem = 0;  // the kernels keep the chain state + likelihood sums in shared memory for the epilogue
   size_t smem_bytes = 0;
   int cpl = 0;
   // wide kernel (K > 256 or B200GLM_FLAG_FORCE_WIDE): 16-row panels streamed as J sub-panels
@@ -116,6 +121,8 @@ struct b200glm_handle {
   double lgamma_sum_total = 0.0;
   bool bad_y = false;        // any shard holds an out-of-range y (after b200glm_comm_init / set_shard_constants_total)
   bool bad_y_local = false;  // this shard does
+  bool inline_theta = true; // B200GLM_NO_INLINE_THETA=1: always upload theta with a host-to-device copy (A/B runs)
+  bool host_mirror = true;  // B200GLM_NO_HOST_MIRROR=1: fetch results with a device-to-host copy + stream sync (A/B runs)
   bool pdl = true;          // B200GLM_NO_PDL=1 in the environment turns programmatic dependent launch off (A/B runs)
   std::vector<Slot*> slots;
   Batch* batch = nullptr;
@@ -196,9 +203,10 @@ kernel_fn handle_kernel(const b200glm_handle* h) {
   return h->wide ? pick_wide_kernel(h->d.family, h->panel_rows, h->spw, h->spc) : pick_kernel(h->d.family, h->cpl);
 }
 
-size_t fixed_smem_bytes(int K, int G, int stage_a, int S) {
+size_t fixed_smem_bytes(int K, int G, int stage_a, int S, int P_state = 0) {
   const int Kpad = (K + 3) & ~3;
   size_t b = 0;
+  if (P_state) b += (size_t)state_smem_doubles(P_state) * 8;   // on-chip chain state
   b += (size_t)Kpad * 8;                                 // sbeta
   b += (size_t)NUM_CONSUMER_WARPS * 32 * 8;              // sr
   b += (size_t)NUM_CONSUMER_WARPS * (Kpad + 4) * 8;      // red
@@ -255,6 +263,7 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
       p.peer.mbox[r] = h->peer_mbox[r] + (size_t)slot_idx * PEER_BUFS * h->d.world * h->peer_stride;
   }
   p.stage_a_in_smem = h->stage_a;
+  p.state_in_smem = h->state_smem;
   p.theta_in = s->theta;
   p.st_in = s->state[s->cur];
   p.st_out = s->state[s->cur ^ 1];
@@ -289,14 +298,32 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
 }
 
 // Enqueue one evaluation (all launches + the optional all-reduce) on the slot's stream.
+// host_theta != NULL (MODE_THETA): theta is still on the host; it travels in the kernel's parameter block when the
+// model is small enough and the main kernel runs, else through the slot's pinned staging + a host-to-device copy.
+// mirror_to_host: the epilogue also writes result / state into s->h_out and releases its sequence word (wait_host_out).
 int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian, int is_var, double eps,
-                 int lik_only = 0, int sigma_is_var = 0) {
-  KernelParams p;
+                 int lik_only = 0, int sigma_is_var = 0, const double* host_theta = nullptr,
+                 bool mirror_to_host = false) {
+  // the parameter block is the last thing cudaLaunchKernelEx copies: static storage keeps 2.5 KB off the stack
+  static thread_local KernelParams p;
   const bool need_likelihood = ((!propto) || is_var) && h->d.N_total != -1;
   const bool rows_anywhere = lik_rows_total(h) > 0;
   const bool exchange = need_likelihood && rows_anywhere && h->peer_on;
   if (exchange) ++s->peer_seq;
   fill_params(h, s, p, mode, propto, jacobian, is_var, eps, lik_only, sigma_is_var);
+  if (host_theta) {
+    if (need_likelihood && rows_anywhere && h->P <= THETA_INLINE_MAX && h->inline_theta) {
+      p.theta_inline_n = h->P;
+      std::memcpy(p.theta_inline, host_theta, sizeof(double) * h->P);
+    } else {
+      std::memcpy(s->h_pinned, host_theta, sizeof(double) * h->P);
+      CUDA_TRY(h, cudaMemcpyAsync(s->theta, s->h_pinned, sizeof(double) * h->P, cudaMemcpyHostToDevice, s->stream));
+    }
+  }
+  if (mirror_to_host) {
+    p.host_out = s->h_out_dev;
+    p.host_seq = ++s->host_seq;
+  }
   p.peer_in_main = (exchange && h->d.G == 0) ? 1 : 0;
   p.peer_in_finish = (exchange && h->d.G > 0) ? 1 : 0;
   if (need_likelihood && rows_anywhere) {
@@ -352,6 +379,36 @@ int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian,
   return B200GLM_OK;
 }
 
+// Wait for the launch that mirrors into s->h_out: poll its sequence word (written by the epilogue after a
+// system-scope fence); every so often ask the stream, so that a failed launch or a path that did not reach the
+// mirrored epilogue ends the wait.  Returns true if the mirror is valid, false if the caller must copy from the device.
+int wait_host_out(b200glm_handle* h, Slot* s, bool* mirrored) {
+  const int P = h->P;
+  volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(s->h_out + (P + 2) + (3 * P + 1));
+  *mirrored = false;
+  for (unsigned spins = 0;; ++spins) {
+    if (*flag == s->host_seq) {
+      std::atomic_thread_fence(std::memory_order_acquire);
+      *mirrored = true;
+      return B200GLM_OK;
+    }
+    if ((spins & 1023u) == 1023u) {
+      const cudaError_t q = cudaStreamQuery(s->stream);
+      if (q == cudaSuccess) {
+        *mirrored = (*flag == s->host_seq);
+        return B200GLM_OK;
+      }
+      if (q != cudaErrorNotReady) {
+        h->set_error(std::string("cudaStreamQuery: ") + cudaGetErrorString(q));
+        return B200GLM_CUDA;
+      }
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+
 int eval_host(b200glm_handle* h, int slot, const double* theta, int propto, int jacobian, int is_var, double* lp,
               double* grad, int lik_only = 0, int sigma_is_var = 0) {
   int rc = validate_slot(h, slot);
@@ -364,13 +421,19 @@ int eval_host(b200glm_handle* h, int slot, const double* theta, int propto, int 
   std::lock_guard<std::mutex> g(s->mu);
   CUDA_TRY(h, cudaSetDevice(h->d.device));
   const int P = h->P;
-  std::memcpy(s->h_pinned, theta, sizeof(double) * P);
-  CUDA_TRY(h, cudaMemcpyAsync(s->theta, s->h_pinned, sizeof(double) * P, cudaMemcpyHostToDevice, s->stream));
-  rc = enqueue_eval(h, s, MODE_THETA, propto, jacobian, is_var, 0.0, lik_only, sigma_is_var);
+  rc = enqueue_eval(h, s, MODE_THETA, propto, jacobian, is_var, 0.0, lik_only, sigma_is_var, theta, h->host_mirror);
   if (rc) return rc;
-  double* hres = s->h_pinned + (3 * P + 1);
-  CUDA_TRY(h, cudaMemcpyAsync(hres, s->result, sizeof(double) * (P + 2), cudaMemcpyDeviceToHost, s->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(s->stream));
+  double* hres = s->h_out;
+  bool mirrored = false;
+  if (h->host_mirror) {
+    rc = wait_host_out(h, s, &mirrored);
+    if (rc) return rc;
+  }
+  if (!mirrored) {
+    hres = s->h_pinned + (3 * P + 1);
+    CUDA_TRY(h, cudaMemcpyAsync(hres, s->result, sizeof(double) * (P + 2), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(s->stream));
+  }
   // neg_binomial_2_log checks y before its include_summand early return (neg_binomial_2_log_glm_lpmf.hpp:130-135)
   if (h->bad_y && (is_var || !propto || h->d.family == B200GLM_NEG_BINOMIAL_2_LOG) && lik_rows_total(h) > 0) {
     static const char* const msg[] = {
@@ -444,6 +507,7 @@ void b200glm_destroy(b200glm_handle* h) {
     cudaFree(s->theta_used);
     cudaFree(s->tl);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    if (s->h_out) cudaFreeHost(s->h_out);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
   }
@@ -506,6 +570,8 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   if (!(d.prior_alpha_sd > 0) || !(d.prior_beta_sd > 0)) return fail(B200GLM_INVALID, "prior scales must be > 0");
   if (d.n_slots < 1) h->d.n_slots = 1;
   if (const char* e = std::getenv("B200GLM_NO_PDL")) h->pdl = !(e[0] == '1');
+  if (const char* e = std::getenv("B200GLM_NO_INLINE_THETA")) h->inline_theta = !(e[0] == '1');
+  if (const char* e = std::getenv("B200GLM_NO_HOST_MIRROR")) h->host_mirror = !(e[0] == '1');
   h->P = (d.G > 0 ? 2 + d.G : 1) + d.K + (fam_has_scale(d.family) ? 1 : 0);
   h->off_beta = d.G > 0 ? 2 + d.G : 1;
   h->C = fam_group_col(d.family, d.K) + (d.G > 0 ? 1 : 0);
@@ -526,6 +592,9 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   // launch geometry
   h->grid = d.grid_ctas > 0 ? d.grid_ctas : prop.multiProcessorCount;
   h->stage_a = (d.G > 0 && d.G <= SMEM_A_MAX_GROUPS) ? 1 : 0;
+  // on-chip chain state for the fused epilogue: G == 0 (the group path finishes in its own launch), <= 32 KB
+  h->state_smem = (d.G == 0 && (size_t)state_smem_doubles(P) * 8 <= 32768) ? 1 : 0;
+  const int P_state = h->state_smem ? P : 0;
   const size_t max_dyn = (size_t)prop.sharedMemPerBlockOptin - 1024;  // static scratch + slack
   if (!h->wide) {
     h->Cpad = h->C;
@@ -539,11 +608,11 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     if (!h->cpl) return fail(B200GLM_INVALID, "K too large");
     const size_t tile_bytes = (size_t)h->C * PANEL_ROWS * 8;
     int S = MAX_STAGES;
-    while (S > 0 && fixed_smem_bytes(d.K, d.G, h->stage_a, S) + (size_t)S * tile_bytes > max_dyn) --S;
+    while (S > 0 && fixed_smem_bytes(d.K, d.G, h->stage_a, S, P_state) + (size_t)S * tile_bytes > max_dyn) --S;
     if (S < 1) return fail(B200GLM_INVALID, "panel does not fit in shared memory");
     if (S > NUM_CONSUMER_WARPS) S = (S / NUM_CONSUMER_WARPS) * NUM_CONSUMER_WARPS;  // stage <-> warp ownership
     h->n_stages = S;
-    h->smem_bytes = fixed_smem_bytes(d.K, d.G, h->stage_a, S) + (size_t)S * tile_bytes;
+    h->smem_bytes = fixed_smem_bytes(d.K, d.G, h->stage_a, S, P_state) + (size_t)S * tile_bytes;
   } else {
     // sub-panels: 8 warp steps wide unless 4 steps already give every warp at most one sub-panel
     const int WR = h->panel_rows, cps = wide_cps(WR);
@@ -555,7 +624,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     h->spw = (h->J + WIDE_CONSUMER_WARPS - 1) / WIDE_CONSUMER_WARPS;
     if (!pick_wide_kernel(d.family, WR, h->spw, h->spc))
       return fail(B200GLM_INVALID, "K too large for the wide kernel (K <= 3000)");
-    const size_t fixed = wide_fixed_doubles(WR, h->J, h->Kc, d.G, h->stage_a) * 8;
+    const size_t fixed = wide_fixed_doubles(WR, h->J, h->Kc, d.G, h->stage_a, P_state) * 8;
     const size_t slot_bytes = (size_t)h->Kc * WR * 8;
     int T = fixed < max_dyn ? (int)((max_dyn - fixed) / (slot_bytes + 16)) : 0;
     if (T > WIDE_MAX_SLOTS) T = WIDE_MAX_SLOTS;
@@ -731,6 +800,9 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     CREATE_TRY(cudaMalloc(&s->result, sizeof(double) * (P + 2)));
     CREATE_TRY(cudaMalloc(&s->theta_used, sizeof(double) * std::max(P, 1)));
     CREATE_TRY(cudaMallocHost(&s->h_pinned, sizeof(double) * (2 * (3 * P + 1) + P + 2)));
+    CREATE_TRY(cudaHostAlloc(&s->h_out, sizeof(double) * ((P + 2) + (3 * P + 1) + 1), cudaHostAllocMapped));
+    std::memset(s->h_out, 0, sizeof(double) * ((P + 2) + (3 * P + 1) + 1));
+    CREATE_TRY(cudaHostGetDevicePointer((void**)&s->h_out_dev, s->h_out, 0));
   }
   *out = h;
   return B200GLM_OK;
@@ -824,12 +896,20 @@ int b200glm_leapfrog(b200glm_handle* h, int32_t slot, double eps, const double* 
     std::memcpy(hm, inv_metric, sizeof(double) * P);
     CUDA_TRY(h, cudaMemcpyAsync(s->inv_metric, hm, sizeof(double) * P, cudaMemcpyHostToDevice, s->stream));
   }
-  rc = enqueue_eval(h, s, MODE_LEAPFROG, 1, 1, 1, eps);
+  rc = enqueue_eval(h, s, MODE_LEAPFROG, 1, 1, 1, eps, 0, 0, nullptr, h->host_mirror);
   if (rc) return rc;
   s->cur ^= 1;
-  double* hp = s->h_pinned;
-  CUDA_TRY(h, cudaMemcpyAsync(hp, s->state[s->cur], sizeof(double) * (3 * P + 1), cudaMemcpyDeviceToHost, s->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(s->stream));
+  double* hp = s->h_out + (P + 2);
+  bool mirrored = false;
+  if (h->host_mirror) {
+    rc = wait_host_out(h, s, &mirrored);
+    if (rc) return rc;
+  }
+  if (!mirrored) {
+    hp = s->h_pinned;
+    CUDA_TRY(h, cudaMemcpyAsync(hp, s->state[s->cur], sizeof(double) * (3 * P + 1), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(s->stream));
+  }
   if (q) std::memcpy(q, hp, sizeof(double) * P);
   if (p) std::memcpy(p, hp + P, sizeof(double) * P);
   if (g) std::memcpy(g, hp + 2 * P, sizeof(double) * P);
@@ -1201,6 +1281,67 @@ int b200glm_batch_sync(b200glm_handle* h) {
 }
 
 void* b200glm_batch_stream(b200glm_handle* h) { return (h && h->batch) ? (void*)h->batch->stream : nullptr; }
+
+int b200glm_measure_peaks(int32_t device, double* read_gbs, double* dmma_tflops) {
+  if (cudaSetDevice(device) != cudaSuccess) return B200GLM_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B200GLM_CUDA;
+  const int sms = prop.multiProcessorCount;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  int rc = B200GLM_OK;
+  if (read_gbs) {
+    const size_t bytes = (size_t)4 << 30;     // 4 GiB >> 126 MB L2
+    double2* buf = nullptr;
+    double* out = nullptr;
+    if (cudaMalloc(&buf, bytes) != cudaSuccess || cudaMalloc(&out, sizeof(double) * sms * 4) != cudaSuccess) {
+      cudaFree(buf);
+      rc = B200GLM_CUDA;
+    } else {
+      cudaMemset(buf, 0, bytes);
+      float best = 1e30f;
+      for (int i = 0; i < 8; ++i) {
+        cudaEventRecord(e0);
+        read_stream_kernel<<<sms * 4, 512>>>(buf, bytes / 16, out);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (i >= 2 && ms < best) best = ms;
+      }
+      *read_gbs = (double)bytes / (best * 1e-3) / 1e9;
+      if (cudaGetLastError() != cudaSuccess) rc = B200GLM_CUDA;
+    }
+    cudaFree(buf);
+    cudaFree(out);
+  }
+  if (dmma_tflops && rc == B200GLM_OK) {
+    double* out = nullptr;
+    const int grid = sms * 4, iters = 8000;
+    if (cudaMalloc(&out, sizeof(double) * grid * 256) != cudaSuccess) {
+      rc = B200GLM_CUDA;
+    } else {
+      float best = 1e30f;
+      for (int i = 0; i < 4; ++i) {
+        cudaEventRecord(e0);
+        dmma_peak_kernel<<<grid, 256>>>(out, iters, 0.999, 0.001);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (i >= 1 && ms < best) best = ms;
+      }
+      // one m8n8k4 DMMA = 8*8*4*2 = 512 flops per warp; 8 warps per CTA, 16 accumulator tiles per iteration
+      *dmma_tflops = 512.0 * 16 * iters * 8.0 * grid / (best * 1e-3) / 1e12;
+      if (cudaGetLastError() != cudaSuccess) rc = B200GLM_CUDA;
+      cudaFree(out);
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+}
 
 int b200glm_timeline_enable(b200glm_handle* h, int32_t slot, int32_t on) {
   int rc = validate_slot(h, slot);

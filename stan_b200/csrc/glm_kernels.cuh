@@ -144,7 +144,7 @@ __device__ __forceinline__ void tl_stamp(const KernelParams& p, int row, int k) 
     p.tl[(size_t)row * 16 + 8 + k] = (unsigned long long)clock64();
   }
 }
-__device__ bool peer_allreduce_lik(const KernelParams& p, int* sh_ok) {
+__device__ bool peer_allreduce_lik(const KernelParams& p, int* sh_ok, double* lik /* P + 2, shared or global */) {
   const PeerParams& pe = p.peer;
   const int n = p.P + 2, tid = threadIdx.x, nt = blockDim.x;
   const int buf = (int)(pe.seq % PEER_BUFS), buf_rearm = (int)((pe.seq + 2) % PEER_BUFS);
@@ -153,7 +153,7 @@ __device__ bool peer_allreduce_lik(const KernelParams& p, int* sh_ok) {
   __syncthreads();
   unsigned long long* mine = reinterpret_cast<unsigned long long*>(pe.mbox[pe.rank]);
   auto own_word = [&](int j) {
-    unsigned long long own = (unsigned long long)__double_as_longlong(__ldcg(p.lik + j));
+    unsigned long long own = (unsigned long long)__double_as_longlong(lik[j]);
     return own == PEER_EMPTY_BITS ? 0x7FF8000000000000ull : own;
   };
   for (int j = tid; j < n; j += nt) {            // every send is in flight before the first poll
@@ -189,7 +189,7 @@ __device__ bool peer_allreduce_lik(const KernelParams& p, int* sh_ok) {
 #pragma unroll
     for (int r = 0; r < MAX_PEERS; ++r)
       if (r < pe.world) v += __longlong_as_double((long long)w[r]);
-    p.lik[j] = v;
+    lik[j] = v;
   }
   __threadfence();
   __syncthreads();
@@ -200,7 +200,13 @@ __device__ void peer_timeout_result(const KernelParams& p) {
     p.result[0] = CUDART_NAN;
     p.result[1 + p.P] = (double)ST_PEER_TIMEOUT;
     if (p.mode == MODE_LEAPFROG) p.st_out[3 * p.P] = CUDART_NAN;
+    if (p.host_out) {
+      p.host_out[0] = CUDART_NAN;
+      p.host_out[1 + p.P] = (double)ST_PEER_TIMEOUT;
+      if (p.mode == MODE_LEAPFROG) p.host_out[(p.P + 2) + 3 * p.P] = CUDART_NAN;
+    }
   }
+  host_out_publish(p);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -209,9 +215,54 @@ __device__ void peer_timeout_result(const KernelParams& p) {
 // arrive (ticket) adds them in fixed CTA order -> bitwise deterministic, then (single GPU, no
 // groups) runs the model epilogue.  Must be called by all threads of the CTA.
 // ------------------------------------------------------------------------------------------
+// On-chip copy of the chain state a launch works on (KernelParams::state_in_smem): theta (the evaluated point),
+// the momentum after begin_update_p, the gradient the step started from, and room for the likelihood sums --
+// everything the epilogue needs, so that the last CTA's tail does not go back to global memory for it.
+struct StateSmem {
+  double *theta, *ph, *g0, *lik;   // P, P, P, P + 2 doubles (NULL: not staged)
+};
+__host__ __device__ constexpr int state_smem_doubles(int P) { return 4 * ((P + 3) & ~1); }
+__device__ __forceinline__ StateSmem carve_state_smem(double* base, int P, int enabled) {
+  const int Pp = (P + 3) & ~1;
+  StateSmem st;
+  st.theta = enabled ? base : nullptr;
+  st.ph = enabled ? base + Pp : nullptr;
+  st.g0 = enabled ? base + 2 * Pp : nullptr;
+  st.lik = enabled ? base + 3 * Pp : nullptr;
+  return st;
+}
+// theta for this launch (leapfrog: begin_update_p + update_q, expl_leapfrog.hpp:16-26), staged by `nthr` threads:
+// beta -> sbeta[0, nb_pad) (zero beyond K), the group intercepts -> sa (if staged), the whole state -> st (if staged),
+// theta -> p.theta_used (CTA 0).  The caller synchronises afterwards.
+__device__ __forceinline__ void stage_theta(const KernelParams& p, int t, int nthr, double* sbeta, int nb_pad,
+                                            double* sa, const StateSmem& st) {
+  const int P = p.P, K = p.K, G = p.G;
+  const bool lf = p.mode == MODE_LEAPFROG;
+  const double he = 0.5 * p.eps;
+  for (int i = t; i < P; i += nthr) {
+    double q, ph = 0.0, g0 = 0.0;
+    if (lf) {
+      g0 = p.st_in[2 * P + i];
+      ph = p.st_in[P + i] - he * g0;
+      q = p.st_in[i] + p.eps * (p.inv_metric[i] * ph);
+    } else {
+      q = p.theta_inline_n ? p.theta_inline[i] : p.theta_in[i];
+    }
+    if (i >= p.off_beta && i < p.off_beta + K) sbeta[i - p.off_beta] = q;
+    if (sa && i >= 2 && i < 2 + G) sa[i - 2] = q;
+    if (st.theta) {
+      st.theta[i] = q;
+      st.ph[i] = ph;
+      st.g0[i] = g0;
+    }
+    if (blockIdx.x == 0) p.theta_used[i] = q;
+  }
+  for (int k = K + t; k < nb_pad; k += nthr) sbeta[k] = 0.0;
+}
+
 template <int FAMILY>
 __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& p, double* sh_scratch,
-                                                            int* sh_is_last) {
+                                                            int* sh_is_last, const StateSmem& st) {
   const int tid = threadIdx.x, nt = blockDim.x, grid = gridDim.x;
   const int K = p.K, G = p.G, P = p.P;
   __threadfence();
@@ -231,52 +282,67 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
   __threadfence();
   // Sum of the grid's partial rows, column by column, in a FIXED tree (bitwise reproducible): the rows are cut
   // into R contiguous segments taken by R adjacent lanes (R = 1, 2, 4 or 8, as many as the CTA has threads for),
-  // each lane keeps 8 independent accumulators so 8 L2 loads are in flight per thread (this loop is on the
-  // critical path of every launch: ~13 us as one dependent chain of 148 loads, ~2 us like this), the segments
-  // meet in a shuffle butterfly.
+  // each lane keeps GS_DEPTH independent accumulators so that many L2 loads are in flight per thread (this loop is
+  // on the critical path of every launch: ~13 us as one dependent chain of 148 loads, 4.7 us eight at a time,
+  // profiles/r2_timeline_*), the segments meet in a shuffle butterfly.
+  constexpr int GS_DEPTH = 40;
+  double* lik = st.lik ? st.lik : p.lik;         // the sums go to the on-chip copy when there is one
   const int n_sums = FAMILY == FAM_NEG_BINOMIAL_2_LOG ? K + 3 : K + 2;
   int R = 1;
   while (R < 8 && 2 * R * n_sums <= nt) R *= 2;
   const int seg_len = (grid + R - 1) / R;
   for (int base = 0; base < n_sums; base += nt / R) {       // warp-uniform trip count (nt and R are multiples)
     const int j = base + tid / R, r = tid & (R - 1);
-    double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double a[GS_DEPTH];
+#pragma unroll
+    for (int u = 0; u < GS_DEPTH; ++u) a[u] = 0.0;
     if (j < n_sums) {
       const int b1 = min(grid, (r + 1) * seg_len);
       int b = r * seg_len;
       const double* src = p.partials + j;
-      for (; b + 8 <= b1; b += 8) {
+      for (; b + GS_DEPTH <= b1; b += GS_DEPTH) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) a[u] += __ldcg(src + (size_t)(b + u) * p.pstride);
+        for (int u = 0; u < GS_DEPTH; ++u) a[u] += __ldcg(src + (size_t)(b + u) * p.pstride);
       }
 #pragma unroll
-      for (int u = 0; u < 7; ++u)
+      for (int u = 0; u < GS_DEPTH - 1; ++u)
         if (b + u < b1) a[u] += __ldcg(src + (size_t)(b + u) * p.pstride);
     }
-    double v = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+#pragma unroll
+    for (int w = GS_DEPTH / 2; w >= 5; w /= 2) {            // 40 -> 20 -> 10 -> 5 partial sums, fixed pairing
+#pragma unroll
+      for (int u = 0; u < w; ++u) a[u] += a[u + w];
+    }
+    double v = ((a[0] + a[1]) + (a[2] + a[3])) + a[4];
     for (int o = 1; o < R; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (j >= n_sums || r != 0) continue;
     if (j < K)
-      p.lik[p.off_beta + j] = v;
+      lik[p.off_beta + j] = v;
     else if (j == K)
-      p.lik[P] = v;
+      lik[P] = v;
     else if (j == K + 2)
-      p.lik[P + 1] = v;      // neg_binomial_2_log: sum of the per-row d/dphi terms
+      lik[P + 1] = v;      // neg_binomial_2_log: sum of the per-row d/dphi terms
     else if (G == 0)
-      p.lik[0] = v;
+      lik[0] = v;
   }
   if (tid == 0) *p.ticket = 0u;
-  if (fam_has_scale(FAMILY) && tid == 0) p.lik[P - 1] = 0.0;  // sigma | phi entry is derived in finish()
-  if (G > 0 && tid < 2) p.lik[tid] = 0.0;
+  if (fam_has_scale(FAMILY) && tid == 0) lik[P - 1] = 0.0;  // sigma | phi entry is derived in finish()
+  if (FAMILY != FAM_NEG_BINOMIAL_2_LOG && tid == 32) lik[P + 1] = 0.0;
+  if (G > 0 && tid < 2) lik[tid] = 0.0;
   __threadfence();
   __syncthreads();
   if (tid == 0) tl_stamp(p, grid, 1);            // sum of the grid's partial rows done
-  if (p.peer_in_main && !peer_allreduce_lik(p, sh_is_last)) {
+  if (p.peer_in_main && !peer_allreduce_lik(p, sh_is_last, lik)) {
     peer_timeout_result(p);
     return;
   }
   if (tid == 0) tl_stamp(p, grid, 2);            // peers' partials received and summed
-  if (p.fuse_finish) finish(p, sh_scratch);
+  if (p.fuse_finish) {
+    const FinishSrc src = {st.theta ? st.theta : p.theta_used, lik, st.ph, st.g0};
+    finish(p, sh_scratch, src);
+  } else if (st.lik) {
+    for (int j = tid; j < P + 2; j += nt) p.lik[j] = lik[j];   // the separate epilogue launch reads the global copy
+  }
   if (tid == 0) tl_stamp(p, grid, 3);            // model epilogue / leapfrog tail written
 }
 
@@ -284,7 +350,7 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
 // The main kernel
 // ------------------------------------------------------------------------------------------
 template <int FAMILY, int CPL>
-__global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelParams p) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_constant__ KernelParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int K = p.K, C = p.C, G = p.G, P = p.P;
   const int S = p.n_stages;
@@ -297,7 +363,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
   double* sr = sbeta + Kpad;                                            // 8 * 32
   double* red = sr + NUM_CONSUMER_WARPS * 32;                           // 8 * (Kpad + 4)
   double* sa = red + NUM_CONSUMER_WARPS * (Kpad + 4);                   // G (optional)
-  double* after_a = sa + (p.stage_a_in_smem ? ((G + 1) & ~1) : 0);
+  double* st_base = sa + (p.stage_a_in_smem ? ((G + 1) & ~1) : 0);      // chain state (optional)
+  const StateSmem st = carve_state_smem(st_base, P, p.state_in_smem);
+  double* after_a = st_base + (p.state_in_smem ? state_smem_doubles(P) : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(after_a);            // S
   uint64_t* empty_bar = full_bar + S;                                   // S
   __shared__ double sh_scratch[64];
@@ -327,17 +395,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
       const double ph = p.st_in[P + i] - (0.5 * p.eps) * p.st_in[2 * P + i];
       return p.st_in[i] + p.eps * (p.inv_metric[i] * ph);
     }
-    return p.theta_in[i];
+    return p.theta_inline_n ? p.theta_inline[i] : p.theta_in[i];
   };
   constexpr int NC = NUM_CONSUMER_WARPS * 32;   // the consumer warps stage theta; the producer is already loading
   double alpha = 0.0;
   LinkConst lc;
   if (warp != NUM_CONSUMER_WARPS) {
-    for (int k = tid; k < Kpad; k += NC) sbeta[k] = k < K ? theta_at(p.off_beta + k) : 0.0;
-    if (p.stage_a_in_smem)
-      for (int g = tid; g < G; g += NC) sa[g] = theta_at(2 + g);
-    if (blockIdx.x == 0)
-      for (int i = tid; i < P; i += NC) p.theta_used[i] = theta_at(i);
+    stage_theta(p, tid, NC, sbeta, Kpad, p.stage_a_in_smem ? sa : nullptr, st);
     alpha = G > 0 ? 0.0 : theta_at(0);
   }
   lc.inv_sigma = 1.0;
@@ -498,7 +562,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const KernelP
     for (int w = 0; w < NUM_CONSUMER_WARPS; ++w) v += red[w * (Kpad + 4) + src];
     my_part[j] = v;
   }
-  cross_cta_reduce_and_finish<FAMILY>(p, sh_scratch, &sh_is_last);
+  cross_cta_reduce_and_finish<FAMILY>(p, sh_scratch, &sh_is_last, st);
 }
 
 // G > 0: deterministic per-group sums of the residual (rows are sorted by group at upload, so a group
@@ -533,17 +597,17 @@ __global__ void __launch_bounds__(256) group_reduce_kernel(const double* __restr
 
 // Leapfrog step of a model whose likelihood term is empty (no rows anywhere, or the binomial size_zero quirk):
 // begin_update_p + update_q (expl_leapfrog.hpp:16-26) without a pass over X; finish_kernel does the rest.
-__global__ void __launch_bounds__(NUM_THREADS) theta_from_state_kernel(const KernelParams p) {
+__global__ void __launch_bounds__(NUM_THREADS) theta_from_state_kernel(const __grid_constant__ KernelParams p) {
   for (int i = threadIdx.x; i < p.P; i += blockDim.x) {
     const double ph = p.st_in[p.P + i] - (0.5 * p.eps) * p.st_in[2 * p.P + i];
     p.theta_used[i] = p.st_in[i] + p.eps * (p.inv_metric[i] * ph);
   }
 }
 
-__global__ void __launch_bounds__(NUM_THREADS) finish_kernel(const KernelParams p) {
+__global__ void __launch_bounds__(NUM_THREADS) finish_kernel(const __grid_constant__ KernelParams p) {
   __shared__ double sh_scratch[64];
   __shared__ int sh_ok;
-  if (p.peer_in_finish && !peer_allreduce_lik(p, &sh_ok)) {
+  if (p.peer_in_finish && !peer_allreduce_lik(p, &sh_ok, p.lik)) {
     peer_timeout_result(p);
     return;
   }

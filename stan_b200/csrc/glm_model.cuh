@@ -41,6 +41,7 @@ struct ModelConst {
 // Row-sharded operation without a separate collective launch: every rank owns a mailbox in its HBM,
 // mapped into every peer (CUDA IPC over NVLink / NVSwitch).  [PEER_BUFS][world][stride] doubles.
 constexpr int MAX_PEERS = 8;
+constexpr int THETA_INLINE_MAX = 256;
 constexpr int PEER_BUFS = 3;       // mailbox buffers rotated by evaluation number (see peer_allreduce_lik)
 // Every 8-byte word of a mailbox is self-validating: it holds PEER_EMPTY until the sender's value lands.
 // PEER_EMPTY is a NaN bit pattern no arithmetic produces; a payload that happens to carry it (a NaN handed in
@@ -66,6 +67,7 @@ struct KernelParams {
   int peer_in_finish;  // finish_kernel does (G > 0: the group sums are only complete by then)
   PeerParams peer;
   int stage_a_in_smem;
+  int state_in_smem;   // the launch keeps (theta, half-updated momentum, old gradient, likelihood sums) in shared memory
   const double* theta_in;   // MODE_THETA: P doubles (device)
   const double* st_in;      // MODE_LEAPFROG: [q(P) p(P) g(P) V]
   double* st_out;
@@ -79,7 +81,16 @@ struct KernelParams {
   double* result;           // [lp, grad(P), status]
   double* theta_used;       // P doubles: the theta this launch evaluated (q_new in leapfrog mode)
   unsigned long long* tl;   // NULL, or the per-phase time stamps of this launch (b200glm_timeline_*): [grid + 1][16]
+  // Host-facing calls (b200glm_log_prob_grad, b200glm_leapfrog): the epilogue also writes its outputs straight into
+  // pinned host memory -- [result (P + 2)] [state (3P + 1)] [sequence word] -- and the host polls the sequence word,
+  // instead of a device-to-host copy plus a stream synchronisation behind the launch (NULL for device-resident callers).
+  double* host_out;
+  unsigned long long host_seq;
+  // MODE_THETA with a small model: theta travels in the kernel's parameter block instead of a host-to-device copy
+  // ahead of the launch (theta_inline_n = P, or 0: read theta_in)
+  int theta_inline_n;
   ModelConst mc;
+  double theta_inline[THETA_INLINE_MAX];
 };
 
 #if defined(__CUDACC__)
@@ -91,14 +102,43 @@ __device__ __forceinline__ double warp_sum(double v) {
 #endif   // the host build supplies a one-lane warp_sum
 
 // ------------------------------------------------------------------------------------------
-// Model epilogue, run by ONE CTA once the likelihood sums are complete in p.lik.
-//   theta: the evaluated point (p.theta_used).
+// Model epilogue, run by ONE CTA once the likelihood sums are complete.
+//   src.theta : the evaluated point            src.lik : [P] likelihood gradient aligned with theta, [P] lp-sum,
+//   src.ph    : leapfrog mode, the momentum after begin_update_p (NULL: recomputed from p.st_in)
+//   src.g0    : leapfrog mode, the gradient the step started from (NULL: p.st_in + 2P)
+// The fused kernels hand in shared-memory copies (the state was read when theta was staged, the sums were formed
+// by this CTA), so the epilogue on the critical path of every launch has no dependent global-memory round trip;
+// finish_kernel and the host build pass the global arrays.
 // ------------------------------------------------------------------------------------------
-__device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratch */) {
+// All of the CTA's writes to the pinned host block are done: make them visible system-wide, then release the
+// sequence word the host polls.  Called by every thread of the CTA.
+__device__ inline void host_out_publish(const KernelParams& p) {
+#if defined(__CUDACC__)
+  if (p.host_out) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(p.host_out + (p.P + 2) + (3 * p.P + 1));
+      *flag = p.host_seq;
+    }
+  }
+#else
+  (void)p;
+#endif
+}
+
+struct FinishSrc {
+  const double* theta;
+  const double* lik;
+  const double* ph;
+  const double* g0;
+};
+
+__device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratch */, const FinishSrc& src) {
   const ModelConst& mc = p.mc;
   const int P = mc.P, K = mc.K, G = mc.G;
-  const double* theta = p.theta_used;
-  const double* lik = p.lik;
+  const double* theta = src.theta;
+  const double* lik = src.lik;
   const int tid = threadIdx.x, nt = blockDim.x;
   const bool dens = (!mc.propto) || mc.is_var;  // include_summand: anything left to compute?
 
@@ -112,8 +152,8 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
   const double ib2 = 1.0 / (mc.prior_beta_sd * mc.prior_beta_sd);
   const double isa2 = 1.0 / (sigma_a * sigma_a);
 
-  // block-wide sums: [0] sum beta^2, [1] sum (a-mu)^2, [2] non-finite count
-  double sb = 0.0, sa = 0.0, bad = 0.0;
+  // block-wide sums: sum beta^2, sum (a-mu)^2, sum (a-mu), non-finite count
+  double sb = 0.0, sa = 0.0, sd = 0.0, bad = 0.0;
   for (int k = tid; k < K; k += nt) {
     const double b = theta[mc.off_beta + k];
     sb += b * b;
@@ -121,39 +161,35 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
   for (int g = tid; g < G; g += nt) {
     const double d = theta[2 + g] - mu_a;
     sa += d * d;
+    sd += d;
   }
   for (int i = tid; i < P; i += nt) {
     if (!isfinite(theta[i]) || !isfinite(lik[i])) bad += 1.0;
   }
   sb = warp_sum(sb);
   sa = warp_sum(sa);
+  sd = warp_sum(sd);
   bad = warp_sum(bad);
   __syncthreads();
   const int w = tid >> 5, nw = (nt + 31) >> 5;
   if ((tid & 31) == 0) {
     sh[w] = sb;
-    sh[16 + w] = sa;
-    sh[32 + w] = bad;
+    sh[12 + w] = sa;
+    sh[24 + w] = bad;
+    sh[36 + w] = sd;
   }
   __syncthreads();
-  if (tid == 0) {
-    double a0 = 0, a1 = 0, a2 = 0;
-    for (int i = 0; i < nw; ++i) {
-      a0 += sh[i];
-      a1 += sh[16 + i];
-      a2 += sh[32 + i];
-    }
-    sh[48] = a0;
-    sh[49] = a1;
-    sh[50] = a2;
+  double sum_b2 = 0.0, sum_d2 = 0.0, n_bad = 0.0, sum_d = 0.0;   // every thread folds the (<= 12) warp sums itself
+  for (int i = 0; i < nw; ++i) {
+    sum_b2 += sh[i];
+    sum_d2 += sh[12 + i];
+    n_bad += sh[24 + i];
+    sum_d += sh[36 + i];
   }
-  __syncthreads();
-  const double sum_b2 = sh[48], sum_d2 = sh[49];
-  const double n_bad = sh[50];
 
-  // ---- value (thread 0) ----
-  if (tid == 0) {
-    double lp = 0.0;
+  // ---- value (computed redundantly by every thread: no broadcast round) ----
+  double lp = 0.0;
+  {
     if (mc.jacobian && !mc.lik_only) {
       if (G > 0) lp += u_sa;                           // lb_constrain.hpp:64
       if (has_scale) lp += u_s;
@@ -206,15 +242,15 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
         }
       }
     }
-    const bool ok = isfinite(lp) && n_bad == 0.0;
-    sh[51] = lp;
-    sh[52] = ok ? 0.0 : 1.0;
   }
-  __syncthreads();
-  const double lp = sh[51];
-  const bool domain = sh[52] != 0.0;
+  const bool domain = !(isfinite(lp) && n_bad == 0.0);
 
-  // ---- gradient wrt unconstrained theta, one thread per entry ----
+  // ---- gradient wrt unconstrained theta and, in leapfrog mode, the second half of the step
+  //      (expl_leapfrog.hpp:28-32 end_update_p; base_hamiltonian.hpp:64-69), one thread per entry ----
+  const bool lf = p.mode == MODE_LEAPFROG;
+  const double he = 0.5 * p.eps;
+  double* hres = p.host_out;                                   // pinned host mirror of result / state (or NULL)
+  double* hst = p.host_out ? p.host_out + (P + 2) : nullptr;
   for (int i = tid; i < P; i += nt) {
     double g = lik[i];
     if (mc.lik_only) {
@@ -224,73 +260,66 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
         g = mc.N_total > 0 ? lik[P + 1] : 0.0;                       // neg_binomial_2_log_glm_lpmf.hpp:240-245
       else if (G > 0 && i < 2)
         g = 0.0;
-      p.result[1 + i] = g;
-      continue;
-    }
-    if (G > 0) {
-      if (i == 0) {
-        g = -mu_a / (mc.prior_alpha_sd * mc.prior_alpha_sd) + 0.0;  // + sum_g (a_g-mu)/sigma_a^2 below
-      } else if (i == 1) {
-        g = 0.0;
-      } else if (i < 2 + G) {
-        g += -(theta[i] - mu_a) * isa2;
+    } else {
+      if (G > 0) {
+        if (i == 0) {
+          g = -mu_a / (mc.prior_alpha_sd * mc.prior_alpha_sd) + 0.0;
+          g += sum_d * isa2;                                          // sum_g (a_g - mu) / sigma_a^2
+        } else if (i == 1) {
+          const double dsa = -sigma_a / (mc.prior_sigma_a_scale * mc.prior_sigma_a_scale)
+                             + sum_d2 * isa2 / sigma_a - G / sigma_a;
+          g = dsa * sigma_a + (mc.jacobian ? 1.0 : 0.0);
+        } else if (i < 2 + G) {
+          g += -(theta[i] - mu_a) * isa2;
+        }
+      } else if (i == 0) {
+        g += -alpha / (mc.prior_alpha_sd * mc.prior_alpha_sd);
       }
-    } else if (i == 0) {
-      g += -alpha / (mc.prior_alpha_sd * mc.prior_alpha_sd);
-    }
-    if (i >= mc.off_beta && i < mc.off_beta + K) g += -theta[i] * ib2;
-    if (has_scale && i == P - 1) {
-      double dlik = 0.0;
-      if (mc.N_total > 0)
-        dlik = mc.family == FAM_NORMAL_ID ? (lik[P] - mc.N_total) / sigma   // normal_id_glm_lpdf.hpp:181-183
-                                          : lik[P + 1];                     // neg_binomial_2_log_glm_lpmf.hpp:240-245
-      const double dpri = -(sigma - mc.prior_sigma_loc) / (mc.prior_sigma_scale * mc.prior_sigma_scale);
-      g = (dlik + dpri) * sigma + (mc.jacobian ? 1.0 : 0.0);
+      if (i >= mc.off_beta && i < mc.off_beta + K) g += -theta[i] * ib2;
+      if (has_scale && i == P - 1) {
+        double dlik = 0.0;
+        if (mc.N_total > 0)
+          dlik = mc.family == FAM_NORMAL_ID ? (lik[P] - mc.N_total) / sigma   // normal_id_glm_lpdf.hpp:181-183
+                                            : lik[P + 1];                     // neg_binomial_2_log_glm_lpmf.hpp:240-245
+        const double dpri = -(sigma - mc.prior_sigma_loc) / (mc.prior_sigma_scale * mc.prior_sigma_scale);
+        g = (dlik + dpri) * sigma + (mc.jacobian ? 1.0 : 0.0);
+      }
     }
     p.result[1 + i] = g;
-  }
-  __syncthreads();
-  if (G > 0 && !mc.lik_only) {  // mu_a and sigma_a entries need sums over the G group intercepts
-    double sd = 0.0;
-    for (int g = tid; g < G; g += nt) sd += theta[2 + g] - mu_a;
-    sd = warp_sum(sd);
-    __syncthreads();
-    if ((tid & 31) == 0) sh[w] = sd;
-    __syncthreads();
-    if (tid == 0) {
-      double tot = 0;
-      for (int i = 0; i < nw; ++i) tot += sh[i];
-      p.result[1 + 0] += tot * isa2;
-      const double dsa = -sigma_a / (mc.prior_sigma_a_scale * mc.prior_sigma_a_scale)
-                         + sum_d2 * isa2 / sigma_a - G / sigma_a;
-      p.result[1 + 1] = dsa * sigma_a + (mc.jacobian ? 1.0 : 0.0);
+    if (hres) hres[1 + i] = g;
+    if (lf) {
+      const double g0 = src.g0 ? src.g0[i] : p.st_in[2 * P + i];
+      const double ph = src.ph ? src.ph[i] : p.st_in[P + i] - he * g0;
+      const double gnew = domain ? -g0 : -g;
+      const double pnew = ph - he * gnew;
+      p.st_out[i] = theta[i];
+      p.st_out[2 * P + i] = gnew;
+      p.st_out[P + i] = pnew;
+      if (hst) {
+        hst[i] = theta[i];
+        hst[2 * P + i] = gnew;
+        hst[P + i] = pnew;
+      }
     }
-    __syncthreads();
   }
   if (tid == 0) {
+    const double status = domain ? (double)ST_DOMAIN : (double)ST_OK;
     p.result[0] = lp;
-    p.result[1 + P] = domain ? (double)ST_DOMAIN : (double)ST_OK;
-  }
-
-  // ---- leapfrog tail (expl_leapfrog.hpp:28-32 end_update_p; base_hamiltonian.hpp:64-69) ----
-  if (p.mode == MODE_LEAPFROG) {
-    const double* q0 = p.st_in;
-    const double* p0 = p.st_in + P;
-    const double* g0 = p.st_in + 2 * P;
-    double* qn = p.st_out;
-    double* pn = p.st_out + P;
-    double* gn = p.st_out + 2 * P;
-    const double he = 0.5 * p.eps;
-    for (int i = tid; i < P; i += nt) {
-      const double ph = p0[i] - he * g0[i];
-      const double gnew = domain ? -g0[i] : -p.result[1 + i];
-      qn[i] = theta[i];
-      gn[i] = gnew;
-      pn[i] = ph - he * gnew;
-      (void)q0;
+    p.result[1 + P] = status;
+    if (lf) p.st_out[3 * P] = domain ? CUDART_INF : -lp;
+    if (hres) {
+      hres[0] = lp;
+      hres[1 + P] = status;
+      if (lf) hst[3 * P] = domain ? CUDART_INF : -lp;
     }
-    if (tid == 0) p.st_out[3 * P] = domain ? CUDART_INF : -lp;
   }
+  host_out_publish(p);
+}
+
+// the epilogue from the global arrays (finish_kernel, host build)
+__device__ inline void finish(const KernelParams& p, double* sh) {
+  const FinishSrc src = {p.theta_used, p.lik, nullptr, nullptr};
+  finish(p, sh, src);
 }
 
 // ------------------------------------------------------------------------------------------

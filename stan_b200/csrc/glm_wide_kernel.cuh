@@ -54,12 +54,13 @@ __host__ __device__ inline int wide_rows_for(int C) { return C <= 512 ? 16 : (C 
 __host__ __device__ inline int wide_cps(int WR) { return 32 / (WR / 4); }
 
 // doubles of dynamic shared memory besides the ring slots and their barriers
-__host__ __device__ inline size_t wide_fixed_doubles(int WR, int J, int KC, int G, int stage_a) {
-  return (size_t)J * KC + 2 * WIDE_CONSUMER_WARPS * WR + 2 * WR + (stage_a ? ((G + 1) & ~1) : 0);
+__host__ __device__ inline size_t wide_fixed_doubles(int WR, int J, int KC, int G, int stage_a, int P_state = 0) {
+  return (size_t)J * KC + 2 * WIDE_CONSUMER_WARPS * WR + 2 * WR + (stage_a ? ((G + 1) & ~1) : 0)
+         + (P_state ? state_smem_doubles(P_state) : 0);
 }
 
 template <int FAMILY, int WR, int SPW, int SPC>
-__global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelParams p) {
+__global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_constant__ KernelParams p) {
   constexpr int LPC = WR / 4, CPS = 32 / LPC;                  // lanes per column, columns per warp step
   constexpr int KC = SPC * CPS;                                // sub-panel width (columns)
   constexpr int SLOT = KC * WR;                                // doubles per ring slot
@@ -71,7 +72,9 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelP
   double* eta_part = sbeta + J * KC;                             // 2 parities x 8 warps x WR
   double* r_sh = eta_part + 2 * WIDE_CONSUMER_WARPS * WR;        // 2 parities x WR
   double* sa = r_sh + 2 * WR;                                    // G (optional)
-  double* after_a = sa + (p.stage_a_in_smem ? ((G + 1) & ~1) : 0);
+  double* st_base = sa + (p.stage_a_in_smem ? ((G + 1) & ~1) : 0);   // chain state (optional)
+  const StateSmem st = carve_state_smem(st_base, P, p.state_in_smem);
+  double* after_a = st_base + (p.state_in_smem ? state_smem_doubles(P) : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(after_a);     // T
   uint64_t* empty_bar = full_bar + T;                            // T
   __shared__ double sh_scratch[64];
@@ -96,14 +99,10 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelP
       const double ph = p.st_in[P + i] - (0.5 * p.eps) * p.st_in[2 * P + i];
       return p.st_in[i] + p.eps * (p.inv_metric[i] * ph);
     }
-    return p.theta_in[i];
+    return p.theta_inline_n ? p.theta_inline[i] : p.theta_in[i];
   };
   pdl_grid_dependency_wait();   // theta / the leapfrog state come from the previous launch on this stream
-  for (int k = tid; k < J * KC; k += WIDE_THREADS) sbeta[k] = k < K ? theta_at(p.off_beta + k) : 0.0;
-  if (p.stage_a_in_smem)
-    for (int g = tid; g < G; g += WIDE_THREADS) sa[g] = theta_at(2 + g);
-  if (blockIdx.x == 0)
-    for (int i = tid; i < P; i += WIDE_THREADS) p.theta_used[i] = theta_at(i);
+  stage_theta(p, tid, WIDE_THREADS, sbeta, J * KC, p.stage_a_in_smem ? sa : nullptr, st);
   __syncthreads();
 
   const long long n_panels = p.n_panels;
@@ -342,7 +341,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const KernelP
     }
   }
 
-  cross_cta_reduce_and_finish<FAMILY>(p, sh_scratch, &sh_is_last);
+  cross_cta_reduce_and_finish<FAMILY>(p, sh_scratch, &sh_is_last, st);
 }
 
 }  // namespace b200glm

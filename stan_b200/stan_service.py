@@ -249,6 +249,17 @@ class FuncGLM:
         return f.value, da, db[:self.K], ds.value
 
 
+def diagnostic(which, draws):
+    """stan::analyze::{ess, rhat, mcse_mean, mcse_sd} (the reference's estimators, compiled into libb200stan.so)
+    for ONE parameter; draws: (n_draws, n_chains)."""
+    L = lib()
+    L.b200stan_diagnostic.restype = C.c_double
+    L.b200stan_diagnostic.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int]
+    d = np.asfortranarray(draws, dtype=np.float64)
+    return L.b200stan_diagnostic({"ess": 0, "rhat": 1, "mcse_mean": 2, "mcse_sd": 3}[which], _dp(d), d.shape[0],
+                                 d.shape[1])
+
+
 def read_stan_csv(path):
     """stan::io::stan_csv_reader::parse: returns dict(header, samples (rows, cols), step_size, metric)."""
     L = lib()
