@@ -194,12 +194,14 @@ int64_t b200glm_launch_count(const b200glm_handle* h);
 int64_t b200glm_bytes_per_gradient(const b200glm_handle* h);
 /* Per-phase time stamps of a slot's gradient launches (measurement only; narrow kernel + the shared tail).
  * enable(on=1) allocates the buffer, from then on every launch of the slot overwrites it; read copies the
- * stamps of the LAST launch: rows = grid + 1 rows of 16 words, word k = %globaltimer in ns (comparable across
+ * stamps of the LAST launch: rows = grid + 2 rows of 16 words, word k = %globaltimer in ns (comparable across
  * the SMs and GPUs of one box), word 8 + k = clock64 of that SM.  Rows [0, grid) are the CTAs: 0 entry,
  * 1 previous launch complete (griddepcontrol.wait over), 2 theta staged, 3 first panel landed, 4 last panel
  * consumed by every warp, 5 partial row written + ticket taken.  Row `grid` is the last CTA's tail: 0 ticket
  * won (word 7 = its CTA id), 1 sum of the grid's partial rows done, 2 peers' partials received and summed,
- * 3 model epilogue / leapfrog tail written.  read(out = NULL) only returns the row count. */
+ * 3 model epilogue / leapfrog tail written.  Row grid + 1 refines the tail (word k only): 0 acquire fence after the
+ * ticket, 1 first batch of partial rows loaded, 2 sums written, 3 epilogue: block sums + value done, 4 gradient and
+ * leapfrog tail written.  read(out = NULL) only returns the row count. */
 int b200glm_timeline_enable(b200glm_handle* h, int32_t slot, int32_t on);
 int b200glm_timeline_read(b200glm_handle* h, int32_t slot, uint64_t* out, int32_t* rows);
 /* Roofline denominators measured on `device` in the caller's process (either pointer may be NULL):

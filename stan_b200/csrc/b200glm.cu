@@ -71,7 +71,8 @@ struct Slot {
   double* inv_metric = nullptr;  // P
   double* partials = nullptr;    // grid * pstride
   unsigned int* ticket = nullptr;
-  double* r_out = nullptr;       // n_panels*32 (G > 0)
+  double* r_out = nullptr;       // n_panels*32 (G > 0, unfused group path)
+  double* gpart = nullptr;       // grid * Gcs (fused group path)
   double* lik = nullptr;         // P + 2
   double* result = nullptr;      // P + 2
   double* theta_used = nullptr;  // P
@@ -111,6 +112,9 @@ struct b200glm_handle {
   double* panels = nullptr;
   long long* seg_ptr = nullptr;  // G+1 (device)
   int grid = 0, n_stages = 0, stage_a = 0;
+  int group_fused = 0, Gcs = 0;   // fused group path (narrow kernel, G > 0): see KernelParams
+  int4* gmeta = nullptr;          // G entries (device)
+  int* cta_g0 = nullptr;          // grid entries (device)
   int state_smem = 0;  // the kernels keep the chain state + likelihood sums in shared memory for the epilogue
   size_t smem_bytes = 0;
   int cpl = 0;
@@ -121,6 +125,7 @@ struct b200glm_handle {
   double lgamma_sum_total = 0.0;
   bool bad_y = false;        // any shard holds an out-of-range y (after b200glm_comm_init / set_shard_constants_total)
   bool bad_y_local = false;  // this shard does
+  bool tl_repeat = false;   // B200GLM_TL_REPEAT=1 (timeline runs only): the last CTA sums the partial rows twice
   bool inline_theta = true; // B200GLM_NO_INLINE_THETA=1: always upload theta with a host-to-device copy (A/B runs)
   bool host_mirror = true;  // B200GLM_NO_HOST_MIRROR=1: fetch results with a device-to-host copy + stream sync (A/B runs)
   bool pdl = true;          // B200GLM_NO_PDL=1 in the environment turns programmatic dependent launch off (A/B runs)
@@ -203,10 +208,11 @@ kernel_fn handle_kernel(const b200glm_handle* h) {
   return h->wide ? pick_wide_kernel(h->d.family, h->panel_rows, h->spw, h->spc) : pick_kernel(h->d.family, h->cpl);
 }
 
-size_t fixed_smem_bytes(int K, int G, int stage_a, int S, int P_state = 0) {
+size_t fixed_smem_bytes(int K, int G, int stage_a, int S, int P_state = 0, int Gcs = 0) {
   const int Kpad = (K + 3) & ~3;
   size_t b = 0;
   if (P_state) b += (size_t)state_smem_doubles(P_state) * 8;   // on-chip chain state
+  b += (size_t)NUM_CONSUMER_WARPS * Gcs * 8;                   // fused group path: per-warp group sums
   b += (size_t)Kpad * 8;                                 // sbeta
   b += (size_t)NUM_CONSUMER_WARPS * 32 * 8;              // sr
   b += (size_t)NUM_CONSUMER_WARPS * (Kpad + 4) * 8;      // red
@@ -248,7 +254,7 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
   p.Kc = h->Kc;
   p.J = h->J;
   p.mode = mode;
-  p.fuse_finish = ((h->d.world <= 1 || h->peer_on) && h->d.G == 0) ? 1 : 0;
+  p.fuse_finish = ((h->d.world <= 1 || h->peer_on) && (h->d.G == 0 || h->group_fused)) ? 1 : 0;
   if (h->peer_on) {
     int slot_idx = 0;
     for (size_t i = 0; i < h->slots.size(); ++i)
@@ -273,10 +279,16 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
   p.pstride = partial_stride(h->d.K);
   p.ticket = s->ticket;
   p.r_out = s->r_out;
+  p.group_fused = h->group_fused;
+  p.Gcs = h->Gcs;
+  p.gpart = s->gpart;
+  p.gmeta = h->gmeta;
+  p.cta_g0 = h->cta_g0;
   p.lik = s->lik;
   p.result = s->result;
   p.theta_used = s->theta_used;
   p.tl = s->tl;
+  p.tl_repeat = (s->tl && h->tl_repeat) ? 1 : 0;
   ModelConst& mc = p.mc;
   mc.family = h->d.family;
   mc.K = h->d.K;
@@ -324,8 +336,9 @@ int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian,
     p.host_out = s->h_out_dev;
     p.host_seq = ++s->host_seq;
   }
-  p.peer_in_main = (exchange && h->d.G == 0) ? 1 : 0;
-  p.peer_in_finish = (exchange && h->d.G > 0) ? 1 : 0;
+  const bool sums_in_main = h->d.G == 0 || h->group_fused;   // the likelihood sums are complete when the main kernel ends
+  p.peer_in_main = (exchange && sums_in_main) ? 1 : 0;
+  p.peer_in_finish = (exchange && !sums_in_main) ? 1 : 0;
   if (need_likelihood && rows_anywhere) {
     // Programmatic dependent launch: this launch's CTAs may take SMs (barrier set-up, first TMA loads of X) while
     // the previous launch on the stream is still in its one-CTA epilogue; the kernels order every read of that
@@ -343,7 +356,7 @@ int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian,
     cfg.numAttrs = 1;
     CUDA_TRY(h, cudaLaunchKernelEx(&cfg, fn, p));
     h->launches++;
-    if (h->d.G > 0) {
+    if (h->d.G > 0 && !h->group_fused) {
       const int gb = std::min(h->d.G, 8 * 148);   // 8 CTAs of 256 threads are resident per SM
       group_reduce_kernel<<<gb, 256, 0, s->stream>>>(s->r_out, h->seg_ptr, h->d.G, s->lik + 2);
       h->launches++;
@@ -502,6 +515,7 @@ void b200glm_destroy(b200glm_handle* h) {
     cudaFree(s->partials);
     cudaFree(s->ticket);
     cudaFree(s->r_out);
+    cudaFree(s->gpart);
     cudaFree(s->lik);
     cudaFree(s->result);
     cudaFree(s->theta_used);
@@ -528,6 +542,8 @@ void b200glm_destroy(b200glm_handle* h) {
   cudaFree(h->mbox);
   cudaFree(h->panels);
   cudaFree(h->seg_ptr);
+  cudaFree(h->gmeta);
+  cudaFree(h->cta_g0);
   delete h;
 }
 
@@ -570,6 +586,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   if (!(d.prior_alpha_sd > 0) || !(d.prior_beta_sd > 0)) return fail(B200GLM_INVALID, "prior scales must be > 0");
   if (d.n_slots < 1) h->d.n_slots = 1;
   if (const char* e = std::getenv("B200GLM_NO_PDL")) h->pdl = !(e[0] == '1');
+  if (const char* e = std::getenv("B200GLM_TL_REPEAT")) h->tl_repeat = (e[0] == '1');
   if (const char* e = std::getenv("B200GLM_NO_INLINE_THETA")) h->inline_theta = !(e[0] == '1');
   if (const char* e = std::getenv("B200GLM_NO_HOST_MIRROR")) h->host_mirror = !(e[0] == '1');
   h->P = (d.G > 0 ? 2 + d.G : 1) + d.K + (fam_has_scale(d.family) ? 1 : 0);
@@ -592,10 +609,33 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   // launch geometry
   h->grid = d.grid_ctas > 0 ? d.grid_ctas : prop.multiProcessorCount;
   h->stage_a = (d.G > 0 && d.G <= SMEM_A_MAX_GROUPS) ? 1 : 0;
-  // on-chip chain state for the fused epilogue: G == 0 (the group path finishes in its own launch), <= 32 KB
-  h->state_smem = (d.G == 0 && (size_t)state_smem_doubles(P) * 8 <= 32768) ? 1 : 0;
-  const int P_state = h->state_smem ? P : 0;
+  // on-chip chain state for the fused epilogue (theta, half-updated momentum, old gradient, likelihood sums)
+  h->state_smem = (size_t)state_smem_doubles(P) * 8 <= 49152 ? 1 : 0;
+  int P_state = h->state_smem ? P : 0;
   const size_t max_dyn = (size_t)prop.sharedMemPerBlockOptin - 1024;  // static scratch + slack
+  // narrow kernel: ring stages for the handle's current (stage_a, state_smem, group_fused / Gcs); called again after the
+  // group sort has decided whether the group path is fused
+  auto config_narrow = [&]() -> bool {
+    const size_t tile_bytes = (size_t)h->C * PANEL_ROWS * 8;
+    auto stages_for = [&](int p_state) {
+      int S = MAX_STAGES;
+      while (S > 0 && fixed_smem_bytes(d.K, d.G, h->stage_a, S, p_state, h->group_fused ? h->Gcs : 0)
+                              + (size_t)S * tile_bytes > max_dyn)
+        --S;
+      if (S > NUM_CONSUMER_WARPS) S = (S / NUM_CONSUMER_WARPS) * NUM_CONSUMER_WARPS;  // stage <-> warp ownership
+      return S;
+    };
+    int S = stages_for(h->state_smem ? P : 0);
+    if (h->state_smem && S < NUM_CONSUMER_WARPS && stages_for(0) > S) {   // the ring comes first
+      h->state_smem = 0;
+      S = stages_for(0);
+    }
+    if (S < 1) return false;
+    h->n_stages = S;
+    h->smem_bytes = fixed_smem_bytes(d.K, d.G, h->stage_a, S, h->state_smem ? P : 0, h->group_fused ? h->Gcs : 0)
+                    + (size_t)S * tile_bytes;
+    return true;
+  };
   if (!h->wide) {
     h->Cpad = h->C;
     const int need_cpl = std::max(1, (d.K + 7) / 8);
@@ -606,13 +646,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
         break;
       }
     if (!h->cpl) return fail(B200GLM_INVALID, "K too large");
-    const size_t tile_bytes = (size_t)h->C * PANEL_ROWS * 8;
-    int S = MAX_STAGES;
-    while (S > 0 && fixed_smem_bytes(d.K, d.G, h->stage_a, S, P_state) + (size_t)S * tile_bytes > max_dyn) --S;
-    if (S < 1) return fail(B200GLM_INVALID, "panel does not fit in shared memory");
-    if (S > NUM_CONSUMER_WARPS) S = (S / NUM_CONSUMER_WARPS) * NUM_CONSUMER_WARPS;  // stage <-> warp ownership
-    h->n_stages = S;
-    h->smem_bytes = fixed_smem_bytes(d.K, d.G, h->stage_a, S, P_state) + (size_t)S * tile_bytes;
+    if (!config_narrow()) return fail(B200GLM_INVALID, "panel does not fit in shared memory");
   } else {
     // sub-panels: 8 warp steps wide unless 4 steps already give every warp at most one sub-panel
     const int WR = h->panel_rows, cps = wide_cps(WR);
@@ -624,16 +658,25 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     h->spw = (h->J + WIDE_CONSUMER_WARPS - 1) / WIDE_CONSUMER_WARPS;
     if (!pick_wide_kernel(d.family, WR, h->spw, h->spc))
       return fail(B200GLM_INVALID, "K too large for the wide kernel (K <= 3000)");
-    const size_t fixed = wide_fixed_doubles(WR, h->J, h->Kc, d.G, h->stage_a, P_state) * 8;
     const size_t slot_bytes = (size_t)h->Kc * WR * 8;
-    int T = fixed < max_dyn ? (int)((max_dyn - fixed) / (slot_bytes + 16)) : 0;
-    if (T > WIDE_MAX_SLOTS) T = WIDE_MAX_SLOTS;
+    size_t fixed = 0;
+    int T = 0;
+    for (;;) {   // the ring comes first: drop the on-chip state if two row panels would not fit with it
+      fixed = wide_fixed_doubles(WR, h->J, h->Kc, d.G, h->stage_a, P_state) * 8;
+      T = fixed < max_dyn ? (int)((max_dyn - fixed) / (slot_bytes + 16)) : 0;
+      if (T > WIDE_MAX_SLOTS) T = WIDE_MAX_SLOTS;
+      if (T >= 2 * h->J || !P_state) break;
+      P_state = 0;
+      h->state_smem = 0;
+    }
     if (T < 2 * h->J) return fail(B200GLM_INVALID, "two row panels do not fit in shared memory (K too large)");
     h->n_stages = T;
     h->smem_bytes = fixed + (size_t)T * (slot_bytes + 16);
   }
+  // the attribute belongs to the kernel, not to the handle: always the device maximum, so that handles of
+  // different shapes sharing one instantiation cannot lower it for each other
   kernel_fn fn = handle_kernel(h);
-  CREATE_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CREATE_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - 1024));
 
   // ---- data upload + re-layout ----
   cudaStream_t st = nullptr;
@@ -725,6 +768,41 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
       std::vector<long long> cursor(seg.begin(), seg.end() - 1);
       for (long long i = 0; i < d.N; ++i) perm[cursor[h_group[i] - 1]++] = i;
     }
+    // Fused group path (narrow kernel): CTA c owns the contiguous panels [c n_panels / grid, (c + 1) n_panels / grid)
+    // of the SORTED rows; it is taken when no CTA meets more than 512 groups (8 warps x Gcs doubles of smem).
+    if (!h->wide && d.N > 0 && !std::getenv("B200GLM_NO_GROUP_FUSION")) {
+      std::vector<int> g0(h->grid, 0), gn(h->grid, 0);
+      auto group_of_row = [&](long long r) {   // 0-based group of sorted row r
+        return (int)(std::upper_bound(seg.begin(), seg.end(), r) - seg.begin()) - 1;
+      };
+      int Gc = 1;
+      for (int c = 0; c < h->grid; ++c) {
+        const long long pb = ((long long)c * h->n_panels) / h->grid, pe = ((long long)(c + 1) * h->n_panels) / h->grid;
+        if (pe <= pb) continue;
+        const long long rb = pb * PANEL_ROWS, re = std::min<long long>(pe * PANEL_ROWS, d.N);
+        g0[c] = group_of_row(rb);
+        gn[c] = group_of_row(re - 1) - g0[c] + 1;
+        Gc = std::max(Gc, gn[c]);
+      }
+      if (Gc <= 512) {
+        h->group_fused = 1;
+        h->Gcs = (Gc + 1) & ~1;
+        std::vector<int4> meta(d.G);
+        for (int g = 0; g < d.G; ++g) meta[g] = make_int4(1, 0, 0, 0);   // empty: lo > hi
+        for (int c = 0; c < h->grid; ++c)
+          for (int j = 0; j < gn[c]; ++j) {
+            const int g = g0[c] + j;
+            if (seg[g + 1] == seg[g]) continue;                            // no rows: stays empty
+            if (meta[g].x > meta[g].y) meta[g] = make_int4(c, c, c * h->Gcs + j, 0);
+            else meta[g].y = c;    // later CTAs: the group is their first one (entry 0)
+          }
+        CREATE_TRY(cudaMalloc(&h->gmeta, sizeof(int4) * d.G));
+        CREATE_TRY(cudaMemcpy(h->gmeta, meta.data(), sizeof(int4) * d.G, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMalloc(&h->cta_g0, sizeof(int) * h->grid));
+        CREATE_TRY(cudaMemcpy(h->cta_g0, g0.data(), sizeof(int) * h->grid, cudaMemcpyHostToDevice));
+        if (!config_narrow()) return fail(B200GLM_INVALID, "panel does not fit in shared memory");
+      }
+    }
     CREATE_TRY(cudaMalloc(&h->seg_ptr, sizeof(long long) * (d.G + 1)));
     CREATE_TRY(cudaMemcpy(h->seg_ptr, seg.data(), sizeof(long long) * (d.G + 1), cudaMemcpyHostToDevice));
     if (d.N > 0) {
@@ -794,7 +872,9 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     CREATE_TRY(cudaMalloc(&s->partials, sizeof(double) * (size_t)h->grid * pstride));
     CREATE_TRY(cudaMalloc(&s->ticket, sizeof(unsigned int)));
     CREATE_TRY(cudaMemset(s->ticket, 0, sizeof(unsigned int)));
-    if (d.G > 0 && h->n_panels > 0) CREATE_TRY(cudaMalloc(&s->r_out, sizeof(double) * h->n_panels * h->panel_rows));
+    if (d.G > 0 && h->n_panels > 0 && !h->group_fused)
+      CREATE_TRY(cudaMalloc(&s->r_out, sizeof(double) * h->n_panels * h->panel_rows));
+    if (h->group_fused) CREATE_TRY(cudaMalloc(&s->gpart, sizeof(double) * (size_t)h->grid * h->Gcs));
     CREATE_TRY(cudaMalloc(&s->lik, sizeof(double) * (P + 2)));
     CREATE_TRY(cudaMemset(s->lik, 0, sizeof(double) * (P + 2)));
     CREATE_TRY(cudaMalloc(&s->result, sizeof(double) * (P + 2)));
@@ -1351,8 +1431,8 @@ int b200glm_timeline_enable(b200glm_handle* h, int32_t slot, int32_t on) {
   CUDA_TRY(h, cudaSetDevice(h->d.device));
   CUDA_TRY(h, cudaStreamSynchronize(s->stream));
   if (on && !s->tl) {
-    CUDA_TRY(h, cudaMalloc(&s->tl, sizeof(unsigned long long) * 16 * (h->grid + 1)));
-    CUDA_TRY(h, cudaMemset(s->tl, 0, sizeof(unsigned long long) * 16 * (h->grid + 1)));
+    CUDA_TRY(h, cudaMalloc(&s->tl, sizeof(unsigned long long) * 16 * (h->grid + 2)));
+    CUDA_TRY(h, cudaMemset(s->tl, 0, sizeof(unsigned long long) * 16 * (h->grid + 2)));
   } else if (!on && s->tl) {
     cudaFree(s->tl);
     s->tl = nullptr;
@@ -1364,7 +1444,7 @@ int b200glm_timeline_read(b200glm_handle* h, int32_t slot, uint64_t* out, int32_
   int rc = validate_slot(h, slot);
   if (rc) return rc;
   Slot* s = h->slots[slot];
-  if (rows) *rows = h->grid + 1;
+  if (rows) *rows = h->grid + 2;
   if (!out) return B200GLM_OK;
   if (!s->tl) {
     h->set_error("b200glm_timeline_enable was not called for this slot");
@@ -1372,7 +1452,7 @@ int b200glm_timeline_read(b200glm_handle* h, int32_t slot, uint64_t* out, int32_
   }
   CUDA_TRY(h, cudaSetDevice(h->d.device));
   CUDA_TRY(h, cudaStreamSynchronize(s->stream));
-  CUDA_TRY(h, cudaMemcpy(out, s->tl, sizeof(unsigned long long) * 16 * (h->grid + 1), cudaMemcpyDeviceToHost));
+  CUDA_TRY(h, cudaMemcpy(out, s->tl, sizeof(unsigned long long) * 16 * (h->grid + 2), cudaMemcpyDeviceToHost));
   return B200GLM_OK;
 }
 

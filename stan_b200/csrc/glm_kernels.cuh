@@ -280,6 +280,7 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
   }
 
   __threadfence();
+  if (tid == 0) tl_stamp(p, grid + 1, 0);        // acquire fence after the ticket
   // Sum of the grid's partial rows, column by column, in a FIXED tree (bitwise reproducible): the rows are cut
   // into R contiguous segments taken by R adjacent lanes (R = 1, 2, 4 or 8, as many as the CTA has threads for),
   // each lane keeps GS_DEPTH independent accumulators so that many L2 loads are in flight per thread (this loop is
@@ -291,6 +292,13 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
   int R = 1;
   while (R < 8 && 2 * R * n_sums <= nt) R *= 2;
   const int seg_len = (grid + R - 1) / R;
+  // measurement only: tl_repeat makes the sum run twice (same result), the first pass stamped on its own, to
+  // separate what a cold pass costs (instruction fetch, first touch of the partial rows) from a warm one
+  for (int rep = (p.tl && p.tl_repeat) ? 0 : 1; rep < 2; ++rep) {
+  if (rep == 1 && p.tl && p.tl_repeat) {
+    __syncthreads();
+    if (tid == 0) tl_stamp(p, grid + 1, 5);      // end of the cold pass
+  }
   for (int base = 0; base < n_sums; base += nt / R) {       // warp-uniform trip count (nt and R are multiples)
     const int j = base + tid / R, r = tid & (R - 1);
     double a[GS_DEPTH];
@@ -308,6 +316,7 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
       for (int u = 0; u < GS_DEPTH - 1; ++u)
         if (b + u < b1) a[u] += __ldcg(src + (size_t)(b + u) * p.pstride);
     }
+    if (tid == 0 && base == 0) tl_stamp(p, grid + 1, 1);   // first batch of partial rows loaded
 #pragma unroll
     for (int w = GS_DEPTH / 2; w >= 5; w /= 2) {            // 40 -> 20 -> 10 -> 5 partial sums, fixed pairing
 #pragma unroll
@@ -325,6 +334,20 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
     else if (G == 0)
       lik[0] = v;
   }
+  }
+  if (p.group_fused) {
+    // per-group residual sums = the gradient wrt a[g] (rvalue(a, index_multi(group)) scatters r back, rvalue.hpp:154-172)
+    for (int g = tid; g < G; g += nt) {
+      const int4 m = __ldg(p.gmeta + g);
+      double v = 0.0;
+      if (m.x <= m.y) {
+        v = __ldcg(p.gpart + m.z);
+        for (int c = m.x + 1; c <= m.y; ++c) v += __ldcg(p.gpart + (size_t)c * p.Gcs);
+      }
+      lik[2 + g] = v;
+    }
+  }
+  if (tid == 0) tl_stamp(p, grid + 1, 2);        // sums written
   if (tid == 0) *p.ticket = 0u;
   if (fam_has_scale(FAMILY) && tid == 0) lik[P - 1] = 0.0;  // sigma | phi entry is derived in finish()
   if (FAMILY != FAM_NEG_BINOMIAL_2_LOG && tid == 32) lik[P + 1] = 0.0;
@@ -365,11 +388,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
   double* sa = red + NUM_CONSUMER_WARPS * (Kpad + 4);                   // G (optional)
   double* st_base = sa + (p.stage_a_in_smem ? ((G + 1) & ~1) : 0);      // chain state (optional)
   const StateSmem st = carve_state_smem(st_base, P, p.state_in_smem);
-  double* after_a = st_base + (p.state_in_smem ? state_smem_doubles(P) : 0);
+  double* sgw = st_base + (p.state_in_smem ? state_smem_doubles(P) : 0);  // 8 warps x Gcs group sums (fused group path)
+  double* after_a = sgw + (p.group_fused ? NUM_CONSUMER_WARPS * p.Gcs : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(after_a);            // S
   uint64_t* empty_bar = full_bar + S;                                   // S
   __shared__ double sh_scratch[64];
   __shared__ int sh_is_last;
+  const bool GF = p.group_fused != 0;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -425,6 +450,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
 
   const long long n_panels = p.n_panels;
   const int grid = gridDim.x;
+  // this CTA's panels: n = 0 .. p_count-1 -> panel p_base + n * p_stride.  Interleaved over the grid by default; one
+  // contiguous range per CTA on the fused group path (rows are sorted by group, so a range meets few groups)
+  const long long p_base = GF ? ((long long)blockIdx.x * n_panels) / grid : (long long)blockIdx.x;
+  const long long p_stride = GF ? 1 : grid;
+  const long long p_count = GF ? ((long long)(blockIdx.x + 1) * n_panels) / grid - p_base
+                               : (n_panels > blockIdx.x ? (n_panels - blockIdx.x + grid - 1) / grid : 0);
 
   double acc[CPL];
 #pragma unroll
@@ -438,7 +469,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
       const uint32_t bytes = (uint32_t)tile_doubles * 8u;
       int s = 0;
       uint32_t round = 0;
-      for (long long pi = blockIdx.x; pi < n_panels; pi += grid) {
+      for (long long n = 0; n < p_count; ++n) {
+        const long long pi = p_base + n * p_stride;
         if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
         mbar_arrive_expect_tx(&full_bar[s], bytes);
         tma_load_1d(tiles + (size_t)s * tile_doubles, p.panels + (size_t)pi * tile_doubles, bytes,
@@ -466,9 +498,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
     for (int m = 0; m < 8; ++m) off[m] = rg + 4 * (m ^ cgl);
     double* my_sr = sr + warp * 32;
 
-    long long n = warp;  // index of this panel in the CTA's sequence
-    for (long long pi = (long long)blockIdx.x + (long long)warp * grid; pi < n_panels;
-         pi += (long long)W_act * grid, n += W_act) {
+    // fused group path: running residual sum of the group this warp is in (flushed to the warp's smem row when the
+    // group changes: the warp meets groups in ascending order, so once per group)
+    const int g_base = GF ? p.cta_g0[blockIdx.x] : 0;
+    double* my_sg = sgw + warp * p.Gcs;
+    int cur_g = -1;
+    double rg_acc = 0.0;
+    auto flush_group = [&]() {
+      const double v = warp_sum(rg_acc);
+      if (lane == 0 && cur_g >= 0) my_sg[cur_g - g_base] += v;
+      rg_acc = 0.0;
+    };
+    if (GF) {
+      for (int j = lane; j < p.Gcs; j += 32) my_sg[j] = 0.0;
+      __syncwarp();
+    }
+
+    for (long long n = warp; n < p_count; n += W_act) {   // n = index of this panel in the CTA's sequence
+      const long long pi = p_base + n * p_stride;
       const int s = (int)(n % S);
       const uint32_t parity = (uint32_t)((n / S) & 1);
       mbar_wait(&full_bar[s], parity);
@@ -490,8 +537,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
       for (; c < K; ++c) e0 = fma(tile[c * 32 + (lane ^ ((c & 3) << 2))], sbeta[c], e0);
       double eta = (e0 + e1) + (e2 + e3);
       const double y = tile[ycol];
+      int gi = -1;
       if (G > 0) {
-        const int gi = (int)tile[gcol] - 1;
+        gi = (int)tile[gcol] - 1;
         const bool gok = gi >= 0 && gi < G;
         eta += p.stage_a_in_smem ? sa[gok ? gi : 0] : theta_at(2 + (gok ? gi : 0));
       } else {
@@ -508,7 +556,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
       lp_acc += lp_i;
       r_acc += r_i;
       if (FAMILY == FAM_NEG_BINOMIAL_2_LOG) x_acc += x_i;
-      if (G > 0) p.r_out[pi * PANEL_ROWS + lane] = r_i;
+      if (GF) {
+        const int g_first = __shfl_sync(0xffffffffu, gi, 0);          // row 0 of a panel always exists
+        if (__all_sync(0xffffffffu, !valid || gi == g_first)) {
+          if (g_first != cur_g) {
+            flush_group();
+            cur_g = g_first;
+          }
+          rg_acc += r_i;
+        } else {
+          // a panel that straddles group boundaries (rare: rows are sorted): one masked warp sum per group, in row order
+          unsigned todo = __ballot_sync(0xffffffffu, valid);
+          while (todo) {
+            const int gsel = __shfl_sync(0xffffffffu, gi, __ffs(todo) - 1);
+            const bool mine = valid && gi == gsel;
+            const double v = warp_sum(mine ? r_i : 0.0);
+            if (lane == 0) my_sg[gsel - g_base] += v;
+            todo &= ~__ballot_sync(0xffffffffu, mine);
+          }
+        }
+      } else if (G > 0) {
+        p.r_out[pi * PANEL_ROWS + lane] = r_i;
+      }
 
       // ---- phase 2: X^T r from the same smem tile ----
       my_sr[lane] = r_i;
@@ -530,6 +599,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
       if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
 
+    if (GF) flush_group();
     // ---- per-warp reduction of the private accumulators ----
 #pragma unroll
     for (int s2 = 0; s2 < CPL; ++s2) {
@@ -549,6 +619,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
   } else {
     // idle consumer warp (fewer stages than warps): contributes zeros to the CTA reduction
     for (int j = lane; j < Kpad + 4; j += 32) red[warp * (Kpad + 4) + j] = 0.0;
+    if (GF)
+      for (int j = lane; j < p.Gcs; j += 32) sgw[warp * p.Gcs + j] = 0.0;
   }
   __syncthreads();
   if (tid == 0) tl_stamp(p, blockIdx.x, 4);      // every warp has consumed its last panel
@@ -561,6 +633,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
 #pragma unroll
     for (int w = 0; w < NUM_CONSUMER_WARPS; ++w) v += red[w * (Kpad + 4) + src];
     my_part[j] = v;
+  }
+  if (GF) {   // this CTA's group sums, warps folded in fixed order
+    double* my_g = p.gpart + (size_t)blockIdx.x * p.Gcs;
+    for (int j = tid; j < p.Gcs; j += NUM_THREADS) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < NUM_CONSUMER_WARPS; ++w) v += sgw[w * p.Gcs + j];
+      my_g[j] = v;
+    }
   }
   cross_cta_reduce_and_finish<FAMILY>(p, sh_scratch, &sh_is_last, st);
 }

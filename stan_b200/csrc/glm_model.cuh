@@ -18,6 +18,12 @@
 
 namespace b200glm {
 
+#if !defined(__CUDACC__)
+struct int4 {   // the host build (tests/host) has no CUDA vector types
+  int x, y, z, w;
+};
+#endif
+
 enum { MODE_THETA = 0, MODE_LEAPFROG = 1 };
 enum { ST_OK = 0, ST_DOMAIN = 1, ST_PEER_TIMEOUT = 2 };
 
@@ -76,10 +82,19 @@ struct KernelParams {
   double* partials;         // [grid][pstride]: [0,K) beta grads, [K] lp-sum, [K+1] r-sum
   int pstride;
   unsigned int* ticket;
-  double* r_out;            // G > 0: residual per (sorted) row
+  double* r_out;            // G > 0, unfused group path: residual per (sorted) row
+  // G > 0, fused group path (narrow kernel): rows are sorted by group and every CTA owns a CONTIGUOUS panel range,
+  // so a CTA meets few groups: it accumulates their residual sums on chip and writes them to gpart[cta][0, Gcs);
+  // the last CTA folds them in CTA order through gmeta[g] = {first CTA, last CTA, index of the first CTA's entry}
+  // (in every later CTA the group is that CTA's first: entry 0).  cta_g0[c] = first group (0-based) of CTA c's range.
+  int group_fused, Gcs;
+  double* gpart;
+  const int4* gmeta;
+  const int* cta_g0;
   double* lik;              // [P] likelihood gradient aligned with theta, [P] lp-sum, [P+1] spare
   double* result;           // [lp, grad(P), status]
   double* theta_used;       // P doubles: the theta this launch evaluated (q_new in leapfrog mode)
+  int tl_repeat;            // measurement only, see cross_cta_reduce_and_finish
   unsigned long long* tl;   // NULL, or the per-phase time stamps of this launch (b200glm_timeline_*): [grid + 1][16]
   // Host-facing calls (b200glm_log_prob_grad, b200glm_leapfrog): the epilogue also writes its outputs straight into
   // pinned host memory -- [result (P + 2)] [state (3P + 1)] [sequence word] -- and the host polls the sequence word,
@@ -124,6 +139,20 @@ __device__ inline void host_out_publish(const KernelParams& p) {
   }
 #else
   (void)p;
+#endif
+}
+
+// measurement only (b200glm_timeline_*): stamp k of the extra tail row
+__device__ inline void finish_stamp(const KernelParams& p, int k) {
+#if defined(__CUDACC__)
+  if (p.tl && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.tl[(size_t)(gridDim.x + 1) * 16 + k] = t;
+  }
+#else
+  (void)p;
+  (void)k;
 #endif
 }
 
@@ -244,6 +273,7 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
     }
   }
   const bool domain = !(isfinite(lp) && n_bad == 0.0);
+  finish_stamp(p, 3);                             // block sums + value done
 
   // ---- gradient wrt unconstrained theta and, in leapfrog mode, the second half of the step
   //      (expl_leapfrog.hpp:28-32 end_update_p; base_hamiltonian.hpp:64-69), one thread per entry ----
@@ -302,6 +332,7 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
       }
     }
   }
+  finish_stamp(p, 4);                             // gradient + leapfrog tail written
   if (tid == 0) {
     const double status = domain ? (double)ST_DOMAIN : (double)ST_OK;
     p.result[0] = lp;

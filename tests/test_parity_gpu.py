@@ -330,3 +330,56 @@ def test_full_size_config2_against_reference():
     assert rel_err(lp, lp_r) < TOL, (lp, lp_r)
     assert rel_err_vec(g, g_r) < TOL
     m.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# Fused group path (SURVEY 2.3 contract for a16: 1 read of X, 0 N-vector traffic, 1 launch): rows are sorted by
+# group, every CTA owns a contiguous panel range and accumulates its few groups' residual sums on chip.
+# ---------------------------------------------------------------------------------------------
+GROUP_SHAPES = [
+    # family, N, K, G, expect_fused
+    ("poisson_log", 80_000, 50, 1000, True),
+    ("poisson_log", 5_000, 8, 3000, True),        # ~19 groups per panel: the boundary-panel path on every panel
+    ("normal_id", 9_999, 31, 17, True),
+    ("bernoulli_logit", 30, 3, 50, True),         # most groups have no rows at all
+    ("neg_binomial_2_log", 20_000, 9, 37, True),
+    ("binomial_logit", 12_345, 6, 5, True),
+    ("poisson_log", 148 * 32 * 40, 4, 100_000, False),   # a CTA's range meets > 512 groups: unfused fallback
+]
+
+
+@pytest.mark.parametrize("fam,N,K,G,fused", GROUP_SHAPES)
+def test_group_path_fused_matches_oracle_and_unfused(fam, N, K, G, fused, monkeypatch):
+    d = make_glm_data(fam, N, K, G)
+    kw = {"trials": d["trials"]} if fam == "binomial_logit" else {}
+    orc = oracle_for(fam, d, G, **kw)
+    m = GLMModel(fam, d["X"], d["y"], d["group"], G, **kw)
+    monkeypatch.setenv("B200GLM_NO_GROUP_FUSION", "1")
+    m_unfused = GLMModel(fam, d["X"], d["y"], d["group"], G, **kw)
+    monkeypatch.delenv("B200GLM_NO_GROUP_FUSION")
+    for th in theta_points(m.P, n_random=2, scale=0.1):
+        n0 = m.launch_count()
+        lp, g = m.log_prob_grad(th)
+        assert m.launch_count() - n0 == (1 if fused else 3)     # one launch, no N-vector of residuals
+        lp_r, g_r = orc.log_prob_grad(th)
+        assert rel_err(lp, lp_r) < TOL, (lp, lp_r)
+        assert rel_err_vec(g, g_r) < TOL
+        lp_u, g_u = m_unfused.log_prob_grad(th)
+        assert rel_err(lp, lp_u) < 1e-13 and rel_err_vec(g, g_u) < 1e-13
+        assert rel_err(m.log_prob(th, False, True), orc.log_prob(th, False, True)) < TOL
+    a, b = m.log_prob_grad(th), m.log_prob_grad(th)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])          # deterministic
+    # leapfrog steps stay on the device and follow the oracle's integrator
+    from oracle.oracle import PortOracle
+    po = PortOracle(fam, d["X"], d["y"], d["group"], G, **kw)
+    rng = np.random.default_rng(3)
+    th, p0 = 0.05 * rng.standard_normal(m.P), rng.standard_normal(m.P)
+    lp, g = m.log_prob_grad(th)
+    m.set_state(th, p0, -g, -lp)
+    q, p, gg, V = th, p0, -g, -lp
+    for _ in range(3):
+        q1, p1, g1, V1 = m.leapfrog(1e-3)
+        q, p, gg, V = po.leapfrog(1e-3, np.ones(m.P), q, p, gg, V)
+    assert np.max(np.abs(q1 - q)) < 1e-12 and rel_err(V1, V) < TOL and rel_err_vec(g1, gg) < TOL
+    m.close()
+    m_unfused.close()

@@ -76,9 +76,9 @@ def main():
             m.leapfrog_async(1e-4)
         m.sync()
         rows.append(m.timeline_read())
-    T = np.stack(rows).astype(np.int64)          # reps x (grid + 1) x 16
-    grid = T.shape[1] - 1
-    cta, tail = T[:, :grid, :], T[:, grid, :]
+    T = np.stack(rows).astype(np.int64)          # reps x (grid + 2) x 16
+    grid = T.shape[1] - 2
+    cta, tail, fine = T[:, :grid, :], T[:, grid, :], T[:, grid + 1, :]
     t0 = cta[:, :, 0].min(axis=1)                # first CTA entry of the launch
     med = lambda x: float(np.median(x))          # noqa: E731
     rel = lambda x: x - t0[:, None] if x.ndim == 2 else x - t0   # noqa: E731
@@ -99,6 +99,12 @@ def main():
             "tail_grid_sum_done": med(rel(tail[:, 1])),
             "tail_peer_exchange_done": med(rel(tail[:, 2])),
             "tail_finish_done": med(rel(tail[:, 3])),
+            "fine_fence_after_ticket": med(rel(fine[:, 0])),
+            "fine_first_rows_loaded": med(rel(fine[:, 1])),
+            "fine_sums_written": med(rel(fine[:, 2])),
+            "fine_finish_value_done": med(rel(fine[:, 3])),
+            "fine_finish_gradient_written": med(rel(fine[:, 4])),
+            "fine_cold_pass_done": med(rel(fine[:, 5])) if os.environ.get("B200GLM_TL_REPEAT") == "1" else None,
         },
     }
     d = out["ns_since_first_cta_entry"]
@@ -111,6 +117,15 @@ def main():
         "peer exchange": (d["tail_peer_exchange_done"] - d["tail_grid_sum_done"]) / 1e3,
         "finish (epilogue + leapfrog tail)": (d["tail_finish_done"] - d["tail_peer_exchange_done"]) / 1e3,
         "launch total (first entry -> finish)": d["tail_finish_done"] / 1e3,
+    }
+    out["tail_fine_us"] = {
+        "ticket won -> acquire fence": (d["fine_fence_after_ticket"] - d["tail_ticket_won"]) / 1e3,
+        "-> first batch of partial rows loaded": (d["fine_first_rows_loaded"] - d["fine_fence_after_ticket"]) / 1e3,
+        "-> sums written": (d["fine_sums_written"] - d["fine_first_rows_loaded"]) / 1e3,
+        "-> fence + barrier (grid sum done)": (d["tail_grid_sum_done"] - d["fine_sums_written"]) / 1e3,
+        "epilogue: -> block sums + value": (d["fine_finish_value_done"] - d["tail_peer_exchange_done"]) / 1e3,
+        "epilogue: -> gradient + leapfrog tail written": (d["fine_finish_gradient_written"] - d["fine_finish_value_done"]) / 1e3,
+        "epilogue: -> published": (d["tail_finish_done"] - d["fine_finish_gradient_written"]) / 1e3,
     }
     hbm_us = m.bytes_per_gradient() / 7.2e12 * 1e6
     out["shard_hbm_time_us_at_7.2TBps"] = hbm_us
