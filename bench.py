@@ -158,10 +158,25 @@ def run_b200(args):
         ns = min(args.cpu_sample_rows, n_local)
         sample = (X[:, :ns].cpu().numpy().T, y[:ns].cpu().numpy(), grp[:ns].cpu().numpy() if G else None,
                   trials[:ns].cpu().numpy() if trials is not None else None)
+    # parity material (every rank): a row sample of this shard for the CPU checker, and -- memory permitting -- the
+    # whole shard as a second, UNSHARDED handle for the additivity check
+    par_rows = min(args.parity_rows, n_local) if not args.no_parity else 0
+    par_sample = None
+    if par_rows:
+        par_sample = (X[:, :par_rows].cpu().numpy().T, y[:par_rows].cpu().numpy(),
+                      grp[:par_rows].cpu().numpy() if G else None,
+                      trials[:par_rows].cpu().numpy() if trials is not None else None)
+    m_local = None
+    free_b, _tot = torch.cuda.mem_get_info()
+    if world > 1 and par_rows and free_b > 1.3 * 8 * n_local * (K + 3):
+        m_local = GLMModel(family, X.data_ptr(), y.data_ptr(), grp.data_ptr() if G else None, G, data_on_device=True,
+                           N=n_local, K=K, ldx=n_local, device=local_rank,
+                           trials=trials.data_ptr() if trials is not None else None)
     del X, y, grp, trials
     torch.cuda.empty_cache()
 
     P = m.num_params_r()
+    bytes_per_gradient = m.bytes_per_gradient()
     rng = np.random.default_rng(11)
     q0 = 0.05 * rng.standard_normal(P)
     p0 = rng.standard_normal(P)
@@ -221,27 +236,58 @@ def run_b200(args):
         e2e_ms = float(t.item())
     e2e_value = args.steps / (e2e_ms / 1000.0)
 
-    if rank != 0:
+    # ---- parity of what was just timed (every rank takes part; rank 0 reports) ----
+    parity = None
+    if par_sample is not None:
+        parity = parity_record(torch, dist, dev, m, m_local, par_sample, family, G, K, rank, world, local_rank)
+    if m_local is not None:
+        m_local.close()
+    # ---- ESS/s inside NUTS at this configuration (every rank takes part; rank 0 reports) ----
+    ess = None
+    if args.ess_iters > 0 and args.config == 2:
         m.close()
+        m = None
+        torch.cuda.empty_cache()
+        ess = ess_record(args, torch, dist, dev, rank, world, local_rank)
+    read_gbs = None
+    if rank == 0:
+        from stan_b200 import _capi
+        try:
+            read_gbs, _ = _capi.measure_peaks(local_rank, read=True, dmma=False)
+        except Exception:
+            read_gbs = None
+
+    if rank != 0:
+        if m is not None:
+            m.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
     peaks, which = measured_peaks()
-    bytes_per_launch = m.bytes_per_gradient()           # this rank's shard: 8*N*K + 4*N
+    bytes_per_launch = bytes_per_gradient               # this rank's shard: 8*N*K + 4*N
     achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
                 "kernel": f"glm_wide_kernel<{family}>" if K > 256 else f"glm_fused_kernel<{family}>", "algorithmic_bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": ms_per_step}
+    if read_gbs:
+        # the kernel reads X once and writes nothing; `peak` above is the driver's read+write COPY figure, which a
+        # read-only stream can exceed.  The same-process read-only figure is the tighter denominator.
+        roofline["read_only_stream_gbs"] = read_gbs
+        roofline["frac_of_read_only_stream"] = achieved / read_gbs
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as f:
                 tj = json.load(f)
             for ent in tj.get("entries", [tj]):
-                if ent.get("N") == n_local and ent.get("K") == K and ent.get("family", FAMILY) == family:
+                if (ent.get("N") == n_local and ent.get("K") == K and ent.get("family", FAMILY) == family
+                        and ent.get("G", 0) == G and ent.get("kernel", "").startswith(roofline["kernel"].split("<")[0])):
+                    # dram__bytes_read.sum + dram__bytes_write.sum of THIS kernel at THIS shard size from a separate
+                    # `ncu --set full` pass (profiles/README.md); null when no capture of this exact shape exists
                     roofline["traffic"] = ent.get("dram_bytes_per_launch")
+                    roofline["traffic_source"] = ent.get("source")
         except Exception:
             pass
 
@@ -267,11 +313,126 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "parity": parity,
+        "ess": ess,
     }
+    if ess and cpu_baseline and ess.get("b200"):
+        # BASELINE.md section 5 step 3 at config 2: the CPU NUTS arm cannot run to an ESS inside a bench (1.8 s per
+        # gradient per core); the same chains cost the same gradient evaluations on the CPU, so its ESS/s is the
+        # chains' ESS per gradient evaluation times the CPU gradient rate measured above (projection, labelled)
+        b = ess["b200"]
+        ess["reference_cpu_projected"] = {
+            "ess_min_per_s": b["ess_min"] / (b["grad_evals"] / cpu_baseline["value"]), "cores": cpu_baseline["cores"],
+            "how": "ess_min of the chains above / (their gradient evaluations / cpu_baseline grad_evals/s); "
+                   "one chain at a time on one core, as the b200 arm runs one chain at a time on the GPU(s)"}
     print(json.dumps(out))
-    m.close()
+    if m is not None:
+        m.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_record(torch, dist, dev, m, m_local, sample, family, G, K, rank, world, local_rank):
+    """Parity of the handles the bench just timed, checked in the same run:
+    (1) kernel vs CPU checker (the compiled reference when present, else the C port) on a row sample of THIS
+        rank's shard: the likelihood term and its partials through b200glm_glm_lpmf, relative error scaled as in
+        tests/conftest.py; max over ranks;
+    (2) world > 1: shard additivity -- the sharded handle's likelihood term (exchange inside the launch) against the
+        sum over ranks of each shard evaluated by an unsharded handle on the same rows.
+    The bar is north_star's 1e-10."""
+    from stan_b200 import GLMModel
+    from oracle.oracle import PortOracle, RefOracle
+    Xs, ys, gs, ts = sample
+    rng = np.random.default_rng(23)
+    na = max(G, 1)
+    alpha, beta = 0.1 * rng.standard_normal(na), 0.1 * rng.standard_normal(K)
+    sigma = 1.3
+    kw = {"trials": ts} if ts is not None else {}
+    ms = GLMModel(family, np.asfortranarray(Xs), ys, gs, G, device=local_rank, **kw)
+    lp, da, db, dsg = ms.glm_lpmf(alpha if G else alpha[0], beta, sigma)
+    ms.close()
+    if RefOracle.available():
+        kind = "reference"
+        lp_r, da_r, db_r, ds_r = RefOracle.glm_function(family, Xs, ys, alpha if G else alpha[0], beta, sigma,
+                                                        group=gs, G=G, trials=ts)
+        g, g_r = np.concatenate([da, db, [dsg]]), np.concatenate([da_r, db_r, [ds_r]])
+    else:
+        kind = "port"
+        po = PortOracle(family, Xs, ys, gs, G, **kw)
+        th = np.zeros(po.P)
+        lp_r, g_r = po.log_prob_grad(th)
+        mm = GLMModel(family, np.asfortranarray(Xs), ys, gs, G, device=local_rank, **kw)
+        lp, g = mm.log_prob_grad(th)
+        mm.close()
+    sc = np.maximum(np.abs(g_r), np.max(np.abs(g_r)))
+    sc = np.where(sc == 0, 1.0, sc)
+    err_sample = max(abs(lp - lp_r) / max(abs(lp_r), 1e-300), float(np.max(np.abs(g - g_r) / sc)))
+    err_add = None
+    if world > 1:
+        e = torch.tensor([err_sample], device=dev, dtype=torch.float64)
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        err_sample = float(e.item())
+        if m_local is not None:
+            lpl, dal, dbl, dsl = m_local.glm_lpmf(alpha if G else alpha[0], beta, sigma)
+            part = torch.tensor(np.concatenate([[lpl], np.atleast_1d(dal), dbl]), device=dev, dtype=torch.float64)
+            dist.all_reduce(part)
+            lps, das, dbs, dss = m.glm_lpmf(alpha if G else alpha[0], beta, sigma)
+            tot = np.concatenate([[lps], np.atleast_1d(das), dbs])
+            ref = part.cpu().numpy()
+            sc = np.maximum(np.abs(ref[1:]), np.max(np.abs(ref[1:])))
+            err_add = max(abs(tot[0] - ref[0]) / abs(ref[0]), float(np.max(np.abs(tot[1:] - ref[1:]) / sc)))
+            e = torch.tensor([err_add], device=dev, dtype=torch.float64)
+            dist.all_reduce(e, op=dist.ReduceOp.MAX)
+            err_add = float(e.item())
+    worst = max(err_sample, err_add or 0.0)
+    return {"ok": bool(worst < 1e-10), "max_rel_err": worst, "tolerance": 1e-10,
+            "sample_vs_cpu_checker": {"max_rel_err": err_sample, "rows_per_rank": int(Xs.shape[0]), "checker": kind,
+                                      "what": "likelihood term + partials (b200glm_glm_lpmf) on a row sample of each rank's shard"},
+            "shard_additivity": None if err_add is None else {
+                "max_rel_err": err_add, "what": "sharded handle (in-launch exchange) vs sum over ranks of the "
+                                                "same shards evaluated unsharded"}}
+
+
+def ess_record(args, torch, dist, dev, rank, world, local_rank):
+    """min ESS/s inside NUTS at the bench configuration: the reference's unmodified hmc_nuts_diag_e_adapt
+    (libb200stan.so) on b200::glm_model, `--ess-chains` chains run one after the other (every rank runs the same
+    deterministic host code on the same seeds; a chain's leapfrog is one launch per rank), `--ess-iters` warm-up +
+    `--ess-iters` sampling iterations each.  ESS by stan::analyze::ess (compiled into the shim)."""
+    from stan_b200 import stan_service
+    from stan_b200.synth import make_shard_ex
+    if not stan_service.available():
+        return {"unavailable": "stan_b200/lib/libb200stan.so not built (needs the reference headers at build time)"}
+    N_total, K = args.rows, args.cols
+    X, y, _, _, r0, r1 = make_shard_ex(torch, dev, args.family, N_total, K, 0, rank, world)
+    torch.cuda.synchronize()
+    sm = stan_service.StanGLM(args.family, X.data_ptr(), y.data_ptr(), device=local_rank, n_slots=1, rank=rank,
+                              world=world, N_total=N_total, data_on_device=True, N=r1 - r0, K=K, ldx=r1 - r0)
+    del X, y
+    torch.cuda.empty_cache()
+    if world > 1:
+        sm.connect_peers_torch(dist, dev)
+        dist.barrier()
+    it = args.ess_iters
+    res = sm.nuts(num_chains=args.ess_chains, seed=4711, num_warmup=it, num_samples=it, delta=0.8, num_threads=1)
+    wall = res["wall"]
+    if world > 1:
+        t = torch.tensor([wall], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+    sm.close()
+    if rank != 0:
+        return None
+    d = res["draws"]
+    P = d.shape[2] - 7
+    ess = [stan_service.diagnostic("ess", d[:, :, 7 + k].T) for k in range(P)]
+    rhat = [stan_service.diagnostic("rhat", d[:, :, 7 + k].T) for k in range(P)]
+    n_grad = float(d[:, :, 4].sum() + res["warm_leapfrogs"].sum() + 2 * it * args.ess_chains)
+    return {"b200": {"chains": args.ess_chains, "iters": f"{it}+{it}", "wall_s": wall, "grad_evals": n_grad,
+                     "grad_evals_per_s": n_grad / wall, "ess_min": float(np.min(ess)), "ess_median": float(np.median(ess)),
+                     "ess_min_per_s": float(np.min(ess)) / wall, "rhat_max": float(np.max(rhat)),
+                     "mean_treedepth": float(d[:, :, 3].mean()), "divergent": int(d[:, :, 5].sum()),
+                     "stepsize": [float(v) for v in res["stepsize"]]},
+            "service": "stan::services::sample::hmc_nuts_diag_e_adapt (unmodified) on b200::glm_model, chains sequential"}
 
 
 def run_b200_batched(args):
@@ -427,7 +588,7 @@ def run_reference(args):
             t.join()
 
     # bounded sample: shrink the row sample until the whole --steps/--warmup run fits in ~2 minutes of wall time
-    budget_s = 120.0
+    budget_s = 240.0
     while True:
         t0 = time.perf_counter()
         step()
@@ -447,8 +608,10 @@ def run_reference(args):
     value = rate_sample * ns / args.rows
     ms_per_step = 1000.0 / value
     cb = {"value": value, "unit": UNIT, "cores": threads, "kind": cls.kind,
-          "sample": f"{ns} of {args.rows} rows; each step = {threads} concurrent chains (threads) each doing one "
-                    f"stan::model::log_prob_grad; rate scaled by rows ({ns}/{args.rows})"}
+          "sample": (f"all {args.rows} rows (the full configuration)" if ns == args.rows else
+                     f"{ns} of {args.rows} rows, rate scaled by rows ({ns}/{args.rows})")
+                    + f"; each step = {threads} concurrent chains (threads) each doing one stan::model::log_prob_grad",
+          "same_config": bool(ns == args.rows)}
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -479,7 +642,13 @@ def main():
                     help="N > 1: how the P+2 likelihood partials are summed over ranks")
     ap.add_argument("--rows", type=int, default=None)
     ap.add_argument("--cols", type=int, default=None)
-    ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=None,
+                    help="rows of the CPU legs' sample (default: 1M for cpu_baseline; ALL rows for --impl reference)")
+    ap.add_argument("--parity-rows", type=int, default=200_000, help="rows per rank checked against the CPU checker")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--ess-iters", type=int, default=100,
+                    help="config 2: warm-up = sampling iterations of the in-bench NUTS run (0 skips it)")
+    ap.add_argument("--ess-chains", type=int, default=4)
     ap.add_argument("--cpu-evals", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -491,16 +660,19 @@ def main():
     args.groups = preset[3] if args.groups is None else args.groups
     args.weak = args.weak or preset[4]
     if args.config == 3 and args.impl == "b200":
+        args.cpu_sample_rows = args.cpu_sample_rows if args.cpu_sample_rows is not None else 1_000_000
         args.steps = args.steps if args.steps is not None else 20
         args.warmup = max(3, args.warmup if args.warmup is not None else 3)
         return run_b200_batched(args)
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 3
         args.warmup = args.warmup if args.warmup is not None else 1
+        args.cpu_sample_rows = args.cpu_sample_rows if args.cpu_sample_rows is not None else args.rows
         run_reference(args)
     else:
         args.steps = args.steps if args.steps is not None else 200
         args.warmup = max(3, args.warmup if args.warmup is not None else 10)
+        args.cpu_sample_rows = args.cpu_sample_rows if args.cpu_sample_rows is not None else 1_000_000
         run_b200(args)
 
 

@@ -125,6 +125,7 @@ struct b200glm_handle {
   double lgamma_sum_total = 0.0;
   bool bad_y = false;        // any shard holds an out-of-range y (after b200glm_comm_init / set_shard_constants_total)
   bool bad_y_local = false;  // this shard does
+  int pdl_prefetch = 2;     // B200GLM_PDL_PREFETCH=<stages> (A/B runs); see the TMA producer in glm_kernels.cuh
   bool tl_repeat = false;   // B200GLM_TL_REPEAT=1 (timeline runs only): the last CTA sums the partial rows twice
   bool inline_theta = true; // B200GLM_NO_INLINE_THETA=1: always upload theta with a host-to-device copy (A/B runs)
   bool host_mirror = true;  // B200GLM_NO_HOST_MIRROR=1: fetch results with a device-to-host copy + stream sync (A/B runs)
@@ -288,6 +289,7 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
   p.result = s->result;
   p.theta_used = s->theta_used;
   p.tl = s->tl;
+  p.pdl_prefetch = h->pdl_prefetch;
   p.tl_repeat = (s->tl && h->tl_repeat) ? 1 : 0;
   ModelConst& mc = p.mc;
   mc.family = h->d.family;
@@ -586,6 +588,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   if (!(d.prior_alpha_sd > 0) || !(d.prior_beta_sd > 0)) return fail(B200GLM_INVALID, "prior scales must be > 0");
   if (d.n_slots < 1) h->d.n_slots = 1;
   if (const char* e = std::getenv("B200GLM_NO_PDL")) h->pdl = !(e[0] == '1');
+  if (const char* e = std::getenv("B200GLM_PDL_PREFETCH")) h->pdl_prefetch = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("B200GLM_TL_REPEAT")) h->tl_repeat = (e[0] == '1');
   if (const char* e = std::getenv("B200GLM_NO_INLINE_THETA")) h->inline_theta = !(e[0] == '1');
   if (const char* e = std::getenv("B200GLM_NO_HOST_MIRROR")) h->host_mirror = !(e[0] == '1');
@@ -622,7 +625,12 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
       while (S > 0 && fixed_smem_bytes(d.K, d.G, h->stage_a, S, p_state, h->group_fused ? h->Gcs : 0)
                               + (size_t)S * tile_bytes > max_dyn)
         --S;
-      if (S > NUM_CONSUMER_WARPS) S = (S / NUM_CONSUMER_WARPS) * NUM_CONSUMER_WARPS;  // stage <-> warp ownership
+      // Any S works: panel n lives in stage n % S and is taken by warp n % 8; a stage cannot be refilled before its
+      // panel is released, so its full-barrier is never more than one phase ahead of a waiter and the parity test is
+      // unambiguous whichever warp waits.  (Round 1 rounded S down to a multiple of 8: at K = 50 that left ONE stage
+      // per warp, and each warp sat out a full TMA latency between panels -- 77 % of DRAM peak instead of ~90.)
+      if (const char* e = std::getenv("B200GLM_STAGES_MULT8"))
+        if (e[0] == '1' && S > NUM_CONSUMER_WARPS) S = (S / NUM_CONSUMER_WARPS) * NUM_CONSUMER_WARPS;
       return S;
     };
     int S = stages_for(h->state_smem ? P : 0);

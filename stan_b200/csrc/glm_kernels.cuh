@@ -469,8 +469,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
       const uint32_t bytes = (uint32_t)tile_doubles * 8u;
       int s = 0;
       uint32_t round = 0;
+      bool dep_waited = false;
       for (long long n = 0; n < p_count; ++n) {
         const long long pi = p_base + n * p_stride;
+        // Under programmatic dependent launch this CTA may have started while the PREVIOUS launch's last CTA is
+        // still in its serial tail (grid sum, exchange, epilogue).  Filling the whole ring right away floods the
+        // memory system with ~30 MB of bulk loads and that tail's few small loads queue behind them (measured:
+        // 5.2 us for 2 rounds of L2 loads, profiles/r2_timeline_*); so only pdl_prefetch stages are requested
+        // before the previous launch has completed, the rest of the ring after.
+        if (n == p.pdl_prefetch && !dep_waited) {
+          pdl_grid_dependency_wait();
+          dep_waited = true;
+        }
         if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
         mbar_arrive_expect_tx(&full_bar[s], bytes);
         tma_load_1d(tiles + (size_t)s * tile_doubles, p.panels + (size_t)pi * tile_doubles, bytes,
@@ -484,8 +494,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
     pdl_grid_dependency_wait();   // the tail below writes what the previous launch's epilogue may still be reading
   } else if (warp < (S < NUM_CONSUMER_WARPS ? S : NUM_CONSUMER_WARPS)) {
     // ===================== consumers =====================
-    // Stage s is only ever consumed by warp s % W_act (S is a multiple of W_act), so every wait
-    // on full[s] is issued by a warp that has observed all earlier phases of that barrier.
+    // Panel n of the CTA's sequence lives in stage n % S and is taken by warp n % W_act.  S need not be a multiple
+    // of W_act: a stage is refilled only after its panel has been released, so full[s] is never more than one
+    // phase ahead of whoever waits on it.
     const int W_act = S < NUM_CONSUMER_WARPS ? S : NUM_CONSUMER_WARPS;
     const int rg = lane & 3, cg = lane >> 2, cgl = cg & 3;
     const int o1 = lane ^ 4, o2 = lane ^ 8, o3 = lane ^ 12;
