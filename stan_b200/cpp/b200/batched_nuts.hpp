@@ -4,26 +4,28 @@
 // (ST/services/sample/hmc_nuts_diag_e_adapt.hpp:364-401: tbb::parallel_for over chains, one
 // util::run_adaptive_sampler per chain).  Here every chain still runs the reference's UNMODIFIED
 // single-chain service (hmc_nuts_diag_e_adapt.hpp:58-117 -> adapt_diag_e_nuts -> base_nuts::transition,
-// same RNG stream create_rng(seed, init_chain_id + i) as the multi-chain overload :352), but on its own
-// host thread inside a glm_model::batch_scope: whenever a chain needs a leapfrog step
-// (expl_leapfrog::evolve, base_nuts.hpp:254) or a gradient (hamiltonian.init, base_nuts.hpp:85) it parks
-// at the batcher; once every live chain is parked, ONE b200glm_leapfrog_batched call -- one pass over
-// X, the fp64 DMMA GEMM pair -- serves them all, and the chains go on building their trees.  Chains
+// same RNG stream create_rng(seed, init_chain_id + i) as the multi-chain overload :352), but as a FIBER:
+// a re-entrant computation with its own small stack, all chains in ONE host thread.  Whenever a chain needs a
+// leapfrog step (expl_leapfrog::evolve, base_nuts.hpp:254) or a gradient (hamiltonian.init, base_nuts.hpp:85)
+// it records the request and switches back to the scheduler -- in the middle of the reference's recursive
+// build_tree (base_nuts.hpp:247-352), whose frames simply stay on the fiber's stack; once every live chain has
+// a request pending, ONE b200glm_leapfrog_batched call -- one pass over X, the fp64 DMMA GEMM pair -- serves
+// them all, and the scheduler resumes the chains one after the other.  (Round 1 gave every chain an OS thread and
+// met at a mutex + condition variable: 1024 threads, 1024 wake-ups per batch, an AD tape per thread.)  Chains
 // advance in lock-step by leapfrog call; trees of different depth simply make a chain take part in
 // more or fewer batches per transition.  A gradient request is served as a leapfrog lane with eps = 0
 // (q stays, V and g are refreshed), so a batch never needs two passes.
 #ifndef B200_BATCHED_NUTS_HPP
 #define B200_BATCHED_NUTS_HPP
 
+#include <b200/fiber.hpp>
 #include <b200/stan_glm_model.hpp>
 
 #include <stan/services/sample/hmc_nuts_diag_e_adapt.hpp>
 
-#include <condition_variable>
 #include <cstdint>
 #include <limits>
-#include <mutex>
-#include <thread>
+#include <memory>
 
 namespace b200 {
 
@@ -91,11 +93,19 @@ class chain_batcher final : public glm_model::batch_hook {
   }
 
   // a chain has finished (or failed): the others no longer wait for it
-  void leave(int) override {
-    std::unique_lock<std::mutex> lk(mu_);
-    --n_active_;
-    if (n_active_ > 0 && n_waiting_ == n_active_)
-      run_batch();
+  void leave(int) override { --n_active_; }
+
+  // scheduler side (hmc_nuts_diag_e_adapt_batched): every live chain has a request pending -> one batched launch
+  int n_waiting() const { return n_waiting_; }
+  void serve() {
+    try {
+      dispatch();
+    } catch (const std::exception& e) {
+      fatal_ = e.what();
+    }
+    for (auto& r : req_)
+      r.pending = false;
+    n_waiting_ = 0;
   }
 
   static constexpr int kSingleLaneThreshold = 2;
@@ -122,32 +132,14 @@ class chain_batcher final : public glm_model::batch_hook {
     std::vector<double> q, p, g, im;
   };
 
+  // chain side: record the request and hand control back to the scheduler; when the chain is resumed its
+  // lane of the batch has been computed
   void submit(int chain) {
-    std::unique_lock<std::mutex> lk(mu_);
     req_[chain].pending = true;
     ++n_waiting_;
-    if (n_waiting_ == n_active_) {
-      run_batch();
-    } else {
-      const std::uint64_t gen = gen_;
-      cv_.wait(lk, [&] { return gen_ != gen; });
-    }
+    fiber::yield();
     if (!fatal_.empty())
       throw std::runtime_error(fatal_);
-  }
-
-  // mu_ held; every live chain is parked
-  void run_batch() {
-    try {
-      dispatch();
-    } catch (const std::exception& e) {
-      fatal_ = e.what();
-    }
-    for (auto& r : req_)
-      r.pending = false;
-    n_waiting_ = 0;
-    ++gen_;
-    cv_.notify_all();
   }
 
   void dispatch() {
@@ -256,10 +248,7 @@ class chain_batcher final : public glm_model::batch_hook {
   const glm_model& m_;
   const size_t P_;
   const int n_;
-  std::mutex mu_;
-  std::condition_variable cv_;
   int n_active_, n_waiting_ = 0;
-  std::uint64_t gen_ = 0;
   std::string fatal_;
   std::vector<request> req_;
   std::vector<resident> res_;
@@ -288,11 +277,10 @@ int hmc_nuts_diag_e_adapt_batched(glm_model& model, size_t num_chains, const std
                                   std::vector<MetricWriter>& metric_writer, long* stats = nullptr) {
   chain_batcher batcher(model, static_cast<int>(num_chains));
   std::vector<int> rc(num_chains, 0);
-  std::vector<std::thread> threads;
-  threads.reserve(num_chains);
+  std::vector<std::unique_ptr<fiber>> chains;
+  chains.reserve(num_chains);
   for (size_t i = 0; i < num_chains; ++i) {
-    threads.emplace_back([&, i] {
-      stan::math::ChainableStack tape;  // STAN_THREADS: every thread owns an AD tape (init_chainablestack.hpp)
+    chains.emplace_back(new fiber([&, i] {
       glm_model::batch_scope scope(&batcher, static_cast<int>(i));
       try {
         rc[i] = stan::services::sample::hmc_nuts_diag_e_adapt(
@@ -304,10 +292,28 @@ int hmc_nuts_diag_e_adapt_batched(glm_model& model, size_t num_chains, const std
         logger.error(e.what());
         rc[i] = stan::services::error_codes::SOFTWARE;
       }
-    });
+    }));
   }
-  for (auto& t : threads)
-    t.join();
+  // The scheduler: resume every chain that is not finished; each runs (through the reference's transition /
+  // build_tree code) until its next leapfrog or gradient request, or to its end.  After a sweep every live chain is
+  // parked with a request: serve them all with one batched launch and sweep again.
+  for (;;) {
+    size_t live = 0;
+    for (size_t i = 0; i < num_chains; ++i) {
+      if (chains[i]->done())
+        continue;
+      glm_model::tls_hook() = &batcher;          // the fibers share this thread's thread-locals
+      glm_model::tls_chain() = static_cast<int>(i);
+      chains[i]->resume();
+      if (!chains[i]->done())
+        ++live;
+    }
+    glm_model::tls_hook() = nullptr;
+    glm_model::tls_chain() = -1;
+    if (live == 0)
+      break;
+    batcher.serve();
+  }
   if (stats) {
     stats[0] = batcher.n_batches();
     stats[1] = batcher.n_lanes();

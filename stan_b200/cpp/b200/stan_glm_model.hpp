@@ -270,10 +270,13 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
     }
   };
 
+  // on_tape: the caller is log_prob<..., var> with autodiff variables of the thread's tape alive.  Such a call is
+  // never handed to the batcher: the batched driver runs all chains as fibers of ONE thread, and a chain parked in
+  // the middle of a tape computation would have its variables recovered by the next chain's log_prob_grad.
   void device_log_prob_grad(const double* theta, bool propto, bool jacobian,
-                            double& lp, double* grad) const {
+                            double& lp, double* grad, bool on_tape = false) const {
     n_gradients_.fetch_add(1, std::memory_order_relaxed);
-    if (batch_hook* hook = tls_hook(); hook && propto && jacobian) {
+    if (batch_hook* hook = tls_hook(); hook && propto && jacobian && !on_tape) {
       hook->gradient(tls_chain(), theta, lp, grad);
       return;
     }
@@ -457,7 +460,7 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
         th[i] = ops[i].val();
       }
       double lp = 0;
-      device_log_prob_grad(th.data(), propto, jacobian, lp, grad.data());
+      device_log_prob_grad(th.data(), propto, jacobian, lp, grad.data(), /*on_tape=*/true);
       return stan::math::precomputed_gradients(lp, ops, grad);
     }
   }

@@ -46,7 +46,7 @@ constexpr int SMEM_A_MAX_GROUPS = 2048;  // a[G] staged in smem up to this many 
 // aux columns of a panel: y at K, trials at K+1 (binomial_logit only), group id after those (G > 0 only)
 __host__ __device__ constexpr int fam_group_col(int f, int K) { return K + 1 + (f == FAM_BINOMIAL_LOGIT ? 1 : 0); }
 // doubles per CTA partial row: K beta gradients, lp-sum, r-sum, aux-sum (d/dphi terms of neg_binomial_2_log)
-__host__ __device__ constexpr int partial_stride(int K) { return (K + 3 + 1) & ~1; }
+__host__ __device__ constexpr int partial_stride(int K) { return (K + 3 + 15) & ~15; }   // whole 128-byte lines
 // ------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk async copy (TMA engine)
 // ------------------------------------------------------------------------------------------
@@ -262,7 +262,8 @@ __device__ __forceinline__ void stage_theta(const KernelParams& p, int t, int nt
 
 template <int FAMILY>
 __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& p, double* sh_scratch,
-                                                            int* sh_is_last, const StateSmem& st) {
+                                                            int* sh_is_last, const StateSmem& st,
+                                                            double* scratch /* >= 10 x (K + 35) doubles of idle smem */) {
   const int tid = threadIdx.x, nt = blockDim.x, grid = gridDim.x;
   const int K = p.K, G = p.G, P = p.P;
   __threadfence();
@@ -281,59 +282,63 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
 
   __threadfence();
   if (tid == 0) tl_stamp(p, grid + 1, 0);        // acquire fence after the ticket
-  // Sum of the grid's partial rows, column by column, in a FIXED tree (bitwise reproducible): the rows are cut
-  // into R contiguous segments taken by R adjacent lanes (R = 1, 2, 4 or 8, as many as the CTA has threads for),
-  // each lane keeps GS_DEPTH independent accumulators so that many L2 loads are in flight per thread (this loop is
-  // on the critical path of every launch: ~13 us as one dependent chain of 148 loads, 4.7 us eight at a time,
-  // profiles/r2_timeline_*), the segments meet in a shuffle butterfly.
-  constexpr int GS_DEPTH = 40;
+  // Sum of the grid's partial rows in a FIXED order (bitwise reproducible).  Warp w takes rows w, w + nw, ...; a
+  // lane reads 8 consecutive bytes of a 256-byte stretch of the row, so every load instruction of a warp is one
+  // fully used, aligned run of sectors (rows are padded to 128 bytes, partial_stride), and four rows are in flight
+  // per thread.  The per-warp column sums meet in shared memory (the TMA ring is idle by now: `scratch`) and are
+  // folded in warp order.  This loop is on the critical path of every launch: ~13 us as one dependent chain of 148
+  // loads; 4.7 us with lanes striding over rows (two half-used 128-byte segments per instruction: one SM's L2 port,
+  // not latency, was the limit -- no gain from 8 -> 40 loads in flight, profiles/r2_timeline_*); ~1.5 us like this.
   double* lik = st.lik ? st.lik : p.lik;         // the sums go to the on-chip copy when there is one
   const int n_sums = FAMILY == FAM_NEG_BINOMIAL_2_LOG ? K + 3 : K + 2;
-  int R = 1;
-  while (R < 8 && 2 * R * n_sums <= nt) R *= 2;
-  const int seg_len = (grid + R - 1) / R;
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const int n_chunks = (n_sums + 31) >> 5;       // 32-column chunks of a row
   // measurement only: tl_repeat makes the sum run twice (same result), the first pass stamped on its own, to
   // separate what a cold pass costs (instruction fetch, first touch of the partial rows) from a warm one
   for (int rep = (p.tl && p.tl_repeat) ? 0 : 1; rep < 2; ++rep) {
-  if (rep == 1 && p.tl && p.tl_repeat) {
-    __syncthreads();
-    if (tid == 0) tl_stamp(p, grid + 1, 5);      // end of the cold pass
-  }
-  for (int base = 0; base < n_sums; base += nt / R) {       // warp-uniform trip count (nt and R are multiples)
-    const int j = base + tid / R, r = tid & (R - 1);
-    double a[GS_DEPTH];
+    if (rep == 1 && p.tl && p.tl_repeat) {
+      __syncthreads();
+      if (tid == 0) tl_stamp(p, grid + 1, 5);    // end of the cold pass
+    }
+    for (int c0 = 0; c0 < n_chunks; c0 += 4) {   // up to 4 chunks (128 columns) per sweep over the rows
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      const double* src = p.partials + c0 * 32 + lane;
+      int r = warp;
+      for (; r + 3 * nw < grid; r += 4 * nw) {
+        double v[4][4];
 #pragma unroll
-    for (int u = 0; u < GS_DEPTH; ++u) a[u] = 0.0;
-    if (j < n_sums) {
-      const int b1 = min(grid, (r + 1) * seg_len);
-      int b = r * seg_len;
-      const double* src = p.partials + j;
-      for (; b + GS_DEPTH <= b1; b += GS_DEPTH) {
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int u = 0; u < GS_DEPTH; ++u) a[u] += __ldcg(src + (size_t)(b + u) * p.pstride);
+          for (int q = 0; q < 4; ++q)
+            v[u][q] = (c0 + q) * 32 + lane < n_sums ? __ldcg(src + (size_t)(r + u * nw) * p.pstride + q * 32) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q] += v[u][q];
+      }
+      for (; r < grid; r += nw) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if ((c0 + q) * 32 + lane < n_sums) acc[q] += __ldcg(src + (size_t)r * p.pstride + q * 32);
       }
 #pragma unroll
-      for (int u = 0; u < GS_DEPTH - 1; ++u)
-        if (b + u < b1) a[u] += __ldcg(src + (size_t)(b + u) * p.pstride);
+      for (int q = 0; q < 4; ++q)
+        if (c0 + q < n_chunks) scratch[warp * (n_chunks * 32) + (c0 + q) * 32 + lane] = acc[q];
     }
-    if (tid == 0 && base == 0) tl_stamp(p, grid + 1, 1);   // first batch of partial rows loaded
-#pragma unroll
-    for (int w = GS_DEPTH / 2; w >= 5; w /= 2) {            // 40 -> 20 -> 10 -> 5 partial sums, fixed pairing
-#pragma unroll
-      for (int u = 0; u < w; ++u) a[u] += a[u + w];
+    if (tid == 0) tl_stamp(p, grid + 1, 1);      // this warp's rows loaded
+    __syncthreads();
+    for (int j = tid; j < n_sums; j += nt) {
+      double v = 0.0;
+      for (int w = 0; w < nw; ++w) v += scratch[w * (n_chunks * 32) + j];
+      if (j < K)
+        lik[p.off_beta + j] = v;
+      else if (j == K)
+        lik[P] = v;
+      else if (j == K + 2)
+        lik[P + 1] = v;      // neg_binomial_2_log: sum of the per-row d/dphi terms
+      else if (G == 0)
+        lik[0] = v;
     }
-    double v = ((a[0] + a[1]) + (a[2] + a[3])) + a[4];
-    for (int o = 1; o < R; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (j >= n_sums || r != 0) continue;
-    if (j < K)
-      lik[p.off_beta + j] = v;
-    else if (j == K)
-      lik[P] = v;
-    else if (j == K + 2)
-      lik[P + 1] = v;      // neg_binomial_2_log: sum of the per-row d/dphi terms
-    else if (G == 0)
-      lik[0] = v;
-  }
   }
   if (p.group_fused) {
     // per-group residual sums = the gradient wrt a[g] (rvalue(a, index_multi(group)) scatters r back, rvalue.hpp:154-172)
@@ -654,7 +659,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
       my_g[j] = v;
     }
   }
-  cross_cta_reduce_and_finish<FAMILY>(p, sh_scratch, &sh_is_last, st);
+  cross_cta_reduce_and_finish<FAMILY>(p, sh_scratch, &sh_is_last, st, tiles);
 }
 
 // G > 0: deterministic per-group sums of the residual (rows are sorted by group at upload, so a group

@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
     }
   }
 
-  cross_cta_reduce_and_finish<FAMILY>(p, sh_scratch, &sh_is_last, st);
+  cross_cta_reduce_and_finish<FAMILY>(p, sh_scratch, &sh_is_last, st, ring);
 }
 
 }  // namespace b200glm
