@@ -48,15 +48,35 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md), polled through NVML every few
+    milliseconds from a thread (the timed region of a 20-step run is ~20 ms: nvidia-smi's loop mode is too coarse for
+    it); falls back to `nvidia-smi -lms` when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.samples = index, None, [], []
+        self.nvml, self.stop_flag, self.t = None, False, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except (ValueError, IndexError):
+                    pass
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -66,11 +86,51 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown")
+                else n.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown",
+                                               getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0)),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown",
+                                               getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0)),
+                "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap",
+                                        getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0))}
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons",
+                              getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+        try:
+            mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                r = get_reasons(self.handle) if get_reasons else 0
+                self.samples.append((time.time(), sm, mx, [k for k, b in bits.items() if b and (r & b)]))
+            except Exception:
+                pass
+            time.sleep(0.003)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
     def stop(self, t0=None, t1=None):
+        if self.nvml is not None:
+            time.sleep(0.01)
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+            inside = [s for s in self.samples if t0 is None or t0 <= s[0] <= t1]
+            how = "NVML every 3 ms, samples inside the timed region"
+            if not inside and self.samples and t0 is not None:   # region shorter than one poll: the nearest samples
+                mid = 0.5 * (t0 + t1)
+                inside = sorted(self.samples, key=lambda s: abs(s[0] - mid))[:2]
+                how = "NVML every 3 ms, the two samples nearest to the timed region"
+            if not inside:
+                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no NVML samples"]}
+            reasons = sorted({r for s in inside for r in s[3]})
+            return {"sm_mhz": float(np.median([s[1] for s in inside])), "sm_max_mhz": inside[0][2],
+                    "samples": len(inside), "reasons": reasons, "how": how}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -90,7 +150,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "how": "nvidia-smi -lms 100"}
 
 
 def dist_env():

@@ -625,12 +625,12 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
       while (S > 0 && fixed_smem_bytes(d.K, d.G, h->stage_a, S, p_state, h->group_fused ? h->Gcs : 0)
                               + (size_t)S * tile_bytes > max_dyn)
         --S;
-      // Any S works: panel n lives in stage n % S and is taken by warp n % 8; a stage cannot be refilled before its
-      // panel is released, so its full-barrier is never more than one phase ahead of a waiter and the parity test is
-      // unambiguous whichever warp waits.  (Round 1 rounded S down to a multiple of 8: at K = 50 that left ONE stage
-      // per warp, and each warp sat out a full TMA latency between panels -- 77 % of DRAM peak instead of ~90.)
+      // Any S works: a stage belongs to one consumer warp for the whole launch (glm_kernels.cuh).  Round 1 rounded S
+      // down to a multiple of 8: at K = 50 that left ONE stage per warp, and each warp sat out a full TMA latency
+      // between panels -- 77 % of DRAM peak instead of ~90.
       if (const char* e = std::getenv("B200GLM_STAGES_MULT8"))
         if (e[0] == '1' && S > NUM_CONSUMER_WARPS) S = (S / NUM_CONSUMER_WARPS) * NUM_CONSUMER_WARPS;
+      if (const char* e = std::getenv("B200GLM_STAGES")) S = std::max(1, std::min(S, std::atoi(e)));   // A/B runs
       return S;
     };
     int S = stages_for(h->state_smem ? P : 0);

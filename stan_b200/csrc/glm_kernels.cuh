@@ -499,10 +499,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
     pdl_grid_dependency_wait();   // the tail below writes what the previous launch's epilogue may still be reading
   } else if (warp < (S < NUM_CONSUMER_WARPS ? S : NUM_CONSUMER_WARPS)) {
     // ===================== consumers =====================
-    // Panel n of the CTA's sequence lives in stage n % S and is taken by warp n % W_act.  S need not be a multiple
-    // of W_act: a stage is refilled only after its panel has been released, so full[s] is never more than one
-    // phase ahead of whoever waits on it.
-    const int W_act = S < NUM_CONSUMER_WARPS ? S : NUM_CONSUMER_WARPS;
+    // Panel n of the CTA's sequence lives in stage n % S; a STAGE belongs to one warp (stage s to warp s % 8) for the
+    // whole launch, so S need not be a multiple of 8 (with 13 stages five warps own two and three own one).  The
+    // ownership is what makes the parity wait sound: a warp has consumed fill k - 1 of a stage before it waits for
+    // fill k, so the barrier can only be in phase k or k + 1.  (Handing panels out round-robin, n % 8, with S = 9 let
+    // a warp wait for fill 1 of a stage whose fill 0 was still in flight -- parity 1 reads as "the phase before phase
+    // 0 is complete", the warp ran ahead on stale data and the ring dead-locked.)
     const int rg = lane & 3, cg = lane >> 2, cgl = cg & 3;
     const int o1 = lane ^ 4, o2 = lane ^ 8, o3 = lane ^ 12;
     const int ycol = K * 32 + (lane ^ ((K & 3) << 2));
@@ -530,10 +532,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
       __syncwarp();
     }
 
-    for (long long n = warp; n < p_count; n += W_act) {   // n = index of this panel in the CTA's sequence
+    uint32_t parity = 0;
+    for (long long n0 = 0; n0 < p_count; n0 += S, parity ^= 1u)          // fill round k = n0 / S of the ring
+    for (int s = warp; s < S; s += NUM_CONSUMER_WARPS) {                 // this warp's stages, in panel order
+      const long long n = n0 + s;                                        // index of the panel in the CTA's sequence
+      if (n >= p_count) break;
       const long long pi = p_base + n * p_stride;
-      const int s = (int)(n % S);
-      const uint32_t parity = (uint32_t)((n / S) & 1);
       mbar_wait(&full_bar[s], parity);
       if (n == 0 && tid == 0) tl_stamp(p, blockIdx.x, 3);   // first panel landed
       const double* tile = tiles + (size_t)s * tile_doubles;
