@@ -13,6 +13,7 @@
 //   (3) a full specialisation of stan::mcmc::expl_leapfrog<diag_e_metric<b200::glm_model, stan::rng_t>>
 //       (ST/mcmc/hmc/integrators/expl_leapfrog.hpp:16-32) whose evolve() is ONE fused device launch on
 //       device-resident (q,p,g); base_hmc only ever calls integrator_.evolve (base_hmc.hpp:113,132; base_nuts.hpp:254).
+//       It reaches the model through the Hamiltonian it is handed (no thread-local lookup).
 // With these, the UNMODIFIED adapt_diag_e_nuts / base_nuts / diag_e_metric / services drive the GPU path.
 //
 // Threading: chains run as TBB tasks on several host threads sharing one const model (hmc_nuts_diag_e_adapt.hpp:387-401).
@@ -180,7 +181,7 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
       b200glm_destroy(h_);
   }
 
-  // Thread-local caches (slot binding, resident leapfrog state, "current model") are keyed by a
+  // Thread-local caches (slot binding, resident leapfrog state) are keyed by a
   // process-unique id, never by address: a new model may be allocated where a destroyed one lived.
   static unsigned long long next_uid() {
     static std::atomic<unsigned long long> n{1};
@@ -286,26 +287,6 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
     double lp = 0;
     check(b200glm_log_prob(h_, slot(), theta, propto, jacobian, &lp));
     return lp;
-  }
-
-  // thread-local "which model did this thread evaluate last" -- how the integrator
-  // specialisation finds the device without touching diag_e_metric (model_ is protected there)
-  struct current_ref {
-    const glm_model* model = nullptr;
-    unsigned long long uid = 0;
-  };
-  static current_ref& current_slot() {
-    static thread_local current_ref cur;
-    return cur;
-  }
-  static void set_current(const glm_model* m) {
-    current_slot().model = m;
-    current_slot().uid = m->uid_;
-  }
-  // nullptr if this thread has not evaluated a model yet or that model no longer exists
-  static const glm_model* current() {
-    const current_ref& c = current_slot();
-    return (c.model != nullptr && registry(0, c.uid)) ? c.model : nullptr;
   }
 
   struct resident_state {
@@ -562,7 +543,6 @@ template <>
 inline void gradient<b200::glm_model>(const b200::glm_model& model, const Eigen::Matrix<double, Eigen::Dynamic, 1>& x,
                                       double& f, Eigen::Matrix<double, Eigen::Dynamic, 1>& grad_f,
                                       std::ostream* /*msgs*/) {
-  b200::glm_model::set_current(&model);
   Eigen::VectorXd g(x.size());
   model.device_log_prob_grad(x.data(), true, true, f, g.data());  // throws before grad_f is touched
   grad_f = std::move(g);
@@ -591,16 +571,17 @@ class expl_leapfrog<diag_e_metric<b200::glm_model, stan::rng_t>>
 
   expl_leapfrog() : base_leapfrog<hamiltonian_t>() {}
 
+  // The model the Hamiltonian was built on.  base_hamiltonian keeps it as a protected reference (model_,
+  // base_hamiltonian.hpp:81) and offers no accessor; a derived type with no members of its own reads it.  This
+  // replaces round 1's thread-local "last model evaluated on this thread", which depended on hamiltonian.init
+  // having run on the same thread before the first evolve.
+  struct model_peek : hamiltonian_t {
+    static const b200::glm_model& get(hamiltonian_t& h) { return static_cast<model_peek&>(h).model_; }
+  };
+
   // one launch: p -= eps/2 g; q += eps M^-1 p; (V,g) = -(lp, grad lp)(q); p -= eps/2 g
   void evolve(point_t& z, hamiltonian_t& hamiltonian, const double epsilon, callbacks::logger& logger) {
-    const b200::glm_model* m = b200::glm_model::current();
-    if (m == nullptr || static_cast<size_t>(z.q.size()) != m->num_params_r()) {
-      // no device evaluation on this thread yet: take the host sub-steps once (they reach the device
-      // through the gradient specialisation, which registers the model for the following calls)
-      base_leapfrog<hamiltonian_t>::evolve(z, hamiltonian, epsilon, logger);
-      return;
-    }
-    m->device_leapfrog(z.q, z.p, z.g, z.V, z.inv_e_metric_, epsilon, logger);
+    model_peek::get(hamiltonian).device_leapfrog(z.q, z.p, z.g, z.V, z.inv_e_metric_, epsilon, logger);
   }
 
   // host sub-steps, kept so the class still satisfies base_leapfrog's interface

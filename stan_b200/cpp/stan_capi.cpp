@@ -23,7 +23,9 @@
 #include <stan/callbacks/structured_writer.hpp>
 #include <stan/callbacks/writer.hpp>
 #include <stan/io/empty_var_context.hpp>
+#include <stan/io/dump.hpp>
 #include <stan/io/json/json_data.hpp>
+#include <stan/model/log_prob_propto.hpp>
 #include <stan/io/stan_csv_reader.hpp>
 #include <stan/callbacks/json_writer.hpp>
 #include <stan/callbacks/unique_stream_writer.hpp>
@@ -150,6 +152,43 @@ void* b200stan_create_from_json(const char* path, int family, const char* name_y
     m = new glm_model(context, cfg);
   });
   return m;
+}
+// The same constructor fed by the reference's R-dump var_context (stan::io::dump, ST/io/dump.hpp), the other data
+// format SURVEY 8f row 4 names.
+void* b200stan_create_from_dump(const char* path, int family, int device, int n_slots, char* err, int errlen) {
+  glm_model* m = nullptr;
+  guarded(err, errlen, [&] {
+    std::ifstream in(path);
+    if (!in.good())
+      throw std::invalid_argument(std::string("cannot open ") + path);
+    stan::io::dump context(in);
+    b200::glm_config cfg;
+    cfg.family = family;
+    cfg.device = device;
+    cfg.n_slots = n_slots;
+    m = new glm_model(context, cfg);
+  });
+  return m;
+}
+// stan::model::log_prob_propto<jacobian> (ST/model/log_prob_propto.hpp:32-52 and the Eigen overload :75-96): the
+// call base_hamiltonian::update_potential makes (base_hamiltonian.hpp:54).  which = 0: std::vector signature,
+// 1: Eigen signature.
+int b200stan_log_prob_propto(void* h, const double* theta, int jacobian, int which, double* lp, char* err,
+                             int errlen) {
+  return guarded(err, errlen, [&] {
+    const glm_model& m = *static_cast<glm_model*>(h);
+    const size_t P = m.num_params_r();
+    if (which == 0) {
+      std::vector<double> th(theta, theta + P);
+      std::vector<int> pi;
+      *lp = jacobian ? stan::model::log_prob_propto<true>(m, th, pi, nullptr)
+                     : stan::model::log_prob_propto<false>(m, th, pi, nullptr);
+    } else {
+      Eigen::VectorXd th = Eigen::Map<const Eigen::VectorXd>(theta, P);
+      *lp = jacobian ? stan::model::log_prob_propto<true>(m, th, nullptr)
+                     : stan::model::log_prob_propto<false>(m, th, nullptr);
+    }
+  });
 }
 // column means removed by center_x (K doubles); returns the number written (0 if not centred)
 int b200stan_means_x(void* h, double* out) {

@@ -367,7 +367,7 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
   if (tid == 0) tl_stamp(p, grid, 2);            // peers' partials received and summed
   if (p.fuse_finish) {
     const FinishSrc src = {st.theta ? st.theta : p.theta_used, lik, st.ph, st.g0};
-    finish(p, sh_scratch, src);
+    finish_t<FAMILY>(p, sh_scratch, src);
   } else if (st.lik) {
     for (int j = tid; j < P + 2; j += nt) p.lik[j] = lik[j];   // the separate epilogue launch reads the global copy
   }
@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
     }
     lp_acc = warp_sum(lp_acc);
     r_acc = warp_sum(r_acc);
-    x_acc = warp_sum(x_acc);
+    if (FAMILY == FAM_NEG_BINOMIAL_2_LOG) x_acc = warp_sum(x_acc);
     if (lane == 0) {
       red[warp * (Kpad + 4) + Kpad] = lp_acc;
       red[warp * (Kpad + 4) + Kpad + 1] = r_acc;

@@ -164,8 +164,12 @@ struct FinishSrc {
   const double* g0;
 };
 
-__device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratch */, const FinishSrc& src) {
+// FAMILY >= 0: the family is a compile-time constant (the fused kernels: only that family's branch is compiled in, which
+// keeps the once-per-launch, cold-instruction-cache epilogue short); FAMILY < 0: taken from p.mc.family at run time.
+template <int FAMILY>
+__device__ void finish_t(const KernelParams& p, double* sh /* >= 64 doubles scratch */, const FinishSrc& src) {
   const ModelConst& mc = p.mc;
+  const int family = FAMILY >= 0 ? FAMILY : mc.family;
   const int P = mc.P, K = mc.K, G = mc.G;
   const double* theta = src.theta;
   const double* lik = src.lik;
@@ -176,7 +180,7 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
   const double mu_a = G > 0 ? theta[0] : 0.0;
   const double u_sa = G > 0 ? theta[1] : 0.0;
   const double sigma_a = G > 0 ? exp(u_sa) : 1.0;
-  const bool has_scale = fam_has_scale(mc.family);   // sigma (normal_id) | phi (neg_binomial_2_log)
+  const bool has_scale = fam_has_scale(family);   // sigma (normal_id) | phi (neg_binomial_2_log)
   const double u_s = has_scale ? theta[P - 1] : 0.0;
   const double sigma = has_scale ? exp(u_s) : 1.0;
   const double ib2 = 1.0 / (mc.prior_beta_sd * mc.prior_beta_sd);
@@ -254,12 +258,12 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
       // likelihood
       if (mc.N_total > 0) {
         const double S = lik[P];
-        if (mc.family == FAM_BERNOULLI_LOGIT) {
+        if (family == FAM_BERNOULLI_LOGIT) {
           lp += S;
-        } else if (mc.family == FAM_POISSON_LOG || mc.family == FAM_BINOMIAL_LOGIT) {
+        } else if (family == FAM_POISSON_LOG || family == FAM_BINOMIAL_LOGIT) {
           lp += S;
           if (!mc.propto) lp -= mc.lgamma_sum;         // poisson_log_glm_lpmf.hpp:127-129, binomial_logit_glm_lpmf.hpp:127-130
-        } else if (mc.family == FAM_NEG_BINOMIAL_2_LOG) {
+        } else if (family == FAM_NEG_BINOMIAL_2_LOG) {
           lp += S;                                     // neg_binomial_2_log_glm_lpmf.hpp:186-197 (row terms)
           if (!mc.propto) lp -= mc.lgamma_sum;         // :163-169
           if (!mc.lik_only || !mc.propto || mc.sigma_is_var)
@@ -285,9 +289,9 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
   for (int i = tid; i < P; i += nt) {
     double g = lik[i];
     if (mc.lik_only) {
-      if (mc.family == FAM_NORMAL_ID && i == P - 1)
+      if (family == FAM_NORMAL_ID && i == P - 1)
         g = mc.N_total > 0 ? (lik[P] - mc.N_total) / sigma : 0.0;    // normal_id_glm_lpdf.hpp:181-183
-      else if (mc.family == FAM_NEG_BINOMIAL_2_LOG && i == P - 1)
+      else if (family == FAM_NEG_BINOMIAL_2_LOG && i == P - 1)
         g = mc.N_total > 0 ? lik[P + 1] : 0.0;                       // neg_binomial_2_log_glm_lpmf.hpp:240-245
       else if (G > 0 && i < 2)
         g = 0.0;
@@ -310,7 +314,7 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
       if (has_scale && i == P - 1) {
         double dlik = 0.0;
         if (mc.N_total > 0)
-          dlik = mc.family == FAM_NORMAL_ID ? (lik[P] - mc.N_total) / sigma   // normal_id_glm_lpdf.hpp:181-183
+          dlik = family == FAM_NORMAL_ID ? (lik[P] - mc.N_total) / sigma   // normal_id_glm_lpdf.hpp:181-183
                                             : lik[P + 1];                     // neg_binomial_2_log_glm_lpmf.hpp:240-245
         const double dpri = -(sigma - mc.prior_sigma_loc) / (mc.prior_sigma_scale * mc.prior_sigma_scale);
         g = (dlik + dpri) * sigma + (mc.jacobian ? 1.0 : 0.0);
@@ -348,10 +352,11 @@ __device__ void finish(const KernelParams& p, double* sh /* >= 64 doubles scratc
   host_out_publish(p);
 }
 
+__device__ inline void finish(const KernelParams& p, double* sh, const FinishSrc& src) { finish_t<-1>(p, sh, src); }
 // the epilogue from the global arrays (finish_kernel, host build)
 __device__ inline void finish(const KernelParams& p, double* sh) {
   const FinishSrc src = {p.theta_used, p.lik, nullptr, nullptr};
-  finish(p, sh, src);
+  finish_t<-1>(p, sh, src);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -84,6 +84,31 @@ class StanGLM:
         self.P = self.L.b200stan_num_params(self.h)
         return self
 
+    @classmethod
+    def from_dump(cls, path, family, device=0, n_slots=8):
+        """The same constructor fed by the reference's R-dump reader stan::io::dump."""
+        self = cls.__new__(cls)
+        self.L = lib()
+        self.rank, self.world = 0, 1
+        f = self.L.b200stan_create_from_dump
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        err = C.create_string_buffer(1024)
+        self.h = C.c_void_p(f(os.fsencode(path), _capi.FAMILY[family], device, n_slots, err, 1024))
+        if not self.h:
+            raise InvalidArgument(err.value.decode() or "b200stan_create_from_dump failed")
+        self.P = self.L.b200stan_num_params(self.h)
+        return self
+
+    def log_prob_propto(self, theta, jacobian=True, eigen=False):
+        """stan::model::log_prob_propto<jacobian>(model, theta) -- both signatures of log_prob_propto.hpp."""
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        lp, err = C.c_double(), C.create_string_buffer(1024)
+        rc = self.L.b200stan_log_prob_propto(self.h, _dp(th), int(jacobian), int(eigen), C.byref(lp), err, 1024)
+        if rc:
+            self._raise(rc, err)
+        return lp.value
+
     def means_x(self):
         """Column means removed from X by center_x (brms-style transformed data); empty if not centred."""
         self.L.b200stan_means_x.argtypes = [C.c_void_p, C.POINTER(C.c_double)]

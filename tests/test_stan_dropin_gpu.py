@@ -299,3 +299,57 @@ def test_csv_and_json_writers_round_trip_through_stan_csv_reader(tmp_path):
             mj = js.load(f)
         assert mj["stepsize"] == pytest.approx(mem["stepsize"][c], rel=1e-12)
         assert np.allclose(mj["inv_metric"], mem["inv_metric"][c], rtol=1e-12, atol=0)
+
+
+def test_log_prob_propto_through_the_reference_function(golden):
+    """SURVEY 8a row a8: stan::model::log_prob_propto<jacobian> (log_prob_propto.hpp:32-52, :75-96) -- the call
+    base_hamiltonian::update_potential makes -- on b200::glm_model, both signatures, against the same function on
+    the reference CPU model (== the value of log_prob_grad<true, jacobian>)."""
+    Ref = ref_oracle()
+    for name in ("bern_small", "pois_groups", "norm_small"):
+        c = golden[name]
+        m = stan_service.StanGLM(c["family"], c["X"], c["y"], c["group"], c["G"])
+        orc = Ref(c["family"], c["X"], c["y"], c["group"], c["G"])
+        for th in theta_points(m.P, n_random=2, scale=0.2):
+            for jac in (True, False):
+                want = orc.log_prob_grad(th, True, jac)[0]
+                assert rel_err(m.log_prob_propto(th, jac, eigen=False), want) < TOL
+                assert rel_err(m.log_prob_propto(th, jac, eigen=True), want) < TOL
+        m.close()
+
+
+def _r_dump(path, **vars_):
+    """CmdStan's R-dump data format (what stan::io::dump parses)."""
+    def num(v):
+        return repr(float(v)) if isinstance(v, (float, np.floating)) else str(int(v))
+    with open(path, "w") as f:
+        for k, v in vars_.items():
+            a = np.asarray(v)
+            if a.ndim == 0:
+                f.write(f"{k} <- {num(a[()])}\n")
+            elif a.ndim == 1:
+                f.write(f"{k} <- c({', '.join(num(x) for x in a)})\n")
+            else:   # column-major, as R stores matrices
+                flat = ", ".join(num(x) for x in a.flatten(order="F"))
+                f.write(f"{k} <- structure(c({flat}), .Dim = c({', '.join(str(d) for d in a.shape)}))\n")
+
+
+def test_dump_ingest_matches_array_construction(tmp_path):
+    """SURVEY 8f row 4: the stanc-style constructor fed by the reference's R-dump reader stan::io::dump
+    (ST/io/dump.hpp) gives the same model as construction from arrays, and validates the data block the same way."""
+    from stan_b200.model import InvalidArgument
+    d = make_glm_data("poisson_log", 500, 4, 7)
+    p = tmp_path / "data.R"
+    _r_dump(str(p), N=500, K=4, X=d["X"], y=d["y"], G=7, group=d["group"])
+    m = stan_service.StanGLM.from_dump(str(p), "poisson_log")
+    ref = stan_service.StanGLM("poisson_log", d["X"], d["y"], d["group"], 7)
+    assert m.P == ref.P == 2 + 7 + 4
+    for th in theta_points(m.P, n_random=2, scale=0.2):
+        a, b = m.log_prob_grad(th), ref.log_prob_grad(th)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    m.close()
+    ref.close()
+    bad = tmp_path / "bad.R"
+    _r_dump(str(bad), N=500, K=4, X=d["X"][:, :3], y=d["y"])            # X has the wrong shape
+    with pytest.raises(InvalidArgument):
+        stan_service.StanGLM.from_dump(str(bad), "poisson_log")
