@@ -197,43 +197,52 @@ def run_b200(args):
         dist.all_gather(allbw, bw)
         weights = [float(t.item()) for t in allbw]
         rows = shard_rows_weighted(N_total, weights, rank)
-    X, y, grp, trials, r0, r1 = make_shard_ex(torch, dev, family, N_total, K, G, rank, world, rows=rows)
-    n_local = r1 - r0
-    torch.cuda.synchronize()
-    m = GLMModel(family, X.data_ptr(), y.data_ptr(), grp.data_ptr() if G else None, G, data_on_device=True,
-                 N=n_local, K=K, ldx=n_local, device=local_rank, rank=rank, world=world, N_total=N_total,
-                 trials=trials.data_ptr() if trials is not None else None)
-    if world > 1 and args.collective == "peer":
-        m.connect_peers_torch(dist, dev)      # in-kernel exchange through peer mailboxes (NVLink), no NCCL call
-    elif world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            uid = torch.frombuffer(bytearray(GLMModel.comm_unique_id()), dtype=torch.uint8).to(dev)
-        dist.broadcast(uid, 0)
-        m.comm_init(bytes(uid.cpu().numpy().tobytes()))
+    streamed = bool(args.streamed)
+    if streamed:
+        m, n_local, N_total, sample, par_sample = build_streamed(torch, dist, dev, args, rank, world, local_rank)
+        m_local, par_rows = None, (par_sample[0].shape[0] if par_sample is not None else 0)
+        if world > 1 and args.collective == "peer":
+            m.connect_peers_torch(dist, dev)
+        elif world > 1:
+            raise SystemExit("--streamed runs with the in-launch peer exchange")
+    else:
+        X, y, grp, trials, r0, r1 = make_shard_ex(torch, dev, family, N_total, K, G, rank, world, rows=rows)
+        n_local = r1 - r0
+        torch.cuda.synchronize()
+        m = GLMModel(family, X.data_ptr(), y.data_ptr(), grp.data_ptr() if G else None, G, data_on_device=True,
+                     N=n_local, K=K, ldx=n_local, device=local_rank, rank=rank, world=world, N_total=N_total,
+                     trials=trials.data_ptr() if trials is not None else None)
+        if world > 1 and args.collective == "peer":
+            m.connect_peers_torch(dist, dev)      # in-kernel exchange through peer mailboxes (NVLink), no NCCL call
+        elif world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                uid = torch.frombuffer(bytearray(GLMModel.comm_unique_id()), dtype=torch.uint8).to(dev)
+            dist.broadcast(uid, 0)
+            m.comm_init(bytes(uid.cpu().numpy().tobytes()))
 
-    # CPU-baseline sample is taken before X is released (rank 0, N=1 only)
-    sample = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ns = min(args.cpu_sample_rows, n_local)
-        sample = (X[:, :ns].cpu().numpy().T, y[:ns].cpu().numpy(), grp[:ns].cpu().numpy() if G else None,
-                  trials[:ns].cpu().numpy() if trials is not None else None)
-    # parity material (every rank): a row sample of this shard for the CPU checker, and -- memory permitting -- the
-    # whole shard as a second, UNSHARDED handle for the additivity check
-    par_rows = min(args.parity_rows, n_local) if not args.no_parity else 0
-    par_sample = None
-    if par_rows:
-        par_sample = (X[:, :par_rows].cpu().numpy().T, y[:par_rows].cpu().numpy(),
-                      grp[:par_rows].cpu().numpy() if G else None,
-                      trials[:par_rows].cpu().numpy() if trials is not None else None)
-    m_local = None
-    free_b, _tot = torch.cuda.mem_get_info()
-    if world > 1 and par_rows and free_b > 1.3 * 8 * n_local * (K + 3):
-        m_local = GLMModel(family, X.data_ptr(), y.data_ptr(), grp.data_ptr() if G else None, G, data_on_device=True,
-                           N=n_local, K=K, ldx=n_local, device=local_rank,
-                           trials=trials.data_ptr() if trials is not None else None)
-    del X, y, grp, trials
-    torch.cuda.empty_cache()
+        # CPU-baseline sample is taken before X is released (rank 0, N=1 only)
+        sample = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            ns = min(args.cpu_sample_rows, n_local)
+            sample = (X[:, :ns].cpu().numpy().T, y[:ns].cpu().numpy(), grp[:ns].cpu().numpy() if G else None,
+                      trials[:ns].cpu().numpy() if trials is not None else None)
+        # parity material (every rank): a row sample of this shard for the CPU checker, and -- memory permitting -- the
+        # whole shard as a second, UNSHARDED handle for the additivity check
+        par_rows = min(args.parity_rows, n_local) if not args.no_parity else 0
+        par_sample = None
+        if par_rows:
+            par_sample = (X[:, :par_rows].cpu().numpy().T, y[:par_rows].cpu().numpy(),
+                          grp[:par_rows].cpu().numpy() if G else None,
+                          trials[:par_rows].cpu().numpy() if trials is not None else None)
+        m_local = None
+        free_b, _tot = torch.cuda.mem_get_info()
+        if world > 1 and par_rows and free_b > 1.3 * 8 * n_local * (K + 3):
+            m_local = GLMModel(family, X.data_ptr(), y.data_ptr(), grp.data_ptr() if G else None, G, data_on_device=True,
+                               N=n_local, K=K, ldx=n_local, device=local_rank,
+                               trials=trials.data_ptr() if trials is not None else None)
+        del X, y, grp, trials
+        torch.cuda.empty_cache()
 
     P = m.num_params_r()
     bytes_per_gradient = m.bytes_per_gradient()
@@ -361,6 +370,8 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(N_total, K, family, G, args.config), "rows_total": N_total,
                    "rows_per_gpu": n_local, "cols": K, "groups": G,
+                   **({"streamed_build_s": getattr(args, "build_seconds", None),
+                       "hbm_gb_per_gpu": round(bytes_per_gradient / 1e9, 1)} if streamed else {}),
                    "sharding": f"rows x{world}" + (f" weighted by per-GPU copy bandwidth {[round(w) for w in weights]} GB/s"
                                                    if weights else "") + ((", likelihood partials exchanged inside the gradient launch (peer mailboxes over NVLink)"
                                                     if args.collective == "peer" else
@@ -390,6 +401,58 @@ def run_b200(args):
         m.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def build_streamed(torch, dist, dev, args, rank, world, local_rank):
+    """BASELINE configs[4] at HBM scale: the design matrix is generated and handed to the backend chunk by chunk
+    (B200GLM_FLAG_STREAMED / b200glm_append_rows), so it is resident ONCE -- as the panels the kernel streams.
+    --rows 0: as many rows per GPU as fit (free memory minus head-room), the same on every rank.
+    Synthetic data: one base chunk of standard normals per rank, chunk c = base * (1 + c / 1024) (cheap to produce,
+    every row distinct); y ~ bernoulli_logit(0.3 + x . beta)."""
+    from stan_b200 import GLMModel
+    K, family = args.cols, args.family
+    if family != "bernoulli_logit" or args.groups:
+        raise SystemExit("--streamed is wired for the bernoulli_logit configuration without groups")
+    chunk = 131_072
+    if args.rows <= 0:
+        free_b, _tot = torch.cuda.mem_get_info()
+        t = torch.tensor([free_b], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        wr = 16 if K + 1 <= 512 else (8 if K + 1 <= 1024 else 4)          # wide_rows_for / wide_cps (glm_wide_kernel.cuh)
+        cps = 32 // (wr // 4)
+        cpad = (K + cps) // cps * cps if K > 256 else K + 1
+        head = 6 * 8 * chunk * K + (6 << 30)                 # generator temporaries + workspaces + slack
+        n_local = int((float(t.item()) - head) // (8 * cpad)) // chunk * chunk
+    else:
+        n_local = args.rows
+    N_total = n_local * world
+    m = GLMModel.streamed(family, n_local, K, device=local_rank, rank=rank, world=world, N_total=N_total)
+    g = torch.Generator(device=dev).manual_seed(20261017 + rank)
+    base = torch.randn((K, chunk), generator=g, device=dev, dtype=torch.float64)
+    beta = torch.from_numpy(np.random.Generator(np.random.Philox(key=[20261017, 1])).standard_normal(K) / np.sqrt(K)).to(dev)
+    sample = par_sample = None
+    Xc = torch.empty_like(base)
+    t0 = time.time()
+    for c, r0 in enumerate(range(0, n_local, chunk)):
+        n = min(chunk, n_local - r0)
+        torch.mul(base, 1.0 + c / 1024.0, out=Xc)
+        u = torch.rand(chunk, generator=g, device=dev, dtype=torch.float64)
+        yc = (u < torch.sigmoid(0.3 + beta @ Xc)).to(torch.int32)
+        if c == 0:
+            pr = 0 if args.no_parity else min(args.parity_rows, 20_000, n)
+            if pr:
+                par_sample = (Xc[:, :pr].cpu().numpy().T, yc[:pr].cpu().numpy(), None, None)
+            if rank == 0 and world == 1 and not args.no_cpu_baseline:
+                ns = min(args.cpu_sample_rows, 100_000, n)
+                sample = (Xc[:, :ns].cpu().numpy().T, yc[:ns].cpu().numpy(), None, None)
+        torch.cuda.synchronize()
+        m.append_rows(Xc.data_ptr(), yc.data_ptr(), None, n=n, ldx=chunk)
+    m.finalize()
+    args.build_seconds = time.time() - t0
+    del base, Xc
+    torch.cuda.empty_cache()
+    return m, n_local, N_total, sample, par_sample
 
 
 def parity_record(torch, dist, dev, m, m_local, sample, family, G, K, rank, world, local_rank):
@@ -695,6 +758,8 @@ def main():
     ap.add_argument("--family", default=None)
     ap.add_argument("--groups", type=int, default=None)
     ap.add_argument("--weak", action="store_true", help="--rows is per GPU (weak scaling)")
+    ap.add_argument("--streamed", action="store_true",
+                    help="config 5: build the handle chunk by chunk (X resident once); --rows 0 = as many rows per GPU as fit")
     ap.add_argument("--balance", action="store_true",
                     help="N > 1: split the rows in proportion to each GPU's measured copy bandwidth (default: equal)")
     ap.add_argument("--chains", type=int, default=1024)

@@ -52,6 +52,11 @@ enum { B200GLM_BERNOULLI_LOGIT = 0, B200GLM_POISSON_LOG = 1, B200GLM_NORMAL_ID =
 /* desc.flags: use the wide-matrix kernel (16-row panels split over the CTA; the default for K > 256)
  * even for a narrow X -- for tests of that kernel at small K */
 #define B200GLM_FLAG_FORCE_WIDE 1
+/* desc.flags: streamed construction -- b200glm_create only reserves the panels for desc.N rows (X, y, trials are
+ * ignored and may be NULL; G must be 0); the rows then arrive through b200glm_append_rows in chunks, each re-laid out
+ * into the panels at once, and b200glm_finalize makes the handle usable.  For matrices that fill the HBM: X is never
+ * resident twice (BASELINE configs[4]: 8 x ~160 GB). */
+#define B200GLM_FLAG_STREAMED 2
 
 typedef struct b200glm_handle b200glm_handle;
 
@@ -83,6 +88,14 @@ typedef struct b200glm_desc {
  * to_matrix_cl).  The caller keeps ownership of every pointer in desc. */
 int b200glm_create(const b200glm_desc* desc, b200glm_handle** out);
 void b200glm_destroy(b200glm_handle* h);
+/* Streamed construction (B200GLM_FLAG_STREAMED): the next n rows of the design matrix -- X column-major n x K with
+ * leading dimension ldx, y_int or y_real, trials (binomial_logit) -- host or device pointers as desc.data_on_device
+ * says.  Every chunk but the last must be a multiple of 32 rows (the panel height).  The buffers may be reused as soon
+ * as the call returns.  (The stanc-generated constructor reads the whole data block at once; this is the analogue for
+ * a matrix that only fits once: SM/opencl/copy.hpp:45 to_matrix_cl, chunk by chunk.) */
+int b200glm_append_rows(b200glm_handle* h, int64_t n, const double* X, int64_t ldx, const int32_t* y_int,
+                        const double* y_real, const int32_t* trials);
+int b200glm_finalize(b200glm_handle* h);
 
 /* prob_grad::num_params_r()  (ST/model/prob_grad.hpp:19-84) */
 int32_t b200glm_num_params(const b200glm_handle* h);

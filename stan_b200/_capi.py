@@ -11,7 +11,7 @@ FAMILY = {"bernoulli_logit": 0, "poisson_log": 1, "normal_id": 2, "binomial_logi
 
 # every symbol include/b200glm.h declares
 SYMBOLS = [
-    "b200glm_create", "b200glm_destroy", "b200glm_num_params", "b200glm_log_prob_grad", "b200glm_log_prob",
+    "b200glm_create", "b200glm_destroy", "b200glm_append_rows", "b200glm_finalize", "b200glm_num_params", "b200glm_log_prob_grad", "b200glm_log_prob",
     "b200glm_set_state", "b200glm_leapfrog", "b200glm_leapfrog_async", "b200glm_grad_async", "b200glm_sync",
     "b200glm_stream", "b200glm_result_device", "b200glm_comm_unique_id", "b200glm_comm_init",
     "b200glm_batch_reserve", "b200glm_log_prob_grad_batched", "b200glm_set_state_batched",
@@ -60,6 +60,9 @@ def lib():
         dp = C.POINTER(C.c_double)
         L.b200glm_create.argtypes = [C.POINTER(Desc), C.POINTER(C.c_void_p)]
         L.b200glm_destroy.argtypes = [C.c_void_p]
+        L.b200glm_append_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
+        L.b200glm_finalize.argtypes = [C.c_void_p]
         L.b200glm_destroy.restype = None
         L.b200glm_num_params.argtypes = [C.c_void_p]
         L.b200glm_log_prob_grad.argtypes = [C.c_void_p, C.c_int32, dp, C.c_int32, C.c_int32, dp, dp]

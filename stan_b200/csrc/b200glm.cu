@@ -125,6 +125,11 @@ struct b200glm_handle {
   double lgamma_sum_total = 0.0;
   bool bad_y = false;        // any shard holds an out-of-range y (after b200glm_comm_init / set_shard_constants_total)
   bool bad_y_local = false;  // this shard does
+  // streamed construction (B200GLM_FLAG_STREAMED): rows arrive through b200glm_append_rows and are re-laid out into the
+  // panels chunk by chunk, so X never has to be resident a second time next to its panel copy
+  bool streamed = false, ready = true;
+  long long rows_appended = 0;
+  double bad_count = 0.0;
   int pdl_prefetch = 2;     // B200GLM_PDL_PREFETCH=<stages> (A/B runs); see the TMA producer in glm_kernels.cuh
   bool tl_repeat = false;   // B200GLM_TL_REPEAT=1 (timeline runs only): the last CTA sums the partial rows twice
   bool inline_theta = true; // B200GLM_NO_INLINE_THETA=1: always upload theta with a host-to-device copy (A/B runs)
@@ -224,6 +229,10 @@ size_t fixed_smem_bytes(int K, int G, int stage_a, int S, int P_state = 0, int G
 
 int validate_slot(b200glm_handle* h, int slot) {
   if (!h) return B200GLM_INVALID;
+  if (!h->ready) {
+    h->set_error("streamed handle: b200glm_finalize has not been called (or not all rows were appended)");
+    return B200GLM_INVALID;
+  }
   if (slot < 0 || slot >= (int)h->slots.size()) {
     h->set_error("slot out of range");
     return B200GLM_INVALID;
@@ -579,12 +588,18 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   } tmp;
   const b200glm_desc& d = h->d;
   if (d.family < 0 || d.family > 4) return fail(B200GLM_INVALID, "unknown family");
-  if (d.N > 0 && d.family == B200GLM_BINOMIAL_LOGIT && !d.trials) return fail(B200GLM_INVALID, "trials is null");
+  h->streamed = (d.flags & B200GLM_FLAG_STREAMED) != 0;
   if (d.N < 0 || d.K < 0 || d.G < 0) return fail(B200GLM_INVALID, "negative size");
-  if (d.N > 0 && d.K > 0 && (!d.X || d.ldx < d.N)) return fail(B200GLM_INVALID, "X null or ldx < N");
-  if (d.N > 0 && d.family == B200GLM_NORMAL_ID && !d.y_real) return fail(B200GLM_INVALID, "y_real is null");
-  if (d.N > 0 && d.family != B200GLM_NORMAL_ID && !d.y_int) return fail(B200GLM_INVALID, "y_int is null");
-  if (d.G > 0 && d.N > 0 && !d.group) return fail(B200GLM_INVALID, "group is null");
+  if (h->streamed) {
+    if (d.G > 0) return fail(B200GLM_INVALID, "streamed construction needs a scalar intercept (G == 0): the group sort needs all rows");
+    h->ready = d.N == 0;
+  } else {
+    if (d.N > 0 && d.family == B200GLM_BINOMIAL_LOGIT && !d.trials) return fail(B200GLM_INVALID, "trials is null");
+    if (d.N > 0 && d.K > 0 && (!d.X || d.ldx < d.N)) return fail(B200GLM_INVALID, "X null or ldx < N");
+    if (d.N > 0 && d.family == B200GLM_NORMAL_ID && !d.y_real) return fail(B200GLM_INVALID, "y_real is null");
+    if (d.N > 0 && d.family != B200GLM_NORMAL_ID && !d.y_int) return fail(B200GLM_INVALID, "y_int is null");
+    if (d.G > 0 && d.N > 0 && !d.group) return fail(B200GLM_INVALID, "group is null");
+  }
   if (!(d.prior_alpha_sd > 0) || !(d.prior_beta_sd > 0)) return fail(B200GLM_INVALID, "prior scales must be > 0");
   if (d.n_slots < 1) h->d.n_slots = 1;
   if (const char* e = std::getenv("B200GLM_NO_PDL")) h->pdl = !(e[0] == '1');
@@ -700,11 +715,12 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   int32_t* d_group = nullptr;
   int32_t* d_trials = nullptr;
   long long* d_perm = nullptr;
+  const bool upload_now = d.N > 0 && !h->streamed;
   bool own_y = false, own_group = false;
   void *t_y = nullptr, *t_yr = nullptr, *t_trials = nullptr, *t_group = nullptr, *t_perm = nullptr, *t_X = nullptr,
        *t_stats = nullptr;   // what `tmp` frees: the OWNED temporaries only (never the caller's device pointers)
   for (void** q : {&t_y, &t_yr, &t_trials, &t_group, &t_perm, &t_X, &t_stats}) tmp.track(q);
-  if (d.N > 0) {
+  if (upload_now) {
     if (d.data_on_device) {
       d_y = const_cast<int32_t*>(d.y_int);
       d_yr = const_cast<double*>(d.y_real);
@@ -735,7 +751,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     }
   }
   // data checks + lgamma constant
-  if (d.N > 0 && d.family != B200GLM_NORMAL_ID) {
+  if (upload_now && d.family != B200GLM_NORMAL_ID) {
     const int nb = 296;
     double* d_stats;
     CREATE_TRY(cudaMalloc(&d_stats, sizeof(double) * 2 * nb));
@@ -821,7 +837,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   }
   // X: device-resident or staged from the host in row chunks
   const int PR = h->panel_rows, SWZ = h->wide ? 0 : 1;
-  if (d.N > 0) {
+  if (upload_now) {
     if (d.data_on_device || d.K == 0) {
       relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(d.X, d.ldx, 0, d_y, d_yr, d_group, d_trials, d_perm, 0, d.N,
                                                                     d.N, d.K, h->C, 0, h->Cpad, h->panels, PR, h->Cpad, SWZ);
@@ -1369,6 +1385,118 @@ int b200glm_batch_sync(b200glm_handle* h) {
 }
 
 void* b200glm_batch_stream(b200glm_handle* h) { return (h && h->batch) ? (void*)h->batch->stream : nullptr; }
+
+int b200glm_append_rows(b200glm_handle* h, int64_t n, const double* X, int64_t ldx, const int32_t* y_int,
+                        const double* y_real, const int32_t* trials) {
+  if (!h) return B200GLM_INVALID;
+  const b200glm_desc& d = h->d;
+  if (!h->streamed || h->ready) {
+    h->set_error("b200glm_append_rows: not a streamed handle, or already finalized");
+    return B200GLM_INVALID;
+  }
+  if (n <= 0 || h->rows_appended + n > d.N) {
+    h->set_error("b200glm_append_rows: chunk is empty or exceeds the rows reserved at b200glm_create");
+    return B200GLM_INVALID;
+  }
+  if (h->rows_appended + n < d.N && n % h->panel_rows != 0) {
+    h->set_error("b200glm_append_rows: every chunk but the last must be a multiple of " + std::to_string(h->panel_rows) + " rows");
+    return B200GLM_INVALID;
+  }
+  if ((d.K > 0 && (!X || ldx < n)) || (d.family == B200GLM_NORMAL_ID ? !y_real : !y_int)
+      || (d.family == B200GLM_BINOMIAL_LOGIT && !trials)) {
+    h->set_error("b200glm_append_rows: null pointer or ldx < n");
+    return B200GLM_INVALID;
+  }
+  CUDA_TRY(h, cudaSetDevice(d.device));
+  cudaStream_t st = h->slots[0]->stream;
+  const double* dX = X;
+  const int32_t* dy = y_int;
+  const double* dyr = y_real;
+  const int32_t* dt = trials;
+  void *tX = nullptr, *ty = nullptr, *tt = nullptr;
+  int rc = B200GLM_OK;
+  auto fail_cuda = [&](cudaError_t e, const char* what) {
+    h->set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    rc = B200GLM_CUDA;
+  };
+  if (!d.data_on_device) {   // host chunk: stage it (the chunk, not the matrix, is what is resident twice)
+    cudaError_t e;
+    if (d.K > 0) {
+      if ((e = cudaMalloc(&tX, sizeof(double) * (size_t)n * d.K)) != cudaSuccess) fail_cuda(e, "cudaMalloc(chunk)");
+      else if ((e = cudaMemcpy2D(tX, sizeof(double) * n, X, sizeof(double) * ldx, sizeof(double) * n, d.K,
+                                 cudaMemcpyHostToDevice)) != cudaSuccess) fail_cuda(e, "cudaMemcpy2D(chunk)");
+      dX = static_cast<const double*>(tX);
+      ldx = n;
+    }
+    const size_t ybytes = (d.family == B200GLM_NORMAL_ID ? sizeof(double) : sizeof(int32_t)) * (size_t)n;
+    if (rc == B200GLM_OK && (e = cudaMalloc(&ty, ybytes)) != cudaSuccess) fail_cuda(e, "cudaMalloc(y)");
+    if (rc == B200GLM_OK && (e = cudaMemcpy(ty, d.family == B200GLM_NORMAL_ID ? (const void*)y_real : (const void*)y_int,
+                                            ybytes, cudaMemcpyHostToDevice)) != cudaSuccess) fail_cuda(e, "cudaMemcpy(y)");
+    dy = static_cast<const int32_t*>(ty);
+    dyr = static_cast<const double*>(ty);
+    if (rc == B200GLM_OK && trials) {
+      if ((e = cudaMalloc(&tt, sizeof(int32_t) * (size_t)n)) != cudaSuccess) fail_cuda(e, "cudaMalloc(trials)");
+      else if ((e = cudaMemcpy(tt, trials, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice)) != cudaSuccess)
+        fail_cuda(e, "cudaMemcpy(trials)");
+      dt = static_cast<const int32_t*>(tt);
+    }
+  }
+  if (rc == B200GLM_OK) {
+    const long long r0 = h->rows_appended;
+    // y / trials pointers are chunk-relative: relayout_kernel indexes them with the GLOBAL row, so shift them back
+    const int32_t* y_g = d.family == B200GLM_NORMAL_ID ? nullptr : dy - r0;
+    const double* yr_g = d.family == B200GLM_NORMAL_ID ? dyr - r0 : nullptr;
+    const int32_t* t_g = dt ? dt - r0 : nullptr;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, d.device);
+    relayout_kernel<<<4 * prop.multiProcessorCount, 256, 0, st>>>(dX, ldx, r0, y_g, yr_g, nullptr, t_g, nullptr, r0, n,
+                                                                  d.N, d.K, h->C, 0, h->Cpad, h->panels, h->panel_rows,
+                                                                  h->Cpad, h->wide ? 0 : 1);
+    if (d.family != B200GLM_NORMAL_ID) {   // data checks + the propto=false constant of this chunk
+      const int nb = 296;
+      double* d_stats = nullptr;
+      cudaError_t e = cudaMalloc(&d_stats, sizeof(double) * 2 * nb);
+      if (e != cudaSuccess) fail_cuda(e, "cudaMalloc(stats)");
+      else {
+        y_stats_kernel<<<nb, 256, 0, st>>>(dy, dt, n, d.family, d_stats);
+        std::vector<double> hs(2 * nb);
+        if ((e = cudaMemcpyAsync(hs.data(), d_stats, sizeof(double) * 2 * nb, cudaMemcpyDeviceToHost, st)) != cudaSuccess
+            || (e = cudaStreamSynchronize(st)) != cudaSuccess)
+          fail_cuda(e, "y_stats");
+        for (int i = 0; i < nb && rc == B200GLM_OK; ++i) {
+          h->bad_count += hs[2 * i];
+          h->lgamma_sum += hs[2 * i + 1];
+        }
+        cudaFree(d_stats);
+      }
+    }
+    cudaError_t e = cudaStreamSynchronize(st);   // the caller may reuse the chunk buffer as soon as this returns
+    if (rc == B200GLM_OK && e != cudaSuccess) fail_cuda(e, "relayout");
+    if (rc == B200GLM_OK && (e = cudaGetLastError()) != cudaSuccess) fail_cuda(e, "relayout");
+  }
+  cudaFree(tX);
+  cudaFree(ty);
+  cudaFree(tt);
+  if (rc == B200GLM_OK) {
+    h->rows_appended += n;
+    h->launches++;
+  }
+  return rc;
+}
+
+int b200glm_finalize(b200glm_handle* h) {
+  if (!h) return B200GLM_INVALID;
+  if (!h->streamed) return B200GLM_OK;
+  if (h->rows_appended != h->d.N) {
+    h->set_error("b200glm_finalize: " + std::to_string(h->rows_appended) + " of " + std::to_string((long long)h->d.N)
+                 + " rows appended");
+    return B200GLM_INVALID;
+  }
+  h->bad_y = h->bad_y_local = h->bad_count > 0;
+  h->lgamma_sum_total = h->lgamma_sum;
+  h->ready = true;
+  return B200GLM_OK;
+}
 
 int b200glm_measure_peaks(int32_t device, double* read_gbs, double* dmma_tflops) {
   if (cudaSetDevice(device) != cudaSuccess) return B200GLM_CUDA;

@@ -263,7 +263,7 @@ __device__ __forceinline__ void stage_theta(const KernelParams& p, int t, int nt
 template <int FAMILY>
 __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& p, double* sh_scratch,
                                                             int* sh_is_last, const StateSmem& st,
-                                                            double* scratch /* >= 10 x (K + 35) doubles of idle smem */) {
+                                                            double* scratch /* idle smem: >= warps x min(512, K + 34) doubles */) {
   const int tid = threadIdx.x, nt = blockDim.x, grid = gridDim.x;
   const int K = p.K, G = p.G, P = p.P;
   __threadfence();
@@ -300,44 +300,50 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
       __syncthreads();
       if (tid == 0) tl_stamp(p, grid + 1, 5);    // end of the cold pass
     }
-    for (int c0 = 0; c0 < n_chunks; c0 += 4) {   // up to 4 chunks (128 columns) per sweep over the rows
-      double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      const double* src = p.partials + c0 * 32 + lane;
-      int r = warp;
-      for (; r + 3 * nw < grid; r += 4 * nw) {
-        double v[4][4];
+    constexpr int CB = 16;                       // chunks (of 32 columns) summed per block: bounds the scratch
+    const int sstride = min(CB, n_chunks) * 32;  // doubles of scratch per warp
+    for (int cb = 0; cb < n_chunks; cb += CB) {
+      const int cb_n = min(CB, n_chunks - cb);
+      if (cb > 0) __syncthreads();               // the previous block's scratch has been folded
+      for (int c0 = cb; c0 < cb + cb_n; c0 += 4) {   // up to 4 chunks (128 columns) per sweep over the rows
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* src = p.partials + c0 * 32 + lane;
+        int r = warp;
+        for (; r + 3 * nw < grid; r += 4 * nw) {
+          double v[4][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              v[u][q] = (c0 + q) * 32 + lane < n_sums ? __ldcg(src + (size_t)(r + u * nw) * p.pstride + q * 32) : 0.0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] += v[u][q];
+        }
+        for (; r < grid; r += nw) {
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            v[u][q] = (c0 + q) * 32 + lane < n_sums ? __ldcg(src + (size_t)(r + u * nw) * p.pstride + q * 32) : 0.0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) acc[q] += v[u][q];
-      }
-      for (; r < grid; r += nw) {
+            if ((c0 + q) * 32 + lane < n_sums) acc[q] += __ldcg(src + (size_t)r * p.pstride + q * 32);
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if ((c0 + q) * 32 + lane < n_sums) acc[q] += __ldcg(src + (size_t)r * p.pstride + q * 32);
+          if (c0 + q < cb + cb_n) scratch[warp * sstride + (c0 + q - cb) * 32 + lane] = acc[q];
       }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (c0 + q < n_chunks) scratch[warp * (n_chunks * 32) + (c0 + q) * 32 + lane] = acc[q];
-    }
-    if (tid == 0) tl_stamp(p, grid + 1, 1);      // this warp's rows loaded
-    __syncthreads();
-    for (int j = tid; j < n_sums; j += nt) {
-      double v = 0.0;
-      for (int w = 0; w < nw; ++w) v += scratch[w * (n_chunks * 32) + j];
-      if (j < K)
-        lik[p.off_beta + j] = v;
-      else if (j == K)
-        lik[P] = v;
-      else if (j == K + 2)
-        lik[P + 1] = v;      // neg_binomial_2_log: sum of the per-row d/dphi terms
-      else if (G == 0)
-        lik[0] = v;
+      if (tid == 0 && cb == 0) tl_stamp(p, grid + 1, 1);   // this warp's rows of the first block loaded
+      __syncthreads();
+      for (int j = cb * 32 + tid; j < min(n_sums, (cb + cb_n) * 32); j += nt) {
+        double v = 0.0;
+        for (int w = 0; w < nw; ++w) v += scratch[w * sstride + (j - cb * 32)];
+        if (j < K)
+          lik[p.off_beta + j] = v;
+        else if (j == K)
+          lik[P] = v;
+        else if (j == K + 2)
+          lik[P + 1] = v;      // neg_binomial_2_log: sum of the per-row d/dphi terms
+        else if (G == 0)
+          lik[0] = v;
+      }
     }
   }
   if (p.group_fused) {

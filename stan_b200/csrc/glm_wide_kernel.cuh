@@ -12,7 +12,7 @@
 //   issued in bursts while P2 freed slots and HBM idled one latency per panel (ncu: 57 % DRAM, 71 % of
 //   the copy roof); with the ring holding >= 2 panels the stream is continuous (89 %).
 //
-// CTA (persistent, one per SM) = 8 consumer warps + 1 TMA producer warp + 1 link warp.
+// CTA (persistent, one per SM) = 8 consumer warps + 1 TMA producer warp + 2 link warps (even / odd row panels).
 //   The shared-memory ring has T >= 2J sub-panel slots: the panel between its eta pass and its X^T r
 //   pass stays resident, the rest holds the following panel(s).
 //   consumer warp w owns sub-panels j = w, w+8, ... of every row panel (so it owns those columns'
@@ -34,11 +34,12 @@
 namespace b200glm {
 
 constexpr int WIDE_CONSUMER_WARPS = 8;
-constexpr int WIDE_THREADS = (WIDE_CONSUMER_WARPS + 2) * 32;
+constexpr int WIDE_LINK_WARPS = 2;   // alternate over the row panels (even / odd), see the link warps below
+constexpr int WIDE_THREADS = (WIDE_CONSUMER_WARPS + 1 + WIDE_LINK_WARPS) * 32;
 constexpr int WIDE_MAX_SLOTS = 96;
 // named barriers: ETA / R, double-buffered by panel parity
-enum { WIDE_BAR_ETA = 1, WIDE_BAR_R = 3 };
-constexpr int WIDE_BAR_COUNT = (WIDE_CONSUMER_WARPS + 1) * 32;  // consumers + link warp
+enum { WIDE_BAR_ETA = 1, WIDE_BAR_R = 3, WIDE_BAR_LINK = 5 };
+constexpr int WIDE_BAR_COUNT = (WIDE_CONSUMER_WARPS + 1) * 32;  // consumers + the link warp of that panel parity
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(after_a);     // T
   uint64_t* empty_bar = full_bar + T;                            // T
   __shared__ double sh_scratch[64];
+  __shared__ double sh_link[4];
   __shared__ int sh_is_last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -254,7 +256,14 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
       }
     }
   } else {
-    // =============================== link warp ===============================
+    // =============================== link warps ===============================
+    // Link warp lw takes the row panels n = lw, lw + 2, ...  The eta / r buffers and both named barriers are already
+    // double-buffered by panel parity, so the two warps never share one.  Why two: the link step of a panel is ONE
+    // dependent fp64 chain (sum of the 8 partial etas, exp, log1p, a division: ~2000 cycles) on WR <= 16 lanes, and a
+    // panel is due every ~2600 cycles at the HBM rate -- with a single link warp that chain set the pace of the
+    // whole CTA (ncu round 1: 2.36 barrier-stall cycles per issue, 75.6 % of DRAM peak against 89 % for the narrow
+    // kernel); the consumers publish eta(n+1) before they wait for r(n), so the two chains overlap.
+    const int lw = warp - (WIDE_CONSUMER_WARPS + 1);
     const int r = lane & (WR - 1);
     const int jy = K / KC, coly = K - jy * KC;            // y lives in column K
     const int jt = (K + 1) / KC, colt = K + 1 - jt * KC;  // binomial population sizes in column K+1
@@ -262,6 +271,18 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
     const int jg = Kg / KC, colg = Kg - jg * KC;          // group id after the y (and trials) columns (G > 0)
     int slot_y = jy, slot_g = jg, slot_t = jt;
     uint32_t par_y = 0, par_g = 0, par_t = 0;
+    auto advance = [&](int& sl, uint32_t& pr, int panels) {   // ring position `panels` row panels further on
+      sl += panels * J;
+      while (sl >= T) {
+        sl -= T;
+        pr ^= 1u;
+      }
+    };
+    if (lw == 1) {
+      advance(slot_y, par_y, 1);
+      advance(slot_g, par_g, 1);
+      advance(slot_t, par_t, 1);
+    }
     const double alpha = G > 0 ? 0.0 : theta_at(0);
     LinkConst lc;
     lc.inv_sigma = 1.0;
@@ -277,7 +298,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
       lc.lg_phi = lgamma(lc.phi);
     }
     double lp_acc = 0.0, r_acc = 0.0, x_acc = 0.0;
-    for (long long n = 0; n < n_my; ++n) {
+    for (long long n = lw; n < n_my; n += WIDE_LINK_WARPS) {
       const int buf = (int)(n & 1);
       const long long pi = blockIdx.x + n * grid;
       mbar_wait(&full_bar[slot_y], par_y);
@@ -315,29 +336,25 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
       }
       __threadfence_block();
       named_bar_arrive(WIDE_BAR_R + buf, WIDE_BAR_COUNT);
-      slot_y += J;
-      if (slot_y >= T) {
-        slot_y -= T;
-        par_y ^= 1u;
-      }
-      slot_g += J;
-      if (slot_g >= T) {
-        slot_g -= T;
-        par_g ^= 1u;
-      }
-      slot_t += J;
-      if (slot_t >= T) {
-        slot_t -= T;
-        par_t ^= 1u;
-      }
+      advance(slot_y, par_y, WIDE_LINK_WARPS);
+      advance(slot_g, par_g, WIDE_LINK_WARPS);
+      advance(slot_t, par_t, WIDE_LINK_WARPS);
     }
     lp_acc = warp_sum(lp_acc);
     r_acc = warp_sum(r_acc);
     x_acc = warp_sum(x_acc);
-    if (lane == 0) {
-      my_part[K] = lp_acc;
-      my_part[K + 1] = r_acc;
-      my_part[K + 2] = x_acc;   // neg_binomial_2_log: sum of the per-row d/dphi terms
+    // the odd-panel warp hands its sums to the even-panel warp (fixed order: even + odd)
+    if (lw == 1 && lane == 0) {
+      sh_link[0] = lp_acc;
+      sh_link[1] = r_acc;
+      sh_link[2] = x_acc;
+    }
+    __threadfence_block();
+    named_bar_sync(WIDE_BAR_LINK, WIDE_LINK_WARPS * 32);
+    if (lw == 0 && lane == 0) {
+      my_part[K] = lp_acc + sh_link[0];
+      my_part[K + 1] = r_acc + sh_link[1];
+      my_part[K + 2] = x_acc + sh_link[2];   // neg_binomial_2_log: sum of the per-row d/dphi terms
     }
   }
 

@@ -49,11 +49,11 @@ def make_desc(family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=
         d.N, d.K, d.ldx = int(N), int(K), int(ldx if ldx is not None else N)
         d.X = int(X) if X else None
         if fam == 2:
-            d.y_real, d.y_int = int(y), None
+            d.y_real, d.y_int = (int(y) if y else None), None
         else:
-            d.y_int, d.y_real = int(y), None
+            d.y_int, d.y_real = (int(y) if y else None), None
         d.group = int(group) if G else None
-        d.trials = int(trials) if fam == 3 else None
+        d.trials = int(trials) if (fam == 3 and trials) else None
     else:
         X = np.asfortranarray(X, dtype=np.float64)
         if X.ndim != 2:
@@ -94,13 +94,16 @@ def make_desc(family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=
 
 class GLMModel:
     def __init__(self, family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=1, N_total=0,
-                 grid_ctas=0, flags=0, data_on_device=False, N=None, K=None, ldx=None, trials=None, **priors):
+                 grid_ctas=0, flags=0, data_on_device=False, N=None, K=None, ldx=None, trials=None,
+                 _host_chunks=False, **priors):
         """X, y, group, trials: numpy arrays (host), or -- with data_on_device=True -- integer device
         pointers (e.g. torch tensor .data_ptr()) with N, K, ldx given explicitly."""
         self.L = _capi.lib()
         self.family = family
         d, keep = make_desc(family, X, y, group, G, device, n_slots, rank, world, N_total, grid_ctas, flags,
                             data_on_device, N, K, ldx, trials, **priors)
+        if _host_chunks:
+            d.data_on_device = 0
         self.N, self.K, self.G = int(d.N), int(d.K), int(G)
         self.rank, self.world = int(rank), int(world)
         h = C.c_void_p()
@@ -123,6 +126,35 @@ class GLMModel:
         if rc == _capi.INVALID:
             raise InvalidArgument(msg)
         raise CudaError(msg)
+
+    # ------------------------------------------------------------------ streamed construction
+    @classmethod
+    def streamed(cls, family, N, K, device=0, data_on_device=True, **kw):
+        """A handle with room for N rows and no data yet (B200GLM_FLAG_STREAMED): feed it with append_rows(), then
+        finalize().  X is then never resident a second time next to its panel copy."""
+        return cls(family, None, None, device=device, data_on_device=True, N=N, K=K, ldx=max(N, 1),
+                   flags=kw.pop("flags", 0) | 2, _host_chunks=not data_on_device, **kw)
+
+    def append_rows(self, X, y, trials=None, n=None, ldx=None):
+        """Next rows: device pointers (ints) with n / ldx given, or numpy arrays (column-major X) for a handle created
+        with data_on_device=False."""
+        if isinstance(X, (int, type(None))) and not isinstance(y, np.ndarray):
+            Xp, yp, tp = X, y, trials
+        else:
+            X = np.asfortranarray(X, dtype=np.float64)
+            y = np.ascontiguousarray(y, dtype=np.float64 if self.family == "normal_id" else np.int32)
+            n, ldx = X.shape[0], max(X.shape[0], 1)
+            Xp, yp = X.ctypes.data, y.ctypes.data
+            tp = None
+            if trials is not None:
+                trials = np.ascontiguousarray(trials, dtype=np.int32)
+                tp = trials.ctypes.data
+        real = self.family == "normal_id"
+        self._check(self.L.b200glm_append_rows(self.h, int(n), Xp, int(ldx if ldx is not None else n),
+                                               None if real else yp, yp if real else None, tp))
+
+    def finalize(self):
+        self._check(self.L.b200glm_finalize(self.h))
 
     def close(self):
         if getattr(self, "h", None):

@@ -383,3 +383,47 @@ def test_group_path_fused_matches_oracle_and_unfused(fam, N, K, G, fused, monkey
     assert np.max(np.abs(q1 - q)) < 1e-12 and rel_err(V1, V) < TOL and rel_err_vec(g1, gg) < TOL
     m.close()
     m_unfused.close()
+
+
+@pytest.mark.parametrize("fam,N,K,flags,chunk", [
+    ("bernoulli_logit", 10_003, 20, 0, 3_200), ("normal_id", 5_000, 300, 0, 1_600), ("binomial_logit", 4_097, 9, 0, 4_096),
+    ("poisson_log", 2_000, 7, 1, 640), ("neg_binomial_2_log", 3_001, 5, 0, 3_200)])
+def test_streamed_construction_equals_one_shot(fam, N, K, flags, chunk):
+    """B200GLM_FLAG_STREAMED + b200glm_append_rows + b200glm_finalize (X never resident twice): bitwise the same model
+    as b200glm_create from the whole matrix; host chunks and device chunks; errors for misuse."""
+    import torch
+    from stan_b200.model import InvalidArgument
+    d = make_glm_data(fam, N, K)
+    kw = {"trials": d["trials"]} if fam == "binomial_logit" else {}
+    one = GLMModel(fam, d["X"], d["y"], flags=flags, **kw)
+    th = theta_points(one.P, n_random=1, scale=0.1)[1]
+    want = one.log_prob_grad(th), one.log_prob(th, False, True)
+    for on_device in (False, True):
+        m = GLMModel.streamed(fam, N, K, data_on_device=on_device, flags=flags)
+        with pytest.raises(InvalidArgument):
+            m.log_prob_grad(th)                                    # not finalized
+        for r0 in range(0, N, chunk):
+            r1 = min(N, r0 + chunk)
+            Xc, yc = np.asfortranarray(d["X"][r0:r1]), d["y"][r0:r1]
+            tc = d["trials"][r0:r1] if fam == "binomial_logit" else None
+            if on_device:
+                Xt = torch.from_numpy(np.ascontiguousarray(Xc.T)).cuda()       # (K, n) row-major == column-major n x K
+                yt = torch.from_numpy(np.ascontiguousarray(yc)).cuda()
+                tt = torch.from_numpy(np.ascontiguousarray(tc)).cuda() if tc is not None else None
+                m.append_rows(Xt.data_ptr(), yt.data_ptr(), tt.data_ptr() if tt is not None else None, n=r1 - r0)
+                torch.cuda.synchronize()
+            else:
+                m.append_rows(Xc, yc, tc)
+        m.finalize()
+        got = m.log_prob_grad(th), m.log_prob(th, False, True)
+        assert got[0][0] == want[0][0] and np.array_equal(got[0][1], want[0][1]) and got[1] == want[1]
+        with pytest.raises(InvalidArgument):
+            m.append_rows(np.asfortranarray(d["X"][:32]), d["y"][:32], d["trials"][:32] if kw else None)   # already complete
+        m.close()
+    m = GLMModel.streamed(fam, N, K, data_on_device=False, flags=flags)
+    with pytest.raises(InvalidArgument):
+        m.append_rows(np.asfortranarray(d["X"][:33]), d["y"][:33], d["trials"][:33] if kw else None)       # not a multiple of the panel height
+    with pytest.raises(InvalidArgument):
+        m.finalize()                                               # rows missing
+    m.close()
+    one.close()
