@@ -622,7 +622,14 @@ def run_b200_batched(args):
         m.log_prob_grad_batched(th)
     e2e_value = C * ne / (time.perf_counter() - t0)
     flops = 4.0 * N * K * C
-    peak = 37.18   # TFLOP/s: register-resident DMMA.8x8x4 loop measured on this pool's B200 (profiles/r1_fp64_peak_microbench.txt)
+    # fp64 tensor-pipe peak measured NOW, in this process and under the clocks of this run (MEASURED_PEAKS.json has
+    # no fp64 entry): register-resident mma.sync.m8n8k4.f64 loop, b200glm_measure_peaks (stan_b200/csrc/measure.cuh)
+    from stan_b200 import _capi
+    clk2 = ClockSampler(local_rank)
+    clk2.start()
+    tp0 = time.time()
+    _, peak = _capi.measure_peaks(local_rank, read=False, dmma=True)
+    peak_clocks = clk2.stop(tp0, time.time())
     achieved = flops / (ms_per_step * 1e-3) / 1e12
     cpu_baseline = None
     if sample is not None:
@@ -640,7 +647,8 @@ def run_b200_batched(args):
                 "call": "b200glm_log_prob_grad_batched(host thetas) -> host lp, grad"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": "measured fp64 DMMA microbenchmark (tools/fp64_peak.cu); cuBLAS DGEMM 35.4",
+                     "traffic": None, "peak_source": "fp64 DMMA register loop measured in this run (b200glm_measure_peaks)",
+                     "peak_clocks": peak_clocks,
                      "kernel": "glm_batched_kernel<normal_id,13>", "algorithmic_flops_per_launch": flops,
                      "avg_launch_ms": ms_per_step},
         "cpu_baseline": cpu_baseline,

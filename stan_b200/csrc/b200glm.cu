@@ -196,6 +196,7 @@ kernel_fn pick_wide_shape(int wr, int spw, int spc) {
   if (wr == 16 && spw == 1 && spc == 4) return glm_wide_kernel<FAMILY, 16, 1, 4>;
   if (wr == 16 && spw == 1 && spc == 8) return glm_wide_kernel<FAMILY, 16, 1, 8>;
   if (wr == 8 && spw == 1 && spc == 8) return glm_wide_kernel<FAMILY, 8, 1, 8>;
+  if (wr == 4 && spw == 1 && spc == 4) return glm_wide_kernel<FAMILY, 4, 1, 4>;
   if (wr == 4 && spw == 1 && spc == 8) return glm_wide_kernel<FAMILY, 4, 1, 8>;
   if (wr == 4 && spw == 2 && spc == 8) return glm_wide_kernel<FAMILY, 4, 2, 8>;
   return nullptr;
@@ -612,6 +613,11 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   h->C = fam_group_col(d.family, d.K) + (d.G > 0 ? 1 : 0);
   h->wide = d.K > 256 || (d.flags & B200GLM_FLAG_FORCE_WIDE);
   h->panel_rows = h->wide ? wide_rows_for(h->C) : PANEL_ROWS;
+  if (h->wide)
+    if (const char* e = std::getenv("B200GLM_WIDE_ROWS")) {   // A/B runs: 16, 8 or 4 rows per panel
+      const int wr = std::atoi(e);
+      if (wr == 16 || wr == 8 || wr == 4) h->panel_rows = wr;
+    }
   h->n_panels = (d.N + h->panel_rows - 1) / h->panel_rows;
   const int P = h->P;
 
@@ -675,7 +681,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     const int WR = h->panel_rows, cps = wide_cps(WR);
     h->Cpad = ((h->C + cps - 1) / cps) * cps;
     h->spc = h->Cpad <= WIDE_CONSUMER_WARPS * 4 * cps ? 4 : 8;
-    if (WR != 16) h->spc = 8;
+    if (WR == 8) h->spc = 8;
     h->Kc = cps * h->spc;
     h->J = (h->Cpad + h->Kc - 1) / h->Kc;
     h->spw = (h->J + WIDE_CONSUMER_WARPS - 1) / WIDE_CONSUMER_WARPS;

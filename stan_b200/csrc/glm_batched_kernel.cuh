@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
   double* sRp = sR + nq * (32 * 16);
   const int MB = (K + 7) >> 3, MB0 = (MB + 1) >> 1;
   const int mb_base = mp ? MB0 : 0, mb_cnt = mp ? MB - MB0 : MB0;
+  const bool dense = (MB - MB0) >= MBH - 1;          // both warps of a pair fill (all but at most one of) their slots
+  const int swr = ((l4 & 1) << 3) | ((l4 & 2) << 1); // residual-patch swizzle of row kr + l4 (see the link step)
 
   double g[MBH][2][2];
 #pragma unroll
@@ -231,7 +233,12 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
           r_acc[ni][e2] += r_i;
           rr[e2] = r_i;
         }
-        *reinterpret_cast<double2*>(sRp + row * 16 + ((8 * ni + 2 * l4) ^ ((row & 3) << 2))) =
+        // residual patch: element (row, chain c) lives at column c ^ f(row & 3), f = {0, 8, 4, 12}.  Any permutation
+        // of {0, 4, 8, 12} keeps the GEMM2 B-fragment reads conflict-free (a half-warp's four rows land in four
+        // different column quads); f(0) ^ f(1) and f(2) ^ f(3) having the 8-bit set is what this 16-byte store needs:
+        // the two rows of a quarter-warp then cover all 16 columns.  (Round 1 used f = 4 (row & 3): both rows on the
+        // same 8 columns, a 2-way conflict on every store -- 65.6 M conflicts per launch at config 3, ncu.)
+        *reinterpret_cast<double2*>(sRp + row * 16 + ((8 * ni + 2 * l4) ^ (((row & 1) << 3) | ((row & 2) << 1)))) =
             make_double2(rr[0], rr[1]);
       }
     }
@@ -239,17 +246,35 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
 
     // ---- GEMM2: G (this warp's features x 16 chains) += X^T (features x 32 rows) * R ----
     const double* tf = tile + (size_t)(mb_base * 8 + lq) * 32;
+    if (dense) {
+      // every m-block slot of this warp is issued: the short warp of the pair (K = 200: 12 of 13 blocks) repeats
+      // its block 0 into an accumulator that is never stored.  No guard around the DMMA pair -- guarded, each
+      // pair came out as ISETP + predicated WARPSYNC + NOP + 2 DMMA (profiles/r1_sass_mnemonics.txt).
 #pragma unroll 2
-    for (int kr = 0; kr < 32; kr += 4) {
-      const int rowb = kr + l4;
-      const double b0 = sRp[rowb * 16 + (lq ^ sw)], b1 = sRp[rowb * 16 + ((8 + lq) ^ sw)];
-      const int ao = rowb ^ fsw;
+      for (int kr = 0; kr < 32; kr += 4) {
+        const int rowb = kr + l4;
+        const double b0 = sRp[rowb * 16 + (lq ^ swr)], b1 = sRp[rowb * 16 + ((8 + lq) ^ swr)];
+        const int ao = rowb ^ fsw;
 #pragma unroll
-      for (int m = 0; m < MBH; ++m) {
-        if (m < mb_cnt) {
-          const double a = tf[m * 256 + ao];
+        for (int m = 0; m < MBH; ++m) {
+          const double a = tf[(m < mb_cnt ? m : 0) * 256 + ao];
           dmma884(g[m][0], a, b0);
           dmma884(g[m][1], a, b1);
+        }
+      }
+    } else {
+#pragma unroll 2
+      for (int kr = 0; kr < 32; kr += 4) {
+        const int rowb = kr + l4;
+        const double b0 = sRp[rowb * 16 + (lq ^ swr)], b1 = sRp[rowb * 16 + ((8 + lq) ^ swr)];
+        const int ao = rowb ^ fsw;
+#pragma unroll
+        for (int m = 0; m < MBH; ++m) {
+          if (m < mb_cnt) {
+            const double a = tf[m * 256 + ao];
+            dmma884(g[m][0], a, b0);
+            dmma884(g[m][1], a, b1);
+          }
         }
       }
     }
