@@ -34,7 +34,7 @@
 namespace b200glm {
 
 constexpr int WIDE_CONSUMER_WARPS = 8;
-constexpr int WIDE_LINK_WARPS = 2;   // alternate over the row panels (even / odd), see the link warps below
+constexpr int WIDE_LINK_WARPS = 1;   // link warps alternate over the row panels; two were measured: no gain (see below)
 constexpr int WIDE_THREADS = (WIDE_CONSUMER_WARPS + 1 + WIDE_LINK_WARPS) * 32;
 constexpr int WIDE_MAX_SLOTS = 96;
 // named barriers: ETA / R, double-buffered by panel parity
@@ -56,7 +56,7 @@ __host__ __device__ inline int wide_cps(int WR) { return 32 / (WR / 4); }
 
 // doubles of dynamic shared memory besides the ring slots and their barriers
 __host__ __device__ inline size_t wide_fixed_doubles(int WR, int J, int KC, int G, int stage_a, int P_state = 0) {
-  return (size_t)J * KC + 2 * WIDE_CONSUMER_WARPS * WR + 2 * WR + (stage_a ? ((G + 1) & ~1) : 0)
+  return (size_t)J * KC + 2 * WIDE_CONSUMER_WARPS * WR + 2 * WR + 6 * WR + (stage_a ? ((G + 1) & ~1) : 0)
          + (P_state ? state_smem_doubles(P_state) : 0);
 }
 
@@ -72,14 +72,17 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
   double* sbeta = ring + (size_t)T * SLOT;                       // J * KC (zero beyond K)
   double* eta_part = sbeta + J * KC;                             // 2 parities x 8 warps x WR
   double* r_sh = eta_part + 2 * WIDE_CONSUMER_WARPS * WR;        // 2 parities x WR
-  double* sa = r_sh + 2 * WR;                                    // G (optional)
+  double* y_sh = r_sh + 2 * WR;                                  // 2 parities x WR: y, trials, group id of the panel's
+  double* t_sh = y_sh + 2 * WR;                                  //   rows, published by the warp that owns their column
+  double* g_sh = t_sh + 2 * WR;
+  double* sa = g_sh + 2 * WR;                                    // G (optional)
   double* st_base = sa + (p.stage_a_in_smem ? ((G + 1) & ~1) : 0);   // chain state (optional)
   const StateSmem st = carve_state_smem(st_base, P, p.state_in_smem);
   double* after_a = st_base + (p.state_in_smem ? state_smem_doubles(P) : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(after_a);     // T
   uint64_t* empty_bar = full_bar + T;                            // T
   __shared__ double sh_scratch[64];
-  __shared__ double sh_link[4];
+  __shared__ double sh_link[4];   // sums handed over by link warps 1.. (unused with one link warp)
   __shared__ int sh_is_last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -133,9 +136,27 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
 #pragma unroll
     for (int a = 0; a < SPW * SPC; ++a) acc[a] = 0.0;
 
+    // Where the aux columns live: y in column K, the binomial population sizes in K + 1, the group id after them.
+    // The warp that owns such a column hands the panel's values to the link warp together with its partial eta.
+    const int Kgc = fam_group_col(FAMILY, K);
+    const int aux_col[3] = {K, K + 1, Kgc};
+    const bool aux_on[3] = {true, FAMILY == FAM_BINOMIAL_LOGIT, G > 0};
+    double* const aux_dst[3] = {y_sh, t_sh, g_sh};
+
+    // REG: the warp keeps its 32 doubles per lane of the panel in REGISTERS between the two passes and releases the
+    // ring slot right after P1, so that the whole ring is look-ahead for the TMA stream.  Built and measured in round 2
+    // (K = 1000: 1.357 ms against 1.351 ms with the panel resident in shared memory; K = 500: 0.668 against 0.636 ms,
+    // 168 registers and a few spills): no gain, so ring capacity is not what holds this kernel at ~5.9 TB/s either,
+    // and the shared-memory-resident form stays.  Two link warps (WIDE_LINK_WARPS) and 4-row panels were measured too
+    // (no gain; 2x slower).  profiles/r2_wide_variants.txt.
+    constexpr bool REG = false;
+    struct Keep {
+      double2 a[SPC], b[SPC];
+    };
+
     // P1 of one whole panel (this warp's sub-panels, at ring position `ahead` panels past slot[]),
     // then publish the warp's partial eta of the panel's rows into parity buffer `buf`
-    auto pass1_publish = [&](int ahead, int buf) {
+    auto pass1_publish = [&](int ahead, int buf, Keep& kp) {
       double eA0 = 0.0, eA1 = 0.0, eB0 = 0.0, eB1 = 0.0;
 #pragma unroll
       for (int i = 0; i < SPW; ++i) {
@@ -151,18 +172,37 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
           }
           mbar_wait(&full_bar[sl], pr);
           const double* tile = ring + (size_t)sl * SLOT + cq * WR;
-          const double* bj = sbeta + (warp + WIDE_CONSUMER_WARPS * i) * KC + cq;
+          const int jsub = warp + WIDE_CONSUMER_WARPS * i;
+          const double* bj = sbeta + jsub * KC + cq;
 #pragma unroll
           for (int t = 0; t < SPC; ++t) {
             if (t < steps[i]) {
               const double b = bj[CPS * t];
               const double2 xa = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offA);
               const double2 xb = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offB);
+              if (REG) {
+                kp.a[t] = xa;
+                kp.b[t] = xb;
+              }
               eA0 = fma(xa.x, b, eA0);
               eA1 = fma(xa.y, b, eA1);
               eB0 = fma(xb.x, b, eB0);
               eB1 = fma(xb.y, b, eB1);
+              const int col = jsub * KC + cq + CPS * t;      // an aux column: beta is zero there, eta is unaffected
+#pragma unroll
+              for (int u = 0; u < 3; ++u)
+                if (aux_on[u] && col == aux_col[u]) {
+                  double* d = aux_dst[u] + buf * WR;
+                  d[offA] = xa.x;
+                  d[offA + 1] = xa.y;
+                  d[offB] = xb.x;
+                  d[offB + 1] = xb.y;
+                }
             }
+          }
+          if (REG) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[sl]);
           }
         }
       }
@@ -184,14 +224,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
       named_bar_arrive(WIDE_BAR_ETA + buf, WIDE_BAR_COUNT);
     };
 
-    if (n_my > 0) pass1_publish(0, 0);
-    for (long long n = 0; n < n_my; ++n) {
-      const int buf = (int)(n & 1);
-      // eta of panel n+1 goes to the link warp BEFORE this warp waits for r of panel n: the link
-      // function of n+1 then overlaps P2(n) (the ring holds at least two panels: T >= 2J)
-      if (n + 1 < n_my) pass1_publish(1, buf ^ 1);
-
-      // ---- P2: X^T r from the same resident sub-panels ----
+    // ---- P2: X^T r from the kept registers (REG) or from the same resident sub-panels ----
+    auto pass2 = [&](int buf, const Keep& kp) {
       named_bar_sync(WIDE_BAR_R + buf, WIDE_BAR_COUNT);
       const double2 rA = *reinterpret_cast<const double2*>(r_sh + buf * WR + offA);
       const double2 rB = *reinterpret_cast<const double2*>(r_sh + buf * WR + offB);
@@ -202,8 +236,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
 #pragma unroll
           for (int t = 0; t < SPC; ++t) {
             if (t < steps[i]) {
-              const double2 xa = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offA);
-              const double2 xb = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offB);
+              const double2 xa = REG ? kp.a[t] : *reinterpret_cast<const double2*>(tile + CPS * WR * t + offA);
+              const double2 xb = REG ? kp.b[t] : *reinterpret_cast<const double2*>(tile + CPS * WR * t + offB);
               double a = acc[i * SPC + t];
               a = fma(xa.x, rA.x, a);
               a = fma(xa.y, rA.y, a);
@@ -212,14 +246,29 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
               acc[i * SPC + t] = a;
             }
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty_bar[slot[i]]);
+          if (!REG) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[slot[i]]);
+          }
         }
         slot[i] += J;
         if (slot[i] >= T) {
           slot[i] -= T;
           par[i] ^= 1u;
         }
+      }
+    };
+
+    // Software pipeline, unrolled by two so that the two register sets have fixed names: eta of panel n+1 goes to
+    // the link warp BEFORE this warp waits for r of panel n, so the link function of n+1 overlaps P2(n).
+    Keep kA, kB;
+    if (n_my > 0) pass1_publish(0, 0, kA);
+    for (long long n = 0; n < n_my; n += 2) {
+      if (n + 1 < n_my) pass1_publish(1, 1, kB);
+      pass2(0, kA);
+      if (n + 1 < n_my) {
+        if (n + 2 < n_my) pass1_publish(1, 0, kA);
+        pass2(1, kB);
       }
     }
 
@@ -257,32 +306,13 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
     }
   } else {
     // =============================== link warps ===============================
-    // Link warp lw takes the row panels n = lw, lw + 2, ...  The eta / r buffers and both named barriers are already
-    // double-buffered by panel parity, so the two warps never share one.  Why two: the link step of a panel is ONE
-    // dependent fp64 chain (sum of the 8 partial etas, exp, log1p, a division: ~2000 cycles) on WR <= 16 lanes, and a
-    // panel is due every ~2600 cycles at the HBM rate -- with a single link warp that chain set the pace of the
-    // whole CTA (ncu round 1: 2.36 barrier-stall cycles per issue, 75.6 % of DRAM peak against 89 % for the narrow
-    // kernel); the consumers publish eta(n+1) before they wait for r(n), so the two chains overlap.
+    // Link warp lw takes the row panels n = lw, lw + WIDE_LINK_WARPS, ...  (the eta / r buffers and both named barriers
+    // are double-buffered by panel parity, so two link warps would never share one).  Two were measured in round 2:
+    // no gain (K = 1000: 1.340 ms against 1.29 ms with one) -- the barrier stall ncu showed in round 1 (2.36 cycles
+    // per issue) was the consumers waiting for r while the resident panels held the ring, not link throughput.
+    // y / trials / group id of the panel's rows arrive in y_sh / t_sh / g_sh with the partial etas.
     const int lw = warp - (WIDE_CONSUMER_WARPS + 1);
     const int r = lane & (WR - 1);
-    const int jy = K / KC, coly = K - jy * KC;            // y lives in column K
-    const int jt = (K + 1) / KC, colt = K + 1 - jt * KC;  // binomial population sizes in column K+1
-    const int Kg = fam_group_col(FAMILY, K);
-    const int jg = Kg / KC, colg = Kg - jg * KC;          // group id after the y (and trials) columns (G > 0)
-    int slot_y = jy, slot_g = jg, slot_t = jt;
-    uint32_t par_y = 0, par_g = 0, par_t = 0;
-    auto advance = [&](int& sl, uint32_t& pr, int panels) {   // ring position `panels` row panels further on
-      sl += panels * J;
-      while (sl >= T) {
-        sl -= T;
-        pr ^= 1u;
-      }
-    };
-    if (lw == 1) {
-      advance(slot_y, par_y, 1);
-      advance(slot_g, par_g, 1);
-      advance(slot_t, par_t, 1);
-    }
     const double alpha = G > 0 ? 0.0 : theta_at(0);
     LinkConst lc;
     lc.inv_sigma = 1.0;
@@ -301,21 +331,15 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
     for (long long n = lw; n < n_my; n += WIDE_LINK_WARPS) {
       const int buf = (int)(n & 1);
       const long long pi = blockIdx.x + n * grid;
-      mbar_wait(&full_bar[slot_y], par_y);
-      const double y = ring[(size_t)slot_y * SLOT + coly * WR + r];
-      double trials = 0.0;
-      if (FAMILY == FAM_BINOMIAL_LOGIT) {
-        mbar_wait(&full_bar[slot_t], par_t);
-        trials = ring[(size_t)slot_t * SLOT + colt * WR + r];
-      }
+      named_bar_sync(WIDE_BAR_ETA + buf, WIDE_BAR_COUNT);
+      const double y = y_sh[buf * WR + r];
+      const double trials = FAMILY == FAM_BINOMIAL_LOGIT ? t_sh[buf * WR + r] : 0.0;
       double off = alpha;
       if (G > 0) {
-        mbar_wait(&full_bar[slot_g], par_g);
-        const int gi = (int)ring[(size_t)slot_g * SLOT + colg * WR + r] - 1;
+        const int gi = (int)g_sh[buf * WR + r] - 1;
         const bool gok = gi >= 0 && gi < G;
         off = p.stage_a_in_smem ? sa[gok ? gi : 0] : theta_at(2 + (gok ? gi : 0));
       }
-      named_bar_sync(WIDE_BAR_ETA + buf, WIDE_BAR_COUNT);
       double eta = 0.0;
 #pragma unroll
       for (int w = 0; w < WIDE_CONSUMER_WARPS; ++w) eta += eta_part[(buf * WIDE_CONSUMER_WARPS + w) * WR + r];
@@ -336,25 +360,29 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
       }
       __threadfence_block();
       named_bar_arrive(WIDE_BAR_R + buf, WIDE_BAR_COUNT);
-      advance(slot_y, par_y, WIDE_LINK_WARPS);
-      advance(slot_g, par_g, WIDE_LINK_WARPS);
-      advance(slot_t, par_t, WIDE_LINK_WARPS);
     }
     lp_acc = warp_sum(lp_acc);
     r_acc = warp_sum(r_acc);
     x_acc = warp_sum(x_acc);
-    // the odd-panel warp hands its sums to the even-panel warp (fixed order: even + odd)
-    if (lw == 1 && lane == 0) {
-      sh_link[0] = lp_acc;
-      sh_link[1] = r_acc;
-      sh_link[2] = x_acc;
+    // the other link warps hand their sums to warp 0 (fixed order)
+    if (lw > 0 && lane == 0) {
+      sh_link[3 * (lw - 1)] = lp_acc;
+      sh_link[3 * (lw - 1) + 1] = r_acc;
+      sh_link[3 * (lw - 1) + 2] = x_acc;
     }
-    __threadfence_block();
-    named_bar_sync(WIDE_BAR_LINK, WIDE_LINK_WARPS * 32);
+    if (WIDE_LINK_WARPS > 1) {
+      __threadfence_block();
+      named_bar_sync(WIDE_BAR_LINK, WIDE_LINK_WARPS * 32);
+    }
     if (lw == 0 && lane == 0) {
-      my_part[K] = lp_acc + sh_link[0];
-      my_part[K + 1] = r_acc + sh_link[1];
-      my_part[K + 2] = x_acc + sh_link[2];   // neg_binomial_2_log: sum of the per-row d/dphi terms
+      for (int o = 0; o < WIDE_LINK_WARPS - 1; ++o) {
+        lp_acc += sh_link[3 * o];
+        r_acc += sh_link[3 * o + 1];
+        x_acc += sh_link[3 * o + 2];
+      }
+      my_part[K] = lp_acc;
+      my_part[K + 1] = r_acc;
+      my_part[K + 2] = x_acc;   // neg_binomial_2_log: sum of the per-row d/dphi terms
     }
   }
 
