@@ -206,12 +206,23 @@ def run_b200(args):
         elif world > 1:
             raise SystemExit("--streamed runs with the in-launch peer exchange")
     else:
-        X, y, grp, trials, r0, r1 = make_shard_ex(torch, dev, family, N_total, K, G, rank, world, rows=rows)
+        if family in ("ordered_logistic", "categorical_logit"):
+            # class-outcome models: standard-normal X, classes drawn uniformly
+            from stan_b200.synth import shard_rows
+            r0, r1 = shard_rows(N_total, rank, world)
+            gen = torch.Generator(device=dev).manual_seed(20261017 + rank)
+            X = torch.randn((K, r1 - r0), generator=gen, device=dev, dtype=torch.float64)
+            y = torch.randint(1, args.classes + 1, (r1 - r0,), generator=gen, device=dev, dtype=torch.int32)
+            grp = trials = None
+            args.no_parity = True            # parity of these families: tests/test_class_models_gpu.py
+        else:
+            X, y, grp, trials, r0, r1 = make_shard_ex(torch, dev, family, N_total, K, G, rank, world, rows=rows)
         n_local = r1 - r0
         torch.cuda.synchronize()
         m = GLMModel(family, X.data_ptr(), y.data_ptr(), grp.data_ptr() if G else None, G, data_on_device=True,
                      N=n_local, K=K, ldx=n_local, device=local_rank, rank=rank, world=world, N_total=N_total,
-                     trials=trials.data_ptr() if trials is not None else None)
+                     trials=trials.data_ptr() if trials is not None else None, n_classes=args.classes
+                     if family in ("ordered_logistic", "categorical_logit") else 0)
         if world > 1 and args.collective == "peer":
             m.connect_peers_torch(dist, dev)      # in-kernel exchange through peer mailboxes (NVLink), no NCCL call
         elif world > 1:
@@ -338,7 +349,8 @@ def run_b200(args):
     achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
-                "kernel": f"glm_wide_kernel<{family}>" if K > 256 else f"glm_fused_kernel<{family}>", "algorithmic_bytes_per_launch": bytes_per_launch,
+                "kernel": (f"glm_class_kernel<{family}, {args.classes} classes>" if family in ("ordered_logistic", "categorical_logit")
+                           else f"glm_wide_kernel<{family}>" if K > 256 else f"glm_fused_kernel<{family}>"), "algorithmic_bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": ms_per_step}
     if read_gbs:
         # the kernel reads X once and writes nothing; `peak` above is the driver's read+write COPY figure, which a
@@ -363,7 +375,8 @@ def run_b200(args):
     cpu_baseline = None
     if sample is not None:
         cpu_baseline = cpu_baseline_leg(sample[0], sample[1], N_total, threads=1, evals=args.cpu_evals,
-                                        family=family, group=sample[2], G=G, trials=sample[3])
+                                        family=family, group=sample[2], G=G, trials=sample[3],
+                                        n_classes=args.classes if family in ("ordered_logistic", "categorical_logit") else 0)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.weak else "strong",
@@ -660,10 +673,13 @@ def run_b200_batched(args):
 # ------------------------------------------------------------------------------------------
 # CPU legs (the only place bench.py executes anything under oracle/)
 # ------------------------------------------------------------------------------------------
-def cpu_baseline_leg(Xs, ys, N_total, threads=1, evals=5, family=FAMILY, group=None, G=0, trials=None):
+def cpu_baseline_leg(Xs, ys, N_total, threads=1, evals=5, family=FAMILY, group=None, G=0, trials=None, n_classes=0):
     from oracle.oracle import PortOracle, RefOracle
     cls = RefOracle if RefOracle.available() else PortOracle
-    orc = cls(family, Xs, ys, group, G, **({"trials": trials} if trials is not None else {}))
+    kw = {"trials": trials} if trials is not None else {}
+    if n_classes:
+        kw["n_classes"] = n_classes
+    orc = cls(family, Xs, ys, group, G, **kw)
     ns, K = Xs.shape
     th = 0.05 * np.random.default_rng(11).standard_normal(orc.P)
     orc.log_prob_grad(th)     # warm
@@ -771,6 +787,7 @@ def main():
     ap.add_argument("--balance", action="store_true",
                     help="N > 1: split the rows in proportion to each GPU's measured copy bandwidth (default: equal)")
     ap.add_argument("--chains", type=int, default=1024)
+    ap.add_argument("--classes", type=int, default=4, help="--family ordered_logistic | categorical_logit: outcome classes")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the P+2 likelihood partials are summed over ranks")
     ap.add_argument("--rows", type=int, default=None)

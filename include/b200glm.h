@@ -35,8 +35,9 @@
 extern "C" {
 #endif
 
-#define B200GLM_ABI_VERSION 3   /* 2: b200glm_desc gained `trials` (appended), families 3 and 4
-                                   3: b200glm_abi_version, shard constants, timeline, (no struct change) */
+#define B200GLM_ABI_VERSION 4   /* 2: b200glm_desc gained `trials` (appended), families 3 and 4
+                                   3: b200glm_abi_version, shard constants, timeline, (no struct change)
+                                   4: b200glm_desc gained `n_classes` (appended), families 5 and 6, streamed build */
 
 /* status codes; the C++ shim maps them to the exceptions the reference throws:
  * DOMAIN -> std::domain_error (recoverable: base_hamiltonian.hpp:65-68, initialize.hpp:104-112),
@@ -47,7 +48,17 @@ enum { B200GLM_OK = 0, B200GLM_DOMAIN = 1, B200GLM_INVALID = 2, B200GLM_CUDA = 3
  * binomial_logit_glm_lpmf.hpp:55, neg_binomial_2_log_glm_lpmf.hpp:64}.  The last two run in
  * the single-chain kernels (narrow and wide-matrix); the batched DMMA kernel serves families 0-2. */
 enum { B200GLM_BERNOULLI_LOGIT = 0, B200GLM_POISSON_LOG = 1, B200GLM_NORMAL_ID = 2, B200GLM_BINOMIAL_LOGIT = 3,
-       B200GLM_NEG_BINOMIAL_2_LOG = 4 };
+       B200GLM_NEG_BINOMIAL_2_LOG = 4,
+       /* SM/prim/prob/ordered_logistic_glm_lpmf.hpp:49 and categorical_logit_glm_lpmf.hpp:47 -- class-outcome models
+        * with their own parameter blocks (y in 1..n_classes, no intercept vector a[group]):
+        *   ordered_logistic:  parameters { vector[K] beta; ordered[C-1] c; }   theta = [beta, c unconstrained]
+        *                      beta ~ N(0, prior_beta_sd); c ~ N(0, prior_alpha_sd); y ~ ordered_logistic_glm(X, beta, c)
+        *   categorical_logit: parameters { vector[C] alpha; matrix[K, C] beta; }   theta = [alpha, beta column-major]
+        *                      alpha ~ N(0, prior_alpha_sd); to_vector(beta) ~ N(0, prior_beta_sd);
+        *                      y ~ categorical_logit_glm(X, alpha, beta)
+        * Served by glm_class_kernel (single chain, K <= 256 | K x classes limits in b200glm_create's error text);
+        * not by the batched, wide-matrix or function-level entry points. */
+       B200GLM_ORDERED_LOGISTIC = 5, B200GLM_CATEGORICAL_LOGIT = 6 };
 
 /* desc.flags: use the wide-matrix kernel (16-row panels split over the CTA; the default for K > 256)
  * even for a narrow X -- for tests of that kernel at small K */
@@ -81,6 +92,7 @@ typedef struct b200glm_desc {
   int32_t grid_ctas;    /* 0 = one persistent CTA per SM */
   int32_t flags;        /* B200GLM_FLAG_* */
   const int32_t* trials; /* binomial_logit: population sizes (N entries; host or device like y_int); else NULL */
+  int32_t n_classes;    /* ordered_logistic / categorical_logit: number of outcome classes C (1..16); else 0 */
 } b200glm_desc;
 
 /* Data upload + one-time re-layout of X into the row-panel format the kernel streams

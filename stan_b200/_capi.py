@@ -6,8 +6,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libb200glm.so")
 
 OK, DOMAIN, INVALID, CUDA = 0, 1, 2, 3
-ABI_VERSION = 3          # B200GLM_ABI_VERSION of include/b200glm.h this binding (Desc layout, signatures) was written for
-FAMILY = {"bernoulli_logit": 0, "poisson_log": 1, "normal_id": 2, "binomial_logit": 3, "neg_binomial_2_log": 4}
+ABI_VERSION = 4          # B200GLM_ABI_VERSION of include/b200glm.h this binding (Desc layout, signatures) was written for
+FAMILY = {"bernoulli_logit": 0, "poisson_log": 1, "normal_id": 2, "binomial_logit": 3, "neg_binomial_2_log": 4,
+          "ordered_logistic": 5, "categorical_logit": 6}
 
 # every symbol include/b200glm.h declares
 SYMBOLS = [
@@ -34,7 +35,7 @@ class Desc(C.Structure):
         ("prior_sigma_a_scale", C.c_double),
         ("device", C.c_int32), ("n_slots", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
         ("N_total", C.c_int64), ("grid_ctas", C.c_int32), ("flags", C.c_int32),
-        ("trials", C.c_void_p),
+        ("trials", C.c_void_p), ("n_classes", C.c_int32),
     ]
 
 

@@ -21,6 +21,7 @@
 #include "glm_kernels.cuh"
 #include "glm_wide_kernel.cuh"
 #include "glm_batched_kernel.cuh"
+#include "glm_class_kernel.cuh"
 #include "measure.cuh"
 
 using namespace b200glm;
@@ -73,6 +74,7 @@ struct Slot {
   unsigned int* ticket = nullptr;
   double* r_out = nullptr;       // n_panels*32 (G > 0, unfused group path)
   double* gpart = nullptr;       // grid * Gcs (fused group path)
+  double* cuts = nullptr;        // ordered_logistic: 2 (C - 1) doubles of epilogue scratch
   double* lik = nullptr;         // P + 2
   double* result = nullptr;      // P + 2
   double* theta_used = nullptr;  // P
@@ -117,7 +119,8 @@ struct b200glm_handle {
   int* cta_g0 = nullptr;          // grid entries (device)
   int state_smem = 0;  // the kernels keep the chain state + likelihood sums in shared memory for the epilogue
   size_t smem_bytes = 0;
-  int cpl = 0;
+  int cpl = 0, cmax = 0;   // cmax: class-outcome models, classes kept in registers
+  int pstride = 0;         // doubles per CTA partial row
   // wide kernel (K > 256 or B200GLM_FLAG_FORCE_WIDE): 16-row panels streamed as J sub-panels
   bool wide = false;
   int panel_rows = PANEL_ROWS, Cpad = 0, Kc = 0, J = 0, spw = 0, spc = 0;
@@ -211,7 +214,27 @@ kernel_fn pick_wide_kernel(int family, int wr, int spw, int spc) {
   }
   return nullptr;
 }
+// class-outcome models: (columns per lane, classes kept in registers) shapes of glm_class_kernel
+struct ClassShape {
+  int cpl, cmax;
+};
+const ClassShape kOrderedShapes[] = {{4, 1}, {13, 1}, {32, 1}};                 // K <= 32, 104, 256
+const ClassShape kCategoricalShapes[] = {{25, 2}, {13, 4}, {7, 8}, {2, 16}};    // K <= 200 / 104 / 56 / 16 with <= 2 / 4 / 8 / 16 classes
+kernel_fn pick_class_kernel(int family, int cpl, int cmax) {
+  if (family == FAM_ORDERED_LOGISTIC) {
+    if (cpl == 4) return glm_class_kernel<true, 4, 1>;
+    if (cpl == 13) return glm_class_kernel<true, 13, 1>;
+    if (cpl == 32) return glm_class_kernel<true, 32, 1>;
+  } else {
+    if (cpl == 25 && cmax == 2) return glm_class_kernel<false, 25, 2>;
+    if (cpl == 13 && cmax == 4) return glm_class_kernel<false, 13, 4>;
+    if (cpl == 7 && cmax == 8) return glm_class_kernel<false, 7, 8>;
+    if (cpl == 2 && cmax == 16) return glm_class_kernel<false, 2, 16>;
+  }
+  return nullptr;
+}
 kernel_fn handle_kernel(const b200glm_handle* h) {
+  if (fam_is_class(h->d.family)) return pick_class_kernel(h->d.family, h->cpl, h->cmax);
   return h->wide ? pick_wide_kernel(h->d.family, h->panel_rows, h->spw, h->spc) : pick_kernel(h->d.family, h->cpl);
 }
 
@@ -245,6 +268,8 @@ int validate_slot(b200glm_handle* h, int slot) {
 // an empty weight vector (size_zero(n, N, alpha, beta, x), binomial_logit_glm_lpmf.hpp:77-79).
 long long lik_rows_total(const b200glm_handle* h) {
   if (h->d.family == B200GLM_BINOMIAL_LOGIT && h->d.K == 0) return 0;
+  // one class: categorical_logit_glm_lpmf.hpp:70-72 returns 0; no cut-points: ordered_logistic_glm_lpmf.hpp:93-95
+  if (fam_is_class(h->d.family) && h->d.n_classes <= 1) return 0;
   return h->d.N_total > 0 ? h->d.N_total : h->d.N;
 }
 
@@ -266,6 +291,7 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
   p.J = h->J;
   p.mode = mode;
   p.fuse_finish = ((h->d.world <= 1 || h->peer_on) && (h->d.G == 0 || h->group_fused)) ? 1 : 0;
+  if (fam_is_class(h->d.family)) p.state_in_smem = 0;
   if (h->peer_on) {
     int slot_idx = 0;
     for (size_t i = 0; i < h->slots.size(); ++i)
@@ -287,7 +313,9 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
   p.inv_metric = s->inv_metric;
   p.eps = eps;
   p.partials = s->partials;
-  p.pstride = partial_stride(h->d.K);
+  p.pstride = h->pstride;
+  p.n_classes = h->d.n_classes;
+  p.cuts = s->cuts;
   p.ticket = s->ticket;
   p.r_out = s->r_out;
   p.group_fused = h->group_fused;
@@ -373,6 +401,10 @@ int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian,
       group_reduce_kernel<<<gb, 256, 0, s->stream>>>(s->r_out, h->seg_ptr, h->d.G, s->lik + 2);
       h->launches++;
     }
+    if (fam_is_class(h->d.family) && h->d.world > 1 && !h->peer_on) {
+      h->set_error("row-sharded class-outcome models need the peer-mailbox exchange (b200glm_peer_connect)");
+      return B200GLM_INVALID;
+    }
     if (h->d.world > 1 && !h->peer_on) {
       if (!h->comm) {
         h->set_error("world > 1 but neither b200glm_peer_connect nor b200glm_comm_init was called");
@@ -384,7 +416,7 @@ int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian,
         return B200GLM_CUDA;
       }
     }
-    if (!p.fuse_finish) {
+    if (!p.fuse_finish && !fam_is_class(h->d.family)) {
       finish_kernel<<<1, NUM_THREADS, 0, s->stream>>>(p);
       h->launches++;
     }
@@ -397,7 +429,10 @@ int enqueue_eval(b200glm_handle* h, Slot* s, int mode, int propto, int jacobian,
     } else {
       CUDA_TRY(h, cudaMemcpyAsync(s->theta_used, s->theta, sizeof(double) * h->P, cudaMemcpyDeviceToDevice, s->stream));
     }
-    finish_kernel<<<1, NUM_THREADS, 0, s->stream>>>(p);
+    if (fam_is_class(h->d.family))
+      class_finish_kernel<<<1, NUM_THREADS, 0, s->stream>>>(p);
+    else
+      finish_kernel<<<1, NUM_THREADS, 0, s->stream>>>(p);
     h->launches++;
   }
   CUDA_TRY(h, cudaGetLastError());
@@ -460,12 +495,18 @@ int eval_host(b200glm_handle* h, int slot, const double* theta, int propto, int 
     CUDA_TRY(h, cudaStreamSynchronize(s->stream));
   }
   // neg_binomial_2_log checks y before its include_summand early return (neg_binomial_2_log_glm_lpmf.hpp:130-135)
-  if (h->bad_y && (is_var || !propto || h->d.family == B200GLM_NEG_BINOMIAL_2_LOG) && lik_rows_total(h) > 0) {
+  // neg_binomial_2_log, ordered_logistic and categorical_logit check y before their include_summand early return
+  // (ordered_logistic_glm_lpmf.hpp:84, categorical_logit_glm_lpmf.hpp:74); ordered_logistic even before size_zero
+  const bool y_checked_always = h->d.family == B200GLM_NEG_BINOMIAL_2_LOG || fam_is_class(h->d.family);
+  const bool lik_on = lik_rows_total(h) > 0 || (h->d.family == B200GLM_ORDERED_LOGISTIC && h->d.N > 0);
+  if (h->bad_y && (is_var || !propto || y_checked_always) && lik_on) {
     static const char* const msg[] = {
         "bernoulli_logit_glm_lpmf: Vector of dependent variables is out of range [0, 1]",
         "poisson_log_glm_lpmf: Vector of dependent variables is negative", "",
         "binomial_logit_glm_lpmf: Successes variable is out of range [0, Population size parameter]",
-        "neg_binomial_2_log_glm_lpmf: Failures variables is negative"};
+        "neg_binomial_2_log_glm_lpmf: Failures variables is negative",
+        "ordered_logistic_glm_lpmf: Vector of dependent variables is out of range [1, N_classes]",
+        "categorical_logit_glm_lpmf: categorical outcome out of support"};
     h->set_error(msg[h->d.family]);
     return B200GLM_DOMAIN;
   }
@@ -528,6 +569,7 @@ void b200glm_destroy(b200glm_handle* h) {
     cudaFree(s->ticket);
     cudaFree(s->r_out);
     cudaFree(s->gpart);
+    cudaFree(s->cuts);
     cudaFree(s->lik);
     cudaFree(s->result);
     cudaFree(s->theta_used);
@@ -588,7 +630,12 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     }
   } tmp;
   const b200glm_desc& d = h->d;
-  if (d.family < 0 || d.family > 4) return fail(B200GLM_INVALID, "unknown family");
+  if (d.family < 0 || d.family > 6) return fail(B200GLM_INVALID, "unknown family");
+  const bool cls = fam_is_class(d.family);
+  if (cls && (d.n_classes < 1 || d.n_classes > CLASS_MAX_CLASSES))
+    return fail(B200GLM_INVALID, "class-outcome models need 1 <= n_classes <= 16");
+  if (cls && (d.G > 0 || (d.flags & (B200GLM_FLAG_FORCE_WIDE | B200GLM_FLAG_STREAMED))))
+    return fail(B200GLM_INVALID, "class-outcome models: no group intercepts, wide-matrix kernel or streamed construction");
   h->streamed = (d.flags & B200GLM_FLAG_STREAMED) != 0;
   if (d.N < 0 || d.K < 0 || d.G < 0) return fail(B200GLM_INVALID, "negative size");
   if (h->streamed) {
@@ -610,8 +657,11 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   if (const char* e = std::getenv("B200GLM_NO_HOST_MIRROR")) h->host_mirror = !(e[0] == '1');
   h->P = (d.G > 0 ? 2 + d.G : 1) + d.K + (fam_has_scale(d.family) ? 1 : 0);
   h->off_beta = d.G > 0 ? 2 + d.G : 1;
-  h->C = fam_group_col(d.family, d.K) + (d.G > 0 ? 1 : 0);
-  h->wide = d.K > 256 || (d.flags & B200GLM_FLAG_FORCE_WIDE);
+  if (d.family == B200GLM_ORDERED_LOGISTIC) h->P = d.K + d.n_classes - 1;        // [beta, unconstrained cut-points]
+  if (d.family == B200GLM_CATEGORICAL_LOGIT) h->P = d.n_classes * (1 + d.K);      // [alpha, beta column-major]
+  if (cls) h->off_beta = d.family == B200GLM_ORDERED_LOGISTIC ? 0 : d.n_classes;
+  h->C = fam_group_col(d.family, d.K) + (d.G > 0 ? 1 : 0);   // class-outcome models: K + 1 (the class in column K)
+  h->wide = !cls && (d.K > 256 || (d.flags & B200GLM_FLAG_FORCE_WIDE));
   h->panel_rows = h->wide ? wide_rows_for(h->C) : PANEL_ROWS;
   if (h->wide)
     if (const char* e = std::getenv("B200GLM_WIDE_ROWS")) {   // A/B runs: 16, 8 or 4 rows per panel
@@ -665,7 +715,32 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
                     + (size_t)S * tile_bytes;
     return true;
   };
-  if (!h->wide) {
+  h->pstride = cls ? class_partial_stride(P) : partial_stride(d.K);
+  if (cls) {
+    h->Cpad = h->C;
+    h->state_smem = 0;
+    const int need_cpl = std::max(1, (d.K + 7) / 8);
+    h->cpl = 0;
+    if (d.family == B200GLM_ORDERED_LOGISTIC) {
+      for (const ClassShape& sh : kOrderedShapes)
+        if (!h->cpl && sh.cpl >= need_cpl) h->cpl = sh.cpl, h->cmax = sh.cmax;
+    } else {
+      for (const ClassShape& sh : kCategoricalShapes)   // fewest classes in registers first (widest K)
+        if (!h->cpl && sh.cmax >= std::max(2, (int)d.n_classes) && sh.cpl >= need_cpl) h->cpl = sh.cpl, h->cmax = sh.cmax;
+    }
+    if (!h->cpl)
+      return fail(B200GLM_INVALID, d.family == B200GLM_ORDERED_LOGISTIC
+                                       ? "ordered_logistic: K <= 256"
+                                       : "categorical_logit: K <= 200 with 2 classes, <= 104 with <= 4, <= 56 with <= 8, "
+                                         "<= 16 with <= 16");
+    const size_t fixed = class_fixed_doubles(d.family == B200GLM_ORDERED_LOGISTIC, d.K, d.n_classes, P) * 8;
+    const size_t tile_bytes = (size_t)h->C * PANEL_ROWS * 8;
+    int S = MAX_STAGES;
+    while (S > 0 && fixed + (size_t)S * (tile_bytes + 16) > max_dyn) --S;
+    if (S < 1) return fail(B200GLM_INVALID, "panel does not fit in shared memory");
+    h->n_stages = S;
+    h->smem_bytes = fixed + (size_t)S * (tile_bytes + 16);
+  } else if (!h->wide) {
     h->Cpad = h->C;
     const int need_cpl = std::max(1, (d.K + 7) / 8);
     h->cpl = 0;
@@ -762,7 +837,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     double* d_stats;
     CREATE_TRY(cudaMalloc(&d_stats, sizeof(double) * 2 * nb));
     t_stats = d_stats;
-    y_stats_kernel<<<nb, 256, 0, st>>>(d_y, d_trials, d.N, d.family, d_stats);
+    y_stats_kernel<<<nb, 256, 0, st>>>(d_y, d_trials, d.N, d.family, d_stats, d.n_classes);
     std::vector<double> hs(2 * nb);
     CREATE_TRY(cudaMemcpyAsync(hs.data(), d_stats, sizeof(double) * 2 * nb, cudaMemcpyDeviceToHost, st));
     CREATE_TRY(cudaStreamSynchronize(st));
@@ -774,6 +849,8 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
       lg += hs[2 * i + 1];
     }
     h->bad_y = h->bad_y_local = bad > 0;
+    if (d.family == B200GLM_CATEGORICAL_LOGIT && d.n_classes == 1)
+      h->bad_y = h->bad_y_local = false;   // N_classes == 1 returns 0 BEFORE the bounds check (categorical...:70-75)
     h->lgamma_sum = lg;
     h->lgamma_sum_total = lg;
   }
@@ -886,7 +963,6 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   (void)own_group;   // the upload temporaries and the stream are released by `tmp`
 
   // ---- slots ----
-  const int pstride = partial_stride(d.K);
   for (int i = 0; i < h->d.n_slots; ++i) {
     Slot* s = new Slot();
     h->slots.push_back(s);
@@ -899,7 +975,9 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     CREATE_TRY(cudaMalloc(&s->inv_metric, sizeof(double) * std::max(P, 1)));
     std::vector<double> ones(std::max(P, 1), 1.0);
     CREATE_TRY(cudaMemcpy(s->inv_metric, ones.data(), sizeof(double) * P, cudaMemcpyHostToDevice));
-    CREATE_TRY(cudaMalloc(&s->partials, sizeof(double) * (size_t)h->grid * pstride));
+    CREATE_TRY(cudaMalloc(&s->partials, sizeof(double) * (size_t)h->grid * h->pstride));
+    if (d.family == B200GLM_ORDERED_LOGISTIC)
+      CREATE_TRY(cudaMalloc(&s->cuts, sizeof(double) * 2 * std::max(1, (int)d.n_classes)));
     CREATE_TRY(cudaMalloc(&s->ticket, sizeof(unsigned int)));
     CREATE_TRY(cudaMemset(s->ticket, 0, sizeof(unsigned int)));
     if (d.G > 0 && h->n_panels > 0 && !h->group_fused)
@@ -935,6 +1013,10 @@ int b200glm_glm_lpmf(b200glm_handle* h, int32_t slot, int32_t propto, int32_t op
   if (!h) return B200GLM_INVALID;
   if (!logp || (h->d.K > 0 && !beta) || !alpha) {
     h->set_error("null pointer argument");
+    return B200GLM_INVALID;
+  }
+  if (fam_is_class(h->d.family)) {
+    h->set_error("b200glm_glm_lpmf serves families 0-4; the class-outcome models are evaluated as whole models");
     return B200GLM_INVALID;
   }
   const int P = h->P, G = h->d.G, K = h->d.K;
@@ -1464,7 +1546,7 @@ int b200glm_append_rows(b200glm_handle* h, int64_t n, const double* X, int64_t l
       cudaError_t e = cudaMalloc(&d_stats, sizeof(double) * 2 * nb);
       if (e != cudaSuccess) fail_cuda(e, "cudaMalloc(stats)");
       else {
-        y_stats_kernel<<<nb, 256, 0, st>>>(dy, dt, n, d.family, d_stats);
+        y_stats_kernel<<<nb, 256, 0, st>>>(dy, dt, n, d.family, d_stats, 0);
         std::vector<double> hs(2 * nb);
         if ((e = cudaMemcpyAsync(hs.data(), d_stats, sizeof(double) * 2 * nb, cudaMemcpyDeviceToHost, st)) != cudaSuccess
             || (e = cudaStreamSynchronize(st)) != cudaSuccess)

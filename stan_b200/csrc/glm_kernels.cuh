@@ -721,6 +721,12 @@ __global__ void __launch_bounds__(NUM_THREADS) finish_kernel(const __grid_consta
   finish(p, sh_scratch);
 }
 
+// class-outcome models whose likelihood term is empty (no rows anywhere, one class): the epilogue alone
+__global__ void __launch_bounds__(NUM_THREADS) class_finish_kernel(const __grid_constant__ KernelParams p) {
+  __shared__ double sh_scratch[64];
+  class_epilogue(p, sh_scratch);
+}
+
 // ------------------------------------------------------------------------------------------
 // One-time re-layout: column-major X (+ y, group) -> row-panel format (optionally through a row
 // permutation that sorts rows by group).  One thread per (panel, column, row).
@@ -774,13 +780,15 @@ __device__ __forceinline__ double binomial_coefficient_log_d(double n, double k)
 // neg_binomial_2_log :130 check_nonnegative(y), :163-169 sum lgamma(y+1)
 __global__ void __launch_bounds__(256) y_stats_kernel(const int32_t* __restrict__ y, const int32_t* __restrict__ trials,
                                                       long long n, int family,
-                                                      double* out /* [gridDim.x][2] = bad, lgamma_sum */) {
+                                                      double* out /* [gridDim.x][2] = bad, lgamma_sum */, int n_classes) {
   __shared__ double sh[16];
   double bad = 0.0, lg = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int v = y[i];
     if (family == FAM_BERNOULLI_LOGIT) {
       if (v < 0 || v > 1) bad += 1.0;
+    } else if (fam_is_class(family)) {        // check_bounded(y, 1, N_classes)
+      if (v < 1 || v > n_classes) bad += 1.0;
     } else if (family == FAM_BINOMIAL_LOGIT) {
       const int t = trials[i];
       if (v < 0 || v > t || t < 0) bad += 1.0;

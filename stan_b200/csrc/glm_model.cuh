@@ -87,6 +87,8 @@ struct KernelParams {
   // so a CTA meets few groups: it accumulates their residual sums on chip and writes them to gpart[cta][0, Gcs);
   // the last CTA folds them in CTA order through gmeta[g] = {first CTA, last CTA, index of the first CTA's entry}
   // (in every later CTA the group is that CTA's first: entry 0).  cta_g0[c] = first group (0-based) of CTA c's range.
+  int n_classes;            // class-outcome models (ordered_logistic, categorical_logit): number of classes C
+  double* cuts;             // ordered_logistic: 2 (C - 1) doubles of scratch for the epilogue
   int group_fused, Gcs;
   double* gpart;
   const int4* gmeta;
@@ -469,6 +471,39 @@ __device__ void finish_class_model(const ClassModelParams& p, double* sh /* >= 8
     }
     if (tid == 0) p.st_out[3 * P] = domain ? CUDART_INF : -lp;
   }
+}
+
+// What the class-model kernels run once the likelihood sums are complete in p.lik: the epilogue above on the launch's
+// KernelParams, then the mirror of result / state into pinned host memory for host-facing calls.
+__device__ inline void class_epilogue(const KernelParams& p, double* sh) {
+  ClassModelParams cp;
+  cp.family_ordered = p.family == FAM_ORDERED_LOGISTIC ? 1 : 0;
+  cp.K = p.K;
+  cp.C = p.n_classes;
+  cp.P = p.P;
+  cp.propto = p.mc.propto;
+  cp.jacobian = p.mc.jacobian;
+  cp.is_var = p.mc.is_var;
+  cp.mode = p.mode;
+  cp.N_total = p.mc.N_total;
+  cp.prior_alpha_sd = p.mc.prior_alpha_sd;
+  cp.prior_beta_sd = p.mc.prior_beta_sd;
+  cp.eps = p.eps;
+  cp.theta_used = p.theta_used;
+  cp.lik = p.lik;
+  cp.cuts = p.cuts;
+  cp.result = p.result;
+  cp.st_in = p.st_in;
+  cp.st_out = p.st_out;
+  finish_class_model(cp, sh);
+  __syncthreads();
+  if (p.host_out) {
+    const int P = p.P;
+    for (int i = threadIdx.x; i < P + 2; i += blockDim.x) p.host_out[i] = p.result[i];
+    if (p.mode == MODE_LEAPFROG)
+      for (int i = threadIdx.x; i < 3 * P + 1; i += blockDim.x) p.host_out[(P + 2) + i] = p.st_out[i];
+  }
+  host_out_publish(p);
 }
 
 }  // namespace b200glm

@@ -38,7 +38,7 @@ DEFAULT_PRIORS = dict(prior_alpha_sd=2.5, prior_beta_sd=2.5, prior_sigma_loc=1.0
 
 
 def make_desc(family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=1, N_total=0,
-              grid_ctas=0, flags=0, data_on_device=False, N=None, K=None, ldx=None, trials=None, **priors):
+              grid_ctas=0, flags=0, data_on_device=False, N=None, K=None, ldx=None, trials=None, n_classes=0, **priors):
     """Fill a b200glm_desc.  X, y, group: numpy arrays (host), or -- with data_on_device=True -- integer
     device pointers (e.g. torch tensor .data_ptr()) with N, K, ldx given explicitly.  Returns (desc, keep):
     `keep` holds the host arrays the descriptor points into (they must outlive the create call)."""
@@ -83,6 +83,7 @@ def make_desc(family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=
             keep.append(trials)
             d.trials = trials.ctypes.data if trials.size else None
     d.family, d.G, d.data_on_device = fam, int(G), int(bool(data_on_device))
+    d.n_classes = int(n_classes)
     pri = dict(DEFAULT_PRIORS)
     pri.update(priors)
     for k, v in pri.items():
@@ -95,16 +96,16 @@ def make_desc(family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=
 class GLMModel:
     def __init__(self, family, X, y, group=None, G=0, device=0, n_slots=1, rank=0, world=1, N_total=0,
                  grid_ctas=0, flags=0, data_on_device=False, N=None, K=None, ldx=None, trials=None,
-                 _host_chunks=False, **priors):
+                 n_classes=0, _host_chunks=False, **priors):
         """X, y, group, trials: numpy arrays (host), or -- with data_on_device=True -- integer device
         pointers (e.g. torch tensor .data_ptr()) with N, K, ldx given explicitly."""
         self.L = _capi.lib()
         self.family = family
         d, keep = make_desc(family, X, y, group, G, device, n_slots, rank, world, N_total, grid_ctas, flags,
-                            data_on_device, N, K, ldx, trials, **priors)
+                            data_on_device, N, K, ldx, trials, n_classes, **priors)
         if _host_chunks:
             d.data_on_device = 0
-        self.N, self.K, self.G = int(d.N), int(d.K), int(G)
+        self.N, self.K, self.G, self.n_classes = int(d.N), int(d.K), int(G), int(n_classes)
         self.rank, self.world = int(rank), int(world)
         h = C.c_void_p()
         rc = self.L.b200glm_create(C.byref(d), C.byref(h))
@@ -172,6 +173,11 @@ class GLMModel:
         return self.P
 
     def param_names(self):
+        if self.family == "ordered_logistic":
+            return [f"beta.{k}" for k in range(1, self.K + 1)] + [f"c.{j}" for j in range(1, self.n_classes)]
+        if self.family == "categorical_logit":
+            return ([f"alpha.{c}" for c in range(1, self.n_classes + 1)]
+                    + [f"beta.{k}.{c}" for c in range(1, self.n_classes + 1) for k in range(1, self.K + 1)])
         n = (["mu_a", "sigma_a"] + [f"a.{g}" for g in range(1, self.G + 1)]) if self.G else ["alpha"]
         n += [f"beta.{k}" for k in range(1, self.K + 1)]
         if self.family == "normal_id":
