@@ -1,6 +1,7 @@
 """Summarise an ncu --set full report into profiles/<name>_summary.txt (+ traffic.json for bench.py).
 
     python profiles/summarize_ncu.py gpurun_out/prof_r1.ncu-rep r1_glm_fused_bernoulli_N10M_K100 10000000 100
+    python profiles/summarize_ncu.py rep name N K family G kernel_prefix     # round 2: traffic of ONE kernel only
 """
 import csv
 import io
@@ -32,6 +33,9 @@ def to_bytes(v, unit):
 def main():
     rep, name = sys.argv[1], sys.argv[2]
     N, K = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (None, None)
+    family = sys.argv[5] if len(sys.argv) > 5 else None
+    G = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+    kprefix = sys.argv[7] if len(sys.argv) > 7 else None
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw[raw.index('"ID"'):])))
     hdr, units = rows[0], rows[1]
@@ -45,7 +49,8 @@ def main():
                 i = hdr.index(k)
                 lines.append(f"{k:95s} {r[i]:>18s} {units[i]}")
         i_r, i_w = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-        traffic.append(to_bytes(r[i_r], units[i_r]) + to_bytes(r[i_w], units[i_w]))
+        if kprefix is None or kprefix in r[hdr.index('Kernel Name')]:   # the dominant kernel only
+            traffic.append(to_bytes(r[i_r], units[i_r]) + to_bytes(r[i_w], units[i_w]))
     with open(os.path.join(here, name + "_summary.txt"), "w") as f:
         f.write("\n".join(lines) + "\n")
     if N is not None:
@@ -54,9 +59,12 @@ def main():
         if os.path.exists(tp):
             with open(tp) as f:
                 old = json.load(f)
-            ents = [e for e in old.get("entries", [old]) if not (e.get("N") == N and e.get("K") == K)]
-        ents.append({"N": N, "K": K, "dram_bytes_per_launch": sum(traffic) / len(traffic),
-                     "source": name + "_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, mean over captured launches)"})
+            ents = [e for e in old.get("entries", [old])
+                    if not (e.get("N") == N and e.get("K") == K and e.get("family") == family and e.get("G", 0) == G)]
+        ents.append({"N": N, "K": K, "family": family, "G": G, "kernel": kprefix or "glm_fused_kernel",
+                     "dram_bytes_per_launch": sum(traffic) / len(traffic),
+                     "source": name + "_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of " +
+                               (kprefix or "every kernel") + ", mean over the captured launches)"})
         with open(tp, "w") as f:
             json.dump({"entries": ents}, f, indent=1)
     print("\n".join(lines))

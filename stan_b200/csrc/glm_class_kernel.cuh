@@ -171,15 +171,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_class_kernel(const __grid_
 
       if (ORDERED) {
         // ---- phase 1: location of row `lane`, link, cut-point partials ----
-        double e0 = 0.0, e1 = 0.0;
+        double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;      // four independent FMA chains, as in the narrow kernel
+        const int o1 = lane ^ 4, o2 = lane ^ 8, o3 = lane ^ 12;
         int c = 0;
-        for (; c + 2 <= K; c += 2) {
-          e0 = fma(tile[c * 32 + (lane ^ ((c & 3) << 2))], sbeta[c], e0);
-          e1 = fma(tile[(c + 1) * 32 + (lane ^ (((c + 1) & 3) << 2))], sbeta[c + 1], e1);
+#pragma unroll 4
+        for (; c + 4 <= K; c += 4) {
+          e0 = fma(tile[(c + 0) * 32 + lane], sbeta[c], e0);
+          e1 = fma(tile[(c + 1) * 32 + o1], sbeta[c + 1], e1);
+          e2 = fma(tile[(c + 2) * 32 + o2], sbeta[c + 2], e2);
+          e3 = fma(tile[(c + 3) * 32 + o3], sbeta[c + 3], e3);
         }
-        if (c < K) e0 = fma(tile[c * 32 + (lane ^ ((c & 3) << 2))], sbeta[c], e0);
+        for (; c < K; ++c) e0 = fma(tile[c * 32 + (lane ^ ((c & 3) << 2))], sbeta[c], e0);
         double lp_i, w_i, d1, d2;
-        ordered_logistic_row(e0 + e1, y, NC, scut, lp_i, w_i, d1, d2);
+        ordered_logistic_row((e0 + e1) + (e2 + e3), y, NC, scut, lp_i, w_i, d1, d2);
         if (!valid) {
           lp_i = 0.0;
           w_i = 0.0;
@@ -206,7 +210,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_class_kernel(const __grid_
         double lin[CMAX];
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) lin[c] = 0.0;
-        for (int k = 0; k < K; ++k) {
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {             // unrolled: the loads of four columns are in flight together
           const double x = tile[k * 32 + (lane ^ ((k & 3) << 2))];
 #pragma unroll
           for (int c = 0; c < CMAX; c += 2) {     // one broadcast 16-byte load per class pair
