@@ -5,12 +5,13 @@
 // util::run_adaptive_sampler per chain).  Here every chain still runs the reference's UNMODIFIED
 // single-chain service (hmc_nuts_diag_e_adapt.hpp:58-117 -> adapt_diag_e_nuts -> base_nuts::transition,
 // same RNG stream create_rng(seed, init_chain_id + i) as the multi-chain overload :352), but as a FIBER:
-// a re-entrant computation with its own small stack, all chains in ONE host thread.  Whenever a chain needs a
+// a re-entrant computation with its own small stack, the chains dealt out to a handful of worker threads (one per
+// core, at most 16 -- not one OS thread per chain).  Whenever a chain needs a
 // leapfrog step (expl_leapfrog::evolve, base_nuts.hpp:254) or a gradient (hamiltonian.init, base_nuts.hpp:85)
 // it records the request and switches back to the scheduler -- in the middle of the reference's recursive
 // build_tree (base_nuts.hpp:247-352), whose frames simply stay on the fiber's stack; once every live chain has
 // a request pending, ONE b200glm_leapfrog_batched call -- one pass over X, the fp64 DMMA GEMM pair -- serves
-// them all, and the scheduler resumes the chains one after the other.  (Round 1 gave every chain an OS thread and
+// them all, and the workers resume their chains one after the other.  (Round 1 gave every chain an OS thread and
 // met at a mutex + condition variable: 1024 threads, 1024 wake-ups per batch, an AD tape per thread.)  Chains
 // advance in lock-step by leapfrog call; trees of different depth simply make a chain take part in
 // more or fewer batches per transition.  A gradient request is served as a leapfrog lane with eps = 0
@@ -23,9 +24,14 @@
 
 #include <stan/services/sample/hmc_nuts_diag_e_adapt.hpp>
 
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <limits>
 #include <memory>
+#include <mutex>
+#include <thread>
 
 namespace b200 {
 
@@ -248,7 +254,7 @@ class chain_batcher final : public glm_model::batch_hook {
   const glm_model& m_;
   const size_t P_;
   const int n_;
-  int n_active_, n_waiting_ = 0;
+  std::atomic<int> n_active_, n_waiting_{0};   // chains of different workers park / leave concurrently
   std::string fatal_;
   std::vector<request> req_;
   std::vector<resident> res_;
@@ -294,25 +300,61 @@ int hmc_nuts_diag_e_adapt_batched(glm_model& model, size_t num_chains, const std
       }
     }));
   }
-  // The scheduler: resume every chain that is not finished; each runs (through the reference's transition /
-  // build_tree code) until its next leapfrog or gradient request, or to its end.  After a sweep every live chain is
-  // parked with a request: serve them all with one batched launch and sweep again.
-  for (;;) {
-    size_t live = 0;
-    for (size_t i = 0; i < num_chains; ++i) {
-      if (chains[i]->done())
-        continue;
-      glm_model::tls_hook() = &batcher;          // the fibers share this thread's thread-locals
-      glm_model::tls_chain() = static_cast<int>(i);
-      chains[i]->resume();
-      if (!chains[i]->done())
-        ++live;
+  // The scheduler.  The chains are dealt out to a few worker threads (not one thread per chain: as many as the host
+  // has cores, at most 16); a worker resumes each of its unfinished chains in turn -- each runs, through the
+  // reference's transition / build_tree code, until its next leapfrog or gradient request, or to its end -- then
+  // meets the other workers; the last one to arrive serves ALL parked chains with one batched launch, and the next
+  // sweep starts.  A fiber is only ever resumed by its own worker (thread-local AD tape, slot binding).  With one
+  // worker this is a plain loop; the workers only spread the host-side tree arithmetic (a few P-vector operations and
+  // copies per leapfrog and chain) over cores -- at 1024 chains that is ~8 ms per full batch on a single core.
+  const int n_workers = static_cast<int>(std::max<size_t>(
+      1, std::min<size_t>({num_chains, std::max(1u, std::thread::hardware_concurrency()), size_t(16)})));
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  size_t live_total = 0;
+  std::uint64_t gen = 0;
+  bool stop = false;
+  auto worker = [&](int t) {
+    stan::math::ChainableStack tape;   // STAN_THREADS: every thread owns an AD tape (init_chainablestack.hpp)
+    for (;;) {
+      size_t live = 0;
+      for (size_t i = t; i < num_chains; i += n_workers) {
+        if (chains[i]->done())
+          continue;
+        glm_model::tls_hook() = &batcher;          // the fibers of a worker share its thread-locals
+        glm_model::tls_chain() = static_cast<int>(i);
+        chains[i]->resume();
+        if (!chains[i]->done())
+          ++live;
+      }
+      glm_model::tls_hook() = nullptr;
+      glm_model::tls_chain() = -1;
+      std::unique_lock<std::mutex> lk(mu);
+      live_total += live;
+      if (++arrived == n_workers) {
+        if (live_total > 0)
+          batcher.serve();
+        stop = live_total == 0;
+        live_total = 0;
+        arrived = 0;
+        ++gen;
+        cv.notify_all();
+      } else {
+        const std::uint64_t g0 = gen;
+        cv.wait(lk, [&] { return gen != g0; });
+      }
+      if (stop)
+        break;
     }
-    glm_model::tls_hook() = nullptr;
-    glm_model::tls_chain() = -1;
-    if (live == 0)
-      break;
-    batcher.serve();
+  };
+  {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_workers; ++t)
+      pool.emplace_back(worker, t);
+    worker(0);
+    for (auto& th : pool)
+      th.join();
   }
   if (stats) {
     stats[0] = batcher.n_batches();
