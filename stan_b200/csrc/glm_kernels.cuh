@@ -363,7 +363,7 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
   if (fam_has_scale(FAMILY) && tid == 0) lik[P - 1] = 0.0;  // sigma | phi entry is derived in finish()
   if (FAMILY != FAM_NEG_BINOMIAL_2_LOG && tid == 32) lik[P + 1] = 0.0;
   if (G > 0 && tid < 2) lik[tid] = 0.0;
-  __threadfence();
+  if (!st.lik) __threadfence();                  // the sums live in global memory only without the on-chip copy
   __syncthreads();
   if (tid == 0) tl_stamp(p, grid, 1);            // sum of the grid's partial rows done
   if (p.peer_in_main && !peer_allreduce_lik(p, sh_is_last, lik)) {

@@ -12,7 +12,7 @@
 //   issued in bursts while P2 freed slots and HBM idled one latency per panel (ncu: 57 % DRAM, 71 % of
 //   the copy roof); with the ring holding >= 2 panels the stream is continuous (89 %).
 //
-// CTA (persistent, one per SM) = 8 consumer warps + 1 TMA producer warp + 2 link warps (even / odd row panels).
+// CTA (persistent, one per SM) = 8 consumer warps + 1 TMA producer warp + 1 link warp.
 //   The shared-memory ring has T >= 2J sub-panel slots: the panel between its eta pass and its X^T r
 //   pass stays resident, the rest holds the following panel(s).
 //   consumer warp w owns sub-panels j = w, w+8, ... of every row panel (so it owns those columns'
@@ -24,6 +24,10 @@
 //   Software pipeline: a consumer publishes eta(n+1) BEFORE it waits for r(n), so the link warp's
 //   fp64 exp/log1p dependency chain for panel n+1 overlaps P2(n); eta / r buffers and the two named
 //   barriers are double-buffered by panel parity.
+//   Round 2 measured three variants of this structure -- two link warps (even / odd panels), 4-row panels, and the
+//   panel kept in registers between the passes with the ring slot released after P1 -- none was faster
+//   (profiles/r2_wide_variants.txt: 1.34 / 2.48 / 1.36 ms against 1.29 ms at K = 1000), so neither link-warp
+//   throughput nor ring capacity is what holds the kernel at ~6 TB/s; the structure below is round 1's.
 //   Lane mapping (both passes): lane = (rq, cq) handles column cq + CPS*t and four rows
 //   {2rq, 2rq+1, 2(rq+LPC), 2(rq+LPC)+1} with two LDS.128; half of the columns swap the order of the
 //   two loads, which makes every quarter-warp cover all 32 banks (conflict free without a swizzle).
@@ -34,12 +38,11 @@
 namespace b200glm {
 
 constexpr int WIDE_CONSUMER_WARPS = 8;
-constexpr int WIDE_LINK_WARPS = 1;   // link warps alternate over the row panels; two were measured: no gain (see below)
-constexpr int WIDE_THREADS = (WIDE_CONSUMER_WARPS + 1 + WIDE_LINK_WARPS) * 32;
+constexpr int WIDE_THREADS = (WIDE_CONSUMER_WARPS + 2) * 32;
 constexpr int WIDE_MAX_SLOTS = 96;
 // named barriers: ETA / R, double-buffered by panel parity
-enum { WIDE_BAR_ETA = 1, WIDE_BAR_R = 3, WIDE_BAR_LINK = 5 };
-constexpr int WIDE_BAR_COUNT = (WIDE_CONSUMER_WARPS + 1) * 32;  // consumers + the link warp of that panel parity
+enum { WIDE_BAR_ETA = 1, WIDE_BAR_R = 3 };
+constexpr int WIDE_BAR_COUNT = (WIDE_CONSUMER_WARPS + 1) * 32;  // consumers + link warp
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -56,7 +59,7 @@ __host__ __device__ inline int wide_cps(int WR) { return 32 / (WR / 4); }
 
 // doubles of dynamic shared memory besides the ring slots and their barriers
 __host__ __device__ inline size_t wide_fixed_doubles(int WR, int J, int KC, int G, int stage_a, int P_state = 0) {
-  return (size_t)J * KC + 2 * WIDE_CONSUMER_WARPS * WR + 2 * WR + 6 * WR + (stage_a ? ((G + 1) & ~1) : 0)
+  return (size_t)J * KC + 2 * WIDE_CONSUMER_WARPS * WR + 2 * WR + (stage_a ? ((G + 1) & ~1) : 0)
          + (P_state ? state_smem_doubles(P_state) : 0);
 }
 
@@ -72,17 +75,13 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
   double* sbeta = ring + (size_t)T * SLOT;                       // J * KC (zero beyond K)
   double* eta_part = sbeta + J * KC;                             // 2 parities x 8 warps x WR
   double* r_sh = eta_part + 2 * WIDE_CONSUMER_WARPS * WR;        // 2 parities x WR
-  double* y_sh = r_sh + 2 * WR;                                  // 2 parities x WR: y, trials, group id of the panel's
-  double* t_sh = y_sh + 2 * WR;                                  //   rows, published by the warp that owns their column
-  double* g_sh = t_sh + 2 * WR;
-  double* sa = g_sh + 2 * WR;                                    // G (optional)
+  double* sa = r_sh + 2 * WR;                                    // G (optional)
   double* st_base = sa + (p.stage_a_in_smem ? ((G + 1) & ~1) : 0);   // chain state (optional)
   const StateSmem st = carve_state_smem(st_base, P, p.state_in_smem);
   double* after_a = st_base + (p.state_in_smem ? state_smem_doubles(P) : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(after_a);     // T
   uint64_t* empty_bar = full_bar + T;                            // T
   __shared__ double sh_scratch[64];
-  __shared__ double sh_link[4];   // sums handed over by link warps 1.. (unused with one link warp)
   __shared__ int sh_is_last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -136,27 +135,9 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
 #pragma unroll
     for (int a = 0; a < SPW * SPC; ++a) acc[a] = 0.0;
 
-    // Where the aux columns live: y in column K, the binomial population sizes in K + 1, the group id after them.
-    // The warp that owns such a column hands the panel's values to the link warp together with its partial eta.
-    const int Kgc = fam_group_col(FAMILY, K);
-    const int aux_col[3] = {K, K + 1, Kgc};
-    const bool aux_on[3] = {true, FAMILY == FAM_BINOMIAL_LOGIT, G > 0};
-    double* const aux_dst[3] = {y_sh, t_sh, g_sh};
-
-    // REG: the warp keeps its 32 doubles per lane of the panel in REGISTERS between the two passes and releases the
-    // ring slot right after P1, so that the whole ring is look-ahead for the TMA stream.  Built and measured in round 2
-    // (K = 1000: 1.357 ms against 1.351 ms with the panel resident in shared memory; K = 500: 0.668 against 0.636 ms,
-    // 168 registers and a few spills): no gain, so ring capacity is not what holds this kernel at ~5.9 TB/s either,
-    // and the shared-memory-resident form stays.  Two link warps (WIDE_LINK_WARPS) and 4-row panels were measured too
-    // (no gain; 2x slower).  profiles/r2_wide_variants.txt.
-    constexpr bool REG = false;
-    struct Keep {
-      double2 a[SPC], b[SPC];
-    };
-
     // P1 of one whole panel (this warp's sub-panels, at ring position `ahead` panels past slot[]),
     // then publish the warp's partial eta of the panel's rows into parity buffer `buf`
-    auto pass1_publish = [&](int ahead, int buf, Keep& kp) {
+    auto pass1_publish = [&](int ahead, int buf) {
       double eA0 = 0.0, eA1 = 0.0, eB0 = 0.0, eB1 = 0.0;
 #pragma unroll
       for (int i = 0; i < SPW; ++i) {
@@ -172,37 +153,18 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
           }
           mbar_wait(&full_bar[sl], pr);
           const double* tile = ring + (size_t)sl * SLOT + cq * WR;
-          const int jsub = warp + WIDE_CONSUMER_WARPS * i;
-          const double* bj = sbeta + jsub * KC + cq;
+          const double* bj = sbeta + (warp + WIDE_CONSUMER_WARPS * i) * KC + cq;
 #pragma unroll
           for (int t = 0; t < SPC; ++t) {
             if (t < steps[i]) {
               const double b = bj[CPS * t];
               const double2 xa = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offA);
               const double2 xb = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offB);
-              if (REG) {
-                kp.a[t] = xa;
-                kp.b[t] = xb;
-              }
               eA0 = fma(xa.x, b, eA0);
               eA1 = fma(xa.y, b, eA1);
               eB0 = fma(xb.x, b, eB0);
               eB1 = fma(xb.y, b, eB1);
-              const int col = jsub * KC + cq + CPS * t;      // an aux column: beta is zero there, eta is unaffected
-#pragma unroll
-              for (int u = 0; u < 3; ++u)
-                if (aux_on[u] && col == aux_col[u]) {
-                  double* d = aux_dst[u] + buf * WR;
-                  d[offA] = xa.x;
-                  d[offA + 1] = xa.y;
-                  d[offB] = xb.x;
-                  d[offB + 1] = xb.y;
-                }
             }
-          }
-          if (REG) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[sl]);
           }
         }
       }
@@ -224,8 +186,14 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
       named_bar_arrive(WIDE_BAR_ETA + buf, WIDE_BAR_COUNT);
     };
 
-    // ---- P2: X^T r from the kept registers (REG) or from the same resident sub-panels ----
-    auto pass2 = [&](int buf, const Keep& kp) {
+    if (n_my > 0) pass1_publish(0, 0);
+    for (long long n = 0; n < n_my; ++n) {
+      const int buf = (int)(n & 1);
+      // eta of panel n+1 goes to the link warp BEFORE this warp waits for r of panel n: the link
+      // function of n+1 then overlaps P2(n) (the ring holds at least two panels: T >= 2J)
+      if (n + 1 < n_my) pass1_publish(1, buf ^ 1);
+
+      // ---- P2: X^T r from the same resident sub-panels ----
       named_bar_sync(WIDE_BAR_R + buf, WIDE_BAR_COUNT);
       const double2 rA = *reinterpret_cast<const double2*>(r_sh + buf * WR + offA);
       const double2 rB = *reinterpret_cast<const double2*>(r_sh + buf * WR + offB);
@@ -236,8 +204,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
 #pragma unroll
           for (int t = 0; t < SPC; ++t) {
             if (t < steps[i]) {
-              const double2 xa = REG ? kp.a[t] : *reinterpret_cast<const double2*>(tile + CPS * WR * t + offA);
-              const double2 xb = REG ? kp.b[t] : *reinterpret_cast<const double2*>(tile + CPS * WR * t + offB);
+              const double2 xa = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offA);
+              const double2 xb = *reinterpret_cast<const double2*>(tile + CPS * WR * t + offB);
               double a = acc[i * SPC + t];
               a = fma(xa.x, rA.x, a);
               a = fma(xa.y, rA.y, a);
@@ -246,29 +214,14 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
               acc[i * SPC + t] = a;
             }
           }
-          if (!REG) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[slot[i]]);
-          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[slot[i]]);
         }
         slot[i] += J;
         if (slot[i] >= T) {
           slot[i] -= T;
           par[i] ^= 1u;
         }
-      }
-    };
-
-    // Software pipeline, unrolled by two so that the two register sets have fixed names: eta of panel n+1 goes to
-    // the link warp BEFORE this warp waits for r of panel n, so the link function of n+1 overlaps P2(n).
-    Keep kA, kB;
-    if (n_my > 0) pass1_publish(0, 0, kA);
-    for (long long n = 0; n < n_my; n += 2) {
-      if (n + 1 < n_my) pass1_publish(1, 1, kB);
-      pass2(0, kA);
-      if (n + 1 < n_my) {
-        if (n + 2 < n_my) pass1_publish(1, 0, kA);
-        pass2(1, kB);
       }
     }
 
@@ -305,14 +258,14 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
       }
     }
   } else {
-    // =============================== link warps ===============================
-    // Link warp lw takes the row panels n = lw, lw + WIDE_LINK_WARPS, ...  (the eta / r buffers and both named barriers
-    // are double-buffered by panel parity, so two link warps would never share one).  Two were measured in round 2:
-    // no gain (K = 1000: 1.340 ms against 1.29 ms with one) -- the barrier stall ncu showed in round 1 (2.36 cycles
-    // per issue) was the consumers waiting for r while the resident panels held the ring, not link throughput.
-    // y / trials / group id of the panel's rows arrive in y_sh / t_sh / g_sh with the partial etas.
-    const int lw = warp - (WIDE_CONSUMER_WARPS + 1);
+    // =============================== link warp ===============================
     const int r = lane & (WR - 1);
+    const int jy = K / KC, coly = K - jy * KC;            // y lives in column K
+    const int jt = (K + 1) / KC, colt = K + 1 - jt * KC;  // binomial population sizes in column K+1
+    const int Kg = fam_group_col(FAMILY, K);
+    const int jg = Kg / KC, colg = Kg - jg * KC;          // group id after the y (and trials) columns (G > 0)
+    int slot_y = jy, slot_g = jg, slot_t = jt;
+    uint32_t par_y = 0, par_g = 0, par_t = 0;
     const double alpha = G > 0 ? 0.0 : theta_at(0);
     LinkConst lc;
     lc.inv_sigma = 1.0;
@@ -328,18 +281,24 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
       lc.lg_phi = lgamma(lc.phi);
     }
     double lp_acc = 0.0, r_acc = 0.0, x_acc = 0.0;
-    for (long long n = lw; n < n_my; n += WIDE_LINK_WARPS) {
+    for (long long n = 0; n < n_my; ++n) {
       const int buf = (int)(n & 1);
       const long long pi = blockIdx.x + n * grid;
-      named_bar_sync(WIDE_BAR_ETA + buf, WIDE_BAR_COUNT);
-      const double y = y_sh[buf * WR + r];
-      const double trials = FAMILY == FAM_BINOMIAL_LOGIT ? t_sh[buf * WR + r] : 0.0;
+      mbar_wait(&full_bar[slot_y], par_y);
+      const double y = ring[(size_t)slot_y * SLOT + coly * WR + r];
+      double trials = 0.0;
+      if (FAMILY == FAM_BINOMIAL_LOGIT) {
+        mbar_wait(&full_bar[slot_t], par_t);
+        trials = ring[(size_t)slot_t * SLOT + colt * WR + r];
+      }
       double off = alpha;
       if (G > 0) {
-        const int gi = (int)g_sh[buf * WR + r] - 1;
+        mbar_wait(&full_bar[slot_g], par_g);
+        const int gi = (int)ring[(size_t)slot_g * SLOT + colg * WR + r] - 1;
         const bool gok = gi >= 0 && gi < G;
         off = p.stage_a_in_smem ? sa[gok ? gi : 0] : theta_at(2 + (gok ? gi : 0));
       }
+      named_bar_sync(WIDE_BAR_ETA + buf, WIDE_BAR_COUNT);
       double eta = 0.0;
 #pragma unroll
       for (int w = 0; w < WIDE_CONSUMER_WARPS; ++w) eta += eta_part[(buf * WIDE_CONSUMER_WARPS + w) * WR + r];
@@ -360,26 +319,26 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
       }
       __threadfence_block();
       named_bar_arrive(WIDE_BAR_R + buf, WIDE_BAR_COUNT);
+      slot_y += J;
+      if (slot_y >= T) {
+        slot_y -= T;
+        par_y ^= 1u;
+      }
+      slot_g += J;
+      if (slot_g >= T) {
+        slot_g -= T;
+        par_g ^= 1u;
+      }
+      slot_t += J;
+      if (slot_t >= T) {
+        slot_t -= T;
+        par_t ^= 1u;
+      }
     }
     lp_acc = warp_sum(lp_acc);
     r_acc = warp_sum(r_acc);
     x_acc = warp_sum(x_acc);
-    // the other link warps hand their sums to warp 0 (fixed order)
-    if (lw > 0 && lane == 0) {
-      sh_link[3 * (lw - 1)] = lp_acc;
-      sh_link[3 * (lw - 1) + 1] = r_acc;
-      sh_link[3 * (lw - 1) + 2] = x_acc;
-    }
-    if (WIDE_LINK_WARPS > 1) {
-      __threadfence_block();
-      named_bar_sync(WIDE_BAR_LINK, WIDE_LINK_WARPS * 32);
-    }
-    if (lw == 0 && lane == 0) {
-      for (int o = 0; o < WIDE_LINK_WARPS - 1; ++o) {
-        lp_acc += sh_link[3 * o];
-        r_acc += sh_link[3 * o + 1];
-        x_acc += sh_link[3 * o + 2];
-      }
+    if (lane == 0) {
       my_part[K] = lp_acc;
       my_part[K + 1] = r_acc;
       my_part[K + 2] = x_acc;   // neg_binomial_2_log: sum of the per-row d/dphi terms

@@ -190,6 +190,31 @@ def test_batched_driver_batches_chains(batched_pair):
     assert bat["batches"] < 0.25 * bat["lanes"], (bat["batches"], bat["lanes"])
 
 
+def test_batched_driver_parallel_match_at_1024_chains():
+    """The reference's parallel-match property (T/unit/services/sample/hmc_nuts_diag_e_adapt_parallel_match_test.cpp:
+    73-140: a chain of the multi-chain service equals the single-chain service run with that chain's id) at the chain
+    count of BASELINE configs[2]: 1024 chains as fibers on a few worker threads, every batch one DMMA launch; chains
+    picked across the range are compared with the UNBATCHED service started with the same seed and chain id, and the
+    pooled posterior with the data-generating parameters."""
+    d = make_glm_data("normal_id", 3_000, 4)
+    m = stan_service.StanGLM("normal_id", d["X"], d["y"], n_slots=4)
+    kw = dict(seed=2024, num_warmup=60, num_samples=40, delta=0.8)
+    bat = m.nuts_batched(num_chains=1024, **kw)
+    assert np.all(np.isfinite(bat["draws"])) and bat["draws"].shape[0] == 1024
+    assert bat["batches"] < 0.02 * bat["lanes"]                  # ~1024 lanes per launch for most of the run
+    for c in (0, 1, 511, 777, 1023):
+        one = m.nuts(num_chains=1, init_chain_id=1 + c, num_threads=1, **kw)
+        a, b = bat["warmup_draws"][c, :5, :], one["warmup_draws"][0, :5, :]
+        assert np.array_equal(a[:, 3:6], b[:, 3:6]), c           # tree depth, leapfrog count, divergence flag
+        assert np.max(np.abs(a[:, 7:] - b[:, 7:])) < 1e-6, c     # draws agree until rounding is amplified
+    m.close()
+    pooled = bat["draws"][:, :, 7:].reshape(-1, bat["draws"].shape[2] - 7)
+    truth = np.concatenate([[d["truth"]["alpha"]], d["truth"]["beta"], [1.0]])
+    sd = pooled.std(axis=0)
+    assert np.all(np.abs(pooled.mean(axis=0) - truth) < 4.0 * sd)   # truth inside the posterior (N = 3000 rows)
+    assert bat["draws"][:, :, 5].sum() == 0                       # no divergences
+
+
 def test_batched_driver_serves_shapes_without_dmma_kernel():
     """Group intercepts are outside the DMMA kernel's scope (G == 0 only): the driver still runs the chains
     in lock-step and serves them lane by lane with the single-chain kernel; posterior == reference CPU."""
