@@ -141,6 +141,18 @@ int b200glm_glm_lpmf(b200glm_handle* h, int32_t slot, int32_t propto, int32_t op
                      int32_t sigma_is_var, const double* alpha, const double* beta, double sigma,
                      double* logp, double* d_alpha, double* d_beta, double* d_sigma);
 
+/* The same entry with PER-ROW operands, the other forms the reference's overloads accept
+ * (SM/opencl/prim/normal_id_glm_lpdf.hpp:68-84: is_alpha_vector, is_sigma_vector; the prim versions likewise):
+ * alpha_rows != NULL: the intercept is an N-vector (alpha is then ignored), its partials -- the per-row residual --
+ * come back in d_alpha_rows (N); sigma_rows != NULL (normal_id only): the scale is an N-vector (sigma ignored), value
+ * -1/2 sum z_i^2 - sum log sigma_i [+ constants], partials (z_i^2 - 1) / sigma_i in d_sigma_rows (N).  All pointers
+ * are HOST pointers; NULL outputs are skipped.  Costs an N-vector upload per vector operand and an N-vector download
+ * per vector of partials on top of the single pass over X.  Scalar-intercept handles (G == 0), K <= 256, unsharded. */
+int b200glm_glm_lpmf_rows(b200glm_handle* h, int32_t slot, int32_t propto, int32_t operands_are_var,
+                          int32_t sigma_is_var, const double* alpha_rows, double alpha, const double* beta,
+                          const double* sigma_rows, double sigma, double* logp, double* d_alpha_rows, double* d_alpha,
+                          double* d_beta, double* d_sigma_rows, double* d_sigma);
+
 /* Device-resident leapfrog (replaces expl_leapfrog::evolve, ST/mcmc/hmc/integrators/
  * base_leapfrog.hpp:17-22 + expl_leapfrog.hpp:16-32, and the update_potential_gradient it calls,
  * base_hamiltonian.hpp:61-70).  set_state uploads z = (q, p, g, V) for a slot;

@@ -18,7 +18,7 @@ SYMBOLS = [
     "b200glm_batch_reserve", "b200glm_log_prob_grad_batched", "b200glm_set_state_batched",
     "b200glm_leapfrog_batched", "b200glm_leapfrog_batched_async", "b200glm_batch_sync", "b200glm_batch_stream",
     "b200glm_peer_export", "b200glm_peer_connect", "b200glm_lgamma_sum_local", "b200glm_set_lgamma_sum_total",
-    "b200glm_glm_lpmf", "b200glm_shard_constants_local", "b200glm_set_shard_constants_total",
+    "b200glm_glm_lpmf", "b200glm_glm_lpmf_rows", "b200glm_shard_constants_local", "b200glm_set_shard_constants_total",
     "b200glm_timeline_enable", "b200glm_timeline_read", "b200glm_abi_version", "b200glm_measure_peaks",
     "b200glm_launch_count", "b200glm_bytes_per_gradient", "b200glm_last_error", "b200glm_version",
 ]
@@ -95,6 +95,8 @@ def lib():
         L.b200glm_set_lgamma_sum_total.argtypes = [C.c_void_p, C.c_double]
         L.b200glm_glm_lpmf.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, dp, dp, C.c_double,
                                        dp, dp, dp, dp]
+        L.b200glm_glm_lpmf_rows.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, dp, C.c_double, dp,
+                                            dp, C.c_double, dp, dp, dp, dp, dp, dp]
         L.b200glm_shard_constants_local.argtypes = [C.c_void_p, dp]
         L.b200glm_set_shard_constants_total.argtypes = [C.c_void_p, dp]
         L.b200glm_timeline_enable.argtypes = [C.c_void_p, C.c_int32, C.c_int32]

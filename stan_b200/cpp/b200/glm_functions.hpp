@@ -51,6 +51,17 @@ grouped_intercept<Vec> by_group(const Vec& a) {
   return {a};
 }
 
+// intercept given PER ROW: alpha is an N-vector (the vector-alpha form of the reference's overloads,
+// SM/opencl/prim/normal_id_glm_lpdf.hpp:68-84 is_alpha_vector)
+template <typename Vec>
+struct row_intercept {
+  const Vec& a;
+};
+template <typename Vec>
+row_intercept<Vec> by_row(const Vec& a) {
+  return {a};
+}
+
 // (y, X [, group]) resident on the device in the panel format the kernels stream
 class glm_data {
  public:
@@ -74,6 +85,7 @@ class glm_data {
     d.n_slots = n_slots;
     d.world = 1;
     family_ = family;
+    N_ = N;
     K_ = K;
     G_ = G;
     n_slots_ = n_slots;
@@ -92,6 +104,7 @@ class glm_data {
     if (h_)
       b200glm_destroy(h_);
   }
+  long long N() const { return N_; }
   y_view y() const { return {this}; }
   x_view x() const { return {this}; }
   trials_view trials() const { return {this}; }
@@ -125,6 +138,21 @@ class glm_data {
  private:
   b200glm_handle* h_ = nullptr;
   int family_ = 0, K_ = 0, G_ = 0, n_slots_ = 1;
+  long long N_ = 0;
+
+ public:
+  // per-row operands (b200glm_glm_lpmf_rows): alpha_rows / sigma_rows may be NULL
+  void evaluate_rows(bool propto, bool operands_are_var, int sigma_is_var, const double* alpha_rows, double alpha,
+                     const double* beta, const double* sigma_rows, double sigma, double& logp, double* d_alpha_rows,
+                     double* d_alpha, double* d_beta, double* d_sigma_rows, double* d_sigma) const {
+    static std::atomic<int> next_thread{0};
+    static thread_local const int thread_ordinal = next_thread.fetch_add(1);
+    const int slot = thread_ordinal % (n_slots_ > 0 ? n_slots_ : 1);
+    const int rc = b200glm_glm_lpmf_rows(h_, slot, propto, operands_are_var, sigma_is_var, alpha_rows, alpha, beta,
+                                         sigma_rows, sigma, &logp, d_alpha_rows, d_alpha, d_beta, d_sigma_rows, d_sigma);
+    if (rc != B200GLM_OK)
+      raise(rc, b200glm_last_error(h_));
+  }
 };
 
 namespace internal {
@@ -190,6 +218,69 @@ template <typename T>
 using is_scalar_operand = std::integral_constant<bool, std::is_arithmetic<T>::value
                                                          || std::is_same<T, stan::math::var>::value>;
 
+// common body of the overloads with per-row operands: T_alpha / T_sigma are scalars or Eigen vectors of size N
+template <bool propto, typename T_alpha, typename T_beta, typename T_sigma>
+stan::return_type_t<T_alpha, T_beta, T_sigma> glm_call_rows(const char* function, int family, const y_view& y,
+                                                              const x_view& x, const T_alpha& alpha, const T_beta& beta,
+                                                              const T_sigma& sigma) {
+  using stan::math::var;
+  using T_ret = stan::return_type_t<T_alpha, T_beta, T_sigma>;
+  if (y.d != x.d || y.d == nullptr)
+    throw std::invalid_argument(std::string(function) + ": y and x must be views of the same b200::glm_data");
+  const glm_data& d = *y.d;
+  if (d.family() != family)
+    throw std::invalid_argument(std::string(function) + ": the glm_data was built for another family");
+  if (static_cast<int>(beta.size()) != d.K())
+    throw std::invalid_argument(std::string(function) + ": Weight vector has the wrong size");
+  constexpr bool alpha_vec = !is_scalar_operand<T_alpha>::value, sigma_vec = !is_scalar_operand<T_sigma>::value;
+  constexpr bool alpha_var = std::is_same<stan::scalar_type_t<T_alpha>, var>::value;
+  constexpr bool beta_var = std::is_same<stan::scalar_type_t<T_beta>, var>::value;
+  constexpr bool sigma_var = std::is_same<stan::scalar_type_t<T_sigma>, var>::value;
+  constexpr bool any_var = alpha_var || beta_var || sigma_var;
+  std::vector<double> va, vb, vs;
+  std::vector<var> ops;
+  if constexpr (alpha_vec) {
+    if (static_cast<long long>(alpha.size()) != d.N())   // check_size_match("Rows of x", N, "size of alpha")
+      throw std::invalid_argument(std::string(function) + ": Vector of intercepts has the wrong size");
+    push_vector(alpha, va, ops);
+  } else {
+    push_scalar(alpha, va, ops);
+  }
+  push_vector(beta, vb, ops);
+  if constexpr (sigma_vec) {
+    if (static_cast<long long>(sigma.size()) != d.N())
+      throw std::invalid_argument(std::string(function) + ": Scale vector has the wrong size");
+    push_vector(sigma, vs, ops);
+  } else {
+    push_scalar(sigma, vs, ops);
+  }
+  double logp = 0, da0 = 0, ds0 = 0;
+  std::vector<double> da(alpha_vec ? va.size() : 0), db(vb.size() + 1), ds(sigma_vec ? vs.size() : 0);
+  d.evaluate_rows(propto, any_var, sigma_var ? ((alpha_var || beta_var) ? 1 : 2) : 0, alpha_vec ? va.data() : nullptr,
+                  va.empty() ? 0.0 : va[0], vb.data(), sigma_vec ? vs.data() : nullptr, vs.empty() ? 1.0 : vs[0], logp,
+                  alpha_vec ? da.data() : nullptr, &da0, db.data(), sigma_vec ? ds.data() : nullptr, &ds0);
+  if constexpr (!any_var) {
+    return logp;
+  } else {
+    std::vector<double> grads;
+    if (alpha_var) {
+      if (alpha_vec)
+        grads.insert(grads.end(), da.begin(), da.end());
+      else
+        grads.push_back(da0);
+    }
+    if (beta_var)
+      grads.insert(grads.end(), db.begin(), db.begin() + vb.size());
+    if (sigma_var) {
+      if (sigma_vec)
+        grads.insert(grads.end(), ds.begin(), ds.end());
+      else
+        grads.push_back(ds0);
+    }
+    return T_ret(stan::math::precomputed_gradients(logp, ops, grads));
+  }
+}
+
 }  // namespace internal
 }  // namespace b200
 
@@ -216,7 +307,8 @@ return_type_t<T_alpha, T_beta> poisson_log_glm_lpmf(const b200::y_view& y, const
       static_cast<T_alpha*>(nullptr));
 }
 template <bool propto = false, typename T_alpha, typename T_beta, typename T_sigma,
-          std::enable_if_t<b200::internal::is_scalar_operand<T_alpha>::value>* = nullptr>
+          std::enable_if_t<b200::internal::is_scalar_operand<T_alpha>::value
+                           && b200::internal::is_scalar_operand<T_sigma>::value>* = nullptr>
 return_type_t<T_alpha, T_beta, T_sigma> normal_id_glm_lpdf(const b200::y_view& y, const b200::x_view& x,
                                                             const T_alpha& alpha, const T_beta& beta,
                                                             const T_sigma& sigma) {
@@ -297,6 +389,48 @@ return_type_t<Vec, T_beta, T_sigma> normal_id_glm_lpdf(const b200::y_view& y, co
       "normal_id_glm_lpdf", B200GLM_NORMAL_ID, y, x, static_cast<int>(alpha.a.size()),
       [&](std::vector<double>& v, std::vector<var>& o) { b200::internal::push_vector(alpha.a, v, o); }, beta, sigma,
       static_cast<Vec*>(nullptr));
+}
+
+// ---- intercept per row: alpha = b200::by_row(a), a an N-vector; normal_id also with a vector scale ----------------
+template <bool propto = false, typename Vec, typename T_beta>
+return_type_t<Vec, T_beta> bernoulli_logit_glm_lpmf(const b200::y_view& y, const b200::x_view& x,
+                                                     const b200::row_intercept<Vec>& alpha, const T_beta& beta) {
+  return b200::internal::glm_call_rows<propto>("bernoulli_logit_glm_lpmf", B200GLM_BERNOULLI_LOGIT, y, x, alpha.a, beta, 1.0);
+}
+template <bool propto = false, typename Vec, typename T_beta>
+return_type_t<Vec, T_beta> poisson_log_glm_lpmf(const b200::y_view& y, const b200::x_view& x,
+                                                 const b200::row_intercept<Vec>& alpha, const T_beta& beta) {
+  return b200::internal::glm_call_rows<propto>("poisson_log_glm_lpmf", B200GLM_POISSON_LOG, y, x, alpha.a, beta, 1.0);
+}
+template <bool propto = false, typename Vec, typename T_beta>
+return_type_t<Vec, T_beta> binomial_logit_glm_lpmf(const b200::y_view& n, const b200::trials_view& N,
+                                                    const b200::x_view& x, const b200::row_intercept<Vec>& alpha,
+                                                    const T_beta& beta) {
+  if (N.d != n.d)
+    throw std::invalid_argument("binomial_logit_glm_lpmf: n and N must be views of the same b200::glm_data");
+  return b200::internal::glm_call_rows<propto>("binomial_logit_glm_lpmf", B200GLM_BINOMIAL_LOGIT, n, x, alpha.a, beta, 1.0);
+}
+template <bool propto = false, typename Vec, typename T_beta, typename T_phi>
+return_type_t<Vec, T_beta, T_phi> neg_binomial_2_log_glm_lpmf(const b200::y_view& y, const b200::x_view& x,
+                                                               const b200::row_intercept<Vec>& alpha,
+                                                               const T_beta& beta, const T_phi& phi) {
+  return b200::internal::glm_call_rows<propto>("neg_binomial_2_log_glm_lpmf", B200GLM_NEG_BINOMIAL_2_LOG, y, x, alpha.a,
+                                               beta, phi);
+}
+// sigma: a scalar or an N-vector (Eigen)
+template <bool propto = false, typename Vec, typename T_beta, typename T_sigma>
+return_type_t<Vec, T_beta, T_sigma> normal_id_glm_lpdf(const b200::y_view& y, const b200::x_view& x,
+                                                        const b200::row_intercept<Vec>& alpha, const T_beta& beta,
+                                                        const T_sigma& sigma) {
+  return b200::internal::glm_call_rows<propto>("normal_id_glm_lpdf", B200GLM_NORMAL_ID, y, x, alpha.a, beta, sigma);
+}
+// scalar intercept with a vector scale
+template <bool propto = false, typename T_alpha, typename T_beta, typename VecS,
+          std::enable_if_t<b200::internal::is_scalar_operand<T_alpha>::value
+                           && !b200::internal::is_scalar_operand<VecS>::value>* = nullptr>
+return_type_t<T_alpha, T_beta, VecS> normal_id_glm_lpdf(const b200::y_view& y, const b200::x_view& x,
+                                                         const T_alpha& alpha, const T_beta& beta, const VecS& sigma) {
+  return b200::internal::glm_call_rows<propto>("normal_id_glm_lpdf", B200GLM_NORMAL_ID, y, x, alpha, beta, sigma);
 }
 
 }  // namespace math

@@ -527,6 +527,54 @@ double b200stan_diagnostic(int which, const double* d, int n_draws, int n_chains
   return std::numeric_limits<double>::quiet_NaN();
 }
 
+// The per-row overloads (b200::by_row(alpha), vector sigma) as one node of a reverse-mode tape:
+// f = scale * glm(y | x, by_row(a), b [, s]) + 0.5 * sum(b^2), all operands vars; sigma_rows may be NULL (scalar sigma).
+int b200stan_func_eval_rows(void* dv, int propto, const double* alpha_rows, const double* beta,
+                            const double* sigma_rows, double sigma, double scale, double* f, double* d_alpha_rows,
+                            double* d_beta, double* d_sigma_rows, double* d_sigma, char* err, int errlen) {
+  const b200::glm_data& d = *static_cast<b200::glm_data*>(dv);
+  const int K = d.K();
+  const long long N = d.N();
+  return guarded(err, errlen, [&] {
+    using stan::math::var;
+    stan::math::nested_rev_autodiff nested;
+    Eigen::Matrix<var, -1, 1> a(N), b(K), sv(sigma_rows ? N : 0);
+    for (long long i = 0; i < N; ++i) a[i] = alpha_rows[i];
+    for (int k = 0; k < K; ++k) b[k] = beta[k];
+    for (long long i = 0; i < sv.size(); ++i) sv[i] = sigma_rows[i];
+    var sg = sigma;
+    var lp = 0;
+    auto call = [&](auto pt) {
+      constexpr bool P = decltype(pt)::value;
+      switch (d.family()) {
+        case B200GLM_BERNOULLI_LOGIT: lp = stan::math::bernoulli_logit_glm_lpmf<P>(d.y(), d.x(), b200::by_row(a), b); break;
+        case B200GLM_POISSON_LOG: lp = stan::math::poisson_log_glm_lpmf<P>(d.y(), d.x(), b200::by_row(a), b); break;
+        case B200GLM_BINOMIAL_LOGIT:
+          lp = stan::math::binomial_logit_glm_lpmf<P>(d.y(), d.trials(), d.x(), b200::by_row(a), b);
+          break;
+        case B200GLM_NEG_BINOMIAL_2_LOG:
+          lp = stan::math::neg_binomial_2_log_glm_lpmf<P>(d.y(), d.x(), b200::by_row(a), b, sg);
+          break;
+        default:
+          lp = sigma_rows ? stan::math::normal_id_glm_lpdf<P>(d.y(), d.x(), b200::by_row(a), b, sv)
+                          : stan::math::normal_id_glm_lpdf<P>(d.y(), d.x(), b200::by_row(a), b, sg);
+      }
+    };
+    if (propto)
+      call(std::true_type());
+    else
+      call(std::false_type());
+    var total = scale * lp + 0.5 * stan::math::dot_self(b);
+    total.grad();
+    *f = total.val();
+    for (long long i = 0; i < N; ++i) d_alpha_rows[i] = a[i].adj();
+    for (int k = 0; k < K; ++k) d_beta[k] = b[k].adj();
+    if (sigma_rows)
+      for (long long i = 0; i < N; ++i) d_sigma_rows[i] = sv[i].adj();
+    *d_sigma = sg.adj();
+  });
+}
+
 const char* b200stan_version() {
   return "b200::glm_model behind stan::services::sample::hmc_nuts_diag_e_adapt (reference headers: stan@9048555, math@2fdd3ed)";
 }

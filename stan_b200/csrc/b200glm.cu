@@ -75,6 +75,9 @@ struct Slot {
   double* r_out = nullptr;       // n_panels*32 (G > 0, unfused group path)
   double* gpart = nullptr;       // grid * Gcs (fused group path)
   double* cuts = nullptr;        // ordered_logistic: 2 (C - 1) doubles of epilogue scratch
+  // b200glm_glm_lpmf_rows (allocated on first use): per-row operands in, per-row partials out, N doubles each
+  double *alpha_rows = nullptr, *sigma_rows = nullptr, *s_out = nullptr;
+  bool use_alpha_rows = false, use_sigma_rows = false;   // set for the duration of one rows evaluation
   double* lik = nullptr;         // P + 2
   double* result = nullptr;      // P + 2
   double* theta_used = nullptr;  // P
@@ -84,7 +87,7 @@ struct Slot {
   double* h_out_dev = nullptr;      // device-side address of h_out
   double* h_out = nullptr;          // pinned: [result P+2][state 3P+1][sequence word], written by the epilogue itself
   unsigned long long* tl = nullptr; // (grid + 1) x 16 time stamps of the last launch (b200glm_timeline_enable)
-  std::mutex mu;
+  std::recursive_mutex mu;          // recursive: b200glm_glm_lpmf_rows holds it around eval_host
 };
 
 // Workspace of the batched (many-chain) path: chain state is feature-major [P][ld] on the device.
@@ -316,6 +319,9 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
   p.pstride = h->pstride;
   p.n_classes = h->d.n_classes;
   p.cuts = s->cuts;
+  p.alpha_rows = s->use_alpha_rows ? s->alpha_rows : nullptr;
+  p.sigma_rows = s->use_sigma_rows ? s->sigma_rows : nullptr;
+  p.s_out = s->s_out;
   p.ticket = s->ticket;
   p.r_out = s->r_out;
   p.group_fused = h->group_fused;
@@ -340,6 +346,7 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
   mc.is_var = is_var;
   mc.lik_only = lik_only;
   mc.sigma_is_var = sigma_is_var;
+  mc.sigma_rows = s->use_sigma_rows ? 1 : 0;
   mc.N_total = (double)lik_rows_total(h);
   mc.lgamma_sum = h->lgamma_sum_total;
   mc.prior_alpha_sd = h->d.prior_alpha_sd;
@@ -478,7 +485,7 @@ int eval_host(b200glm_handle* h, int slot, const double* theta, int propto, int 
     return B200GLM_INVALID;
   }
   Slot* s = h->slots[slot];
-  std::lock_guard<std::mutex> g(s->mu);
+  std::lock_guard<std::recursive_mutex> g(s->mu);
   CUDA_TRY(h, cudaSetDevice(h->d.device));
   const int P = h->P;
   rc = enqueue_eval(h, s, MODE_THETA, propto, jacobian, is_var, 0.0, lik_only, sigma_is_var, theta, h->host_mirror);
@@ -570,6 +577,9 @@ void b200glm_destroy(b200glm_handle* h) {
     cudaFree(s->r_out);
     cudaFree(s->gpart);
     cudaFree(s->cuts);
+    cudaFree(s->alpha_rows);
+    cudaFree(s->sigma_rows);
+    cudaFree(s->s_out);
     cudaFree(s->lik);
     cudaFree(s->result);
     cudaFree(s->theta_used);
@@ -1043,6 +1053,95 @@ int b200glm_glm_lpmf(b200glm_handle* h, int32_t slot, int32_t propto, int32_t op
   return B200GLM_OK;
 }
 
+int b200glm_glm_lpmf_rows(b200glm_handle* h, int32_t slot, int32_t propto, int32_t operands_are_var,
+                          int32_t sigma_is_var, const double* alpha_rows, double alpha, const double* beta,
+                          const double* sigma_rows, double sigma, double* logp, double* d_alpha_rows, double* d_alpha,
+                          double* d_beta, double* d_sigma_rows, double* d_sigma) {
+  int rc = validate_slot(h, slot);
+  if (rc) return rc;
+  const b200glm_desc& d = h->d;
+  if (!logp || (d.K > 0 && !beta)) {
+    h->set_error("null pointer argument");
+    return B200GLM_INVALID;
+  }
+  if (fam_is_class(d.family) || d.G > 0 || h->wide || d.world > 1) {
+    h->set_error("b200glm_glm_lpmf_rows: per-row operands are served for families 0-4 with a scalar-intercept handle "
+                 "(G == 0), K <= 256, unsharded");
+    return B200GLM_INVALID;
+  }
+  if (sigma_rows && d.family != B200GLM_NORMAL_ID) {
+    h->set_error("b200glm_glm_lpmf_rows: a per-row scale is an operand of normal_id_glm_lpdf only");
+    return B200GLM_INVALID;
+  }
+  const long long N = d.N;
+  const bool has_scale = fam_has_scale(d.family);
+  if (has_scale && !sigma_rows && !(sigma > 0.0 && std::isfinite(sigma))) {
+    h->set_error(d.family == B200GLM_NORMAL_ID ? "normal_id_glm_lpdf: Scale vector is not positive finite"
+                                                 : "neg_binomial_2_log_glm_lpmf: Precision parameter is not positive finite");
+    return B200GLM_DOMAIN;
+  }
+  if (sigma_rows)
+    for (long long i = 0; i < N; ++i)
+      if (!(sigma_rows[i] > 0.0 && std::isfinite(sigma_rows[i]))) {
+        h->set_error("normal_id_glm_lpdf: Scale vector is not positive finite");   // normal_id_glm_lpdf.hpp:93
+        return B200GLM_DOMAIN;
+      }
+  if (alpha_rows)
+    for (long long i = 0; i < N; ++i)
+      if (!std::isfinite(alpha_rows[i])) {
+        h->set_error("Intercept is not finite");
+        return B200GLM_DOMAIN;
+      }
+  Slot* s = h->slots[slot];
+  const int P = h->P, K = d.K;
+  std::vector<double> th(P, 0.0), g(P, 0.0);
+  std::lock_guard<std::recursive_mutex> lk_all(s->mu);   // the per-row flags of the slot belong to this call
+  {
+    CUDA_TRY(h, cudaSetDevice(d.device));
+    const size_t nb = sizeof(double) * (size_t)std::max<long long>(N, 1);
+    if (alpha_rows) {
+      if (!s->alpha_rows) CUDA_TRY(h, cudaMalloc(&s->alpha_rows, nb));
+      if (!s->r_out) CUDA_TRY(h, cudaMalloc(&s->r_out, sizeof(double) * std::max<long long>(h->n_panels * h->panel_rows, 1)));
+      CUDA_TRY(h, cudaMemcpyAsync(s->alpha_rows, alpha_rows, sizeof(double) * N, cudaMemcpyHostToDevice, s->stream));
+    }
+    if (sigma_rows) {
+      if (!s->sigma_rows) CUDA_TRY(h, cudaMalloc(&s->sigma_rows, nb));
+      if (!s->s_out) CUDA_TRY(h, cudaMalloc(&s->s_out, nb));
+      CUDA_TRY(h, cudaMemcpyAsync(s->sigma_rows, sigma_rows, sizeof(double) * N, cudaMemcpyHostToDevice, s->stream));
+    }
+    s->use_alpha_rows = alpha_rows != nullptr;
+    s->use_sigma_rows = sigma_rows != nullptr;
+  }
+  th[0] = alpha_rows ? 0.0 : alpha;
+  if (K > 0) std::memcpy(th.data() + h->off_beta, beta, sizeof(double) * K);
+  if (has_scale) th[P - 1] = sigma_rows ? 0.0 : std::log(sigma);
+  rc = eval_host(h, slot, th.data(), propto ? 1 : 0, 0, operands_are_var ? 1 : 0, logp, g.data(), 1,
+                 sigma_is_var == 2 ? 2 : (sigma_is_var ? 1 : 0));
+  const bool evaluated = ((!propto) || operands_are_var) && N > 0;   // else the kernel did not run: partials are zero
+  if (rc == B200GLM_OK) {
+    if (d_alpha_rows && alpha_rows) {
+      if (evaluated) {
+        if (cudaMemcpy(d_alpha_rows, s->r_out, sizeof(double) * N, cudaMemcpyDeviceToHost) != cudaSuccess) rc = B200GLM_CUDA;
+      } else {
+        std::memset(d_alpha_rows, 0, sizeof(double) * N);
+      }
+    }
+    if (d_sigma_rows && sigma_rows) {
+      if (evaluated) {
+        if (cudaMemcpy(d_sigma_rows, s->s_out, sizeof(double) * N, cudaMemcpyDeviceToHost) != cudaSuccess) rc = B200GLM_CUDA;
+      } else {
+        std::memset(d_sigma_rows, 0, sizeof(double) * N);
+      }
+    }
+  }
+  s->use_alpha_rows = s->use_sigma_rows = false;
+  if (rc) return rc;
+  if (d_alpha) *d_alpha = alpha_rows ? 0.0 : g[0];
+  if (d_beta && K > 0) std::memcpy(d_beta, g.data() + h->off_beta, sizeof(double) * K);
+  if (d_sigma) *d_sigma = (has_scale && !sigma_rows) ? g[P - 1] : 0.0;
+  return B200GLM_OK;
+}
+
 int b200glm_set_state(b200glm_handle* h, int32_t slot, const double* q, const double* p, const double* g, double V) {
   int rc = validate_slot(h, slot);
   if (rc) return rc;
@@ -1051,7 +1150,7 @@ int b200glm_set_state(b200glm_handle* h, int32_t slot, const double* q, const do
     return B200GLM_INVALID;
   }
   Slot* s = h->slots[slot];
-  std::lock_guard<std::mutex> lk(s->mu);
+  std::lock_guard<std::recursive_mutex> lk(s->mu);
   CUDA_TRY(h, cudaSetDevice(h->d.device));
   const int P = h->P;
   double* hp = s->h_pinned;
@@ -1080,7 +1179,7 @@ int b200glm_leapfrog(b200glm_handle* h, int32_t slot, double eps, const double* 
   int rc = validate_slot(h, slot);
   if (rc) return rc;
   Slot* s = h->slots[slot];
-  std::lock_guard<std::mutex> lk(s->mu);
+  std::lock_guard<std::recursive_mutex> lk(s->mu);
   CUDA_TRY(h, cudaSetDevice(h->d.device));
   const int P = h->P;
   if (inv_metric) {
@@ -1651,7 +1750,7 @@ int b200glm_timeline_enable(b200glm_handle* h, int32_t slot, int32_t on) {
   int rc = validate_slot(h, slot);
   if (rc) return rc;
   Slot* s = h->slots[slot];
-  std::lock_guard<std::mutex> lk(s->mu);
+  std::lock_guard<std::recursive_mutex> lk(s->mu);
   CUDA_TRY(h, cudaSetDevice(h->d.device));
   CUDA_TRY(h, cudaStreamSynchronize(s->stream));
   if (on && !s->tl) {

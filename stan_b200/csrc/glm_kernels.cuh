@@ -290,7 +290,7 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
   // loads; 4.7 us with lanes striding over rows (two half-used 128-byte segments per instruction: one SM's L2 port,
   // not latency, was the limit -- no gain from 8 -> 40 loads in flight, profiles/r2_timeline_*); ~1.5 us like this.
   double* lik = st.lik ? st.lik : p.lik;         // the sums go to the on-chip copy when there is one
-  const int n_sums = FAMILY == FAM_NEG_BINOMIAL_2_LOG ? K + 3 : K + 2;
+  const int n_sums = fam_has_aux_sum(FAMILY) ? K + 3 : K + 2;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const int n_chunks = (n_sums + 31) >> 5;       // 32-column chunks of a row
   // measurement only: tl_repeat makes the sum run twice (same result), the first pass stamped on its own, to
@@ -361,7 +361,7 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
   if (tid == 0) tl_stamp(p, grid + 1, 2);        // sums written
   if (tid == 0) *p.ticket = 0u;
   if (fam_has_scale(FAMILY) && tid == 0) lik[P - 1] = 0.0;  // sigma | phi entry is derived in finish()
-  if (FAMILY != FAM_NEG_BINOMIAL_2_LOG && tid == 32) lik[P + 1] = 0.0;
+  if (!fam_has_aux_sum(FAMILY) && tid == 32) lik[P + 1] = 0.0;
   if (G > 0 && tid < 2) lik[tid] = 0.0;
   if (!st.lik) __threadfence();                  // the sums live in global memory only without the on-chip copy
   __syncthreads();
@@ -573,7 +573,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
       }
       const bool valid = (pi * PANEL_ROWS + lane) < p.n_rows;
       double lp_i, r_i, x_i;
-      link_ext<FAMILY>(eta, y, FAMILY == FAM_BINOMIAL_LOGIT ? tile[tcol] : 0.0, lc, lp_i, r_i, x_i);
+      if (p.alpha_rows || p.sigma_rows) {
+        // function-level call with per-row operands (G == 0: rows are in the caller's order)
+        const long long row = pi * PANEL_ROWS + lane;
+        if (p.alpha_rows && valid) eta += __ldg(p.alpha_rows + row);
+        LinkConst lcr = lc;
+        double sg = 1.0;
+        if (FAMILY == FAM_NORMAL_ID && p.sigma_rows) {
+          sg = valid ? __ldg(p.sigma_rows + row) : 1.0;
+          lcr.inv_sigma = 1.0 / sg;
+        }
+        link_ext<FAMILY>(eta, y, FAMILY == FAM_BINOMIAL_LOGIT ? tile[tcol] : 0.0, lcr, lp_i, r_i, x_i);
+        if (FAMILY == FAM_NORMAL_ID && p.sigma_rows) {
+          x_i = log(sg);                                              // sum log sigma_i rides in the aux sum
+          if (valid) p.s_out[row] = (lp_i - 1.0) * lcr.inv_sigma;    // normal_id_glm_lpdf.hpp:181-183, per row
+        }
+        if (p.alpha_rows && valid) p.r_out[row] = r_i;
+      } else {
+        link_ext<FAMILY>(eta, y, FAMILY == FAM_BINOMIAL_LOGIT ? tile[tcol] : 0.0, lc, lp_i, r_i, x_i);
+      }
       if (!valid) {
         lp_i = 0.0;
         r_i = 0.0;
@@ -581,7 +599,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
       }
       lp_acc += lp_i;
       r_acc += r_i;
-      if (FAMILY == FAM_NEG_BINOMIAL_2_LOG) x_acc += x_i;
+      if (fam_has_aux_sum(FAMILY)) x_acc += x_i;
       if (GF) {
         const int g_first = __shfl_sync(0xffffffffu, gi, 0);          // row 0 of a panel always exists
         if (__all_sync(0xffffffffu, !valid || gi == g_first)) {
@@ -636,7 +654,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) glm_fused_kernel(const __grid_
     }
     lp_acc = warp_sum(lp_acc);
     r_acc = warp_sum(r_acc);
-    if (FAMILY == FAM_NEG_BINOMIAL_2_LOG) x_acc = warp_sum(x_acc);
+    if (fam_has_aux_sum(FAMILY)) x_acc = warp_sum(x_acc);
     if (lane == 0) {
       red[warp * (Kpad + 4) + Kpad] = lp_acc;
       red[warp * (Kpad + 4) + Kpad + 1] = r_acc;

@@ -35,6 +35,7 @@ struct ModelConst {
   int propto, jacobian, is_var;  // semantics of this evaluation (see include/b200glm.h)
   int lik_only;                  // function-level call (b200glm_glm_lpmf): the GLM term alone -- no priors, no
                                  // Jacobian; the sigma entry of the gradient is d/d sigma, not d/d log sigma
+  int sigma_rows;                // lik_only + normal_id with a per-row scale: lik[P + 1] holds sum log sigma_i
   int sigma_is_var;              // lik_only + normal_id: keep -N log sigma under propto (normal_id_glm_lpdf.hpp:205);
                                  // lik_only + neg_binomial_2_log: phi is an autodiff variable (the phi-only terms
                                  // stay); 2 = phi is the ONLY variable operand (y * theta drops under propto)
@@ -87,6 +88,12 @@ struct KernelParams {
   // so a CTA meets few groups: it accumulates their residual sums on chip and writes them to gpart[cta][0, Gcs);
   // the last CTA folds them in CTA order through gmeta[g] = {first CTA, last CTA, index of the first CTA's entry}
   // (in every later CTA the group is that CTA's first: entry 0).  cta_g0[c] = first group (0-based) of CTA c's range.
+  // function-level entry with per-row operands (b200glm_glm_lpmf_rows; narrow kernel, G == 0): intercept alpha_i and /
+  // or scale sigma_i per row, in the caller's row order; r_out then receives d logp / d alpha_i (the residual), s_out
+  // d logp / d sigma_i = (z_i^2 - 1) / sigma_i   (SM/opencl/prim/normal_id_glm_lpdf.hpp:68-84 and :117-150)
+  const double* alpha_rows;
+  const double* sigma_rows;
+  double* s_out;
   int n_classes;            // class-outcome models (ordered_logistic, categorical_logit): number of classes C
   double* cuts;             // ordered_logistic: 2 (C - 1) doubles of scratch for the epilogue
   int group_fused, Gcs;
@@ -273,7 +280,7 @@ __device__ void finish_t(const KernelParams& p, double* sh /* >= 64 doubles scra
         } else {
           if (!mc.propto) lp += NEG_LOG_SQRT_TWO_PI_D * mc.N_total;   // normal_id_glm_lpdf.hpp:202-204
           if (!mc.lik_only || !mc.propto || mc.sigma_is_var)
-            lp -= mc.N_total * u_s;                                   // :205-212, log sigma = u_s
+            lp -= mc.sigma_rows ? lik[P + 1] : mc.N_total * u_s;      // :205-212, log sigma = u_s | sum log sigma_i
           lp -= 0.5 * S;                                              // :213
         }
       }

@@ -218,6 +218,28 @@ class GLMModel:
                                             _dp(a), _dp(b), float(sigma), C.byref(lp), _dp(da), _dp(db), C.byref(ds)))
         return lp.value, da, db[:self.K], ds.value
 
+    def glm_lpmf_rows(self, beta, alpha=0.0, sigma=1.0, alpha_rows=None, sigma_rows=None, propto=True,
+                      operands_are_var=True, sigma_is_var=True, slot=0):
+        """Function-level entry with per-row operands: an N-vector intercept (alpha_rows) and / or, for normal_id, an
+        N-vector scale (sigma_rows).  Returns lp, d_alpha (scalar or N-vector), d_beta, d_sigma (scalar or N-vector)."""
+        b = np.ascontiguousarray(beta, dtype=np.float64)
+        if b.shape != (self.K,):
+            raise InvalidArgument("beta has the wrong size")
+        ar = None if alpha_rows is None else np.ascontiguousarray(alpha_rows, dtype=np.float64)
+        sr = None if sigma_rows is None else np.ascontiguousarray(sigma_rows, dtype=np.float64)
+        for v, what in ((ar, "Vector of intercepts"), (sr, "Scale vector")):
+            if v is not None and v.shape != (self.N,):
+                raise InvalidArgument(f"{what} has the wrong size")       # check_size_match(N, size(alpha | sigma))
+        lp, da, ds = C.c_double(), C.c_double(), C.c_double()
+        db = np.empty(max(self.K, 1))
+        dar = None if ar is None else np.empty(self.N)
+        dsr = None if sr is None else np.empty(self.N)
+        self._check(self.L.b200glm_glm_lpmf_rows(
+            self.h, slot, int(propto), int(operands_are_var), int(sigma_is_var), None if ar is None else _dp(ar),
+            float(alpha), _dp(b), None if sr is None else _dp(sr), float(sigma), C.byref(lp),
+            None if dar is None else _dp(dar), C.byref(da), _dp(db), None if dsr is None else _dp(dsr), C.byref(ds)))
+        return lp.value, (da.value if dar is None else dar), db[:self.K], (ds.value if dsr is None else dsr)
+
     def set_state(self, q, p, g, V, slot=0):
         q, p, g = (self._theta(a) for a in (q, p, g))
         self._check(self.L.b200glm_set_state(self.h, slot, _dp(q), _dp(p), _dp(g), float(V)))

@@ -274,6 +274,24 @@ class FuncGLM:
         return f.value, da, db[:self.K], ds.value
 
 
+def func_eval_rows(fg, alpha_rows, beta, sigma_rows=None, sigma=1.0, propto=True, scale=1.0):
+    """FuncGLM with the per-row overloads (b200::by_row(alpha), vector sigma), every operand a var:
+    returns f = scale * glm(...) + 0.5 * sum(beta^2) and its adjoints (d_alpha_rows, d_beta, d_sigma_rows | d_sigma)."""
+    L = fg.L
+    a = np.ascontiguousarray(alpha_rows, dtype=np.float64)
+    b = np.ascontiguousarray(beta, dtype=np.float64)
+    s = None if sigma_rows is None else np.ascontiguousarray(sigma_rows, dtype=np.float64)
+    f, ds, err = C.c_double(), C.c_double(), C.create_string_buffer(1024)
+    da, db = np.zeros_like(a), np.zeros(max(fg.K, 1))
+    dsr = np.zeros_like(a)
+    rc = L.b200stan_func_eval_rows(fg.h, int(propto), _dp(a), _dp(b), None if s is None else _dp(s),
+                                   C.c_double(float(sigma)), C.c_double(float(scale)), C.byref(f), _dp(da), _dp(db),
+                                   _dp(dsr), C.byref(ds), err, 1024)
+    if rc:
+        StanGLM._raise(rc, err)
+    return f.value, da, db[:fg.K], (dsr if s is not None else ds.value)
+
+
 def diagnostic(which, draws):
     """stan::analyze::{ess, rhat, mcse_mean, mcse_sd} (the reference's estimators, compiled into libb200stan.so)
     for ONE parameter; draws: (n_draws, n_chains)."""
