@@ -143,8 +143,14 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
   const std::vector<double>& means_x() const { return means_x_; }
 
   static size_t count_params(const b200glm_desc& d) {
+    if (d.family == B200GLM_ORDERED_LOGISTIC)       // parameters { vector[K] beta; ordered[C-1] c; }
+      return d.K + (d.n_classes > 0 ? d.n_classes - 1 : 0);
+    if (d.family == B200GLM_CATEGORICAL_LOGIT)      // parameters { vector[C] alpha; matrix[K, C] beta; }
+      return static_cast<size_t>(d.n_classes) * (1 + d.K);
     return (d.G > 0 ? 2 + d.G : 1) + d.K + (has_scale(d.family) ? 1 : 0);
   }
+  bool is_ordered() const { return desc_.family == B200GLM_ORDERED_LOGISTIC; }
+  bool is_categorical() const { return desc_.family == B200GLM_CATEGORICAL_LOGIT; }
   // families with a trailing positive scalar parameter: sigma (normal_id) or phi (neg_binomial_2_log)
   static bool has_scale(int family) { return family == B200GLM_NORMAL_ID || family == B200GLM_NEG_BINOMIAL_2_LOG; }
   const char* scale_name() const { return desc_.family == B200GLM_NEG_BINOMIAL_2_LOG ? "phi" : "sigma"; }
@@ -383,6 +389,21 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
   // appends, as stanc-generated models do: mcmc_writer::write_sample_names (services/util/mcmc_writer.hpp:66-77)
   // passes a vector that already holds the sample and sampler column names
   void flat_names(std::vector<std::string>& names) const {
+    if (is_ordered()) {
+      for (int k = 1; k <= desc_.K; ++k)
+        names.emplace_back("beta." + std::to_string(k));
+      for (int j = 1; j < desc_.n_classes; ++j)
+        names.emplace_back("c." + std::to_string(j));
+      return;
+    }
+    if (is_categorical()) {
+      for (int c = 1; c <= desc_.n_classes; ++c)
+        names.emplace_back("alpha." + std::to_string(c));
+      for (int c = 1; c <= desc_.n_classes; ++c)     // matrix[K, C] in column-major order, as stanc writes it
+        for (int k = 1; k <= desc_.K; ++k)
+          names.emplace_back("beta." + std::to_string(k) + "." + std::to_string(c));
+      return;
+    }
     if (desc_.G > 0) {
       names.emplace_back("mu_a");
       names.emplace_back("sigma_a");
@@ -397,6 +418,14 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
       names.emplace_back(scale_name());
   }
   void get_param_names(std::vector<std::string>& names, bool = true, bool = true) const override {
+    if (is_ordered()) {
+      names = {"beta", "c"};
+      return;
+    }
+    if (is_categorical()) {
+      names = {"alpha", "beta"};
+      return;
+    }
     if (desc_.G > 0)
       names = {"mu_a", "sigma_a", "a", "beta"};
     else
@@ -406,6 +435,16 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
   }
   void get_dims(std::vector<std::vector<size_t>>& dimss, bool = true, bool = true) const override {
     dimss.clear();
+    if (is_ordered()) {
+      dimss.push_back({static_cast<size_t>(desc_.K)});
+      dimss.push_back({static_cast<size_t>(desc_.n_classes > 0 ? desc_.n_classes - 1 : 0)});
+      return;
+    }
+    if (is_categorical()) {
+      dimss.push_back({static_cast<size_t>(desc_.n_classes)});
+      dimss.push_back({static_cast<size_t>(desc_.K), static_cast<size_t>(desc_.n_classes)});
+      return;
+    }
     if (desc_.G > 0) {
       dimss.push_back({});
       dimss.push_back({});
@@ -459,6 +498,13 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
     const size_t P = num_params_r();
     for (size_t i = 0; i < P; ++i)
       c[i] = u[i];
+    if (is_ordered()) {   // ordered_constrain.hpp:34-37
+      for (int k = 1; k < desc_.n_classes - 1; ++k)
+        c[desc_.K + k] = c[desc_.K + k - 1] + std::exp(u[desc_.K + k]);
+      return;
+    }
+    if (is_categorical())
+      return;
     if (desc_.G > 0)
       c[1] = std::exp(u[1]);
     if (has_scale(desc_.family))
@@ -469,6 +515,13 @@ class glm_model final : public stan::model::model_base_crtp<glm_model> {
     const size_t P = num_params_r();
     for (size_t i = 0; i < P; ++i)
       u[i] = c[i];
+    if (is_ordered()) {   // ordered_free
+      for (int k = 1; k < desc_.n_classes - 1; ++k)
+        u[desc_.K + k] = std::log(c[desc_.K + k] - c[desc_.K + k - 1]);
+      return;
+    }
+    if (is_categorical())
+      return;
     if (desc_.G > 0)
       u[1] = stan::math::lb_free(c[1], 0);
     if (has_scale(desc_.family))

@@ -47,14 +47,14 @@ class StanGLM:
     """b200::glm_model driven through the reference's C++ interfaces."""
 
     def __init__(self, family, X, y, group=None, G=0, device=0, n_slots=8, rank=0, world=1, N_total=0,
-                 data_on_device=False, N=None, K=None, ldx=None, **priors):
+                 data_on_device=False, N=None, K=None, ldx=None, n_classes=0, **priors):
         """Arguments as GLMModel.  rank/world/N_total: this process holds row shard `rank` of `world` (one
         process per GPU); call connect_peers_torch() before the first evaluation and use n_slots=1 and one
         host thread: every rank must issue the same sequence of evaluations, which the reference's
         deterministic host code does by construction when it is given the same seeds."""
         self.L = lib()
         d, keep = make_desc(family, X, y, group, G, device, n_slots, rank, world, N_total,
-                            data_on_device=data_on_device, N=N, K=K, ldx=ldx, **priors)
+                            data_on_device=data_on_device, N=N, K=K, ldx=ldx, n_classes=n_classes, **priors)
         self.rank, self.world = int(rank), int(world)
         err = C.create_string_buffer(1024)
         self.h = C.c_void_p(self.L.b200stan_create(C.byref(d), err, 1024))

@@ -378,3 +378,40 @@ def test_dump_ingest_matches_array_construction(tmp_path):
     _r_dump(str(bad), N=500, K=4, X=d["X"][:, :3], y=d["y"])            # X has the wrong shape
     with pytest.raises(InvalidArgument):
         stan_service.StanGLM.from_dump(str(bad), "poisson_log")
+
+
+@pytest.mark.parametrize("fam,K,C", [("ordered_logistic", 4, 4), ("categorical_logit", 3, 3)])
+def test_class_outcome_models_through_the_unmodified_service(fam, K, C):
+    """The two class-outcome GLMs driven by the reference's hmc_nuts_diag_e_adapt through b200::glm_model (names,
+    dims, ordered_constrain in write_array): model API == reference CPU model, same-seed first draws, posterior means
+    within Monte-Carlo standard error, constrained cut-points come out ordered."""
+    Ref = ref_oracle()
+    d = make_glm_data(fam, 3_000, K, n_classes=C)
+    m = stan_service.StanGLM(fam, d["X"], d["y"], n_classes=C)
+    ro = Ref(fam, d["X"], d["y"], n_classes=C)
+    assert m.P == ro.P
+    for th in theta_points(m.P, n_random=2, scale=0.3):
+        for propto in (True, False):
+            a, b = m.log_prob_grad(th, propto, True), ro.log_prob_grad(th, propto, True)
+            assert rel_err(a[0], b[0]) < TOL and rel_err_vec(a[1], b[1]) < TOL
+        g, gr = m.gradient(th), ro.gradient(th)
+        assert rel_err(g[0], gr[0]) < TOL and rel_err_vec(g[1], gr[1]) < TOL
+    kw = dict(num_chains=4, seed=11, num_warmup=300, num_samples=300, delta=0.8, num_threads=4)
+    dev = m.nuts(**kw)
+    c = m.counters()
+    m.close()
+    ref = ro.nuts(**kw)
+    a, b = dev["warmup_draws"][:, :4, :], ref["warmup_draws"][:, :4, :]
+    assert np.array_equal(a[:, :, 3:6], b[:, :, 3:6])
+    assert np.max(np.abs(a[:, :, 7:] - b[:, :, 7:])) < 1e-6
+    assert c["leapfrogs"] >= dev["draws"][:, :, 4].sum()          # the fused device leapfrog served them
+    zs = []
+    for k in range(dev["draws"].shape[2] - 7):
+        x, y = dev["draws"][:, :, 7 + k].T, ref["draws"][:, :, 7 + k].T
+        zs.append(abs(x.mean() - y.mean()) / np.hypot(Ref.mcse_mean(x), Ref.mcse_mean(y)))
+        assert Ref.rhat(x) < 1.05
+    assert max(zs) < 4.5, zs
+    assert dev["draws"][:, :, 5].sum() == 0
+    if fam == "ordered_logistic":                                  # write_array applies ordered_constrain
+        cuts = dev["draws"][:, :, 7 + K:]
+        assert np.all(np.diff(cuts, axis=2) > 0)
