@@ -284,7 +284,7 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
   if (tid == 0) tl_stamp(p, grid + 1, 0);        // acquire fence after the ticket
   // Sum of the grid's partial rows in a FIXED order (bitwise reproducible).  Warp w takes rows w, w + nw, ...; a
   // lane reads 8 consecutive bytes of a 256-byte stretch of the row, so every load instruction of a warp is one
-  // fully used, aligned run of sectors (rows are padded to 128 bytes, partial_stride), and four rows are in flight
+  // fully used, aligned run of sectors (rows are padded to 128 bytes, partial_stride), and eight rows are in flight
   // per thread.  The per-warp column sums meet in shared memory (the TMA ring is idle by now: `scratch`) and are
   // folded in warp order.  This loop is on the critical path of every launch: ~13 us as one dependent chain of 148
   // loads; 4.7 us with lanes striding over rows (two half-used 128-byte segments per instruction: one SM's L2 port,
@@ -309,6 +309,18 @@ __device__ __forceinline__ void cross_cta_reduce_and_finish(const KernelParams& 
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         const double* src = p.partials + c0 * 32 + lane;
         int r = warp;
+        for (; r + 7 * nw < grid; r += 8 * nw) {      // 8 rows x 4 chunks = 32 loads in flight per thread
+          double v[8][4];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              v[u][q] = (c0 + q) * 32 + lane < n_sums ? __ldcg(src + (size_t)(r + u * nw) * p.pstride + q * 32) : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] += v[u][q];
+        }
         for (; r + 3 * nw < grid; r += 4 * nw) {
           double v[4][4];
 #pragma unroll
