@@ -65,6 +65,25 @@ def config3(args):
     truth = np.concatenate([[d["truth"]["alpha"]], d["truth"]["beta"], [1.0]])
     post_mean = res["draws"][:, :, 7:].mean(axis=(0, 1))
     s["max_abs_post_mean_minus_truth"] = float(np.max(np.abs(post_mean - truth)))
+    # Known answer: with N >> K and the weak priors of the model the posterior of (alpha, beta) is the least-squares
+    # Gaussian N(b_ols, s^2 (A^T A)^-1), A = [1 X], to O(1/N).  Pooled posterior mean / sd of every coefficient against it,
+    # and per chain: how many chains have their own mean further than 5 pooled-MCSE-of-one-chain from the pooled mean.
+    A = np.column_stack([np.ones(N), d["X"]])
+    coef, *_ = np.linalg.lstsq(A, d["y"], rcond=None)
+    resid = d["y"] - A @ coef
+    s2 = float(resid @ resid) / (N - K - 1)
+    se = np.sqrt(s2 * np.diag(np.linalg.inv(A.T @ A)))
+    draws = res["draws"][:, :, 7:7 + K + 1]
+    pooled_mean, pooled_sd = draws.mean(axis=(0, 1)), draws.reshape(-1, K + 1).std(axis=0)
+    s["ols_check"] = {
+        "max_abs_z_of_posterior_mean_vs_ols": float(np.max(np.abs(pooled_mean - coef) / se)),
+        "posterior_sd_over_ols_se_min_max": [float(np.min(pooled_sd / se)), float(np.max(pooled_sd / se))],
+        "sigma_posterior_mean_vs_ols_s": [float(res["draws"][:, :, 7 + K + 1].mean()), float(np.sqrt(s2))],
+    }
+    chain_means = draws.mean(axis=1)                                   # (chains, K + 1)
+    n_draws = draws.shape[1]
+    z_chain = np.abs(chain_means - pooled_mean) / (pooled_sd / np.sqrt(max(n_draws / 4.0, 1.0)))   # ESS >= draws / 4
+    s["ols_check"]["chains_with_a_mean_beyond_5_mcse"] = int((z_chain.max(axis=1) > 5.0).sum())
     out = {"workload": f"normal_id_glm N={N} K={K}, NUTS diag_e {args.chains} batched chains {args.warmup}+{args.samples} "
                        "via b200::hmc_nuts_diag_e_adapt_batched (single-chain reference service per chain)",
            "host_threads": os.cpu_count(), "data_gen_s": t_gen, "b200": dict(s, counters=m.counters())}
