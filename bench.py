@@ -409,6 +409,13 @@ def run_b200(args):
         "parity": parity,
         "ess": ess,
     }
+    if ess is not None and world == 1 and not args.no_cpu_baseline:
+        # BASELINE configs[0] in full, both arms measured in this run: the reference's CPU-runnable case (N=10k, K=20,
+        # 4 chains x 1000+1000) through the same unmodified service on b200::glm_model and on the reference CPU model
+        try:
+            ess["config1_both_arms"] = ess_config1_record()
+        except Exception as e:                                   # the bench line must not depend on this extra
+            ess["config1_both_arms"] = {"error": str(e)[:200]}
     if ess and cpu_baseline and ess.get("b200"):
         # BASELINE.md section 5 step 3 at config 2: the CPU NUTS arm cannot run to an ESS inside a bench (1.8 s per
         # gradient per core); the same chains cost the same gradient evaluations on the CPU, so its ESS/s is the
@@ -578,6 +585,38 @@ def ess_record(args, torch, dist, dev, rank, world, local_rank):
                      "mean_treedepth": float(d[:, :, 3].mean()), "divergent": int(d[:, :, 5].sum()),
                      "stepsize": [float(v) for v in res["stepsize"]]},
             "service": "stan::services::sample::hmc_nuts_diag_e_adapt (unmodified) on b200::glm_model, chains sequential"}
+
+
+def ess_config1_record():
+    """bernoulli_logit N=10k K=20, NUTS diag_e 4 chains 1000+1000, same seeds on both arms: wall time, gradient
+    evaluations/s and min ESS/s of the GPU arm (libb200stan.so) and of the reference CPU arm (oracle/_ref, 4 threads),
+    and the largest posterior-mean z-score between them."""
+    from stan_b200 import make_glm_data, stan_service
+    from oracle.oracle import RefOracle
+    if not (stan_service.available() and RefOracle.available()):
+        return {"unavailable": "needs libb200stan.so and oracle/_ref"}
+    d = make_glm_data("bernoulli_logit", 10_000, 20)
+    kw = dict(num_chains=4, seed=4711, num_warmup=1000, num_samples=1000, delta=0.8, num_threads=4)
+    m = stan_service.StanGLM("bernoulli_logit", d["X"], d["y"], n_slots=8)
+    dev = m.nuts(**kw)
+    m.close()
+    ref = RefOracle("bernoulli_logit", d["X"], d["y"]).nuts(**kw)
+
+    def arm(r):
+        dr = r["draws"]
+        ess = [stan_service.diagnostic("ess", dr[:, :, 7 + k].T) for k in range(dr.shape[2] - 7)]
+        n_grad = float(dr[:, :, 4].sum() + r["warm_leapfrogs"].sum() + dr.shape[0] * 2000)
+        return {"wall_s": r["wall"], "grad_evals_per_s": n_grad / r["wall"], "ess_min": float(np.min(ess)),
+                "ess_min_per_s": float(np.min(ess)) / r["wall"], "divergent": int(dr[:, :, 5].sum())}
+    zs = []
+    for k in range(dev["draws"].shape[2] - 7):
+        a, b = dev["draws"][:, :, 7 + k].T, ref["draws"][:, :, 7 + k].T
+        zs.append(abs(a.mean() - b.mean()) / np.hypot(stan_service.diagnostic("mcse_mean", a),
+                                                       stan_service.diagnostic("mcse_mean", b)))
+    out = {"workload": "bernoulli_logit_glm N=10000 K=20, NUTS diag_e 4 chains 1000+1000 (BASELINE configs[0])",
+           "b200": arm(dev), "reference_cpu": dict(arm(ref), threads=4), "posterior_mean_max_z": float(max(zs))}
+    out["ess_per_s_ratio"] = out["b200"]["ess_min_per_s"] / out["reference_cpu"]["ess_min_per_s"]
+    return out
 
 
 def run_b200_batched(args):

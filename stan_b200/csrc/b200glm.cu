@@ -1367,8 +1367,19 @@ int b200glm_batch_reserve(b200glm_handle* h, int32_t max_chains) {
   }
   if (h->batch) {
     if (max_chains <= h->batch->max_chains) return B200GLM_OK;  // idempotent for a smaller or equal request
-    h->set_error("batch workspace already reserved with fewer chain slots");
-    return B200GLM_INVALID;
+    // a larger request: release the workspace and reserve again (chain state is not preserved; callers re-upload it)
+    Batch* b = h->batch;
+    cudaSetDevice(h->d.device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (double* q : {b->Q, b->Pm, b->Gd, b->V, b->IM, b->theta_c, b->p_half, b->partials, b->reduced, b->result, b->state_out,
+                      b->theta_in, b->eps_d})
+      cudaFree(q);
+    cudaFree(b->chains_d);
+    if (b->h_pin) cudaFreeHost(b->h_pin);
+    if (b->h_pin_i) cudaFreeHost(b->h_pin_i);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+    h->batch = nullptr;
   }
   if (h->wide || h->d.G > 0 || h->d.world > 1 || h->d.K > BATCH_MAX_K || h->d.family > B200GLM_NORMAL_ID) {
     h->set_error("batched chains need K <= 208, a scalar intercept (G == 0), an unsharded handle and one of the "

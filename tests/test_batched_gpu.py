@@ -169,3 +169,24 @@ def test_row_split_small_batches(fam, N, K):
         assert rel_err_vec(qd[i], ref[i][0]) < 1e-9 and rel_err_vec(gd[i], ref[i][2]) < 1e-9
         assert rel_err(Vd[i], ref[i][3]) < 1e-9
     m.close()
+
+
+def test_batch_workspace_grows_on_a_larger_reservation():
+    """A second b200glm_batch_reserve with MORE chains re-reserves the workspace (round 1 returned INVALID, which the
+    batched driver read as "shape not supported" and silently fell back to lane-by-lane launches)."""
+    from oracle.oracle import PortOracle
+    d = make_glm_data("poisson_log", 3_000, 9)
+    po = PortOracle("poisson_log", d["X"], d["y"])
+    m = GLMModel("poisson_log", d["X"], d["y"])
+    th = 0.1 * np.random.default_rng(4).standard_normal((70, m.P))
+    m.batch_reserve(8)
+    lp8, g8, _ = m.log_prob_grad_batched(th[:8])
+    m.batch_reserve(70)                                    # grows
+    lp, g, st = m.log_prob_grad_batched(th)
+    assert not st.any() and np.array_equal(lp[:8], lp8) and np.array_equal(g[:8], g8)
+    for c in (0, 9, 69):
+        lp_r, g_r = po.log_prob_grad(th[c])
+        assert rel_err(lp[c], lp_r) < TOL and rel_err_vec(g[c], g_r) < TOL
+    m.batch_reserve(16)                                    # smaller: keeps the larger workspace
+    assert m.log_prob_grad_batched(th)[2].sum() == 0
+    m.close()

@@ -427,3 +427,30 @@ def test_streamed_construction_equals_one_shot(fam, N, K, flags, chunk):
         m.finalize()                                               # rows missing
     m.close()
     one.close()
+
+
+def test_launch_timeline_and_peak_measurements():
+    """Measurement entry points of the C ABI: b200glm_timeline_* (per-phase %globaltimer stamps of a gradient launch,
+    monotone along the launch, result unchanged with the stamps on) and b200glm_measure_peaks (read-only-stream HBM
+    bandwidth and fp64 DMMA peak in the caller's process: plausible for a B200)."""
+    from stan_b200 import _capi
+    d = make_glm_data("bernoulli_logit", 200_000, 40)
+    m = GLMModel("bernoulli_logit", d["X"], d["y"])
+    th = theta_points(m.P, n_random=1, scale=0.1)[1]
+    want = m.log_prob_grad(th)
+    m.timeline_enable(True)
+    got = m.log_prob_grad(th)
+    assert got[0] == want[0] and np.array_equal(got[1], want[1])
+    T = m.timeline_read().astype(np.int64)
+    grid = T.shape[0] - 2
+    cta, tail, fine = T[:grid, :6], T[grid], T[grid + 1]
+    assert np.all(np.diff(cta, axis=1) >= 0) and np.all(cta[:, 0] > 0)       # entry <= ... <= ticket, every CTA
+    assert 0 <= tail[7] < grid and tail[0] >= cta[:, 5].max() - 64           # the last CTA's ticket comes last (32 ns ticks)
+    assert tail[0] <= fine[0] <= fine[1] <= fine[2] <= tail[1] <= tail[2] <= fine[3] <= fine[4] <= tail[3]
+    assert (tail[3] - cta[:, 0].min()) < 5_000_000                           # a 64 MB launch ends within 5 ms
+    m.timeline_enable(False)
+    with pytest.raises(stan_b200.InvalidArgument):
+        m.timeline_read()
+    m.close()
+    read_gbs, dmma = _capi.measure_peaks(0, read=True, dmma=True)
+    assert 4000 < read_gbs < 9000 and 25 < dmma < 45
