@@ -57,6 +57,48 @@ def nuts_through_the_reference_service(rank, world, local, dev):
     return failures
 
 
+def class_outcome_models_sharded(rank, world, local, dev):
+    """ordered_logistic / categorical_logit with the rows sharded over the ranks (exchange inside glm_class_kernel's
+    launch): == the unsharded oracle, replicated results bitwise identical on every rank, leapfrog included."""
+    failures = []
+    if os.environ.get("MGPU_TRANSPORT", "peer") != "peer":
+        return failures                                      # the class kernels exchange through the mailboxes only
+    from oracle.oracle import PortOracle
+    for fam, N, K, Cn in [("ordered_logistic", 50_001, 12, 5), ("categorical_logit", 40_000, 9, 4)]:
+        d = make_glm_data(fam, N, K, n_classes=Cn)
+        r0, r1 = shard_rows(N, rank, world)
+        m = GLMModel(fam, d["X"][r0:r1], d["y"][r0:r1], device=local, rank=rank, world=world, N_total=N, n_classes=Cn)
+        m.connect_peers_torch(dist, dev)
+        rng = np.random.default_rng(6)
+        th, p0 = 0.2 * rng.standard_normal(m.P), rng.standard_normal(m.P)
+        n0 = m.launch_count()
+        lp, g = m.log_prob_grad(th)
+        if m.launch_count() - n0 != 1:
+            failures.append(f"{fam}: a sharded gradient took {m.launch_count() - n0} launches")
+        m.set_state(th, p0, -g, -lp)
+        for _ in range(3):
+            q1, p1, g1, V1 = m.leapfrog(1e-3)
+        buf = torch.tensor(np.concatenate([[lp, V1], g, q1, p1]), device=dev)
+        ref = buf.clone()
+        dist.broadcast(ref, 0)
+        if not torch.equal(buf, ref):
+            failures.append(f"{fam}: ranks disagree")
+        if rank == 0:
+            po = PortOracle(fam, d["X"], d["y"], n_classes=Cn)
+            lp_r, g_r = po.log_prob_grad(th)
+            sc = np.maximum(np.abs(g_r), np.abs(g_r).max())
+            e = max(abs(lp - lp_r) / abs(lp_r), float(np.max(np.abs(g - g_r) / sc)))
+            q, p, gg, V = th, p0, -g_r, -lp_r
+            for _ in range(3):
+                q, p, gg, V = po.leapfrog(1e-3, np.ones(m.P), q, p, gg, V)
+            e = max(e, float(np.max(np.abs(q1 - q))), abs(V1 - V) / abs(V))
+            if not e < 1e-10:
+                failures.append(f"{fam} sharded: err {e}")
+            print(f"{fam} N={N} K={K} C={Cn} world={world}: max err {e:.2e}", flush=True)
+        m.close()
+    return failures
+
+
 def bad_y_is_reported_by_every_rank(rank, world, local, dev):
     """An out-of-range y held by ONE shard (the reference checks y on every call, poisson_log_glm_lpmf.hpp:84) must
     make every rank return the domain error, not only the rank that holds it -- otherwise the replicated host code
@@ -145,6 +187,7 @@ def main():
                 failures.append(f"{fam}: err {e}")
             print(f"{fam} N={N} K={K} G={G} world={world}: max err {e:.2e}", flush=True)
         m.close()
+    failures += class_outcome_models_sharded(rank, world, local, dev)
     failures += bad_y_is_reported_by_every_rank(rank, world, local, dev)
     failures += nuts_through_the_reference_service(rank, world, local, dev)
     n_fail = torch.tensor([len(failures)], device=dev)
