@@ -183,7 +183,9 @@ def test_batch_workspace_grows_on_a_larger_reservation():
     lp8, g8, _ = m.log_prob_grad_batched(th[:8])
     m.batch_reserve(70)                                    # grows
     lp, g, st = m.log_prob_grad_batched(th)
-    assert not st.any() and np.array_equal(lp[:8], lp8) and np.array_equal(g[:8], g8)
+    assert not st.any()
+    for c in range(8):      # 8 lanes ran the row-split variant, 70 the normal mode: equal to rounding
+        assert rel_err(lp[c], lp8[c]) < 1e-12 and rel_err_vec(g[c], g8[c]) < 1e-12
     for c in (0, 9, 69):
         lp_r, g_r = po.log_prob_grad(th[c])
         assert rel_err(lp[c], lp_r) < TOL and rel_err_vec(g[c], g_r) < TOL
