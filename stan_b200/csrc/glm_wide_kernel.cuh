@@ -12,7 +12,7 @@
 //   issued in bursts while P2 freed slots and HBM idled one latency per panel (ncu: 57 % DRAM, 71 % of
 //   the copy roof); with the ring holding >= 2 panels the stream is continuous (89 %).
 //
-// CTA (persistent, one per SM) = 8 consumer warps + 1 TMA producer warp + 2 link warps (alternate row panels).
+// CTA (persistent, one per SM) = 8 consumer warps + 1 TMA producer warp + 1 link warp.
 //   The shared-memory ring has T >= 2J sub-panel slots: the panel between its eta pass and its X^T r
 //   pass stays resident, the rest holds the following panel(s).
 //   consumer warp w owns sub-panels j = w, w+8, ... of every row panel (so it owns those columns'
@@ -24,10 +24,11 @@
 //   Software pipeline: a consumer publishes eta(n+1) BEFORE it waits for r(n), so the link warp's
 //   fp64 exp/log1p dependency chain for panel n+1 overlaps P2(n); eta / r buffers and the two named
 //   barriers are double-buffered by panel parity.
-//   Round 2: three variants measured alone changed nothing (two link warps with look-ahead 1, 4-row panels, the panel
-//   kept in registers with the ring slot released after P1: profiles/r2_wide_variants.txt); the combination that the
-//   stall counters pointed to -- two link warps AND a look-ahead of two panels (three eta / r buffers) -- is the
-//   structure below.
+//   Round 2 measured four variants of the consumer / link pipeline -- two link warps (even / odd panels), 4-row
+//   panels, the panel kept in registers between the passes with the ring slot released after P1, two link warps with a
+//   look-ahead of two panels -- and K = 1000 stayed within 1 % of 1.347 ms in all of them
+//   (profiles/r2_wide_variants.txt): the limiter was the single-lane TMA issue loop (see the producer below), not
+//   the pipeline; the consumer / link structure is round 1's.
 //   Lane mapping (both passes): lane = (rq, cq) handles column cq + CPS*t and four rows
 //   {2rq, 2rq+1, 2(rq+LPC), 2(rq+LPC)+1} with two LDS.128; half of the columns swap the order of the
 //   two loads, which makes every quarter-warp cover all 32 banks (conflict free without a swizzle).
@@ -38,13 +39,11 @@
 namespace b200glm {
 
 constexpr int WIDE_CONSUMER_WARPS = 8;
-constexpr int WIDE_LINK_WARPS = 2;   // link warp lw takes the row panels n = lw, lw + 2, ...
-constexpr int WIDE_NB = 3;           // eta / r buffers and named-barrier pairs, rotated by panel number (look-ahead 2)
-constexpr int WIDE_THREADS = (WIDE_CONSUMER_WARPS + 1 + WIDE_LINK_WARPS) * 32;
+constexpr int WIDE_THREADS = (WIDE_CONSUMER_WARPS + 2) * 32;
 constexpr int WIDE_MAX_SLOTS = 96;
 // named barriers: ETA / R, double-buffered by panel parity
-enum { WIDE_BAR_ETA = 1, WIDE_BAR_R = 1 + WIDE_NB, WIDE_BAR_LINK = 1 + 2 * WIDE_NB };
-constexpr int WIDE_BAR_COUNT = (WIDE_CONSUMER_WARPS + 1) * 32;  // consumers + the link warp of that panel
+enum { WIDE_BAR_ETA = 1, WIDE_BAR_R = 3 };
+constexpr int WIDE_BAR_COUNT = (WIDE_CONSUMER_WARPS + 1) * 32;  // consumers + link warp
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -61,7 +60,7 @@ __host__ __device__ inline int wide_cps(int WR) { return 32 / (WR / 4); }
 
 // doubles of dynamic shared memory besides the ring slots and their barriers
 __host__ __device__ inline size_t wide_fixed_doubles(int WR, int J, int KC, int G, int stage_a, int P_state = 0) {
-  return (size_t)J * KC + WIDE_NB * WIDE_CONSUMER_WARPS * WR + WIDE_NB * WR + (WR & 1) + (stage_a ? ((G + 1) & ~1) : 0)
+  return (size_t)J * KC + 2 * WIDE_CONSUMER_WARPS * WR + 2 * WR + (stage_a ? ((G + 1) & ~1) : 0)
          + (P_state ? state_smem_doubles(P_state) : 0);
 }
 
@@ -75,16 +74,15 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
 
   double* ring = reinterpret_cast<double*>(smem_raw);            // T * SLOT
   double* sbeta = ring + (size_t)T * SLOT;                       // J * KC (zero beyond K)
-  double* eta_part = sbeta + J * KC;                             // WIDE_NB buffers x 8 warps x WR
-  double* r_sh = eta_part + WIDE_NB * WIDE_CONSUMER_WARPS * WR;  // WIDE_NB buffers x WR
-  double* sa = r_sh + WIDE_NB * WR + (WR & 1);                   // G (optional)
+  double* eta_part = sbeta + J * KC;                             // 2 parities x 8 warps x WR
+  double* r_sh = eta_part + 2 * WIDE_CONSUMER_WARPS * WR;        // 2 parities x WR
+  double* sa = r_sh + 2 * WR;                                    // G (optional)
   double* st_base = sa + (p.stage_a_in_smem ? ((G + 1) & ~1) : 0);   // chain state (optional)
   const StateSmem st = carve_state_smem(st_base, P, p.state_in_smem);
   double* after_a = st_base + (p.state_in_smem ? state_smem_doubles(P) : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(after_a);     // T
   uint64_t* empty_bar = full_bar + T;                            // T
   __shared__ double sh_scratch[64];
-  __shared__ double sh_link[4];
   __shared__ int sh_is_last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -147,10 +145,12 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
         if (steps[i] > 0) {
           int sl = slot[i];
           uint32_t pr = par[i];
-          sl += ahead * J;            // ahead <= 2 and T >= (ahead + 1) J: at most one wrap
-          if (sl >= T) {
-            sl -= T;
-            pr ^= 1u;
+          if (ahead) {
+            sl += J;
+            if (sl >= T) {
+              sl -= T;
+              pr ^= 1u;
+            }
           }
           mbar_wait(&full_bar[sl], pr);
           const double* tile = ring + (size_t)sl * SLOT + cq * WR;
@@ -187,15 +187,12 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
       named_bar_arrive(WIDE_BAR_ETA + buf, WIDE_BAR_COUNT);
     };
 
-    // Look-ahead LA: eta of panel n + LA goes to the link warps BEFORE this warp waits for r of panel n, so the link
-    // step (one dependent fp64 chain per panel, ~1 us) of panels n + 1 .. n + LA overlaps P2(n).  LA = 2 with the ring
-    // holding three panels (T >= 3 J) and two link warps working on alternate panels; LA = 1 when only two fit.
-    const int LA = T >= 3 * J ? 2 : 1;
-    for (int a = 0; a < LA; ++a)
-      if (a < n_my) pass1_publish(a, a % WIDE_NB);
-    int buf = 0;
+    if (n_my > 0) pass1_publish(0, 0);
     for (long long n = 0; n < n_my; ++n) {
-      if (n + LA < n_my) pass1_publish(LA, (buf + LA) % WIDE_NB);
+      const int buf = (int)(n & 1);
+      // eta of panel n+1 goes to the link warp BEFORE this warp waits for r of panel n: the link
+      // function of n+1 then overlaps P2(n) (the ring holds at least two panels: T >= 2J)
+      if (n + 1 < n_my) pass1_publish(1, buf ^ 1);
 
       // ---- P2: X^T r from the same resident sub-panels ----
       named_bar_sync(WIDE_BAR_R + buf, WIDE_BAR_COUNT);
@@ -227,7 +224,6 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
           par[i] ^= 1u;
         }
       }
-      if (++buf == WIDE_NB) buf = 0;
     }
 
     // ---- this warp's columns of the CTA partial (sum over the row-lanes of each column) ----
@@ -244,34 +240,26 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
     }
   } else if (warp == WIDE_CONSUMER_WARPS) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // Lane j of the producer warp streams sub-panel j of EVERY row panel (J <= 16 lanes busy): the wait on the slot's
+    // empty-barrier, the expect_tx and the bulk copy of a panel's J sub-panels are then ONE pass of warp instructions
+    // instead of J iterations of a single-lane loop.  That loop was what held this kernel at ~6.0 TB/s in rounds 1-2
+    // whatever the consumers did (five pipeline variants within 1 % of 1.347 ms at K = 1000,
+    // profiles/r2_wide_variants.txt): ~390 cycles per 8 KB copy = 21 B/cycle/SM = 6.1 TB/s over 148 SMs.
+    if (lane < J) {
       const uint64_t pol = policy_evict_first();
-      int sl = 0;
-      uint32_t round = 0;
-      for (long long n = 0; n < n_my; ++n) {
+      const uint32_t bytes = (uint32_t)min(KC, Cpad - lane * KC) * WR * 8u;
+      long long q = lane;                     // index of this lane's next sub-panel in the CTA's stream: n * J + lane
+      for (long long n = 0; n < n_my; ++n, q += J) {
+        const int sl = (int)(q % T);
+        const long long round = q / T;
         const double* src = p.panels + (size_t)(blockIdx.x + n * grid) * Cpad * WR;
-        for (int j = 0; j < J; ++j) {
-          if (round > 0) mbar_wait(&empty_bar[sl], (round - 1) & 1);
-          const uint32_t bytes = (uint32_t)min(KC, Cpad - j * KC) * WR * 8u;
-          mbar_arrive_expect_tx(&full_bar[sl], bytes);
-          tma_load_1d(ring + (size_t)sl * SLOT, src + (size_t)j * KC * WR, bytes, &full_bar[sl], pol);
-          if (++sl == T) {
-            sl = 0;
-            ++round;
-          }
-        }
+        if (round > 0) mbar_wait(&empty_bar[sl], (uint32_t)((round - 1) & 1));
+        mbar_arrive_expect_tx(&full_bar[sl], bytes);
+        tma_load_1d(ring + (size_t)sl * SLOT, src + (size_t)lane * KC * WR, bytes, &full_bar[sl], pol);
       }
     }
   } else {
-    // =============================== link warps ===============================
-    // Link warp lw takes the row panels n = lw, lw + 2, ...; the eta / r buffers and both named barriers rotate over
-    // WIDE_NB = 3 panels, so the two warps never share one.  Together with the consumers' look-ahead of two panels the
-    // link step of a panel (sum of the 8 partial etas, exp, log1p, a division: one dependent fp64 chain on WR <= 16
-    // lanes) has two panel times to complete before its r is needed.  Round 1 (one link warp, look-ahead 1): consumers
-    // stalled 2.4-2.7 cycles per issue at the r barrier (ncu) and the kernel ran at ~5.9 TB/s; two link warps alone, or
-    // a larger ring alone (register-resident panels), changed nothing -- the consumers still waited for r(n) with only
-    // eta(n+1) published.
-    const int lw = warp - (WIDE_CONSUMER_WARPS + 1);
+    // =============================== link warp ===============================
     const int r = lane & (WR - 1);
     const int jy = K / KC, coly = K - jy * KC;            // y lives in column K
     const int jt = (K + 1) / KC, colt = K + 1 - jt * KC;  // binomial population sizes in column K+1
@@ -279,18 +267,6 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
     const int jg = Kg / KC, colg = Kg - jg * KC;          // group id after the y (and trials) columns (G > 0)
     int slot_y = jy, slot_g = jg, slot_t = jt;
     uint32_t par_y = 0, par_g = 0, par_t = 0;
-    auto advance = [&](int& sl, uint32_t& pr, int panels) {   // ring position `panels` row panels further on
-      sl += panels * J;
-      while (sl >= T) {
-        sl -= T;
-        pr ^= 1u;
-      }
-    };
-    if (lw == 1) {
-      advance(slot_y, par_y, 1);
-      advance(slot_g, par_g, 1);
-      advance(slot_t, par_t, 1);
-    }
     const double alpha = G > 0 ? 0.0 : theta_at(0);
     LinkConst lc;
     lc.inv_sigma = 1.0;
@@ -306,8 +282,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
       lc.lg_phi = lgamma(lc.phi);
     }
     double lp_acc = 0.0, r_acc = 0.0, x_acc = 0.0;
-    for (long long n = lw; n < n_my; n += WIDE_LINK_WARPS) {
-      const int buf = (int)(n % WIDE_NB);
+    for (long long n = 0; n < n_my; ++n) {
+      const int buf = (int)(n & 1);
       const long long pi = blockIdx.x + n * grid;
       mbar_wait(&full_bar[slot_y], par_y);
       const double y = ring[(size_t)slot_y * SLOT + coly * WR + r];
@@ -344,25 +320,29 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
       }
       __threadfence_block();
       named_bar_arrive(WIDE_BAR_R + buf, WIDE_BAR_COUNT);
-      advance(slot_y, par_y, WIDE_LINK_WARPS);
-      advance(slot_g, par_g, WIDE_LINK_WARPS);
-      advance(slot_t, par_t, WIDE_LINK_WARPS);
+      slot_y += J;
+      if (slot_y >= T) {
+        slot_y -= T;
+        par_y ^= 1u;
+      }
+      slot_g += J;
+      if (slot_g >= T) {
+        slot_g -= T;
+        par_g ^= 1u;
+      }
+      slot_t += J;
+      if (slot_t >= T) {
+        slot_t -= T;
+        par_t ^= 1u;
+      }
     }
     lp_acc = warp_sum(lp_acc);
     r_acc = warp_sum(r_acc);
     x_acc = warp_sum(x_acc);
-    // the odd-panel warp hands its sums to the even-panel warp (fixed order: even + odd)
-    if (lw == 1 && lane == 0) {
-      sh_link[0] = lp_acc;
-      sh_link[1] = r_acc;
-      sh_link[2] = x_acc;
-    }
-    __threadfence_block();
-    named_bar_sync(WIDE_BAR_LINK, WIDE_LINK_WARPS * 32);
-    if (lw == 0 && lane == 0) {
-      my_part[K] = lp_acc + sh_link[0];
-      my_part[K + 1] = r_acc + sh_link[1];
-      my_part[K + 2] = x_acc + sh_link[2];   // neg_binomial_2_log: sum of the per-row d/dphi terms
+    if (lane == 0) {
+      my_part[K] = lp_acc;
+      my_part[K + 1] = r_acc;
+      my_part[K + 2] = x_acc;   // neg_binomial_2_log: sum of the per-row d/dphi terms
     }
   }
 
