@@ -294,6 +294,26 @@ class RefOracle:
         return dict(draws=draws[:, num_warmup:, :], warmup_draws=draws[:, :num_warmup, :], stepsize=step,
                     inv_metric=inv_metric, warm_leapfrogs=warm_lf, wall=wall.value)
 
+    def nuts_device_host(self, num_chains=4, seed=1, init_chain_id=1, init_radius=2.0, num_warmup=1000, num_samples=1000,
+                         stepsize=1.0, max_depth=10, delta=0.8):
+        """The PRODUCT's device-NUTS driver and per-chain state machine (stan_b200/cpp/b200/device_nuts.hpp,
+        stan_b200/csrc/nuts_tree.cuh) built for the host over the reference's model and integrator
+        (oracle/ref/nuts_host_backend.hpp): the CPU check of SURVEY 8f row 2.  Same outputs as nuts()."""
+        W = 7 + self.P
+        draws = np.empty((num_chains, num_warmup + num_samples, W))
+        step = np.empty(num_chains)
+        inv_metric = np.empty((num_chains, self.P))
+        stats = (C.c_long * 4)()
+        err = C.create_string_buffer(2048)
+        rc = self.L.ref_glm_nuts_device_host(self.h, num_chains, C.c_uint(seed), C.c_uint(init_chain_id),
+                                             C.c_double(init_radius), num_warmup, num_samples, C.c_double(stepsize),
+                                             max_depth, C.c_double(delta), _dp(draws), _dp(step), _dp(inv_metric), stats,
+                                             err, 2048)
+        if rc:
+            raise OracleError(rc, err.value.decode())
+        return dict(draws=draws[:, num_warmup:, :], warmup_draws=draws[:, :num_warmup, :], stepsize=step,
+                    inv_metric=inv_metric, rounds=stats[0], lanes=stats[1], uniforms=stats[2], normal_vectors=stats[3])
+
     # ---- stan::analyze ----
     @classmethod
     def _chains(cls, draws):

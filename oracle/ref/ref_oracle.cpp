@@ -7,8 +7,11 @@
 //   ref_glm_gradient      -> stan::model::gradient                        (src/stan/model/gradient.hpp:22-35)
 //   ref_glm_leapfrog      -> expl_leapfrog<diag_e_metric>::evolve         (mcmc/hmc/integrators/base_leapfrog.hpp:17-22)
 //   ref_glm_nuts          -> services::sample::hmc_nuts_diag_e_adapt      (services/sample/hmc_nuts_diag_e_adapt.hpp:58,331)
+//   ref_glm_nuts_device_host -> the PRODUCT's device-NUTS driver + state machine (b200/device_nuts.hpp, nuts_tree.cuh) built for
+//                            the host over the reference's model and integrator (nuts_host_backend.hpp): CPU check of SURVEY 8f row 2
 //   ref_ess / ref_mcse_*  -> stan::analyze::{ess, mcse_mean, mcse_sd, rhat, split_rank_normalized_ess}
 #include "ref_glm_model.hpp"
+#include "nuts_host_backend.hpp"
 
 #include <stan/analyze/mcmc/ess.hpp>
 #include <stan/analyze/mcmc/mcse.hpp>
@@ -263,6 +266,54 @@ int ref_glm_nuts(void* h, int num_chains, unsigned seed, unsigned init_chain_id,
       if (inv_metric_out)
         std::memcpy(inv_metric_out + static_cast<size_t>(c) * P,
                     metric_w[c].inv_metric.data(), P * sizeof(double));
+    }
+  });
+  return g ? g : rc;
+}
+
+// The product's device-side NUTS (driver + per-chain state machine) on the host backend; same outputs as ref_glm_nuts.
+// stats: 4 longs {rounds, lanes, uniform variates generated, normal vectors generated}.
+int ref_glm_nuts_device_host(void* h, int num_chains, unsigned seed, unsigned init_chain_id, double init_radius,
+                             int num_warmup, int num_samples, double stepsize, int max_depth, double delta,
+                             double* draws, double* stepsize_out, double* inv_metric_out, long* stats, char* err,
+                             int errlen) {
+  auto& m = *static_cast<ref_glm_model*>(h);
+  const int P = static_cast<int>(m.num_params_r());
+  int rc = 0;
+  int g = guarded(err, errlen, [&] {
+    std::vector<std::shared_ptr<stan::io::var_context>> inits, metrics;
+    for (int c = 0; c < num_chains; ++c) {
+      inits.emplace_back(std::make_shared<stan::io::empty_var_context>());
+      metrics.emplace_back(std::make_shared<stan::io::array_var_context>(
+          stan::services::util::create_unit_e_diag_inv_metric(P)));
+    }
+    stan::callbacks::interrupt interrupt;
+    err_logger logger;
+    std::vector<stan::callbacks::writer> init_w(num_chains), diag_w(num_chains);
+    std::vector<mem_writer> sample_w(num_chains);
+    std::vector<mem_metric_writer> metric_w(num_chains);
+    oracle_ref::nuts_host_backend<ref_glm_model> backend(m);
+    b200::nuts_backend be = backend.table();
+    rc = b200::hmc_nuts_diag_e_adapt_device(m, be, num_chains, inits, metrics, seed, init_chain_id, init_radius,
+                                            num_warmup, num_samples, 1, true, 0, stepsize, 0.0, max_depth, delta, 0.05,
+                                            0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w, diag_w,
+                                            metric_w, stats);
+    if (rc != 0)
+      throw std::runtime_error("hmc_nuts_diag_e_adapt_device rc=" + std::to_string(rc) + ": " + logger.errors);
+    const int W = 7 + P, T = num_warmup + num_samples;
+    for (int c = 0; c < num_chains; ++c) {
+      auto& rows = sample_w[c].rows;
+      if (static_cast<int>(rows.size()) != T)
+        throw std::runtime_error("unexpected number of draws");
+      for (int i = 0; i < T; ++i) {
+        if (static_cast<int>(rows[i].size()) != W)
+          throw std::runtime_error("unexpected draw width");
+        std::memcpy(draws + (static_cast<size_t>(c) * T + i) * W, rows[i].data(), W * sizeof(double));
+      }
+      if (stepsize_out)
+        stepsize_out[c] = metric_w[c].stepsize;
+      if (inv_metric_out)
+        std::memcpy(inv_metric_out + static_cast<size_t>(c) * P, metric_w[c].inv_metric.data(), P * sizeof(double));
     }
   });
   return g ? g : rc;

@@ -137,6 +137,7 @@ struct b200glm_handle {
   long long rows_appended = 0;
   double bad_count = 0.0;
   int pdl_prefetch = 2;     // B200GLM_PDL_PREFETCH=<stages> (A/B runs); see the TMA producer in glm_kernels.cuh
+  int wide_producer = 1;    // B200GLM_WIDE_PRODUCER=single|lanes (A/B runs); see the TMA producer in glm_wide_kernel.cuh
   bool tl_repeat = false;   // B200GLM_TL_REPEAT=1 (timeline runs only): the last CTA sums the partial rows twice
   bool inline_theta = true; // B200GLM_NO_INLINE_THETA=1: always upload theta with a host-to-device copy (A/B runs)
   bool host_mirror = true;  // B200GLM_NO_HOST_MIRROR=1: fetch results with a device-to-host copy + stream sync (A/B runs)
@@ -335,6 +336,7 @@ void fill_params(b200glm_handle* h, Slot* s, KernelParams& p, int mode, int prop
   p.tl = s->tl;
   p.pdl_prefetch = h->pdl_prefetch;
   p.tl_repeat = (s->tl && h->tl_repeat) ? 1 : 0;
+  p.wide_producer = h->wide_producer;
   ModelConst& mc = p.mc;
   mc.family = h->d.family;
   mc.K = h->d.K;
@@ -663,6 +665,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   if (const char* e = std::getenv("B200GLM_NO_PDL")) h->pdl = !(e[0] == '1');
   if (const char* e = std::getenv("B200GLM_PDL_PREFETCH")) h->pdl_prefetch = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("B200GLM_TL_REPEAT")) h->tl_repeat = (e[0] == '1');
+  if (const char* e = std::getenv("B200GLM_WIDE_PRODUCER")) h->wide_producer = (e[0] == 's') ? 0 : 1;
   if (const char* e = std::getenv("B200GLM_NO_INLINE_THETA")) h->inline_theta = !(e[0] == '1');
   if (const char* e = std::getenv("B200GLM_NO_HOST_MIRROR")) h->host_mirror = !(e[0] == '1');
   h->P = (d.G > 0 ? 2 + d.G : 1) + d.K + (fam_has_scale(d.family) ? 1 : 0);

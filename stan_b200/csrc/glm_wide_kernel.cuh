@@ -245,17 +245,42 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
     // instead of J iterations of a single-lane loop.  That loop was what held this kernel at ~6.0 TB/s in rounds 1-2
     // whatever the consumers did (five pipeline variants within 1 % of 1.347 ms at K = 1000,
     // profiles/r2_wide_variants.txt): ~390 cycles per 8 KB copy = 21 B/cycle/SM = 6.1 TB/s over 148 SMs.
-    if (lane < J) {
+    if (p.wide_producer == 0) {
+      // round 1's producer: one lane walks the ring slot by slot (B200GLM_WIDE_PRODUCER=single, and the default for the
+      // panel heights where the lane-parallel form measured slower)
+      if (lane == 0) {
+        const uint64_t pol = policy_evict_first();
+        int sl = 0;
+        uint32_t round = 0;
+        for (long long n = 0; n < n_my; ++n) {
+          const double* src = p.panels + (size_t)(blockIdx.x + n * grid) * Cpad * WR;
+          for (int j = 0; j < J; ++j) {
+            if (round > 0) mbar_wait(&empty_bar[sl], (round - 1) & 1);
+            const uint32_t bytes = (uint32_t)min(KC, Cpad - j * KC) * WR * 8u;
+            mbar_arrive_expect_tx(&full_bar[sl], bytes);
+            tma_load_1d(ring + (size_t)sl * SLOT, src + (size_t)j * KC * WR, bytes, &full_bar[sl], pol);
+            if (++sl == T) {
+              sl = 0;
+              ++round;
+            }
+          }
+        }
+      }
+    } else if (lane < J) {
       const uint64_t pol = policy_evict_first();
       const uint32_t bytes = (uint32_t)min(KC, Cpad - lane * KC) * WR * 8u;
-      long long q = lane;                     // index of this lane's next sub-panel in the CTA's stream: n * J + lane
-      for (long long n = 0; n < n_my; ++n, q += J) {
-        const int sl = (int)(q % T);
-        const long long round = q / T;
+      int sl = lane;                          // ring slot of this lane's next sub-panel (n * J + lane) mod T
+      uint32_t round = 0;                     // ... and how often the ring has wrapped for it
+      for (long long n = 0; n < n_my; ++n) {
         const double* src = p.panels + (size_t)(blockIdx.x + n * grid) * Cpad * WR;
-        if (round > 0) mbar_wait(&empty_bar[sl], (uint32_t)((round - 1) & 1));
+        if (round > 0) mbar_wait(&empty_bar[sl], (round - 1) & 1);
         mbar_arrive_expect_tx(&full_bar[sl], bytes);
         tma_load_1d(ring + (size_t)sl * SLOT, src + (size_t)lane * KC * WR, bytes, &full_bar[sl], pol);
+        sl += J;                              // T >= 2 J: at most one wrap
+        if (sl >= T) {
+          sl -= T;
+          ++round;
+        }
       }
     }
   } else {

@@ -1,0 +1,89 @@
+"""Device-side NUTS, checked WITHOUT a GPU: the product's driver (stan_b200/cpp/b200/device_nuts.hpp) and
+per-chain state machine (stan_b200/csrc/nuts_tree.cuh -- the code the kernels run with one warp per chain) are built for
+the host by the checker (oracle/ref/nuts_host_backend.hpp: one-lane policy, leapfrog steps by the reference's own
+integrator on the reference's own model) and run against stan::services::sample::hmc_nuts_diag_e_adapt on the same seeds.
+
+What is being compared is exactly what moved to the device: the iterative build_tree (base_nuts.hpp:247-352), transition()
+(:78-204), init_stepsize (base_hmc.hpp:78-143), dual averaging (stepsize_adaptation.hpp:55-71), the metric windows
+(var_adaptation.hpp:17-46, windowed_adaptation.hpp) and the host's engine bookkeeping (normal / uniform variates in the
+reference's order, rewound to what the device consumed).  Every draw column is compared: lp__, accept_stat__, stepsize__,
+treedepth__, n_leapfrog__, divergent__, energy__, parameters.  Dot products are summed in a different order than Eigen's,
+so agreement is to rounding, amplified by the dynamics as the run goes on; the bars below say how far."""
+import numpy as np
+import pytest
+
+from oracle.oracle import RefOracle
+from stan_b200.synth import make_glm_data
+
+pytestmark = pytest.mark.skipif(not RefOracle.available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def _both(fam, N, K, G=0, **kw):
+    d = make_glm_data(fam, N, K, G)
+    ro = RefOracle(fam, d["X"], d["y"], d["group"], G)
+    a, b = ro.nuts(**kw), ro.nuts_device_host(**kw)
+    A = np.concatenate([a["warmup_draws"], a["draws"]], axis=1)
+    B = np.concatenate([b["warmup_draws"], b["draws"]], axis=1)
+    return a, b, A, B
+
+
+def _err(A, B):
+    return np.abs(A - B) / (1.0 + np.abs(A))
+
+
+@pytest.mark.parametrize("fam,N,K", [("bernoulli_logit", 500, 4), ("normal_id", 400, 3), ("poisson_log", 300, 6)])
+def test_whole_run_matches_the_reference_sampler(fam, N, K):
+    """150 warm-up (three metric windows, four init_stepsize searches) + 50 sampling iterations, 3 chains: every column of
+    every draw, the adapted step size and the adapted metric."""
+    kw = dict(num_chains=3, seed=11, init_chain_id=2, num_warmup=150, num_samples=50, stepsize=1.0, max_depth=10, delta=0.8)
+    a, b, A, B = _both(fam, N, K, **kw)
+    assert np.array_equal(A[:, :, 3:6], B[:, :, 3:6])          # treedepth__, n_leapfrog__, divergent__: same trees
+    e = _err(A, B).max(axis=(0, 2))
+    assert e[:20].max() < 1e-12 and e.max() < 1e-6            # rounding, amplified over 200 iterations
+    assert np.abs(a["stepsize"] - b["stepsize"]).max() < 1e-8
+    assert np.abs(a["inv_metric"] - b["inv_metric"]).max() < 1e-8
+    # the host generated exactly one vector of normal variates per momentum refresh
+    assert b["normal_vectors"] >= 3 * 200
+
+
+def test_hierarchical_model_matches_until_rounding_is_amplified():
+    """a = a[group] with sigma_a: depth-5 trees and chaotic dynamics.  The first iterations agree to the last bit or two,
+    the difference then grows smoothly (rounding amplified), never by a jump (which a logic difference would give)."""
+    kw = dict(num_chains=2, seed=11, num_warmup=150, num_samples=20, stepsize=1.0, max_depth=10, delta=0.8)
+    a, b, A, B = _both("poisson_log", 600, 3, 5, **kw)
+    per_iter = _err(A, B).max(axis=(0, 2))
+    assert per_iter[:12].max() < 1e-13
+    assert per_iter[:30].max() < 1e-8
+    first_tree_diff = np.argmax((A[:, :, 4] != B[:, :, 4]).any(axis=0)) if (A[:, :, 4] != B[:, :, 4]).any() else len(per_iter)
+    assert first_tree_diff >= 40
+
+
+@pytest.mark.parametrize("num_warmup,num_samples,max_depth,stepsize", [
+    (0, 30, 10, 0.3),      # no warm-up: complete_adaptation still sets the step size to exp(0) = 1 (reference quirk)
+    (10, 30, 10, 1.0),     # num_warmup < 20: no metric estimation, dual averaging only
+    (60, 20, 10, 1.0),     # windows do not fit: the 15 % / 75 % / 10 % schedule
+    (100, 30, 3, 1.0),     # trees cut at max_depth
+    (100, 20, 10, 50.0),   # absurd initial step size: init_stepsize halves it many times; early divergences
+])
+def test_schedules_and_limits(num_warmup, num_samples, max_depth, stepsize):
+    kw = dict(num_chains=2, seed=5, num_warmup=num_warmup, num_samples=num_samples, stepsize=stepsize,
+              max_depth=max_depth, delta=0.8)
+    a, b, A, B = _both("bernoulli_logit", 400, 5, **kw)
+    assert np.array_equal(A[:, :, 3:6], B[:, :, 3:6])
+    e = _err(A, B).max(axis=(0, 2))
+    assert e[:20].max() < 1e-12 and e.max() < 1e-6
+    assert np.abs(a["stepsize"] - b["stepsize"]).max() < 1e-8
+    assert np.abs(a["inv_metric"] - b["inv_metric"]).max() < 1e-8
+    if max_depth == 3:
+        assert (A[:, :, 3] == 3).any() and (A[:, :, 4] <= 7).all()
+    if num_warmup == 0:
+        assert np.all(A[:, :, 2] == 1.0)
+
+
+def test_divergent_transitions_are_reproduced():
+    """A step size far too large for a sharp posterior, no adaptation to repair it: divergent__ = 1 rows must coincide."""
+    kw = dict(num_chains=2, seed=3, num_warmup=0, num_samples=60, stepsize=1.0, max_depth=10, delta=0.8)
+    a, b, A, B = _both("poisson_log", 4000, 4, **kw)
+    assert A[:, :, 5].sum() > 0
+    assert np.array_equal(A[:, :, 3:6], B[:, :, 3:6])
+    assert _err(A, B).max() < 1e-6
