@@ -33,6 +33,8 @@ def summarize(res, Ref, num_chains):
     ess = [Ref.ess(d[:, :, 7 + k].T) for k in range(P)]
     n_grad_sampling = float(d[:, :, 4].sum() + d.shape[0] * d.shape[1])
     n_grad_warm = float(res["warm_leapfrogs"].sum() + res["warmup_draws"].shape[0] * res["warmup_draws"].shape[1])
+    if "rounds" in res:   # device-side driver: no gradient per transition start (the sample's gradient is kept); exact count
+        n_grad_warm, n_grad_sampling = float(res["lanes"]), 0.0
     return dict(wall_s=res["wall"], grad_evals=n_grad_warm + n_grad_sampling,
                 grad_evals_per_s=(n_grad_warm + n_grad_sampling) / res["wall"],
                 ess_min=float(np.min(ess)), ess_median=float(np.median(ess)),
@@ -51,12 +53,19 @@ def config3(args):
     d = make_glm_data("normal_id", N, K)
     t_gen = time.time() - t0
     m = stan_service.StanGLM("normal_id", d["X"], d["y"], n_slots=16)
-    res = m.nuts_batched(num_chains=args.chains, seed=4711, num_warmup=args.warmup, num_samples=args.samples, delta=0.8)
+    run = m.nuts_device if args.driver == "device" else m.nuts_batched
+    res = run(num_chains=args.chains, seed=4711, num_warmup=args.warmup, num_samples=args.samples, delta=0.8)
     s = summarize(res, RefOracle, args.chains)
     s.pop("stepsize")
     s["stepsize_median"] = float(np.median(res["stepsize"]))
-    s.update(batches=res["batches"], lanes=res["lanes"], mean_lanes_per_batch=res["lanes"] / max(res["batches"], 1),
-             batch_size_hist=res["batch_size_hist"])
+    if args.driver == "device":
+        s.update(driver="device-side transition + adaptation (b200::hmc_nuts_diag_e_adapt_device)", rounds=res["rounds"],
+                 lanes=res["lanes"], mean_lanes_per_round=res["lanes"] / max(res["rounds"], 1),
+                 uniforms_generated=res["uniforms"], normal_vectors_generated=res["normal_vectors"])
+    else:
+        s.update(driver="host tree building, fibers (b200::hmc_nuts_diag_e_adapt_batched)", batches=res["batches"],
+                 lanes=res["lanes"], mean_lanes_per_batch=res["lanes"] / max(res["batches"], 1),
+                 batch_size_hist=res["batch_size_hist"])
     per_chain = res["warm_leapfrogs"] + res["draws"][:, :, 4].sum(axis=1)
     pc = lambda a: [float(np.percentile(a, q)) for q in (50, 90, 99, 100)]
     s["per_chain_leapfrogs_p50_p90_p99_max"] = pc(per_chain)
@@ -85,7 +94,9 @@ def config3(args):
     z_chain = np.abs(chain_means - pooled_mean) / (pooled_sd / np.sqrt(max(n_draws / 4.0, 1.0)))   # ESS >= draws / 4
     s["ols_check"]["chains_with_a_mean_beyond_5_mcse"] = int((z_chain.max(axis=1) > 5.0).sum())
     out = {"workload": f"normal_id_glm N={N} K={K}, NUTS diag_e {args.chains} batched chains {args.warmup}+{args.samples} "
-                       "via b200::hmc_nuts_diag_e_adapt_batched (single-chain reference service per chain)",
+                       + ("via b200::hmc_nuts_diag_e_adapt_device (transition and adaptation on the device)"
+                          if args.driver == "device" else
+                          "via b200::hmc_nuts_diag_e_adapt_batched (single-chain reference service per chain)"),
            "host_threads": os.cpu_count(), "data_gen_s": t_gen, "b200": dict(s, counters=m.counters())}
     m.close()
     print(json.dumps(out))
@@ -167,6 +178,10 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=-1, help="CPU arm iterations (warmup=samples); 0 skips, -1 same")
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--cols", type=int, default=0)
+    ap.add_argument("--driver", choices=["service", "batched", "device"], default=None,
+                    help="service = the unmodified reference service (default for configs 1, 2, 4); batched = host tree "
+                         "building over the batched leapfrog (default for config 3); device = transition + adaptation on "
+                         "the device (configs 1 and 3)")
     args = ap.parse_args()
     from oracle.oracle import RefOracle
     from stan_b200 import make_glm_data, stan_service
@@ -188,9 +203,16 @@ def main():
     t0 = time.time()
     m = stan_service.StanGLM("bernoulli_logit", d["X"], d["y"], n_slots=max(8, args.chains))
     t_upload = time.time() - t0
-    dev = m.nuts(**kw)
+    if args.driver in ("device", "batched"):
+        kd = {k: v for k, v in kw.items() if k != "num_threads"}
+        dev = (m.nuts_device if args.driver == "device" else m.nuts_batched)(**kd)
+    else:
+        dev = m.nuts(**kw)
+    how = {"device": "b200::hmc_nuts_diag_e_adapt_device (transition and adaptation on the device)",
+           "batched": "b200::hmc_nuts_diag_e_adapt_batched (host tree building, batched leapfrog)"}.get(
+               args.driver, "unmodified hmc_nuts_diag_e_adapt")
     out = {"workload": f"bernoulli_logit_glm N={N} K={K}, NUTS diag_e {args.chains} chains {args.warmup}+{args.samples} "
-                       "via unmodified hmc_nuts_diag_e_adapt", "host_threads": os.cpu_count(),
+                       f"via {how}", "host_threads": os.cpu_count(),
            "data_gen_s": t_gen, "upload_relayout_s": t_upload,
            "b200": dict(summarize(dev, RefOracle, args.chains), counters=m.counters())}
     m.close()

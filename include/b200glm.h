@@ -198,6 +198,47 @@ int b200glm_leapfrog_batched_async(b200glm_handle* h, int32_t n, double eps);
 int b200glm_batch_sync(b200glm_handle* h);
 void* b200glm_batch_stream(b200glm_handle* h);
 
+/* Device-side NUTS transition + adaptation for the batch.  Replaces, per chain,
+ * stan::mcmc::adapt_diag_e_nuts<Model, rng_t>::transition (ST/mcmc/hmc/nuts/adapt_diag_e_nuts.hpp:26-44), i.e.
+ * base_nuts::transition + build_tree (base_nuts.hpp:78-204, 247-352), base_hmc::init_stepsize (base_hmc.hpp:78-143),
+ * stepsize_adaptation::learn_stepsize / complete_adaptation (stepsize_adaptation.hpp:55-71) and
+ * var_adaptation::learn_variance (var_adaptation.hpp:17-46), run by a per-chain state machine right behind the batched
+ * leapfrog: q, p, g, the tree, the dual-averaging state and the Welford accumulators stay on the device; only draws,
+ * 40 bytes of status per chain and round, and the adapted metric leave it.  Randomness stays the caller's (the
+ * reference's per-chain boost engine): P normal variates per momentum refresh and the uniform variates of the direction
+ * / multinomial decisions, written into the pinned buffers below in the order the reference draws them; the status
+ * says how many uniform variates were consumed.  Host driver: b200::hmc_nuts_diag_e_adapt_device
+ * (stan_b200/cpp/b200/device_nuts.hpp), the argument list of ST/services/sample/hmc_nuts_diag_e_adapt.hpp:331-404.
+ *   nuts_reserve     batch_reserve(n_chains) + the per-chain tree state ((17 + 5 max_depth) P doubles)
+ *   nuts_buffers     pinned host buffers shared with the kernels: normals [n][P], uniforms [n][64] (a ring indexed
+ *                    by the running count), status [n], draws [n][P + 8] (parameters, lp__, accept_stat__, stepsize__,
+ *                    treedepth__, n_leapfrog__, divergent__, energy__, iteration), metric [n][P]
+ *   nuts_init_chain  initial point, diagonal inverse metric, nominal step size of one chain
+ *   nuts_round       one round for the listed chains: begin (chains whose normal variates were supplied) ->
+ *                    ONE batched leapfrog -> tree / adaptation step; returns when the status is up to date */
+typedef struct b200glm_nuts_config {
+  int32_t max_depth, num_warmup, num_samples;
+  /* stan::mcmc::windowed_adaptation after set_window_params(): num_warmup_, adapt_init_buffer_, adapt_term_buffer_,
+   * adapt_base_window_, adapt_window_size_, adapt_next_window_ */
+  uint32_t w_num_warmup, w_init_buffer, w_term_buffer, w_base_window, w_size0, w_next0;
+  double max_deltaH, delta, gamma, kappa, t0;
+} b200glm_nuts_config;
+typedef struct b200glm_nuts_status {
+  int32_t phase;          /* 1 initial gradient, 2 / 3 init_stepsize, 4 inside a transition, 5 done, 6 failed */
+  int32_t need_normals;   /* the chain waits for P fresh normal variates in its row of `normals` */
+  int32_t iter;           /* transitions completed */
+  int32_t fail_code;      /* 1 posterior improper, 2 no acceptably small step size, 3 metric overflow (base_hmc.hpp:131-140) */
+  int32_t adapt_done, reserved;
+  uint64_t n_unif;        /* uniform variates consumed so far */
+  double eps_nom;         /* nominal step size */
+} b200glm_nuts_status;
+int b200glm_nuts_reserve(b200glm_handle* h, int32_t n_chains, const b200glm_nuts_config* cfg);
+int b200glm_nuts_buffers(b200glm_handle* h, double** normals, double** uniforms, b200glm_nuts_status** status,
+                         double** draws, double** metric);
+int b200glm_nuts_init_chain(b200glm_handle* h, int32_t chain, const double* q0, const double* inv_metric,
+                            double stepsize);
+int b200glm_nuts_round(b200glm_handle* h, int32_t n_lanes, const int32_t* chains);
+
 /* Row-sharded operation: one process per GPU, likelihood partials combined by one NCCL
  * all-reduce of P+2 doubles per gradient (replaces nothing in the reference's GLM path; the
  * analogue is map_rect's gatherv, SM/prim/functor/mpi_parallel_call.hpp:354-392).

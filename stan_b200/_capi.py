@@ -21,6 +21,7 @@ SYMBOLS = [
     "b200glm_glm_lpmf", "b200glm_glm_lpmf_rows", "b200glm_shard_constants_local", "b200glm_set_shard_constants_total",
     "b200glm_timeline_enable", "b200glm_timeline_read", "b200glm_abi_version", "b200glm_measure_peaks",
     "b200glm_launch_count", "b200glm_bytes_per_gradient", "b200glm_last_error", "b200glm_version",
+    "b200glm_nuts_reserve", "b200glm_nuts_buffers", "b200glm_nuts_init_chain", "b200glm_nuts_round",
 ]
 
 
@@ -40,6 +41,21 @@ class Desc(C.Structure):
 
 
 _lib = None
+
+
+class NutsConfig(C.Structure):
+    """b200glm_nuts_config (include/b200glm.h): device-side NUTS, SURVEY 8f row 2"""
+    _fields_ = [("max_depth", C.c_int32), ("num_warmup", C.c_int32), ("num_samples", C.c_int32),
+                ("w_num_warmup", C.c_uint32), ("w_init_buffer", C.c_uint32), ("w_term_buffer", C.c_uint32),
+                ("w_base_window", C.c_uint32), ("w_size0", C.c_uint32), ("w_next0", C.c_uint32),
+                ("max_deltaH", C.c_double), ("delta", C.c_double), ("gamma", C.c_double), ("kappa", C.c_double),
+                ("t0", C.c_double)]
+
+
+class NutsStatus(C.Structure):
+    """b200glm_nuts_status"""
+    _fields_ = [("phase", C.c_int32), ("need_normals", C.c_int32), ("iter", C.c_int32), ("fail_code", C.c_int32),
+                ("adapt_done", C.c_int32), ("reserved", C.c_int32), ("n_unif", C.c_uint64), ("eps_nom", C.c_double)]
 
 
 def lib():
@@ -102,6 +118,11 @@ def lib():
         L.b200glm_timeline_enable.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.b200glm_timeline_read.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64), ip]
         L.b200glm_measure_peaks.argtypes = [C.c_int32, dp, dp]
+        L.b200glm_nuts_reserve.argtypes = [C.c_void_p, C.c_int32, C.POINTER(NutsConfig)]
+        L.b200glm_nuts_buffers.argtypes = [C.c_void_p, C.POINTER(dp), C.POINTER(dp), C.POINTER(C.POINTER(NutsStatus)),
+                                           C.POINTER(dp), C.POINTER(dp)]
+        L.b200glm_nuts_init_chain.argtypes = [C.c_void_p, C.c_int32, dp, dp, C.c_double]
+        L.b200glm_nuts_round.argtypes = [C.c_void_p, C.c_int32, ip]
         L.b200glm_launch_count.argtypes = [C.c_void_p]
         L.b200glm_launch_count.restype = C.c_int64
         L.b200glm_bytes_per_gradient.argtypes = [C.c_void_p]

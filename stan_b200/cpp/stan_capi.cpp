@@ -6,6 +6,8 @@
 //                             with Model = b200::glm_model; base_nuts, diag_e_metric, adaptation, writers untouched
 //   b200stan_nuts_batched  -> b200::hmc_nuts_diag_e_adapt_batched (b200/batched_nuts.hpp): the same single-chain service per
 //                             chain, all chains served by one batched DMMA launch per leapfrog step
+//   b200stan_nuts_device   -> b200::hmc_nuts_diag_e_adapt_device (b200/device_nuts.hpp): transition + adaptation in the per-chain
+//                             state machine on the device (b200glm_nuts_*), the host keeps the chains' boost engines
 //   b200stan_func_eval     -> stan::math::{bernoulli_logit,poisson_log,normal_id}_glm_lp*f overloads on b200::glm_data views
 //                             (b200/glm_functions.hpp): the function-level slot the OpenCL backend uses
 //   b200stan_log_prob_grad -> stan::model::log_prob_grad<propto,jacobian>    (tape path via precomputed_gradients)
@@ -13,6 +15,7 @@
 //   b200stan_leapfrog      -> stan::mcmc::expl_leapfrog<diag_e_metric<...>>::evolve (device-resident specialisation)
 #include <b200/stan_glm_model.hpp>
 #include <b200/batched_nuts.hpp>
+#include <b200/device_nuts.hpp>
 #include <b200/glm_functions.hpp>
 
 #include <stan/analyze/mcmc/ess.hpp>
@@ -277,7 +280,7 @@ int b200stan_leapfrog(void* h, double eps, const double* inv_metric, int n_steps
 }
 
 // draws: [chain][warmup+sample][7 + P] (lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__, params)
-static int nuts_impl(void* h, bool batched, int num_chains, unsigned seed, unsigned init_chain_id, double init_radius,
+static int nuts_impl(void* h, int mode /* 0 reference service, 1 batched host driver, 2 device-side */, int num_chains, unsigned seed, unsigned init_chain_id, double init_radius,
                      int num_warmup, int num_samples, double stepsize, int max_depth, double delta, int num_threads,
                      double* draws, double* stepsize_out, double* inv_metric_out, double* warm_leapfrogs,
                      double* wall_seconds, long* batch_stats, char* err, int errlen) {
@@ -285,7 +288,8 @@ static int nuts_impl(void* h, bool batched, int num_chains, unsigned seed, unsig
   const int P = static_cast<int>(m.num_params_r());
   int rc = 0;
   int g = guarded(err, errlen, [&] {
-    if (!batched)
+    const bool batched = mode == 1;
+    if (mode == 0)
       stan::math::init_threadpool_tbb(num_threads > 0 ? num_threads : num_chains);
     std::vector<std::shared_ptr<stan::io::var_context>> inits, metrics;
     for (int c = 0; c < num_chains; ++c) {
@@ -299,7 +303,30 @@ static int nuts_impl(void* h, bool batched, int num_chains, unsigned seed, unsig
     std::vector<draw_writer> sample_w(num_chains);
     std::vector<metric_writer> metric_w(num_chains);
     auto t0 = std::chrono::steady_clock::now();
-    if (batched)
+    if (mode == 2) {
+      // the C ABI of libb200glm.so as the driver's backend table
+      static_assert(sizeof(b200::nuts_config) == sizeof(b200glm_nuts_config), "nuts_config mirrors b200glm_nuts_config");
+      static_assert(sizeof(b200::nuts_status) == sizeof(b200glm_nuts_status), "nuts_status mirrors b200glm_nuts_status");
+      b200::nuts_backend be;
+      be.ctx = m.handle();
+      be.reserve = [](void* c, std::int32_t n, const b200::nuts_config* cfg) {
+        return b200glm_nuts_reserve(static_cast<b200glm_handle*>(c), n, reinterpret_cast<const b200glm_nuts_config*>(cfg));
+      };
+      be.buffers = [](void* c, double** no, double** un, b200::nuts_status** st, double** dr, double** me) {
+        return b200glm_nuts_buffers(static_cast<b200glm_handle*>(c), no, un, reinterpret_cast<b200glm_nuts_status**>(st), dr, me);
+      };
+      be.init_chain = [](void* c, std::int32_t chain, const double* q0, const double* im, double eps) {
+        return b200glm_nuts_init_chain(static_cast<b200glm_handle*>(c), chain, q0, im, eps);
+      };
+      be.round = [](void* c, std::int32_t n, const std::int32_t* chains) {
+        return b200glm_nuts_round(static_cast<b200glm_handle*>(c), n, chains);
+      };
+      be.last_error = [](void* c) { return b200glm_last_error(static_cast<b200glm_handle*>(c)); };
+      rc = b200::hmc_nuts_diag_e_adapt_device(m, be, num_chains, inits, metrics, seed, init_chain_id, init_radius,
+                                              num_warmup, num_samples, 1, true, 0, stepsize, 0.0, max_depth, delta, 0.05,
+                                              0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w, diag_w,
+                                              metric_w, batch_stats);
+    } else if (batched)
       rc = b200::hmc_nuts_diag_e_adapt_batched(
           m, num_chains, inits, metrics, seed, init_chain_id, init_radius, num_warmup, num_samples, 1, true, 0,
           stepsize, 0.0, max_depth, delta, 0.05, 0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w, diag_w,
@@ -340,7 +367,7 @@ int b200stan_nuts(void* h, int num_chains, unsigned seed, unsigned init_chain_id
                   int num_samples, double stepsize, int max_depth, double delta, int num_threads, double* draws,
                   double* stepsize_out, double* inv_metric_out, double* warm_leapfrogs, double* wall_seconds,
                   char* err, int errlen) {
-  return nuts_impl(h, false, num_chains, seed, init_chain_id, init_radius, num_warmup, num_samples, stepsize, max_depth,
+  return nuts_impl(h, 0, num_chains, seed, init_chain_id, init_radius, num_warmup, num_samples, stepsize, max_depth,
                    delta, num_threads, draws, stepsize_out, inv_metric_out, warm_leapfrogs, wall_seconds, nullptr, err,
                    errlen);
 }
@@ -350,9 +377,18 @@ int b200stan_nuts_batched(void* h, int num_chains, unsigned seed, unsigned init_
                           int num_warmup, int num_samples, double stepsize, int max_depth, double delta, double* draws,
                           double* stepsize_out, double* inv_metric_out, double* warm_leapfrogs, double* wall_seconds,
                           long* batch_stats, char* err, int errlen) {
-  return nuts_impl(h, true, num_chains, seed, init_chain_id, init_radius, num_warmup, num_samples, stepsize, max_depth,
+  return nuts_impl(h, 1, num_chains, seed, init_chain_id, init_radius, num_warmup, num_samples, stepsize, max_depth,
                    delta, 0, draws, stepsize_out, inv_metric_out, warm_leapfrogs, wall_seconds, batch_stats, err,
                    errlen);
+}
+
+// stats[4] = {rounds, leapfrog lanes served, uniform variates generated, vectors of normal variates generated}
+int b200stan_nuts_device(void* h, int num_chains, unsigned seed, unsigned init_chain_id, double init_radius,
+                         int num_warmup, int num_samples, double stepsize, int max_depth, double delta, double* draws,
+                         double* stepsize_out, double* inv_metric_out, double* warm_leapfrogs, double* wall_seconds,
+                         long* stats, char* err, int errlen) {
+  return nuts_impl(h, 2, num_chains, seed, init_chain_id, init_radius, num_warmup, num_samples, stepsize, max_depth,
+                   delta, 0, draws, stepsize_out, inv_metric_out, warm_leapfrogs, wall_seconds, stats, err, errlen);
 }
 
 // ---- output formats: the reference's own writers and reader -------------------------

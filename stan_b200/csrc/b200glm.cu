@@ -20,6 +20,7 @@
 
 #include "glm_kernels.cuh"
 #include "glm_wide_kernel.cuh"
+#include "nuts_kernels.cuh"
 #include "glm_batched_kernel.cuh"
 #include "glm_class_kernel.cuh"
 #include "measure.cuh"
@@ -106,7 +107,35 @@ struct Batch {
   double* h_pin = nullptr;      // pinned staging, max_chains * (3P + 1) doubles (+ ints)
   int32_t* h_pin_i = nullptr;
   std::mutex mu;
+  // device-side NUTS (b200glm_nuts_*): per-chain state machine behind the batched leapfrog
+  struct Nuts {
+    NutsConfig cfg;
+    int n_chains = 0;
+    size_t vstride = 0;
+    NutsChain* chains = nullptr;     // device
+    double* vec = nullptr;           // device [n][vstride]
+    double* eps_c = nullptr;         // device [ld]
+    double *normals = nullptr, *uniforms = nullptr, *draws = nullptr, *metric = nullptr;   // pinned host
+    NutsStatus* status = nullptr;    // pinned host
+    int32_t* lanes_d = nullptr;      // device: the lane list of the last round (re-uploaded only when it changes)
+    std::vector<int32_t> lanes_h;
+  };
+  Nuts* nuts = nullptr;
 };
+
+void free_nuts(Batch* b) {
+  if (!b || !b->nuts) return;
+  Batch::Nuts* u = b->nuts;
+  cudaFree(u->chains);
+  cudaFree(u->vec);
+  cudaFree(u->eps_c);
+  cudaFree(u->lanes_d);
+  for (double* q : {u->normals, u->uniforms, u->draws, u->metric})
+    if (q) cudaFreeHost(q);
+  if (u->status) cudaFreeHost(u->status);
+  delete u;
+  b->nuts = nullptr;
+}
 
 }  // namespace
 
@@ -137,7 +166,7 @@ struct b200glm_handle {
   long long rows_appended = 0;
   double bad_count = 0.0;
   int pdl_prefetch = 2;     // B200GLM_PDL_PREFETCH=<stages> (A/B runs); see the TMA producer in glm_kernels.cuh
-  int wide_producer = 1;    // B200GLM_WIDE_PRODUCER=single|lanes (A/B runs); see the TMA producer in glm_wide_kernel.cuh
+  int wide_producer = -1;   // -1 = chosen at create from the ring depth; B200GLM_WIDE_PRODUCER=single|lanes|poll (A/B runs); see the TMA producer in glm_wide_kernel.cuh
   bool tl_repeat = false;   // B200GLM_TL_REPEAT=1 (timeline runs only): the last CTA sums the partial rows twice
   bool inline_theta = true; // B200GLM_NO_INLINE_THETA=1: always upload theta with a host-to-device copy (A/B runs)
   bool host_mirror = true;  // B200GLM_NO_HOST_MIRROR=1: fetch results with a device-to-host copy + stream sync (A/B runs)
@@ -593,6 +622,7 @@ void b200glm_destroy(b200glm_handle* h) {
   }
   if (Batch* b = h->batch) {
     if (b->stream) cudaStreamSynchronize(b->stream);
+    free_nuts(b);
     for (double* q : {b->Q, b->Pm, b->Gd, b->V, b->IM, b->theta_c, b->p_half, b->partials, b->reduced, b->result, b->state_out,
                       b->theta_in, b->eps_d})
       cudaFree(q);
@@ -665,7 +695,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   if (const char* e = std::getenv("B200GLM_NO_PDL")) h->pdl = !(e[0] == '1');
   if (const char* e = std::getenv("B200GLM_PDL_PREFETCH")) h->pdl_prefetch = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("B200GLM_TL_REPEAT")) h->tl_repeat = (e[0] == '1');
-  if (const char* e = std::getenv("B200GLM_WIDE_PRODUCER")) h->wide_producer = (e[0] == 's') ? 0 : 1;
+  if (const char* e = std::getenv("B200GLM_WIDE_PRODUCER")) h->wide_producer = e[0] == 's' ? 0 : (e[0] == 'l' ? 1 : 2);
   if (const char* e = std::getenv("B200GLM_NO_INLINE_THETA")) h->inline_theta = !(e[0] == '1');
   if (const char* e = std::getenv("B200GLM_NO_HOST_MIRROR")) h->host_mirror = !(e[0] == '1');
   h->P = (d.G > 0 ? 2 + d.G : 1) + d.K + (fam_has_scale(d.family) ? 1 : 0);
@@ -789,6 +819,9 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     if (T < 2 * h->J) return fail(B200GLM_INVALID, "two row panels do not fit in shared memory (K too large)");
     h->n_stages = T;
     h->smem_bytes = fixed + (size_t)T * (slot_bytes + 16);
+    // TMA producer form (glm_wide_kernel.cuh): the lanes' joint wait needs a whole panel of free slots beyond the two
+    // resident panels; with a shallower ring the single-lane loop is the faster one (measured, profiles/r2_wide_variants.txt)
+    if (h->wide_producer < 0) h->wide_producer = T >= 3 * h->J ? 1 : 0;
   }
   // the attribute belongs to the kernel, not to the handle: always the device maximum, so that handles of
   // different shapes sharing one instantiation cannot lower it for each other
@@ -1293,7 +1326,7 @@ int batch_check(b200glm_handle* h, int n) {
 
 // begin -> main -> finish for n lanes on the batch stream.  chains_d / eps_d may be NULL.
 int enqueue_batched(b200glm_handle* h, int n, int mode, int propto, int jacobian, const int32_t* chains_d,
-                    const double* eps_d, double eps_scalar, bool mirror_state) {
+                    const double* eps_d, double eps_scalar, bool mirror_state, bool eps_by_chain = false) {
   Batch* b = h->batch;
   const int NCB = (n + BATCH_CB - 1) / BATCH_CB;
   int NS = std::max(1, b->sms / NCB);
@@ -1312,6 +1345,7 @@ int enqueue_batched(b200glm_handle* h, int n, int mode, int propto, int jacobian
   sp.mode = mode;
   sp.chains = chains_d;
   sp.eps = eps_d;
+  sp.eps_by_chain = eps_by_chain ? 1 : 0;
   sp.eps_scalar = eps_scalar;
   sp.theta_in = b->theta_in;
   sp.Q = b->Q;
@@ -1374,6 +1408,7 @@ int b200glm_batch_reserve(b200glm_handle* h, int32_t max_chains) {
     Batch* b = h->batch;
     cudaSetDevice(h->d.device);
     if (b->stream) cudaStreamSynchronize(b->stream);
+    free_nuts(b);
     for (double* q : {b->Q, b->Pm, b->Gd, b->V, b->IM, b->theta_c, b->p_half, b->partials, b->reduced, b->result, b->state_out,
                       b->theta_in, b->eps_d})
       cudaFree(q);
@@ -1586,6 +1621,176 @@ int b200glm_batch_sync(b200glm_handle* h) {
 }
 
 void* b200glm_batch_stream(b200glm_handle* h) { return (h && h->batch) ? (void*)h->batch->stream : nullptr; }
+
+// ---- device-side NUTS: nuts_tree.cuh / nuts_kernels.cuh behind the batched leapfrog ----
+static NutsDeviceParams nuts_params(b200glm_handle* h) {
+  Batch* b = h->batch;
+  Batch::Nuts* u = b->nuts;
+  NutsDeviceParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.cfg = u->cfg;
+  p.chains = u->chains;
+  p.vec = u->vec;
+  p.vstride = u->vstride;
+  p.Q = b->Q;
+  p.Pm = b->Pm;
+  p.Gd = b->Gd;
+  p.IM = b->IM;
+  p.V = b->V;
+  p.ld = (size_t)b->ld;
+  p.eps_c = u->eps_c;
+  p.normals = u->normals;
+  p.unif = u->uniforms;
+  p.status = u->status;
+  p.draws = u->draws;
+  p.metric = u->metric;
+  return p;
+}
+
+int b200glm_nuts_reserve(b200glm_handle* h, int32_t n_chains, const b200glm_nuts_config* c) {
+  if (!h) return B200GLM_INVALID;
+  if (!c || n_chains < 1 || c->max_depth < 1 || c->max_depth > NUTS_DEPTH_CAP || c->num_warmup < 0 || c->num_samples < 0) {
+    h->set_error("b200glm_nuts_reserve: needs n_chains >= 1, 1 <= max_depth <= 16, num_warmup / num_samples >= 0");
+    return B200GLM_INVALID;
+  }
+  int rc = b200glm_batch_reserve(h, n_chains);
+  if (rc) return rc;
+  Batch* b = h->batch;
+  std::lock_guard<std::mutex> lk(b->mu);
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  CUDA_TRY(h, cudaStreamSynchronize(b->stream));
+  free_nuts(b);
+  Batch::Nuts* u = new Batch::Nuts();
+  b->nuts = u;
+  const size_t P = h->P, n = (size_t)n_chains;
+  u->n_chains = n_chains;
+  u->cfg.P = h->P;
+  u->cfg.max_depth = c->max_depth;
+  u->cfg.max_deltaH = c->max_deltaH;
+  u->cfg.delta = c->delta;
+  u->cfg.gamma = c->gamma;
+  u->cfg.kappa = c->kappa;
+  u->cfg.t0 = c->t0;
+  u->cfg.w_num_warmup = c->w_num_warmup;
+  u->cfg.w_init_buffer = c->w_init_buffer;
+  u->cfg.w_term_buffer = c->w_term_buffer;
+  u->cfg.w_base_window = c->w_base_window;
+  u->cfg.w_size0 = c->w_size0;
+  u->cfg.w_next0 = c->w_next0;
+  u->cfg.num_warmup = c->num_warmup;
+  u->cfg.num_samples = c->num_samples;
+  u->vstride = nuts_vec_doubles(h->P, c->max_depth);
+  CUDA_TRY(h, cudaMalloc(&u->chains, sizeof(NutsChain) * n));
+  CUDA_TRY(h, cudaMemset(u->chains, 0, sizeof(NutsChain) * n));
+  CUDA_TRY(h, cudaMalloc(&u->vec, sizeof(double) * u->vstride * n));
+  CUDA_TRY(h, cudaMemset(u->vec, 0, sizeof(double) * u->vstride * n));
+  CUDA_TRY(h, cudaMalloc(&u->eps_c, sizeof(double) * b->ld));
+  CUDA_TRY(h, cudaMemset(u->eps_c, 0, sizeof(double) * b->ld));
+  CUDA_TRY(h, cudaMalloc(&u->lanes_d, sizeof(int32_t) * b->ld));
+  CUDA_TRY(h, cudaMallocHost(&u->normals, sizeof(double) * n * P));
+  CUDA_TRY(h, cudaMallocHost(&u->uniforms, sizeof(double) * n * NUTS_UNIF_CAP));
+  CUDA_TRY(h, cudaMallocHost(&u->draws, sizeof(double) * n * (P + NUTS_DRAW_EXTRA)));
+  CUDA_TRY(h, cudaMallocHost(&u->metric, sizeof(double) * n * P));
+  CUDA_TRY(h, cudaMallocHost(&u->status, sizeof(NutsStatus) * n));
+  std::memset(u->normals, 0, sizeof(double) * n * P);
+  std::memset(u->uniforms, 0, sizeof(double) * n * NUTS_UNIF_CAP);
+  std::memset(u->draws, 0, sizeof(double) * n * (P + NUTS_DRAW_EXTRA));
+  std::memset(u->metric, 0, sizeof(double) * n * P);
+  std::memset(u->status, 0, sizeof(NutsStatus) * n);
+  return B200GLM_OK;
+}
+
+static int nuts_check(b200glm_handle* h) {
+  if (!h) return B200GLM_INVALID;
+  if (!h->batch || !h->batch->nuts) {
+    h->set_error("b200glm_nuts_reserve was not called");
+    return B200GLM_INVALID;
+  }
+  return B200GLM_OK;
+}
+
+int b200glm_nuts_buffers(b200glm_handle* h, double** normals, double** uniforms, b200glm_nuts_status** status,
+                         double** draws, double** metric) {
+  int rc = nuts_check(h);
+  if (rc) return rc;
+  static_assert(sizeof(b200glm_nuts_status) == sizeof(NutsStatus), "b200glm_nuts_status mirrors NutsStatus");
+  Batch::Nuts* u = h->batch->nuts;
+  if (normals) *normals = u->normals;
+  if (uniforms) *uniforms = u->uniforms;
+  if (status) *status = reinterpret_cast<b200glm_nuts_status*>(u->status);
+  if (draws) *draws = u->draws;
+  if (metric) *metric = u->metric;
+  return B200GLM_OK;
+}
+
+int b200glm_nuts_init_chain(b200glm_handle* h, int32_t chain, const double* q0, const double* inv_metric,
+                            double stepsize) {
+  int rc = nuts_check(h);
+  if (rc) return rc;
+  Batch* b = h->batch;
+  Batch::Nuts* u = b->nuts;
+  if (chain < 0 || chain >= u->n_chains || !q0 || !inv_metric) {
+    h->set_error("b200glm_nuts_init_chain: chain out of range or null pointer");
+    return B200GLM_INVALID;
+  }
+  std::lock_guard<std::mutex> lk(b->mu);
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  const size_t P = h->P;
+  std::memcpy(u->normals + (size_t)chain * P, q0, sizeof(double) * P);        // staged in the chain's own rows
+  std::memcpy(u->metric + (size_t)chain * P, inv_metric, sizeof(double) * P);
+  NutsDeviceParams p = nuts_params(h);
+  p.init_chain = chain;
+  p.stepsize = stepsize;
+  nuts_init_kernel<<<1, 32, 0, b->stream>>>(p);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaStreamSynchronize(b->stream));
+  return B200GLM_OK;
+}
+
+int b200glm_nuts_round(b200glm_handle* h, int32_t n, const int32_t* chains) {
+  int rc = nuts_check(h);
+  if (rc) return rc;
+  rc = batch_check(h, n);
+  if (rc) return rc;
+  Batch* b = h->batch;
+  Batch::Nuts* u = b->nuts;
+  if (!chains) {
+    h->set_error("null pointer argument");
+    return B200GLM_INVALID;
+  }
+  std::lock_guard<std::mutex> lk(b->mu);
+  CUDA_TRY(h, cudaSetDevice(h->d.device));
+  bool any_begin = false;
+  for (int i = 0; i < n; ++i) {
+    if (chains[i] < 0 || chains[i] >= u->n_chains) {
+      h->set_error("chain out of range");
+      return B200GLM_INVALID;
+    }
+    any_begin = any_begin || u->status[chains[i]].need_normals != 0;   // the status of the previous round (pinned)
+  }
+  // the lane list only changes when a chain finishes: upload it then (the previous round has completed, so the
+  // pinned staging block is free)
+  if ((int)u->lanes_h.size() != n || std::memcmp(u->lanes_h.data(), chains, sizeof(int32_t) * n) != 0) {
+    u->lanes_h.assign(chains, chains + n);
+    std::memcpy(b->h_pin_i, chains, sizeof(int32_t) * n);
+    CUDA_TRY(h, cudaMemcpyAsync(u->lanes_d, b->h_pin_i, sizeof(int32_t) * n, cudaMemcpyHostToDevice, b->stream));
+  }
+  NutsDeviceParams p = nuts_params(h);
+  p.n_lanes = n;
+  p.lanes = u->lanes_d;
+  if (any_begin) {   // chains that were waiting for normal variates: the caller has supplied them
+    nuts_begin_kernel<<<(n + 7) / 8, 256, 0, b->stream>>>(p);
+    h->launches++;
+  }
+  rc = enqueue_batched(h, n, MODE_LEAPFROG, 1, 1, u->lanes_d, u->eps_c, 0.0, false, true);
+  if (rc) return rc;
+  nuts_step_kernel<<<(n + 7) / 8, 256, 0, b->stream>>>(p);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaStreamSynchronize(b->stream));
+  return B200GLM_OK;
+}
 
 int b200glm_append_rows(b200glm_handle* h, int64_t n, const double* X, int64_t ldx, const int32_t* y_int,
                         const double* y_real, const int32_t* trials) {

@@ -338,6 +338,7 @@ struct BatchedStepParams {
   int mode;                 // MODE_THETA: theta_in -> result; MODE_LEAPFROG: chain state advanced
   const int32_t* chains;    // [n] chain slot of lane i (device); NULL = identity
   const double* eps;        // [n] per-lane step size (device); NULL = eps_scalar
+  int eps_by_chain;         // eps is indexed by chain slot, not by lane (device-side NUTS: the state machine sets it)
   double eps_scalar;
   const double* theta_in;   // MODE_THETA: [n][P] chain-major
   double *Q, *Pm, *Gd, *V, *IM;   // chain state [P][ld_state] (V: [ld_state])
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(256) batched_begin_kernel(const BatchedStepPar
     if (i < p.n) {
       if (p.mode == MODE_LEAPFROG) {
         const int c = p.chains ? p.chains[i] : i;
-        const double eps = p.eps ? p.eps[i] : p.eps_scalar;
+        const double eps = p.eps ? p.eps[p.eps_by_chain ? c : i] : p.eps_scalar;
         const size_t o = (size_t)k * p.ld_state + c;
         ph = p.Pm[o] - (0.5 * eps) * p.Gd[o];
         th = p.Q[o] + eps * (p.IM[o] * ph);
@@ -514,7 +515,7 @@ __global__ void __launch_bounds__(256) batched_finish_kernel(const BatchedStepPa
   // ---- end_update_p + write-back (expl_leapfrog.hpp:28-32; base_hamiltonian.hpp:64-69) ----
   const bool domain = sh_dom[lane] != 0.0;
   const int c = p.chains ? p.chains[i] : i;
-  const double eps = p.eps ? p.eps[i] : p.eps_scalar;
+  const double eps = p.eps ? p.eps[p.eps_by_chain ? c : i] : p.eps_scalar;
   const double he = 0.5 * eps;
   double* so = p.state_out ? p.state_out + (size_t)i * (3 * P + 1) : nullptr;
   for (int k = w; k < P; k += 8) {

@@ -234,6 +234,27 @@ class StanGLM:
                         ["<=2", "<=16", "<=32", "<=64", "<=128", "<=256", "<=512", ">512"])})
 
 
+    def nuts_device(self, num_chains=4, seed=1, init_chain_id=1, init_radius=2.0, num_warmup=1000, num_samples=1000,
+                    stepsize=1.0, max_depth=10, delta=0.8):
+        """b200::hmc_nuts_diag_e_adapt_device: the NUTS transition (iterative build_tree, U-turn checks, multinomial
+        sampling) and the adaptation (dual averaging, Welford metric windows, init_stepsize) run per chain on the
+        device right behind the batched leapfrog; the host keeps the chains' boost engines and collects the draws."""
+        W = 7 + self.P
+        draws = np.empty((num_chains, num_warmup + num_samples, W))
+        step, inv_metric = np.empty(num_chains), np.empty((num_chains, self.P))
+        warm_lf, wall, err = np.empty(num_chains), C.c_double(), C.create_string_buffer(4096)
+        stats = (C.c_long * 10)()
+        rc = self.L.b200stan_nuts_device(self.h, num_chains, C.c_uint(seed), C.c_uint(init_chain_id),
+                                         C.c_double(init_radius), num_warmup, num_samples, C.c_double(stepsize),
+                                         max_depth, C.c_double(delta), _dp(draws), _dp(step), _dp(inv_metric),
+                                         _dp(warm_lf), C.byref(wall), stats, err, 4096)
+        if rc:
+            self._raise(rc, err)
+        return dict(draws=draws[:, num_warmup:, :], warmup_draws=draws[:, :num_warmup, :], stepsize=step,
+                    inv_metric=inv_metric, warm_leapfrogs=warm_lf, wall=wall.value, rounds=int(stats[0]),
+                    lanes=int(stats[1]), uniforms=int(stats[2]), normal_vectors=int(stats[3]))
+
+
 class FuncGLM:
     """b200::glm_data + the stan::math overloads of b200/glm_functions.hpp (function-level binding),
     exercised as one node of a reverse-mode tape: f = scale * glm_lpmf(...) + 0.5 * sum(beta^2)."""

@@ -114,6 +114,8 @@ def test_desc_struct_layout_matches_the_header(tmp_path):
     if not cc:
         pytest.skip("no C compiler")
     checks = (("b200glm_desc", os.path.join(ROOT, "include", "b200glm.h"), _capi.Desc),
+              ("b200glm_nuts_config", os.path.join(ROOT, "include", "b200glm.h"), _capi.NutsConfig),
+              ("b200glm_nuts_status", os.path.join(ROOT, "include", "b200glm.h"), _capi.NutsStatus),
               ("glm_spec", os.path.join(ROOT, "oracle", "glm_oracle.h"), GlmSpec))
     for struct, header, mirror in checks:
         fields = [f[0] for f in mirror._fields_]
