@@ -571,20 +571,42 @@ def ess_record(args, torch, dist, dev, rank, world, local_rank):
         t = torch.tensor([wall], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         wall = float(t.item())
+    # second arm, unsharded handles only: the same chains (same seeds) through b200::hmc_nuts_diag_e_adapt_device -- the
+    # chains advance TOGETHER, one pass over X per leapfrog of all of them (batched fp64 DMMA kernel, row-split variant
+    # for <= 16 lanes), tree building and adaptation on the device
+    dres, derr = None, None
+    if world == 1:
+        try:
+            dres = sm.nuts_device(num_chains=args.ess_chains, seed=4711, num_warmup=it, num_samples=it, delta=0.8)
+        except Exception as e:   # a shape outside the batched kernel (K > 208): reported, not fatal
+            derr = str(e)[:200]
     sm.close()
     if rank != 0:
         return None
+
+    def arm(r, wall_s, n_grad):
+        d = r["draws"]
+        P = d.shape[2] - 7
+        ess = [stan_service.diagnostic("ess", d[:, :, 7 + k].T) for k in range(P)]
+        rhat = [stan_service.diagnostic("rhat", d[:, :, 7 + k].T) for k in range(P)]
+        return {"chains": args.ess_chains, "iters": f"{it}+{it}", "wall_s": wall_s, "grad_evals": n_grad,
+                "grad_evals_per_s": n_grad / wall_s, "ess_min": float(np.min(ess)), "ess_median": float(np.median(ess)),
+                "ess_min_per_s": float(np.min(ess)) / wall_s, "rhat_max": float(np.max(rhat)),
+                "mean_treedepth": float(d[:, :, 3].mean()), "divergent": int(d[:, :, 5].sum()),
+                "stepsize": [float(v) for v in r["stepsize"]]}
     d = res["draws"]
-    P = d.shape[2] - 7
-    ess = [stan_service.diagnostic("ess", d[:, :, 7 + k].T) for k in range(P)]
-    rhat = [stan_service.diagnostic("rhat", d[:, :, 7 + k].T) for k in range(P)]
-    n_grad = float(d[:, :, 4].sum() + res["warm_leapfrogs"].sum() + 2 * it * args.ess_chains)
-    return {"b200": {"chains": args.ess_chains, "iters": f"{it}+{it}", "wall_s": wall, "grad_evals": n_grad,
-                     "grad_evals_per_s": n_grad / wall, "ess_min": float(np.min(ess)), "ess_median": float(np.median(ess)),
-                     "ess_min_per_s": float(np.min(ess)) / wall, "rhat_max": float(np.max(rhat)),
-                     "mean_treedepth": float(d[:, :, 3].mean()), "divergent": int(d[:, :, 5].sum()),
-                     "stepsize": [float(v) for v in res["stepsize"]]},
-            "service": "stan::services::sample::hmc_nuts_diag_e_adapt (unmodified) on b200::glm_model, chains sequential"}
+    out = {"b200": arm(res, wall, float(d[:, :, 4].sum() + res["warm_leapfrogs"].sum() + 2 * it * args.ess_chains)),
+           "service": "stan::services::sample::hmc_nuts_diag_e_adapt (unmodified) on b200::glm_model, chains sequential"}
+    if dres is not None:
+        out["b200_device_driver"] = dict(
+            arm(dres, dres["wall"], float(dres["lanes"])), rounds=dres["rounds"],
+            service="b200::hmc_nuts_diag_e_adapt_device: same seeds, the chains advance together (one pass over X per "
+                    "leapfrog of all chains), NUTS transition and adaptation on the device")
+        out["b200_device_driver"]["first_draws_max_abs_diff_vs_service"] = float(
+            np.max(np.abs(dres["warmup_draws"][:, :3, 7:] - res["warmup_draws"][:, :3, 7:])))
+    elif derr:
+        out["b200_device_driver"] = {"unavailable": derr}
+    return out
 
 
 def ess_config1_record():

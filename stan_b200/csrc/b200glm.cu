@@ -728,6 +728,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   h->stage_a = (d.G > 0 && d.G <= SMEM_A_MAX_GROUPS) ? 1 : 0;
   // on-chip chain state for the fused epilogue (theta, half-updated momentum, old gradient, likelihood sums)
   h->state_smem = (size_t)state_smem_doubles(P) * 8 <= 49152 ? 1 : 0;
+  if (std::getenv("B200GLM_NO_STATE_SMEM")) h->state_smem = 0;   // A/B runs
   int P_state = h->state_smem ? P : 0;
   const size_t max_dyn = (size_t)prop.sharedMemPerBlockOptin - 1024;  // static scratch + slack
   // narrow kernel: ring stages for the handle's current (stage_a, state_smem, group_fused / Gcs); called again after the
