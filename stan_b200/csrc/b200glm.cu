@@ -20,6 +20,7 @@
 
 #include "glm_kernels.cuh"
 #include "glm_wide_kernel.cuh"
+#include "glm_multi_kernel.cuh"
 #include "nuts_kernels.cuh"
 #include "glm_batched_kernel.cuh"
 #include "glm_class_kernel.cuh"
@@ -98,6 +99,8 @@ struct Batch {
   size_t smem = 0;
   int rs_pairs = 0, rs_S = 0;   // row-split variant (<= 16 lanes): active warp pairs, ring stages per pair
   size_t rs_smem = 0;
+  int mu_cpl = 0, mu_S = 0;     // few-chain FMA kernel (<= 4 lanes, K <= 128; glm_multi_kernel.cuh): 0 = not available
+  size_t mu_smem = 0;
   cudaStream_t stream = nullptr;
   double *Q = nullptr, *Pm = nullptr, *Gd = nullptr, *V = nullptr, *IM = nullptr;
   double *theta_c = nullptr, *p_half = nullptr, *partials = nullptr, *reduced = nullptr, *result = nullptr,
@@ -166,7 +169,7 @@ struct b200glm_handle {
   long long rows_appended = 0;
   double bad_count = 0.0;
   int pdl_prefetch = 2;     // B200GLM_PDL_PREFETCH=<stages> (A/B runs); see the TMA producer in glm_kernels.cuh
-  int wide_producer = -1;   // -1 = chosen at create from the ring depth; B200GLM_WIDE_PRODUCER=single|lanes|poll (A/B runs); see the TMA producer in glm_wide_kernel.cuh
+  int wide_producer = -1;   // -1 = chosen at create from the ring depth; B200GLM_WIDE_PRODUCER=single|lanes (A/B runs); see the TMA producer in glm_wide_kernel.cuh
   bool tl_repeat = false;   // B200GLM_TL_REPEAT=1 (timeline runs only): the last CTA sums the partial rows twice
   bool inline_theta = true; // B200GLM_NO_INLINE_THETA=1: always upload theta with a host-to-device copy (A/B runs)
   bool host_mirror = true;  // B200GLM_NO_HOST_MIRROR=1: fetch results with a device-to-host copy + stream sync (A/B runs)
@@ -695,7 +698,7 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
   if (const char* e = std::getenv("B200GLM_NO_PDL")) h->pdl = !(e[0] == '1');
   if (const char* e = std::getenv("B200GLM_PDL_PREFETCH")) h->pdl_prefetch = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("B200GLM_TL_REPEAT")) h->tl_repeat = (e[0] == '1');
-  if (const char* e = std::getenv("B200GLM_WIDE_PRODUCER")) h->wide_producer = e[0] == 's' ? 0 : (e[0] == 'l' ? 1 : 2);
+  if (const char* e = std::getenv("B200GLM_WIDE_PRODUCER")) h->wide_producer = e[0] == 's' ? 0 : 1;
   if (const char* e = std::getenv("B200GLM_NO_INLINE_THETA")) h->inline_theta = !(e[0] == '1');
   if (const char* e = std::getenv("B200GLM_NO_HOST_MIRROR")) h->host_mirror = !(e[0] == '1');
   h->P = (d.G > 0 ? 2 + d.G : 1) + d.K + (fam_has_scale(d.family) ? 1 : 0);
@@ -809,11 +812,13 @@ int b200glm_create(const b200glm_desc* desc, b200glm_handle** out) {
     const size_t slot_bytes = (size_t)h->Kc * WR * 8;
     size_t fixed = 0;
     int T = 0;
-    for (;;) {   // the ring comes first: drop the on-chip state if two row panels would not fit with it
+    for (;;) {   // the ring comes first: drop the on-chip state if THREE row panels would not fit with it (the two
+                 // resident panels + a whole panel of look-ahead: what the lane-parallel TMA producer needs; K = 1000:
+                 // T = 23 -> 27 slots, 1.35 -> 1.14 ms per gradient at N = 1M)
       fixed = wide_fixed_doubles(WR, h->J, h->Kc, d.G, h->stage_a, P_state) * 8;
       T = fixed < max_dyn ? (int)((max_dyn - fixed) / (slot_bytes + 16)) : 0;
       if (T > WIDE_MAX_SLOTS) T = WIDE_MAX_SLOTS;
-      if (T >= 2 * h->J || !P_state) break;
+      if (T >= 3 * h->J || !P_state) break;
       P_state = 0;
       h->state_smem = 0;
     }
@@ -1312,6 +1317,26 @@ batched_fn pick_batched(int family, int mbh, bool row_split = false) {
   return row_split ? pick_batched_rs<true>(family, mbh) : pick_batched_rs<false>(family, mbh);
 }
 
+// few-chain FMA kernel (glm_multi_kernel.cuh): 4 chains per pass, column slots CPL in {4, 8, 13, 16}
+template <int FAMILY>
+batched_fn pick_multi_cpl(int cpl) {
+  switch (cpl) {
+    case 4: return glm_multi_kernel<FAMILY, 4, 4>;
+    case 8: return glm_multi_kernel<FAMILY, 8, 4>;
+    case 13: return glm_multi_kernel<FAMILY, 13, 4>;
+    case 16: return glm_multi_kernel<FAMILY, 16, 4>;
+  }
+  return nullptr;
+}
+batched_fn pick_multi(int family, int cpl) {
+  switch (family) {
+    case FAM_BERNOULLI_LOGIT: return pick_multi_cpl<FAM_BERNOULLI_LOGIT>(cpl);
+    case FAM_POISSON_LOG: return pick_multi_cpl<FAM_POISSON_LOG>(cpl);
+    case FAM_NORMAL_ID: return pick_multi_cpl<FAM_NORMAL_ID>(cpl);
+  }
+  return nullptr;
+}
+
 int batch_check(b200glm_handle* h, int n) {
   if (!h) return B200GLM_INVALID;
   if (!h->batch) {
@@ -1332,6 +1357,7 @@ int enqueue_batched(b200glm_handle* h, int n, int mode, int propto, int jacobian
   const int NCB = (n + BATCH_CB - 1) / BATCH_CB;
   int NS = std::max(1, b->sms / NCB);
   if ((long long)NS > std::max<long long>(h->n_panels, 1)) NS = (int)std::max<long long>(h->n_panels, 1);
+  const bool multi = n <= 4 && b->mu_cpl > 0;   // a few chains: the FMA kernel (one CTA per SM, every CTA a row slice)
   BatchedStepParams sp;
   std::memset(&sp, 0, sizeof(sp));
   sp.n = n;
@@ -1375,8 +1401,8 @@ int enqueue_batched(b200glm_handle* h, int n, int mode, int propto, int jacobian
   bp.P = h->P;
   bp.off_beta = h->off_beta;
   bp.family = h->d.family;
-  const bool row_split = n <= 16 && b->rs_pairs >= 2;
-  bp.n_stages = row_split ? b->rs_S : b->S;
+  const bool row_split = !multi && n <= 16 && b->rs_pairs >= 2;
+  bp.n_stages = multi ? b->mu_S : (row_split ? b->rs_S : b->S);
   bp.pairs = row_split ? b->rs_pairs : 4;
   sp.fold = row_split ? b->rs_pairs : 0;
   bp.NCB = NCB;
@@ -1385,7 +1411,10 @@ int enqueue_batched(b200glm_handle* h, int n, int mode, int propto, int jacobian
   bp.n_lanes = n;
   bp.theta_c = b->theta_c;
   bp.partials = b->partials;
-  pick_batched(h->d.family, b->mbh, row_split)<<<NCB * NS, BATCH_THREADS, row_split ? b->rs_smem : b->smem, b->stream>>>(bp);
+  if (multi)
+    pick_multi(h->d.family, b->mu_cpl)<<<NS, MULTI_THREADS, b->mu_smem, b->stream>>>(bp);
+  else
+    pick_batched(h->d.family, b->mbh, row_split)<<<NCB * NS, BATCH_THREADS, row_split ? b->rs_smem : b->smem, b->stream>>>(bp);
   batched_reduce_kernel<<<(h->d.K + 2) * NCB, BATCH_CB, 0, b->stream>>>(sp);
   batched_finish_kernel<<<(n + 31) / 32, 256, 0, b->stream>>>(sp);
   h->launches += 4;
@@ -1463,6 +1492,25 @@ int b200glm_batch_reserve(b200glm_handle* h, int32_t max_chains) {
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->rs_smem));
     } else {
       b->rs_pairs = 0;
+    }
+  }
+  // few-chain FMA kernel: K <= 128, as many ring stages as fit (at least 8: one per consumer warp)
+  if (h->d.K >= 1 && h->d.K <= MULTI_MAX_K && !std::getenv("B200GLM_NO_MULTI")) {
+    const int need = (h->d.K + 7) / 8;
+    for (int c : {4, 8, 13, 16})
+      if (c >= need) {
+        b->mu_cpl = c;
+        break;
+      }
+    int S2 = 16;
+    while (S2 > 0 && multi_smem_bytes(h->d.K, h->C, S2, 4) > max_dyn) --S2;
+    if (S2 >= 4 && b->mu_cpl && (size_t)S2 * h->C * 32 >= (size_t)NUM_CONSUMER_WARPS * (((h->d.K + 7) & ~7) + 2) * 4) {
+      b->mu_S = S2;
+      b->mu_smem = multi_smem_bytes(h->d.K, h->C, S2, 4);
+      CUDA_TRY(h, cudaFuncSetAttribute(pick_multi(h->d.family, b->mu_cpl), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)b->mu_smem));
+    } else {
+      b->mu_cpl = 0;
     }
   }
   const size_t P = h->P, ld = b->ld;

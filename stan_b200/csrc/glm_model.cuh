@@ -105,8 +105,7 @@ struct KernelParams {
   double* theta_used;       // P doubles: the theta this launch evaluated (q_new in leapfrog mode)
   int pdl_prefetch;         // ring stages the TMA producer may request before the previous launch has completed
   int tl_repeat;            // measurement only, see cross_cta_reduce_and_finish
-  int wide_producer;        // wide kernel: 0 = one lane issues every bulk copy; lane j streams sub-panel j, 1 = the lanes
-                            // wait for their slots together, 2 = every lane polls its own slot
+  int wide_producer;        // wide kernel: 0 = one lane issues every bulk copy, 1 = lane j streams sub-panel j
   unsigned long long* tl;   // NULL, or the per-phase time stamps of this launch (b200glm_timeline_*): [grid + 1][16]
   // Host-facing calls (b200glm_log_prob_grad, b200glm_leapfrog): the epilogue also writes its outputs straight into
   // pinned host memory -- [result (P + 2)] [state (3P + 1)] [sequence word] -- and the host polls the sequence word,

@@ -246,8 +246,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
     // whatever the consumers did (five pipeline variants within 1 % of 1.347 ms at K = 1000,
     // profiles/r2_wide_variants.txt): ~390 cycles per 8 KB copy = 21 B/cycle/SM = 6.1 TB/s over 148 SMs.
     if (p.wide_producer == 0) {
-      // round 1's producer: one lane walks the ring slot by slot (B200GLM_WIDE_PRODUCER=single, and the default for the
-      // panel heights where the lane-parallel form measured slower)
+      // round 1's producer: one lane walks the ring slot by slot (B200GLM_WIDE_PRODUCER=single; the default only when the
+      // ring cannot hold three row panels)
       if (lane == 0) {
         const uint64_t pol = policy_evict_first();
         int sl = 0;
@@ -271,40 +271,20 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) glm_wide_kernel(const __grid_
       const uint32_t bytes = (uint32_t)min(KC, Cpad - lane * KC) * WR * 8u;
       int sl = lane;                          // ring slot of this lane's next sub-panel (n * J + lane) mod T
       uint32_t round = 0;                     // ... and how often the ring has wrapped for it
-      if (p.wide_producer == 1) {
-        // all lanes wait together: a panel's J copies go out when the LAST of its J slots is free
-        for (long long n = 0; n < n_my; ++n) {
-          const double* src = p.panels + (size_t)(blockIdx.x + n * grid) * Cpad * WR;
-          if (round > 0) mbar_wait(&empty_bar[sl], (round - 1) & 1);
-          mbar_arrive_expect_tx(&full_bar[sl], bytes);
-          tma_load_1d(ring + (size_t)sl * SLOT, src + (size_t)lane * KC * WR, bytes, &full_bar[sl], pol);
-          sl += J;                            // T >= 2 J: at most one wrap
-          if (sl >= T) {
-            sl -= T;
-            ++round;
-          }
-        }
-      } else {
-        // every lane on its own: poll the slot (non-blocking test), copy when it is free.  With fewer than J slots
-        // beyond the two resident panels (T < 3 J, e.g. K = 1000 with the chain state on chip: T = 23, J = 8) the
-        // joint wait above cannot request ANY of panel n + 2 before P2(n) has released its slots -- one DRAM latency
-        // exposed per panel (measured: 1.54 ms against 1.35 ms for the single-lane loop); here the free slots are
-        // requested at once and only the missing one waits.
-        long long n = 0;
-        while (n < n_my) {
-          if (round == 0 || mbar_test(&empty_bar[sl], (round - 1) & 1)) {
-            const double* src = p.panels + (size_t)(blockIdx.x + n * grid) * Cpad * WR;
-            mbar_arrive_expect_tx(&full_bar[sl], bytes);
-            tma_load_1d(ring + (size_t)sl * SLOT, src + (size_t)lane * KC * WR, bytes, &full_bar[sl], pol);
-            sl += J;
-            if (sl >= T) {
-              sl -= T;
-              ++round;
-            }
-            ++n;
-          } else {
-            __nanosleep(64);
-          }
+      // The lanes wait for their slots together: a panel's J copies go out when the last of its J slots is free, so the
+      // ring must hold a whole panel beyond the two resident ones (T >= 3 J; the host drops the on-chip chain state for
+      // that).  With T = 23, J = 8 (K = 1000 with the state on chip) this form ran at 1.53 ms against 1.35 ms for the
+      // single-lane loop; with T = 27 at 1.14 ms = 7.0 TB/s (profiles/r2_wide_variants.txt).  A form in which every lane
+      // polls its own slot (mbarrier.test_wait) measured the same as this one in every shape and was dropped.
+      for (long long n = 0; n < n_my; ++n) {
+        const double* src = p.panels + (size_t)(blockIdx.x + n * grid) * Cpad * WR;
+        if (round > 0) mbar_wait(&empty_bar[sl], (round - 1) & 1);
+        mbar_arrive_expect_tx(&full_bar[sl], bytes);
+        tma_load_1d(ring + (size_t)sl * SLOT, src + (size_t)lane * KC * WR, bytes, &full_bar[sl], pol);
+        sl += J;                            // T >= 2 J: at most one wrap
+        if (sl >= T) {
+          sl -= T;
+          ++round;
         }
       }
     }

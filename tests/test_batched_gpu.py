@@ -192,3 +192,56 @@ def test_batch_workspace_grows_on_a_larger_reservation():
     m.batch_reserve(16)                                    # smaller: keeps the larger workspace
     assert m.log_prob_grad_batched(th)[2].sum() == 0
     m.close()
+
+
+@pytest.mark.parametrize("fam,N,K", [("bernoulli_logit", 9_001, 100), ("normal_id", 6_000, 128), ("poisson_log", 4_000, 17),
+                                     ("bernoulli_logit", 70_000, 33), ("normal_id", 150, 8), ("poisson_log", 31, 3)])
+def test_few_chain_fma_kernel(fam, N, K, monkeypatch):
+    """Batches of <= 4 lanes with K <= 128 run glm_multi_kernel (four chains per pass on the FMA path, X read from
+    shared memory once per phase for all of them): same answers as the oracle, as the DMMA path evaluating the same chains
+    (B200GLM_NO_MULTI=1) to rounding, independent of the lane a chain sits in and of how many lanes there are, and through
+    the leapfrog entry point."""
+    from oracle.oracle import PortOracle
+    d = make_glm_data(fam, N, K)
+    po = PortOracle(fam, d["X"], d["y"])
+    m = GLMModel(fam, d["X"], d["y"])
+    m.batch_reserve(8)
+    monkeypatch.setenv("B200GLM_NO_MULTI", "1")
+    m_dmma = GLMModel(fam, d["X"], d["y"])
+    m_dmma.batch_reserve(8)
+    monkeypatch.delenv("B200GLM_NO_MULTI")
+    rng = np.random.default_rng(8)
+    th = 0.1 * rng.standard_normal((4, m.P))
+    lp4, g4, st = m.log_prob_grad_batched(th)
+    assert not st.any()
+    lpd, gd, _ = m_dmma.log_prob_grad_batched(th)
+    for c in range(4):
+        lp_r, g_r = po.log_prob_grad(th[c])
+        assert rel_err(lp4[c], lp_r) < TOL and rel_err_vec(g4[c], g_r) < TOL, c
+        assert rel_err(lp4[c], lpd[c]) < 1e-12 and rel_err_vec(g4[c], gd[c]) < 1e-12, c
+    for n in (1, 2, 3):                                   # fewer lanes: the same chains, bit for bit
+        lp, g, _ = m.log_prob_grad_batched(th[:n])
+        assert np.array_equal(lp, lp4[:n]) and np.array_equal(g, g4[:n])
+    lp_r4, g_r4, _ = m.log_prob_grad_batched(th[::-1].copy())
+    assert np.array_equal(lp_r4[::-1], lp4) and np.array_equal(g_r4[::-1], g4)
+    for propto, jac in ((0, 1), (1, 0)):
+        lp, g, _ = m.log_prob_grad_batched(th[:3], propto, jac)
+        for c in range(3):
+            lp_r, g_r = po.log_prob_grad(th[c], propto, jac)
+            assert rel_err(lp[c], lp_r) < TOL and rel_err_vec(g[c], g_r) < TOL
+    # three leapfrog steps of 3 chain slots scattered over the 8
+    chains = np.array([6, 1, 4], dtype=np.int32)
+    q, p = th[:3].copy(), rng.standard_normal((3, m.P))
+    im = np.exp(0.3 * rng.standard_normal((3, m.P)))
+    lp, g, _ = m.log_prob_grad_batched(q)
+    m.set_state_batched(q, p, -g, -lp, im, chains)
+    eps = 1e-3 * (1 + rng.random(3))
+    ref = [(q[i], p[i], -g[i], -lp[i]) for i in range(3)]
+    for _ in range(3):
+        qd, pd, gd2, Vd, st = m.leapfrog_batched(eps, chains)
+        ref = [po.leapfrog(eps[i], im[i], *ref[i]) for i in range(3)]
+    for i in range(3):
+        assert rel_err_vec(qd[i], ref[i][0]) < 1e-9 and rel_err_vec(gd2[i], ref[i][2]) < 1e-9
+        assert rel_err(Vd[i], ref[i][3]) < 1e-9
+    m.close()
+    m_dmma.close()
