@@ -209,10 +209,11 @@ void* b200glm_batch_stream(b200glm_handle* h);
  * / multinomial decisions, written into the pinned buffers below in the order the reference draws them; the status
  * says how many uniform variates were consumed.  Host driver: b200::hmc_nuts_diag_e_adapt_device
  * (stan_b200/cpp/b200/device_nuts.hpp), the argument list of ST/services/sample/hmc_nuts_diag_e_adapt.hpp:331-404.
- *   nuts_reserve     batch_reserve(n_chains) + the per-chain tree state ((17 + 5 max_depth) P doubles)
+ *   nuts_reserve     batch_reserve(n_chains) + the per-chain tree state ((19 + 6 max_depth) P doubles)
  *   nuts_buffers     pinned host buffers shared with the kernels: normals [n][P], uniforms [n][64] (a ring indexed
- *                    by the running count), status [n], draws [n][P + 8] (parameters, lp__, accept_stat__, stepsize__,
- *                    treedepth__, n_leapfrog__, divergent__, energy__, iteration), metric [n][P]
+ *                    by the running count), status [n], draws [n][3 P + 8] (parameters, lp__, accept_stat__, stepsize__,
+ *                    treedepth__, n_leapfrog__, divergent__, energy__, iteration, then the selected state's momentum
+ *                    and gradient: the diagnostic writer's columns), metric [n][P]
  *   nuts_init_chain  initial point, diagonal inverse metric, nominal step size of one chain
  *   nuts_round       one round for the listed chains: begin (chains whose normal variates were supplied) ->
  *                    ONE batched leapfrog -> tree / adaptation step; returns when the status is up to date */

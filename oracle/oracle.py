@@ -314,6 +314,20 @@ class RefOracle:
         return dict(draws=draws[:, num_warmup:, :], warmup_draws=draws[:, :num_warmup, :], stepsize=step,
                     inv_metric=inv_metric, rounds=stats[0], lanes=stats[1], uniforms=stats[2], normal_vectors=stats[3])
 
+    def nuts_transcript(self, which, num_chains=2, seed=1, init_chain_id=1, num_warmup=30, num_samples=20, num_thin=1,
+                        save_warmup=True, refresh=0, stepsize=1.0, max_depth=10):
+        """Everything the sample writer (S<chain>|), the diagnostic writer (D<chain>|) and the logger (L|) receive, as
+        lines of text: which = 0 the reference's hmc_nuts_diag_e_adapt (chains one after the other), which = 1 the
+        product's device-NUTS driver on the host backend."""
+        buf = C.create_string_buffer(64 << 20)
+        err = C.create_string_buffer(2048)
+        rc = self.L.ref_glm_nuts_transcript(self.h, int(which), num_chains, C.c_uint(seed), C.c_uint(init_chain_id),
+                                            num_warmup, num_samples, num_thin, int(save_warmup), refresh,
+                                            C.c_double(stepsize), max_depth, buf, C.c_long(len(buf)), err, 2048)
+        if rc:
+            raise OracleError(rc, err.value.decode())
+        return buf.value.decode().splitlines()
+
     # ---- stan::analyze ----
     @classmethod
     def _chains(cls, draws):

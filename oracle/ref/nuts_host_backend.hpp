@@ -67,7 +67,7 @@ struct nuts_host_backend {
       a->assign(PC, 0.0);
     b.V.assign(n, 0.0);
     b.uniforms.assign(static_cast<size_t>(n) * b200glm::NUTS_UNIF_CAP, 0.0);
-    b.draws.assign(static_cast<size_t>(n) * (b.P + b200glm::NUTS_DRAW_EXTRA), 0.0);
+    b.draws.assign(static_cast<size_t>(n) * b200glm::nuts_draw_doubles(b.P), 0.0);
     b.status.assign(n, b200glm::NutsStatus());
     return 0;
   }
@@ -133,7 +133,7 @@ struct nuts_host_backend {
         s.v() = z.V;
         b200glm::nuts_after_leapfrog<LN>(b.cfg, ch, v, s,
                                          b.uniforms.data() + static_cast<size_t>(c) * b200glm::NUTS_UNIF_CAP,
-                                         b.draws.data() + static_cast<size_t>(c) * (b.P + b200glm::NUTS_DRAW_EXTRA),
+                                         b.draws.data() + static_cast<size_t>(c) * b200glm::nuts_draw_doubles(b.P),
                                          b.metric.data() + static_cast<size_t>(c) * b.P);
         b200glm::nuts_publish(ch, b.status[c]);
       }

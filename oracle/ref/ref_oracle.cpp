@@ -319,6 +319,103 @@ int ref_glm_nuts_device_host(void* h, int num_chains, unsigned seed, unsigned in
   return g ? g : rc;
 }
 
+// Transcript of a run: everything the sample writer, the diagnostic writer and the logger receive, as text, for
+//   which = 0: stan::services::sample::hmc_nuts_diag_e_adapt (the reference), which = 1: the product's device-NUTS driver
+// on the host backend -- with the service options the other entry points fix (num_thin, save_warmup, refresh).
+// Lines: "S<chain>|..." sample writer, "D<chain>|..." diagnostic writer, "L|..." logger info.  Numbers with 17 digits.
+namespace {
+struct text_writer : public stan::callbacks::writer {
+  std::string tag;
+  std::string* out = nullptr;
+  std::mutex* mu = nullptr;
+  void put(const std::string& line) {
+    std::lock_guard<std::mutex> g(*mu);
+    *out += tag + "|" + line + "\n";
+  }
+  void operator()(const std::vector<std::string>& n) override {
+    std::string l;
+    for (size_t i = 0; i < n.size(); ++i)
+      l += (i ? "," : "") + n[i];
+    put(l);
+  }
+  void operator()(const std::vector<double>& v) override {
+    std::stringstream ss;
+    ss.precision(17);
+    for (size_t i = 0; i < v.size(); ++i)
+      ss << (i ? "," : "") << v[i];
+    put(ss.str());
+  }
+  void operator()() override { put(""); }
+  void operator()(const std::string& m) override { put("#" + m); }
+};
+struct text_logger : public stan::callbacks::logger {
+  std::string* out = nullptr;
+  std::mutex* mu = nullptr;
+  std::string errors;
+  void info(const std::string& m) override {
+    std::lock_guard<std::mutex> g(*mu);
+    *out += "L|" + m + "\n";
+  }
+  void info(const std::stringstream& m) override { info(m.str()); }
+  void error(const std::string& m) override {
+    std::lock_guard<std::mutex> g(*mu);
+    errors += m + "\n";
+  }
+  void error(const std::stringstream& m) override { error(m.str()); }
+};
+}  // namespace
+
+int ref_glm_nuts_transcript(void* h, int which, int num_chains, unsigned seed, unsigned init_chain_id, int num_warmup,
+                            int num_samples, int num_thin, int save_warmup, int refresh, double stepsize, int max_depth,
+                            char* out, long out_len, char* err, int errlen) {
+  auto& m = *static_cast<ref_glm_model*>(h);
+  const int P = static_cast<int>(m.num_params_r());
+  int rc = 0;
+  int g = guarded(err, errlen, [&] {
+    std::vector<std::shared_ptr<stan::io::var_context>> inits, metrics;
+    for (int c = 0; c < num_chains; ++c) {
+      inits.emplace_back(std::make_shared<stan::io::empty_var_context>());
+      metrics.emplace_back(std::make_shared<stan::io::array_var_context>(
+          stan::services::util::create_unit_e_diag_inv_metric(P)));
+    }
+    stan::callbacks::interrupt interrupt;
+    std::string text;
+    std::mutex mu;
+    text_logger logger;
+    logger.out = &text;
+    logger.mu = &mu;
+    std::vector<stan::callbacks::writer> init_w(num_chains);
+    std::vector<text_writer> sample_w(num_chains), diag_w(num_chains);
+    for (int c = 0; c < num_chains; ++c) {
+      sample_w[c].tag = "S" + std::to_string(c);
+      diag_w[c].tag = "D" + std::to_string(c);
+      sample_w[c].out = diag_w[c].out = &text;
+      sample_w[c].mu = diag_w[c].mu = &mu;
+    }
+    std::vector<mem_metric_writer> metric_w(num_chains);
+    if (which == 0) {
+      stan::math::init_threadpool_tbb(1);
+      rc = stan::services::sample::hmc_nuts_diag_e_adapt(   // the multi-chain overload (:331-404)
+          m, num_chains, inits, metrics, seed, init_chain_id, 2.0, num_warmup, num_samples, num_thin, save_warmup != 0,
+          refresh, stepsize, 0.0, max_depth, 0.8, 0.05, 0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w,
+          diag_w, metric_w);
+    } else {
+      oracle_ref::nuts_host_backend<ref_glm_model> backend(m);
+      b200::nuts_backend be = backend.table();
+      rc = b200::hmc_nuts_diag_e_adapt_device(m, be, num_chains, inits, metrics, seed, init_chain_id, 2.0, num_warmup,
+                                              num_samples, num_thin, save_warmup != 0, refresh, stepsize, 0.0, max_depth,
+                                              0.8, 0.05, 0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w,
+                                              diag_w, metric_w);
+    }
+    if (rc != 0)
+      throw std::runtime_error("sampler rc=" + std::to_string(rc) + ": " + logger.errors);
+    if (static_cast<long>(text.size()) + 1 > out_len)
+      throw std::runtime_error("transcript buffer too small");
+    std::memcpy(out, text.c_str(), text.size() + 1);
+  });
+  return g ? g : rc;
+}
+
 // draws: column-major n_draws x n_chains (one parameter)
 // The bare reference GLM densities (function level), for the parity test of b200glm_glm_lpmf:
 //   stan::math::{bernoulli_logit,poisson_log,normal_id,binomial_logit,neg_binomial_2_log}_glm_lp*f<propto>(

@@ -12,8 +12,9 @@
 // direction / multinomial decision one uniform variate, produced in the reference's order and handed to the device
 // through pinned memory; the device reports how many it consumed and the engine is put back to exactly that point.  A
 // chain therefore gives the reference's draws for the same seed (up to the summation order of dot products).
-// Per round the host reads 40 bytes of status per chain, and P + 8 doubles for a chain that finished a transition (the
-// draw); q, p, g never leave the device.
+// Per round the host reads 40 bytes of status per chain, and 3 P + 8 doubles for a chain that finished a transition (the
+// draw, and the selected state's momentum and gradient for the diagnostic writer); inside a trajectory q, p, g never leave
+// the device.
 //
 // The backend is a table of C functions (in the product: b200glm_nuts_* of libb200glm.so; tests substitute a host build of
 // the same state machine to check this driver against the reference without a GPU).
@@ -87,7 +88,7 @@ struct window_probe : stan::mcmc::windowed_adaptation {
 // ps_point::get_param_names / get_params); the values are those of the chain's latest draw
 class device_sampler_view : public stan::mcmc::base_mcmc {
  public:
-  explicit device_sampler_view(int P) : q(P, 0.0), g(P, 0.0), inv_metric(P, 1.0) {}
+  explicit device_sampler_view(int P) : q(P, 0.0), p(P, 0.0), g(P, 0.0), inv_metric(P, 1.0) {}
   stan::mcmc::sample transition(stan::mcmc::sample& s, stan::callbacks::logger&) override { return s; }
   void get_sampler_param_names(std::vector<std::string>& names) override {
     for (const char* n : {"stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__"})
@@ -115,14 +116,13 @@ class device_sampler_view : public stan::mcmc::base_mcmc {
     for (auto& n : model_names)
       names.emplace_back("g_" + n);
   }
-  // the momentum of the selected state stays on the device: reported as 0
   void get_sampler_diagnostics(std::vector<double>& values) override {
     values.insert(values.end(), q.begin(), q.end());
-    values.insert(values.end(), q.size(), 0.0);
+    values.insert(values.end(), p.begin(), p.end());
     values.insert(values.end(), g.begin(), g.end());
   }
   double stepsize = 0, treedepth = 0, n_leapfrog = 0, divergent = 0, energy = 0, nom_stepsize = 0;
-  std::vector<double> q, g, inv_metric;
+  std::vector<double> q, p, g, inv_metric;
 };
 
 // base_hmc::write_sampler_state_struct
@@ -239,7 +239,7 @@ int hmc_nuts_diag_e_adapt_device(Model& model, nuts_backend& be, size_t num_chai
     writer[i]->write_diagnostic_names(s, *view[i], model);
   }
 
-  const int DW = P + kNutsDrawExtra;
+  const int DW = 3 * P + kNutsDrawExtra;   // nuts_draw_doubles(P): q, the 8 scalars, p, g
   const int total = num_warmup + num_samples;
   std::vector<std::int32_t> lanes;
   lanes.reserve(C);
@@ -286,6 +286,8 @@ int hmc_nuts_diag_e_adapt_device(Model& model, nuts_backend& be, size_t num_chai
         h.seen_iter = st.iter;
         detail::device_sampler_view& v = *view[i];
         v.q.assign(d, d + P);
+        v.p.assign(d + P + kNutsDrawExtra, d + 2 * P + kNutsDrawExtra);
+        v.g.assign(d + 2 * P + kNutsDrawExtra, d + 3 * P + kNutsDrawExtra);
         v.stepsize = d[P + 2];
         v.treedepth = d[P + 3];
         v.n_leapfrog = d[P + 4];

@@ -1738,12 +1738,12 @@ int b200glm_nuts_reserve(b200glm_handle* h, int32_t n_chains, const b200glm_nuts
   CUDA_TRY(h, cudaMalloc(&u->lanes_d, sizeof(int32_t) * b->ld));
   CUDA_TRY(h, cudaMallocHost(&u->normals, sizeof(double) * n * P));
   CUDA_TRY(h, cudaMallocHost(&u->uniforms, sizeof(double) * n * NUTS_UNIF_CAP));
-  CUDA_TRY(h, cudaMallocHost(&u->draws, sizeof(double) * n * (P + NUTS_DRAW_EXTRA)));
+  CUDA_TRY(h, cudaMallocHost(&u->draws, sizeof(double) * n * nuts_draw_doubles((int)P)));
   CUDA_TRY(h, cudaMallocHost(&u->metric, sizeof(double) * n * P));
   CUDA_TRY(h, cudaMallocHost(&u->status, sizeof(NutsStatus) * n));
   std::memset(u->normals, 0, sizeof(double) * n * P);
   std::memset(u->uniforms, 0, sizeof(double) * n * NUTS_UNIF_CAP);
-  std::memset(u->draws, 0, sizeof(double) * n * (P + NUTS_DRAW_EXTRA));
+  std::memset(u->draws, 0, sizeof(double) * n * nuts_draw_doubles((int)P));
   std::memset(u->metric, 0, sizeof(double) * n * P);
   std::memset(u->status, 0, sizeof(NutsStatus) * n);
   return B200GLM_OK;

@@ -32,7 +32,7 @@ struct NutsDeviceParams {
   const double* normals;      // pinned [C][P]
   const double* unif;         // pinned [C][NUTS_UNIF_CAP]
   NutsStatus* status;         // pinned [C]
-  double* draws;              // pinned [C][P + NUTS_DRAW_EXTRA]
+  double* draws;              // pinned [C][nuts_draw_doubles(P)]
   double* metric;             // pinned [C][P]
   double stepsize;            // nuts_init_kernel only
   int init_chain;             // nuts_init_kernel only
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) nuts_step_kernel(const NutsDeviceParams p
   const int c = p.lanes[i], P = p.cfg.P;
   NutsChain ch = p.chains[c];
   nuts_after_leapfrog<NutsWarp>(p.cfg, ch, p.vec + (size_t)c * p.vstride, nuts_slot(p, c),
-                                p.unif + (size_t)c * NUTS_UNIF_CAP, p.draws + (size_t)c * (P + NUTS_DRAW_EXTRA),
+                                p.unif + (size_t)c * NUTS_UNIF_CAP, p.draws + (size_t)c * nuts_draw_doubles(P),
                                 p.metric + (size_t)c * P);
   __syncwarp();
   if ((threadIdx.x & 31) == 0) {

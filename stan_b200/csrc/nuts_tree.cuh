@@ -13,7 +13,7 @@
 // A chain advances by ROUNDS: [nuts_begin: start a transition or an init_stepsize iteration when the host has supplied the
 // normal variates it needs] -> one leapfrog step of every live chain (the batched gradient kernels) -> [nuts_after_leapfrog:
 // everything the reference does between two evolve() calls].  The leapfrog state (q, p, g, V, inverse metric) is the batched
-// kernels' feature-major chain slot; the tree state lives in a chain-major block of (17 + 5 max_depth) P doubles.
+// kernels' feature-major chain slot; the tree state lives in a chain-major block of (19 + 6 max_depth) P doubles.
 // Randomness is the reference's: P normal variates per momentum refresh and the uniform variates of the direction /
 // multinomial draws are produced by the host from the chain's own boost engine IN THE REFERENCE'S ORDER and consumed here
 // in that order, so a chain reproduces the reference's draws for the same seed (up to summation order in dot products).
@@ -37,7 +37,9 @@ namespace b200glm {
 constexpr int NUTS_DEPTH_CAP = 16;    // max_depth <= 16
 constexpr int NUTS_UNIF_CAP = 64;     // per-chain ring of uniform variates (a round consumes at most max_depth + 3)
 constexpr int NUTS_DRAW_EXTRA = 8;    // after the P parameters: lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__,
-                                      // divergent__, energy__, spare
+                                      // divergent__, energy__, iteration; then the selected state's momentum (P) and
+                                      // gradient (P) for the diagnostic writer (ps_point::get_params)
+NT_HD size_t nuts_draw_doubles(int P) { return (size_t)3 * P + NUTS_DRAW_EXTRA; }
 
 enum { NPH_IDLE = 0, NPH_INIT_GRAD = 1, NPH_SS_FIRST = 2, NPH_SS_LOOP = 3, NPH_TREE = 4, NPH_DONE = 5, NPH_FAILED = 6 };
 enum { NFAIL_NONE = 0, NFAIL_IMPROPER = 1, NFAIL_NO_STEPSIZE = 2, NFAIL_METRIC_OVERFLOW = 3 };
@@ -60,13 +62,14 @@ enum {
   NV_RHO = 6,     // rho of the whole trajectory
   NV_QS = 7,      // current sample z_sample.q (between transitions: the chain's position)
   NV_GS = 8,      // ... its gradient
-  NV_IM = 9,      // chain-major copy of the diagonal inverse metric
-  NV_WM = 10,     // Welford mean
-  NV_WM2 = 11,    // Welford sum of squares
-  NV_CUR = 12,    // summary of the subtree being completed: rho, p_beg, p_end, q_propose, g_propose
-  NV_STACK = 17   // [level] summaries of completed subtrees waiting for their sibling
+  NV_PS = 9,      // ... its momentum (only reported: the diagnostic writer's p columns)
+  NV_IM = 10,     // chain-major copy of the diagonal inverse metric
+  NV_WM = 11,     // Welford mean
+  NV_WM2 = 12,    // Welford sum of squares
+  NV_CUR = 13,    // summary of the subtree being completed: rho, p_beg, p_end, z_propose (q, g, p)
+  NV_STACK = 19   // [level] summaries of completed subtrees waiting for their sibling
 };
-enum { NS_RHO = 0, NS_PBEG = 1, NS_PEND = 2, NS_QP = 3, NS_GP = 4, NS_VECS = 5 };
+enum { NS_RHO = 0, NS_PBEG = 1, NS_PEND = 2, NS_QP = 3, NS_GP = 4, NS_PP = 5, NS_VECS = 6 };
 NT_HD size_t nuts_vec_doubles(int P, int max_depth) { return (size_t)(NV_STACK + NS_VECS * max_depth) * (size_t)P; }
 
 struct NutsChain {
@@ -214,6 +217,7 @@ NT_HD void nuts_begin(const NutsConfig& cfg, NutsChain& ch, double* v, const Nut
       ze[(size_t)4 * P + k] = p;
       ze[(size_t)5 * P + k] = g;
       v[(size_t)NV_RHO * P + k] = p;
+      v[(size_t)NV_PS * P + k] = p;
     }
   }
   t = 0.5 * LN::sum(t);
@@ -280,14 +284,18 @@ NT_HD void nuts_copy(int P, double* dst, const double* src, int n_vecs) {
 }
 
 // End of a transition (base_nuts.hpp:193-203) and what adapt_diag_e_nuts::transition does after it (:29-43).
-// draw: P + NUTS_DRAW_EXTRA doubles; metric_out: P doubles, rewritten when a window ends.
+// draw: nuts_draw_doubles(P) doubles; metric_out: P doubles, rewritten when a window ends.
 template <class LN>
 NT_HD void nuts_end_transition(const NutsConfig& cfg, NutsChain& ch, double* v, const NutsSlot& s, double* draw,
                                double* metric_out) {
   const int P = cfg.P;
   const double accept = ch.sum_metro / (double)ch.n_leapfrog;
   const double* qs = v + (size_t)NV_QS * P;
-  for (int k = LN::lane(); k < P; k += LN::lanes()) draw[k] = qs[k];
+  for (int k = LN::lane(); k < P; k += LN::lanes()) {
+    draw[k] = qs[k];
+    draw[(size_t)P + NUTS_DRAW_EXTRA + k] = v[(size_t)NV_PS * P + k];
+    draw[(size_t)2 * P + NUTS_DRAW_EXTRA + k] = v[(size_t)NV_GS * P + k];
+  }
   if (LN::lane() == 0) {
     draw[P + 0] = -ch.Vs;
     draw[P + 1] = accept;
@@ -448,6 +456,7 @@ NT_HD void nuts_after_leapfrog(const NutsConfig& cfg, NutsChain& ch, double* v, 
     cur[(size_t)NS_PEND * P + k] = p;
     cur[(size_t)NS_QP * P + k] = s.q(k);
     cur[(size_t)NS_GP * P + k] = s.g(k);
+    cur[(size_t)NS_PP * P + k] = p;
   }
   ch.cur_lsw = nuts_log_sum_exp(-INFINITY, w);
   ch.cur_V = Vn;
@@ -470,7 +479,7 @@ NT_HD void nuts_after_leapfrog(const NutsConfig& cfg, NutsChain& ch, double* v, 
                                         cur + (size_t)NS_RHO * P, cur + (size_t)NS_PBEG * P, cur + (size_t)NS_PEND * P,
                                         cur + (size_t)NS_RHO * P, cur + (size_t)NS_PBEG * P);
     if (!take_final) {
-      nuts_copy<LN>(P, cur + (size_t)NS_QP * P, a + (size_t)NS_QP * P, 2);
+      nuts_copy<LN>(P, cur + (size_t)NS_QP * P, a + (size_t)NS_QP * P, 3);
       ch.cur_V = ch.st_V[level];
       ch.cur_h = ch.st_h[level];
     }
@@ -503,6 +512,7 @@ NT_HD void nuts_after_leapfrog(const NutsConfig& cfg, NutsChain& ch, double* v, 
   if (take) {
     nuts_copy<LN>(P, v + (size_t)NV_QS * P, cur + (size_t)NS_QP * P, 1);
     nuts_copy<LN>(P, v + (size_t)NV_GS * P, cur + (size_t)NS_GP * P, 1);
+    nuts_copy<LN>(P, v + (size_t)NV_PS * P, cur + (size_t)NS_PP * P, 1);
     ch.Vs = ch.cur_V;
     ch.hs = ch.cur_h;
   }

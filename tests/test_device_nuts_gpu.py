@@ -164,8 +164,11 @@ def test_nuts_c_abi_round_by_round():
     assert [status[c].phase for c in range(3)] == [5, 1, 5]
     assert status[0].iter == 3 and status[2].iter == 3 and status[0].adapt_done == 1
     assert status[0].eps_nom == 1.0            # num_warmup == 0: complete_adaptation leaves exp(0) (reference quirk)
-    row = np.ctypeslib.as_array(draws, shape=(3, P + 8))
+    row = np.ctypeslib.as_array(draws, shape=(3, 3 * P + 8))
     assert np.all(np.isfinite(row[[0, 2]])) and row[0, P + 7] == 2 and row[0, P + 4] >= 1
-    lp, _ = m.log_prob_grad(row[0, :P])
+    lp, g = m.log_prob_grad(row[0, :P])
     assert abs(lp - row[0, P]) < 1e-9 * abs(lp)                                     # lp__ of the draw is the model's
+    assert np.max(np.abs(row[0, 2 * P + 8:] + g)) < 1e-9 * np.max(np.abs(g))        # ... and its gradient columns (of V = -lp)
+    energy = -lp + 0.5 * np.sum(row[0, P + 8:2 * P + 8] ** 2)                       # H = V + p.p / 2 (unit metric)
+    assert abs(energy - row[0, P + 6]) < 1e-9 * abs(energy)
     m.close()
