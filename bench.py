@@ -645,13 +645,18 @@ def run_b200_batched(args):
     """BASELINE configs[2]: normal_id_glm N=1M K=200, 1024 batched chains on one B200.  A step = one
     batched leapfrog (every chain advances once = `chains` gradient evaluations): fp64 DMMA GEMM pair."""
     import torch
+    import torch.distributed as dist
     from stan_b200 import GLMModel
     rank, local_rank, world = dist_env()
-    if world != 1:
-        raise SystemExit("--config 3 is a single-GPU configuration")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    N, K, C = args.rows, args.cols, args.chains
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, K, C_total = args.rows, args.cols, args.chains
+    # N GPUs: the CHAINS are what shards (the way the reference's multi-chain service parallelises,
+    # hmc_nuts_diag_e_adapt.hpp:387-401): every rank holds all of X (1.6 GB) and --chains / N of the chains; no
+    # data-path collective (DESIGN 5).  Strong scaling: the job (N x K x chains) is fixed.
+    C = C_total // world + (1 if rank < C_total % world else 0)
     g = torch.Generator(device=dev).manual_seed(20261017)
     X = torch.randn((K, N), generator=g, device=dev, dtype=torch.float64)
     beta = torch.randn(K, generator=g, device=dev, dtype=torch.float64) / K ** 0.5
@@ -681,6 +686,8 @@ def run_b200_batched(args):
     time.sleep(0.3)
     launches0 = m.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     t_wall0 = time.time()
     e0.record(stream)
@@ -688,11 +695,18 @@ def run_b200_batched(args):
         m.leapfrog_batched_async(C, eps)
     e1.record(stream)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t_wall1 = time.time()
-    ms_per_step = e0.elapsed_time(e1) / args.steps
+    ms = e0.elapsed_time(e1)
+    if world > 1:   # max over ranks, measured on the devices
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
     launches = m.launch_count() - launches0
     clk = clocks.stop(t_wall0, t_wall1)
-    value = C * 1000.0 / ms_per_step
+    value = C_total * 1000.0 / ms_per_step
     # e2e: host thetas in, host lp/grad out, every step
     th = q0.copy()
     for _ in range(3):
@@ -703,8 +717,13 @@ def run_b200_batched(args):
     for i in range(ne):
         th[0, 0] = q0[0, 0] + 1e-6 * i
         m.log_prob_grad_batched(th)
-    e2e_value = C * ne / (time.perf_counter() - t0)
-    flops = 4.0 * N * K * C
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = C_total * ne / e2e_s
+    flops = 4.0 * N * K * C                     # this rank's launch (the roofline is per kernel launch)
     # fp64 tensor-pipe peak measured NOW, in this process and under the clocks of this run (MEASURED_PEAKS.json has
     # no fp64 entry): register-resident mma.sync.m8n8k4.f64 loop, b200glm_measure_peaks (stan_b200/csrc/measure.cuh)
     from stan_b200 import _capi
@@ -715,18 +734,23 @@ def run_b200_batched(args):
     peak_clocks = clk2.stop(tp0, time.time())
     achieved = flops / (ms_per_step * 1e-3) / 1e12
     cpu_baseline = None
+    if rank != 0:
+        m.close()
+        dist.destroy_process_group()
+        return
     if sample is not None:
         cpu_baseline = cpu_baseline_leg(sample[0], sample[1], N, threads=1, evals=args.cpu_evals, family="normal_id")
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"normal_id_glm N={N} K={K} fp64, {C} batched chains (BASELINE configs[2])",
-                   "rows_total": N, "cols": K, "chains": C,
+        "config": {"workload": f"normal_id_glm N={N} K={K} fp64, {C_total} batched chains (BASELINE configs[2])",
+                   "rows_total": N, "cols": K, "chains": C_total, "chains_per_gpu": C,
+                   "sharding": "single GPU" if world == 1 else f"chains x{world} (X replicated on every GPU, no collective)",
                    "l2": f"X {8e-9 * N * K:.2f} GB >> 126 MB L2, no flush needed",
                    "step": "one batched leapfrog: begin + fused DMMA GEMM pair + slice reduce + finish (device-resident state)"},
         "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * P * C, "d2h_bytes_per_step": 8 * (P + 2) * C,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * P * C_total, "d2h_bytes_per_step": 8 * (P + 2) * C_total,
                 "call": "b200glm_log_prob_grad_batched(host thetas) -> host lp, grad"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -738,6 +762,8 @@ def run_b200_batched(args):
     }
     print(json.dumps(out))
     m.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------

@@ -49,12 +49,47 @@ def config3(args):
     from oracle.oracle import RefOracle
     from stan_b200 import make_glm_data, stan_service
     N, K = args.rows or 1_000_000, args.cols or 200
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
     t0 = time.time()
     d = make_glm_data("normal_id", N, K)
     t_gen = time.time() - t0
-    m = stan_service.StanGLM("normal_id", d["X"], d["y"], n_slots=16)
+    m = stan_service.StanGLM("normal_id", d["X"], d["y"], n_slots=16, device=local)
     run = m.nuts_device if args.driver == "device" else m.nuts_batched
-    res = run(num_chains=args.chains, seed=4711, num_warmup=args.warmup, num_samples=args.samples, delta=0.8)
+    if world > 1:
+        # N GPUs: the chains shard (X replicated, no data-path collective) -- rank r runs chains [c0, c1) with the chain
+        # ids they have in the single-GPU run, so the union of the ranks' draws IS that run's set of chains
+        import tempfile
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        c0, c1 = rank * args.chains // world, (rank + 1) * args.chains // world
+        dist.barrier()
+        res = run(num_chains=c1 - c0, init_chain_id=1 + c0, seed=4711, num_warmup=args.warmup, num_samples=args.samples,
+                  delta=0.8)
+        wall = torch.tensor([res["wall"]], device=torch.device("cuda", local), dtype=torch.float64)
+        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        tmp = os.path.join(tempfile.gettempdir(), f"bench_nuts_cfg3_{os.environ.get('MASTER_PORT', '0')}")
+        os.makedirs(tmp, exist_ok=True)
+        keys = ("draws", "warmup_draws", "stepsize", "inv_metric", "warm_leapfrogs")
+        np.savez(os.path.join(tmp, f"r{rank}.npz"), **{k: res[k] for k in keys},
+                 counts=np.array([res.get("rounds", res.get("batches", 0)), res["lanes"]]))
+        dist.barrier()
+        if rank != 0:
+            m.close()
+            dist.destroy_process_group()
+            return
+        parts = [np.load(os.path.join(tmp, f"r{r}.npz")) for r in range(world)]
+        for k in keys:
+            res[k] = np.concatenate([p_[k] for p_ in parts], axis=0)
+        res["wall"] = float(wall.item())
+        res["lanes"] = int(sum(p_["counts"][1] for p_ in parts))
+        res["rounds" if args.driver == "device" else "batches"] = int(max(p_["counts"][0] for p_ in parts))
+        res.pop("batch_size_hist", None)
+        res["batch_size_hist"] = None
+        dist.destroy_process_group()
+    else:
+        res = run(num_chains=args.chains, seed=4711, num_warmup=args.warmup, num_samples=args.samples, delta=0.8)
     s = summarize(res, RefOracle, args.chains)
     s.pop("stepsize")
     s["stepsize_median"] = float(np.median(res["stepsize"]))
@@ -97,6 +132,7 @@ def config3(args):
                        + ("via b200::hmc_nuts_diag_e_adapt_device (transition and adaptation on the device)"
                           if args.driver == "device" else
                           "via b200::hmc_nuts_diag_e_adapt_batched (single-chain reference service per chain)"),
+           "n_gpus": world, "sharding": "single GPU" if world == 1 else f"chains x{world} (X replicated, no collective)",
            "host_threads": os.cpu_count(), "data_gen_s": t_gen, "b200": dict(s, counters=m.counters())}
     m.close()
     print(json.dumps(out))
@@ -187,10 +223,10 @@ def main():
     from stan_b200 import make_glm_data, stan_service
 
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
+    if args.config == 3:
+        return config3(args)          # under torchrun: the chains shard over the ranks
     if world > 1:
         return sharded(args, world, rank, local)
-    if args.config == 3:
-        return config3(args)
     if args.config == 4:
         return config4(args)
     N, K = {1: (10_000, 20), 2: (10_000_000, 100)}[args.config]
