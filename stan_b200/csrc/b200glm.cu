@@ -1503,10 +1503,10 @@ int b200glm_batch_reserve(b200glm_handle* h, int32_t max_chains) {
         break;
       }
     int S2 = 16;
-    while (S2 > 0 && multi_smem_bytes(h->d.K, h->C, S2, 4) > max_dyn) --S2;
-    if (S2 >= 4 && b->mu_cpl && (size_t)S2 * h->C * 32 >= (size_t)NUM_CONSUMER_WARPS * (((h->d.K + 7) & ~7) + 2) * 4) {
+    while (S2 > 0 && multi_smem_bytes(h->d.K, h->C, S2, 4, b->mu_cpl) > max_dyn) --S2;
+    if (S2 >= 4 && b->mu_cpl && (size_t)S2 * multi_stage_cols(h->C, b->mu_cpl) * 32 >= (size_t)NUM_CONSUMER_WARPS * (((h->d.K + 7) & ~7) + 2) * 4) {
       b->mu_S = S2;
-      b->mu_smem = multi_smem_bytes(h->d.K, h->C, S2, 4);
+      b->mu_smem = multi_smem_bytes(h->d.K, h->C, S2, 4, b->mu_cpl);
       CUDA_TRY(h, cudaFuncSetAttribute(pick_multi(h->d.family, b->mu_cpl), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)b->mu_smem));
     } else {

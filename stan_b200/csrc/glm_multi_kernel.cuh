@@ -29,10 +29,14 @@ namespace b200glm {
 constexpr int MULTI_THREADS = NUM_CONSUMER_WARPS * 32;
 constexpr int MULTI_MAX_K = 128;   // CPL <= 16 column slots x 4 chains = 64 fp64 accumulators per lane
 
-__host__ __device__ inline size_t multi_smem_bytes(int K, int C, int S, int NCH) {
+// columns per ring stage: the panel's C columns, padded so that phase 2 may read all 8 CPL column slots of every lane
+// without a guard (what lies beyond column C is never stored)
+__host__ __device__ inline int multi_stage_cols(int C, int cpl) { return C > 8 * cpl ? C : 8 * cpl; }
+
+__host__ __device__ inline size_t multi_smem_bytes(int K, int C, int S, int NCH, int cpl) {
   const int Kpad = (K + 7) & ~7;
   // the warps' partial rows (8 x (Kpad + 2) x NCH doubles) reuse the ring once every panel has been consumed
-  return ((size_t)S * C * 32 + (size_t)Kpad * NCH + 2 * NCH + (size_t)NUM_CONSUMER_WARPS * 32 * NCH) * 8
+  return ((size_t)S * multi_stage_cols(C, cpl) * 32 + (size_t)Kpad * NCH + 2 * NCH + (size_t)NUM_CONSUMER_WARPS * 32 * NCH) * 8
          + (size_t)S * 8;
 }
 
@@ -41,9 +45,10 @@ __global__ void __launch_bounds__(MULTI_THREADS, 1) glm_multi_kernel(const Batch
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int K = p.K, C = p.C, S = p.n_stages, P = p.P;
   const int Kpad = (K + 7) & ~7;
-  const int tile_doubles = C * 32;
-  double* tiles = reinterpret_cast<double*>(smem_raw);                    // S * tile_doubles
-  double* sbeta = tiles + (size_t)S * tile_doubles;                       // [Kpad][NCH]
+  const int tile_doubles = C * 32;                                        // what a bulk copy brings
+  const int stage_doubles = multi_stage_cols(C, CPL) * 32;                // ring stage stride
+  double* tiles = reinterpret_cast<double*>(smem_raw);                    // S * stage_doubles
+  double* sbeta = tiles + (size_t)S * stage_doubles;                      // [Kpad][NCH]
   double* salpha = sbeta + (size_t)Kpad * NCH;                            // [NCH]
   double* sisig = salpha + NCH;                                           // [NCH]
   double* sr = sisig + NCH;                                               // [8 warps][32 rows][NCH]
@@ -77,7 +82,7 @@ __global__ void __launch_bounds__(MULTI_THREADS, 1) glm_multi_kernel(const Batch
   auto request = [&](long long n, int s) {
     const long long pi = blockIdx.x + n * grid;
     mbar_arrive_expect_tx(&full_bar[s], tile_bytes);
-    tma_load_1d(tiles + (size_t)s * tile_doubles, p.panels + (size_t)pi * tile_doubles, tile_bytes, &full_bar[s], pol);
+    tma_load_1d(tiles + (size_t)s * stage_doubles, p.panels + (size_t)pi * tile_doubles, tile_bytes, &full_bar[s], pol);
   };
 
   double acc[CPL][NCH];
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(MULTI_THREADS, 1) glm_multi_kernel(const Batch
         if (n >= p_count) break;
         const long long pi = blockIdx.x + n * grid;
         mbar_wait(&full_bar[s], parity);
-        const double* tile = tiles + (size_t)s * tile_doubles;
+        const double* tile = tiles + (size_t)s * stage_doubles;
 
         // ---- phase 1: eta of row `lane` for every chain; even / odd feature pairs in separate accumulators:
         //      2 NCH independent FMA chains per lane ----
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(MULTI_THREADS, 1) glm_multi_kernel(const Batch
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           double lp_i, r_i;
-          link<FAMILY>((ea[c] + eb[c]) + salpha[c], y, sisig[c], lp_i, r_i);
+          link_bf<FAMILY>((ea[c] + eb[c]) + salpha[c], y, sisig[c], lp_i, r_i);   // branch-free: the chains interleave
           if (!valid) {
             lp_i = 0.0;
             r_i = 0.0;
@@ -172,15 +177,15 @@ __global__ void __launch_bounds__(MULTI_THREADS, 1) glm_multi_kernel(const Batch
               rr[m][c] = v.x;
               rr[m][c + 1] = v.y;
             }
+          // row outermost: successive FMAs into one accumulator are 4 CPL instructions apart (no dependency stalls),
+          // no guard on the column (the stage is padded to 8 CPL columns; sums of columns >= K are never stored)
 #pragma unroll
-          for (int s2 = 0; s2 < CPL; ++s2) {
-            if (cg + 8 * s2 < K) {
+          for (int m = 0; m < 4; ++m) {
 #pragma unroll
-              for (int m = 0; m < 4; ++m) {
-                const double x = base[s2 * 256 + off[mh + m]];
+            for (int s2 = 0; s2 < CPL; ++s2) {
+              const double x = base[s2 * 256 + off[mh + m]];
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) acc[s2][c] = fma(x, rr[m][c], acc[s2][c]);
-              }
+              for (int c = 0; c < NCH; ++c) acc[s2][c] = fma(x, rr[m][c], acc[s2][c]);
             }
           }
         }

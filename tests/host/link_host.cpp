@@ -60,6 +60,36 @@ int link_rows(int family, int n, const double* eta, const double* y, const doubl
 
 double digamma_host(double v) { return digamma_pos(v); }
 
+// link<> and its branch-free form link_bf<> (glm_multi_kernel.cuh uses the latter) on the same rows, and the special
+// functions of link_bf on their own
+int link_pair_rows(int family, int n, const double* eta, const double* y, double inv_sigma, double* lp, double* r,
+                   double* lp_bf, double* r_bf) {
+  for (int i = 0; i < n; ++i) {
+    switch (family) {
+      case FAM_BERNOULLI_LOGIT:
+        link<FAM_BERNOULLI_LOGIT>(eta[i], y[i], inv_sigma, lp[i], r[i]);
+        link_bf<FAM_BERNOULLI_LOGIT>(eta[i], y[i], inv_sigma, lp_bf[i], r_bf[i]);
+        break;
+      case FAM_POISSON_LOG:
+        link<FAM_POISSON_LOG>(eta[i], y[i], inv_sigma, lp[i], r[i]);
+        link_bf<FAM_POISSON_LOG>(eta[i], y[i], inv_sigma, lp_bf[i], r_bf[i]);
+        break;
+      case FAM_NORMAL_ID:
+        link<FAM_NORMAL_ID>(eta[i], y[i], inv_sigma, lp[i], r[i]);
+        link_bf<FAM_NORMAL_ID>(eta[i], y[i], inv_sigma, lp_bf[i], r_bf[i]);
+        break;
+      default: return 1;
+    }
+  }
+  return 0;
+}
+void fm_exp_rows(int n, const double* x, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = fm_exp(x[i]);
+}
+void fm_log1p_rows(int n, const double* u, double* out, double* rw) {
+  for (int i = 0; i < n; ++i) out[i] = fm_log1p(u[i], rw[i]);
+}
+
 // The model epilogue finish() (glm_model.cuh) as one host thread.
 //   ic = {family, K, G, P, off_beta, propto, jacobian, is_var, lik_only, sigma_is_var, mode}
 //   dc = {N_total, lgamma_sum, prior_alpha_sd, prior_beta_sd, prior_sigma_loc, prior_sigma_scale, prior_sigma_a_scale, eps}

@@ -40,6 +40,11 @@ def host_lib(tmp_path_factory):
     L.ordered_logistic_rows.restype = None
     L.categorical_logit_rows.argtypes = [C.c_int, C.c_int, ip, dp, dp]
     L.categorical_logit_rows.restype = None
+    L.link_pair_rows.argtypes = [C.c_int, C.c_int, dp, dp, C.c_double, dp, dp, dp, dp]
+    L.fm_exp_rows.argtypes = [C.c_int, dp, dp]
+    L.fm_exp_rows.restype = None
+    L.fm_log1p_rows.argtypes = [C.c_int, dp, dp, dp]
+    L.fm_log1p_rows.restype = None
     return L
 
 
@@ -174,3 +179,59 @@ def test_rows_categorical_logit(host_lib):
             assert abs(lp[i] + prior - lp_o) <= 1e-13 * max(abs(lp_o), 1.0), (Cn, i)
             assert np.max(np.abs(lin[i] - alpha[i] / SD ** 2 - g_o[:Cn])) <= 1e-13 * max(np.max(np.abs(g_o)), 1.0)
             assert np.max(np.abs(lin[i] - beta[i] / SD ** 2 - g_o[Cn:])) <= 1e-13 * max(np.max(np.abs(g_o)), 1.0)
+
+
+# ---- the branch-free link step of glm_multi_kernel (link_bf<>, fm_exp / fm_log1p in glm_link.cuh) ----
+def _ulps(a, b):
+    return np.abs(a - b) / np.spacing(np.abs(b))
+
+
+def test_fast_exp_and_log1p_against_libm(host_lib):
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-700, 700, 200_000), rng.uniform(-25, 25, 200_000), rng.uniform(-1e-3, 1e-3, 1000),
+                        [0.0, -0.0, 700.0, -700.0, 1e-300, 20.0, -20.0, 21.0]])
+    out = np.empty_like(x)
+    host_lib.fm_exp_rows(x.size, dp(x), dp(out))
+    assert _ulps(out, np.exp(x)).max() <= 1.0                       # the fast path of CUDA's exp: < 1 ulp
+    u = np.concatenate([np.exp(rng.uniform(-50, 21, 300_000)), rng.uniform(0, 3, 100_000), [0.0, 1e-300, 1.0, 0.41, 0.42,
+                        np.sqrt(2) - 1, 4.85e8]])
+    l1p, rw = np.empty_like(u), np.empty_like(u)
+    host_lib.fm_log1p_rows(u.size, dp(u), dp(l1p), dp(rw))
+    ref = np.log1p(u)
+    ok = ref > 0
+    assert _ulps(l1p[ok], ref[ok]).max() <= 2.0                     # fdlibm's algorithm: < 1 ulp, + the reciprocal's
+    assert np.all(l1p[~ok] == 0.0)
+    assert np.max(np.abs(rw * (1.0 + u) - 1.0)) < 4e-16
+
+
+@pytest.mark.parametrize("fam", [0, 1, 2])
+def test_branch_free_link_equals_link(host_lib, fam):
+    """link_bf<> against link<> row by row: random etas, the bernoulli cut-offs from both sides, huge |eta|, infinities
+    and NaN (which branch is taken and what propagates must be the same), both outcomes."""
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rng = np.random.default_rng(6)
+    eta = np.concatenate([rng.normal(0, 3, 100_000), rng.uniform(-30, 30, 100_000),
+                          [20.0, -20.0, np.nextafter(20.0, 30), np.nextafter(20.0, 0), np.nextafter(-20.0, -30),
+                           np.nextafter(-20.0, 0), 0.0, 50.0, -50.0, 699.0, -699.0, 705.0, -705.0, 745.0, -745.0, 800.0,
+                           -800.0, 1e6, -1e6, np.inf, -np.inf, np.nan]])
+    if fam == 1:
+        y = rng.poisson(3.0, eta.size).astype(float)
+    elif fam == 0:
+        y = rng.integers(0, 2, eta.size).astype(float)
+    else:
+        y = rng.normal(0, 2, eta.size)
+    n = eta.size
+    lp, r, lpb, rb = (np.empty(n) for _ in range(4))
+    assert host_lib.link_pair_rows(fam, n, dp(eta), dp(y), C.c_double(0.7), dp(lp), dp(r), dp(lpb), dp(rb)) == 0
+    with np.errstate(invalid="ignore", over="ignore"):
+        for a, b in ((lp, lpb), (r, rb)):
+            assert np.array_equal(np.isnan(a), np.isnan(b))
+            assert np.array_equal(np.isinf(a), np.isinf(b)) and np.array_equal(a[np.isinf(a)], b[np.isinf(b)])
+            fin = np.isfinite(a)
+            tiny = fin & (np.abs(a) < 1e-290)                 # exp(-t) beyond t = 700: below 1e-304 in both
+            assert np.all(np.abs(b[tiny]) < 1e-290)
+            big = fin & ~tiny
+            # poisson: y eta - exp(eta) cancels; measure against the larger term
+            scale = np.maximum(np.abs(a[big]), np.abs(y[big] * eta[big]) if fam == 1 else 0.0)
+            assert np.max(np.abs(a[big] - b[big]) / scale) < 1e-15 * (8 if fam == 1 else 4)
