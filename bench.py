@@ -331,6 +331,14 @@ def run_b200(args):
         parity = parity_record(torch, dist, dev, m, m_local, par_sample, family, G, K, rank, world, local_rank)
     if m_local is not None:
         m_local.close()
+    # ---- four chains per pass (glm_multi_kernel): the same X, one batched leapfrog of 4 chain slots per
+    #      step, device-resident; unsharded scalar-intercept handles with K <= 128 only ----
+    four = None
+    if world == 1 and G == 0 and K <= 128 and family in ("bernoulli_logit", "poisson_log", "normal_id") and not streamed:
+        try:
+            four = four_chains_record(args, torch, m, dev, bytes_per_gradient, q0)
+        except Exception as e:                       # an extra: must not break the bench line
+            four = {"error": str(e)[:200]}
     # ---- ESS/s inside NUTS at this configuration (every rank takes part; rank 0 reports) ----
     ess = None
     if args.ess_iters > 0 and args.config == 2:
@@ -407,6 +415,7 @@ def run_b200(args):
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "parity": parity,
+        "four_chains": four,
         "ess": ess,
     }
     if ess is not None and world == 1 and not args.no_cpu_baseline:
@@ -543,6 +552,45 @@ def parity_record(torch, dist, dev, m, m_local, sample, family, G, K, rank, worl
             "shard_additivity": None if err_add is None else {
                 "max_rel_err": err_add, "what": "sharded handle (in-launch exchange) vs sum over ranks of the "
                                                 "same shards evaluated unsharded"}}
+
+
+def four_chains_record(args, torch, m, dev, bytes_per_pass, q0):
+    """Gradient evaluations/s with FOUR chains advanced per pass over X (b200glm_leapfrog_batched_async with 4 chain
+    slots -> glm_multi_kernel + the batched prologue / reduce / epilogue launches), timed like `value`: CUDA events on
+    the batch stream, args.warmup + args.steps steps, state resident on the device.  The roofline entry counts the
+    ALGORITHMIC bytes of one pass (X once) -- four gradient evaluations ride on them."""
+    C4 = 4
+    m.batch_reserve(C4)
+    rng = np.random.default_rng(12)
+    q = q0[None, :] + 0.01 * rng.standard_normal((C4, q0.size))
+    p = rng.standard_normal((C4, q0.size))
+    lp, g, st = m.log_prob_grad_batched(q)
+    if st.any():
+        return {"error": "domain error at the starting points"}
+    m.set_state_batched(q, p, -g, -lp)
+    stream = torch.cuda.ExternalStream(m.batch_stream_ptr(), device=dev)
+    for _ in range(args.warmup):
+        m.leapfrog_batched_async(C4, 1e-4)
+    torch.cuda.synchronize()
+    l0 = m.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        m.leapfrog_batched_async(C4, 1e-4)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    peak, which = measured_peaks()
+    achieved = bytes_per_pass / (ms * 1e-3) / 1e9
+    return {"chains": C4, "value": C4 * 1000.0 / ms, "unit": UNIT, "ms_per_step": ms,
+            "gpu_launches": int(m.launch_count() - l0),
+            "step": "one batched leapfrog of 4 chain slots: batched_begin + glm_multi_kernel (one pass over X for the four "
+                    "chains) + batched_reduce + batched_finish, device-resident state",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peak["hbm_gbs"], "peak_source": which,
+                         "kernel": "glm_multi_kernel (4 chains per pass)",
+                         "algorithmic_bytes_per_launch": int(bytes_per_pass), "avg_launch_ms": ms,
+                         "note": "time of the whole 4-launch step over the bytes of ONE pass over X"}}
 
 
 def ess_record(args, torch, dist, dev, rank, world, local_rank):

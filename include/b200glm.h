@@ -24,7 +24,7 @@
  * Environment switches (read at b200glm_create / b200glm_batch_reserve; for A/B measurements only):
  *   B200GLM_NO_PDL=1       launch without the programmatic-dependent-launch attribute
  *   B200GLM_NO_ROWSPLIT=1  serve batches of <= 16 lanes with the normal batched kernel, not its row-split variant
- *   B200GLM_NO_MULTI=1     serve batches of <= 4 lanes (K <= 128) with the DMMA kernels, not the few-chain FMA kernel
+ *   B200GLM_NO_MULTI=1     serve batches of <= 8 lanes (K <= 128) with the DMMA kernels, not the few-chain FMA kernel
  *   B200GLM_WIDE_PRODUCER=single|lanes   wide-matrix kernel: one lane issues every bulk copy | lane j streams sub-panel j
  *   B200GLM_NO_STATE_SMEM=1  keep the chain state of the fused epilogue in global memory
  *   B200GLM_NO_GROUP_FUSION=1, B200GLM_PDL_PREFETCH=<stages>, B200GLM_WIDE_ROWS=16|8|4, B200GLM_TL_REPEAT=1  
@@ -181,8 +181,9 @@ const double* b200glm_result_device(b200glm_handle* h, int32_t slot);
  * fp64 GEMMs on the DMMA tensor path (BASELINE configs[2]).  This is the device side of a multi-chain
  * driver in ST/services/sample (hmc_nuts_diag_e_adapt.hpp:364-401 runs chains as independent TBB
  * tasks, each calling stan::model::gradient on its own; here the calls of all chains that are waiting
- * for a leapfrog step are served together).  Requires K <= 208, G == 0, world == 1.  Batches of <= 4 lanes with
- * K <= 128 take glm_multi_kernel: four chains per pass on the FMA path, HBM-bound like the single-chain kernel.
+ * for a leapfrog step are served together).  Requires K <= 208, G == 0, world == 1.  Batches of <= 8 lanes with
+ * K <= 128 take glm_multi_kernel: four chains per pass on the FMA path (5-8 lanes: two passes), HBM-bound like the
+ * single-chain kernel.
  * All per-chain arrays are chain-major HOST arrays: theta[i*P + k] belongs to lane i.
  *   batch_reserve            allocate state for chain slots [0, max_chains) (inverse metric = 1)
  *   log_prob_grad_batched    == n calls of b200glm_log_prob_grad; status[i] (may be NULL) gets the

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -122,6 +123,10 @@ struct Batch {
     NutsStatus* status = nullptr;    // pinned host
     int32_t* lanes_d = nullptr;      // device: the lane list of the last round (re-uploaded only when it changes)
     std::vector<int32_t> lanes_h;
+    // a round is 6-7 small launches; for small models their launch gaps are the round.  One CUDA graph per lane count
+    // (the launches' parameters depend on nothing else: lane list, steps and state are read from device memory)
+    std::map<int, std::pair<cudaGraphExec_t, int>> graphs;   // n -> (executable, launches inside)
+    bool use_graphs = true;
   };
   Nuts* nuts = nullptr;
 };
@@ -133,6 +138,7 @@ void free_nuts(Batch* b) {
   cudaFree(u->vec);
   cudaFree(u->eps_c);
   cudaFree(u->lanes_d);
+  for (auto& g : u->graphs) cudaGraphExecDestroy(g.second.first);
   for (double* q : {u->normals, u->uniforms, u->draws, u->metric})
     if (q) cudaFreeHost(q);
   if (u->status) cudaFreeHost(u->status);
@@ -1357,7 +1363,8 @@ int enqueue_batched(b200glm_handle* h, int n, int mode, int propto, int jacobian
   const int NCB = (n + BATCH_CB - 1) / BATCH_CB;
   int NS = std::max(1, b->sms / NCB);
   if ((long long)NS > std::max<long long>(h->n_panels, 1)) NS = (int)std::max<long long>(h->n_panels, 1);
-  const bool multi = n <= 4 && b->mu_cpl > 0;   // a few chains: the FMA kernel (one CTA per SM, every CTA a row slice)
+  const bool multi = n <= MULTI_MAX_LANES && b->mu_cpl > 0;   // a few chains: the FMA kernel, four per pass (one CTA
+                                                              // per SM, every CTA a row slice)
   BatchedStepParams sp;
   std::memset(&sp, 0, sizeof(sp));
   sp.n = n;
@@ -1411,9 +1418,13 @@ int enqueue_batched(b200glm_handle* h, int n, int mode, int propto, int jacobian
   bp.n_lanes = n;
   bp.theta_c = b->theta_c;
   bp.partials = b->partials;
-  if (multi)
-    pick_multi(h->d.family, b->mu_cpl)<<<NS, MULTI_THREADS, b->mu_smem, b->stream>>>(bp);
-  else
+  if (multi) {
+    for (int l0 = 0; l0 < n; l0 += 4) {   // 5-8 lanes: a second pass (2 x 1.3 ms at cfg2's shape against 4.95 ms DMMA)
+      bp.lane0 = l0;
+      pick_multi(h->d.family, b->mu_cpl)<<<NS, MULTI_THREADS, b->mu_smem, b->stream>>>(bp);
+      if (l0) h->launches++;
+    }
+  } else
     pick_batched(h->d.family, b->mbh, row_split)<<<NCB * NS, BATCH_THREADS, row_split ? b->rs_smem : b->smem, b->stream>>>(bp);
   batched_reduce_kernel<<<(h->d.K + 2) * NCB, BATCH_CB, 0, b->stream>>>(sp);
   batched_finish_kernel<<<(n + 31) / 32, 256, 0, b->stream>>>(sp);
@@ -1729,6 +1740,7 @@ int b200glm_nuts_reserve(b200glm_handle* h, int32_t n_chains, const b200glm_nuts
   u->cfg.num_warmup = c->num_warmup;
   u->cfg.num_samples = c->num_samples;
   u->vstride = nuts_vec_doubles(h->P, c->max_depth);
+  u->use_graphs = !std::getenv("B200GLM_NO_GRAPH");
   CUDA_TRY(h, cudaMalloc(&u->chains, sizeof(NutsChain) * n));
   CUDA_TRY(h, cudaMemset(u->chains, 0, sizeof(NutsChain) * n));
   CUDA_TRY(h, cudaMalloc(&u->vec, sizeof(double) * u->vstride * n));
@@ -1828,14 +1840,48 @@ int b200glm_nuts_round(b200glm_handle* h, int32_t n, const int32_t* chains) {
   NutsDeviceParams p = nuts_params(h);
   p.n_lanes = n;
   p.lanes = u->lanes_d;
-  if (any_begin) {   // chains that were waiting for normal variates: the caller has supplied them
-    nuts_begin_kernel<<<(n + 7) / 8, 256, 0, b->stream>>>(p);
+  auto enqueue_round = [&](bool with_begin) -> int {
+    if (with_begin) {   // chains that were waiting for normal variates (the caller has supplied them); others pass through
+      nuts_begin_kernel<<<(n + 7) / 8, 256, 0, b->stream>>>(p);
+      h->launches++;
+    }
+    int r = enqueue_batched(h, n, MODE_LEAPFROG, 1, 1, u->lanes_d, u->eps_c, 0.0, false, true);
+    if (r) return r;
+    nuts_step_kernel<<<(n + 7) / 8, 256, 0, b->stream>>>(p);
     h->launches++;
+    return B200GLM_OK;
+  };
+  if (u->use_graphs) {
+    auto it = u->graphs.find(n);
+    if (it == u->graphs.end()) {
+      const long long l0 = h->launches;
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      bool ok = cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        rc = enqueue_round(true);
+        ok = cudaStreamEndCapture(b->stream, &graph) == cudaSuccess && rc == B200GLM_OK && graph != nullptr;
+      }
+      const int inside = (int)(h->launches - l0);
+      h->launches = l0;
+      if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+      if (!ok) {            // capture not possible here: fall back to plain launches for the rest of the run
+        cudaGetLastError();
+        u->use_graphs = false;
+      } else {
+        it = u->graphs.emplace(n, std::make_pair(exec, inside)).first;
+      }
+    }
+    if (u->use_graphs) {
+      CUDA_TRY(h, cudaGraphLaunch(it->second.first, b->stream));
+      h->launches += it->second.second;
+      CUDA_TRY(h, cudaStreamSynchronize(b->stream));
+      return B200GLM_OK;
+    }
   }
-  rc = enqueue_batched(h, n, MODE_LEAPFROG, 1, 1, u->lanes_d, u->eps_c, 0.0, false, true);
+  rc = enqueue_round(any_begin);
   if (rc) return rc;
-  nuts_step_kernel<<<(n + 7) / 8, 256, 0, b->stream>>>(p);
-  h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   CUDA_TRY(h, cudaStreamSynchronize(b->stream));
   return B200GLM_OK;

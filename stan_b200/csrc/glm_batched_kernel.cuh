@@ -47,6 +47,7 @@ struct BatchedParams {
   int ldc;                 // padded number of chain lanes (NCB * 64)
   int n_lanes;             // active lanes; warp pairs whose 16 chains are all padding do no work
   int pairs;               // row-split mode: active warp pairs PA (n_stages is then the stages PER PAIR)
+  int lane0;               // glm_multi_kernel: first lane of this pass (lanes [lane0, lane0 + 4))
   const double* theta_c;   // [P][ldc] feature-major: the point each lane is evaluated at
   double* partials;        // [NS][NCB][K + 2][64]: rows [0,K) = X^T r, row K = lp-sum, row K+1 = r-sum
 };

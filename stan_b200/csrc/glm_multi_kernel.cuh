@@ -1,4 +1,5 @@
-// glm_multi_kernel.cuh -- a FEW chains (<= 4: Stan's default chain count) in one pass over X, on the FMA path.
+// glm_multi_kernel.cuh -- a FEW chains (four per pass: Stan's default chain count; batches of 5-8 lanes take two passes)
+// in one pass over X, on the FMA path.
 //
 // The single-chain gradient is HBM-bound with the fp64 pipe at 15 %: the same panel stream can feed the
 // arithmetic of four chains.  The DMMA path of glm_batched_kernel.cuh is the wrong tool here -- its chain blocks are 16
@@ -27,6 +28,7 @@
 namespace b200glm {
 
 constexpr int MULTI_THREADS = NUM_CONSUMER_WARPS * 32;
+constexpr int MULTI_MAX_LANES = 8;   // batches of up to 8 lanes: one or two passes of four chains
 constexpr int MULTI_MAX_K = 128;   // CPL <= 16 column slots x 4 chains = 64 fp64 accumulators per lane
 
 // columns per ring stage: the panel's C columns, padded so that phase 2 may read all 8 CPL column slots of every lane
@@ -63,14 +65,15 @@ __global__ void __launch_bounds__(MULTI_THREADS, 1) glm_multi_kernel(const Batch
     fence_proxy_async();
   }
   // the chains' coefficients, chain-minor: one broadcast 16-byte load per chain pair in phase 1
+  const int lane0 = p.lane0;   // this pass evaluates lanes [lane0, lane0 + NCH) of the batch
   for (int j = tid; j < Kpad * NCH; j += MULTI_THREADS) {
     const int k = j / NCH, c = j - k * NCH;
-    sbeta[j] = (k < K && c < p.n_lanes) ? p.theta_c[(size_t)(p.off_beta + k) * p.ldc + c] : 0.0;
+    sbeta[j] = (k < K && lane0 + c < p.n_lanes) ? p.theta_c[(size_t)(p.off_beta + k) * p.ldc + lane0 + c] : 0.0;
   }
   if (tid < NCH) {
-    const bool act = tid < p.n_lanes;
-    salpha[tid] = act ? p.theta_c[tid] : 0.0;
-    sisig[tid] = (FAMILY == FAM_NORMAL_ID && act) ? 1.0 / exp(p.theta_c[(size_t)(P - 1) * p.ldc + tid]) : 1.0;
+    const bool act = lane0 + tid < p.n_lanes;
+    salpha[tid] = act ? p.theta_c[lane0 + tid] : 0.0;
+    sisig[tid] = (FAMILY == FAM_NORMAL_ID && act) ? 1.0 / exp(p.theta_c[(size_t)(P - 1) * p.ldc + lane0 + tid]) : 1.0;
   }
   __syncthreads();
 
@@ -219,17 +222,17 @@ __global__ void __launch_bounds__(MULTI_THREADS, 1) glm_multi_kernel(const Batch
   }
   __syncthreads();
 
-  // ---- CTA partial in the batched layout: [slice = CTA][row in [0, K + 2)][64 chain columns], warps in fixed order ----
-  double* part = p.partials + (size_t)blockIdx.x * (K + 2) * BATCH_CB;
-  for (int j = tid; j < (K + 2) * BATCH_CB; j += MULTI_THREADS) {
-    const int row = j / BATCH_CB, c = j - row * BATCH_CB;
+  // ---- CTA partial in the batched layout: [slice = CTA][row in [0, K + 2)][64 chain columns]; this pass owns columns
+  //      [lane0, lane0 + NCH), warps folded in fixed order (the other columns belong to other passes or to no lane:
+  //      the epilogue only reads the columns of live lanes) ----
+  double* part = p.partials + (size_t)blockIdx.x * (K + 2) * BATCH_CB + lane0;
+  for (int j = tid; j < (K + 2) * NCH; j += MULTI_THREADS) {
+    const int row = j / NCH, c = j - row * NCH;
+    const int src = row < K ? row : Kpad + (row - K);
     double v = 0.0;
-    if (c < NCH) {
-      const int src = row < K ? row : Kpad + (row - K);
 #pragma unroll
-      for (int w = 0; w < NUM_CONSUMER_WARPS; ++w) v += red[((size_t)w * (Kpad + 2) + src) * NCH + c];
-    }
-    part[j] = v;
+    for (int w = 0; w < NUM_CONSUMER_WARPS; ++w) v += red[((size_t)w * (Kpad + 2) + src) * NCH + c];
+    part[(size_t)row * BATCH_CB + c] = v;
   }
 }
 

@@ -222,6 +222,14 @@ def test_few_chain_fma_kernel(fam, N, K, monkeypatch):
     for n in (1, 2, 3):                                   # fewer lanes: the same chains, bit for bit
         lp, g, _ = m.log_prob_grad_batched(th[:n])
         assert np.array_equal(lp, lp4[:n]) and np.array_equal(g, g4[:n])
+    th7 = np.concatenate([th, 0.1 * rng.standard_normal((3, m.P))])   # 5-8 lanes: two passes of four chains
+    lp7, g7, st7 = m.log_prob_grad_batched(th7)
+    assert not st7.any() and np.array_equal(lp7[:4], lp4) and np.array_equal(g7[:4], g4)
+    lpd7, gd7, _ = m_dmma.log_prob_grad_batched(th7)
+    for c in range(4, 7):
+        lp_r, g_r = po.log_prob_grad(th7[c])
+        assert rel_err(lp7[c], lp_r) < TOL and rel_err_vec(g7[c], g_r) < TOL, c
+        assert rel_err(lp7[c], lpd7[c]) < 1e-12 and rel_err_vec(g7[c], gd7[c]) < 1e-12, c
     lp_r4, g_r4, _ = m.log_prob_grad_batched(th[::-1].copy())
     assert np.array_equal(lp_r4[::-1], lp4) and np.array_equal(g_r4[::-1], g4)
     for propto, jac in ((0, 1), (1, 0)):
