@@ -39,9 +39,11 @@
 extern "C" {
 #endif
 
-#define B200GLM_ABI_VERSION 4   /* 2: b200glm_desc gained `trials` (appended), families 3 and 4
+#define B200GLM_ABI_VERSION 5   /* 2: b200glm_desc gained `trials` (appended), families 3 and 4
                                    3: b200glm_abi_version, shard constants, timeline, (no struct change)
-                                   4: b200glm_desc gained `n_classes` (appended), families 5 and 6, streamed build */
+                                   4: b200glm_desc gained `n_classes` (appended), families 5 and 6, streamed build
+                                   5: b200glm_nuts_config gained `stepsize_jitter` (appended); a chain's row of the
+                                      `uniforms` buffer is 72 doubles (the 64-entry ring + the jitter variate) */
 
 /* status codes; the C++ shim maps them to the exceptions the reference throws:
  * DOMAIN -> std::domain_error (recoverable: base_hamiltonian.hpp:65-68, initialize.hpp:104-112),
@@ -216,8 +218,8 @@ void* b200glm_batch_stream(b200glm_handle* h);
  * says how many uniform variates were consumed.  Host driver: b200::hmc_nuts_diag_e_adapt_device
  * (stan_b200/cpp/b200/device_nuts.hpp), the argument list of ST/services/sample/hmc_nuts_diag_e_adapt.hpp:331-404.
  *   nuts_reserve     batch_reserve(n_chains) + the per-chain tree state ((19 + 6 max_depth) P doubles)
- *   nuts_buffers     pinned host buffers shared with the kernels: normals [n][P], uniforms [n][64] (a ring indexed
- *                    by the running count), status [n], draws [n][3 P + 8] (parameters, lp__, accept_stat__, stepsize__,
+ *   nuts_buffers     pinned host buffers shared with the kernels: normals [n][P], uniforms [n][72] (entries [0, 64): a ring indexed
+ *                    by the running count; entry 64: the step-size jitter variate of the transition about to start), status [n], draws [n][3 P + 8] (parameters, lp__, accept_stat__, stepsize__,
  *                    treedepth__, n_leapfrog__, divergent__, energy__, iteration, then the selected state's momentum
  *                    and gradient: the diagnostic writer's columns), metric [n][P]
  *   nuts_init_chain  initial point, diagonal inverse metric, nominal step size of one chain
@@ -229,6 +231,7 @@ typedef struct b200glm_nuts_config {
    * adapt_base_window_, adapt_window_size_, adapt_next_window_ */
   uint32_t w_num_warmup, w_init_buffer, w_term_buffer, w_base_window, w_size0, w_next0;
   double max_deltaH, delta, gamma, kappa, t0;
+  double stepsize_jitter;   /* base_hmc::epsilon_jitter_ (base_hmc.hpp:195-200); appended in ABI 5 */
 } b200glm_nuts_config;
 typedef struct b200glm_nuts_status {
   int32_t phase;          /* 1 initial gradient, 2 / 3 init_stepsize, 4 inside a transition, 5 done, 6 failed */

@@ -59,6 +59,7 @@ struct nuts_host_backend {
     b.cfg.w_next0 = c->w_next0;
     b.cfg.num_warmup = c->num_warmup;
     b.cfg.num_samples = c->num_samples;
+    b.cfg.stepsize_jitter = c->stepsize_jitter;
     b.vstride = b200glm::nuts_vec_doubles(b.P, c->max_depth);
     const size_t PC = static_cast<size_t>(b.P) * n;
     b.chains.assign(n, b200glm::NutsChain());
@@ -66,7 +67,7 @@ struct nuts_host_backend {
     for (auto* a : {&b.Q, &b.Pm, &b.Gd, &b.IM, &b.normals, &b.metric})
       a->assign(PC, 0.0);
     b.V.assign(n, 0.0);
-    b.uniforms.assign(static_cast<size_t>(n) * b200glm::NUTS_UNIF_CAP, 0.0);
+    b.uniforms.assign(static_cast<size_t>(n) * b200glm::NUTS_UNIF_STRIDE, 0.0);
     b.draws.assign(static_cast<size_t>(n) * b200glm::nuts_draw_doubles(b.P), 0.0);
     b.status.assign(n, b200glm::NutsStatus());
     return 0;
@@ -112,7 +113,7 @@ struct nuts_host_backend {
         if (ch.need_normals
             && (ch.phase == b200glm::NPH_SS_FIRST || ch.phase == b200glm::NPH_SS_LOOP || ch.phase == b200glm::NPH_TREE))
           b200glm::nuts_begin<LN>(b.cfg, ch, v, s, b.normals.data() + static_cast<size_t>(c) * b.P,
-                                  b.uniforms.data() + static_cast<size_t>(c) * b200glm::NUTS_UNIF_CAP);
+                                  b.uniforms.data() + static_cast<size_t>(c) * b200glm::NUTS_UNIF_STRIDE);
         for (int k = 0; k < b.P; ++k) {
           z.q(k) = s.q(k);
           z.p(k) = s.p(k);
@@ -132,7 +133,7 @@ struct nuts_host_backend {
         }
         s.v() = z.V;
         b200glm::nuts_after_leapfrog<LN>(b.cfg, ch, v, s,
-                                         b.uniforms.data() + static_cast<size_t>(c) * b200glm::NUTS_UNIF_CAP,
+                                         b.uniforms.data() + static_cast<size_t>(c) * b200glm::NUTS_UNIF_STRIDE,
                                          b.draws.data() + static_cast<size_t>(c) * b200glm::nuts_draw_doubles(b.P),
                                          b.metric.data() + static_cast<size_t>(c) * b.P);
         b200glm::nuts_publish(ch, b.status[c]);

@@ -205,6 +205,10 @@ int ref_glm_leapfrog(void* h, double eps, const double* inv_metric, int init,
   });
 }
 
+// stepsize_jitter of the two NUTS entry points below (set before the call; kept out of their argument lists)
+static double g_stepsize_jitter = 0.0;
+void ref_set_stepsize_jitter(double j) { g_stepsize_jitter = j; }
+
 // Full NUTS through the reference entry point.  draws: [chain][warmup+sample][7 + P] doubles
 // (lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__, params...).
 // warm_leapfrogs[chain] receives sum(n_leapfrog__) over warm-up (save_warmup is forced on
@@ -234,7 +238,7 @@ int ref_glm_nuts(void* h, int num_chains, unsigned seed, unsigned init_chain_id,
     auto t0 = std::chrono::steady_clock::now();
     rc = stan::services::sample::hmc_nuts_diag_e_adapt(
         m, num_chains, inits, metrics, seed, init_chain_id, init_radius,
-        num_warmup, num_samples, 1, true, 0, stepsize, 0.0, max_depth, delta,
+        num_warmup, num_samples, 1, true, 0, stepsize, g_stepsize_jitter, max_depth, delta,
         0.05, 0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w,
         diag_w, metric_w);
     auto t1 = std::chrono::steady_clock::now();
@@ -295,7 +299,7 @@ int ref_glm_nuts_device_host(void* h, int num_chains, unsigned seed, unsigned in
     oracle_ref::nuts_host_backend<ref_glm_model> backend(m);
     b200::nuts_backend be = backend.table();
     rc = b200::hmc_nuts_diag_e_adapt_device(m, be, num_chains, inits, metrics, seed, init_chain_id, init_radius,
-                                            num_warmup, num_samples, 1, true, 0, stepsize, 0.0, max_depth, delta, 0.05,
+                                            num_warmup, num_samples, 1, true, 0, stepsize, g_stepsize_jitter, max_depth, delta, 0.05,
                                             0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w, diag_w,
                                             metric_w, stats);
     if (rc != 0)

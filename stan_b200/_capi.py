@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libb200glm.so")
 
 OK, DOMAIN, INVALID, CUDA = 0, 1, 2, 3
-ABI_VERSION = 4          # B200GLM_ABI_VERSION of include/b200glm.h this binding (Desc layout, signatures) was written for
+ABI_VERSION = 5          # B200GLM_ABI_VERSION of include/b200glm.h this binding (Desc layout, signatures) was written for
 FAMILY = {"bernoulli_logit": 0, "poisson_log": 1, "normal_id": 2, "binomial_logit": 3, "neg_binomial_2_log": 4,
           "ordered_logistic": 5, "categorical_logit": 6}
 
@@ -49,7 +49,7 @@ class NutsConfig(C.Structure):
                 ("w_num_warmup", C.c_uint32), ("w_init_buffer", C.c_uint32), ("w_term_buffer", C.c_uint32),
                 ("w_base_window", C.c_uint32), ("w_size0", C.c_uint32), ("w_next0", C.c_uint32),
                 ("max_deltaH", C.c_double), ("delta", C.c_double), ("gamma", C.c_double), ("kappa", C.c_double),
-                ("t0", C.c_double)]
+                ("t0", C.c_double), ("stepsize_jitter", C.c_double)]
 
 
 class NutsStatus(C.Structure):

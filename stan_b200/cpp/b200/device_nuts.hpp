@@ -51,6 +51,7 @@ struct nuts_config {
   std::int32_t max_depth, num_warmup, num_samples;
   std::uint32_t w_num_warmup, w_init_buffer, w_term_buffer, w_base_window, w_size0, w_next0;
   double max_deltaH, delta, gamma, kappa, t0;
+  double stepsize_jitter;
 };
 struct nuts_status {
   std::int32_t phase, need_normals, iter, fail_code;
@@ -59,6 +60,7 @@ struct nuts_status {
   double eps_nom;
 };
 constexpr int kNutsUnifCap = 64;      // NUTS_UNIF_CAP
+constexpr int kNutsUnifStride = 72;   // NUTS_UNIF_STRIDE: the ring, then the step-size jitter variate
 constexpr int kNutsDrawExtra = 8;     // NUTS_DRAW_EXTRA
 constexpr int kNutsPhaseDone = 5, kNutsPhaseFailed = 6;
 
@@ -156,10 +158,6 @@ int hmc_nuts_diag_e_adapt_device(Model& model, nuts_backend& be, size_t num_chai
   using stan::services::error_codes;
   const int C = static_cast<int>(num_chains);
   const int P = static_cast<int>(model.num_params_r());
-  if (stepsize_jitter != 0) {
-    logger.error("hmc_nuts_diag_e_adapt_device: stepsize_jitter is not supported (use the batched host driver)");
-    return error_codes::CONFIG;
-  }
   if (max_depth < 1 || max_depth > 16 || P < 1 || C < 1) {
     logger.error("hmc_nuts_diag_e_adapt_device: needs 1 <= max_depth <= 16, at least one parameter and one chain");
     return error_codes::CONFIG;
@@ -201,6 +199,8 @@ int hmc_nuts_diag_e_adapt_device(Model& model, nuts_backend& be, size_t num_chai
   cfg.gamma = gamma > 0 ? gamma : 0.05;
   cfg.kappa = kappa > 0 ? kappa : 0.75;
   cfg.t0 = t0 > 0 ? t0 : 10;
+  // base_hmc::set_stepsize_jitter ignores values outside [0, 1] (the constructor's 0 stays)
+  cfg.stepsize_jitter = (stepsize_jitter > 0 && stepsize_jitter < 1) ? stepsize_jitter : 0.0;
   for (int i = 0; i < C; ++i) {   // every chain's service logs the window warnings
     detail::window_probe wp;
     wp.set_window_params(num_warmup, init_buffer, term_buffer, window, logger);
@@ -322,15 +322,18 @@ int hmc_nuts_diag_e_adapt_device(Model& model, nuts_backend& be, size_t num_chai
       }
       // ---- randomness for the next round ----
       boost::uniform_01<stan::rng_t&> unif(h.rng);
-      double* ur = uniforms + static_cast<size_t>(i) * kNutsUnifCap;
+      double* ur = uniforms + static_cast<size_t>(i) * kNutsUnifStride;
       if (st.need_normals) {
         // put the engine where the reference's would be: after the normal variates of the previous refresh and the
         // uniform variates the device actually consumed since
         h.rng = h.mark;
         for (std::uint64_t k = h.base; k < st.n_unif; ++k)
           (void)unif();
-        if (st.phase == 4 /* NPH_TREE */)
+        if (st.phase == 4 /* NPH_TREE */) {
           refresh_msg(i, st.iter);
+          if (cfg.stepsize_jitter != 0)   // sample_stepsize() comes first in transition() (base_nuts.hpp:80, then :84 sample_p)
+            ur[kNutsUnifCap] = unif();
+        }
         boost::variate_generator<stan::rng_t&, boost::normal_distribution<> > gaus(h.rng, boost::normal_distribution<>());
         double* nr = normals + static_cast<size_t>(i) * P;
         for (int k = 0; k < P; ++k)

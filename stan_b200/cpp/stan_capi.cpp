@@ -279,6 +279,10 @@ int b200stan_leapfrog(void* h, double eps, const double* inv_metric, int n_steps
   });
 }
 
+// stepsize_jitter of the NUTS entry points below (the services' argument; set before the call, 0 by default)
+static double g_stepsize_jitter = 0.0;
+void b200stan_set_stepsize_jitter(double j) { g_stepsize_jitter = j; }
+
 // draws: [chain][warmup+sample][7 + P] (lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__, params)
 static int nuts_impl(void* h, int mode /* 0 reference service, 1 batched host driver, 2 device-side */, int num_chains, unsigned seed, unsigned init_chain_id, double init_radius,
                      int num_warmup, int num_samples, double stepsize, int max_depth, double delta, int num_threads,
@@ -323,18 +327,18 @@ static int nuts_impl(void* h, int mode /* 0 reference service, 1 batched host dr
       };
       be.last_error = [](void* c) { return b200glm_last_error(static_cast<b200glm_handle*>(c)); };
       rc = b200::hmc_nuts_diag_e_adapt_device(m, be, num_chains, inits, metrics, seed, init_chain_id, init_radius,
-                                              num_warmup, num_samples, 1, true, 0, stepsize, 0.0, max_depth, delta, 0.05,
+                                              num_warmup, num_samples, 1, true, 0, stepsize, g_stepsize_jitter, max_depth, delta, 0.05,
                                               0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w, diag_w,
                                               metric_w, batch_stats);
     } else if (batched)
       rc = b200::hmc_nuts_diag_e_adapt_batched(
           m, num_chains, inits, metrics, seed, init_chain_id, init_radius, num_warmup, num_samples, 1, true, 0,
-          stepsize, 0.0, max_depth, delta, 0.05, 0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w, diag_w,
+          stepsize, g_stepsize_jitter, max_depth, delta, 0.05, 0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w, diag_w,
           metric_w, batch_stats);
     else
       rc = stan::services::sample::hmc_nuts_diag_e_adapt(
           m, num_chains, inits, metrics, seed, init_chain_id, init_radius, num_warmup, num_samples, 1, true, 0,
-          stepsize, 0.0, max_depth, delta, 0.05, 0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w, diag_w,
+          stepsize, g_stepsize_jitter, max_depth, delta, 0.05, 0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w, diag_w,
           metric_w);
     auto t1 = std::chrono::steady_clock::now();
     if (wall_seconds)

@@ -1739,6 +1739,7 @@ int b200glm_nuts_reserve(b200glm_handle* h, int32_t n_chains, const b200glm_nuts
   u->cfg.w_next0 = c->w_next0;
   u->cfg.num_warmup = c->num_warmup;
   u->cfg.num_samples = c->num_samples;
+  u->cfg.stepsize_jitter = c->stepsize_jitter;
   u->vstride = nuts_vec_doubles(h->P, c->max_depth);
   u->use_graphs = !std::getenv("B200GLM_NO_GRAPH");
   CUDA_TRY(h, cudaMalloc(&u->chains, sizeof(NutsChain) * n));
@@ -1749,12 +1750,12 @@ int b200glm_nuts_reserve(b200glm_handle* h, int32_t n_chains, const b200glm_nuts
   CUDA_TRY(h, cudaMemset(u->eps_c, 0, sizeof(double) * b->ld));
   CUDA_TRY(h, cudaMalloc(&u->lanes_d, sizeof(int32_t) * b->ld));
   CUDA_TRY(h, cudaMallocHost(&u->normals, sizeof(double) * n * P));
-  CUDA_TRY(h, cudaMallocHost(&u->uniforms, sizeof(double) * n * NUTS_UNIF_CAP));
+  CUDA_TRY(h, cudaMallocHost(&u->uniforms, sizeof(double) * n * NUTS_UNIF_STRIDE));
   CUDA_TRY(h, cudaMallocHost(&u->draws, sizeof(double) * n * nuts_draw_doubles((int)P)));
   CUDA_TRY(h, cudaMallocHost(&u->metric, sizeof(double) * n * P));
   CUDA_TRY(h, cudaMallocHost(&u->status, sizeof(NutsStatus) * n));
   std::memset(u->normals, 0, sizeof(double) * n * P);
-  std::memset(u->uniforms, 0, sizeof(double) * n * NUTS_UNIF_CAP);
+  std::memset(u->uniforms, 0, sizeof(double) * n * NUTS_UNIF_STRIDE);
   std::memset(u->draws, 0, sizeof(double) * n * nuts_draw_doubles((int)P));
   std::memset(u->metric, 0, sizeof(double) * n * P);
   std::memset(u->status, 0, sizeof(NutsStatus) * n);

@@ -30,7 +30,7 @@ struct NutsDeviceParams {
   size_t ld;
   double* eps_c;              // [ld] step of every chain's next leapfrog lane (read by the batched kernels)
   const double* normals;      // pinned [C][P]
-  const double* unif;         // pinned [C][NUTS_UNIF_CAP]
+  const double* unif;         // pinned [C][NUTS_UNIF_STRIDE]
   NutsStatus* status;         // pinned [C]
   double* draws;              // pinned [C][nuts_draw_doubles(P)]
   double* metric;             // pinned [C][P]
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) nuts_begin_kernel(const NutsDeviceParams 
   NutsChain ch = p.chains[c];
   if (!ch.need_normals || !(ch.phase == NPH_SS_FIRST || ch.phase == NPH_SS_LOOP || ch.phase == NPH_TREE)) return;
   nuts_begin<NutsWarp>(p.cfg, ch, p.vec + (size_t)c * p.vstride, nuts_slot(p, c), p.normals + (size_t)c * P,
-                       p.unif + (size_t)c * NUTS_UNIF_CAP);
+                       p.unif + (size_t)c * NUTS_UNIF_STRIDE);
   __syncwarp();
   if ((threadIdx.x & 31) == 0) {
     p.chains[c] = ch;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) nuts_step_kernel(const NutsDeviceParams p
   const int c = p.lanes[i], P = p.cfg.P;
   NutsChain ch = p.chains[c];
   nuts_after_leapfrog<NutsWarp>(p.cfg, ch, p.vec + (size_t)c * p.vstride, nuts_slot(p, c),
-                                p.unif + (size_t)c * NUTS_UNIF_CAP, p.draws + (size_t)c * nuts_draw_doubles(P),
+                                p.unif + (size_t)c * NUTS_UNIF_STRIDE, p.draws + (size_t)c * nuts_draw_doubles(P),
                                 p.metric + (size_t)c * P);
   __syncwarp();
   if ((threadIdx.x & 31) == 0) {

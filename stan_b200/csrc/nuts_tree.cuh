@@ -36,6 +36,9 @@ namespace b200glm {
 
 constexpr int NUTS_DEPTH_CAP = 16;    // max_depth <= 16
 constexpr int NUTS_UNIF_CAP = 64;     // per-chain ring of uniform variates (a round consumes at most max_depth + 3)
+constexpr int NUTS_UNIF_STRIDE = NUTS_UNIF_CAP + 8;   // a chain's row of `uniforms`: the ring, then at [NUTS_UNIF_CAP] the
+                                      // step-size jitter variate of the transition about to start (drawn BEFORE the
+                                      // momentum: base_nuts.hpp:80 precedes :84), then padding to a 64-byte multiple
 constexpr int NUTS_DRAW_EXTRA = 8;    // after the P parameters: lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__,
                                       // divergent__, energy__, iteration; then the selected state's momentum (P) and
                                       // gradient (P) for the diagnostic writer (ps_point::get_params)
@@ -54,6 +57,7 @@ struct NutsConfig {
   // 15 % / 75 % / 10 % schedule the cursor is still the constructor's (size 0, next window = UINT_MAX: no metric update ever)
   unsigned w_size0, w_next0;
   int num_warmup, num_samples;           // transitions with / without adaptation
+  double stepsize_jitter;                // base_hmc::epsilon_jitter_ (0: sample_stepsize() draws nothing)
 };
 
 // offsets (in units of P doubles) into a chain's vector block
@@ -225,7 +229,8 @@ NT_HD void nuts_begin(const NutsConfig& cfg, NutsChain& ch, double* v, const Nut
   ch.H0 = t + ch.Vs;
   ch.need_normals = 0;
   if (tree) {
-    ch.eps = ch.eps_nom;   // sample_stepsize(), no jitter
+    ch.eps = ch.eps_nom;   // sample_stepsize() (base_hmc.hpp:195-200): the variate is only drawn when jitter != 0
+    if (cfg.stepsize_jitter != 0.0) ch.eps *= 1.0 + cfg.stepsize_jitter * (2.0 * unif[NUTS_UNIF_CAP] - 1.0);
     ch.lsw = 0.0;
     ch.n_leapfrog = 0;
     ch.sum_metro = 0.0;

@@ -184,9 +184,16 @@ class StanGLM:
             self._raise(rc, err)
         return q, p, g, V.value
 
+    def _set_jitter(self, j):
+        """the services' stepsize_jitter argument for the next nuts* call (base_hmc::set_stepsize_jitter keeps (0, 1) only)"""
+        self.L.b200stan_set_stepsize_jitter.argtypes = [C.c_double]
+        self.L.b200stan_set_stepsize_jitter.restype = None
+        self.L.b200stan_set_stepsize_jitter(float(j))
+
     def nuts(self, num_chains=4, seed=1, init_chain_id=1, init_radius=2.0, num_warmup=1000, num_samples=1000,
-             stepsize=1.0, max_depth=10, delta=0.8, num_threads=0):
+             stepsize=1.0, max_depth=10, delta=0.8, num_threads=0, stepsize_jitter=0.0):
         """stan::services::sample::hmc_nuts_diag_e_adapt, unmodified, on b200::glm_model."""
+        self._set_jitter(stepsize_jitter)
         W = 7 + self.P
         draws = np.empty((num_chains, num_warmup + num_samples, W))
         step, inv_metric = np.empty(num_chains), np.empty((num_chains, self.P))
@@ -213,9 +220,10 @@ class StanGLM:
         return [f"{prefix}_{init_chain_id + c}.csv" for c in range(num_chains)]
 
     def nuts_batched(self, num_chains=4, seed=1, init_chain_id=1, init_radius=2.0, num_warmup=1000, num_samples=1000,
-                     stepsize=1.0, max_depth=10, delta=0.8):
+                     stepsize=1.0, max_depth=10, delta=0.8, stepsize_jitter=0.0):
         """b200::hmc_nuts_diag_e_adapt_batched: one host thread per chain running the reference's single-chain
         service; all chains' leapfrog steps served together by one batched fp64 DMMA launch."""
+        self._set_jitter(stepsize_jitter)
         W = 7 + self.P
         draws = np.empty((num_chains, num_warmup + num_samples, W))
         step, inv_metric = np.empty(num_chains), np.empty((num_chains, self.P))
@@ -235,10 +243,11 @@ class StanGLM:
 
 
     def nuts_device(self, num_chains=4, seed=1, init_chain_id=1, init_radius=2.0, num_warmup=1000, num_samples=1000,
-                    stepsize=1.0, max_depth=10, delta=0.8):
+                    stepsize=1.0, max_depth=10, delta=0.8, stepsize_jitter=0.0):
         """b200::hmc_nuts_diag_e_adapt_device: the NUTS transition (iterative build_tree, U-turn checks, multinomial
         sampling) and the adaptation (dual averaging, Welford metric windows, init_stepsize) run per chain on the
         device right behind the batched leapfrog; the host keeps the chains' boost engines and collects the draws."""
+        self._set_jitter(stepsize_jitter)
         W = 7 + self.P
         draws = np.empty((num_chains, num_warmup + num_samples, W))
         step, inv_metric = np.empty(num_chains), np.empty((num_chains, self.P))

@@ -119,6 +119,26 @@ def test_device_nuts_other_families_first_draws(fam):
     assert max(zs) < 4.5, zs
 
 
+def test_device_nuts_with_stepsize_jitter():
+    """stepsize_jitter = 0.3 through all three drivers on the same seeds: one more uniform variate per transition, drawn
+    before the momentum (base_hmc.hpp:195-200, base_nuts.hpp:80) -- the device-side chains stay the service's chains."""
+    d = make_glm_data("bernoulli_logit", 3_000, 8)
+    m = stan_service.StanGLM("bernoulli_logit", d["X"], d["y"])
+    kw = dict(num_chains=6, seed=21, num_warmup=60, num_samples=40, delta=0.8, stepsize_jitter=0.3)
+    dev, seq, bat = m.nuts_device(**kw), m.nuts(num_threads=2, **kw), m.nuts_batched(**kw)
+    plain = m.nuts_device(**dict(kw, stepsize_jitter=0.0))
+    m.close()
+    for other in (seq, bat):
+        a, b = dev["warmup_draws"][:, :6, :], other["warmup_draws"][:, :6, :]
+        assert np.array_equal(a[:, :, 3:6], b[:, :, 3:6])
+        assert np.max(np.abs(a[:, :, 7:] - b[:, :, 7:])) < 1e-6
+        assert np.max(np.abs(a[:, :, 1:3] - b[:, :, 1:3])) < 1e-8
+    ratio = dev["draws"][:, :, 2] / dev["stepsize"][:, None]
+    assert ratio.min() >= 0.7 - 1e-9 and ratio.max() <= 1.3 + 1e-9 and ratio.std() > 0.05
+    assert np.all(plain["draws"][:, :, 2] == plain["stepsize"][:, None])
+    assert not np.array_equal(plain["warmup_draws"][:, :6, 7:], dev["warmup_draws"][:, :6, 7:])
+
+
 def test_nuts_c_abi_round_by_round():
     """b200glm_nuts_* called directly: reserve -> buffers -> init_chain -> rounds.  After the first round (gradient at
     the initial point) every chain asks for normal variates; a chain that never receives work stays where it is; the
@@ -129,7 +149,7 @@ def test_nuts_c_abi_round_by_round():
     L, h, P = _capi.lib(), m.h, m.P
     cfg = _capi.NutsConfig(max_depth=6, num_warmup=0, num_samples=3, w_num_warmup=0, w_init_buffer=0, w_term_buffer=0,
                            w_base_window=0, w_size0=0, w_next0=0xFFFFFFFF, max_deltaH=1000.0, delta=0.8, gamma=0.05,
-                           kappa=0.75, t0=10.0)
+                           kappa=0.75, t0=10.0, stepsize_jitter=0.5)
     assert L.b200glm_nuts_round(h, 1, (C.c_int32 * 1)(0)) == _capi.INVALID        # not reserved yet
     assert L.b200glm_nuts_reserve(h, 3, C.byref(cfg)) == _capi.OK
     dp = C.POINTER(C.c_double)
@@ -151,13 +171,19 @@ def test_nuts_c_abi_round_by_round():
     # drive chains 0 and 2 to the end with numpy randomness (any stream is a valid sampler; the reference's stream is
     # the driver's business): 3 transitions each
     n_rounds = 0
+    STRIDE = 72                                 # a chain's row of `uniforms`: the 64-entry ring, then the jitter variate
+    u_jitter = {0: None, 2: None}
     while any(status[c].phase not in (5, 6) for c in (0, 2)) and n_rounds < 2000:
         for c in (0, 2):
+            u = rng.random(STRIDE)
             if status[c].need_normals:
                 z = rng.standard_normal(P)
                 C.memmove(C.addressof(normals.contents) + 8 * c * P, z.ctypes.data, 8 * P)
-            u = rng.random(64)
-            C.memmove(C.addressof(unif.contents) + 8 * c * 64, u.ctypes.data, 8 * 64)
+                if status[c].phase == 4:
+                    u_jitter[c] = u[64]         # read when the transition starts
+            C.memmove(C.addressof(unif.contents) + 8 * c * STRIDE, u.ctypes.data, 8 * 64)
+            if status[c].need_normals:
+                C.memmove(C.addressof(unif.contents) + 8 * (c * STRIDE + 64), u[64:].ctypes.data, 8)
         live = [c for c in (0, 2) if status[c].phase not in (5, 6)]
         assert L.b200glm_nuts_round(h, len(live), (C.c_int32 * len(live))(*live)) == _capi.OK
         n_rounds += 1
@@ -166,6 +192,8 @@ def test_nuts_c_abi_round_by_round():
     assert status[0].eps_nom == 1.0            # num_warmup == 0: complete_adaptation leaves exp(0) (reference quirk)
     row = np.ctypeslib.as_array(draws, shape=(3, 3 * P + 8))
     assert np.all(np.isfinite(row[[0, 2]])) and row[0, P + 7] == 2 and row[0, P + 4] >= 1
+    for c in (0, 2):                           # stepsize__ = eps_nom (1 + jitter (2 u - 1)), base_hmc.hpp:195-200
+        assert row[c, P + 2] == 1.0 * (1.0 + 0.5 * (2.0 * u_jitter[c] - 1.0))
     lp, g = m.log_prob_grad(row[0, :P])
     assert abs(lp - row[0, P]) < 1e-9 * abs(lp)                                     # lp__ of the draw is the model's
     assert np.max(np.abs(row[0, 2 * P + 8:] + g)) < 1e-9 * np.max(np.abs(g))        # ... and its gradient columns (of V = -lp)

@@ -80,6 +80,25 @@ def test_schedules_and_limits(num_warmup, num_samples, max_depth, stepsize):
         assert np.all(A[:, :, 2] == 1.0)
 
 
+def test_stepsize_jitter_is_the_reference_s():
+    """stepsize_jitter > 0: sample_stepsize() (base_hmc.hpp:195-200) draws ONE uniform variate per transition, before the
+    momentum (base_nuts.hpp:80 precedes :84) -- every later variate of the chain moves by one, so any slip in the host's
+    engine bookkeeping shows in the first rows.  stepsize__ is the jittered value; dual averaging acts on the nominal one.
+    Values outside (0, 1) are ignored by base_hmc::set_stepsize_jitter."""
+    kw = dict(num_chains=2, seed=7, num_warmup=100, num_samples=40, stepsize=1.0, max_depth=10, delta=0.8)
+    a, b, A, B = _both("bernoulli_logit", 400, 5, stepsize_jitter=0.4, **kw)
+    assert np.array_equal(A[:, :, 3:6], B[:, :, 3:6])
+    e = _err(A, B).max(axis=(0, 2))
+    assert e[:20].max() < 1e-12 and e.max() < 1e-6
+    assert np.abs(a["stepsize"] - b["stepsize"]).max() < 1e-8
+    ratio = B[:, 100:, 2] / b["stepsize"][:, None]            # after warm-up: eps / eps_nom in [0.6, 1.4], not constant
+    assert ratio.min() >= 0.6 - 1e-9 and ratio.max() <= 1.4 + 1e-9 and ratio.std() > 0.1
+    a0, b0, A0, B0 = _both("bernoulli_logit", 400, 5, **kw)
+    assert not np.array_equal(A0, A)                          # the jitter changed the reference's chains ...
+    a1, b1, A1, B1 = _both("bernoulli_logit", 400, 5, stepsize_jitter=1.5, **kw)
+    assert np.array_equal(A1, A0) and np.array_equal(B1, B0)  # ... and an out-of-range value changes nothing
+
+
 def test_divergent_transitions_are_reproduced():
     """A step size far too large for a sharp posterior, no adaptation to repair it: divergent__ = 1 rows must coincide."""
     kw = dict(num_chains=2, seed=3, num_warmup=0, num_samples=60, stepsize=1.0, max_depth=10, delta=0.8)
