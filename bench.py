@@ -619,15 +619,22 @@ def ess_record(args, torch, dist, dev, rank, world, local_rank):
         t = torch.tensor([wall], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         wall = float(t.item())
-    # second arm, unsharded handles only: the same chains (same seeds) through b200::hmc_nuts_diag_e_adapt_device -- the
-    # chains advance TOGETHER, one pass over X per leapfrog of all of them (batched fp64 DMMA kernel, row-split variant
-    # for <= 16 lanes), tree building and adaptation on the device
+    # second arm: the same chains (same seeds) through b200::hmc_nuts_diag_e_adapt_device -- the chains advance
+    # TOGETHER, one pass over X per leapfrog of all of them (few-chain FMA kernel for <= 8 lanes, fp64 DMMA kernels
+    # above), tree building and adaptation on the device.  On row shards every rank passes over ITS rows
+    # for all chains and one NCCL all-reduce per round combines the (K + 2) x chains partial sums.
     dres, derr = None, None
-    if world == 1:
+    if world == 1 or not args.no_ess_device_sharded:
         try:
+            if world > 1:
+                sm.comm_init_torch(dist, dev)
             dres = sm.nuts_device(num_chains=args.ess_chains, seed=4711, num_warmup=it, num_samples=it, delta=0.8)
-        except Exception as e:   # a shape outside the batched kernel (K > 208): reported, not fatal
-            derr = str(e)[:200]
+        except Exception as e:   # a shape outside the batched kernel (K > 208): reported, not fatal (deterministic: every
+            derr = str(e)[:200]  # rank takes the same branch)
+        if dres is not None and world > 1:
+            t = torch.tensor([dres["wall"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dres["wall"] = float(t.item())
     sm.close()
     if rank != 0:
         return None
@@ -943,6 +950,9 @@ def main():
     ap.add_argument("--ess-iters", type=int, default=100,
                     help="config 2: warm-up = sampling iterations of the in-bench NUTS run (0 skips it)")
     ap.add_argument("--ess-chains", type=int, default=4)
+    ap.add_argument("--no-ess-device-sharded", action="store_true",
+                    help="N > 1: skip the device-side NUTS arm on row shards (chains advance together, one NCCL "
+                         "all-reduce per round); the unmodified service arm always runs")
     ap.add_argument("--cpu-evals", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

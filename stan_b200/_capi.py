@@ -161,6 +161,24 @@ def connect_peers_torch(handle, world, dist, dev):
     dist.barrier()
 
 
+def comm_init_torch(handle, rank, world, dist, dev):
+    """b200glm_comm_init for torch.distributed callers: rank 0 obtains the ncclUniqueId, torch.distributed broadcasts it
+    (plumbing), every rank joins the handle's own NCCL communicator.  Needed by the NCCL transport of the single-chain
+    path and by batched chains on row shards (one all-reduce of the partial sums per batched evaluation)."""
+    import torch
+    L = lib()
+    uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        buf = C.create_string_buffer(128)
+        if L.b200glm_comm_unique_id(buf) != OK:
+            raise RuntimeError("ncclGetUniqueId failed (libnccl.so.2 not loadable?)")
+        uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev)
+    dist.broadcast(uid, 0)
+    raw = bytes(uid.cpu().numpy().tobytes())
+    if L.b200glm_comm_init(handle, C.create_string_buffer(raw, 128), rank, world) != OK:
+        raise RuntimeError((L.b200glm_last_error(handle) or b"b200glm_comm_init failed").decode())
+
+
 def measure_peaks(device=0, read=True, dmma=False):
     """(read-only-stream HBM GB/s, fp64 DMMA TFLOP/s) measured now on `device`; None for what was not asked."""
     r, t = C.c_double(), C.c_double()

@@ -1427,6 +1427,18 @@ int enqueue_batched(b200glm_handle* h, int n, int mode, int propto, int jacobian
   } else
     pick_batched(h->d.family, b->mbh, row_split)<<<NCB * NS, BATCH_THREADS, row_split ? b->rs_smem : b->smem, b->stream>>>(bp);
   batched_reduce_kernel<<<(h->d.K + 2) * NCB, BATCH_CB, 0, b->stream>>>(sp);
+  if (h->d.world > 1) {
+    // row shards: every rank holds the sums over ITS rows for all chains; one all-reduce of the [K + 2][ldc] block makes
+    // them the sums over all rows, identical on every rank (so the replicated epilogue, the device-side state machines
+    // and the replicated host drivers stay in step).  The analogue of the P + 2 doubles of the single-chain path.
+    ncclResult_t r = nccl().AllReduce(b->reduced, b->reduced, (size_t)(h->d.K + 2) * sp.ldc, ncclFloat64, ncclSum,
+                                      h->comm, b->stream);
+    if (r != 0) {
+      h->set_error(std::string("ncclAllReduce (batched partial sums): ") +
+                   (nccl().GetErrorString ? nccl().GetErrorString(r) : "?"));
+      return B200GLM_CUDA;
+    }
+  }
   batched_finish_kernel<<<(n + 31) / 32, 256, 0, b->stream>>>(sp);
   h->launches += 4;
   CUDA_TRY(h, cudaGetLastError());
@@ -1460,9 +1472,14 @@ int b200glm_batch_reserve(b200glm_handle* h, int32_t max_chains) {
     delete b;
     h->batch = nullptr;
   }
-  if (h->wide || h->d.G > 0 || h->d.world > 1 || h->d.K > BATCH_MAX_K || h->d.family > B200GLM_NORMAL_ID) {
-    h->set_error("batched chains need K <= 208, a scalar intercept (G == 0), an unsharded handle and one of the "
-                 "bernoulli_logit / poisson_log / normal_id families");
+  if (h->wide || h->d.G > 0 || h->d.K > BATCH_MAX_K || h->d.family > B200GLM_NORMAL_ID) {
+    h->set_error("batched chains need K <= 208, a scalar intercept (G == 0) and one of the bernoulli_logit / poisson_log "
+                 "/ normal_id families");
+    return B200GLM_INVALID;
+  }
+  if (h->d.world > 1 && !h->comm) {   // row shards: the slice sums of all chains are combined by ONE all-reduce per round
+    h->set_error("batched chains on a row-sharded handle need b200glm_comm_init first (one NCCL all-reduce of the "
+                 "(K + 2) x chains partial sums per batched evaluation)");
     return B200GLM_INVALID;
   }
   CUDA_TRY(h, cudaSetDevice(h->d.device));
@@ -1741,7 +1758,7 @@ int b200glm_nuts_reserve(b200glm_handle* h, int32_t n_chains, const b200glm_nuts
   u->cfg.num_samples = c->num_samples;
   u->cfg.stepsize_jitter = c->stepsize_jitter;
   u->vstride = nuts_vec_doubles(h->P, c->max_depth);
-  u->use_graphs = !std::getenv("B200GLM_NO_GRAPH");
+  u->use_graphs = !std::getenv("B200GLM_NO_GRAPH") && h->d.world <= 1;   // row shards: the round contains a collective
   CUDA_TRY(h, cudaMalloc(&u->chains, sizeof(NutsChain) * n));
   CUDA_TRY(h, cudaMemset(u->chains, 0, sizeof(NutsChain) * n));
   CUDA_TRY(h, cudaMalloc(&u->vec, sizeof(double) * u->vstride * n));

@@ -348,6 +348,10 @@ class GLMModel:
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self._check(self.L.b200glm_comm_init(self.h, buf, self.rank, self.world))
 
+    def comm_init_torch(self, dist, dev):
+        """comm_init with the unique id broadcast over torch.distributed (plumbing)."""
+        _capi.comm_init_torch(self.h, self.rank, self.world, dist, dev)
+
     def peer_export(self):
         """64-byte IPC handle of this rank's mailbox (gather over ranks, then peer_connect)."""
         buf = C.create_string_buffer(64)

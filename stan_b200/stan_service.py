@@ -121,6 +121,12 @@ class StanGLM:
         the gradient / leapfrog launch over NVLink; no collective call per gradient)."""
         _capi.connect_peers_torch(C.c_void_p(self.L.b200stan_backend_handle(self.h)), self.world, dist, dev)
 
+    def comm_init_torch(self, dist, dev):
+        """Row-sharded model: join the backend handle's NCCL communicator (needed by nuts_device / nuts_batched on row
+        shards: the partial sums of all chains are combined by one all-reduce per round; the single-chain path keeps
+        the in-kernel mailbox exchange when connect_peers_torch was called as well)."""
+        _capi.comm_init_torch(C.c_void_p(self.L.b200stan_backend_handle(self.h)), self.rank, self.world, dist, dev)
+
     def close(self):
         if getattr(self, "h", None):
             self.L.b200stan_destroy(self.h)

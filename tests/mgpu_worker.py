@@ -99,6 +99,86 @@ def class_outcome_models_sharded(rank, world, local, dev):
     return failures
 
 
+def batched_chains_on_row_shards(rank, world, local, dev):
+    """Several chains per pass over a ROW-SHARDED X (few-chain FMA kernel for <= 8 lanes, DMMA kernels above): every
+    rank sums its rows for all chains, one NCCL all-reduce of the (K + 2) x chains block per batched evaluation.  ==
+    the unsharded oracle chain by chain, bitwise identical on every rank, batched leapfrog included; then the
+    device-side NUTS driver on row shards == the same driver on the unsharded model (same seeds)."""
+    failures = []
+    from oracle.oracle import PortOracle
+    for fam, N, K, Cn in [("bernoulli_logit", 120_003, 40, 4), ("poisson_log", 60_001, 20, 7), ("normal_id", 90_001, 33, 20)]:
+        d = make_glm_data(fam, N, K)
+        r0, r1 = shard_rows(N, rank, world)
+        m = GLMModel(fam, d["X"][r0:r1], d["y"][r0:r1], device=local, rank=rank, world=world, N_total=N)
+        try:
+            m.batch_reserve(Cn)
+            failures.append(f"{fam}: batch_reserve before comm_init was accepted on a sharded handle")
+        except Exception:
+            pass
+        m.comm_init_torch(dist, dev)
+        m.batch_reserve(Cn)
+        rng = np.random.default_rng(8)
+        th = 0.1 * rng.standard_normal((Cn, m.P))
+        p0 = rng.standard_normal((Cn, m.P))
+        lp, g, st = m.log_prob_grad_batched(th)
+        m.set_state_batched(th, p0, -g, -lp)
+        for _ in range(3):
+            q1, p1, g1, V1, st1 = m.leapfrog_batched(np.full(Cn, 1e-3))
+        buf = torch.tensor(np.concatenate([lp, V1, g.ravel(), q1.ravel(), p1.ravel()]), device=dev)
+        ref = buf.clone()
+        dist.broadcast(ref, 0)
+        if not torch.equal(buf, ref):
+            failures.append(f"{fam} batched on shards: ranks disagree")
+        if st.any() or np.any(st1):
+            failures.append(f"{fam} batched on shards: status {st} {st1}")
+        if rank == 0:
+            po = PortOracle(fam, d["X"], d["y"])
+            e = 0.0
+            for c in range(Cn):
+                lp_r, g_r = po.log_prob_grad(th[c])
+                sc = np.maximum(np.abs(g_r), np.abs(g_r).max())
+                e = max(e, abs(lp[c] - lp_r) / abs(lp_r), float(np.max(np.abs(g[c] - g_r) / sc)))
+                q, p, gg, V = th[c], p0[c], -g_r, -lp_r
+                for _ in range(3):
+                    q, p, gg, V = po.leapfrog(1e-3, np.ones(m.P), q, p, gg, V)
+                e = max(e, float(np.max(np.abs(q1[c] - q))), abs(V1[c] - V) / abs(V))
+            if not e < 1e-10:
+                failures.append(f"{fam} batched on shards: err {e}")
+            print(f"{fam} N={N} K={K} chains={Cn} batched on row shards, world={world}: max err {e:.2e}", flush=True)
+        m.close()
+    from stan_b200 import stan_service
+    if stan_service.available():
+        N, K = 80_001, 10
+        d = make_glm_data("bernoulli_logit", N, K)
+        r0, r1 = shard_rows(N, rank, world)
+        kw = dict(num_chains=4, seed=31, num_warmup=80, num_samples=40, delta=0.8)
+        m = stan_service.StanGLM("bernoulli_logit", d["X"][r0:r1], d["y"][r0:r1], device=local, n_slots=1, rank=rank,
+                                 world=world, N_total=N)
+        m.connect_peers_torch(dist, dev)       # util::initialize's single-chain gradients: in-kernel exchange
+        m.comm_init_torch(dist, dev)           # the batched rounds: one all-reduce each
+        res = m.nuts_device(**kw)
+        m.close()
+        buf = torch.tensor(np.concatenate([res["draws"].ravel(), res["warmup_draws"].ravel()]), device=dev)
+        ref = buf.clone()
+        dist.broadcast(ref, 0)
+        if not torch.equal(buf, ref):
+            failures.append("device NUTS on row shards: ranks hold different draws")
+        if rank == 0:
+            one = stan_service.StanGLM("bernoulli_logit", d["X"], d["y"], device=local, n_slots=1)
+            full = one.nuts_device(**kw)
+            one.close()
+            a, b = res["warmup_draws"][:, :5, :], full["warmup_draws"][:, :5, :]
+            if not (np.array_equal(a[:, :, 3:6], b[:, :, 3:6]) and np.max(np.abs(a[:, :, 7:] - b[:, :, 7:])) < 1e-6):
+                failures.append("device NUTS on row shards: first draws differ from the unsharded model")
+            ma, mb = res["draws"][:, :, 7:].mean(axis=(0, 1)), full["draws"][:, :, 7:].mean(axis=(0, 1))
+            sd = full["draws"][:, :, 7:].std(axis=(0, 1))
+            if not np.all(np.abs(ma - mb) < 1.0 * sd):
+                failures.append("device NUTS on row shards: posterior means off")
+            print(f"device NUTS on row shards world={world}: {res['rounds']} rounds, wall {res['wall']:.2f} s "
+                  f"(unsharded {full['wall']:.2f} s)", flush=True)
+    return failures
+
+
 def bad_y_is_reported_by_every_rank(rank, world, local, dev):
     """An out-of-range y held by ONE shard (the reference checks y on every call, poisson_log_glm_lpmf.hpp:84) must
     make every rank return the domain error, not only the rank that holds it -- otherwise the replicated host code
@@ -188,6 +268,7 @@ def main():
             print(f"{fam} N={N} K={K} G={G} world={world}: max err {e:.2e}", flush=True)
         m.close()
     failures += class_outcome_models_sharded(rank, world, local, dev)
+    failures += batched_chains_on_row_shards(rank, world, local, dev)
     failures += bad_y_is_reported_by_every_rank(rank, world, local, dev)
     failures += nuts_through_the_reference_service(rank, world, local, dev)
     n_fail = torch.tensor([len(failures)], device=dev)
