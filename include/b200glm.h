@@ -183,7 +183,9 @@ const double* b200glm_result_device(b200glm_handle* h, int32_t slot);
  * fp64 GEMMs on the DMMA tensor path (BASELINE configs[2]).  This is the device side of a multi-chain
  * driver in ST/services/sample (hmc_nuts_diag_e_adapt.hpp:364-401 runs chains as independent TBB
  * tasks, each calling stan::model::gradient on its own; here the calls of all chains that are waiting
- * for a leapfrog step are served together).  Requires K <= 208, G == 0, world == 1.  Batches of <= 8 lanes with
+ * for a leapfrog step are served together).  Requires K <= 208, G == 0; on a row-sharded handle (world > 1)
+ * b200glm_comm_init must have been called: every rank sums its rows for all chains and one NCCL all-reduce of the
+ * (K + 2) x chains block per batched evaluation combines them (identical on every rank).  Batches of <= 8 lanes with
  * K <= 128 take glm_multi_kernel: four chains per pass on the FMA path (5-8 lanes: two passes), HBM-bound like the
  * single-chain kernel.
  * All per-chain arrays are chain-major HOST arrays: theta[i*P + k] belongs to lane i.
