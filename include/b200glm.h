@@ -52,7 +52,7 @@ enum { B200GLM_OK = 0, B200GLM_DOMAIN = 1, B200GLM_INVALID = 2, B200GLM_CUDA = 3
 
 /* SM/prim/prob/{bernoulli_logit_glm_lpmf.hpp:49, poisson_log_glm_lpmf.hpp:51, normal_id_glm_lpdf.hpp:54,
  * binomial_logit_glm_lpmf.hpp:55, neg_binomial_2_log_glm_lpmf.hpp:64}.  The last two run in
- * the single-chain kernels (narrow and wide-matrix); the batched DMMA kernel serves families 0-2. */
+ * the single-chain kernels (narrow and wide-matrix); the batched kernels (DMMA and few-chain) serve families 0-3. */
 enum { B200GLM_BERNOULLI_LOGIT = 0, B200GLM_POISSON_LOG = 1, B200GLM_NORMAL_ID = 2, B200GLM_BINOMIAL_LOGIT = 3,
        B200GLM_NEG_BINOMIAL_2_LOG = 4,
        /* SM/prim/prob/ordered_logistic_glm_lpmf.hpp:49 and categorical_logit_glm_lpmf.hpp:47 -- class-outcome models

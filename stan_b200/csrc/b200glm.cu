@@ -1315,6 +1315,7 @@ batched_fn pick_batched_rs(int family, int mbh) {
     case FAM_BERNOULLI_LOGIT: return pick_batched_mbh<FAM_BERNOULLI_LOGIT, RS>(mbh);
     case FAM_POISSON_LOG: return pick_batched_mbh<FAM_POISSON_LOG, RS>(mbh);
     case FAM_NORMAL_ID: return pick_batched_mbh<FAM_NORMAL_ID, RS>(mbh);
+    case FAM_BINOMIAL_LOGIT: return pick_batched_mbh<FAM_BINOMIAL_LOGIT, RS>(mbh);
   }
   return nullptr;
 }
@@ -1339,6 +1340,7 @@ batched_fn pick_multi(int family, int cpl) {
     case FAM_BERNOULLI_LOGIT: return pick_multi_cpl<FAM_BERNOULLI_LOGIT>(cpl);
     case FAM_POISSON_LOG: return pick_multi_cpl<FAM_POISSON_LOG>(cpl);
     case FAM_NORMAL_ID: return pick_multi_cpl<FAM_NORMAL_ID>(cpl);
+    case FAM_BINOMIAL_LOGIT: return pick_multi_cpl<FAM_BINOMIAL_LOGIT>(cpl);
   }
   return nullptr;
 }
@@ -1472,9 +1474,9 @@ int b200glm_batch_reserve(b200glm_handle* h, int32_t max_chains) {
     delete b;
     h->batch = nullptr;
   }
-  if (h->wide || h->d.G > 0 || h->d.K > BATCH_MAX_K || h->d.family > B200GLM_NORMAL_ID) {
+  if (h->wide || h->d.G > 0 || h->d.K > BATCH_MAX_K || h->d.family > B200GLM_BINOMIAL_LOGIT) {
     h->set_error("batched chains need K <= 208, a scalar intercept (G == 0) and one of the bernoulli_logit / poisson_log "
-                 "/ normal_id families");
+                 "/ normal_id / binomial_logit families");
     return B200GLM_INVALID;
   }
   if (h->d.world > 1 && !h->comm) {   // row shards: the slice sums of all chains are combined by ONE all-reduce per round

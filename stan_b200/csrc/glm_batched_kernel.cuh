@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
     for (int mi = 0; mi < 2; ++mi) {
       const int row = 16 * mp + 8 * mi + lq;
       const double y = tile[ycol + (row ^ ysw)];
+      const double aux = FAMILY == FAM_BINOMIAL_LOGIT ? tile[ycol + 32 + (row ^ (((p.K + 1) & 3) << 2))] : 0.0;   // population size
       const bool valid = pi * 32 + row < p.n_rows;
 #pragma unroll
       for (int ni = 0; ni < 2; ++ni) {
@@ -225,7 +226,12 @@ __global__ void __launch_bounds__(BATCH_THREADS, 1) glm_batched_kernel(const Bat
 #pragma unroll
         for (int e2 = 0; e2 < 2; ++e2) {
           double lp_i, r_i;
-          link<FAMILY>(e[mi][ni][e2] + (e2 ? al.y : al.x), y, e2 ? is.y : is.x, lp_i, r_i);
+          if (FAMILY == FAM_BINOMIAL_LOGIT) {
+            double x_i;
+            link_ext<FAMILY>(e[mi][ni][e2] + (e2 ? al.y : al.x), y, aux, LinkConst(), lp_i, r_i, x_i);
+          } else {
+            link<FAMILY>(e[mi][ni][e2] + (e2 ? al.y : al.x), y, e2 ? is.y : is.x, lp_i, r_i);
+          }
           if (!valid) {
             lp_i = 0.0;
             r_i = 0.0;
@@ -488,9 +494,9 @@ __global__ void __launch_bounds__(256) batched_finish_kernel(const BatchedStepPa
       if (mc.N_total > 0) {
         if (mc.family == FAM_BERNOULLI_LOGIT) {
           lp += S;
-        } else if (mc.family == FAM_POISSON_LOG) {
+        } else if (mc.family == FAM_POISSON_LOG || mc.family == FAM_BINOMIAL_LOGIT) {
           lp += S;
-          if (!mc.propto) lp -= mc.lgamma_sum;
+          if (!mc.propto) lp -= mc.lgamma_sum;   // poisson_log_glm_lpmf.hpp:127-129, binomial_logit_glm_lpmf.hpp:127-130
         } else {
           if (!mc.propto) lp += NEG_LOG_SQRT_TWO_PI_D * mc.N_total;
           lp -= mc.N_total * u_s;

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(MULTI_THREADS, 1) glm_multi_kernel(const Batch
     const int rg = lane & 3, cg = lane >> 2, cgl = cg & 3;
     const int o1 = lane ^ 4, o2 = lane ^ 8, o3 = lane ^ 12;
     const int ycol = K * 32 + (lane ^ ((K & 3) << 2));
+    const int tcol = (K + 1) * 32 + (lane ^ (((K + 1) & 3) << 2));   // binomial_logit: population sizes
     int off[8];
 #pragma unroll
     for (int m = 0; m < 8; ++m) off[m] = rg + 4 * (m ^ cgl);
@@ -149,12 +150,13 @@ __global__ void __launch_bounds__(MULTI_THREADS, 1) glm_multi_kernel(const Batch
           for (int c = 0; c < NCH; ++c) ea[c] = fma(x, sbeta[(size_t)k * NCH + c], ea[c]);
         }
         const double y = tile[ycol];
+        const double aux = FAMILY == FAM_BINOMIAL_LOGIT ? tile[tcol] : 0.0;
         const bool valid = (pi * PANEL_ROWS + lane) < p.n_rows;
         double rres[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           double lp_i, r_i;
-          link_bf<FAMILY>((ea[c] + eb[c]) + salpha[c], y, sisig[c], lp_i, r_i);   // branch-free: the chains interleave
+          link_bf<FAMILY>((ea[c] + eb[c]) + salpha[c], y, sisig[c], lp_i, r_i, aux);   // branch-free: the chains interleave
           if (!valid) {
             lp_i = 0.0;
             r_i = 0.0;

@@ -62,10 +62,19 @@ double digamma_host(double v) { return digamma_pos(v); }
 
 // link<> and its branch-free form link_bf<> (glm_multi_kernel.cuh uses the latter) on the same rows, and the special
 // functions of link_bf on their own
+// (binomial_logit: aux = population sizes, link_ext<> is the reference form)
 int link_pair_rows(int family, int n, const double* eta, const double* y, double inv_sigma, double* lp, double* r,
-                   double* lp_bf, double* r_bf) {
+                   double* lp_bf, double* r_bf, const double* aux) {
+  LinkConst lc;
+  memset(&lc, 0, sizeof(lc));
   for (int i = 0; i < n; ++i) {
     switch (family) {
+      case FAM_BINOMIAL_LOGIT: {
+        double x;
+        link_ext<FAM_BINOMIAL_LOGIT>(eta[i], y[i], aux[i], lc, lp[i], r[i], x);
+        link_bf<FAM_BINOMIAL_LOGIT>(eta[i], y[i], inv_sigma, lp_bf[i], r_bf[i], aux[i]);
+        break;
+      }
       case FAM_BERNOULLI_LOGIT:
         link<FAM_BERNOULLI_LOGIT>(eta[i], y[i], inv_sigma, lp[i], r[i]);
         link_bf<FAM_BERNOULLI_LOGIT>(eta[i], y[i], inv_sigma, lp_bf[i], r_bf[i]);

@@ -253,3 +253,66 @@ def test_few_chain_fma_kernel(fam, N, K, monkeypatch):
         assert rel_err(Vd[i], ref[i][3]) < 1e-9
     m.close()
     m_dmma.close()
+
+
+@pytest.mark.parametrize("N,K", [(9_001, 100), (4_000, 17), (2_500, 22), (31, 3)])
+def test_binomial_logit_in_the_batched_kernels(N, K):
+    """binomial_logit_glm (population sizes in panel column K + 1) through all three batched kernels: the few-chain FMA
+    kernel (<= 8 lanes; branch-free link_bf<>), the row-split DMMA variant (9-16 lanes) and the DMMA kernel (40 lanes;
+    link_ext<>): per chain against the oracle, the kernels against each other and against the single-chain kernel to
+    rounding, propto on / off (the binomial-coefficient constant), and three leapfrog steps."""
+    from oracle.oracle import PortOracle
+    fam = "binomial_logit"
+    d = make_glm_data(fam, N, K)
+    po = PortOracle(fam, d["X"], d["y"], trials=d["trials"])
+    m = GLMModel(fam, d["X"], d["y"], trials=d["trials"])
+    m.batch_reserve(64)
+    rng = np.random.default_rng(17)
+    th = 0.1 * rng.standard_normal((40, m.P))
+    big = {}
+    for propto, jac in ((1, 1), (0, 1)):
+        lp_big, g_big, st = m.log_prob_grad_batched(th, propto, jac)       # 40 lanes: DMMA kernel
+        assert not st.any()
+        big[propto] = (lp_big, g_big)
+        for c in (0, 1, 17, 39):
+            lp_r, g_r = po.log_prob_grad(th[c], propto, jac)
+            assert rel_err(lp_big[c], lp_r) < TOL and rel_err_vec(g_big[c], g_r) < TOL, (propto, c)
+    lp_big, g_big = big[1]
+    lp1, g1 = m.log_prob_grad(th[1])
+    assert rel_err(lp_big[1], lp1) < 1e-12 and rel_err_vec(g_big[1], g1) < 1e-12
+    for n in (1, 4, 7, 12):                                                 # few-chain kernel (<= 8), row-split (12)
+        lp, g, st = m.log_prob_grad_batched(th[:n])
+        assert not st.any()
+        for c in range(n):
+            lp_r, g_r = po.log_prob_grad(th[c])
+            assert rel_err(lp[c], lp_r) < TOL and rel_err_vec(g[c], g_r) < TOL, (n, c)
+            assert rel_err(lp[c], lp_big[c]) < 1e-12 and rel_err_vec(g[c], g_big[c]) < 1e-12, (n, c)
+    q, p = th[:5].copy(), rng.standard_normal((5, m.P))
+    lp, g, _ = m.log_prob_grad_batched(q)
+    m.set_state_batched(q, p, -g, -lp)
+    eps = 1e-3 * (1 + rng.random(5))
+    ref = [(q[i], p[i], -g[i], -lp[i]) for i in range(5)]
+    for _ in range(3):
+        qd, pd, gd, Vd, st = m.leapfrog_batched(eps)
+        ref = [po.leapfrog(eps[i], np.ones(m.P), *ref[i]) for i in range(5)]
+    for i in range(5):
+        assert rel_err_vec(qd[i], ref[i][0]) < 1e-9 and rel_err_vec(gd[i], ref[i][2]) < 1e-9
+        assert rel_err(Vd[i], ref[i][3]) < 1e-9
+    m.close()
+
+
+def test_binomial_logit_device_nuts_matches_the_service():
+    """Device-side NUTS on a binomial_logit model (few-chain kernel, 4 chains) == the unmodified service, same seeds."""
+    from stan_b200 import stan_service
+    if not stan_service.available():
+        pytest.skip("libb200stan.so not built")
+    d = make_glm_data("binomial_logit", 3_000, 6)
+    m = stan_service.StanGLM("binomial_logit", d["X"], d["y"], trials=d["trials"])
+    kw = dict(num_chains=4, seed=5, num_warmup=60, num_samples=30, delta=0.8)
+    dev, seq = m.nuts_device(**kw), m.nuts(num_threads=2, **kw)
+    m.close()
+    a, b = dev["warmup_draws"][:, :5, :], seq["warmup_draws"][:, :5, :]
+    assert np.array_equal(a[:, :, 3:6], b[:, :, 3:6])
+    assert np.max(np.abs(a[:, :, 7:] - b[:, :, 7:])) < 1e-6
+    assert np.abs(dev["draws"][:, :, 7:].mean(axis=(0, 1)) - seq["draws"][:, :, 7:].mean(axis=(0, 1))).max() < \
+        1.0 * seq["draws"][:, :, 7:].std(axis=(0, 1)).max()

@@ -205,7 +205,7 @@ def test_fast_exp_and_log1p_against_libm(host_lib):
     assert np.max(np.abs(rw * (1.0 + u) - 1.0)) < 4e-16
 
 
-@pytest.mark.parametrize("fam", [0, 1, 2])
+@pytest.mark.parametrize("fam", [0, 1, 2, 3])
 def test_branch_free_link_equals_link(host_lib, fam):
     """link_bf<> against link<> row by row: random etas, the bernoulli cut-offs from both sides, huge |eta|, infinities
     and NaN (which branch is taken and what propagates must be the same), both outcomes."""
@@ -215,7 +215,11 @@ def test_branch_free_link_equals_link(host_lib, fam):
                           [20.0, -20.0, np.nextafter(20.0, 30), np.nextafter(20.0, 0), np.nextafter(-20.0, -30),
                            np.nextafter(-20.0, 0), 0.0, 50.0, -50.0, 699.0, -699.0, 705.0, -705.0, 745.0, -745.0, 800.0,
                            -800.0, 1e6, -1e6, np.inf, -np.inf, np.nan]])
-    if fam == 1:
+    aux = np.zeros(eta.size)
+    if fam == 3:                                              # binomial_logit: population sizes incl. 0, y in [0, n]
+        aux = rng.integers(0, 40, eta.size).astype(float)
+        y = np.floor(rng.uniform(0, 1, eta.size) * (aux + 1))
+    elif fam == 1:
         y = rng.poisson(3.0, eta.size).astype(float)
     elif fam == 0:
         y = rng.integers(0, 2, eta.size).astype(float)
@@ -223,7 +227,7 @@ def test_branch_free_link_equals_link(host_lib, fam):
         y = rng.normal(0, 2, eta.size)
     n = eta.size
     lp, r, lpb, rb = (np.empty(n) for _ in range(4))
-    assert host_lib.link_pair_rows(fam, n, dp(eta), dp(y), C.c_double(0.7), dp(lp), dp(r), dp(lpb), dp(rb)) == 0
+    assert host_lib.link_pair_rows(fam, n, dp(eta), dp(y), C.c_double(0.7), dp(lp), dp(r), dp(lpb), dp(rb), dp(aux)) == 0
     with np.errstate(invalid="ignore", over="ignore"):
         for a, b in ((lp, lpb), (r, rb)):
             assert np.array_equal(np.isnan(a), np.isnan(b))
@@ -234,4 +238,10 @@ def test_branch_free_link_equals_link(host_lib, fam):
             big = fin & ~tiny
             # poisson: y eta - exp(eta) cancels; measure against the larger term
             scale = np.maximum(np.abs(a[big]), np.abs(y[big] * eta[big]) if fam == 1 else 0.0)
-            assert np.max(np.abs(a[big] - b[big]) / scale) < 1e-15 * (8 if fam == 1 else 4)
+            tol = 1e-15 * (8 if fam == 1 else 4)
+            if fam == 3:
+                # r = y - n inv_logit(eta) cancels: measure against y; the reference forms inv_logit as exp(log_inv_logit),
+                # whose own rounding error grows like |eta| ulp -- the branch-free form (a reciprocal) is the tighter one
+                scale = np.maximum(scale, y[big])
+                tol = 4e-15 + 2.5e-16 * np.abs(eta[big])
+            assert np.all(np.abs(a[big] - b[big]) / scale < tol)
