@@ -170,11 +170,12 @@ def comm_init_torch(handle, rank, world, dist, dev):
     uid = torch.zeros(128, dtype=torch.uint8, device=dev)
     if rank == 0:
         buf = C.create_string_buffer(128)
-        if L.b200glm_comm_unique_id(buf) != OK:
-            raise RuntimeError("ncclGetUniqueId failed (libnccl.so.2 not loadable?)")
-        uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev)
+        if L.b200glm_comm_unique_id(buf) == OK:      # on failure the zero id is broadcast: EVERY rank raises below
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev)
     dist.broadcast(uid, 0)
     raw = bytes(uid.cpu().numpy().tobytes())
+    if not any(raw):
+        raise RuntimeError("ncclGetUniqueId failed on rank 0 (libnccl.so.2 not loadable?)")
     if L.b200glm_comm_init(handle, C.create_string_buffer(raw, 128), rank, world) != OK:
         raise RuntimeError((L.b200glm_last_error(handle) or b"b200glm_comm_init failed").decode())
 
