@@ -208,6 +208,15 @@ int ref_glm_leapfrog(void* h, double eps, const double* inv_metric, int init,
 // stepsize_jitter of the two NUTS entry points below (set before the call; kept out of their argument lists)
 static double g_stepsize_jitter = 0.0;
 void ref_set_stepsize_jitter(double j) { g_stepsize_jitter = j; }
+// initial diagonal inverse metric of every chain for the two NUTS entry points below (n = 0: the unit metric)
+static std::vector<double> g_init_inv_metric;
+void ref_set_init_inv_metric(const double* m, int n) { g_init_inv_metric.assign(m, m + (n > 0 ? n : 0)); }
+static stan::io::array_var_context init_metric_context(int P) {
+  if (static_cast<int>(g_init_inv_metric.size()) != P)
+    return stan::services::util::create_unit_e_diag_inv_metric(P);
+  return stan::io::array_var_context(std::vector<std::string>{"inv_metric"}, g_init_inv_metric,
+                                     std::vector<std::vector<size_t>>{{static_cast<size_t>(P)}});
+}
 
 // Full NUTS through the reference entry point.  draws: [chain][warmup+sample][7 + P] doubles
 // (lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__, params...).
@@ -227,8 +236,7 @@ int ref_glm_nuts(void* h, int num_chains, unsigned seed, unsigned init_chain_id,
     std::vector<std::shared_ptr<stan::io::var_context>> inits, metrics;
     for (int c = 0; c < num_chains; ++c) {
       inits.emplace_back(std::make_shared<stan::io::empty_var_context>());
-      metrics.emplace_back(std::make_shared<stan::io::array_var_context>(
-          stan::services::util::create_unit_e_diag_inv_metric(P)));
+      metrics.emplace_back(std::make_shared<stan::io::array_var_context>(init_metric_context(P)));
     }
     stan::callbacks::interrupt interrupt;
     err_logger logger;
@@ -288,8 +296,7 @@ int ref_glm_nuts_device_host(void* h, int num_chains, unsigned seed, unsigned in
     std::vector<std::shared_ptr<stan::io::var_context>> inits, metrics;
     for (int c = 0; c < num_chains; ++c) {
       inits.emplace_back(std::make_shared<stan::io::empty_var_context>());
-      metrics.emplace_back(std::make_shared<stan::io::array_var_context>(
-          stan::services::util::create_unit_e_diag_inv_metric(P)));
+      metrics.emplace_back(std::make_shared<stan::io::array_var_context>(init_metric_context(P)));
     }
     stan::callbacks::interrupt interrupt;
     err_logger logger;

@@ -99,6 +99,24 @@ def test_stepsize_jitter_is_the_reference_s():
     assert np.array_equal(A1, A0) and np.array_equal(B1, B0)  # ... and an out-of-range value changes nothing
 
 
+@pytest.mark.parametrize("num_warmup", [10, 120])
+def test_initial_inverse_metric_is_used(num_warmup):
+    """A non-unit diagonal inverse metric handed in through the init_inv_metric contexts (read_diag_inv_metric,
+    hmc_nuts_diag_e_adapt.hpp:76-79): momenta are drawn with it, the sharp momenta of the U-turn checks use it, and with
+    num_warmup < 20 it is never replaced -- the chains must stay the reference's, and differ from the unit-metric ones."""
+    im = np.exp(np.random.default_rng(2).normal(0, 0.7, 6))          # alpha + 5 betas
+    kw = dict(num_chains=2, seed=13, num_warmup=num_warmup, num_samples=30, stepsize=0.5, max_depth=10, delta=0.8)
+    a, b, A, B = _both("bernoulli_logit", 400, 5, init_inv_metric=im, **kw)
+    assert np.array_equal(A[:, :, 3:6], B[:, :, 3:6])
+    e = _err(A, B).max(axis=(0, 2))
+    assert e[:20].max() < 1e-12 and e.max() < 1e-6
+    assert np.abs(a["inv_metric"] - b["inv_metric"]).max() < 1e-8
+    if num_warmup < 20:
+        assert np.allclose(b["inv_metric"], im[None, :], rtol=0, atol=1e-15)
+    a0, b0, A0, B0 = _both("bernoulli_logit", 400, 5, **kw)
+    assert not np.array_equal(B0[:, :5, 7:], B[:, :5, 7:])
+
+
 def test_divergent_transitions_are_reproduced():
     """A step size far too large for a sharp posterior, no adaptation to repair it: divergent__ = 1 rows must coincide."""
     kw = dict(num_chains=2, seed=3, num_warmup=0, num_samples=60, stepsize=1.0, max_depth=10, delta=0.8)
