@@ -285,16 +285,25 @@ class RefOracle:
             m = np.ascontiguousarray(m, dtype=np.float64)
             self.L.ref_set_init_inv_metric(_dp(m), int(m.size))
 
+    def _set_adapt(self, adapt):
+        """adapt: None (the services' defaults) or dict(gamma, kappa, t0, init_buffer, term_buffer, window)"""
+        a = dict(gamma=0.05, kappa=0.75, t0=10.0, init_buffer=75, term_buffer=50, window=25)
+        a.update(adapt or {})
+        self.L.ref_set_adapt_params.argtypes = [C.c_double, C.c_double, C.c_double, C.c_uint, C.c_uint, C.c_uint]
+        self.L.ref_set_adapt_params.restype = None
+        self.L.ref_set_adapt_params(a["gamma"], a["kappa"], a["t0"], a["init_buffer"], a["term_buffer"], a["window"])
+
     def _set_jitter(self, j):
         self.L.ref_set_stepsize_jitter.argtypes = [C.c_double]
         self.L.ref_set_stepsize_jitter.restype = None
         self.L.ref_set_stepsize_jitter(float(j))
 
     def nuts(self, num_chains=4, seed=1, init_chain_id=1, init_radius=2.0, num_warmup=1000, num_samples=1000,
-             stepsize=1.0, max_depth=10, delta=0.8, num_threads=0, stepsize_jitter=0.0, init_inv_metric=None):
+             stepsize=1.0, max_depth=10, delta=0.8, num_threads=0, stepsize_jitter=0.0, init_inv_metric=None, adapt=None):
         W = 7 + self.P
         self._set_jitter(stepsize_jitter)
         self._set_init_inv_metric(init_inv_metric)
+        self._set_adapt(adapt)
         draws = np.empty((num_chains, num_warmup + num_samples, W))
         step = np.empty(num_chains)
         inv_metric = np.empty((num_chains, self.P))
@@ -311,13 +320,14 @@ class RefOracle:
                     inv_metric=inv_metric, warm_leapfrogs=warm_lf, wall=wall.value)
 
     def nuts_device_host(self, num_chains=4, seed=1, init_chain_id=1, init_radius=2.0, num_warmup=1000, num_samples=1000,
-                         stepsize=1.0, max_depth=10, delta=0.8, stepsize_jitter=0.0, init_inv_metric=None):
+                         stepsize=1.0, max_depth=10, delta=0.8, stepsize_jitter=0.0, init_inv_metric=None, adapt=None):
         """The PRODUCT's device-NUTS driver and per-chain state machine (stan_b200/cpp/b200/device_nuts.hpp,
         stan_b200/csrc/nuts_tree.cuh) built for the host over the reference's model and integrator
         (oracle/ref/nuts_host_backend.hpp): the CPU check of SURVEY 8f row 2.  Same outputs as nuts()."""
         W = 7 + self.P
         self._set_jitter(stepsize_jitter)
         self._set_init_inv_metric(init_inv_metric)
+        self._set_adapt(adapt)
         draws = np.empty((num_chains, num_warmup + num_samples, W))
         step = np.empty(num_chains)
         inv_metric = np.empty((num_chains, self.P))

@@ -208,6 +208,18 @@ int ref_glm_leapfrog(void* h, double eps, const double* inv_metric, int init,
 // stepsize_jitter of the two NUTS entry points below (set before the call; kept out of their argument lists)
 static double g_stepsize_jitter = 0.0;
 void ref_set_stepsize_jitter(double j) { g_stepsize_jitter = j; }
+// gamma, kappa, t0, init_buffer, term_buffer, window of the two NUTS entry points below (the services' defaults)
+static double g_gamma = 0.05, g_kappa = 0.75, g_t0 = 10.0;
+static unsigned g_init_buffer = 75, g_term_buffer = 50, g_window = 25;
+void ref_set_adapt_params(double gamma, double kappa, double t0, unsigned init_buffer, unsigned term_buffer,
+                          unsigned window) {
+  g_gamma = gamma;
+  g_kappa = kappa;
+  g_t0 = t0;
+  g_init_buffer = init_buffer;
+  g_term_buffer = term_buffer;
+  g_window = window;
+}
 // initial diagonal inverse metric of every chain for the two NUTS entry points below (n = 0: the unit metric)
 static std::vector<double> g_init_inv_metric;
 void ref_set_init_inv_metric(const double* m, int n) { g_init_inv_metric.assign(m, m + (n > 0 ? n : 0)); }
@@ -247,7 +259,7 @@ int ref_glm_nuts(void* h, int num_chains, unsigned seed, unsigned init_chain_id,
     rc = stan::services::sample::hmc_nuts_diag_e_adapt(
         m, num_chains, inits, metrics, seed, init_chain_id, init_radius,
         num_warmup, num_samples, 1, true, 0, stepsize, g_stepsize_jitter, max_depth, delta,
-        0.05, 0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w,
+        g_gamma, g_kappa, g_t0, g_init_buffer, g_term_buffer, g_window, interrupt, logger, init_w, sample_w,
         diag_w, metric_w);
     auto t1 = std::chrono::steady_clock::now();
     if (wall_seconds)
@@ -306,8 +318,8 @@ int ref_glm_nuts_device_host(void* h, int num_chains, unsigned seed, unsigned in
     oracle_ref::nuts_host_backend<ref_glm_model> backend(m);
     b200::nuts_backend be = backend.table();
     rc = b200::hmc_nuts_diag_e_adapt_device(m, be, num_chains, inits, metrics, seed, init_chain_id, init_radius,
-                                            num_warmup, num_samples, 1, true, 0, stepsize, g_stepsize_jitter, max_depth, delta, 0.05,
-                                            0.75, 10.0, 75, 50, 25, interrupt, logger, init_w, sample_w, diag_w,
+                                            num_warmup, num_samples, 1, true, 0, stepsize, g_stepsize_jitter, max_depth, delta, g_gamma,
+                                            g_kappa, g_t0, g_init_buffer, g_term_buffer, g_window, interrupt, logger, init_w, sample_w, diag_w,
                                             metric_w, stats);
     if (rc != 0)
       throw std::runtime_error("hmc_nuts_diag_e_adapt_device rc=" + std::to_string(rc) + ": " + logger.errors);

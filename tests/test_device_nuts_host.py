@@ -117,6 +117,25 @@ def test_initial_inverse_metric_is_used(num_warmup):
     assert not np.array_equal(B0[:, :5, 7:], B[:, :5, 7:])
 
 
+@pytest.mark.parametrize("adapt,delta", [
+    (dict(gamma=0.1, kappa=0.6, t0=5.0, init_buffer=20, term_buffer=10, window=8), 0.9),    # many short metric windows
+    (dict(init_buffer=10, term_buffer=60, window=30), 0.65),     # the last window absorbs the rest (windowed_adaptation.hpp:97-113)
+    (dict(gamma=-1.0, kappa=0.0, t0=-3.0), 1.5),                 # out of range: the setters keep 0.05 / 0.75 / 10 / 0.5
+    (dict(init_buffer=100, term_buffer=100, window=100), 0.8),   # does not fit 150: the 15 % / 75 % / 10 % schedule
+])
+def test_adaptation_parameters_of_the_service(adapt, delta):
+    """gamma / kappa / t0 / delta (stepsize_adaptation's setters, which ignore out-of-range values) and init_buffer /
+    term_buffer / window (windowed_adaptation::set_window_params) other than the defaults: same chains, same adapted step
+    size, same adapted metric as the reference service."""
+    kw = dict(num_chains=2, seed=17, num_warmup=150, num_samples=30, stepsize=1.0, max_depth=10, delta=delta, adapt=adapt)
+    a, b, A, B = _both("poisson_log", 300, 4, **kw)
+    assert np.array_equal(A[:, :, 3:6], B[:, :, 3:6])
+    e = _err(A, B).max(axis=(0, 2))
+    assert e[:20].max() < 1e-12 and e.max() < 1e-6
+    assert np.abs(a["stepsize"] - b["stepsize"]).max() < 1e-8
+    assert np.abs(a["inv_metric"] - b["inv_metric"]).max() < 1e-8
+
+
 def test_divergent_transitions_are_reproduced():
     """A step size far too large for a sharp posterior, no adaptation to repair it: divergent__ = 1 rows must coincide."""
     kw = dict(num_chains=2, seed=3, num_warmup=0, num_samples=60, stepsize=1.0, max_depth=10, delta=0.8)
