@@ -254,6 +254,27 @@ def test_error_behaviour_matches_reference():
     m.close()
 
 
+@pytest.mark.parametrize("fam,K", [("bernoulli_logit", 6), ("poisson_log", 6), ("normal_id", 6), ("bernoulli_logit", 300)])
+def test_nan_in_x_is_a_domain_error_in_every_kernel(fam, K):
+    """A NaN in the matrix of independent variables makes the row's term NaN, the sum non-finite, and the reference
+    throws domain_error from check_finite("Matrix of independent variables", ...) (bernoulli_logit_glm_lpmf.hpp:128-131,
+    poisson_log_glm_lpmf.hpp:120-123, normal_id_glm_lpdf.hpp:192-197; rev test `..._glm_error_checking`, xw3) -- also when
+    the weight of that column is zero (0 * NaN).  Narrow / wide kernel, and per lane in the batched kernels."""
+    d = make_glm_data(fam, 5_000, K)
+    X = d["X"].copy()
+    X[4_321, 2] = np.nan
+    m = GLMModel(fam, X, d["y"])
+    for th in (0.1 * np.ones(m.P), np.zeros(m.P)):
+        with pytest.raises(stan_b200.DomainError):
+            m.log_prob_grad(th)
+    if K <= 208:
+        m.batch_reserve(20)
+        th = 0.1 * np.random.default_rng(0).standard_normal((20, m.P))
+        for n in (3, 12, 20):                      # few-chain kernel, row-split DMMA, DMMA
+            assert m.log_prob_grad_batched(th[:n])[2].all()
+    m.close()
+
+
 def test_empty_and_tiny():
     m = GLMModel("bernoulli_logit", np.zeros((0, 3)), np.zeros(0, np.int32))
     from oracle.oracle import PortOracle
