@@ -136,6 +136,18 @@ def test_adaptation_parameters_of_the_service(adapt, delta):
     assert np.abs(a["inv_metric"] - b["inv_metric"]).max() < 1e-8
 
 
+def test_deep_trees_up_to_max_depth():
+    """delta = 0.99 on a 62-parameter hierarchical model: step sizes small enough for trees of depth 9 and 10 (1023
+    leapfrogs, ten levels of the explicit subtree stack, up to eleven uniform variates consumed in one round).  Tree depths,
+    leapfrog counts and divergence flags of all 210 iterations are the reference's; so is the adapted step size."""
+    kw = dict(num_chains=4, seed=23, num_warmup=150, num_samples=60, stepsize=1.0, max_depth=10, delta=0.99)
+    a, b, A, B = _both("poisson_log", 200, 2, 60, **kw)
+    assert A[:, :, 3].max() == 10 and (A[:, :, 4] == 1023).any()
+    assert np.array_equal(A[:, :, 3:6], B[:, :, 3:6])
+    assert _err(A, B)[:, :20].max() < 1e-10 and _err(A, B).max() < 1e-5
+    assert np.abs(a["stepsize"] - b["stepsize"]).max() < 1e-8
+
+
 def test_divergent_transitions_are_reproduced():
     """A step size far too large for a sharp posterior, no adaptation to repair it: divergent__ = 1 rows must coincide."""
     kw = dict(num_chains=2, seed=3, num_warmup=0, num_samples=60, stepsize=1.0, max_depth=10, delta=0.8)
